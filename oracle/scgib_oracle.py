@@ -1,0 +1,353 @@
+"""Pure-torch CPU restatement of the S-CGIB pre-training hot path.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): the checker and the timed CPU baseline.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+DGL calls are replaced by index operations that follow DGL 1.1.0 semantics;
+that part is restated, not executed ("parity unpinned" for DGL internals; the reference's own
+Python is pinned by tests/golden, see oracle/__init__.py).
+
+Two flavours of the same math:
+
+* ``faithful``   - loop-for-loop: per-graph Python loops with growing ``torch.cat``
+                   (models.py:631-660, 738-748) and the dense N x N reconstruction
+                   (models.py:762-768).  Ground truth at small B and the timed "reference CPU path".
+* ``vectorised`` - segment ops + the Gram identity for the reconstruction loss; proven equal
+                   to ``faithful`` in tests/test_oracle.py and used at B = 4096/8192.
+
+Noise enters as explicit tensors (``gate_u [N]``, ``feat_u [N,d]``); when omitted the faithful
+path draws it exactly as the reference does on a CPU run (models.py:599, 650).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .graph_ref import RefEgoBatch, RefGraph
+
+
+# --------------------------------------------------------------------------------------
+# graph tensors
+# --------------------------------------------------------------------------------------
+@dataclass
+class TGraph:
+    """Torch view of a RefGraph / RefEgoBatch: what DGLGraph supplies to the reference."""
+    seg_ptr: torch.Tensor   # int64 [S+1] segment (graph / ego-net) offsets over rows
+    indptr: torch.Tensor    # int64 [V+1]
+    indices: torch.Tensor   # int64 [E]
+    src: torch.Tensor       # int64 [E]
+    dst: torch.Tensor       # int64 [E]
+
+    @property
+    def num_nodes(self):
+        return self.indptr.numel() - 1
+
+    def batch_num_nodes(self):
+        return self.seg_ptr[1:] - self.seg_ptr[:-1]
+
+    def seg_ids(self):
+        n = self.batch_num_nodes()
+        return torch.repeat_interleave(torch.arange(n.numel()), n)
+
+
+def tgraph_from_ref(g: RefGraph) -> TGraph:
+    indptr = torch.from_numpy(g.indptr.astype(np.int64))
+    indices = torch.from_numpy(g.indices.astype(np.int64))
+    dst = torch.repeat_interleave(torch.arange(g.num_nodes), indptr[1:] - indptr[:-1])
+    return TGraph(torch.from_numpy(g.graph_ptr.astype(np.int64)), indptr, indices, indices, dst)
+
+
+def tgraph_from_ego(e: RefEgoBatch) -> TGraph:
+    indptr = torch.from_numpy(e.sub_indptr.astype(np.int64))
+    indices = torch.from_numpy(e.sub_indices.astype(np.int64))
+    dst = torch.repeat_interleave(torch.arange(e.num_rows), indptr[1:] - indptr[:-1])
+    return TGraph(torch.from_numpy(e.ego_ptr.astype(np.int64)), indptr, indices, indices, dst)
+
+
+def sum_nodes(g: TGraph, h: torch.Tensor) -> torch.Tensor:
+    """dgl.sum_nodes: segment sum by batch_num_nodes (models.py:716, 725, 733, 684)."""
+    out = torch.zeros(g.seg_ptr.numel() - 1, h.shape[1], dtype=h.dtype)
+    return out.index_add(0, g.seg_ids(), h)
+
+
+# --------------------------------------------------------------------------------------
+# modules (state_dict keys identical to the reference's)
+# --------------------------------------------------------------------------------------
+class MLP(nn.Module):
+    """models.py:38-49."""
+
+    def __init__(self, num_features, num_classes, dims=16):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(num_features, dims), nn.ReLU(), nn.Linear(dims, num_classes))
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class GINConvRef(nn.Module):
+    """DGL 1.1.0 GINConv(apply_func, 'sum', init_eps=0, learn_eps=False):
+    rst = (1 + eps) * h_dst + sum_{u->v} h_u ; rst = apply_func(rst).  eps is a buffer."""
+
+    def __init__(self, apply_func):
+        super().__init__()
+        self.apply_func = apply_func
+        self.register_buffer("eps", torch.FloatTensor([0.0]))
+
+    def forward(self, g: TGraph, h):
+        neigh = torch.zeros_like(h).index_add(0, g.dst, h[g.src])
+        rst = (1 + self.eps.to(h.dtype)) * h + neigh
+        return self.apply_func(rst)
+
+
+class GIN(nn.Module):
+    """models.py:52-72.  ``num_gin_layers`` = number of GINConv (4 in the published code:
+    ``num_layers = 5; range(num_layers - 1)``)."""
+
+    def __init__(self, input_dim, hidden_dim=64, num_gin_layers=4):
+        super().__init__()
+        self.ginlayers = nn.ModuleList()
+        self.batch_norms = nn.ModuleList()
+        for layer in range(num_gin_layers):
+            mlp = MLP(input_dim if layer == 0 else hidden_dim, hidden_dim, hidden_dim)
+            self.ginlayers.append(GINConvRef(mlp))
+            self.batch_norms.append(nn.BatchNorm1d(hidden_dim))
+
+    def forward(self, g, h):
+        for i, layer in enumerate(self.ginlayers):
+            h = layer(g, h)
+            h = self.batch_norms[i](h)
+            h = F.relu(h)
+        return h
+
+
+class _LSTMHolder(nn.Module):
+    """Stand-in for dgl.nn.Set2Set(hidden, 2, 1): only the parameter container (``s2s.lstm.*``)
+    so that state_dict keys / parameter order / init RNG consumption match models.py:565."""
+
+    def __init__(self, input_dim, n_iters, n_layers):
+        super().__init__()
+        self.lstm = nn.LSTM(2 * input_dim, input_dim, n_layers)
+
+
+class OracleMainmodel(nn.Module):
+    """models.py:546-782 (Mainmodel), GIN encoder, readout 'sum', recons_type 'adj', useAtt 1.
+    Construction order follows models.py:547-593 so a seeded default init matches."""
+
+    def __init__(self, in_dim, hidden_dim=64, d_transfer=32, num_gin_layers=4):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.fc1 = nn.Linear(hidden_dim, 1)
+        self.in_dim = d_transfer
+        self.transfer_d = nn.Linear(in_dim, d_transfer, bias=False)
+        self.embedding_h = nn.Linear(d_transfer, hidden_dim, bias=False)
+        self.attn_layer = nn.Linear(hidden_dim * 2, 1)
+        self.reduce_d = nn.Linear(2 * hidden_dim, hidden_dim)
+        self.s2s = _LSTMHolder(hidden_dim, 2, 1)
+        self.reconstructX = nn.Sequential(nn.Linear(hidden_dim, d_transfer))
+        self.MLP = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(),
+                                 nn.Linear(hidden_dim, hidden_dim))
+        self.Encoder1 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.Encoder2 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.compressor = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim),
+                                        nn.ReLU(), nn.Linear(hidden_dim, 1))
+
+    # ---------------------------------------------------------------- faithful pieces
+    def compress(self, graph_features, gate_u=None):
+        """models.py:595-604.  ``gate_u`` [n,1] replaces torch.rand(p.size())."""
+        p = self.compressor(graph_features)
+        bias = 0.0 + 0.0001
+        u = torch.rand(p.size()) if gate_u is None else gate_u.reshape(p.size()).to(p.dtype)
+        eps = (bias - (1 - bias)) * u + (1 - bias)
+        gate_inputs = (torch.log(eps) - torch.log(1 - eps)).to(p.dtype)
+        gate_inputs = (gate_inputs + p) / 1.0
+        gate_inputs = torch.sigmoid(gate_inputs).squeeze()
+        return gate_inputs, p
+
+    def compression(self, graph_features, nodes_list, gate_u=None, feat_u=None):
+        """models.py:631-660, loop-for-loop (incl. the KL overwrite of models.py:659)."""
+        epsilon = 0.0000001
+        noisy_all = torch.tensor((), dtype=graph_features.dtype)
+        p_all = torch.tensor((), dtype=graph_features.dtype)
+        KL_all = torch.tensor((), dtype=graph_features.dtype)
+        split = torch.split(graph_features, tuple(nodes_list))
+        off = 0
+        for i in range(len(nodes_list)):
+            features = split[i]
+            n = features.shape[0]
+            gu = None if gate_u is None else gate_u[off:off + n]
+            lambda_pos, p = self.compress(features, gu)
+            lambda_pos = lambda_pos.reshape(-1, 1)
+            lambda_neg = 1 - lambda_pos
+            static = features.clone().detach()
+            std, mean = torch.std_mean(static, dim=0)
+            noisy_mean = lambda_pos * features + lambda_neg * mean
+            noisy_std = lambda_neg * std
+            fu = torch.rand_like(noisy_mean) if feat_u is None else feat_u[off:off + n].to(noisy_mean.dtype)
+            noisy = noisy_mean + fu * noisy_std
+            noisy_all = torch.cat((noisy_all, noisy), 0)
+            p_all = torch.cat((p_all, p), 0)
+            KL = 0.5 * ((noisy_std ** 2) / (std + epsilon) ** 2) + torch.sum(
+                ((noisy_mean - mean) / (std + epsilon)) ** 2, dim=0)
+            KL_all = torch.cat((KL, KL), 0)
+            off += n
+        return noisy_all, p_all, KL_all
+
+    def sim(self, z1, z2):
+        """models.py:606-609."""
+        return torch.mm(F.normalize(z1), F.normalize(z2).t())
+
+    def batched_semi_loss(self, z1, z2, batch_size):
+        """models.py:611-629."""
+        num_nodes = z1.size(0)
+        num_batches = (num_nodes - 1) // batch_size + 1
+        f = lambda x: torch.exp(x / 1)
+        indices = torch.arange(0, num_nodes)
+        losses = []
+        for i in range(num_batches):
+            mask = indices[i * batch_size:(i + 1) * batch_size]
+            refl = f(self.sim(z1[mask], z1))
+            btw = f(self.sim(z1[mask], z2))
+            losses.append(-torch.log(btw[:, i * batch_size:(i + 1) * batch_size].diag()
+                                     / (refl.sum(1) + btw.sum(1)
+                                        - refl[:, i * batch_size:(i + 1) * batch_size].diag())))
+        return torch.cat(losses).mean()
+
+    def loss_recon_adj(self, interaction_map, g: TGraph):
+        """models.py:762-768: dense N x N over the whole batched graph."""
+        row_num = interaction_map.shape[0]
+        adj = torch.zeros(row_num, row_num, dtype=interaction_map.dtype)
+        adj[g.src, g.dst] = 1.0
+        recon = torch.mm(interaction_map, interaction_map.t())
+        return torch.sum((recon - adj) ** 2) / row_num
+
+    def extract_features(self, g: TGraph, batch_x, eg: TGraph, x_subs, gate_u=None, feat_u=None):
+        """models.py:702-750 (readout 'sum', useAtt)."""
+        nodes_list = [int(v) for v in g.batch_num_nodes()]
+        graph_features = self.Encoder1(g, batch_x)
+        subgraphs_features = self.Encoder2(eg, x_subs)
+        graph_features_readout = sum_nodes(g, graph_features)
+        noisy, p, KL_tensor = self.compression(graph_features, nodes_list, gate_u, feat_u)
+        sub_readout = sum_nodes(eg, subgraphs_features)
+        noisy_readout = sum_nodes(g, noisy)
+        subgs_att = torch.tensor((), dtype=noisy.dtype)
+        split = torch.split(sub_readout, tuple(nodes_list))
+        for i in range(len(split)):
+            cp = noisy_readout[i].repeat(nodes_list[i], 1)
+            interaction = torch.cat((cp, split[i]), -1)
+            att = F.softmax(self.attn_layer(interaction), dim=0)
+            subgs_att = torch.cat((subgs_att, split[i] * att), 0)
+        interaction_map = torch.cat((noisy, subgs_att), -1)
+        self._dbg = dict(graph_features=graph_features, sub_readout=sub_readout, p=p)
+        return interaction_map, KL_tensor, noisy, graph_features_readout
+
+    def forward_faithful(self, g: TGraph, x_norm, eg: TGraph, x_subs_norm, gate_u=None, feat_u=None,
+                         batch_size=None):
+        """models.py:662-700 / 1158-1195.  x_norm / x_subs_norm are the F.normalize'd raw features
+        (exp_pretraining.py:312-314).  Returns dict with the three losses and the embeddings."""
+        batch_x = self.transfer_d(x_norm)
+        x_subs = self.transfer_d(x_subs_norm)
+        imap, KL_tensor, noisy, g_readout = self.extract_features(g, batch_x, eg, x_subs, gate_u, feat_u)
+        Z = self.MLP(imap)
+        KL_loss = torch.mean(KL_tensor)
+        noisy2 = sum_nodes(g, noisy)
+        bs = batch_size if batch_size is not None else noisy2.shape[0]
+        con = self.batched_semi_loss(noisy2, g_readout, bs)
+        rec = self.loss_recon_adj(Z, g)
+        return dict(KL=KL_loss, contrastive=con, recon=rec, interaction_map=imap, Z=Z, noisy=noisy,
+                    graph_readout=g_readout, core_readout=noisy2)
+
+    # ---------------------------------------------------------------- vectorised (same math)
+    def forward_vectorised(self, g: TGraph, x_norm, eg: TGraph, ego_nodes, gate_u, feat_u):
+        """Segment-op restatement (no per-graph loops, Gram identity for the recon loss;
+        SURVEY.md F5/F14 + Appendix A).  ``ego_nodes`` [Ns] int64 maps ego rows to parent nodes."""
+        dt = x_norm.dtype
+        t = self.transfer_d(x_norm)
+        H = self.Encoder1(g, t)
+        S = self.Encoder2(eg, t[ego_nodes])
+        seg = g.seg_ids()
+        nB = g.seg_ptr.numel() - 1
+        n = g.batch_num_nodes().to(dt)
+        R = sum_nodes(g, H)
+        # compressor with per-graph BatchNorm (models.py:589-596 applied per split, :642)
+        lin1, bn, _, lin2 = self.compressor
+        q = lin1(H)
+        qm = torch.zeros(nB, q.shape[1], dtype=dt).index_add(0, seg, q) / n[:, None]
+        qc = q - qm[seg]
+        qv = torch.zeros(nB, q.shape[1], dtype=dt).index_add(0, seg, qc * qc) / n[:, None]
+        qh = qc / torch.sqrt(qv[seg] + bn.eps)
+        if self.training:
+            # B sequential EMA updates (one per graph, graph order) in closed form: r <- 0.9 r + 0.1 stat_i
+            with torch.no_grad():
+                w = 0.1 * 0.9 ** torch.arange(nB - 1, -1, -1, dtype=dt)
+                bn.running_mean.mul_(0.9 ** nB).add_((w[:, None] * qm).sum(0))
+                bn.running_var.mul_(0.9 ** nB).add_((w[:, None] * qv * (n / (n - 1))[:, None]).sum(0))
+                bn.num_batches_tracked += nB
+        p = lin2(F.relu(qh * bn.weight + bn.bias))
+        eps = (0.0001 - (1 - 0.0001)) * gate_u.to(dt) + (1 - 0.0001)
+        lam = torch.sigmoid((torch.log(eps) - torch.log(1 - eps)).to(dt)[:, None] + p)
+        Hd = H.detach()
+        mu = torch.zeros(nB, H.shape[1], dtype=dt).index_add(0, seg, Hd) / n[:, None]
+        var = torch.zeros(nB, H.shape[1], dtype=dt).index_add(0, seg, (Hd - mu[seg]) ** 2) / (n[:, None] - 1)
+        sd = torch.sqrt(var)
+        m = lam * H + (1 - lam) * mu[seg]
+        s = (1 - lam) * sd[seg]
+        noisy = m + feat_u.to(dt) * s
+        # KL: last graph only (models.py:657-659)
+        last = seg == (nB - 1)
+        e = 0.0000001
+        KLt = 0.5 * (s[last] ** 2) / (sd[-1] + e) ** 2 + torch.sum(((m[last] - mu[-1]) / (sd[-1] + e)) ** 2, dim=0)
+        KL = KLt.mean()
+        # ego pooling, attention (softmax shift invariance: core half and bias cancel, F14)
+        C = sum_nodes(eg, S)
+        core = sum_nodes(g, noisy)
+        logit = self.attn_layer(torch.cat((core[seg], C), -1)).squeeze(-1)
+        mx = torch.full((nB,), -float("inf"), dtype=dt).scatter_reduce(0, seg, logit, "amax")
+        ex = torch.exp(logit - mx[seg])
+        den = torch.zeros(nB, dtype=dt).index_add(0, seg, ex)
+        alpha = ex / den[seg]
+        imap = torch.cat((noisy, C * alpha[:, None]), -1)
+        Z = self.MLP(imap)
+        # contrastive (models.py:606-629), one chunk
+        z1 = F.normalize(core)
+        z2 = F.normalize(R)
+        refl = torch.exp(z1 @ z1.t())
+        btw = torch.exp(z1 @ z2.t())
+        con = (-torch.log(btw.diag() / (refl.sum(1) + btw.sum(1) - refl.diag()))).mean()
+        # recon via Gram identity: ||ZZ^T - A||_F^2 = ||Z^T Z||_F^2 - 2 sum_E z_i.z_j + nnz(A)
+        G = Z.t() @ Z
+        edge = (Z[g.src] * Z[g.dst]).sum()
+        rec = ((G * G).sum() - 2 * edge + g.src.numel()) / Z.shape[0]
+        return dict(KL=KL, contrastive=con, recon=rec, interaction_map=imap, Z=Z, noisy=noisy,
+                    graph_readout=R, core_readout=core, H=H, C=C, alpha=alpha, lam=lam.squeeze(-1), t=t)
+
+
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x) as used at exp_pretraining.py:312-314 (p=2, dim=1, eps=1e-12)."""
+    return F.normalize(x)
+
+
+def draw_noise_like_reference(nodes_list, d, seed):
+    """Reproduce the CPU RNG stream of one reference forward on CPU: per graph, n gate draws
+    (torch.rand(p.size()), models.py:599) then n*d feature draws (rand_like, models.py:650)."""
+    gen_state = torch.get_rng_state()
+    torch.manual_seed(seed)
+    gate, feat = [], []
+    for n in nodes_list:
+        gate.append(torch.rand(n, 1))
+        feat.append(torch.rand(n, d))
+    torch.set_rng_state(gen_state)
+    return torch.cat(gate).squeeze(1), torch.cat(feat)
+
+
+def oracle_train_step(model: OracleMainmodel, opt, g, x_norm, eg, x_subs_norm, gate_u=None, feat_u=None):
+    """exp_pretraining.py:307-324: zero_grad, forward, loss = KL + recon + contrastive, backward, Adam."""
+    opt.zero_grad()
+    out = model.forward_faithful(g, x_norm, eg, x_subs_norm, gate_u, feat_u)
+    loss = out["KL"] + out["recon"] + out["contrastive"]
+    loss.backward()
+    opt.step()
+    return float(loss.detach())

@@ -1,0 +1,122 @@
+"""Minimal stand-in for the DGL 1.1.0 call surface used by the reference's models.py hot path.
+
+Test tooling only: lets tests/golden/make_golden.py import the UNMODIFIED /root/reference/models.py
+in a container without DGL/PyG/ogb/pyro/torch_scatter and run Mainmodel.forward on CPU to
+record golden vectors.  The DGL semantics below are restated from the library's v1.1.0
+behaviour; everything else executed for the golden vectors is the reference's
+own code.
+"""
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+
+class StubGraph:
+    """What the reference needs from a (batched) DGLGraph."""
+
+    def __init__(self, seg_ptr, src, dst, num_nodes):
+        self._seg_ptr = torch.as_tensor(seg_ptr, dtype=torch.int64)
+        self._src = torch.as_tensor(src, dtype=torch.int64)
+        self._dst = torch.as_tensor(dst, dtype=torch.int64)
+        self._n = int(num_nodes)
+        self.ndata = {}
+
+    def batch_num_nodes(self):
+        return self._seg_ptr[1:] - self._seg_ptr[:-1]
+
+    def num_nodes(self):
+        return self._n
+
+    def edges(self):
+        return self._src, self._dst
+
+    def to(self, device):
+        return self
+
+    def adj(self):
+        g = self
+
+        class _Adj:
+            def to_dense(self_inner):
+                a = torch.zeros(g._n, g._n)
+                a[g._src, g._dst] = 1.0
+                return a
+        return _Adj()
+
+
+def sum_nodes(g, key):
+    h = g.ndata[key]
+    n = g.batch_num_nodes()
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    return torch.zeros(n.numel(), h.shape[1], dtype=h.dtype).index_add(0, seg, h)
+
+
+class GINConv(nn.Module):
+    """dgl.nn.pytorch.conv.GINConv(apply_func, aggregator_type='sum', init_eps=0, learn_eps=False)."""
+
+    def __init__(self, apply_func=None, aggregator_type="sum", init_eps=0, learn_eps=False, activation=None):
+        super().__init__()
+        assert aggregator_type == "sum" and not learn_eps and activation is None
+        self.apply_func = apply_func
+        self.register_buffer("eps", torch.FloatTensor([init_eps]))
+
+    def forward(self, g, feat):
+        neigh = torch.zeros_like(feat).index_add(0, g._dst, feat[g._src])
+        rst = (1 + self.eps) * feat + neigh
+        if self.apply_func is not None:
+            rst = self.apply_func(rst)
+        return rst
+
+
+class Set2Set(nn.Module):
+    """Parameter container only (the pre-training default readout is 'sum')."""
+
+    def __init__(self, input_dim, n_iters, n_layers):
+        super().__init__()
+        self.input_dim, self.output_dim, self.n_iters, self.n_layers = input_dim, 2 * input_dim, n_iters, n_layers
+        self.lstm = nn.LSTM(self.output_dim, self.input_dim, n_layers)
+        self.lstm.reset_parameters()
+
+    def forward(self, graph, feat):
+        raise NotImplementedError("Set2Set readout is outside the golden scope")
+
+
+class _Dummy:
+    def __init__(self, *a, **k):
+        raise NotImplementedError
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    """Register stand-ins for every third-party import at the top of reference models.py:4-35."""
+    dummy_names = ["GCNConv", "SAGEConv", "global_mean_pool", "AsGraphPredDataset", "GraphDataLoader",
+                   "collate_dgl", "DglGraphPropPredDataset", "Evaluator", "AtomEncoder", "GraphConv",
+                   "scatter_mean", "scatter_add", "scatter_std", "SumPooling", "GINDataset"]
+    d = {n: _Dummy for n in dummy_names}
+    dgl = _mod("dgl", sum_nodes=sum_nodes, StubGraph=StubGraph)
+    dgl.nn = _mod("dgl.nn", Set2Set=Set2Set, GraphConv=_Dummy, SAGEConv=_Dummy, GINConv=GINConv)
+    dgl.sparse = _mod("dgl.sparse")
+    dgl.function = _mod("dgl.function")
+    dgl.data = _mod("dgl.data", AsGraphPredDataset=_Dummy, GINDataset=_Dummy)
+    dgl.dataloading = _mod("dgl.dataloading", GraphDataLoader=_Dummy)
+    pt = _mod("dgl.nn.pytorch")
+    pt.glob = _mod("dgl.nn.pytorch.glob", SumPooling=_Dummy)
+    pt.conv = _mod("dgl.nn.pytorch.conv", GINConv=GINConv, GraphConv=_Dummy)
+    dgl.nn.pytorch = pt
+    tg = _mod("torch_geometric")
+    tg.nn = _mod("torch_geometric.nn", GCNConv=_Dummy, SAGEConv=_Dummy, global_mean_pool=_Dummy)
+    ogb = _mod("ogb")
+    ogb.graphproppred = _mod("ogb.graphproppred", collate_dgl=_Dummy, DglGraphPropPredDataset=_Dummy,
+                             Evaluator=_Dummy)
+    _mod("ogb.graphproppred.mol_encoder", AtomEncoder=_Dummy)
+    _mod("pyro")
+    _mod("torch_scatter", scatter_mean=_Dummy, scatter_add=_Dummy, scatter_std=_Dummy)
+    return dgl

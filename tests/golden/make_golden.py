@@ -1,0 +1,97 @@
+"""Generate golden vectors by running the UNMODIFIED reference models.py (CPU) on a DGL stand-in.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/pretrain_k{K}_b{B}.pt.  The fixtures travel to the GPU box; this script and
+/root/reference do not need to.
+"""
+import argparse
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle.graph_ref import ego_batch_ref, synth_batch  # noqa: E402
+
+
+def load_reference_models(ref_root="/root/reference"):
+    import dgl_stub
+    dgl_stub.install()
+    sys.path.insert(0, ref_root)
+    return importlib.import_module("models"), dgl_stub
+
+
+def make(seed, B, k, ref_models, dgl_stub, out_path):
+    g = synth_batch(seed, B)
+    e = ego_batch_ref(g, k)
+    s, d = g.edges()
+    bg = dgl_stub.StubGraph(g.graph_ptr, s, d, g.num_nodes)
+    bg.ndata["x"] = torch.from_numpy(g.x)
+    # ego batch: sub-graph s is the ego-net of global node s (exp_pretraining.py:269-274, 308-309)
+    es_dst = np.repeat(np.arange(e.num_rows), np.diff(e.sub_indptr))
+    eg = dgl_stub.StubGraph(e.ego_ptr, e.sub_indices, es_dst, e.num_rows)
+    eg.ndata["x"] = torch.from_numpy(g.x[e.ego_nodes])
+
+    args = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
+    torch.manual_seed(seed)
+    model = ref_models.Mainmodel(args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    model.train()
+    state0 = {n: t.detach().clone() for n, t in model.state_dict().items()}
+
+    # exp_pretraining.py:300-322
+    batch_x = F.normalize(bg.ndata["x"].float())
+    x_subs = F.normalize(eg.ndata["x"].float())
+    noise_seed = 1000 + seed
+    torch.manual_seed(noise_seed)
+    _, KL, con, rec = model.forward(bg, batch_x, eg, None, x_subs, 1, bg.edges(), 2, "cpu", B)
+    # re-run the two pieces the forward does not return (deterministic given the same RNG state)
+    torch.manual_seed(noise_seed)
+    imap, KLt, noisy, readout = model.extract_features(bg.batch_num_nodes(), bg,
+                                                       model.transfer_d(batch_x), eg,
+                                                       model.transfer_d(x_subs), "cpu")
+    Z = model.MLP(imap)
+    # BN running stats were updated twice now; restore and do the graded forward/backward once more
+    model.load_state_dict(state0)
+    model.zero_grad()
+    torch.manual_seed(noise_seed)
+    _, KL2, con2, rec2 = model.forward(bg, batch_x, eg, None, x_subs, 1, bg.edges(), 2, "cpu", B)
+    assert torch.equal(KL, KL2) and torch.equal(con, con2) and torch.equal(rec, rec2)
+    loss = KL2 + rec2 + con2
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    state1 = {n: t.detach().clone() for n, t in model.state_dict().items()
+              if "running" in n or "num_batches" in n}
+    used = set(grads) | {n for n in state0 if "running" in n or "num_batches" in n or n.endswith(".eps")}
+    fx = dict(
+        meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, reference="models.py Mainmodel (unmodified) on dgl_stub",
+                  torch=torch.__version__),
+        graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
+        ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
+        state={n: t for n, t in state0.items() if n in used},
+        state_after=state1,
+        out=dict(KL=KL.detach(), contrastive=con.detach(), recon=rec.detach(), interaction_map=imap.detach(),
+                 Z=Z.detach(), noisy=noisy.detach(), graph_readout=readout.detach(), KL_tensor=KLt.detach()),
+        grads=grads,
+    )
+    torch.save(fx, out_path)
+    print(out_path, os.path.getsize(out_path), "bytes", "KL %.6f con %.6f rec %.6f" % (KL, con, rec),
+          "grads:", len(grads))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    a = ap.parse_args()
+    ref_models, dgl_stub = load_reference_models(a.ref)
+    make(0, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k1_b6.pt"))
+    make(1, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k2_b4.pt"))
+    make(2, 3, 3, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k3_b3.pt"))

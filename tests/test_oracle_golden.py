@@ -1,0 +1,101 @@
+"""Oracle vs golden vectors recorded from the unmodified reference models.py (tests/golden/README.md)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.graph_ref import RefEgoBatch, RefGraph, ego_batch_ref
+from oracle.scgib_oracle import (OracleMainmodel, draw_noise_like_reference, normalize_rows,
+                                 tgraph_from_ego, tgraph_from_ref)
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pretrain_*.pt")))
+
+
+def load_fixture(path):
+    fx = torch.load(path, weights_only=False)
+    g = RefGraph(**fx["graph"])
+    e = RefEgoBatch(**fx["ego"])
+    return fx, g, e
+
+
+def oracle_from_fixture(fx, dtype=torch.float32):
+    m = OracleMainmodel(9, 64, 32, 4)
+    missing, unexpected = m.load_state_dict(fx["state"], strict=False)
+    assert not unexpected
+    m.train()
+    return m.to(dtype)
+
+
+def is_zero_grad_param(n):
+    return n.endswith("apply_func.mlp.2.bias") or n in ("attn_layer.bias", "compressor.0.bias")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_ego_batch_matches_fixture(path):
+    fx, g, e = load_fixture(path)
+    e2 = ego_batch_ref(g, fx["meta"]["k"])
+    for f in ("ego_ptr", "ego_nodes", "sub_indptr", "sub_indices"):
+        assert np.array_equal(getattr(e, f), getattr(e2, f))
+
+
+@pytest.mark.parametrize("flavour", ["faithful", "vectorised"])
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_oracle_forward_backward_matches_reference(path, flavour):
+    fx, g, e = load_fixture(path)
+    m = oracle_from_fixture(fx)
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    x = normalize_rows(torch.from_numpy(g.x))
+    ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    if flavour == "faithful":
+        out = m.forward_faithful(tg, x, te, x[ego_nodes], gate_u, feat_u)
+        tol = 2e-6
+    else:
+        out = m.forward_vectorised(tg, x, te, ego_nodes, gate_u, feat_u)
+        tol = 1e-5
+    ref = fx["out"]
+    for k in ("KL", "contrastive", "recon"):
+        assert abs(float(out[k]) - float(ref[k])) <= tol * abs(float(ref[k])), (k, float(out[k]), float(ref[k]))
+    for k in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(out[k], ref[k]) <= tol, (k, rel(out[k], ref[k]))
+    (out["KL"] + out["recon"] + out["contrastive"]).backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(grads) == set(fx["grads"])
+    gmax = max(float(v.abs().max()) for v in fx["grads"].values())
+    for n, gref in fx["grads"].items():
+        got = grads[n]
+        if is_zero_grad_param(n):
+            # mathematically zero (bias in front of a BatchNorm; softmax shift): rounding noise only
+            assert float(got.abs().max()) <= 1e-5 * gmax and float(gref.abs().max()) <= 1e-5 * gmax, n
+            continue
+        if n == "attn_layer.weight":
+            assert float(got[:, :64].abs().max()) <= 1e-5 * gmax and float(gref[:, :64].abs().max()) <= 1e-5 * gmax
+            got, gref = got[:, 64:], gref[:, 64:]
+        assert rel(got, gref) <= 50 * tol, (n, rel(got, gref))
+    # BN running statistics after one training forward
+    sd = m.state_dict()
+    for n, t in fx["state_after"].items():
+        if t.dtype.is_floating_point:
+            assert rel(sd[n], t) <= 1e-5, n
+        else:
+            assert torch.equal(sd[n], t), n
+
+
+@pytest.mark.parametrize("path", GOLD[:1], ids=[os.path.basename(p) for p in GOLD[:1]])
+def test_reference_noise_stream_is_reproduced_without_injection(path):
+    """With no injected noise the faithful oracle consumes the CPU RNG exactly like the reference
+    (gate torch.rand then rand_like, per graph)."""
+    fx, g, e = load_fixture(path)
+    m = oracle_from_fixture(fx)
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    x = normalize_rows(torch.from_numpy(g.x))
+    ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    torch.manual_seed(fx["meta"]["noise_seed"])
+    out = m.forward_faithful(tg, x, te, x[ego_nodes])
+    assert rel(out["noisy"], fx["out"]["noisy"]) <= 2e-6
