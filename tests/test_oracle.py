@@ -105,12 +105,12 @@ def test_faithful_equals_vectorised_fp64(k):
     g, e, m, x, en, gu, fu = _setup(3, 24, k, torch.float64)
     tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
     a = m.forward_faithful(tg, x, te, x[en], gu, fu)
+    ga = torch.autograd.grad(a["KL"] + a["recon"] + a["contrastive"], [p for p in m.parameters()], allow_unused=True)
     b = m.forward_vectorised(tg, x, te, en, gu, fu)
     for key in ("KL", "contrastive", "recon"):
         assert abs(float(a[key]) - float(b[key])) <= 1e-11 * abs(float(a[key])), key
     for key in ("interaction_map", "Z", "noisy", "graph_readout", "core_readout"):
         assert float((a[key] - b[key]).abs().max()) <= 1e-11 * float(a[key].abs().max()), key
-    ga = torch.autograd.grad(a["KL"] + a["recon"] + a["contrastive"], [p for p in m.parameters()], allow_unused=True)
     gb = torch.autograd.grad(b["KL"] + b["recon"] + b["contrastive"], [p for p in m.parameters()], allow_unused=True)
     for (n, _), u, v in zip(m.named_parameters(), ga, gb):
         if u is None:
