@@ -1,0 +1,199 @@
+/*
+ * scgib.h - C ABI of libscgib.so: the B200 (sm_100a) implementation of the S-CGIB per-batch
+ * pre-training hot path.
+ *
+ * The reference (O-JounLee/S-CGIB) has no FFI layer: its hot path is Python (models.py) calling
+ * DGL 1.1.0 / PyTorch kernels.  Each entry point below replaces the reference call sites it
+ * cites (file:line relative to the reference tree); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless marked (host).
+ *  - the caller owns every buffer (inputs, outputs, workspace); the library never allocates or
+ *    frees device memory and keeps no pointer after return.
+ *  - fp32 tensors are row-major, contiguous, rows 16-byte aligned; index arrays are int32.
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant
+ *    and stateless.  No host synchronisation unless documented.
+ *  - return value: 0 = ok; negative = SCGIB_E_* (argument/shape error, nothing launched);
+ *    positive = cudaError_t of the failing launch.
+ */
+#ifndef SCGIB_H_
+#define SCGIB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGIB_VERSION 100
+#if defined(__GNUC__)
+#define SCGIB_API __attribute__((visibility("default")))
+#else
+#define SCGIB_API
+#endif
+
+enum {
+  SCGIB_OK = 0,
+  SCGIB_E_NULL = -1,      /* required pointer is NULL */
+  SCGIB_E_SHAPE = -2,     /* unsupported dimension (hidden must be 64, d_transfer 32, 1 <= L <= 8, F <= 32) */
+  SCGIB_E_ALIGN = -3,     /* pointer not 16-byte aligned */
+  SCGIB_E_WORKSPACE = -4, /* workspace too small */
+  SCGIB_E_RANGE = -5,     /* size out of range (e.g. k < 1, graph with < 2 nodes) */
+};
+
+SCGIB_API int scgib_version(void);
+SCGIB_API const char* scgib_error_string(int code);
+/* Number of SMs of the current device (host query, cached). */
+SCGIB_API int scgib_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Model description.  Parameters live in ONE flat fp32 buffer (so the gradient all-reduce and
+ * the optimiser touch a single tensor); scgib_param_layout gives the offset of every tensor.
+ * State-dict names on the reference side are listed in INTEGRATION.md.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ScgibDims {
+  int32_t in_dim;     /* F: raw feature width (9 PCQM4Mv2 / mol-PCBA, 11 QM9)  exp_pretraining.py:219 */
+  int32_t d_transfer; /* 32                                                      exp_pretraining.py:378 */
+  int32_t hidden;     /* 64                                                      exp_pretraining.py:390 */
+  int32_t gin_layers; /* L: GINConv per encoder (4 in models.py:57-58)                               */
+} ScgibDims;
+
+/* Slots of the flat parameter buffer, in layout order.  Per-encoder/per-layer slots are
+ * addressed as SCGIB_P_ENC + (enc * L + layer) * SCGIB_ENC_SLOTS + {W1,B1,W2,B2,GAMMA,BETA}. */
+enum {
+  SCGIB_ENC_W1 = 0, SCGIB_ENC_B1, SCGIB_ENC_W2, SCGIB_ENC_B2, SCGIB_ENC_GAMMA, SCGIB_ENC_BETA,
+  SCGIB_ENC_SLOTS
+};
+enum {
+  SCGIB_P_HEAD_W1 = 0, /* MLP.0.weight [H,2H]        models.py:569-572 */
+  SCGIB_P_HEAD_B1,     /* MLP.0.bias   [H]                              */
+  SCGIB_P_HEAD_W2,     /* MLP.2.weight [H,H]                            */
+  SCGIB_P_HEAD_B2,     /* MLP.2.bias   [H]                              */
+  SCGIB_P_COMP_W1,     /* compressor.0.weight [H,H]  models.py:589-593 */
+  SCGIB_P_COMP_B1,     /* compressor.0.bias [H]                         */
+  SCGIB_P_COMP_GAMMA,  /* compressor.1.weight [H]                       */
+  SCGIB_P_COMP_BETA,   /* compressor.1.bias [H]                         */
+  SCGIB_P_COMP_W2,     /* compressor.3.weight [1,H]                     */
+  SCGIB_P_COMP_B2,     /* compressor.3.bias [1]                         */
+  SCGIB_P_ATTN_W,      /* attn_layer.weight [1,2H]   models.py:562     */
+  SCGIB_P_ATTN_B,      /* attn_layer.bias [1]                           */
+  SCGIB_P_TRANSFER,    /* transfer_d.weight [DT,F]   models.py:559     */
+  SCGIB_P_ENC,         /* first encoder slot; 2*L*SCGIB_ENC_SLOTS slots follow */
+};
+/* Number of slots for `d`; offsets[i], sizes[i] (in floats) for each slot; returns total floats
+ * (each slot padded to a multiple of 4 floats).  (host) pointers; either may be NULL. */
+SCGIB_API int64_t scgib_param_layout(const ScgibDims* d, int64_t* offsets, int64_t* sizes);
+SCGIB_API int32_t scgib_param_slots(const ScgibDims* d);
+
+/* One mini-batch: the batched parent graph (dgl.batch, molecules.py:359) and the flattened
+ * batch of one k-hop ego-net per node (exp_pretraining.py:308-309), both as symmetric CSR. */
+typedef struct ScgibBatch {
+  int32_t B, N, E;             /* graphs, nodes, directed edges of the parent batch            */
+  int32_t Ns, Es;              /* rows / directed edges of the ego batch                        */
+  const int32_t* graph_ptr;    /* [B+1] node offset of each graph   (batch_num_nodes)           */
+  const int32_t* indptr;       /* [N+1]                                                         */
+  const int32_t* indices;      /* [E]   global node ids, ascending per row                      */
+  const int32_t* ego_ptr;      /* [N+1] ego-net v = rows ego_ptr[v]..ego_ptr[v+1]               */
+  const int32_t* ego_nodes;    /* [Ns]  parent node of each ego row (ascending per ego-net)     */
+  const int32_t* ego_seed;     /* [Ns]  seed node v of the ego-net each row belongs to          */
+  const int32_t* sub_indptr;   /* [Ns+1]                                                        */
+  const int32_t* sub_indices;  /* [Es]  ego-batch row ids                                       */
+  const float* x;              /* [N,F] node features                                           */
+  int32_t normalize_x;         /* 1: apply F.normalize(x) (exp_pretraining.py:312) inside; 0: x is used as given */
+  const float* gate_u;         /* [N]   U[0,1) gate noise       (torch.rand,  models.py:599)    */
+  const float* feat_u;         /* [N,H] U[0,1) feature noise    (rand_like,   models.py:650)    */
+} ScgibBatch;
+
+/* ------------------------------------------------------------------------------------------
+ * k-hop ego-network extraction  (replaces dgl.khop_in_subgraph per node + dgl.batch:
+ * exp_pretraining.py:271, 308-309; exp_pcqm4mv2.py:422,425).  Two phases around one
+ * host-visible size read:
+ *   1. scgib_ego_count : per-seed ball size and induced edge count, exclusive scans.
+ *                        ego_ptr[N+1], ego_eptr[N+1] are written; ego_ptr[N] = Ns, ego_eptr[N] = Es.
+ *   2. scgib_ego_fill  : node lists (bit-exact with the reference: ascending parent ids,
+ *                        containing the seed), seed ids and the induced CSR.
+ * status[0] is set non-zero if a ball exceeds SCGIB_EGO_CAP nodes (fill output is then invalid).
+ * ------------------------------------------------------------------------------------------ */
+#define SCGIB_EGO_CAP 128
+SCGIB_API size_t scgib_ego_workspace_bytes(int32_t N);
+SCGIB_API int scgib_ego_count(const int32_t* indptr, const int32_t* indices, int32_t N, int32_t k,
+                    int32_t* ego_ptr, int32_t* ego_eptr, int32_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_ego_fill(const int32_t* indptr, const int32_t* indices, int32_t N, int32_t k,
+                   const int32_t* ego_ptr, const int32_t* ego_eptr,
+                   int32_t* ego_nodes, int32_t* ego_seed, int32_t* sub_indptr, int32_t* sub_indices,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole pre-training step (Mainmodel.forward / Mainmodel_continue.forward, models.py:662-700,
+ * 1158-1195, + loss.backward(), exp_pretraining.py:315-322).
+ *
+ * Workspace: one caller-owned device buffer of scgib_pretrain_workspace_bytes() bytes, 256-byte
+ * aligned.  `forward` leaves the saved activations there; `backward` must be called with the
+ * same workspace, batch and params before the next forward.
+ *
+ * outputs (device): losses[4] = {KL, contrastive, recon, KL+recon+contrastive};
+ *   optional embeddings (NULL to skip): interaction_map [N,2H] (models.py:749), Z [N,H]
+ *   (models.py:676), noisy [N,H], graph_readout [B,H] (models.py:716).
+ * bn_running: [2*L+1][2][H] running_mean/running_var of Encoder1 BNs, Encoder2 BNs, compressor
+ *   BN (in that order), updated in place like nn.BatchNorm1d(momentum 0.1) in train mode
+ *   (NULL to skip).
+ * ------------------------------------------------------------------------------------------ */
+SCGIB_API size_t scgib_pretrain_workspace_bytes(const ScgibDims* d, int32_t B, int32_t N, int32_t E,
+                                      int32_t Ns, int32_t Es);
+SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
+                               const ScgibBatch* batch, float* losses,
+                               float* interaction_map, float* Z, float* noisy, float* graph_readout,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* grads: flat buffer with the layout of `params`; every used slot is overwritten (not
+ * accumulated); unused reference parameters are not part of the buffer.
+ * loss_scale[3] (host): d(total)/d{KL, contrastive, recon}; the reference uses {1,1,1}. */
+SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* batch,
+                                const float* loss_scale, float* grads,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adam with L2-in-gradient weight decay over one flat buffer (torch.optim.Adam(lr, weight_decay),
+ * exp_pretraining.py:86,112,323).  step = 1-based step count; grad_scale multiplies the gradient
+ * first (1/world_size after a sum all-reduce). */
+SCGIB_API int scgib_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        int64_t n, int64_t step, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Individual operators (what the autograd Functions of the drop-in modules call; also the
+ * unit-test surface).  H = 64.
+ * ------------------------------------------------------------------------------------------ */
+/* F.normalize(x) then transfer_d (exp_pretraining.py:312-314, models.py:668): t[N,DT]. */
+SCGIB_API int scgib_input_proj_fwd_f32(const float* x, const float* Wt, int32_t N, int32_t F, int32_t DT,
+                             float* t, void* stream);
+
+/* One GINConv + (deferred) BatchNorm layer (models.py:66-72; DGL GINConv sum, eps=0):
+ *   a_v = f(in[map(v)]) + sum_{u in N(v)} f(in[map(u)]),  f = relu(BN_in(.)) or identity (bn_in NULL)
+ *   y   = W2 relu(W1 a + b1) + b2          (pre-BN output, saved)
+ * and the batch statistics of y over all V rows: bn_out = {mean[H], rstd[H]} (biased var, eps 1e-5).
+ * bn_in = {mean[H], rstd[H], gamma[H], beta[H]} of the producing layer.  a_out/r_out (saved for
+ * backward) may be NULL.  running = {running_mean[H], running_var[H]} or NULL.
+ * workspace >= scgib_gin_workspace_bytes(V). */
+SCGIB_API size_t scgib_gin_workspace_bytes(int32_t V);
+SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, const int32_t* row_map, const float* bn_in,
+                            const int32_t* indptr, const int32_t* indices, int32_t V,
+                            const float* W1, const float* b1, const float* W2, const float* b2,
+                            float* a_out, float* r_out, float* y_out, float* bn_out, float* running,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[s] = sum_{rows in segment s} f(in[row])  (dgl.sum_nodes, models.py:716,725,733,684);
+ * f = relu(BN(.)) when bn = {mean,rstd,gamma,beta} is given, identity otherwise. */
+SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn,
+                          float* out, void* stream);
+
+/* Debugging aid: byte offset of a named intermediate inside the pre-training workspace ("t", "H", "q", "C",
+ * "alpha", "lam", "y<enc>_<layer>", "gH", ...), -1 if unknown.  Tests compare intermediates with the oracle. */
+SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,
+                                                  int32_t Es, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGIB_H_ */

@@ -1,0 +1,466 @@
+// api.cu - the extern "C" surface of libscgib.so (include/scgib.h): parameter layout, workspace carving and the
+// launch sequences of the whole pre-training forward / backward.  No device memory is allocated here.
+#include <stdio.h>
+#include <string.h>
+#include "kernels.cuh"
+#include "../../include/scgib.h"
+
+namespace scgib {
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+static bool dims_ok(const ScgibDims* d) {
+  return d && d->hidden == HID && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&
+         d->in_dim <= 32;
+}
+
+struct Layout {
+  int64_t off[SCGIB_P_ENC + 2 * 8 * SCGIB_ENC_SLOTS];
+  int64_t size[SCGIB_P_ENC + 2 * 8 * SCGIB_ENC_SLOTS];
+  int n;
+  int64_t total;
+  int64_t enc(int e, int l, int L, int slot) const { return off[SCGIB_P_ENC + (e * L + l) * SCGIB_ENC_SLOTS + slot]; }
+};
+
+static Layout make_layout(const ScgibDims* d) {
+  Layout lo;
+  const int L = d->gin_layers;
+  int64_t sizes[SCGIB_P_ENC] = {
+      (int64_t)HID * 2 * HID, HID, (int64_t)HID * HID, HID,      // head
+      (int64_t)HID * HID, HID, HID, HID, HID, 1,                  // compressor
+      2 * HID, 1,                                                 // attention
+      (int64_t)DTR * d->in_dim};                                  // transfer_d
+  int n = 0;
+  int64_t o = 0;
+  auto push = [&](int64_t s) { lo.off[n] = o; lo.size[n] = s; o += (s + 3) / 4 * 4; ++n; };
+  for (int i = 0; i < SCGIB_P_ENC; ++i) push(sizes[i]);
+  for (int e = 0; e < 2; ++e)
+    for (int l = 0; l < L; ++l) {
+      const int kin = (l == 0) ? DTR : HID;
+      push((int64_t)HID * kin); push(HID); push((int64_t)HID * HID); push(HID); push(HID); push(HID);
+    }
+  lo.n = n;
+  lo.total = o;
+  return lo;
+}
+
+// ---------------------------------------------------------------- workspace
+struct Ws {
+  // transposed weights
+  float *enc_w1t[2][8], *enc_w2t[2][8], *head_w1t, *head_w2t, *comp_w1t;
+  float* t;
+  float *a[2][8], *r[2][8], *y[2][8];
+  float* bn[2][8];      // {mean, rstd, gamma, beta}
+  float* cvec;
+  float* small_part;    // BN partials (fwd) / dgamma,dbeta partials (bwd) / gate partials / input-proj partials
+  unsigned int* counters;
+  float *H, *q, *C, *logit, *alpha, *lam, *noisy, *Z, *r_head, *readout, *core, *gstat, *cstat, *kl;
+  float *rpart, *G, *edge;
+  float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout;
+  float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o, *Ga, *ga0[2];
+  float* ppart;
+  size_t bytes;
+};
+
+static size_t small_part_floats(int N, int Ns) {
+  const int Vmax = N > Ns ? N : Ns;
+  size_t a = (size_t)((Vmax + 127) / 128) * 2 * HID;                 // gin fwd tile partials
+  size_t b = (size_t)gin_bwd_pre_grid(Vmax) * 2 * HID;               // dgamma/dbeta partials
+  size_t c = (size_t)2 * num_sms() * 5 * HID;                        // gate partials
+  size_t d = (size_t)input_proj_bwd_grid(N, Ns) * DTR * 32;          // transfer_d partials
+  size_t m = a > b ? a : b;
+  m = m > c ? m : c;
+  return m > d ? m : d;
+}
+
+static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int Ns, int Es, void* base) {
+  Ws w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  const int L = d->gin_layers;
+  const int V[2] = {N, Ns};
+  const int Vmax = N > Ns ? N : Ns;
+  for (int e = 0; e < 2; ++e)
+    for (int l = 0; l < L; ++l) {
+      const int kin = l == 0 ? DTR : HID;
+      w.enc_w1t[e][l] = take((size_t)kin * HID);
+      w.enc_w2t[e][l] = take((size_t)HID * HID);
+      w.a[e][l] = take((size_t)V[e] * kin);
+      w.r[e][l] = take((size_t)V[e] * HID);
+      w.y[e][l] = take((size_t)V[e] * HID);
+      w.bn[e][l] = take(4 * HID);
+    }
+  w.head_w1t = take(2 * HID * HID); w.head_w2t = take(HID * HID); w.comp_w1t = take(HID * HID);
+  w.t = take((size_t)N * DTR);
+  w.cvec = take(2 * HID);
+  w.small_part = take(small_part_floats(N, Ns));
+  w.counters = (unsigned int*)take(64);
+  w.H = take((size_t)N * HID); w.q = take((size_t)N * HID); w.C = take((size_t)N * HID);
+  w.logit = take(N); w.alpha = take(N); w.lam = take(N);
+  w.noisy = take((size_t)N * HID); w.Z = take((size_t)N * HID); w.r_head = take((size_t)N * HID);
+  w.readout = take((size_t)B * HID); w.core = take((size_t)B * HID);
+  w.gstat = take((size_t)B * 4 * HID); w.cstat = take((size_t)B * 2 * HID); w.kl = take(4);
+  w.rpart = take((size_t)num_sms() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
+  const int js = contrastive_jsplit(B);
+  w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID);
+  w.n1 = take(B); w.n2 = take(B); w.diag = take(B); w.D = take(B);
+  w.rowsum = take((size_t)js * B);
+  w.g1p = take((size_t)js * B * HID); w.g2p = take((size_t)js * B * HID);
+  w.g_core = take((size_t)B * HID); w.g_readout = take((size_t)B * HID);
+  w.gZ = take((size_t)N * HID); w.gI = take((size_t)N * 2 * HID); w.gp = take(N);
+  w.g_q = take((size_t)N * HID); w.gH = take((size_t)N * HID); w.gC = take((size_t)N * HID);
+  w.g_o = take((size_t)Vmax * HID); w.Ga = take((size_t)Vmax * HID);
+  w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
+  w.ppart = take((size_t)num_sms() * lo.total);
+  w.bytes = o;
+  (void)E; (void)Es;
+  return w;
+}
+
+static int check_batch(const ScgibBatch* b) {
+  if (!b) return SCGIB_E_NULL;
+  if (b->B < 1 || b->N < 2 || b->Ns < b->N || b->E < 0 || b->Es < 0) return SCGIB_E_RANGE;
+  if (!b->graph_ptr || !b->indptr || !b->ego_ptr || !b->ego_nodes || !b->ego_seed || !b->sub_indptr || !b->x ||
+      !b->gate_u || !b->feat_u)
+    return SCGIB_E_NULL;
+  if ((b->E > 0 && !b->indices) || (b->Es > 0 && !b->sub_indices)) return SCGIB_E_NULL;
+  if (((uintptr_t)b->feat_u & 15u) != 0) return SCGIB_E_ALIGN;
+  return SCGIB_OK;
+}
+
+}  // namespace scgib
+
+using namespace scgib;
+
+extern "C" SCGIB_API int scgib_version(void) { return SCGIB_VERSION; }
+
+extern "C" SCGIB_API const char* scgib_error_string(int code) {
+  switch (code) {
+    case SCGIB_OK: return "ok";
+    case SCGIB_E_NULL: return "required pointer is NULL";
+    case SCGIB_E_SHAPE: return "unsupported dimensions (hidden must be 64, d_transfer 32, 1 <= gin_layers <= 8, in_dim <= 32)";
+    case SCGIB_E_ALIGN: return "pointer not 16-byte aligned";
+    case SCGIB_E_WORKSPACE: return "workspace too small";
+    case SCGIB_E_RANGE: return "size out of range";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown scgib error";
+  }
+}
+
+extern "C" SCGIB_API int scgib_num_sms(void) { return num_sms(); }
+
+extern "C" SCGIB_API int32_t scgib_param_slots(const ScgibDims* d) {
+  if (!dims_ok(d)) return SCGIB_E_SHAPE;
+  return SCGIB_P_ENC + 2 * d->gin_layers * SCGIB_ENC_SLOTS;
+}
+
+extern "C" SCGIB_API int64_t scgib_param_layout(const ScgibDims* d, int64_t* offsets, int64_t* sizes) {
+  if (!dims_ok(d)) return SCGIB_E_SHAPE;
+  const Layout lo = make_layout(d);
+  for (int i = 0; i < lo.n; ++i) {
+    if (offsets) offsets[i] = lo.off[i];
+    if (sizes) sizes[i] = lo.size[i];
+  }
+  return lo.total;
+}
+
+extern "C" SCGIB_API size_t scgib_pretrain_workspace_bytes(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns, int32_t Es) {
+  if (!dims_ok(d)) return 0;
+  const Layout lo = make_layout(d);
+  return carve(d, lo, B, N, E, Ns, Es, nullptr).bytes;
+}
+
+extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
+                                          const ScgibBatch* b, float* losses, float* interaction_map, float* Z,
+                                          float* noisy, float* graph_readout, void* workspace, size_t workspace_bytes,
+                                          void* stream_) {
+  if (!dims_ok(d)) return SCGIB_E_SHAPE;
+  if (!params || !losses || !workspace) return SCGIB_E_NULL;
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)params & 15u) != 0) return SCGIB_E_ALIGN;
+  const Layout lo = make_layout(d);
+  const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int L = d->gin_layers;
+
+  cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
+  // k-major weight copies for the forward GEMMs
+  {
+    TransposeJobs jobs;
+    jobs.n = 0;
+    auto add = [&](const float* src, float* dst, int rows, int cols) { jobs.job[jobs.n++] = TransposeJob{src, dst, rows, cols}; };
+    for (int e = 0; e < 2; ++e)
+      for (int l = 0; l < L; ++l) {
+        add(params + lo.enc(e, l, L, SCGIB_ENC_W1), w.enc_w1t[e][l], HID, l == 0 ? DTR : HID);
+        add(params + lo.enc(e, l, L, SCGIB_ENC_W2), w.enc_w2t[e][l], HID, HID);
+        if (jobs.n >= 22) { launch_transposes(jobs, s); jobs.n = 0; }
+      }
+    add(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1t, HID, 2 * HID);
+    add(params + lo.off[SCGIB_P_HEAD_W2], w.head_w2t, HID, HID);
+    add(params + lo.off[SCGIB_P_COMP_W1], w.comp_w1t, HID, HID);
+    launch_transposes(jobs, s);
+  }
+  launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s);
+  // the two GIN encoders (models.py:704, 707)
+  for (int e = 0; e < 2; ++e) {
+    for (int l = 0; l < L; ++l) {
+      GinFwdArgs a;
+      a.in = l == 0 ? w.t : w.y[e][l - 1];
+      a.row_map = (e == 1 && l == 0) ? b->ego_nodes : nullptr;
+      a.bn_in = l == 0 ? nullptr : w.bn[e][l - 1];
+      a.indptr = e == 0 ? b->indptr : b->sub_indptr;
+      a.indices = e == 0 ? b->indices : b->sub_indices;
+      a.V = e == 0 ? b->N : b->Ns;
+      a.W1t = w.enc_w1t[e][l]; a.b1 = params + lo.enc(e, l, L, SCGIB_ENC_B1);
+      a.W2t = w.enc_w2t[e][l]; a.b2 = params + lo.enc(e, l, L, SCGIB_ENC_B2);
+      a.gamma = params + lo.enc(e, l, L, SCGIB_ENC_GAMMA); a.beta = params + lo.enc(e, l, L, SCGIB_ENC_BETA);
+      a.a_out = w.a[e][l]; a.r_out = w.r[e][l]; a.y_out = w.y[e][l];
+      a.part = w.small_part; a.counter = w.counters + 0;
+      a.bn_out = w.bn[e][l];
+      a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
+      launch_gin_fwd(a, l == 0 ? DTR : HID, s);
+    }
+  }
+  {
+    GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q};
+    launch_gate_lin_fwd(a, s);
+  }
+  {
+    EgoPoolFwdArgs a{w.y[1][L - 1], w.bn[1][L - 1], b->ego_ptr, b->N, params + lo.off[SCGIB_P_ATTN_W] + HID, w.C, w.logit};
+    launch_ego_pool_fwd(a, s);
+  }
+  {
+    GraphGateFwdArgs a;
+    a.graph_ptr = b->graph_ptr; a.B = b->B; a.N = b->N; a.H = w.H; a.q = w.q;
+    a.gamma_c = params + lo.off[SCGIB_P_COMP_GAMMA]; a.beta_c = params + lo.off[SCGIB_P_COMP_BETA];
+    a.wc2 = params + lo.off[SCGIB_P_COMP_W2]; a.bc2 = params + lo.off[SCGIB_P_COMP_B2];
+    a.gate_u = b->gate_u; a.feat_u = b->feat_u; a.logit = w.logit;
+    a.noisy = w.noisy; a.lam = w.lam; a.alpha = w.alpha; a.readout = w.readout; a.core = w.core;
+    a.gstat = w.gstat; a.cstat = bn_running ? w.cstat : nullptr; a.kl = w.kl;
+    launch_graph_gate_fwd(a, s);
+    if (bn_running) launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s);
+  }
+  {
+    HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
+                  params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.r_head, w.Z};
+    launch_head_fwd(a, s);
+  }
+  {
+    const int grid = num_sms();
+    ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
+    launch_recon_fwd(a, grid, s);
+    launch_recon_reduce(w.rpart, grid, w.G, w.edge, s);
+  }
+  const int js = contrastive_jsplit(b->B);
+  {
+    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag};
+    launch_normalize(a, s);
+    ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum};
+    launch_contrastive_fwd(c, s);
+  }
+  {
+    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, w.kl, w.D, losses};
+    launch_loss_finalize(a, s);
+  }
+  if (Z) cudaMemcpyAsync(Z, w.Z, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (noisy) cudaMemcpyAsync(noisy, w.noisy, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (graph_readout) cudaMemcpyAsync(graph_readout, w.readout, (size_t)b->B * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* b,
+                                           const float* loss_scale, float* grads, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  if (!dims_ok(d)) return SCGIB_E_SHAPE;
+  if (!params || !grads || !workspace || !loss_scale) return SCGIB_E_NULL;
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)params & 15u) != 0 || ((uintptr_t)grads & 15u) != 0) return SCGIB_E_ALIGN;
+  const Layout lo = make_layout(d);
+  const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int L = d->gin_layers;
+  const int GP = num_sms();
+  const float s_kl = loss_scale[0], s_con = loss_scale[1], s_rec = loss_scale[2];
+
+  cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
+  const int js = contrastive_jsplit(b->B);
+  {
+    ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
+    launch_contrastive_bwd(a, s);
+    ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
+    launch_contrastive_bwd_finalize(f, s);
+  }
+  {
+    ReconBwdArgs a{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+    launch_recon_bwd(a, s);
+  }
+  {
+    HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
+                  params + lo.off[SCGIB_P_HEAD_W2], w.gI, w.ppart, lo.total,
+                  lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_W2], lo.off[SCGIB_P_HEAD_B2]};
+    launch_head_bwd(a, GP, s);
+  }
+  {
+    GraphGateBwdArgs a;
+    a.graph_ptr = b->graph_ptr; a.B = b->B; a.N = b->N; a.H = w.H; a.q = w.q; a.C = w.C;
+    a.gamma_c = params + lo.off[SCGIB_P_COMP_GAMMA]; a.beta_c = params + lo.off[SCGIB_P_COMP_BETA];
+    a.wc2 = params + lo.off[SCGIB_P_COMP_W2]; a.w_cand = params + lo.off[SCGIB_P_ATTN_W] + HID;
+    a.feat_u = b->feat_u; a.lam = w.lam; a.alpha = w.alpha; a.gstat = w.gstat;
+    a.gI = w.gI; a.g_core = w.g_core; a.g_readout = w.g_readout; a.kl_scale = s_kl;
+    a.gp = w.gp; a.g_q = w.g_q; a.gH = w.gH; a.gC = w.gC;
+    a.part = w.small_part; a.counter = w.counters + 1;
+    a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
+    a.d_wc2 = grads + lo.off[SCGIB_P_COMP_W2]; a.d_bc2 = grads + lo.off[SCGIB_P_COMP_B2];
+    a.d_attn_w = grads + lo.off[SCGIB_P_ATTN_W]; a.d_attn_b = grads + lo.off[SCGIB_P_ATTN_B];
+    launch_graph_gate_bwd(a, s);
+  }
+  {
+    GateLinBwdArgs a{w.g_q, w.H, b->N, params + lo.off[SCGIB_P_COMP_W1], w.gH, w.ppart, lo.total,
+                     lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1]};
+    launch_gate_lin_bwd(a, GP, s);
+  }
+  for (int e = 0; e < 2; ++e) {
+    const int V = e == 0 ? b->N : b->Ns;
+    const int32_t* indptr = e == 0 ? b->indptr : b->sub_indptr;
+    const int32_t* indices = e == 0 ? b->indices : b->sub_indices;
+    for (int l = L - 1; l >= 0; --l) {
+      const int kin = l == 0 ? DTR : HID;
+      GinBwdPreArgs pa;
+      if (l == L - 1) {
+        pa.src = e == 0 ? w.gH : w.gC; pa.indptr = nullptr; pa.indices = nullptr; pa.map = e == 0 ? nullptr : b->ego_seed;
+      } else {
+        pa.src = w.Ga; pa.indptr = indptr; pa.indices = indices; pa.map = nullptr;
+      }
+      pa.y = w.y[e][l]; pa.bn = w.bn[e][l]; pa.V = V; pa.g_o = w.g_o; pa.part = w.small_part; pa.counter = w.counters + 2;
+      pa.d_gamma = grads + lo.enc(e, l, L, SCGIB_ENC_GAMMA); pa.d_beta = grads + lo.enc(e, l, L, SCGIB_ENC_BETA);
+      pa.cvec = w.cvec;
+      launch_gin_bwd_pre(pa, s);
+      GinBwdMainArgs ma;
+      ma.g_o = w.g_o; ma.y = w.y[e][l]; ma.r = w.r[e][l]; ma.a = w.a[e][l]; ma.bn = w.bn[e][l]; ma.cvec = w.cvec;
+      ma.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); ma.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
+      ma.V = V; ma.g_a = l == 0 ? w.ga0[e] : w.Ga; ma.part = w.ppart; ma.pstride = lo.total;
+      ma.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); ma.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
+      ma.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); ma.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
+      launch_gin_bwd_main(ma, kin, GP, s);
+    }
+  }
+  {
+    InputProjBwdArgs a;
+    a.ga[0] = w.ga0[0]; a.ga[1] = w.ga0[1];
+    a.indptr[0] = b->indptr; a.indptr[1] = b->sub_indptr; a.indices[0] = b->indices; a.indices[1] = b->sub_indices;
+    a.map[0] = nullptr; a.map[1] = b->ego_nodes; a.V[0] = b->N; a.V[1] = b->Ns;
+    a.x = b->x; a.F = d->in_dim; a.normalize = b->normalize_x; a.part = w.small_part; a.counter = w.counters + 3;
+    a.d_Wt = grads + lo.off[SCGIB_P_TRANSFER];
+    launch_input_proj_bwd(a, s);
+  }
+  {
+    ReduceRanges r;
+    r.n = 0;
+    auto add = [&](int64_t off, int64_t len) { r.off[r.n] = off; r.len[r.n] = len; ++r.n; };
+    add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1]);
+    add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1]);
+    for (int e = 0; e < 2; ++e)
+      for (int l = 0; l < L; ++l) add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1));
+    launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return SCGIB_E_NULL;
+  if (n < 1 || step < 1) return SCGIB_E_RANGE;
+  launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- individual operators
+extern "C" SCGIB_API int scgib_input_proj_fwd_f32(const float* x, const float* Wt, int32_t N, int32_t F, int32_t DT, float* t, void* stream) {
+  if (!x || !Wt || !t) return SCGIB_E_NULL;
+  if (DT != DTR || F < 1 || F > 32) return SCGIB_E_SHAPE;
+  if (N < 1) return SCGIB_E_RANGE;
+  launch_input_proj_fwd(x, Wt, N, F, 1, t, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API size_t scgib_gin_workspace_bytes(int32_t V) {
+  return al((size_t)((V + 127) / 128) * 2 * HID * sizeof(float)) + al(HID * HID * sizeof(float)) * 2 + 256;
+}
+
+extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, const int32_t* row_map, const float* bn_in,
+                                       const int32_t* indptr, const int32_t* indices, int32_t V, const float* W1,
+                                       const float* b1, const float* W2, const float* b2, float* a_out, float* r_out,
+                                       float* y_out, float* bn_out, float* running, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  if (!in || !indptr || !W1 || !b1 || !W2 || !b2 || !y_out || !bn_out || !workspace) return SCGIB_E_NULL;
+  if (kin != DTR && kin != HID) return SCGIB_E_SHAPE;
+  if (bn_in && kin != HID) return SCGIB_E_SHAPE;
+  if (V < 1) return SCGIB_E_RANGE;
+  if (workspace_bytes < scgib_gin_workspace_bytes(V)) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  char* p = (char*)workspace;
+  float* w1t = (float*)p; p += al(HID * HID * sizeof(float));
+  float* w2t = (float*)p; p += al(HID * HID * sizeof(float));
+  unsigned int* counter = (unsigned int*)p; p += 256;
+  float* part = (float*)p;
+  cudaMemsetAsync(counter, 0, 256, s);
+  TransposeJobs jobs;
+  jobs.n = 2;
+  jobs.job[0] = TransposeJob{W1, w1t, HID, kin};
+  jobs.job[1] = TransposeJob{W2, w2t, HID, HID};
+  launch_transposes(jobs, s);
+  GinFwdArgs a;
+  a.in = in; a.row_map = row_map; a.bn_in = bn_in; a.indptr = indptr; a.indices = indices; a.V = V;
+  a.W1t = w1t; a.b1 = b1; a.W2t = w2t; a.b2 = b2;
+  a.gamma = nullptr; a.beta = nullptr;
+  a.a_out = a_out; a.r_out = r_out; a.y_out = y_out; a.part = part; a.counter = counter; a.bn_out = bn_out; a.running = running;
+  launch_gin_fwd(a, kin, s);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn, float* out, void* stream) {
+  if (!in || !seg_ptr || !out) return SCGIB_E_NULL;
+  if (S < 1) return SCGIB_E_RANGE;
+  launch_segment_sum(in, seg_ptr, S, bn, out, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- debugging aid
+// Byte offset of a named workspace buffer (tests compare intermediates with the oracle); -1 if unknown.
+extern "C" SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E,
+                                                             int32_t Ns, int32_t Es, const char* name) {
+  if (!dims_ok(d) || !name) return -1;
+  const Layout lo = make_layout(d);
+  const Ws w = carve(d, lo, B, N, E, Ns, Es, nullptr);
+  struct { const char* n; const void* p; } tab[] = {
+      {"t", w.t}, {"H", w.H}, {"q", w.q}, {"C", w.C}, {"logit", w.logit}, {"alpha", w.alpha}, {"lam", w.lam},
+      {"noisy", w.noisy}, {"Z", w.Z}, {"r_head", w.r_head}, {"readout", w.readout}, {"core", w.core}, {"gstat", w.gstat},
+      {"kl", w.kl}, {"G", w.G}, {"edge", w.edge}, {"z1", w.z1}, {"z2", w.z2}, {"D", w.D}, {"diag", w.diag},
+      {"g_core", w.g_core}, {"g_readout", w.g_readout}, {"gZ", w.gZ}, {"gI", w.gI}, {"gp", w.gp}, {"g_q", w.g_q},
+      {"gH", w.gH}, {"gC", w.gC}, {"ga0_1", w.ga0[0]}, {"ga0_2", w.ga0[1]}, {"cvec", w.cvec}};
+  for (auto& e : tab)
+    if (!strcmp(e.n, name)) return (int64_t)((const char*)e.p - (const char*)nullptr);
+  int e = 0, l = 0;
+  char kind = 0;
+  if (sscanf(name, "%c%d_%d", &kind, &e, &l) == 3 && (e == 1 || e == 2) && l >= 0 && l < d->gin_layers) {
+    const void* p = kind == 'y' ? w.y[e - 1][l] : kind == 'a' ? w.a[e - 1][l] : kind == 'r' ? w.r[e - 1][l]
+                    : kind == 'b' ? w.bn[e - 1][l] : nullptr;
+    if (p) return (int64_t)((const char*)p - (const char*)nullptr);
+  }
+  return -1;
+}

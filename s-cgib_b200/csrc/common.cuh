@@ -1,0 +1,173 @@
+// common.cuh - shared device helpers for the S-CGIB sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scgib {
+
+constexpr int HID = 64;        // hidden width (exp_pretraining.py:390)
+constexpr int DTR = 32;        // d_transfer   (exp_pretraining.py:378)
+constexpr int kThreads = 256;  // CTA size of every tile kernel
+constexpr float kBnEps = 1e-5f;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 make4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 relu4(float4 a) {
+  return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+
+// relu(BN(y)) for 4 consecutive channels: ((y - mean) * rstd) * gamma + beta
+struct Bn4 {
+  float4 mean, rstd, gamma, beta;
+  __device__ __forceinline__ void load(const float* bn, int c) {  // bn = {mean[H], rstd[H], gamma[H], beta[H]}
+    mean = ldg4(bn + c); rstd = ldg4(bn + HID + c); gamma = ldg4(bn + 2 * HID + c); beta = ldg4(bn + 3 * HID + c);
+  }
+  __device__ __forceinline__ float4 xhat(float4 y) const {
+    return make_float4((y.x - mean.x) * rstd.x, (y.y - mean.y) * rstd.y, (y.z - mean.z) * rstd.z, (y.w - mean.w) * rstd.w);
+  }
+  __device__ __forceinline__ float4 pre(float4 y) const {  // BN output before the ReLU
+    float4 h = xhat(y);
+    return make_float4(fmaf(h.x, gamma.x, beta.x), fmaf(h.y, gamma.y, beta.y), fmaf(h.z, gamma.z, beta.z), fmaf(h.w, gamma.w, beta.w));
+  }
+  __device__ __forceinline__ float4 act(float4 y) const { return relu4(pre(y)); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// "last CTA finalises" pattern: every CTA publishes its partials, the last one to arrive reduces
+// them in a fixed order (deterministic, no float atomics) and resets the counter for the next launch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-tiled FP32 tile GEMMs out of shared memory (256 threads).
+//   gemm_nn : C[TILE_M][N] += A[TILE_M][K] (row-major, lda) * B[K][N] (k-major, ldb)
+//             thread (tr, tc): rows tr*TM..+TM, cols tc*4..+4 ; TM = TILE_M*N/1024
+//   gemm_tn : C[NX][NY]   += X[rows][NX]^T * Y[rows][NY]    (reduction over the tile rows)
+//             thread (ti, tj) of a 16x16 arrangement: ti*TO..+TO of NX, tj*TJ..+TJ of NY
+// ------------------------------------------------------------------------------------------------
+template <int TILE_M, int N>
+struct NNMap {
+  static constexpr int CG = N / 4;
+  static constexpr int RG = kThreads / CG;
+  static constexpr int TM = TILE_M / RG;
+  static_assert(TM >= 1 && TM * RG == TILE_M, "bad tile");
+  __device__ static __forceinline__ int tc() { return threadIdx.x % CG; }
+  __device__ static __forceinline__ int tr() { return threadIdx.x / CG; }
+  __device__ static __forceinline__ int row0() { return tr() * TM; }
+  __device__ static __forceinline__ int col0() { return tc() * 4; }
+};
+
+template <int TILE_M, int K, int N>
+__device__ __forceinline__ void gemm_nn(const float* __restrict__ As, int lda, const float* __restrict__ Bs, int ldb,
+                                        float (&acc)[NNMap<TILE_M, N>::TM][4]) {
+  using M = NNMap<TILE_M, N>;
+  const float* a0 = As + M::row0() * lda;
+  const float* b0 = Bs + M::col0();
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float4 b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = ld4(b0 + (k + i) * ldb);
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) {
+      const float4 a = ld4(a0 + m * lda + k);
+      acc[m][0] = fmaf(a.x, b[0].x, acc[m][0]); acc[m][1] = fmaf(a.x, b[0].y, acc[m][1]);
+      acc[m][2] = fmaf(a.x, b[0].z, acc[m][2]); acc[m][3] = fmaf(a.x, b[0].w, acc[m][3]);
+      acc[m][0] = fmaf(a.y, b[1].x, acc[m][0]); acc[m][1] = fmaf(a.y, b[1].y, acc[m][1]);
+      acc[m][2] = fmaf(a.y, b[1].z, acc[m][2]); acc[m][3] = fmaf(a.y, b[1].w, acc[m][3]);
+      acc[m][0] = fmaf(a.z, b[2].x, acc[m][0]); acc[m][1] = fmaf(a.z, b[2].y, acc[m][1]);
+      acc[m][2] = fmaf(a.z, b[2].z, acc[m][2]); acc[m][3] = fmaf(a.z, b[2].w, acc[m][3]);
+      acc[m][0] = fmaf(a.w, b[3].x, acc[m][0]); acc[m][1] = fmaf(a.w, b[3].y, acc[m][1]);
+      acc[m][2] = fmaf(a.w, b[3].z, acc[m][2]); acc[m][3] = fmaf(a.w, b[3].w, acc[m][3]);
+    }
+  }
+}
+
+template <int NX, int NY>
+struct TNMap {
+  static constexpr int TO = NX / 16;
+  static constexpr int TJ = NY / 16;
+  static_assert(TO >= 1 && TJ >= 1 && TO % 2 == 0 && TJ % 2 == 0, "bad tn tile");
+  __device__ static __forceinline__ int ti() { return threadIdx.x / 16; }
+  __device__ static __forceinline__ int tj() { return threadIdx.x % 16; }
+  __device__ static __forceinline__ int o0() { return ti() * TO; }
+  __device__ static __forceinline__ int j0() { return tj() * TJ; }
+};
+
+template <int NX, int NY>
+__device__ __forceinline__ void gemm_tn(const float* __restrict__ Xs, int ldx, const float* __restrict__ Ys, int ldy,
+                                        int rows, float (&acc)[TNMap<NX, NY>::TO][TNMap<NX, NY>::TJ]) {
+  using M = TNMap<NX, NY>;
+  const float* x0 = Xs + M::o0();
+  const float* y0 = Ys + M::j0();
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    float xv[M::TO], yv[M::TJ];
+#pragma unroll
+    for (int i = 0; i < M::TO; i += 2) {
+      const float2 t = *reinterpret_cast<const float2*>(x0 + r * ldx + i);
+      xv[i] = t.x; xv[i + 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < M::TJ; j += 2) {
+      const float2 t = *reinterpret_cast<const float2*>(y0 + r * ldy + j);
+      yv[j] = t.x; yv[j + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < M::TO; ++i)
+#pragma unroll
+      for (int j = 0; j < M::TJ; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+  }
+}
+
+// cooperative copy of a dense [rows][cols] fp32 matrix (global, contiguous) into smem with leading dim ld
+template <int COLS>
+__device__ __forceinline__ void load_matrix(float* __restrict__ dst, int ld, const float* __restrict__ src, int rows) {
+  constexpr int C4 = COLS / 4;
+  for (int i = threadIdx.x; i < rows * C4; i += kThreads) {
+    const int r = i / C4, c = (i % C4) * 4;
+    st4(dst + r * ld + c, ldg4(src + (size_t)r * COLS + c));
+  }
+}
+
+// load a [TILE_M][COLS] row tile of a global [V][COLS] matrix into smem (zero-fill rows >= V)
+template <int TILE_M, int COLS>
+__device__ __forceinline__ void load_row_tile(float* __restrict__ dst, int ld, const float* __restrict__ src,
+                                              int row_base, int V) {
+  constexpr int C4 = COLS / 4;
+  for (int i = threadIdx.x; i < TILE_M * C4; i += kThreads) {
+    const int r = i / C4, c = (i % C4) * 4;
+    const int v = row_base + r;
+    float4 val = make4(0.f);
+    if (v < V) val = ld4(src + (size_t)v * COLS + c);
+    st4(dst + r * ld + c, val);
+  }
+}
+
+}  // namespace scgib

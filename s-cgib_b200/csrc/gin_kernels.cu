@@ -1,0 +1,523 @@
+// gin_kernels.cu - input projection and the GIN encoder (forward + backward) as fused row-tile kernels.
+//
+// Reference call sites replaced (paths relative to the reference tree):
+//   F.normalize + transfer_d        exp_pretraining.py:312-314, models.py:668-669
+//   GIN.forward                     models.py:66-72   (DGL GINConv 'sum', eps = 0 buffer; MLP models.py:38-49;
+//                                                      BatchNorm1d train mode over all rows; ReLU)
+// One forward launch per GINConv layer:
+//   gather-aggregate (CSR segmented reduce, float4 lanes, BN+ReLU of the previous layer applied on load)
+//   -> 2-GEMM MLP out of shared memory -> y (pre-BN) + per-tile (mean, M2) -> last CTA finalises the batch
+//   statistics (Chan combine in fp64, fixed order) and the running-stat EMA.
+// Backward per layer: `gin_bwd_pre` (gather of the upstream gradient, ReLU/BN mask, d gamma / d beta with an
+// in-kernel deterministic finalise) then `gin_bwd_main` (BN backward, 4 tile GEMMs: g_r, g_a, dW2, dW1).
+#include "kernels.cuh"
+
+namespace scgib {
+
+// ------------------------------------------------------------------------------------------------
+// x_hat = x / max(||x||_2, 1e-12);  t = x_hat Wt^T          (Wt [DTR][F])
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt, int N, int F, int normalize,
+                      float* __restrict__ t) {
+  __shared__ float s_w[32 * DTR];  // [f][o]
+  for (int i = threadIdx.x; i < F * DTR; i += kThreads) {
+    const int o = i / F, f = i % F;
+    s_w[f * DTR + o] = Wt[i];
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 7;  // output quad
+  for (int v = blockIdx.x * (kThreads / 8) + (threadIdx.x >> 3); v < N; v += gridDim.x * (kThreads / 8)) {
+    const float* xr = x + (size_t)v * F;
+    float ss = 0.f;
+    for (int f = 0; f < F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
+    const float inv = normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    float4 acc = make4(0.f);
+    for (int f = 0; f < F; ++f) {
+      const float a = __ldg(xr + f) * inv;
+      const float4 w = ld4(s_w + f * DTR + q * 4);
+      acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
+    }
+    st4(t + (size_t)v * DTR + q * 4, acc);
+  }
+}
+
+void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s) {
+  const int grid = min((N + 31) / 32, 148 * 8);
+  input_proj_fwd_kernel<<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched transposes of small weight matrices (forward kernels want k-major copies)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) transpose_many_kernel(TransposeJobs jobs) {
+  const TransposeJob j = jobs.job[blockIdx.x];
+  for (int i = threadIdx.x; i < j.rows * j.cols; i += kThreads) {
+    const int c = i / j.rows, r = i % j.rows;   // consecutive threads write consecutive dst elements
+    j.dst[(size_t)c * j.rows + r] = __ldg(j.src + (size_t)r * j.cols + c);
+  }
+}
+void launch_transposes(const TransposeJobs& jobs, cudaStream_t s) {
+  if (jobs.n > 0) transpose_many_kernel<<<jobs.n, kThreads, 0, s>>>(jobs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GIN layer forward
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 128;        // rows per tile
+constexpr int GLD = HID + 4;   // smem leading dim (row-major tiles)
+
+template <int KIN>
+struct GinFwdSmem {
+  float tile[GT * GLD];        // A tile [GT][KIN+4] then R tile [GT][HID+4]
+  float w1t[KIN * HID];
+  float w2t[HID * HID];
+  float red[16 * HID];
+  float b1[HID], b2[HID], mean[HID];
+  double dred[4 * HID];
+};
+
+template <int KIN>
+__global__ void __launch_bounds__(kThreads, 2)
+gin_fwd_kernel(GinFwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GinFwdSmem<KIN>& sm = *reinterpret_cast<GinFwdSmem<KIN>*>(smem_raw);
+  constexpr int LDA = KIN + 4;
+  constexpr int LPR = KIN / 4;             // lanes per row in the gather
+  constexpr int RPP = kThreads / LPR;      // rows per pass
+  using M = NNMap<GT, HID>;
+
+  load_matrix<HID>(sm.w1t, HID, p.W1t, KIN);
+  load_matrix<HID>(sm.w2t, HID, p.W2t, HID);
+  if (threadIdx.x < HID) { sm.b1[threadIdx.x] = p.b1[threadIdx.x]; sm.b2[threadIdx.x] = p.b2[threadIdx.x]; }
+
+  const int n_tiles = (p.V + GT - 1) / GT;
+  const int gl = threadIdx.x % LPR, gr = threadIdx.x / LPR;
+  Bn4 bn;
+  const bool has_bn = (p.bn_in != nullptr);
+  if (has_bn) bn.load(p.bn_in, gl * 4);   // KIN == HID whenever a BN precedes the layer
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int base = tile * GT;
+    __syncthreads();  // previous tile's readers of sm.tile are done (also covers the weight loads)
+    // ---- gather-aggregate: a_v = f(in[map(v)]) + sum_u f(in[map(u)])
+    for (int r = gr; r < GT; r += RPP) {
+      const int v = base + r;
+      float4 acc = make4(0.f);
+      if (v < p.V) {
+        const int sv = p.row_map ? __ldg(p.row_map + v) : v;
+        float4 h = ld4(p.in + (size_t)sv * KIN + gl * 4);
+        acc = has_bn ? bn.act(h) : h;
+        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
+        for (int e = e0; e < e1; ++e) {
+          const int u = __ldg(p.indices + e);
+          const int su = p.row_map ? __ldg(p.row_map + u) : u;
+          h = ld4(p.in + (size_t)su * KIN + gl * 4);
+          acc = add4(acc, has_bn ? bn.act(h) : h);
+        }
+        if (p.a_out) st4(p.a_out + (size_t)v * KIN + gl * 4, acc);
+      }
+      st4(sm.tile + r * LDA + gl * 4, acc);
+    }
+    __syncthreads();
+    // ---- u = W1 a + b1 ; r = relu(u)
+    float acc[M::TM][4];
+    const int c0 = M::col0(), r0 = M::row0();
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) { acc[m][0] = sm.b1[c0]; acc[m][1] = sm.b1[c0 + 1]; acc[m][2] = sm.b1[c0 + 2]; acc[m][3] = sm.b1[c0 + 3]; }
+    gemm_nn<GT, KIN, HID>(sm.tile, LDA, sm.w1t, HID, acc);
+    __syncthreads();  // everyone finished reading the A tile
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) {
+      const float4 rv = relu4(make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
+      st4(sm.tile + (r0 + m) * GLD + c0, rv);
+      const int v = base + r0 + m;
+      if (p.r_out && v < p.V) st4(p.r_out + (size_t)v * HID + c0, rv);
+    }
+    __syncthreads();
+    // ---- y = W2 r + b2
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) { acc[m][0] = sm.b2[c0]; acc[m][1] = sm.b2[c0 + 1]; acc[m][2] = sm.b2[c0 + 2]; acc[m][3] = sm.b2[c0 + 3]; }
+    gemm_nn<GT, HID, HID>(sm.tile, GLD, sm.w2t, HID, acc);
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) {
+      const int v = base + r0 + m;
+      if (v < p.V) {
+        st4(p.y_out + (size_t)v * HID + c0, make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
+        ps[0] += acc[m][0]; ps[1] += acc[m][1]; ps[2] += acc[m][2]; ps[3] += acc[m][3];
+      }
+    }
+    // ---- per-tile column mean and centred second moment
+    const int cnt = min(GT, p.V - base);
+    st4(sm.red + M::tr() * HID + c0, make_float4(ps[0], ps[1], ps[2], ps[3]));
+    __syncthreads();
+    if (threadIdx.x < HID) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < M::RG; ++g) s += sm.red[g * HID + threadIdx.x];
+      sm.mean[threadIdx.x] = s / (float)cnt;
+    }
+    __syncthreads();
+    {
+      const float4 mu = ld4(sm.mean + c0);
+      ps[0] = ps[1] = ps[2] = ps[3] = 0.f;
+#pragma unroll
+      for (int m = 0; m < M::TM; ++m) {
+        if (base + r0 + m < p.V) {
+          float d;
+          d = acc[m][0] - mu.x; ps[0] = fmaf(d, d, ps[0]);
+          d = acc[m][1] - mu.y; ps[1] = fmaf(d, d, ps[1]);
+          d = acc[m][2] - mu.z; ps[2] = fmaf(d, d, ps[2]);
+          d = acc[m][3] - mu.w; ps[3] = fmaf(d, d, ps[3]);
+        }
+      }
+      st4(sm.red + M::tr() * HID + c0, make_float4(ps[0], ps[1], ps[2], ps[3]));
+    }
+    __syncthreads();
+    if (threadIdx.x < HID) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < M::RG; ++g) s += sm.red[g * HID + threadIdx.x];
+      p.part[(size_t)tile * 2 * HID + threadIdx.x] = sm.mean[threadIdx.x];
+      p.part[(size_t)tile * 2 * HID + HID + threadIdx.x] = s;
+    }
+  }
+  // ---- batch statistics: last CTA combines the per-tile (n, mean, M2) in fp64, fixed order
+  if (!last_cta_arrives(p.counter)) return;
+  const int c = threadIdx.x & (HID - 1), seg = threadIdx.x >> 6;
+  double s = 0.0;
+  for (int t = seg; t < n_tiles; t += 4) {
+    const double n = (double)min(GT, p.V - t * GT);
+    s += n * (double)__ldcg(p.part + (size_t)t * 2 * HID + c);
+  }
+  sm.dred[seg * HID + c] = s;
+  __syncthreads();
+  const double mean = (sm.dred[c] + sm.dred[HID + c] + sm.dred[2 * HID + c] + sm.dred[3 * HID + c]) / (double)p.V;
+  __syncthreads();
+  double q = 0.0;
+  for (int t = seg; t < n_tiles; t += 4) {
+    const double n = (double)min(GT, p.V - t * GT);
+    const double d = (double)__ldcg(p.part + (size_t)t * 2 * HID + c) - mean;
+    q += (double)__ldcg(p.part + (size_t)t * 2 * HID + HID + c) + n * d * d;
+  }
+  sm.dred[seg * HID + c] = q;
+  __syncthreads();
+  if (threadIdx.x < HID) {
+    const double var = (sm.dred[c] + sm.dred[HID + c] + sm.dred[2 * HID + c] + sm.dred[3 * HID + c]) / (double)p.V;
+    p.bn_out[c] = (float)mean;
+    p.bn_out[HID + c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+    if (p.gamma) { p.bn_out[2 * HID + c] = p.gamma[c]; p.bn_out[3 * HID + c] = p.beta[c]; }
+    if (p.running) {
+      const double unb = p.V > 1 ? var * (double)p.V / (double)(p.V - 1) : var;
+      p.running[c] = 0.9f * p.running[c] + 0.1f * (float)mean;
+      p.running[HID + c] = 0.9f * p.running[HID + c] + 0.1f * (float)unb;
+    }
+  }
+}
+
+int gin_fwd_grid(int V) {
+  const int n_tiles = (V + GT - 1) / GT;
+  return min(n_tiles, 2 * num_sms());
+}
+
+void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
+  const int grid = gin_fwd_grid(a.V);
+  if (kin == DTR) {
+    static bool once = (cudaFuncSetAttribute(gin_fwd_kernel<DTR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(GinFwdSmem<DTR>)), true);
+    (void)once;
+    gin_fwd_kernel<DTR><<<grid, kThreads, sizeof(GinFwdSmem<DTR>), s>>>(a);
+  } else {
+    static bool once = (cudaFuncSetAttribute(gin_fwd_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(GinFwdSmem<HID>)), true);
+    (void)once;
+    gin_fwd_kernel<HID><<<grid, kThreads, sizeof(GinFwdSmem<HID>), s>>>(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GIN layer backward, part 1: upstream gradient of h' = relu(BN(y)), ReLU mask, d gamma / d beta
+//   mode CSR   : G_v = Ga_v + sum_{u in N(v)} Ga_u      (A symmetric => gather form, no atomics)
+//   mode direct: G_v = src[map ? map[v] : v]
+//   g_o = G * [gamma*yhat+beta > 0] ; dbeta = sum g_o ; dgamma = sum g_o*yhat
+// Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+gin_bwd_pre_kernel(GinBwdPreArgs p) {
+  __shared__ float s_red[16 * 2 * HID];
+  __shared__ double s_d[2 * 2 * HID];
+  const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  Bn4 bn;
+  bn.load(p.bn, l * 4);
+  float4 db = make4(0.f), dg = make4(0.f);
+  for (int v = blockIdx.x * 16 + hw; v < p.V; v += gridDim.x * 16) {
+    float4 g;
+    if (p.indptr) {
+      g = ld4(p.src + (size_t)v * HID + l * 4);
+      const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
+      for (int e = e0; e < e1; ++e) g = add4(g, ld4(p.src + (size_t)__ldg(p.indices + e) * HID + l * 4));
+    } else {
+      const int sv = p.map ? __ldg(p.map + v) : v;
+      g = ld4(p.src + (size_t)sv * HID + l * 4);
+    }
+    const float4 y = ld4(p.y + (size_t)v * HID + l * 4);
+    const float4 xh = bn.xhat(y);
+    const float4 o = bn.pre(y);
+    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    st4(p.g_o + (size_t)v * HID + l * 4, g);
+    db = add4(db, g);
+    dg.x = fmaf(g.x, xh.x, dg.x); dg.y = fmaf(g.y, xh.y, dg.y); dg.z = fmaf(g.z, xh.z, dg.z); dg.w = fmaf(g.w, xh.w, dg.w);
+  }
+  st4(s_red + hw * 2 * HID + l * 4, db);
+  st4(s_red + hw * 2 * HID + HID + l * 4, dg);
+  __syncthreads();
+  if (threadIdx.x < 2 * HID) {
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) s += s_red[h * 2 * HID + threadIdx.x];
+    p.part[(size_t)blockIdx.x * 2 * HID + threadIdx.x] = s;
+  }
+  if (!last_cta_arrives(p.counter)) return;
+  // 256 threads: column j = tid & 127 (0..63 dbeta, 64..127 dgamma), 2 interleaved segments
+  {
+    const int j = threadIdx.x & (2 * HID - 1), seg = threadIdx.x >> 7;
+    double s = 0.0;
+    for (int b = seg; b < (int)gridDim.x; b += 2) s += (double)__ldcg(p.part + (size_t)b * 2 * HID + j);
+    s_d[seg * 2 * HID + j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < HID) {
+    const int c = threadIdx.x;
+    const double dbeta = s_d[c] + s_d[2 * HID + c];
+    const double dgamma = s_d[HID + c] + s_d[2 * HID + HID + c];
+    p.d_beta[c] = (float)dbeta;
+    p.d_gamma[c] = (float)dgamma;
+    const double gamma = (double)p.bn[2 * HID + c];
+    p.cvec[c] = (float)(gamma * dbeta / (double)p.V);
+    p.cvec[HID + c] = (float)(gamma * dgamma / (double)p.V);
+  }
+}
+
+int gin_bwd_pre_grid(int V) { return min((V + 15) / 16, 8 * num_sms()); }
+
+void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s) {
+  gin_bwd_pre_kernel<<<gin_bwd_pre_grid(a.V), kThreads, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GIN layer backward, part 2 (persistent, one CTA per SM, static tile striding => deterministic):
+//   g_y = rstd * (gamma*g_o - c1 - yhat*c2)
+//   g_u = (g_y W2) * [r > 0] ; g_a = g_u W1 -> Ga
+//   dW2 += g_y^T r ; db2 += sum g_y ; dW1 += g_u^T a ; db1 += sum g_u     (per-CTA partials)
+// ------------------------------------------------------------------------------------------------
+template <int KIN>
+struct GinBwdSmem {
+  float gy[GT * GLD];
+  float gu[GT * GLD];
+  float r[GT * GLD];
+  float a[GT * (KIN + 4)];
+  float w2[HID * HID];     // natural [out][in]  = k-major for g_y W2
+  float w1[HID * KIN];     // natural [out][in]  = k-major for g_u W1
+};
+
+template <int KIN>
+__global__ void __launch_bounds__(kThreads, 1)
+gin_bwd_main_kernel(GinBwdMainArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GinBwdSmem<KIN>& sm = *reinterpret_cast<GinBwdSmem<KIN>*>(smem_raw);
+  constexpr int LDA = KIN + 4;
+  using M2 = NNMap<GT, HID>;   // g_r tile
+  using M1 = NNMap<GT, KIN>;   // g_a tile
+  using T2 = TNMap<HID, HID>;  // dW2
+  using T1 = TNMap<HID, KIN>;  // dW1
+
+  load_matrix<HID>(sm.w2, HID, p.W2, HID);
+  load_matrix<KIN>(sm.w1, KIN, p.W1, HID);
+
+  float dW2[T2::TO][T2::TJ], dW1[T1::TO][T1::TJ];
+#pragma unroll
+  for (int i = 0; i < T2::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T2::TJ; ++j) dW2[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < T1::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T1::TJ; ++j) dW1[i][j] = 0.f;
+  float dbias = 0.f;  // threads 0..63: db2[c]; threads 64..127: db1[c-64]
+
+  const int n_tiles = (p.V + GT - 1) / GT;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int base = tile * GT;
+    __syncthreads();
+    // ---- stage g_y, r, a
+    for (int i = threadIdx.x; i < GT * (HID / 4); i += kThreads) {
+      const int r = i / (HID / 4), c = (i % (HID / 4)) * 4;
+      const int v = base + r;
+      float4 gy = make4(0.f), rr = make4(0.f);
+      if (v < p.V) {
+        const float4 go = ld4(p.g_o + (size_t)v * HID + c);
+        const float4 y = ld4(p.y + (size_t)v * HID + c);
+        const float4 mean = ldg4(p.bn + c), rstd = ldg4(p.bn + HID + c), gamma = ldg4(p.bn + 2 * HID + c);
+        const float4 c1 = ldg4(p.cvec + c), c2 = ldg4(p.cvec + HID + c);
+        gy.x = rstd.x * (gamma.x * go.x - c1.x - (y.x - mean.x) * rstd.x * c2.x);
+        gy.y = rstd.y * (gamma.y * go.y - c1.y - (y.y - mean.y) * rstd.y * c2.y);
+        gy.z = rstd.z * (gamma.z * go.z - c1.z - (y.z - mean.z) * rstd.z * c2.z);
+        gy.w = rstd.w * (gamma.w * go.w - c1.w - (y.w - mean.w) * rstd.w * c2.w);
+        rr = ld4(p.r + (size_t)v * HID + c);
+      }
+      st4(sm.gy + r * GLD + c, gy);
+      st4(sm.r + r * GLD + c, rr);
+    }
+    load_row_tile<GT, KIN>(sm.a, LDA, p.a, base, p.V);
+    __syncthreads();
+    // ---- g_u = (g_y W2) * [r > 0]
+    {
+      float acc[M2::TM][4];
+#pragma unroll
+      for (int m = 0; m < M2::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+      gemm_nn<GT, HID, HID>(sm.gy, GLD, sm.w2, HID, acc);
+      const int c0 = M2::col0(), r0 = M2::row0();
+#pragma unroll
+      for (int m = 0; m < M2::TM; ++m) {
+        const float4 rr = ld4(sm.r + (r0 + m) * GLD + c0);
+        st4(sm.gu + (r0 + m) * GLD + c0,
+            make_float4(rr.x > 0.f ? acc[m][0] : 0.f, rr.y > 0.f ? acc[m][1] : 0.f,
+                        rr.z > 0.f ? acc[m][2] : 0.f, rr.w > 0.f ? acc[m][3] : 0.f));
+      }
+    }
+    __syncthreads();
+    // ---- g_a = g_u W1 -> global
+    {
+      float acc[M1::TM][4];
+#pragma unroll
+      for (int m = 0; m < M1::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+      gemm_nn<GT, HID, KIN>(sm.gu, GLD, sm.w1, KIN, acc);
+      const int c0 = M1::col0(), r0 = M1::row0();
+#pragma unroll
+      for (int m = 0; m < M1::TM; ++m) {
+        const int v = base + r0 + m;
+        if (v < p.V) st4(p.g_a + (size_t)v * KIN + c0, make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
+      }
+    }
+    // ---- weight gradients (rows beyond V are zero in gy/gu)
+    gemm_tn<HID, HID>(sm.gy, GLD, sm.r, GLD, GT, dW2);
+    gemm_tn<HID, KIN>(sm.gu, GLD, sm.a, LDA, GT, dW1);
+    if (threadIdx.x < 2 * HID) {
+      const float* src = (threadIdx.x < HID) ? sm.gy : sm.gu;
+      const int c = threadIdx.x & (HID - 1);
+      float s = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < GT; ++r) s += src[r * GLD + c];
+      dbias += s;
+    }
+  }
+  // ---- per-CTA partials (every CTA writes, also when it had no tile)
+  float* part = p.part + (size_t)blockIdx.x * p.pstride;
+#pragma unroll
+  for (int i = 0; i < T2::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T2::TJ; ++j) part[p.off_W2 + (T2::o0() + i) * HID + T2::j0() + j] = dW2[i][j];
+#pragma unroll
+  for (int i = 0; i < T1::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T1::TJ; ++j) part[p.off_W1 + (T1::o0() + i) * KIN + T1::j0() + j] = dW1[i][j];
+  if (threadIdx.x < HID) part[p.off_b2 + threadIdx.x] = dbias;
+  else if (threadIdx.x < 2 * HID) part[p.off_b1 + threadIdx.x - HID] = dbias;
+}
+
+void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s) {
+  if (kin == DTR) {
+    static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<DTR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(GinBwdSmem<DTR>)), true);
+    (void)once;
+    gin_bwd_main_kernel<DTR><<<grid, kThreads, sizeof(GinBwdSmem<DTR>), s>>>(a);
+  } else {
+    static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(GinBwdSmem<HID>)), true);
+    (void)once;
+    gin_bwd_main_kernel<HID><<<grid, kThreads, sizeof(GinBwdSmem<HID>), s>>>(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// transfer_d backward: dWt[o][f] = sum_rows gt_row[o] * x_hat[map(row)][f],
+//   gt_row = Ga0_row + sum_{u in N(row)} Ga0_u   (layer-0 aggregation backward; Ga0 is [V][DTR])
+// Two row sets (parent batch, ego batch) in one launch; last CTA finalises into grads.
+// ------------------------------------------------------------------------------------------------
+constexpr int PT = 128;   // rows per tile
+constexpr int FP = 32;    // padded feature width
+
+__global__ void __launch_bounds__(kThreads)
+input_proj_bwd_kernel(InputProjBwdArgs p) {
+  __shared__ float s_g[PT * (DTR + 1)];
+  __shared__ float s_x[PT * (FP + 1)];
+  const int o = threadIdx.x & 31, fg = threadIdx.x >> 5;  // thread owns dWt[o][fg*4 .. fg*4+3]
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tiles0 = (p.V[0] + PT - 1) / PT, tiles1 = (p.V[1] + PT - 1) / PT;
+  for (int t = blockIdx.x; t < tiles0 + tiles1; t += gridDim.x) {
+    const int set = t < tiles0 ? 0 : 1;
+    const int base = (set == 0 ? t : t - tiles0) * PT;
+    const int V = p.V[set];
+    const float* ga = p.ga[set];
+    const int32_t* indptr = p.indptr[set];
+    const int32_t* indices = p.indices[set];
+    const int32_t* map = p.map[set];
+    __syncthreads();
+    {  // gather gt rows: 8 lanes x float4 per row
+      const int l = threadIdx.x & 7;
+      for (int r = threadIdx.x >> 3; r < PT; r += kThreads / 8) {
+        const int v = base + r;
+        float4 g = make4(0.f);
+        if (v < V) {
+          g = ld4(ga + (size_t)v * DTR + l * 4);
+          const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+          for (int e = e0; e < e1; ++e) g = add4(g, ld4(ga + (size_t)__ldg(indices + e) * DTR + l * 4));
+        }
+        float* d = s_g + r * (DTR + 1) + l * 4;
+        d[0] = g.x; d[1] = g.y; d[2] = g.z; d[3] = g.w;
+      }
+    }
+    {  // x_hat rows: one thread per (row, half) is plenty
+      for (int r = threadIdx.x; r < PT; r += kThreads) {
+        const int v = base + r;
+        float* d = s_x + r * (FP + 1);
+        if (v < V) {
+          const float* xr = p.x + (size_t)(map ? __ldg(map + v) : v) * p.F;
+          float ss = 0.f;
+          for (int f = 0; f < p.F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
+          const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+          for (int f = 0; f < FP; ++f) d[f] = f < p.F ? __ldg(xr + f) * inv : 0.f;
+        } else {
+          for (int f = 0; f < FP; ++f) d[f] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    for (int r = 0; r < PT; ++r) {
+      const float g = s_g[r * (DTR + 1) + o];
+      const float* xr = s_x + r * (FP + 1) + fg * 4;
+      acc[0] = fmaf(g, xr[0], acc[0]); acc[1] = fmaf(g, xr[1], acc[1]);
+      acc[2] = fmaf(g, xr[2], acc[2]); acc[3] = fmaf(g, xr[3], acc[3]);
+    }
+  }
+  float* part = p.part + (size_t)blockIdx.x * DTR * FP;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
+  if (!last_cta_arrives(p.counter)) return;
+  for (int idx = threadIdx.x; idx < DTR * FP; idx += kThreads) {
+    double s = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(p.part + (size_t)b * DTR * FP + idx);
+    const int oo = idx / FP, f = idx % FP;
+    if (f < p.F) p.d_Wt[oo * p.F + f] = (float)s;
+  }
+}
+
+int input_proj_bwd_grid(int V0, int V1) {
+  return min((V0 + PT - 1) / PT + (V1 + PT - 1) / PT, 2 * num_sms());
+}
+void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s) {
+  input_proj_bwd_kernel<<<input_proj_bwd_grid(a.V[0], a.V[1]), kThreads, 0, s>>>(a);
+}
+
+}  // namespace scgib

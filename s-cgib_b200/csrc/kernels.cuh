@@ -1,0 +1,217 @@
+// kernels.cuh - argument blocks and host launchers shared by the .cu files of libscgib.
+#pragma once
+#include "common.cuh"
+
+namespace scgib {
+
+int num_sms();
+
+// ---------------------------------------------------------------- gin_kernels.cu
+struct TransposeJob { const float* src; float* dst; int rows, cols; };  // dst[c][r] = src[r][c]
+struct TransposeJobs { TransposeJob job[24]; int n; };
+void launch_transposes(const TransposeJobs& jobs, cudaStream_t s);
+
+void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s);
+
+struct GinFwdArgs {
+  const float* in;          // [*, KIN]  t (layer 0) or the previous layer's pre-BN output y
+  const int32_t* row_map;   // optional: input row of output row j (ego batch layer 0: ego_nodes)
+  const float* bn_in;       // optional {mean, rstd, gamma, beta}[HID] of the producing layer
+  const int32_t* indptr;
+  const int32_t* indices;
+  int V;
+  const float *W1t, *b1, *W2t, *b2;   // W1t [KIN][HID], W2t [HID][HID]  (k-major copies)
+  const float *gamma, *beta;          // this layer's BN affine (copied into bn_out for the consumers)
+  float *a_out, *r_out, *y_out;       // a/r optional (saved for backward)
+  float* part;                        // [n_tiles][2][HID]
+  unsigned int* counter;
+  float* bn_out;                      // {mean, rstd, gamma, beta}[HID]
+  float* running;                     // optional {running_mean, running_var}[HID]
+};
+int gin_fwd_grid(int V);
+void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);
+
+struct GinBwdPreArgs {
+  const float* src;         // CSR mode: Ga [V][HID]; direct mode: rows gathered through map
+  const int32_t* indptr;    // non-null => CSR mode
+  const int32_t* indices;
+  const int32_t* map;       // direct mode only, optional
+  const float* y;           // [V][HID] this layer's pre-BN output
+  const float* bn;          // {mean, rstd, gamma, beta}
+  int V;
+  float* g_o;               // [V][HID]
+  float* part;              // [grid][2][HID]
+  unsigned int* counter;
+  float *d_gamma, *d_beta;  // [HID] final gradients
+  float* cvec;              // {c1, c2}[HID]
+};
+int gin_bwd_pre_grid(int V);
+void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s);
+
+struct GinBwdMainArgs {
+  const float *g_o, *y, *r, *a;
+  const float *bn, *cvec;
+  const float *W1, *W2;     // natural [out][in]
+  int V;
+  float* g_a;               // [V][KIN]
+  float* part;              // per-CTA partial gradients: part[cta * pstride + off_*]
+  int64_t pstride;
+  int64_t off_W1, off_b1, off_W2, off_b2;
+};
+void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);
+
+struct InputProjBwdArgs {
+  const float* ga[2];       // layer-0 input gradients of the two encoders, [V][DTR]
+  const int32_t* indptr[2];
+  const int32_t* indices[2];
+  const int32_t* map[2];    // row -> parent node (null = identity)
+  int V[2];
+  const float* x;           // [N][F] features
+  int F;
+  int normalize;            // apply F.normalize to x rows
+  float* part;              // [grid][DTR*32]
+  unsigned int* counter;
+  float* d_Wt;              // [DTR][F]
+};
+int input_proj_bwd_grid(int V0, int V1);
+void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------- head_kernels.cu
+// H = relu(BN(y_last)) materialised; q = H Wc1^T + bc1   (compressor.0, models.py:590)
+struct GateLinFwdArgs {
+  const float* y; const float* bn; int N;
+  const float* Wc1t; const float* bc1;   // Wc1t [HID][HID] k-major
+  float* H; float* q;
+};
+void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s);
+
+// gH += g_q Wc1 ; dWc1 = g_q^T H ; dbc1 = sum g_q     (persistent, per-CTA partials)
+struct GateLinBwdArgs {
+  const float* g_q; const float* H; int N;
+  const float* Wc1;                      // natural
+  float* gH;                             // in/out [N][HID]
+  float* part; int64_t pstride; int64_t off_W, off_b;
+};
+void launch_gate_lin_bwd(const GateLinBwdArgs& a, int grid, cudaStream_t s);
+
+// C_v = sum_{j in ego(v)} relu(BN(y2_last_j)) ; logit_v = w_cand . C_v
+struct EgoPoolFwdArgs {
+  const float* y; const float* bn; const int32_t* ego_ptr; int N;
+  const float* w_cand;                   // attn_layer.weight[0, HID:2*HID]
+  float* C; float* logit;
+};
+void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s);
+
+void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, cudaStream_t s);
+
+// Per-graph gate + attention softmax (warp per graph): models.py:595-604, 631-660, 738-748
+struct GraphGateFwdArgs {
+  const int32_t* graph_ptr; int B; int N;
+  const float *H, *q;                    // [N][HID]
+  const float *gamma_c, *beta_c, *wc2, *bc2;
+  const float *gate_u, *feat_u;          // [N], [N][HID]
+  const float* logit;                    // [N]
+  float* noisy;                          // [N][HID]  Z^c
+  float* lam;                            // [N]
+  float* alpha;                          // [N]
+  float* readout;                        // [B][HID]  R_g   (graph_features_readout)
+  float* core;                           // [B][HID]  sum_v Z^c_v
+  float* gstat;                          // [B][4][HID] mu_g, sigma_g, mu^c_g, rstd^c_g (saved)
+  float* cstat;                          // optional [B][2][HID] compressor-BN batch mean / unbiased var per graph
+  float* kl;                             // [1] KL loss (last graph)
+};
+void launch_graph_gate_fwd(const GraphGateFwdArgs& a, cudaStream_t s);
+
+// compressor BatchNorm running stats: B sequential EMA updates in closed form (models.py:642 per graph)
+void launch_compressor_ema(const float* cstat, int B, float* running, cudaStream_t s);
+
+struct GraphGateBwdArgs {
+  const int32_t* graph_ptr; int B; int N;
+  const float *H, *q, *C;                // saved
+  const float *gamma_c, *beta_c, *wc2;
+  const float* w_cand;
+  const float *feat_u, *lam, *alpha, *gstat;
+  const float* gI;                       // [N][2*HID] gradient wrt interaction_map (head backward)
+  const float* g_core;                   // [B][HID]  contrastive gradient wrt core readout
+  const float* g_readout;                // [B][HID]  contrastive gradient wrt graph readout
+  float kl_scale;                        // d total / d KL
+  float* gp;                             // [N] scratch
+  float* g_q;                            // [N][HID]
+  float* gH;                             // [N][HID]  direct part (lin backward adds g_q Wc1)
+  float* gC;                             // [N][HID]
+  float* part;                           // [grid][5*HID]: dgamma_c, dbeta_c, dwc2, dw_cand, (dbc2 at [4*HID])
+  unsigned int* counter;
+  float *d_gamma_c, *d_beta_c, *d_wc2, *d_bc2, *d_attn_w, *d_attn_b;   // final gradients
+};
+void launch_graph_gate_bwd(const GraphGateBwdArgs& a, cudaStream_t s);
+
+// Z = Wm2 relu(Wm1 [noisy || alpha*C] + bm1) + bm2       (models.py:676, 749)
+struct HeadFwdArgs {
+  const float *noisy, *C, *alpha; int N;
+  const float *W1t, *b1, *W2t, *b2;      // W1t [2*HID][HID], W2t [HID][HID]
+  float* imap;                           // optional [N][2*HID]
+  float* r;                              // [N][HID] saved
+  float* Z;                              // [N][HID]
+};
+void launch_head_fwd(const HeadFwdArgs& a, cudaStream_t s);
+
+struct HeadBwdArgs {
+  const float* gZ;                       // [N][HID]
+  const float *noisy, *C, *alpha, *r; int N;
+  const float *W1, *W2;                  // natural: W1 [HID][2*HID], W2 [HID][HID]
+  float* gI;                             // [N][2*HID]
+  float* part; int64_t pstride; int64_t off_W1, off_b1, off_W2, off_b2;
+};
+void launch_head_bwd(const HeadBwdArgs& a, int grid, cudaStream_t s);
+
+// ---------------------------------------------------------------- loss_kernels.cu
+// recon: per-CTA partials of Z^T Z and of sum_{(i,j) in E} z_i . z_j     (models.py:762-768, Gram identity)
+struct ReconFwdArgs {
+  const float* Z; const int32_t* indptr; const int32_t* indices; int N;
+  float* part;                           // [grid][HID*HID + 4]
+};
+void launch_recon_fwd(const ReconFwdArgs& a, int grid, cudaStream_t s);
+// G = sum of partials; edge = sum; one small kernel
+void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, cudaStream_t s);
+// gZ = scale * (4/N) * (Z G - A Z)
+struct ReconBwdArgs {
+  const float* Z; const float* G; const int32_t* indptr; const int32_t* indices; int N;
+  float scale; float* gZ;
+};
+void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s);
+
+// contrastive (models.py:606-629)
+struct NormalizeArgs { const float *core, *readout; int B; float *z1, *z2, *n1, *n2, *diag; };
+void launch_normalize(const NormalizeArgs& a, cudaStream_t s);
+struct ContrastiveFwdArgs { const float *z1, *z2; int B; int jsplit; float* rowsum; };  // rowsum [jsplit][B]
+void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s);
+struct ContrastiveBwdArgs {
+  const float *z1, *z2, *D; int B; int jsplit;
+  float* g1p; float* g2p;                // [jsplit][B][HID] partial gradients wrt z1_hat / z2_hat
+};
+void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s);
+struct ContrastiveBwdFinArgs {
+  const float *g1p, *g2p, *z1, *z2, *n1, *n2; int B; int jsplit; float scale;
+  float *g_core, *g_readout;
+};
+void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, cudaStream_t s);
+int contrastive_jsplit(int B);
+
+struct LossFinalizeArgs {
+  const float* rowsum; int jsplit; const float* diag; int B;   // contrastive
+  const float* G; const float* edge_sum; int N; int E;          // recon
+  const float* kl;
+  float* D;                                                      // [B] contrastive denominators (saved)
+  float* losses;                                                 // {KL, contrastive, recon, total}
+};
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s);
+
+// grads[off..off+len) = sum_c part[c*pstride + off + i] for each listed range
+struct ReduceRanges { int64_t off[40]; int64_t len[40]; int n; };
+void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
+                            cudaStream_t s);
+
+void launch_adam(float* params, const float* grads, float* m, float* v, int64_t n, int64_t step, float lr, float b1,
+                 float b2, float eps, float wd, float gscale, cudaStream_t s);
+
+}  // namespace scgib

@@ -1,0 +1,406 @@
+// loss_kernels.cu - adjacency-reconstruction loss (Gram identity), the InfoNCE-style contrastive loss
+// (flash-style: the B x B similarity matrices are never materialised), loss finalisation, the deterministic
+// reduction of per-CTA parameter-gradient partials and the fused Adam step.
+//
+// Reference call sites replaced (paths relative to the reference tree):
+//   loss_recon_adj (dense N x N)        models.py:762-768    ||ZZ^T - A||_F^2 / N  ==  (||Z^T Z||_F^2 - 2 sum_E z_i.z_j + |E|) / N
+//   sim / batched_semi_loss             models.py:606-629
+//   KL_Loss = mean(KL_tensor)           models.py:679
+//   loss = KL + recon + contrastive     exp_pretraining.py:321
+//   torch.optim.Adam(lr, wd=5e-5)       exp_pretraining.py:86, 112, 323
+#include "kernels.cuh"
+
+namespace scgib {
+
+constexpr int GT = 128;
+constexpr int GLD = HID + 4;
+constexpr int CT = 64;   // contrastive tile
+
+// ------------------------------------------------------------------------------------------------
+// recon forward: per-CTA partial Gram matrix + partial edge-dot sum
+// ------------------------------------------------------------------------------------------------
+struct ReconFwdSmem { float z[GT * GLD]; float red[kThreads / 32]; };
+
+__global__ void __launch_bounds__(kThreads, 2)
+recon_fwd_kernel(ReconFwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ReconFwdSmem& sm = *reinterpret_cast<ReconFwdSmem*>(smem_raw);
+  using T = TNMap<HID, HID>;
+  float G[T::TO][T::TJ];
+#pragma unroll
+  for (int i = 0; i < T::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T::TJ; ++j) G[i][j] = 0.f;
+  float ed = 0.f;
+  const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  const int n_tiles = (p.N + GT - 1) / GT;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int base = tile * GT;
+    __syncthreads();
+    load_row_tile<GT, HID>(sm.z, GLD, p.Z, base, p.N);
+    __syncthreads();
+    gemm_tn<HID, HID>(sm.z, GLD, sm.z, GLD, GT, G);
+    for (int r = hw; r < GT; r += 16) {
+      const int v = base + r;
+      if (v < p.N) {
+        float4 nb = make4(0.f);
+        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
+        for (int e = e0; e < e1; ++e) nb = add4(nb, ld4(p.Z + (size_t)__ldg(p.indices + e) * HID + l * 4));
+        const float4 zv = ld4(sm.z + r * GLD + l * 4);
+        ed += zv.x * nb.x + zv.y * nb.y + zv.z * nb.z + zv.w * nb.w;
+      }
+    }
+  }
+  float* part = p.part + (size_t)blockIdx.x * (HID * HID + 4);
+#pragma unroll
+  for (int i = 0; i < T::TO; ++i)
+#pragma unroll
+    for (int j = 0; j < T::TJ; ++j) part[(T::o0() + i) * HID + T::j0() + j] = G[i][j];
+  ed = warp_sum(ed);
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = ed;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) s += sm.red[w];
+    part[HID * HID] = s;
+  }
+}
+void launch_recon_fwd(const ReconFwdArgs& a, int grid, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(recon_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ReconFwdSmem)), true);
+  (void)once;
+  recon_fwd_kernel<<<grid, kThreads, sizeof(ReconFwdSmem), s>>>(a);
+}
+
+__global__ void __launch_bounds__(kThreads)
+recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum) {
+  const int j = blockIdx.x * kThreads + threadIdx.x;
+  if (j > HID * HID) return;
+  double s = 0.0;
+  for (int c = 0; c < grid; ++c) s += (double)part[(size_t)c * (HID * HID + 4) + j];
+  if (j < HID * HID) G[j] = (float)s; else edge_sum[0] = (float)s;
+}
+void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, cudaStream_t s) {
+  recon_reduce_kernel<<<(HID * HID + 1 + kThreads - 1) / kThreads, kThreads, 0, s>>>(part, grid, G, edge_sum);
+}
+
+// recon backward: gZ = scale * (4/N) * (Z G - A Z)
+struct ReconBwdSmem { float z[GT * GLD]; float g[HID * HID]; };
+
+__global__ void __launch_bounds__(kThreads, 2)
+recon_bwd_kernel(ReconBwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ReconBwdSmem& sm = *reinterpret_cast<ReconBwdSmem*>(smem_raw);
+  using M = NNMap<GT, HID>;
+  load_matrix<HID>(sm.g, HID, p.G, HID);
+  const float k = p.scale * 4.f / (float)p.N;
+  const int n_tiles = (p.N + GT - 1) / GT;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int base = tile * GT;
+    __syncthreads();
+    load_row_tile<GT, HID>(sm.z, GLD, p.Z, base, p.N);
+    __syncthreads();
+    float acc[M::TM][4];
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+    gemm_nn<GT, HID, HID>(sm.z, GLD, sm.g, HID, acc);
+    const int c0 = M::col0(), r0 = M::row0();
+#pragma unroll
+    for (int m = 0; m < M::TM; ++m) {
+      const int v = base + r0 + m;
+      if (v < p.N) {
+        float4 nb = make4(0.f);
+        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
+        for (int e = e0; e < e1; ++e) nb = add4(nb, ld4(p.Z + (size_t)__ldg(p.indices + e) * HID + c0));
+        st4(p.gZ + (size_t)v * HID + c0,
+            make_float4(k * (acc[m][0] - nb.x), k * (acc[m][1] - nb.y), k * (acc[m][2] - nb.z), k * (acc[m][3] - nb.w)));
+      }
+    }
+  }
+}
+void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(recon_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ReconBwdSmem)), true);
+  (void)once;
+  const int grid = min((a.N + GT - 1) / GT, 2 * num_sms());
+  recon_bwd_kernel<<<grid, kThreads, sizeof(ReconBwdSmem), s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// contrastive loss
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
+// z1 = core / max(||core||, 1e-12), z2 = readout / max(||readout||, 1e-12), diag = z1 . z2   (warp per row)
+__global__ void __launch_bounds__(kThreads)
+normalize_kernel(NormalizeArgs p) {
+  const int lane = threadIdx.x & 31, c = 2 * lane;
+  for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
+    const float2 a = ld2(p.core + (size_t)i * HID + c), b = ld2(p.readout + (size_t)i * HID + c);
+    const float na = fmaxf(sqrtf(warp_sum(a.x * a.x + a.y * a.y)), 1e-12f);
+    const float nb = fmaxf(sqrtf(warp_sum(b.x * b.x + b.y * b.y)), 1e-12f);
+    const float2 za = make_float2(a.x / na, a.y / na), zb = make_float2(b.x / nb, b.y / nb);
+    st2(p.z1 + (size_t)i * HID + c, za);
+    st2(p.z2 + (size_t)i * HID + c, zb);
+    const float d = warp_sum(za.x * zb.x + za.y * zb.y);
+    if (lane == 0) { p.n1[i] = na; p.n2[i] = nb; p.diag[i] = d; }
+  }
+}
+void launch_normalize(const NormalizeArgs& a, cudaStream_t s) {
+  normalize_kernel<<<min((a.B + 7) / 8, 8 * num_sms()), kThreads, 0, s>>>(a);
+}
+
+int contrastive_jsplit(int B) {
+  const int iblocks = (B + CT - 1) / CT;
+  int js = (2 * num_sms() + iblocks - 1) / iblocks;
+  const int jblocks = iblocks;
+  if (js > jblocks) js = jblocks;
+  if (js < 1) js = 1;
+  return js;
+}
+
+// S[i][j] = a_i . b_j for a 64x64 tile pair; thread (ti,tj): rows ti*4+ii, columns tj+16*jj (conflict-free float4 reads)
+__device__ __forceinline__ void sim_tile(const float* __restrict__ As, const float* __restrict__ Bs, float (&s)[4][4]) {
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < HID; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = ld4(As + (ti * 4 + i) * GLD + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = ld4(Bs + (tj + 16 * j) * GLD + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        s[i][j] = fmaf(a[i].x, b[j].x, fmaf(a[i].y, b[j].y, fmaf(a[i].z, b[j].z, fmaf(a[i].w, b[j].w, s[i][j]))));
+  }
+}
+
+struct ConFwdSmem { float zi[CT * GLD]; float zj1[CT * GLD]; float zj2[CT * GLD]; };
+
+__global__ void __launch_bounds__(kThreads, 2)
+contrastive_fwd_kernel(ContrastiveFwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ConFwdSmem& sm = *reinterpret_cast<ConFwdSmem*>(smem_raw);
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const int ibase = blockIdx.x * CT;
+  const int jblocks = (p.B + CT - 1) / CT;
+  load_row_tile<CT, HID>(sm.zi, GLD, p.z1, ibase, p.B);
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int jb = blockIdx.y; jb < jblocks; jb += gridDim.y) {
+    const int jbase = jb * CT;
+    __syncthreads();
+    load_row_tile<CT, HID>(sm.zj1, GLD, p.z1, jbase, p.B);
+    load_row_tile<CT, HID>(sm.zj2, GLD, p.z2, jbase, p.B);
+    __syncthreads();
+    float s[4][4];
+    sim_tile(sm.zi, sm.zj1, s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gi = ibase + ti * 4 + i, gj = jbase + tj + 16 * j;
+        if (gj < p.B && gj != gi) rs[i] += expf(s[i][j]);       // refl_sim.sum(1) - refl_sim.diag()
+      }
+    sim_tile(sm.zi, sm.zj2, s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = jbase + tj + 16 * j;
+        if (gj < p.B) rs[i] += expf(s[i][j]);                    // between_sim.sum(1)
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = rs[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int gi = ibase + ti * 4 + i;
+    if (tj == 0 && gi < p.B) p.rowsum[(size_t)blockIdx.y * p.B + gi] = v;
+  }
+}
+void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(contrastive_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ConFwdSmem)), true);
+  (void)once;
+  dim3 grid((a.B + CT - 1) / CT, a.jsplit);
+  contrastive_fwd_kernel<<<grid, kThreads, sizeof(ConFwdSmem), s>>>(a);
+}
+
+// backward.  blockIdx.z == 0: rows of z1 (g1);  blockIdx.z == 1: rows of z2 (g2).
+//   g1_i = sum_{j!=i} e^{s_r(i,j)} (1/D_i + 1/D_j) z1_j + sum_j e^{s_b(i,j)}/D_i z2_j
+//   g2_j = sum_i e^{s_b(i,j)}/D_i z1_i
+// (the 1/B factor and the -z2_i / -z1_j terms are applied in the finalise kernel)
+struct ConBwdSmem { float zi[CT * GLD]; float zj1[CT * GLD]; float zj2[CT * GLD]; float P[CT * GLD]; float Di[CT]; float Dj[CT]; };
+
+__global__ void __launch_bounds__(kThreads, 2)
+contrastive_bwd_kernel(ContrastiveBwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ConBwdSmem& sm = *reinterpret_cast<ConBwdSmem*>(smem_raw);
+  using M = NNMap<CT, HID>;
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const bool mode1 = (blockIdx.z == 1);
+  const int ibase = blockIdx.x * CT;
+  const int jblocks = (p.B + CT - 1) / CT;
+  load_row_tile<CT, HID>(sm.zi, GLD, mode1 ? p.z2 : p.z1, ibase, p.B);
+  if (threadIdx.x < CT) sm.Di[threadIdx.x] = (ibase + threadIdx.x < p.B) ? 1.f / p.D[ibase + threadIdx.x] : 0.f;
+  float acc[M::TM][4];
+#pragma unroll
+  for (int m = 0; m < M::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+  for (int jb = blockIdx.y; jb < jblocks; jb += gridDim.y) {
+    const int jbase = jb * CT;
+    __syncthreads();
+    load_row_tile<CT, HID>(sm.zj1, GLD, p.z1, jbase, p.B);
+    if (!mode1) load_row_tile<CT, HID>(sm.zj2, GLD, p.z2, jbase, p.B);
+    if (threadIdx.x < CT) sm.Dj[threadIdx.x] = (jbase + threadIdx.x < p.B) ? 1.f / p.D[jbase + threadIdx.x] : 0.f;
+    __syncthreads();
+    float s[4][4];
+    sim_tile(sm.zi, sm.zj1, s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int li = ti * 4 + i, lj = tj + 16 * j;
+        const int gi = ibase + li, gj = jbase + lj;
+        float w;
+        if (mode1) w = sm.Dj[lj];                                   // rows are z2_j', columns z1_i: weight 1/D_i of the column
+        else w = (gj != gi) ? sm.Di[li] + sm.Dj[lj] : 0.f;
+        sm.P[li * GLD + lj] = (gj < p.B && gi < p.B) ? expf(s[i][j]) * w : 0.f;
+      }
+    __syncthreads();
+    gemm_nn<CT, CT, HID>(sm.P, GLD, sm.zj1, GLD, acc);
+    if (!mode1) {
+      sim_tile(sm.zi, sm.zj2, s);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int li = ti * 4 + i, lj = tj + 16 * j;
+          sm.P[li * GLD + lj] = (jbase + lj < p.B && ibase + li < p.B) ? expf(s[i][j]) * sm.Di[li] : 0.f;
+        }
+      __syncthreads();
+      gemm_nn<CT, CT, HID>(sm.P, GLD, sm.zj2, GLD, acc);
+    }
+  }
+  float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
+  const int c0 = M::col0(), r0 = M::row0();
+#pragma unroll
+  for (int m = 0; m < M::TM; ++m) {
+    const int gi = ibase + r0 + m;
+    if (gi < p.B) st4(out + (size_t)gi * HID + c0, make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
+  }
+}
+void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(contrastive_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ConBwdSmem)), true);
+  (void)once;
+  dim3 grid((a.B + CT - 1) / CT, a.jsplit, 2);
+  contrastive_bwd_kernel<<<grid, kThreads, sizeof(ConBwdSmem), s>>>(a);
+}
+
+// g wrt the un-normalised readouts: (g - z_hat (z_hat . g)) / max(||z||, 1e-12)     (warp per row)
+__global__ void __launch_bounds__(kThreads)
+contrastive_bwd_finalize_kernel(ContrastiveBwdFinArgs p) {
+  const int lane = threadIdx.x & 31, c = 2 * lane;
+  const float k = p.scale / (float)p.B;
+  for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
+    float2 g1 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f);
+    for (int js = 0; js < p.jsplit; ++js) {
+      const float2 a = ld2(p.g1p + ((size_t)js * p.B + i) * HID + c), b = ld2(p.g2p + ((size_t)js * p.B + i) * HID + c);
+      g1.x += a.x; g1.y += a.y; g2.x += b.x; g2.y += b.y;
+    }
+    const float2 z1 = ld2(p.z1 + (size_t)i * HID + c), z2 = ld2(p.z2 + (size_t)i * HID + c);
+    g1.x = k * (g1.x - z2.x); g1.y = k * (g1.y - z2.y);
+    g2.x = k * (g2.x - z1.x); g2.y = k * (g2.y - z1.y);
+    const float d1 = warp_sum(z1.x * g1.x + z1.y * g1.y), d2 = warp_sum(z2.x * g2.x + z2.y * g2.y);
+    const float n1 = p.n1[i], n2 = p.n2[i];
+    st2(p.g_core + (size_t)i * HID + c, make_float2((g1.x - z1.x * d1) / n1, (g1.y - z1.y * d1) / n1));
+    st2(p.g_readout + (size_t)i * HID + c, make_float2((g2.x - z2.x * d2) / n2, (g2.y - z2.y * d2) / n2));
+  }
+}
+void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, cudaStream_t s) {
+  contrastive_bwd_finalize_kernel<<<min((a.B + 7) / 8, 8 * num_sms()), kThreads, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses = {KL, contrastive, recon, total}; also the contrastive denominators D_i (saved for backward)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+loss_finalize_kernel(LossFinalizeArgs p) {
+  __shared__ double s_a[kThreads], s_b[kThreads];
+  double con = 0.0, fro = 0.0;
+  for (int i = threadIdx.x; i < p.B; i += kThreads) {
+    float d = 0.f;
+    for (int js = 0; js < p.jsplit; ++js) d += p.rowsum[(size_t)js * p.B + i];
+    p.D[i] = d;
+    con += (double)(logf(d) - p.diag[i]);      // -log(exp(s_b(i,i)) / D_i)
+  }
+  for (int j = threadIdx.x; j < HID * HID; j += kThreads) { const double g = (double)p.G[j]; fro += g * g; }
+  s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float kl = p.kl[0];
+    const float c = (float)(s_a[0] / (double)p.B);
+    const float r = (float)((s_b[0] - 2.0 * (double)p.edge_sum[0] + (double)p.E) / (double)p.N);
+    p.losses[0] = kl; p.losses[1] = c; p.losses[2] = r; p.losses[3] = kl + r + c;
+  }
+}
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_finalize_kernel<<<1, kThreads, 0, s>>>(a); }
+
+// ------------------------------------------------------------------------------------------------
+// grads[off+i] = sum_c part[c*pstride + off + i]   (fixed order => run-to-run bit-stable)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+reduce_partials_kernel(const float* __restrict__ part, int64_t pstride, int nparts, ReduceRanges r, float* __restrict__ grads) {
+  const int64_t off = r.off[blockIdx.y], len = r.len[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (int64_t)gridDim.x * kThreads) {
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += (double)part[(size_t)c * pstride + off + i];
+    grads[off + i] = (float)s;
+  }
+}
+void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
+                            cudaStream_t s) {
+  if (r.n == 0) return;
+  dim3 grid(32, r.n);   // largest range is 8192 floats = 32 CTAs x 256
+  reduce_partials_kernel<<<grid, kThreads, 0, s>>>(part, pstride, nparts, r, grads);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (L2-in-gradient weight decay), same update order as torch.optim.Adam's single-tensor path
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr, float b1, float b2, float eps, float wd, float gscale, float step_size, float bc2_sqrt) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i] * gscale);
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);          // lerp(m, g, 1-b1)
+    const float vi = fmaf(1.f - b2, gi * gi, b2 * v[i]);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+void launch_adam(float* params, const float* grads, float* m, float* v, int64_t n, int64_t step, float lr, float b1,
+                 float b2, float eps, float wd, float gscale, cudaStream_t s) {
+  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+  int64_t gb = (n + kThreads - 1) / kThreads;
+  const int grid = (int)(gb < 4 * (int64_t)num_sms() ? gb : 4 * (int64_t)num_sms());
+  adam_kernel<<<grid, kThreads, 0, s>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, gscale, (float)(lr / bc1),
+                                        (float)sqrt(bc2));
+}
+
+}  // namespace scgib

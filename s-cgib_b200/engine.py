@@ -1,0 +1,259 @@
+"""PretrainEngine - host driver of the S-CGIB pre-training step on one GPU.
+
+Owns the flat parameter / gradient / Adam-state buffers and the kernel workspace and calls the
+C ABI (include/scgib.h).  One forward = one C call (~30 kernel launches), one backward = one C call;
+there is no per-graph Python loop and no host synchronisation inside a step.
+
+Reference path replaced: exp_pretraining.py:300-324 (train_epoch_pre_training body) and
+models.py:662-700 / 1158-1195 (Mainmodel(.continue).forward).
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .graph import BatchedGraph, EgoBatch, EgoWorkspace, khop_ego_batch
+
+HID, DTR = 64, 32
+
+
+def param_names(gin_layers: int):
+    """Reference state-dict name of every slot of the flat parameter buffer."""
+    names = ["MLP.0.weight", "MLP.0.bias", "MLP.2.weight", "MLP.2.bias",
+             "compressor.0.weight", "compressor.0.bias", "compressor.1.weight", "compressor.1.bias",
+             "compressor.3.weight", "compressor.3.bias", "attn_layer.weight", "attn_layer.bias", "transfer_d.weight"]
+    for e in (1, 2):
+        for l in range(gin_layers):
+            p = "Encoder%d." % e
+            names += [p + "ginlayers.%d.apply_func.mlp.0.weight" % l, p + "ginlayers.%d.apply_func.mlp.0.bias" % l,
+                      p + "ginlayers.%d.apply_func.mlp.2.weight" % l, p + "ginlayers.%d.apply_func.mlp.2.bias" % l,
+                      p + "batch_norms.%d.weight" % l, p + "batch_norms.%d.bias" % l]
+    return names
+
+
+def param_shapes(in_dim: int, gin_layers: int):
+    shapes = [(HID, 2 * HID), (HID,), (HID, HID), (HID,), (HID, HID), (HID,), (HID,), (HID,), (1, HID), (1,),
+              (1, 2 * HID), (1,), (DTR, in_dim)]
+    for _e in range(2):
+        for l in range(gin_layers):
+            shapes += [(HID, DTR if l == 0 else HID), (HID,), (HID, HID), (HID,), (HID,), (HID,)]
+    return shapes
+
+
+def bn_buffer_names(gin_layers: int):
+    names = []
+    for e in (1, 2):
+        for l in range(gin_layers):
+            names.append("Encoder%d.batch_norms.%d" % (e, l))
+    names.append("compressor.1")
+    return names
+
+
+class DeviceBatch:
+    """Everything one step needs, resident on the device: parent CSR, ego CSR, features, noise."""
+
+    def __init__(self, g: BatchedGraph, ego: EgoBatch, x: torch.Tensor, normalize_x: bool = True):
+        self.g, self.ego, self.x, self.normalize_x = g, ego, x.contiguous(), normalize_x
+        self.B, self.N, self.E = g.batch_size, g.num_nodes(), g.num_edges()
+        self.Ns, self.Es = ego.num_nodes(), ego.num_edges()
+
+    def c_struct(self, gate_u, feat_u):
+        b = _lib.Batch()
+        b.B, b.N, b.E, b.Ns, b.Es = self.B, self.N, self.E, self.Ns, self.Es
+        g, e = self.g, self.ego
+        b.graph_ptr, b.indptr, b.indices = g.graph_ptr.data_ptr(), g.indptr.data_ptr(), g.indices.data_ptr()
+        b.ego_ptr, b.ego_nodes, b.ego_seed = e.ego_ptr.data_ptr(), e.ego_nodes.data_ptr(), e.ego_seed.data_ptr()
+        b.sub_indptr, b.sub_indices = e.sub_indptr.data_ptr(), e.sub_indices.data_ptr()
+        b.x, b.normalize_x = self.x.data_ptr(), int(self.normalize_x)
+        b.gate_u, b.feat_u = gate_u.data_ptr(), feat_u.data_ptr()
+        return b
+
+    def algorithmic_bytes(self, gin_layers=4, F=9, s=4):
+        """SURVEY.md §8(d) 'algorithmic bytes per training step' evaluated on this batch's actual sizes."""
+        N, E, Ns, Es, d = self.N, self.E, self.Ns, self.Es, HID
+
+        def enc(V, D):
+            tot = 0
+            for l in range(gin_layers):
+                din = DTR if l == 0 else d
+                tot += V * (din + d) * s + 4 * (V + 1 + D)
+            return tot
+        fwd = enc(N, E) + enc(Ns, Es) + N * F * 4 + Ns * 4 + N * DTR * s + (Ns + N) * d * s + 2 * N * d * s + \
+            (N + 1) * d * s + 2 * N * d * s + N * d * s + 4 * (N + 1 + E) + 4 * d * s
+        ego = 4 * (N + 1 + E) + 4 * (2 * Ns + 1 + Es + N + 1)
+        return 3 * fwd + ego
+
+
+class PretrainEngine:
+    def __init__(self, in_dim: int, gin_layers: int = 4, hidden: int = 64, d_transfer: int = 32,
+                 device="cuda:0", seed: Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PretrainEngine needs a CUDA device: the hot path has no CPU fallback")
+        self.dims = _lib.Dims(int(in_dim), int(d_transfer), int(hidden), int(gin_layers))
+        n = self.lib.scgib_param_slots(ctypes.byref(self.dims))
+        if n < 0:
+            _lib.check(n, "param_slots")
+        off = (ctypes.c_int64 * n)()
+        sz = (ctypes.c_int64 * n)()
+        self.total = int(self.lib.scgib_param_layout(ctypes.byref(self.dims), off, sz))
+        self.offsets, self.sizes = list(off), list(sz)
+        self.names = param_names(gin_layers)
+        self.shapes = param_shapes(in_dim, gin_layers)
+        assert len(self.names) == n == len(self.shapes)
+        self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.bn_running = torch.zeros(2 * gin_layers + 1, 2, hidden, dtype=torch.float32, device=self.device)
+        self.bn_running[:, 1] = 1.0
+        self.num_batches_tracked = 0
+        self.step_count = 0
+        self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._ws = None
+        self._loss_scale = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
+        self.ego_ws = EgoWorkspace()
+        self._noise_gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self._noise_gen.manual_seed(seed)
+            self.reset_parameters(seed)
+
+    # ---------------------------------------------------------------- parameters
+    def views(self) -> "OrderedDict[str, torch.Tensor]":
+        out = OrderedDict()
+        for name, o, s, shp in zip(self.names, self.offsets, self.sizes, self.shapes):
+            out[name] = self.params[o:o + s].view(shp)
+        return out
+
+    def grad_views(self):
+        out = OrderedDict()
+        for name, o, s, shp in zip(self.names, self.offsets, self.sizes, self.shapes):
+            out[name] = self.grads[o:o + s].view(shp)
+        return out
+
+    def reset_parameters(self, seed=0):
+        """nn.Linear / BatchNorm1d default initialisation (kaiming_uniform(a=sqrt(5)), bias U(-1/sqrt(fan_in), ..))."""
+        gen = torch.Generator().manual_seed(seed)
+        v = self.views()
+        for name, t in v.items():
+            if "batch_norms" in name or name.startswith("compressor.1"):
+                t.fill_(1.0 if name.endswith("weight") else 0.0)
+                continue
+            wname = name[:-4] + "weight" if name.endswith("bias") else name
+            fan_in = v[wname].shape[1]
+            bound = 1.0 / fan_in ** 0.5
+            t.copy_((torch.rand(t.shape, generator=gen) * 2 - 1) * bound)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict=False):
+        """Load reference-named tensors (e.g. a state_dict of models.Mainmodel)."""
+        v = self.views()
+        for name, t in v.items():
+            if name in sd:
+                t.copy_(sd[name].reshape(t.shape))
+            elif strict:
+                raise KeyError(name)
+        for i, base in enumerate(bn_buffer_names(self.dims.gin_layers)):
+            if base + ".running_mean" in sd:
+                self.bn_running[i, 0].copy_(sd[base + ".running_mean"])
+                self.bn_running[i, 1].copy_(sd[base + ".running_var"])
+
+    def state_dict(self):
+        sd = OrderedDict((k, t.detach().clone()) for k, t in self.views().items())
+        for i, base in enumerate(bn_buffer_names(self.dims.gin_layers)):
+            sd[base + ".running_mean"] = self.bn_running[i, 0].clone()
+            sd[base + ".running_var"] = self.bn_running[i, 1].clone()
+        return sd
+
+    # ---------------------------------------------------------------- data
+    def make_batch(self, g: BatchedGraph, k: int = 1, normalize_x: bool = True) -> DeviceBatch:
+        """H2D of a host batch (if needed) + on-GPU k-hop ego-net extraction."""
+        if g.device != self.device:
+            g = g.to(self.device, non_blocking=True)
+        ego = khop_ego_batch(g, k, self.ego_ws)
+        return DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+
+    def draw_noise(self, N):
+        """U[0,1) gate / feature noise (reference: CPU torch.rand per graph, device rand_like: models.py:599, 650)."""
+        return (torch.rand(N, device=self.device, generator=self._noise_gen),
+                torch.rand(N, HID, device=self.device, generator=self._noise_gen))
+
+    def _workspace(self, b: DeviceBatch):
+        need = self.lib.scgib_pretrain_workspace_bytes(ctypes.byref(self.dims), b.B, b.N, b.E, b.Ns, b.Es)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(int(need * 1.1) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def debug_buffer(self, name: str, shape):
+        """View of a named intermediate of the last forward/backward inside the workspace (tests only)."""
+        b = self._last[0]
+        off = self.lib.scgib_pretrain_workspace_offset(ctypes.byref(self.dims), b.B, b.N, b.E, b.Ns, b.Es, name.encode())
+        if off < 0:
+            raise KeyError(name)
+        n = 1
+        for v in shape:
+            n *= v
+        return self._ws[off:off + 4 * n].view(torch.float32).view(shape)
+
+    # ---------------------------------------------------------------- step
+    def forward(self, b: DeviceBatch, gate_u=None, feat_u=None, want=False, update_running=True,
+                params: Optional[torch.Tensor] = None):
+        """Returns the device tensor losses[4] = {KL, contrastive, recon, total}; with ``want`` also a dict of
+        embeddings (interaction_map [N,128], Z, noisy, graph_readout)."""
+        if gate_u is None:
+            gate_u, feat_u = self.draw_noise(b.N)
+        self._last = (b, gate_u.contiguous(), feat_u.contiguous())
+        cb = b.c_struct(self._last[1], self._last[2])
+        ws = self._workspace(b)
+        emb = None
+        if want:
+            emb = dict(interaction_map=torch.empty(b.N, 2 * HID, device=self.device),
+                       Z=torch.empty(b.N, HID, device=self.device), noisy=torch.empty(b.N, HID, device=self.device),
+                       graph_readout=torch.empty(b.B, HID, device=self.device))
+        p = self.params if params is None else params
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_pretrain_forward_f32(
+            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if update_running else None,
+            ctypes.byref(cb), _lib.ptr(self.losses),
+            _lib.ptr(emb["interaction_map"]) if want else None, _lib.ptr(emb["Z"]) if want else None,
+            _lib.ptr(emb["noisy"]) if want else None, _lib.ptr(emb["graph_readout"]) if want else None,
+            _lib.ptr(ws), ws.numel(), st), "pretrain_forward")
+        if update_running:
+            self.num_batches_tracked += 1
+        return (self.losses, emb) if want else self.losses
+
+    def backward(self, loss_scale=(1.0, 1.0, 1.0), params: Optional[torch.Tensor] = None):
+        """Gradients of scale . {KL, contrastive, recon} into the flat ``grads`` buffer (overwritten)."""
+        b, gate_u, feat_u = self._last
+        cb = b.c_struct(gate_u, feat_u)
+        ws = self._workspace(b)
+        self._loss_scale[0], self._loss_scale[1], self._loss_scale[2] = loss_scale
+        p = self.params if params is None else params
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_pretrain_backward_f32(ctypes.byref(self.dims), _lib.ptr(p), ctypes.byref(cb),
+                                                        self._loss_scale, _lib.ptr(self.grads), _lib.ptr(ws),
+                                                        ws.numel(), st), "pretrain_backward")
+        return self.grads
+
+    def adam_step(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, grad_scale=1.0):
+        """torch.optim.Adam(lr, weight_decay=5e-5) of exp_pretraining.py:86 over the flat buffer."""
+        self.step_count += 1
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_adam_step_f32(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg),
+                                                _lib.ptr(self.exp_avg_sq), self.total, self.step_count, lr, betas[0],
+                                                betas[1], eps, weight_decay, grad_scale, st), "adam")
+
+    def train_step(self, b: DeviceBatch, gate_u=None, feat_u=None, lr=1e-4, weight_decay=5e-5, world_size=1):
+        """forward + backward (+ gradient all-reduce) + Adam; returns the device losses tensor (no host sync)."""
+        losses = self.forward(b, gate_u, feat_u)
+        self.backward()
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.adam_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / world_size)
+        return losses

@@ -1,0 +1,215 @@
+"""DGL-free batched graphs for the S-CGIB hot path.
+
+``BatchedGraph`` re-provides the slice of the DGLGraph surface the reference uses
+(``dgl.batch`` molecules.py:359; ``.to / .ndata / .edges / .batch_num_nodes / .adj().to_dense()``
+exp_pretraining.py:303-310, models.py:665, 764) on top of int32 CSR tensors, and
+``khop_ego_batch`` replaces the offline ``dgl.khop_in_subgraph`` loop + per-step ``dgl.batch`` of
+the ego-nets (exp_pretraining.py:271, 308-309) with two CUDA kernels per batch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _DenseAdj:
+    def __init__(self, g):
+        self._g = g
+
+    def to_dense(self):
+        src, dst = self._g.edges()
+        n = self._g.num_nodes()
+        a = torch.zeros(n, n, dtype=torch.float32, device=src.device)
+        a[src.long(), dst.long()] = 1.0
+        return a
+
+
+class BatchedGraph:
+    """A batch of undirected graphs stored as one symmetric CSR (neighbours ascending, global ids)."""
+
+    def __init__(self, graph_ptr, indptr, indices, x=None):
+        self.graph_ptr = torch.as_tensor(graph_ptr, dtype=torch.int32)
+        self.indptr = torch.as_tensor(indptr, dtype=torch.int32)
+        self.indices = torch.as_tensor(indices, dtype=torch.int32)
+        self.ndata = {}
+        if x is not None:
+            self.ndata["x"] = torch.as_tensor(x)
+
+    # ---- DGLGraph-compatible surface
+    @property
+    def device(self):
+        return self.indptr.device
+
+    @property
+    def batch_size(self):
+        return self.graph_ptr.numel() - 1
+
+    def num_nodes(self):
+        return self.indptr.numel() - 1
+
+    def num_edges(self):
+        return self.indices.numel()
+
+    def nodes(self):
+        return torch.arange(self.num_nodes(), device=self.device)
+
+    def batch_num_nodes(self):
+        return (self.graph_ptr[1:] - self.graph_ptr[:-1]).long()
+
+    def edges(self):
+        deg = (self.indptr[1:] - self.indptr[:-1]).long()
+        dst = torch.repeat_interleave(torch.arange(self.num_nodes(), device=self.device), deg)
+        return self.indices.long(), dst
+
+    def adj(self):
+        return _DenseAdj(self)
+
+    def to(self, device, non_blocking=False):
+        g = BatchedGraph.__new__(BatchedGraph)
+        g.graph_ptr = self.graph_ptr.to(device, non_blocking=non_blocking)
+        g.indptr = self.indptr.to(device, non_blocking=non_blocking)
+        g.indices = self.indices.to(device, non_blocking=non_blocking)
+        g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
+        return g
+
+    def pin_memory(self):
+        g = BatchedGraph.__new__(BatchedGraph)
+        g.graph_ptr, g.indptr, g.indices = self.graph_ptr.pin_memory(), self.indptr.pin_memory(), self.indices.pin_memory()
+        g.ndata = {k: v.pin_memory() for k, v in self.ndata.items()}
+        return g
+
+    def validate(self):
+        n = self.batch_num_nodes()
+        if int(n.min()) < 2:
+            raise ValueError("every graph needs >= 2 nodes (per-graph BatchNorm / unbiased std, models.py:642-647)")
+        return self
+
+
+def graph(edges, num_nodes: Optional[int] = None, x=None) -> BatchedGraph:
+    """``dgl.graph((src, dst))`` followed by ``dgl.to_bidirected`` (util.py:317-318): reverse edges
+    added, duplicates dropped, num_nodes = max id + 1, neighbours ascending."""
+    src = np.asarray(edges[0], dtype=np.int64)
+    dst = np.asarray(edges[1], dtype=np.int64)
+    if num_nodes is None:
+        num_nodes = int(max(src.max(initial=-1), dst.max(initial=-1)) + 1)
+    s = np.concatenate([src, dst])
+    d = np.concatenate([dst, src])
+    key = np.unique(d * num_nodes + s)          # sorted by (dst, src): CSR rows with ascending neighbours
+    dd, ss = key // num_nodes, key % num_nodes
+    indptr = np.zeros(num_nodes + 1, dtype=np.int64)
+    np.add.at(indptr, dd + 1, 1)
+    return BatchedGraph(np.asarray([0, num_nodes]), np.cumsum(indptr), ss, x)
+
+
+to_bidirected = lambda g: g  # graphs built by ``graph`` are already bidirected
+
+
+def batch(graphs: Sequence[BatchedGraph]) -> BatchedGraph:
+    """``dgl.batch``: concatenate in list order with node-id offsets; ``ndata`` concatenated."""
+    gp, ip, idx = [torch.zeros(1, dtype=torch.int32)], [torch.zeros(1, dtype=torch.int32)], []
+    noff = eoff = 0
+    for g in graphs:
+        gp.append(g.graph_ptr[1:] + noff)
+        ip.append(g.indptr[1:] + eoff)
+        idx.append(g.indices + noff)
+        noff += g.num_nodes()
+        eoff += g.num_edges()
+    out = BatchedGraph(torch.cat(gp), torch.cat(ip), torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int32))
+    keys = graphs[0].ndata.keys() if graphs else ()
+    for k in keys:
+        out.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
+    return out
+
+
+def sum_nodes(g: BatchedGraph, key: str):
+    """``dgl.sum_nodes`` through the CUDA segment kernel."""
+    from .ops import segment_sum
+    return segment_sum(g.ndata[key], g.graph_ptr)
+
+
+class EgoBatch:
+    """Flattened batch of one k-hop ego-net per parent node (what ``dgl.batch(chain(batch_subgraphs))``
+    yields in the reference).  Row j is parent node ``ego_nodes[j]`` inside the ego-net of ``ego_seed[j]``."""
+
+    def __init__(self, parent: BatchedGraph, k, ego_ptr, ego_nodes, ego_seed, sub_indptr, sub_indices):
+        self.parent, self.k = parent, k
+        self.ego_ptr, self.ego_nodes, self.ego_seed = ego_ptr, ego_nodes, ego_seed
+        self.sub_indptr, self.sub_indices = sub_indptr, sub_indices
+
+    @property
+    def device(self):
+        return self.ego_ptr.device
+
+    @property
+    def batch_size(self):
+        return self.ego_ptr.numel() - 1
+
+    def num_nodes(self):
+        return self.ego_nodes.numel()
+
+    def num_edges(self):
+        return self.sub_indices.numel()
+
+    def batch_num_nodes(self):
+        return (self.ego_ptr[1:] - self.ego_ptr[:-1]).long()
+
+    def to(self, device, non_blocking=False):
+        return self if torch.device(device) == self.device else EgoBatch(
+            self.parent.to(device), self.k, *[t.to(device) for t in (self.ego_ptr, self.ego_nodes, self.ego_seed,
+                                                                     self.sub_indptr, self.sub_indices)])
+
+    @property
+    def ndata(self):
+        # x_subs rows are copies of parent rows: a lazy gather, only for API compatibility
+        return {k: v[self.ego_nodes.long()] for k, v in self.parent.ndata.items()}
+
+
+class EgoWorkspace:
+    """Reusable device buffers for ``khop_ego_batch`` (grown on demand)."""
+
+    def __init__(self):
+        self.ws = None
+        self.ptrs = None
+        self.status = None
+        self.host = None
+
+
+def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, stream=None) -> EgoBatch:
+    """k-hop ego-net of every node of ``g`` on the GPU (bit-exact with ``dgl.khop_in_subgraph`` node lists).
+    One host synchronisation (to read Ns / Es between the count and the fill kernel)."""
+    lib = _lib.load()
+    if g.device.type != "cuda":
+        raise RuntimeError("khop_ego_batch needs the graph on a CUDA device (no CPU fallback)")
+    dev = g.device
+    N = g.num_nodes()
+    st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    ws = ws or EgoWorkspace()
+    need = lib.scgib_ego_workspace_bytes(N)
+    if ws.ws is None or ws.ws.numel() < need or ws.ws.device != dev:
+        ws.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws.host = torch.empty(3, dtype=torch.int32).pin_memory()
+    ego_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    ego_eptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.scgib_ego_count(_lib.ptr(g.indptr), _lib.ptr(g.indices), N, int(k), _lib.ptr(ego_ptr),
+                                   _lib.ptr(ego_eptr), _lib.ptr(status), _lib.ptr(ws.ws), ws.ws.numel(), st),
+               "ego_count")
+    ws.host[0:1].copy_(ego_ptr[N:], non_blocking=True)
+    ws.host[1:2].copy_(ego_eptr[N:], non_blocking=True)
+    ws.host[2:3].copy_(status, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    Ns, Es, bad = (int(v) for v in ws.host)
+    if bad:
+        raise RuntimeError("an ego-net exceeds SCGIB_EGO_CAP=%d nodes" % _lib.EGO_CAP)
+    ego_nodes = torch.empty(Ns, dtype=torch.int32, device=dev)
+    ego_seed = torch.empty(Ns, dtype=torch.int32, device=dev)
+    sub_indptr = torch.empty(Ns + 1, dtype=torch.int32, device=dev)
+    sub_indices = torch.empty(max(Es, 1), dtype=torch.int32, device=dev)[:Es]
+    _lib.check(lib.scgib_ego_fill(_lib.ptr(g.indptr), _lib.ptr(g.indices), N, int(k), _lib.ptr(ego_ptr),
+                                  _lib.ptr(ego_eptr), _lib.ptr(ego_nodes), _lib.ptr(ego_seed), _lib.ptr(sub_indptr),
+                                  _lib.ptr(sub_indices), st), "ego_fill")
+    return EgoBatch(g, k, ego_ptr, ego_nodes, ego_seed, sub_indptr, sub_indices)

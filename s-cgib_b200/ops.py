@@ -1,0 +1,58 @@
+"""Thin wrappers over the individual-operator entry points of the C ABI (unit-test surface and the
+building blocks of the drop-in modules).  Every function requires CUDA tensors; nothing falls back to torch."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+HID, DTR = 64, 32
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and t.device.type != "cuda":
+            raise RuntimeError("scgib_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def input_proj(x: torch.Tensor, Wt: torch.Tensor) -> torch.Tensor:
+    """transfer_d(F.normalize(x))  (exp_pretraining.py:312, models.py:668)."""
+    _cuda(x, Wt)
+    x, Wt = x.contiguous().float(), Wt.contiguous().float()
+    t = torch.empty(x.shape[0], DTR, device=x.device)
+    _lib.check(_lib.load().scgib_input_proj_fwd_f32(_lib.ptr(x), _lib.ptr(Wt), x.shape[0], x.shape[1], Wt.shape[0],
+                                                    _lib.ptr(t), _stream(x)), "input_proj_fwd")
+    return t
+
+
+def gin_layer_fwd(h, indptr, indices, W1, b1, W2, b2, row_map=None, bn_in=None, running=None, save=False):
+    """One GINConv + batch statistics (models.py:66-72).  Returns (y, bn{mean,rstd}[2,64], a, r)."""
+    _cuda(h, indptr, W1)
+    lib = _lib.load()
+    V = indptr.numel() - 1
+    kin = h.shape[1]
+    y = torch.empty(V, HID, device=h.device)
+    a = torch.empty(V, kin, device=h.device) if save else None
+    r = torch.empty(V, HID, device=h.device) if save else None
+    bn_out = torch.zeros(4, HID, device=h.device)
+    ws = torch.empty(lib.scgib_gin_workspace_bytes(V), dtype=torch.uint8, device=h.device)
+    _lib.check(lib.scgib_gin_layer_fwd_f32(_lib.ptr(h.contiguous()), kin, _lib.ptr(row_map), _lib.ptr(bn_in),
+                                           _lib.ptr(indptr), _lib.ptr(indices), V, _lib.ptr(W1.contiguous()),
+                                           _lib.ptr(b1), _lib.ptr(W2.contiguous()), _lib.ptr(b2), _lib.ptr(a),
+                                           _lib.ptr(r), _lib.ptr(y), _lib.ptr(bn_out), _lib.ptr(running), _lib.ptr(ws),
+                                           ws.numel(), _stream(h)), "gin_layer_fwd")
+    return y, bn_out[:2], a, r
+
+
+def segment_sum(h, seg_ptr, bn=None):
+    """dgl.sum_nodes (models.py:716, 725, 733, 684); optional fused relu(BN(.)) on load."""
+    _cuda(h, seg_ptr)
+    S = seg_ptr.numel() - 1
+    out = torch.empty(S, HID, device=h.device)
+    _lib.check(_lib.load().scgib_segment_sum_f32(_lib.ptr(h.contiguous()), _lib.ptr(seg_ptr), S, _lib.ptr(bn),
+                                                 _lib.ptr(out), _stream(h)), "segment_sum")
+    return out

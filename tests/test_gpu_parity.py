@@ -1,0 +1,250 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  The CUDA path is called through the C ABI
+(ctypes) and compared with (1) the golden vectors recorded from the unmodified reference models.py and
+(2) the CPU oracle on seeded synthetic batches.
+
+Tolerances (BASELINE.json north_star): embeddings and losses 1e-5 relative (fp32, max-norm);
+gradients 2e-4 relative (they pass through ~20 more fp32 reductions than the forward); ego-net index lists
+bit-exact.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.graph_ref import (RefEgoBatch, RefGraph, batch_ref, ego_batch_ref, graph_from_bonds, path_graph,
+                              synth_batch)
+from oracle.scgib_oracle import (OracleMainmodel, draw_noise_like_reference, normalize_rows, tgraph_from_ego,
+                                 tgraph_from_ref)
+from tests.helpers import (compare_grads, engine_from_oracle, oracle_grads, product_ego_from_ref, product_graph, rel)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pretrain_*.pt")))
+FWD_TOL, GRAD_TOL = 1e-5, 2e-4
+
+
+def _ego_equal(ego, e: RefEgoBatch):
+    assert np.array_equal(ego.ego_ptr.cpu().numpy(), e.ego_ptr)
+    assert np.array_equal(ego.ego_nodes.cpu().numpy(), e.ego_nodes)
+    assert np.array_equal(ego.sub_indptr.cpu().numpy(), e.sub_indptr)
+    assert np.array_equal(ego.sub_indices.cpu().numpy(), e.sub_indices)
+    seed = np.repeat(np.arange(len(e.ego_ptr) - 1), np.diff(e.ego_ptr))
+    assert np.array_equal(ego.ego_seed.cpu().numpy(), seed)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("seed,B", [(0, 64), (3, 257)])
+def test_ego_extraction_bit_exact(seed, B, k):
+    from scgib_b200.graph import khop_ego_batch
+    g = synth_batch(seed, B)
+    _ego_equal(khop_ego_batch(product_graph(g, DEV), k), ego_batch_ref(g, k))
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_ego_extraction_adversarial(k):
+    from scgib_b200.graph import khop_ego_batch
+    ring = graph_from_bonds(12, [(i, (i + 1) % 12) for i in range(12)])
+    star = graph_from_bonds(40, [(0, i) for i in range(1, 40)])          # degree 39 > one warp of neighbours
+    iso = graph_from_bonds(6, [(0, 5), (2, 3)])                          # isolated interior nodes 1, 4
+    g = batch_ref([ring, star, iso, path_graph(2), path_graph(33)])
+    _ego_equal(khop_ego_batch(product_graph(g, DEV), k), ego_batch_ref(g, k))
+
+
+def test_ego_extraction_large_matches_properties():
+    """Full-size batch (B=4096): sizes, sortedness, seed membership, symmetry of the induced CSR."""
+    from scgib_b200.graph import khop_ego_batch
+    from scgib_b200.synth import synth_batch as psynth
+    g = psynth(5, 4096).to(DEV)
+    ego = khop_ego_batch(g, 2)
+    ptr, nodes, seed = ego.ego_ptr.long(), ego.ego_nodes.long(), ego.ego_seed.long()
+    assert int(ptr[-1]) == nodes.numel() and int(ego.sub_indptr[-1]) == ego.sub_indices.numel()
+    d = nodes[1:] - nodes[:-1]
+    same = seed[1:] == seed[:-1]
+    assert bool((d[same] > 0).all())                                        # ascending inside each ego-net
+    assert int((nodes == seed).sum()) == g.num_nodes()                      # each ego-net contains its seed once
+    deg = (ego.sub_indptr[1:] - ego.sub_indptr[:-1]).long()
+    dst = torch.repeat_interleave(torch.arange(nodes.numel(), device=DEV), deg)
+    src = ego.sub_indices.long()
+    assert bool((seed[src] == seed[dst]).all())
+    key = src * nodes.numel() + dst
+    assert torch.equal(torch.sort(key)[0], torch.sort(dst * nodes.numel() + src)[0])   # symmetric
+
+
+def test_input_proj_and_segment_sum():
+    from scgib_b200 import ops
+    torch.manual_seed(0)
+    x = torch.rand(1000, 9) * 10
+    W = torch.randn(32, 9)
+    ref = torch.nn.functional.normalize(x) @ W.t()
+    assert rel(ops.input_proj(x.to(DEV), W.to(DEV)), ref) <= 2e-6
+    h = torch.randn(1000, 64)
+    ptr = torch.tensor([0, 3, 3, 500, 1000], dtype=torch.int32)
+    ref = torch.stack([h[0:3].sum(0), h[3:3].sum(0), h[3:500].sum(0), h[500:].sum(0)])
+    assert rel(ops.segment_sum(h.to(DEV), ptr.to(DEV)), ref) <= 2e-6
+
+
+@pytest.mark.parametrize("kin", [32, 64])
+def test_gin_layer_forward(kin):
+    from scgib_b200 import ops
+    from oracle.scgib_oracle import GINConvRef, MLP
+    g = synth_batch(1, 300)
+    tg = tgraph_from_ref(g)
+    torch.manual_seed(kin)
+    conv = GINConvRef(MLP(kin, 64, 64))
+    h = torch.randn(g.num_nodes, kin)
+    y_ref = conv(tg, h)
+    lin1, lin2 = conv.apply_func.mlp[0], conv.apply_func.mlp[2]
+    pg = product_graph(g, DEV)
+    y, bn, a, r = ops.gin_layer_fwd(h.to(DEV), pg.indptr, pg.indices, lin1.weight.detach().to(DEV),
+                                    lin1.bias.detach().to(DEV), lin2.weight.detach().to(DEV),
+                                    lin2.bias.detach().to(DEV), save=True)
+    assert rel(y, y_ref) <= 2e-6
+    assert rel(bn[0], y_ref.mean(0)) <= 1e-5
+    assert rel(bn[1], 1.0 / torch.sqrt(y_ref.var(0, unbiased=False) + 1e-5)) <= 1e-5
+    neigh = torch.zeros_like(h).index_add(0, tg.dst, h[tg.src])
+    assert rel(a, h + neigh) <= 2e-6
+
+
+def _run_engine(m, g, e, k, gate_u, feat_u, from_gpu_ego=True):
+    from scgib_b200.engine import DeviceBatch
+    from scgib_b200.graph import khop_ego_batch
+    eng = engine_from_oracle(m, DEV)
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, k) if from_gpu_ego else product_ego_from_ref(pg, e, k, DEV)
+    b = DeviceBatch(pg, ego, pg.ndata["x"], normalize_x=True)
+    losses, emb = eng.forward(b, gate_u.to(DEV), feat_u.to(DEV), want=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    return eng, losses.cpu(), emb
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_golden_reference_parity(path):
+    """CUDA path vs the unmodified reference models.py (golden vectors): losses, embeddings, all 61 gradients,
+    BN running statistics."""
+    fx = torch.load(path, weights_only=False)
+    g, e = RefGraph(**fx["graph"]), RefEgoBatch(**fx["ego"])
+    k = fx["meta"]["k"]
+    m = OracleMainmodel(9, 64, 32, 4)
+    m.load_state_dict(fx["state"], strict=False)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
+    ref = fx["out"]
+    for i, name in enumerate(("KL", "contrastive", "recon")):
+        assert abs(float(losses[i]) - float(ref[name])) <= FWD_TOL * abs(float(ref[name])), (name, float(losses[i]), float(ref[name]))
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(emb[name], ref[name]) <= FWD_TOL, (name, rel(emb[name], ref[name]))
+    compare_grads(eng, fx["grads"], GRAD_TOL)
+    sd = eng.state_dict()
+    for n, t in fx["state_after"].items():
+        if t.dtype.is_floating_point:
+            assert rel(sd[n], t) <= 1e-5, n
+
+
+@pytest.mark.parametrize("seed,B,k", [(11, 128, 1), (12, 96, 2), (13, 40, 3)])
+def test_parity_vs_faithful_oracle(seed, B, k):
+    """config 1 size (B=128): loop-for-loop oracle incl. the dense N x N reconstruction."""
+    g = synth_batch(seed, B)
+    e = ego_batch_ref(g, k)
+    torch.manual_seed(seed)
+    m = OracleMainmodel(9)
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, seed + 100)
+    out = m.forward_faithful(tgraph_from_ref(g), x, tgraph_from_ego(e), x[en], gate_u, feat_u)
+    ref_grads = oracle_grads(m, out)
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
+    for i, name in enumerate(("KL", "contrastive", "recon")):
+        assert abs(float(losses[i]) - float(out[name])) <= FWD_TOL * abs(float(out[name])), (name, float(losses[i]), float(out[name]))
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(emb[name], out[name]) <= FWD_TOL, (name, rel(emb[name], out[name]))
+    compare_grads(eng, ref_grads, GRAD_TOL)
+
+
+@pytest.mark.parametrize("B,k", [(4096, 1)])
+def test_parity_full_size_vs_vectorised_oracle_fp64(B, k):
+    """config 2 size (B=4096, ~61k nodes): the vectorised oracle in fp64 is the ground truth; the CUDA fp32 path
+    must be as close to it as fp32 allows (1e-5 on embeddings/losses)."""
+    g = synth_batch(21, B)
+    e = ego_batch_ref(g, k)
+    torch.manual_seed(21)
+    m = OracleMainmodel(9)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 121)
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
+    m64 = OracleMainmodel(9).double()
+    m64.load_state_dict({k_: v.double() if v.dtype.is_floating_point else v for k_, v in m.state_dict().items()})
+    x = normalize_rows(torch.from_numpy(g.x).double())
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    out = m64.forward_vectorised(tgraph_from_ref(g), x, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())
+    ref_grads = oracle_grads(m64, out)
+    for i, name in enumerate(("KL", "contrastive", "recon")):
+        assert abs(float(losses[i]) - float(out[name])) <= FWD_TOL * abs(float(out[name])), (name, float(losses[i]), float(out[name]))
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(emb[name], out[name]) <= FWD_TOL, (name, rel(emb[name], out[name]))
+    compare_grads(eng, ref_grads, GRAD_TOL)
+
+
+def test_forward_backward_deterministic():
+    """No float atomics anywhere: two runs are bit-identical."""
+    g = synth_batch(31, 512)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(31)
+    m = OracleMainmodel(9)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 131)
+    eng1, l1, emb1 = _run_engine(m, g, e, 1, gate_u, feat_u)
+    g1 = eng1.grads.clone()
+    eng2, l2, emb2 = _run_engine(m, g, e, 1, gate_u, feat_u)
+    assert torch.equal(l1, l2) and torch.equal(emb1["Z"], emb2["Z"]) and torch.equal(g1, eng2.grads)
+
+
+def test_adam_matches_torch():
+    from scgib_b200.engine import PretrainEngine
+    eng = PretrainEngine(9, device=DEV, seed=3)
+    p0 = eng.params.clone()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-4, weight_decay=5e-5)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    for step in range(5):
+        gr = torch.randn(eng.total, device=DEV, generator=gen)
+        eng.grads.copy_(gr)
+        eng.adam_step(lr=1e-4, weight_decay=5e-5)
+        ref.grad = gr.clone()
+        opt.step()
+    assert rel(eng.params - p0, ref.detach() - p0) <= 1e-5
+
+
+def test_train_steps_follow_oracle_trajectory():
+    """5 optimiser steps (forward + backward + Adam) track the oracle's loss trajectory."""
+    from scgib_b200.engine import DeviceBatch
+    from scgib_b200.graph import khop_ego_batch
+    g = synth_batch(41, 64)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(41)
+    m = OracleMainmodel(9)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=5e-5)
+    eng = engine_from_oracle(m, DEV)
+    pg = product_graph(g, DEV)
+    b = DeviceBatch(pg, khop_ego_batch(pg, 1), pg.ndata["x"])
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    for step in range(5):
+        gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 200 + step)
+        opt.zero_grad()
+        out = m.forward_faithful(tg, x, te, x[en], gate_u, feat_u)
+        loss = out["KL"] + out["recon"] + out["contrastive"]
+        loss.backward()
+        opt.step()
+        got = eng.train_step(b, gate_u.to(DEV), feat_u.to(DEV), lr=1e-3)
+        assert abs(float(got[3]) - float(loss)) <= 1e-4 * abs(float(loss)), (step, float(got[3]), float(loss))
+
+
+def test_bad_arguments_raise():
+    from scgib_b200 import _lib
+    from scgib_b200.engine import PretrainEngine
+    with pytest.raises(RuntimeError):
+        PretrainEngine(9, hidden=48, device=DEV)          # unsupported width -> SCGIB_E_SHAPE
+    with pytest.raises(RuntimeError):
+        PretrainEngine(9, device="cpu")                   # no CPU fallback
