@@ -193,6 +193,13 @@ SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int
 SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,
                                                   int32_t Es, const char* name);
 
+/* Per-launch timing with CUDA events recorded on the launching stream (used by bench.py for the roofline
+ * numbers).  enable(1) clears the record; every later kernel launch of this library is bracketed by two events;
+ * after synchronising the stream, profile_get(i) returns the static kernel-family name and the elapsed ms. */
+SCGIB_API void scgib_profile_enable(int on);
+SCGIB_API int scgib_profile_count(void);
+SCGIB_API int scgib_profile_get(int i, const char** name, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

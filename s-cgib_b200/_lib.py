@@ -52,6 +52,9 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "scgib_profile_enable": (None, [c_int]),
+    "scgib_profile_count": (c_int, []),
+    "scgib_profile_get": (c_int, [c_int, POINTER(c_char_p), POINTER(c_float)]),
     "scgib_pretrain_workspace_offset": (c_int64, [POINTER(Dims), c_int32, c_int32, c_int32, c_int32, c_int32, c_char_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

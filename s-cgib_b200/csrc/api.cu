@@ -19,6 +19,29 @@ int num_sms() {
 
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
+// Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers).
+struct Prof {
+  bool on = false;
+  int n = 0;
+  static constexpr int kMax = 512;
+  cudaEvent_t ev[2 * kMax];
+  int made = 0;
+  const char* name[kMax];
+};
+static Prof g_prof;
+static inline void prof_begin(const char* name, cudaStream_t s) {
+  if (!g_prof.on || g_prof.n >= Prof::kMax) return;
+  while (g_prof.made < 2 * (g_prof.n + 1)) cudaEventCreate(&g_prof.ev[g_prof.made++]);
+  g_prof.name[g_prof.n] = name;
+  cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+}
+static inline void prof_end(cudaStream_t s) {
+  if (!g_prof.on || g_prof.n >= Prof::kMax) return;
+  cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s);
+  ++g_prof.n;
+}
+#define PROF(name, stmt) do { prof_begin(name, s); stmt; prof_end(s); } while (0)
+
 static bool dims_ok(const ScgibDims* d) {
   return d && d->hidden == HID && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&
          d->in_dim <= 32;
@@ -210,9 +233,9 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
     add(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1t, HID, 2 * HID);
     add(params + lo.off[SCGIB_P_HEAD_W2], w.head_w2t, HID, HID);
     add(params + lo.off[SCGIB_P_COMP_W1], w.comp_w1t, HID, HID);
-    launch_transposes(jobs, s);
+    PROF("transpose_weights", launch_transposes(jobs, s));
   }
-  launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s);
+  PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s));
   // the two GIN encoders (models.py:704, 707)
   for (int e = 0; e < 2; ++e) {
     for (int l = 0; l < L; ++l) {
@@ -230,16 +253,16 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
       a.part = w.small_part; a.counter = w.counters + 0;
       a.bn_out = w.bn[e][l];
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
-      launch_gin_fwd(a, l == 0 ? DTR : HID, s);
+      PROF(e == 0 ? "gin_fwd.enc1" : "gin_fwd.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
     }
   }
   {
     GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q};
-    launch_gate_lin_fwd(a, s);
+    PROF("gate_lin_fwd", launch_gate_lin_fwd(a, s));
   }
   {
     EgoPoolFwdArgs a{w.y[1][L - 1], w.bn[1][L - 1], b->ego_ptr, b->N, params + lo.off[SCGIB_P_ATTN_W] + HID, w.C, w.logit};
-    launch_ego_pool_fwd(a, s);
+    PROF("ego_pool_fwd", launch_ego_pool_fwd(a, s));
   }
   {
     GraphGateFwdArgs a;
@@ -249,30 +272,30 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
     a.gate_u = b->gate_u; a.feat_u = b->feat_u; a.logit = w.logit;
     a.noisy = w.noisy; a.lam = w.lam; a.alpha = w.alpha; a.readout = w.readout; a.core = w.core;
     a.gstat = w.gstat; a.cstat = bn_running ? w.cstat : nullptr; a.kl = w.kl;
-    launch_graph_gate_fwd(a, s);
-    if (bn_running) launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s);
+    PROF("graph_gate_fwd", launch_graph_gate_fwd(a, s));
+    if (bn_running) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s));
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
                   params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.r_head, w.Z};
-    launch_head_fwd(a, s);
+    PROF("head_fwd", launch_head_fwd(a, s));
   }
   {
     const int grid = num_sms();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
-    launch_recon_fwd(a, grid, s);
-    launch_recon_reduce(w.rpart, grid, w.G, w.edge, s);
+    PROF("recon_fwd", launch_recon_fwd(a, grid, s));
+    PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, s));
   }
   const int js = contrastive_jsplit(b->B);
   {
     NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag};
-    launch_normalize(a, s);
+    PROF("normalize", launch_normalize(a, s));
     ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum};
-    launch_contrastive_fwd(c, s);
+    PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
   }
   {
     LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, w.kl, w.D, losses};
-    launch_loss_finalize(a, s);
+    PROF("loss_finalize", launch_loss_finalize(a, s));
   }
   if (Z) cudaMemcpyAsync(Z, w.Z, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (noisy) cudaMemcpyAsync(noisy, w.noisy, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -300,19 +323,19 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
   const int js = contrastive_jsplit(b->B);
   {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
-    launch_contrastive_bwd(a, s);
+    PROF("contrastive_bwd", launch_contrastive_bwd(a, s));
     ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
-    launch_contrastive_bwd_finalize(f, s);
+    PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, s));
   }
   {
     ReconBwdArgs a{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
-    launch_recon_bwd(a, s);
+    PROF("recon_bwd", launch_recon_bwd(a, s));
   }
   {
     HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
                   params + lo.off[SCGIB_P_HEAD_W2], w.gI, w.ppart, lo.total,
                   lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_W2], lo.off[SCGIB_P_HEAD_B2]};
-    launch_head_bwd(a, GP, s);
+    PROF("head_bwd", launch_head_bwd(a, GP, s));
   }
   {
     GraphGateBwdArgs a;
@@ -326,12 +349,12 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
     a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
     a.d_wc2 = grads + lo.off[SCGIB_P_COMP_W2]; a.d_bc2 = grads + lo.off[SCGIB_P_COMP_B2];
     a.d_attn_w = grads + lo.off[SCGIB_P_ATTN_W]; a.d_attn_b = grads + lo.off[SCGIB_P_ATTN_B];
-    launch_graph_gate_bwd(a, s);
+    PROF("graph_gate_bwd", launch_graph_gate_bwd(a, s));
   }
   {
     GateLinBwdArgs a{w.g_q, w.H, b->N, params + lo.off[SCGIB_P_COMP_W1], w.gH, w.ppart, lo.total,
                      lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1]};
-    launch_gate_lin_bwd(a, GP, s);
+    PROF("gate_lin_bwd", launch_gate_lin_bwd(a, GP, s));
   }
   for (int e = 0; e < 2; ++e) {
     const int V = e == 0 ? b->N : b->Ns;
@@ -348,14 +371,14 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
       pa.y = w.y[e][l]; pa.bn = w.bn[e][l]; pa.V = V; pa.g_o = w.g_o; pa.part = w.small_part; pa.counter = w.counters + 2;
       pa.d_gamma = grads + lo.enc(e, l, L, SCGIB_ENC_GAMMA); pa.d_beta = grads + lo.enc(e, l, L, SCGIB_ENC_BETA);
       pa.cvec = w.cvec;
-      launch_gin_bwd_pre(pa, s);
+      PROF(e == 0 ? "gin_bwd_pre.enc1" : "gin_bwd_pre.enc2", launch_gin_bwd_pre(pa, s));
       GinBwdMainArgs ma;
       ma.g_o = w.g_o; ma.y = w.y[e][l]; ma.r = w.r[e][l]; ma.a = w.a[e][l]; ma.bn = w.bn[e][l]; ma.cvec = w.cvec;
       ma.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); ma.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
       ma.V = V; ma.g_a = l == 0 ? w.ga0[e] : w.Ga; ma.part = w.ppart; ma.pstride = lo.total;
       ma.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); ma.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
       ma.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); ma.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
-      launch_gin_bwd_main(ma, kin, GP, s);
+      PROF(e == 0 ? "gin_bwd_main.enc1" : "gin_bwd_main.enc2", launch_gin_bwd_main(ma, kin, GP, s));
     }
   }
   {
@@ -365,7 +388,7 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
     a.map[0] = nullptr; a.map[1] = b->ego_nodes; a.V[0] = b->N; a.V[1] = b->Ns;
     a.x = b->x; a.F = d->in_dim; a.normalize = b->normalize_x; a.part = w.small_part; a.counter = w.counters + 3;
     a.d_Wt = grads + lo.off[SCGIB_P_TRANSFER];
-    launch_input_proj_bwd(a, s);
+    PROF("input_proj_bwd", launch_input_proj_bwd(a, s));
   }
   {
     ReduceRanges r;
@@ -375,7 +398,7 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
     add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1]);
     for (int e = 0; e < 2; ++e)
       for (int l = 0; l < L; ++l) add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1));
-    launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s);
+    PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
   }
   return (int)cudaGetLastError();
 }
@@ -385,7 +408,8 @@ extern "C" SCGIB_API int scgib_adam_step_f32(float* params, const float* grads, 
                                    float grad_scale, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq) return SCGIB_E_NULL;
   if (n < 1 || step < 1) return SCGIB_E_RANGE;
-  launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  PROF("adam", launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, s));
   return (int)cudaGetLastError();
 }
 
@@ -463,4 +487,14 @@ extern "C" SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d,
     if (p) return (int64_t)((const char*)p - (const char*)nullptr);
   }
   return -1;
+}
+
+// ---------------------------------------------------------------- per-launch timing (bench.py)
+extern "C" SCGIB_API void scgib_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; }
+extern "C" SCGIB_API int scgib_profile_count(void) { return g_prof.n; }
+// Name and elapsed milliseconds of recorded launch i (the caller has synchronised the stream).
+extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) {
+  if (i < 0 || i >= g_prof.n || !name || !ms) return SCGIB_E_RANGE;
+  *name = g_prof.name[i];
+  return (int)cudaEventElapsedTime(ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]);
 }
