@@ -2,6 +2,7 @@
 // launch sequences of the whole pre-training forward / backward.  No device memory is allocated here.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "../../include/scgib.h"
 
@@ -40,7 +41,19 @@ static inline void prof_end(cudaStream_t s) {
   cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s);
   ++g_prof.n;
 }
-#define PROF(name, stmt) do { prof_begin(name, s); stmt; prof_end(s); } while (0)
+// SCGIB_DEBUG_SYNC=1: synchronise after every launch and report the first failing kernel by name.
+static inline bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static inline void debug_check(const char* name, cudaStream_t s) {
+  if (!debug_sync()) return;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "[scgib] kernel '%s' failed: %s\n", name, cudaGetErrorString(e)); fflush(stderr); }
+}
+#define PROF(name, stmt) do { prof_begin(name, s); stmt; prof_end(s); debug_check(name, s); } while (0)
 
 static bool dims_ok(const ScgibDims* d) {
   return d && d->hidden == HID && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&

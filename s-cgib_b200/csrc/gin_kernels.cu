@@ -20,7 +20,7 @@ namespace scgib {
 __global__ void __launch_bounds__(kThreads)
 input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt, int N, int F, int normalize,
                       float* __restrict__ t) {
-  __shared__ float s_w[32 * DTR];  // [f][o]
+  __shared__ __align__(16) float s_w[32 * DTR];  // [f][o]
   for (int i = threadIdx.x; i < F * DTR; i += kThreads) {
     const int o = i / F, f = i % F;
     s_w[f * DTR + o] = Wt[i];
@@ -245,7 +245,7 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 gin_bwd_pre_kernel(GinBwdPreArgs p) {
-  __shared__ float s_red[16 * 2 * HID];
+  __shared__ __align__(16) float s_red[16 * 2 * HID];
   __shared__ double s_d[2 * 2 * HID];
   const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
   Bn4 bn;

@@ -272,7 +272,7 @@ void launch_compressor_ema(const float* cstat, int B, float* running, cudaStream
 
 __global__ void __launch_bounds__(kThreads)
 graph_gate_bwd_kernel(GraphGateBwdArgs p) {
-  __shared__ float s_red[(kThreads / 32) * 5 * HID];
+  __shared__ __align__(16) float s_red[(kThreads / 32) * 5 * HID];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = 2 * lane;
   const float2 gam = ld2(p.gamma_c + c), bet = ld2(p.beta_c + c), w2 = ld2(p.wc2 + c), wc = ld2(p.w_cand + c);

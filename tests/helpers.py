@@ -41,24 +41,46 @@ def oracle_grads(m, out):
     return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
 
 
-def compare_grads(eng, ref_grads, tol, report=None):
-    """Compare the engine's flat gradient buffer with reference-named gradients."""
+def fp64_truth(m, g, e, gate_u, feat_u):
+    """fp64 vectorised oracle (forward + all parameter gradients) with the weights of ``m``: the ground truth
+    both the fp32 reference run and the fp32 CUDA path are measured against."""
+    m64 = OracleMainmodel(m.transfer_d.in_features, 64, 32, len(m.Encoder1.ginlayers)).double()
+    m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
+    x = normalize_rows(torch.from_numpy(g.x).double())
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    out = m64.forward_vectorised(tgraph_from_ref(g), x, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())
+    return out, oracle_grads(m64, out)
+
+
+def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_grads, fwd_tol=1e-5, grad_tol=2e-4,
+                        slack=5.0):
+    """The CUDA fp32 result must be as close to the fp64 truth as the tolerance of BASELINE.json (1e-5 relative on
+    losses/embeddings; 2e-4 on gradients) - or, where fp32 itself cannot reach that, within ``slack`` x the distance
+    of the reference-precision (fp32 torch) run from the same truth.  The fp32 floor is set by ill-conditioned terms
+    of the reference math itself - e.g. the KL gradient ~ (H - mu_g) / (sigma_g + 1e-7)^2 with sigma_g ~ 1e-3 - whose
+    error depends on each implementation's rounding of H, so two correct fp32 implementations differ by small factors."""
+    report = []
+
+    def one(name, got, ref, truth, tol):
+        e_got, e_ref = rel(got, truth), rel(ref, truth)
+        bound = max(tol, slack * e_ref)
+        report.append((name, e_got, e_ref, bound))
+        assert e_got <= bound, (name, "cuda-vs-fp64 %.3e" % e_got, "fp32ref-vs-fp64 %.3e" % e_ref, "bound %.3e" % bound)
+
+    for i, name in enumerate(("KL", "contrastive", "recon")):
+        one(name, losses[i].reshape(1), ref_out[name].reshape(1), truth_out[name].reshape(1), fwd_tol)
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        one(name, emb[name], ref_out[name], truth_out[name], fwd_tol)
     gv = eng.grad_views()
-    gmax = max(float(v.abs().max()) for v in ref_grads.values())
-    worst = ("", 0.0)
+    gmax = max(float(v.abs().max()) for v in truth_grads.values())
     for n, got in gv.items():
-        ref = ref_grads[n].to(got.device).reshape(got.shape)
+        truth = truth_grads[n].reshape(got.shape)
+        ref = ref_grads[n].reshape(got.shape)
         if is_zero_grad_param(n):
-            err = float(got.abs().max()) / gmax
-            bound = 1e-5
-        elif n == "attn_layer.weight":
-            assert float(got[:, :64].abs().max()) == 0.0
-            err = rel(got[:, 64:], ref[:, 64:]); bound = tol
-        else:
-            err = rel(got, ref); bound = tol
-        if report is not None:
-            report.append((n, err, bound))
-        if err / bound > worst[1]:
-            worst = (n, err / bound)
-        assert err <= bound, (n, err, bound)
-    return worst
+            assert float(got.abs().max()) <= 1e-5 * gmax, n
+            continue
+        if n == "attn_layer.weight":
+            assert float(got[:, :64].abs().max()) == 0.0          # core half: exactly zero (SURVEY F14)
+            got, ref, truth = got[:, 64:], ref[:, 64:], truth[:, 64:]
+        one("grad " + n, got, ref, truth, grad_tol)
+    return report
