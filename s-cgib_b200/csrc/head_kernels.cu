@@ -259,15 +259,29 @@ void launch_graph_gate_fwd(const GraphGateFwdArgs& a, cudaStream_t s) {
 }
 
 // running stats of the compressor BN after B sequential per-graph updates (closed form, fixed order)
-__global__ void __launch_bounds__(2 * HID)
+// r_B = 0.9^B r_0 + sum_g 0.1 * 0.9^(B-1-g) stat_g ; graphs older than kEmaWindow contribute < 0.9^768 ~ 1e-35.
+constexpr int kEmaWindow = 768;
+constexpr int kEmaSeg = 8;
+__global__ void __launch_bounds__(2 * HID * kEmaSeg)
 compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict__ running) {
-  const int j = threadIdx.x;  // 0..63 mean, 64..127 var
-  double r = (double)running[j];
-  for (int g = 0; g < B; ++g) r = 0.9 * r + 0.1 * (double)cstat[(size_t)g * 2 * HID + j];
-  running[j] = (float)r;
+  __shared__ double s_part[kEmaSeg][2 * HID];
+  const int j = threadIdx.x & (2 * HID - 1);  // 0..63 mean, 64..127 var
+  const int seg = threadIdx.x / (2 * HID);
+  const int g0 = B > kEmaWindow ? B - kEmaWindow : 0;
+  double acc = 0.0;
+  for (int g = g0 + seg; g < B; g += kEmaSeg)
+    acc += 0.1 * pow(0.9, (double)(B - 1 - g)) * (double)cstat[(size_t)g * 2 * HID + j];
+  s_part[seg][j] = acc;
+  __syncthreads();
+  if (seg == 0) {
+    double r = pow(0.9, (double)B) * (double)running[j];
+#pragma unroll
+    for (int k = 0; k < kEmaSeg; ++k) r += s_part[k][j];
+    running[j] = (float)r;
+  }
 }
 void launch_compressor_ema(const float* cstat, int B, float* running, cudaStream_t s) {
-  compressor_ema_kernel<<<1, 2 * HID, 0, s>>>(cstat, B, running);
+  compressor_ema_kernel<<<1, 2 * HID * kEmaSeg, 0, s>>>(cstat, B, running);
 }
 
 __global__ void __launch_bounds__(kThreads)

@@ -12,7 +12,7 @@ from oracle.scgib_oracle import OracleMainmodel, draw_noise_like_reference, norm
 from tests.helpers import engine_from_oracle, is_zero_grad_param, product_graph, rel
 
 
-def main(B=64, k=1, seed=7):
+def main(B=64, k=1, seed=7, nseed=None):
     dev = "cuda:0"
     from scgib_b200.engine import DeviceBatch
     from scgib_b200.graph import khop_ego_batch
@@ -20,7 +20,7 @@ def main(B=64, k=1, seed=7):
     e = ego_batch_ref(g, k)
     torch.manual_seed(seed)
     m = OracleMainmodel(9)
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, seed + 1)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, seed + 1 if nseed is None else nseed)
     m64 = OracleMainmodel(9).double()
     m64.load_state_dict({n: v.double() if v.dtype.is_floating_point else v for n, v in m.state_dict().items()})
     tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
@@ -35,7 +35,16 @@ def main(B=64, k=1, seed=7):
             y = layer(gr, h); y.retain_grad(); keep["y%s_%d" % (tag, i)] = y
             h = F.relu(encoder.batch_norms[i](y))
         return h
+    a_in = {}
+    def pre_hook(tag):
+        def f(mod, inp):
+            inp[0].retain_grad(); a_in[tag] = inp[0]
+        return f
+    for tag, encm in (("1", m64.Encoder1), ("2", m64.Encoder2)):
+        for l, layer in enumerate(encm.ginlayers):
+            layer.apply_func.register_forward_pre_hook(pre_hook("%s_%d" % (tag, l)))
     out = m64.forward_vectorised(tg, x, te, en, gate_u.double(), feat_u.double())
+    a_saved = dict(a_in)
     for name in ("H", "C", "Z", "noisy", "core_readout", "graph_readout"):
         out[name].retain_grad()
     enc(m64.Encoder1, tg, t, "1"); enc(m64.Encoder2, te, t[en], "2")     # per-layer pre-BN outputs (same math)
@@ -77,6 +86,15 @@ def main(B=64, k=1, seed=7):
     cmp("gZ", eng.debug_buffer("gZ", (N, 64)), out["Z"].grad)
     cmp("gH(total)", eng.debug_buffer("gH", (N, 64)), out["H"].grad)
     cmp("gC", eng.debug_buffer("gC", (N, 64)), out["C"].grad)
+    cmp("g_a enc1 layer0", eng.debug_buffer("ga0_1", (N, 32)), a_saved["1_0"].grad)
+    cmp("g_a enc2 layer0", eng.debug_buffer("ga0_2", (Ns, 32)), a_saved["2_0"].grad)
+    for l in range(4):
+        cmp("a1_%d (saved)" % l, eng.debug_buffer("a1_%d" % l, (N, 32 if l == 0 else 64)), a_saved["1_%d" % l])
+    seg = tg.seg_ids()
+    lastmask = (seg == seg.max())
+    gh_got, gh_ref = eng.debug_buffer("gH", (N, 64)).cpu().double(), out["H"].grad
+    rows.append(("gH rows of last graph", float((gh_got[lastmask] - gh_ref[lastmask]).abs().max() / gh_ref.abs().max()), float(gh_ref[lastmask].abs().max())))
+    rows.append(("gH rows of other graphs", float((gh_got[~lastmask] - gh_ref[~lastmask]).abs().max() / gh_ref.abs().max()), float(gh_ref[~lastmask].abs().max())))
     gv = eng.grad_views()
     gmax = max(float(v.abs().max()) for v in ref_grads.values())
     for n, got in gv.items():
