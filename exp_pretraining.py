@@ -1,0 +1,173 @@
+"""Drop-in for the reference's ``exp_pretraining.py`` CLI (same flags and defaults, reference
+exp_pretraining.py:359-406) on the B200 path.
+
+    python exp_pretraining.py --encoder GIN --dims 64 --num_layers 4 --k_transition 1 --device cuda:0
+
+Differences forced by the environment: the OGB / QM9 / mol-PCBA datasets and the DGL ``pts/*.bin`` files are not
+available offline, so ``load_graphdataset`` reads a packed CSR shard ``pts/<name>_csr.pt`` if present and otherwise
+generates ``--synthetic`` molecules of the dataset's shape; k-hop ego-nets are extracted on the GPU per batch
+instead of being loaded from ``pts/<name>_subgraphs_khop_<k>.pt``.
+"""
+import argparse
+import logging
+import os
+import random
+import time
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+from torch.utils.data import DataLoader
+
+from molecules import MoleculeDataset
+from models import Mainmodel, Mainmodel_continue
+from scgib_b200.graph import BatchedGraph, khop_ego_batch
+from scgib_b200.synth import synth_batch
+
+
+def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
+    best_epoch, best_model, best_loss = 0, model, 100000000
+    for epoch in range(1, args.pt_epoches):
+        epoch_train_loss, KL_Loss, contrastive_loss, reconstruction_loss = train_epoch_pre_training(
+            model, args, optimizer, device, pre_train_loader1, epoch, 1, batch_size)
+        if best_loss >= epoch_train_loss:
+            best_model, best_epoch, best_loss = model, epoch, epoch_train_loss
+        if epoch - best_epoch > 50:
+            break
+        print("Epoch:%d	|Best_epoch:%d	|Train_loss:%0.4f" % (epoch, best_epoch, epoch_train_loss))
+    return best_model, best_epoch
+
+
+def train_epoch_pre_training(model, args, optimizer, device, data_loader, epoch, k_transition, batch_size=16):
+    """reference exp_pretraining.py:290-333, one difference: ego-nets come from the GPU extraction kernel."""
+    model.train()
+    epoch_loss = epoch_KL = epoch_con = epoch_rec = 0
+    count = 0
+    for it, (batch_graphs, _, batch_subgraphs, batch_logMs) in enumerate(data_loader):
+        count = it
+        batch_graphs = batch_graphs.to(device)
+        batch_x = batch_graphs.ndata['x'].float().to(device)
+        edge_index = None
+        optimizer.zero_grad()
+        flatten_batch_subgraphs = khop_ego_batch(batch_graphs, args.k_transition)
+        x_subs = None                                   # rows of batch_x (ego_nodes); never materialised
+        batch_x = F.normalize(batch_x)
+        _, KL_Loss, contrastive_loss, reconstruction_loss = model.forward(
+            batch_graphs, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, 1, edge_index, 2, device, batch_size)
+        loss = KL_Loss + reconstruction_loss + contrastive_loss
+        loss.backward()
+        optimizer.step()
+        epoch_loss += loss.detach().item()
+        epoch_KL += KL_Loss.detach(); epoch_con += contrastive_loss.detach(); epoch_rec += reconstruction_loss.detach()
+    n = count + 1
+    return epoch_loss / n, epoch_KL / n, epoch_con / n, epoch_rec / n
+
+
+def load_graphdataset(dataset_name):
+    args.dataset = dataset_name
+    args.num_features = dict(zip(args.dataset_list, args.feature_list))[dataset_name]
+    path = "pts/%s_csr.pt" % dataset_name
+    samples_all = []
+    if os.path.exists(path):
+        shard = torch.load(path)
+        big = BatchedGraph(shard["graph_ptr"], shard["indptr"], shard["indices"], shard["x"])
+    else:
+        print("[I] %s not found: generating %d synthetic molecules of the %s shape" % (path, args.synthetic, dataset_name))
+        big = synth_batch(hash(dataset_name) % 1000, args.synthetic)
+        if args.num_features != big.ndata["x"].shape[1]:
+            big.ndata["x"] = torch.cat([big.ndata["x"], torch.rand(big.num_nodes(), args.num_features - 9)], 1)
+    gp, ip = big.graph_ptr.tolist(), big.indptr
+    for i in range(len(gp) - 1):
+        n0, n1 = gp[i], gp[i + 1]
+        e0, e1 = int(ip[n0]), int(ip[n1])
+        g = BatchedGraph([0, n1 - n0], ip[n0:n1 + 1] - e0, big.indices[e0:e1] - n0, big.ndata["x"][n0:n1])
+        samples_all.append((g, torch.zeros(1), None, None))
+    random.shuffle(samples_all)
+    return MoleculeDataset(samples_all, 'pre_training'), args.num_features
+
+
+def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feature3):
+    """Three-stage sequential pre-training, reference exp_pretraining.py:81-145."""
+    model = Mainmodel(args, feature1, hidden_dim=args.dims, num_layers=args.num_layers, num_heads=args.num_heads,
+                      k_transition=args.k_transition, encoder=args.encoder).to(device)
+    batch_size = args.batch_size
+    loaders = [DataLoader(d.data_all, batch_size=batch_size, shuffle=True, collate_fn=d.collate)
+               for d in (dataset_full1, dataset_full2, dataset_full3)]
+    features = [feature1, feature2, feature3]
+    Path(args.output_path).mkdir(parents=True, exist_ok=True)
+    if args.pretrained_mode == 1:
+        tag = f'{args.encoder}_{args.dims}_{args.num_layers}_{args.k_transition}.pt'
+        file_name_cpt = args.output_path + f'pre_training_{args.dataset_list[0]}_{tag}'
+        prev = file_name_cpt
+        for stage in range(len(args.dataset_list)):
+            name = "_".join(args.dataset_list[:stage + 1])
+            file_check = args.output_path + f'pre_training_{name}_{tag}'
+            if not os.path.exists(file_check):
+                if stage == 0:
+                    torch.save(model, file_check)
+                wrapped = Mainmodel_continue(args, features[stage], hidden_dim=args.dims, num_layers=args.num_layers,
+                                             num_heads=args.num_heads, k_transition=args.k_transition, num_classes=1,
+                                             cp_filename=prev if stage else file_check, encoder=args.encoder).to(device)
+                optimizer = torch.optim.Adam(wrapped.parameters(), lr=args.lr, weight_decay=5e-5)
+                best_model, _ = run_pretraining(wrapped, loaders[stage], optimizer, batch_size, device)
+                torch.save(best_model, file_check)
+            prev = file_check
+            print(f"Finished pre-trained model step {stage + 1}...")
+    print(f"\nFinished pretraining models on {str(args.dataset_list)} ...")
+    return 0
+
+
+def main():
+    timestr = time.strftime("%Y%m%d-%H%M%S")
+    Path("./exp_logs").mkdir(parents=True, exist_ok=True)
+    logging.basicConfig(filename="exp_logs/" + args.dataset + "-" + timestr + ".log", filemode="w", level=logging.INFO)
+    logging.info("Starting on device: %s", device)
+    logging.info("Config: %s ", args)
+    args.dataset_list = ['PCQM4Mv2', 'QM9', 'mol-PCBA']
+    args.feature_list = [9, 11, 9]
+    sets = [load_graphdataset(n) for n in args.dataset_list]
+    for i in range(args.run_times):
+        run(i, sets[0][0], sets[0][1], sets[1][0], sets[1][1], sets[2][0], sets[2][1])
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Experiments")
+    parser.add_argument("--dataset", default="pre-train", help="Dataset")
+    parser.add_argument("--model", default="Mainmodel", help="GNN Model")
+    parser.add_argument("--run_times", type=int, default=1)
+    parser.add_argument("--drop", type=float, default=0.1, help="dropout")
+    parser.add_argument("--custom_masks", default=True, action='store_true', help="custom train/val/test masks")
+    parser.add_argument("--device", default="cuda:0", help="GPU ids")
+    parser.add_argument("--pretrained_mode", type=int, default=1)
+    parser.add_argument("--domain_adapt", type=int, default=0)
+    parser.add_argument("--d_transfer", type=int, default=32)
+    parser.add_argument("--layer_relax", type=int, default=0)
+    parser.add_argument("--readout_f", default="sum")
+    parser.add_argument("--batch_size", type=int, default=128)
+    parser.add_argument("--testmode", type=int, default=0)
+    parser.add_argument("--lr", type=float, default=1e-4, help="learning rate")
+    parser.add_argument("--pt_epoches", type=int, default=100)
+    parser.add_argument("--ft_epoches", type=int, default=100)
+    parser.add_argument("--useAtt", type=int, default=1)
+    parser.add_argument("--dims", type=int, default=64, help="hidden dims")
+    parser.add_argument("--task", default="graph_classification")
+    parser.add_argument("--encoder", default="GIN")
+    parser.add_argument("--recons_type", default="adj")
+    parser.add_argument("--k_transition", type=int, default=1)
+    parser.add_argument("--num_layers", type=int, default=4)
+    parser.add_argument("--num_heads", type=int, default=4)
+    parser.add_argument("--output_path", default="outputs/", help="outputs model")
+    parser.add_argument("--pre_training", default="1", help="pre_training or not")
+    parser.add_argument("--index_excel", type=int, default="-1", help="index_excel")
+    parser.add_argument("--file_name", default="outputs_excels.xlsx", help="file_name dataset")
+    # additions of the B200 port (not in the reference)
+    parser.add_argument("--gin_layers", type=int, default=4, help="GINConv per encoder (4 in the published models.py; 5 = paper / shipped checkpoint)")
+    parser.add_argument("--synthetic", type=int, default=2048, help="synthetic molecules per dataset when pts/<name>_csr.pt is absent")
+    return parser
+
+
+if __name__ == '__main__':
+    args = build_parser().parse_args()
+    print(args)
+    device = torch.device(args.device)
+    main()

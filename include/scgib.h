@@ -104,6 +104,8 @@ typedef struct ScgibBatch {
   int32_t normalize_x;         /* 1: apply F.normalize(x) (exp_pretraining.py:312) inside; 0: x is used as given */
   const float* gate_u;         /* [N]   U[0,1) gate noise       (torch.rand,  models.py:599)    */
   const float* feat_u;         /* [N,H] U[0,1) feature noise    (rand_like,   models.py:650)    */
+  const float* t_override;     /* optional [N,DT]: already-transferred features (the batch_x argument of
+                                  extract_features, models.py:702); x / transfer_d are then not used (forward only) */
 } ScgibBatch;
 
 /* ------------------------------------------------------------------------------------------

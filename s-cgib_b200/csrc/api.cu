@@ -167,8 +167,8 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
 static int check_batch(const ScgibBatch* b) {
   if (!b) return SCGIB_E_NULL;
   if (b->B < 1 || b->N < 2 || b->Ns < b->N || b->E < 0 || b->Es < 0) return SCGIB_E_RANGE;
-  if (!b->graph_ptr || !b->indptr || !b->ego_ptr || !b->ego_nodes || !b->ego_seed || !b->sub_indptr || !b->x ||
-      !b->gate_u || !b->feat_u)
+  if (!b->graph_ptr || !b->indptr || !b->ego_ptr || !b->ego_nodes || !b->ego_seed || !b->sub_indptr ||
+      (!b->x && !b->t_override) || !b->gate_u || !b->feat_u)
     return SCGIB_E_NULL;
   if ((b->E > 0 && !b->indices) || (b->Es > 0 && !b->sub_indices)) return SCGIB_E_NULL;
   if (((uintptr_t)b->feat_u & 15u) != 0) return SCGIB_E_ALIGN;
@@ -248,7 +248,10 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
     add(params + lo.off[SCGIB_P_COMP_W1], w.comp_w1t, HID, HID);
     PROF("transpose_weights", launch_transposes(jobs, s));
   }
-  PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s));
+  if (b->t_override)
+    cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  else
+    PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s));
   // the two GIN encoders (models.py:704, 707)
   for (int e = 0; e < 2; ++e) {
     for (int l = 0; l < L; ++l) {
@@ -323,6 +326,7 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
   if (!params || !grads || !workspace || !loss_scale) return SCGIB_E_NULL;
   int rc = check_batch(b);
   if (rc) return rc;
+  if (b->t_override) return SCGIB_E_NULL;   // forward-only mode: no gradient path to transfer_d
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)params & 15u) != 0 || ((uintptr_t)grads & 15u) != 0) return SCGIB_E_ALIGN;
   const Layout lo = make_layout(d);
   const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);

@@ -56,8 +56,9 @@ def bn_buffer_names(gin_layers: int):
 class DeviceBatch:
     """Everything one step needs, resident on the device: parent CSR, ego CSR, features, noise."""
 
-    def __init__(self, g: BatchedGraph, ego: EgoBatch, x: torch.Tensor, normalize_x: bool = True):
-        self.g, self.ego, self.x, self.normalize_x = g, ego, x.contiguous(), normalize_x
+    def __init__(self, g: BatchedGraph, ego: EgoBatch, x: torch.Tensor, normalize_x: bool = True, t_override=None):
+        self.g, self.ego, self.x, self.normalize_x = g, ego, (None if x is None else x.contiguous()), normalize_x
+        self.t_override = None if t_override is None else t_override.contiguous().float()
         self.B, self.N, self.E = g.batch_size, g.num_nodes(), g.num_edges()
         self.Ns, self.Es = ego.num_nodes(), ego.num_edges()
 
@@ -68,7 +69,8 @@ class DeviceBatch:
         b.graph_ptr, b.indptr, b.indices = g.graph_ptr.data_ptr(), g.indptr.data_ptr(), g.indices.data_ptr()
         b.ego_ptr, b.ego_nodes, b.ego_seed = e.ego_ptr.data_ptr(), e.ego_nodes.data_ptr(), e.ego_seed.data_ptr()
         b.sub_indptr, b.sub_indices = e.sub_indptr.data_ptr(), e.sub_indices.data_ptr()
-        b.x, b.normalize_x = self.x.data_ptr(), int(self.normalize_x)
+        b.x, b.normalize_x = (self.x.data_ptr() if self.x is not None else None), int(self.normalize_x)
+        b.t_override = None if self.t_override is None else self.t_override.data_ptr()
         b.gate_u, b.feat_u = gate_u.data_ptr(), feat_u.data_ptr()
         return b
 

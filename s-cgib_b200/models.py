@@ -1,0 +1,315 @@
+"""Drop-in replacements for the reference's model classes on the pre-training hot path.
+
+Same class names, constructor arguments, ``forward`` signatures, return values and state-dict keys as the reference
+(models.py:38-72 MLP / GIN, :546-782 Mainmodel, :1010-1276 Mainmodel_continue); the computation runs in the sm_100a
+kernels of libscgib.so through one autograd Function per step.  There is no PyTorch fallback: on a CPU device or
+without the library the forward raises.
+
+Parameters stay ordinary ``nn.Parameter`` objects (optimisers, ``state_dict`` and ``torch.save(model)`` work), but
+their storage is re-pointed at one flat device buffer so the kernels, the gradient all-reduce and the fused Adam
+see a single tensor.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .engine import HID, DeviceBatch, PretrainEngine, bn_buffer_names, param_names
+from .graph import BatchedGraph, EgoBatch, khop_ego_batch
+
+DEFAULT_GIN_LAYERS = 4   # reference models.py:57-58: ``num_layers = 5; range(num_layers - 1)``
+
+
+class MLP(nn.Module):
+    """reference models.py:38-49."""
+
+    def __init__(self, num_features, num_classes, dims=16):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(num_features, dims), nn.ReLU(), nn.Linear(dims, num_classes))
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class GINConv(nn.Module):
+    """Parameter container with DGL GINConv's attribute names (``apply_func``, buffer ``eps`` = [0.])."""
+
+    def __init__(self, apply_func=None, aggregator_type="sum", init_eps=0, learn_eps=False):
+        super().__init__()
+        if aggregator_type != "sum" or learn_eps:
+            raise NotImplementedError("only GINConv('sum', learn_eps=False) is on the S-CGIB path (models.py:63)")
+        self.apply_func = apply_func
+        self.register_buffer("eps", torch.FloatTensor([init_eps]))
+
+
+class GIN(nn.Module):
+    """reference models.py:52-72.  ``forward(g, h)`` runs the fused CUDA layers (inference of the encoder alone:
+    no autograd; training goes through Mainmodel.forward)."""
+
+    def __init__(self, input_dim, hidden_dim=64, num_gin_layers=DEFAULT_GIN_LAYERS):
+        super().__init__()
+        if hidden_dim != HID:
+            raise NotImplementedError("libscgib is built for hidden_dim=64 (exp_pretraining.py:390)")
+        self.ginlayers = nn.ModuleList()
+        self.batch_norms = nn.ModuleList()
+        for layer in range(num_gin_layers):
+            mlp = MLP(input_dim if layer == 0 else hidden_dim, hidden_dim, hidden_dim)
+            self.ginlayers.append(GINConv(mlp, learn_eps=False))
+            self.batch_norms.append(nn.BatchNorm1d(hidden_dim))
+
+    @torch.no_grad()
+    def forward(self, g, h):
+        from . import ops
+        indptr, indices = (g.sub_indptr, g.sub_indices) if isinstance(g, EgoBatch) else (g.indptr, g.indices)
+        bn_in = None
+        for i, layer in enumerate(self.ginlayers):
+            lin1, lin2 = layer.apply_func.mlp[0], layer.apply_func.mlp[2]
+            bn = self.batch_norms[i]
+            running = torch.stack([bn.running_mean, bn.running_var]).contiguous() if self.training else None
+            y, stats, _, _ = ops.gin_layer_fwd(h, indptr, indices, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
+                                               bn_in=bn_in, running=running)
+            if self.training:
+                bn.running_mean.copy_(running[0]); bn.running_var.copy_(running[1]); bn.num_batches_tracked += 1
+                mean, rstd = stats[0], stats[1]
+            else:
+                mean, rstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+            bn_in = torch.stack([mean, rstd, bn.weight, bn.bias]).contiguous()
+            h = y
+        return torch.relu((h - bn_in[0]) * bn_in[1] * bn_in[2] + bn_in[3])
+
+
+class _Set2SetParams(nn.Module):
+    """``dgl.nn.Set2Set(hidden, 2, 1)`` as a parameter container (``s2s.lstm.*`` keys); the pre-training default
+    readout is 'sum' (exp_pretraining.py:380), so it never runs on this path."""
+
+    def __init__(self, input_dim, n_iters, n_layers):
+        super().__init__()
+        self.lstm = nn.LSTM(2 * input_dim, input_dim, n_layers)
+
+
+class _PretrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bridge, batch, gate_u, feat_u, *params):
+        eng = bridge.engine
+        losses = eng.forward(batch, gate_u, feat_u, update_running=bridge.training)
+        ctx.bridge = bridge
+        ctx.n = len(params)
+        out = losses.clone()
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_kl, g_con, g_rec):
+        eng = ctx.bridge.engine
+        scale = torch.stack([g_kl, g_con, g_rec]).tolist()        # one host read per backward
+        eng.backward(tuple(scale))
+        gv = eng.grad_views()
+        grads = [gv[name].clone() for name in ctx.bridge.slot_names]
+        return (None, None, None, None) + tuple(grads)
+
+
+class _Bridge:
+    """Keeps the module's parameters / BN buffers aliased to the engine's flat buffers."""
+
+    def __init__(self, owner, in_dim, gin_layers):
+        self.owner, self.in_dim, self.gin_layers = owner, in_dim, gin_layers
+        self.engine = None
+        self.slot_names = param_names(gin_layers)
+        self.training = True
+
+    def _resolve(self, name):
+        """Slot name -> (module holding it, attribute path).  transfer_d / MLP come from the outer module, the rest
+        from the module whose extract_features runs (the loaded ``self.model`` for Mainmodel_continue)."""
+        o = self.owner
+        inner = getattr(o, "model", None) or o
+        root = o if (name.startswith("transfer_d") or name.startswith("MLP.")) else inner
+        obj = root
+        parts = name.split(".")
+        for p in parts[:-1]:
+            obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+        return obj, parts[-1]
+
+    def sync(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("S-CGIB B200 path: the model must be on a CUDA device (no CPU fallback)")
+        if self.engine is None or self.engine.device != device:
+            self.engine = PretrainEngine(self.in_dim, gin_layers=self.gin_layers, device=device)
+        views = self.engine.views()
+        params = []
+        for name in self.slot_names:
+            mod, attr = self._resolve(name)
+            p = getattr(mod, attr)
+            v = views[name]
+            if p.data_ptr() != v.data_ptr():
+                v.copy_(p.data.to(device).reshape(v.shape))
+                p.data = v
+            params.append(p)
+        inner = getattr(self.owner, "model", None) or self.owner
+        for i, base in enumerate(bn_buffer_names(self.gin_layers)):
+            obj = inner
+            for p in base.split("."):
+                obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+            for j, attr in enumerate(("running_mean", "running_var")):
+                buf = getattr(obj, attr)
+                v = self.engine.bn_running[i, j]
+                if buf.data_ptr() != v.data_ptr():
+                    v.copy_(buf.data.to(device))
+                    buf.data = v
+        self._bn_modules = inner
+        return params
+
+
+def _check_args(args, encoder):
+    if encoder != "GIN":
+        print("scgib_b200: only --encoder GIN is implemented on the B200 path (reference models.py:573-587)")
+        raise SystemExit()
+    if getattr(args, "readout_f", "sum") != "sum" or getattr(args, "recons_type", "adj") != "adj" or \
+            not getattr(args, "useAtt", 1):
+        raise NotImplementedError("B200 path covers the reference defaults: --readout_f sum --recons_type adj --useAtt 1")
+
+
+class _HotPathMixin:
+    """forward / extract_features shared by Mainmodel and Mainmodel_continue."""
+
+    def _device_batch(self, batch_g, batch_x, flatten_batch_subgraphs, device, t_override=None):
+        g = batch_g if batch_g.device == torch.device(device) else batch_g.to(device)
+        ego = flatten_batch_subgraphs
+        if not isinstance(ego, EgoBatch):
+            raise TypeError("flatten_batch_subgraphs must be an scgib_b200.graph.EgoBatch (khop_ego_batch)")
+        if ego.device != g.device:
+            ego = ego.to(g.device)
+        x = None if batch_x is None else batch_x.to(g.device).float()
+        # exp_pretraining.py:312 already applied F.normalize to batch_x: use it as given
+        return DeviceBatch(g, ego, x, normalize_x=False, t_override=t_override)
+
+    def _noise(self, N, device):
+        # reference: gate noise from the CPU generator (models.py:599), feature noise on the device (models.py:650)
+        return torch.rand(N).to(device, non_blocking=True), torch.rand(N, HID, device=device)
+
+    def forward(self, batch_g, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, current_epoch, edge_index,
+                k_transition, device, batch_size=16):
+        """reference models.py:662-700 / 1158-1195 -> (None, KL_Loss, contrastive_loss, reconstruction_loss)."""
+        self.batch_size = batch_size
+        self.device = device
+        if batch_size < batch_g.batch_size:
+            raise NotImplementedError("batched_semi_loss with batch_size < number of graphs (never the case in the CLI)")
+        params = self._bridge.sync(device)
+        self._bridge.training = self.training
+        b = self._device_batch(batch_g, batch_x, flatten_batch_subgraphs, device)
+        gate_u, feat_u = self._noise(b.N, b.g.device)
+        kl, con, rec = _PretrainFn.apply(self._bridge, b, gate_u, feat_u, *params)
+        if self.training:
+            self._bump_batches_tracked(b.B)
+        return None, kl, con, rec
+
+    def _bump_batches_tracked(self, B):
+        inner = self._bridge._bn_modules
+        for enc in (inner.Encoder1, inner.Encoder2):
+            for bn in enc.batch_norms:
+                bn.num_batches_tracked += 1
+        inner.compressor[1].num_batches_tracked += B     # one BatchNorm call per graph (models.py:642)
+
+    @torch.no_grad()
+    def extract_features(self, nodes_list, batch_g, batch_x, flatten_batch_subgraphs, x_subs, device):
+        """reference models.py:702-750 (forward only here): ``batch_x`` is already transfer_d'ed [N, d_transfer].
+        Returns (interaction_map [N,2d], KL_tensor, noisy_node_feature [N,d], graph_features_readout [B,d])."""
+        br = getattr(self, "_bridge", None) or _Bridge(self, self.in_dim_raw, self.gin_layers)
+        self._bridge = br
+        br.sync(device)
+        b = self._device_batch(batch_g, None, flatten_batch_subgraphs, device, t_override=batch_x.to(device))
+        gate_u, feat_u = self._noise(b.N, b.g.device)
+        losses, emb = br.engine.forward(b, gate_u, feat_u, want=True, update_running=self.training)
+        self.graph_features = None
+        return emb["interaction_map"], losses[0:1].clone(), emb["noisy"], emb["graph_readout"]
+
+
+class Mainmodel(_HotPathMixin, nn.Module):
+    """reference models.py:546-782.  Construction order follows the reference so a seeded default init gives the same
+    weights; the modules the default configuration never uses (fc1, embedding_h, reduce_d, s2s, reconstructX) are kept
+    for state-dict compatibility."""
+
+    def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, encoder):
+        super().__init__()
+        _check_args(args, encoder)
+        self.tau = 1.0
+        self.recons_type = args.recons_type
+        self.useAtt = args.useAtt
+        self.readout = args.readout_f
+        self.hidden_dim = hidden_dim
+        self.k_transition = k_transition
+        self.gin_layers = int(getattr(args, "gin_layers", DEFAULT_GIN_LAYERS))
+        self.in_dim_raw = in_dim
+        self.fc1 = nn.Linear(hidden_dim, 1)
+        self.in_dim = args.d_transfer
+        self.transfer_d = nn.Linear(in_dim, self.in_dim, bias=False)
+        self.embedding_h = nn.Linear(self.in_dim, hidden_dim, bias=False)
+        self.attn_layer = nn.Linear(self.hidden_dim * 2, 1)
+        self.reduce_d = nn.Linear(2 * self.hidden_dim, self.hidden_dim)
+        self.device = args.device
+        self.s2s = _Set2SetParams(hidden_dim, 2, 1)
+        self.reconstructX = nn.Sequential(nn.Linear(self.hidden_dim, self.in_dim))
+        self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                 nn.Linear(self.hidden_dim, self.hidden_dim))
+        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.compressor = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.BatchNorm1d(self.hidden_dim),
+                                        nn.ReLU(), nn.Linear(self.hidden_dim, 1))
+        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+
+    def __getstate__(self):     # torch.save(model) (exp_pretraining.py:107): drop the engine, keep plain tensors
+        st = self.__dict__.copy()
+        st["_bridge"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        for p in self.parameters():
+            p.data = p.data.clone()
+        self._bridge = _Bridge(self, self.in_dim_raw, self.gin_layers)
+
+
+class Mainmodel_continue(_HotPathMixin, nn.Module):
+    """reference models.py:1010-1276: wraps a pickled model (``torch.load(cp_filename)``), owns a new transfer_d and
+    MLP head and trains them together with the LOADED module's encoders/compressor/attention (models.py:1167)."""
+
+    def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, num_classes, cp_filename, encoder):
+        super().__init__()
+        _check_args(args, encoder)
+        self.tau = 1.0
+        self.readout = args.readout_f
+        self.gin_layers = int(getattr(args, "gin_layers", DEFAULT_GIN_LAYERS))
+        self.in_dim_raw = in_dim
+        self.s2s = _Set2SetParams(hidden_dim, 2, 1)
+        self.s2s_rev = _Set2SetParams(in_dim, 2, 1)
+        self.in_dim = args.d_transfer
+        self.transfer_d = nn.Linear(in_dim, self.in_dim, bias=False)
+        self.recons_type = args.recons_type
+        self.batch_size = args.batch_size
+        self.useAtt = args.useAtt
+        self.embedding_h = nn.Linear(self.in_dim, hidden_dim, bias=False)
+        self.hidden_dim = hidden_dim
+        self.k_transition = k_transition
+        self.reduce_d = nn.Linear(2 * self.hidden_dim, self.hidden_dim)
+        self.attn_layer = nn.Linear(2 * self.hidden_dim, 1)
+        self.num_nodes = -1
+        self.device = args.device
+        self.r_transfer_d = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                          nn.Linear(self.hidden_dim, in_dim * 2))
+        out_dim = 1 if getattr(args, "task", "graph_classification") == "graph_regression" else num_classes
+        self.predict = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                     nn.Linear(self.hidden_dim, out_dim))
+        self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                 nn.Linear(self.hidden_dim, self.hidden_dim))
+        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.model = torch.load(cp_filename, map_location=args.device, weights_only=False)
+        for p in self.model.parameters():
+            p.requires_grad = True
+        self.compressor = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.BatchNorm1d(self.hidden_dim),
+                                        nn.ReLU(), nn.Linear(self.hidden_dim, 1))
+        self.reconstructX = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                          nn.Linear(self.hidden_dim, in_dim))
+        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+
+    __getstate__ = Mainmodel.__getstate__
+    __setstate__ = Mainmodel.__setstate__

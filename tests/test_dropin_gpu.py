@@ -1,0 +1,102 @@
+"""Drop-in boundary on the GPU: the reference's class names / signatures (models.Mainmodel, Mainmodel_continue,
+exp_pretraining.train_epoch_pre_training) run the CUDA path and agree with the oracle."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.graph_ref import ego_batch_ref, synth_batch
+from oracle.scgib_oracle import OracleMainmodel, normalize_rows, tgraph_from_ego, tgraph_from_ref
+from tests.helpers import product_graph, rel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _args(**kw):
+    a = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device=DEV, batch_size=128,
+                              task="graph_classification", k_transition=1)
+    a.__dict__.update(kw)
+    return a
+
+
+def test_mainmodel_forward_backward_matches_oracle(monkeypatch):
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    g = synth_batch(51, 48)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(51)
+    ref = OracleMainmodel(9)
+    torch.manual_seed(51)
+    m = models.Mainmodel(_args(), 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=1, encoder="GIN")
+    # same construction order + seed => identical default initialisation as the reference-ordered oracle
+    for (n1, p1), (n2, p2) in zip(ref.state_dict().items(), m.state_dict().items()):
+        assert n1 == n2 and torch.equal(p1, p2), (n1, n2)
+    m = m.to(DEV)
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, 1)
+    x = F.normalize(pg.ndata["x"].float())
+    gate_u, feat_u = torch.rand(g.num_nodes), torch.rand(g.num_nodes, 64)
+    monkeypatch.setattr(m, "_noise", lambda N, dev: (gate_u.to(dev), feat_u.to(dev)))
+    m.train()
+    _, kl, con, rec = m.forward(pg, x, ego, None, None, 1, None, 2, DEV, 48)
+    (kl + rec + con).backward()
+    xr = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    out = ref.forward_faithful(tgraph_from_ref(g), xr, tgraph_from_ego(e), xr[en], gate_u, feat_u)
+    (out["KL"] + out["recon"] + out["contrastive"]).backward()
+    for name, got in (("KL", kl), ("contrastive", con), ("recon", rec)):
+        assert abs(float(got) - float(out[name])) <= 1e-5 * abs(float(out[name])), name
+    refg = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(refg) <= set(got)
+    errs = sorted(rel(got[n], refg[n]) for n in refg if float(refg[n].abs().max()) > 1e-3)
+    assert errs[len(errs) // 2] <= 5e-5 and errs[-1] <= 5e-3
+    # BN running statistics are live module buffers
+    assert rel(m.Encoder1.batch_norms[0].running_mean, ref.Encoder1.batch_norms[0].running_mean) <= 1e-5
+    assert int(m.compressor[1].num_batches_tracked) == 48
+    # an ordinary optimiser step moves the aliased flat parameters
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    before = m._bridge.engine.params.clone()
+    opt.step()
+    assert not torch.equal(before, m._bridge.engine.params)
+
+
+def test_exp_pretraining_cli_stages(tmp_path, monkeypatch):
+    """One epoch of each of the three stages through the reference's CLI surface; checkpoints use the reference's
+    naming scheme and reload through Mainmodel_continue."""
+    import exp_pretraining as ep
+    monkeypatch.chdir(tmp_path)
+    ep.args = ep.build_parser().parse_args(["--device", DEV, "--pt_epoches", "2", "--batch_size", "32", "--synthetic", "96",
+                                            "--output_path", str(tmp_path) + "/outputs/"])
+    ep.device = torch.device(DEV)
+    ep.main()
+    names = sorted(os.listdir(tmp_path / "outputs"))
+    assert names == ["pre_training_PCQM4Mv2_GIN_64_4_1.pt", "pre_training_PCQM4Mv2_QM9_GIN_64_4_1.pt",
+                     "pre_training_PCQM4Mv2_QM9_mol-PCBA_GIN_64_4_1.pt"]
+    last = torch.load(tmp_path / "outputs" / names[-1], weights_only=False)
+    assert type(last).__name__ == "Mainmodel_continue" and type(last.model).__name__ == "Mainmodel_continue"
+    assert all(torch.isfinite(p).all() for p in last.parameters())
+
+
+def test_unsupported_encoder_exits_like_reference():
+    import models
+    with pytest.raises(SystemExit):
+        models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GCN")
+
+
+def test_extract_features_api():
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    g = synth_batch(52, 16)
+    torch.manual_seed(52)
+    m = models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GIN").to(DEV)
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, 1)
+    t = m.transfer_d(F.normalize(pg.ndata["x"].float()))
+    imap, kl_t, noisy, readout = m.extract_features(pg.batch_num_nodes(), pg, t, ego, None, DEV)
+    assert imap.shape == (g.num_nodes, 128) and noisy.shape == (g.num_nodes, 64) and readout.shape == (16, 64)
+    assert torch.equal(imap[:, :64], noisy) and torch.isfinite(kl_t).all()
