@@ -179,6 +179,46 @@ class PretrainEngine:
         ego = khop_ego_batch(g, k, self.ego_ws)
         return DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
 
+    def prefetch_batch(self, g: BatchedGraph, k: int = 1, normalize_x: bool = True, slots: int = 3):
+        """Data-loader style pipelining: H2D (if ``g`` is a pinned host batch) and k-hop ego-net extraction of the
+        NEXT batch on a side stream while the current step's kernels run.  The one host read of (Ns, Es) waits for the
+        side stream only, so the launch queue of the training stream never drains.  Buffers come from a small ring of
+        preallocated slots (no allocator traffic in steady state); a slot is reused only after the training stream has
+        finished the step that read it.  Pair with ``wait_batch``."""
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.device)
+            self._slots = [dict(bufs={}, done=None, dev={}) for _ in range(slots)]
+            self._slot_i = 0
+        slot = self._slots[self._slot_i % len(self._slots)]
+        self._slot_i += 1
+        with torch.cuda.stream(self._side):
+            if slot["done"] is not None:
+                self._side.wait_event(slot["done"])
+            if g.device != self.device:                      # pinned host batch: H2D into the slot's device buffers
+                def put(name, t):
+                    d = slot["dev"].get(name)
+                    if d is None or d.numel() < t.numel() or d.dtype != t.dtype:
+                        d = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, device=self.device)
+                        slot["dev"][name] = d
+                    v = d[:t.numel()].view(t.shape)
+                    v.copy_(t, non_blocking=True)
+                    return v
+                gd = BatchedGraph.__new__(BatchedGraph)
+                gd.graph_ptr, gd.indptr, gd.indices = put("graph_ptr", g.graph_ptr), put("indptr", g.indptr), put("indices", g.indices)
+                gd.ndata = {"x": put("x", g.ndata["x"])}
+                g = gd
+            ego = khop_ego_batch(g, k, self.ego_ws, out=slot["bufs"])
+            b = DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+            b._slot = slot
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return b, ev
+
+    def wait_batch(self, handle) -> DeviceBatch:
+        b, ev = handle
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return b
+
     def draw_noise(self, N):
         """U[0,1) gate / feature noise (reference: CPU torch.rand per graph, device rand_like: models.py:599, 650)."""
         return (torch.rand(N, device=self.device, generator=self._noise_gen),
@@ -258,4 +298,8 @@ class PretrainEngine:
             import torch.distributed as dist
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
         self.adam_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / world_size)
+        slot = getattr(b, "_slot", None)
+        if slot is not None:                      # the slot's buffers may be overwritten once this step has run
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(torch.cuda.current_stream(self.device))
         return losses

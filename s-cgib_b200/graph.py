@@ -178,9 +178,11 @@ class EgoWorkspace:
         self.host = None
 
 
-def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, stream=None) -> EgoBatch:
+def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, stream=None, out=None) -> EgoBatch:
     """k-hop ego-net of every node of ``g`` on the GPU (bit-exact with ``dgl.khop_in_subgraph`` node lists).
-    One host synchronisation (to read Ns / Es between the count and the fill kernel)."""
+    One host synchronisation (to read Ns / Es between the count and the fill kernel).
+    ``out``: optional dict of preallocated int32 device buffers {ego_ptr, ego_eptr, ego_nodes, ego_seed, sub_indptr,
+    sub_indices, status}; buffers that are too small are replaced in the dict."""
     lib = _lib.load()
     if g.device.type != "cuda":
         raise RuntimeError("khop_ego_batch needs the graph on a CUDA device (no CPU fallback)")
@@ -190,26 +192,32 @@ def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, s
     ws = ws or EgoWorkspace()
     need = lib.scgib_ego_workspace_bytes(N)
     if ws.ws is None or ws.ws.numel() < need or ws.ws.device != dev:
-        ws.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws.ws = torch.empty(int(need * 1.5), dtype=torch.uint8, device=dev)
+    if ws.host is None:
         ws.host = torch.empty(3, dtype=torch.int32).pin_memory()
-    ego_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    ego_eptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    status = torch.empty(1, dtype=torch.int32, device=dev)
+    out = {} if out is None else out
+
+    def buf(name, n):
+        t = out.get(name)
+        if t is None or t.numel() < n or t.device != dev:
+            t = torch.empty(int(n * 1.25) + 16, dtype=torch.int32, device=dev)
+            out[name] = t
+        return t
+
+    ego_ptr, ego_eptr, status = buf("ego_ptr", N + 1), buf("ego_eptr", N + 1), buf("status", 1)
     _lib.check(lib.scgib_ego_count(_lib.ptr(g.indptr), _lib.ptr(g.indices), N, int(k), _lib.ptr(ego_ptr),
                                    _lib.ptr(ego_eptr), _lib.ptr(status), _lib.ptr(ws.ws), ws.ws.numel(), st),
                "ego_count")
-    ws.host[0:1].copy_(ego_ptr[N:], non_blocking=True)
-    ws.host[1:2].copy_(ego_eptr[N:], non_blocking=True)
-    ws.host[2:3].copy_(status, non_blocking=True)
+    ws.host[0:1].copy_(ego_ptr[N:N + 1], non_blocking=True)
+    ws.host[1:2].copy_(ego_eptr[N:N + 1], non_blocking=True)
+    ws.host[2:3].copy_(status[0:1], non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     Ns, Es, bad = (int(v) for v in ws.host)
     if bad:
         raise RuntimeError("an ego-net exceeds SCGIB_EGO_CAP=%d nodes" % _lib.EGO_CAP)
-    ego_nodes = torch.empty(Ns, dtype=torch.int32, device=dev)
-    ego_seed = torch.empty(Ns, dtype=torch.int32, device=dev)
-    sub_indptr = torch.empty(Ns + 1, dtype=torch.int32, device=dev)
-    sub_indices = torch.empty(max(Es, 1), dtype=torch.int32, device=dev)[:Es]
+    ego_nodes, ego_seed = buf("ego_nodes", Ns), buf("ego_seed", Ns)
+    sub_indptr, sub_indices = buf("sub_indptr", Ns + 1), buf("sub_indices", max(Es, 1))
     _lib.check(lib.scgib_ego_fill(_lib.ptr(g.indptr), _lib.ptr(g.indices), N, int(k), _lib.ptr(ego_ptr),
                                   _lib.ptr(ego_eptr), _lib.ptr(ego_nodes), _lib.ptr(ego_seed), _lib.ptr(sub_indptr),
                                   _lib.ptr(sub_indices), st), "ego_fill")
-    return EgoBatch(g, k, ego_ptr, ego_nodes, ego_seed, sub_indptr, sub_indices)
+    return EgoBatch(g, k, ego_ptr[:N + 1], ego_nodes[:Ns], ego_seed[:Ns], sub_indptr[:Ns + 1], sub_indices[:Es])
