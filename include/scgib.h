@@ -195,6 +195,14 @@ SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int
 SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,
                                                   int32_t Es, const char* name);
 
+/* GIN forward implementation: 0 = FP32 FFMA register tiles (default), 1 = tcgen05 3xTF32 tensor-core kernel
+ * (also selectable with the environment variable SCGIB_TC=1). */
+SCGIB_API void scgib_set_tensor_cores(int on);
+
+/* Probe of the tcgen05 tile-GEMM primitives (tests only): one 3xTF32 GEMM of fp32 tiles A [M,64], B [64 or M,64] in
+ * operand-major mode 0/1/2 (umma_test.cu); out[128][64] = dump of all TMEM lanes. */
+SCGIB_API int scgib_debug_umma(const float* A, const float* B, float* out, int32_t M, int32_t mode, void* stream);
+
 /* Per-launch timing with CUDA events recorded on the launching stream (used by bench.py for the roofline
  * numbers).  enable(1) clears the record; every later kernel launch of this library is bracketed by two events;
  * after synchronising the stream, profile_get(i) returns the static kernel-family name and the elapsed ms. */

@@ -18,6 +18,12 @@ int num_sms() {
   return n;
 }
 
+static int g_use_tc = -1;
+bool use_tensor_cores() {
+  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] == '1') ? 1 : 0; }   // opt-in: DESIGN.md section 3
+  return g_use_tc == 1;
+}
+
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers).
@@ -110,7 +116,7 @@ struct Ws {
 
 static size_t small_part_floats(int N, int Ns) {
   const int Vmax = N > Ns ? N : Ns;
-  size_t a = (size_t)((Vmax + 127) / 128) * 2 * HID;                 // gin fwd tile partials
+  size_t a = (size_t)((Vmax + 63) / 64) * 2 * HID;                   // gin fwd tile partials (64-row tiles)
   size_t b = (size_t)gin_bwd_pre_grid(Vmax) * 2 * HID;               // dgamma/dbeta partials
   size_t c = (size_t)2 * num_sms() * 5 * HID;                        // gate partials
   size_t d = (size_t)input_proj_bwd_grid(N, Ns) * DTR * 32;          // transfer_d partials
@@ -264,12 +270,16 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
       a.V = e == 0 ? b->N : b->Ns;
       a.W1t = w.enc_w1t[e][l]; a.b1 = params + lo.enc(e, l, L, SCGIB_ENC_B1);
       a.W2t = w.enc_w2t[e][l]; a.b2 = params + lo.enc(e, l, L, SCGIB_ENC_B2);
+      a.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); a.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
       a.gamma = params + lo.enc(e, l, L, SCGIB_ENC_GAMMA); a.beta = params + lo.enc(e, l, L, SCGIB_ENC_BETA);
       a.a_out = w.a[e][l]; a.r_out = w.r[e][l]; a.y_out = w.y[e][l];
       a.part = w.small_part; a.counter = w.counters + 0;
       a.bn_out = w.bn[e][l];
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
-      PROF(e == 0 ? "gin_fwd.enc1" : "gin_fwd.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
+      if (use_tensor_cores())
+        PROF(e == 0 ? "gin_fwd_tc.enc1" : "gin_fwd_tc.enc2", launch_gin_fwd_tc(a, l == 0 ? DTR : HID, s));
+      else
+        PROF(e == 0 ? "gin_fwd.enc1" : "gin_fwd.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
     }
   }
   {
@@ -440,7 +450,7 @@ extern "C" SCGIB_API int scgib_input_proj_fwd_f32(const float* x, const float* W
 }
 
 extern "C" SCGIB_API size_t scgib_gin_workspace_bytes(int32_t V) {
-  return al((size_t)((V + 127) / 128) * 2 * HID * sizeof(float)) + al(HID * HID * sizeof(float)) * 2 + 256;
+  return al((size_t)((V + 63) / 64) * 2 * HID * sizeof(float)) + al(HID * HID * sizeof(float)) * 2 + 256;
 }
 
 extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, const int32_t* row_map, const float* bn_in,
@@ -467,10 +477,10 @@ extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, c
   launch_transposes(jobs, s);
   GinFwdArgs a;
   a.in = in; a.row_map = row_map; a.bn_in = bn_in; a.indptr = indptr; a.indices = indices; a.V = V;
-  a.W1t = w1t; a.b1 = b1; a.W2t = w2t; a.b2 = b2;
+  a.W1t = w1t; a.b1 = b1; a.W2t = w2t; a.b2 = b2; a.W1 = W1; a.W2 = W2;
   a.gamma = nullptr; a.beta = nullptr;
   a.a_out = a_out; a.r_out = r_out; a.y_out = y_out; a.part = part; a.counter = counter; a.bn_out = bn_out; a.running = running;
-  launch_gin_fwd(a, kin, s);
+  if (use_tensor_cores()) launch_gin_fwd_tc(a, kin, s); else launch_gin_fwd(a, kin, s);
   return (int)cudaGetLastError();
 }
 
@@ -515,3 +525,6 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
   *name = g_prof.name[i];
   return (int)cudaEventElapsedTime(ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]);
 }
+
+// Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
+extern "C" SCGIB_API void scgib_set_tensor_cores(int on) { g_use_tc = on ? 1 : 0; }

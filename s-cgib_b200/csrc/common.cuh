@@ -35,6 +35,48 @@ struct Bn4 {
   __device__ __forceinline__ float4 act(float4 y) const { return relu4(pre(y)); }
 };
 
+// GIN aggregation a_v = f(in[map(v)]) + sum_{u in N(v)} f(in[map(u)]) for NR rows at once per thread (lane `gl` owns
+// 4 channels).  The NR dependent chains (indptr -> indices -> [row_map] -> features) are interleaved so that NR times
+// more loads are in flight: the gather is latency-bound, not bandwidth-bound (degree ~2, 256-byte rows).
+template <int KIN, int NR>
+__device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, const int32_t* __restrict__ row_map,
+                                                 const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                 int V, const int (&v)[NR], int gl, const Bn4* bn, float4 (&acc)[NR]) {
+  int e0[NR], e1[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    const bool ok = v[j] < V;
+    e0[j] = ok ? __ldg(indptr + v[j]) : 0;
+    e1[j] = ok ? __ldg(indptr + v[j] + 1) : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    acc[j] = make4(0.f);
+    if (v[j] < V) {
+      const int sv = row_map ? __ldg(row_map + v[j]) : v[j];
+      const float4 h = ld4(in + (size_t)sv * KIN + gl * 4);
+      acc[j] = bn ? bn->act(h) : h;
+    }
+  }
+  int maxd = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) maxd = max(maxd, e1[j] - e0[j]);
+  for (int s = 0; s < maxd; ++s) {
+    int u[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) u[j] = (e0[j] + s < e1[j]) ? __ldg(indices + e0[j] + s) : -1;
+    if (row_map) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) if (u[j] >= 0) u[j] = __ldg(row_map + u[j]);
+    }
+    float4 h[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) h[j] = (u[j] >= 0) ? ld4(in + (size_t)u[j] * KIN + gl * 4) : make4(0.f);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) if (u[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h[j]) : h[j]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -100,24 +100,19 @@ gin_fwd_kernel(GinFwdArgs p) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * GT;
     __syncthreads();  // previous tile's readers of sm.tile are done (also covers the weight loads)
-    // ---- gather-aggregate: a_v = f(in[map(v)]) + sum_u f(in[map(u)])
-    for (int r = gr; r < GT; r += RPP) {
-      const int v = base + r;
-      float4 acc = make4(0.f);
-      if (v < p.V) {
-        const int sv = p.row_map ? __ldg(p.row_map + v) : v;
-        float4 h = ld4(p.in + (size_t)sv * KIN + gl * 4);
-        acc = has_bn ? bn.act(h) : h;
-        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
-        for (int e = e0; e < e1; ++e) {
-          const int u = __ldg(p.indices + e);
-          const int su = p.row_map ? __ldg(p.row_map + u) : u;
-          h = ld4(p.in + (size_t)su * KIN + gl * 4);
-          acc = add4(acc, has_bn ? bn.act(h) : h);
-        }
-        if (p.a_out) st4(p.a_out + (size_t)v * KIN + gl * 4, acc);
+    // ---- gather-aggregate: a_v = f(in[map(v)]) + sum_u f(in[map(u)])   (all row passes of the thread interleaved)
+    {
+      constexpr int NR = GT / RPP;
+      int vv[NR];
+      float4 agg[NR];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) vv[j] = base + gr + j * RPP;
+      gather_aggregate<KIN, NR>(p.in, p.row_map, p.indptr, p.indices, p.V, vv, gl, has_bn ? &bn : nullptr, agg);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        if (p.a_out && vv[j] < p.V) st4(p.a_out + (size_t)vv[j] * KIN + gl * 4, agg[j]);
+        st4(sm.tile + (gr + j * RPP) * LDA + gl * 4, agg[j]);
       }
-      st4(sm.tile + r * LDA + gl * 4, acc);
     }
     __syncthreads();
     // ---- u = W1 a + b1 ; r = relu(u)
@@ -251,23 +246,35 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
   Bn4 bn;
   bn.load(p.bn, l * 4);
   float4 db = make4(0.f), dg = make4(0.f);
-  for (int v = blockIdx.x * 16 + hw; v < p.V; v += gridDim.x * 16) {
-    float4 g;
+  constexpr int NR = 4;
+  for (int v0 = blockIdx.x * 16 + hw; v0 < p.V; v0 += gridDim.x * 16 * NR) {
+    int vv[NR];
+    float4 g[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) vv[j] = v0 + j * gridDim.x * 16;
     if (p.indptr) {
-      g = ld4(p.src + (size_t)v * HID + l * 4);
-      const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
-      for (int e = e0; e < e1; ++e) g = add4(g, ld4(p.src + (size_t)__ldg(p.indices + e) * HID + l * 4));
+      gather_aggregate<HID, NR>(p.src, nullptr, p.indptr, p.indices, p.V, vv, l, nullptr, g);
     } else {
-      const int sv = p.map ? __ldg(p.map + v) : v;
-      g = ld4(p.src + (size_t)sv * HID + l * 4);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        g[j] = make4(0.f);
+        if (vv[j] < p.V) g[j] = ld4(p.src + (size_t)(p.map ? __ldg(p.map + vv[j]) : vv[j]) * HID + l * 4);
+      }
     }
-    const float4 y = ld4(p.y + (size_t)v * HID + l * 4);
-    const float4 xh = bn.xhat(y);
-    const float4 o = bn.pre(y);
-    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
-    st4(p.g_o + (size_t)v * HID + l * 4, g);
-    db = add4(db, g);
-    dg.x = fmaf(g.x, xh.x, dg.x); dg.y = fmaf(g.y, xh.y, dg.y); dg.z = fmaf(g.z, xh.z, dg.z); dg.w = fmaf(g.w, xh.w, dg.w);
+    float4 y[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if (vv[j] >= p.V) continue;
+      const float4 xh = bn.xhat(y[j]);
+      const float4 o = bn.pre(y[j]);
+      float4 gg = g[j];
+      gg.x = o.x > 0.f ? gg.x : 0.f; gg.y = o.y > 0.f ? gg.y : 0.f; gg.z = o.z > 0.f ? gg.z : 0.f; gg.w = o.w > 0.f ? gg.w : 0.f;
+      st4(p.g_o + (size_t)vv[j] * HID + l * 4, gg);
+      db = add4(db, gg);
+      dg.x = fmaf(gg.x, xh.x, dg.x); dg.y = fmaf(gg.y, xh.y, dg.y); dg.z = fmaf(gg.z, xh.z, dg.z); dg.w = fmaf(gg.w, xh.w, dg.w);
+    }
   }
   st4(s_red + hw * 2 * HID + l * 4, db);
   st4(s_red + hw * 2 * HID + HID + l * 4, dg);

@@ -20,7 +20,8 @@ struct GinFwdArgs {
   const int32_t* indptr;
   const int32_t* indices;
   int V;
-  const float *W1t, *b1, *W2t, *b2;   // W1t [KIN][HID], W2t [HID][HID]  (k-major copies)
+  const float *W1t, *b1, *W2t, *b2;   // W1t [KIN][HID], W2t [HID][HID]  (k-major copies, FFMA kernel)
+  const float *W1, *W2;               // natural [out][in] (tensor-core kernel: K-major B operand)
   const float *gamma, *beta;          // this layer's BN affine (copied into bn_out for the consumers)
   float *a_out, *r_out, *y_out;       // a/r optional (saved for backward)
   float* part;                        // [n_tiles][2][HID]
@@ -29,7 +30,10 @@ struct GinFwdArgs {
   float* running;                     // optional {running_mean, running_var}[HID]
 };
 int gin_fwd_grid(int V);
-void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);
+void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
+int gin_fwd_tc_tiles(int V);
+void launch_gin_fwd_tc(const GinFwdArgs& a, int kin, cudaStream_t s);     // tcgen05 3xTF32 (gin_tc.cu)
+bool use_tensor_cores();                                                  // SCGIB_TC=1 selects the tcgen05 forward
 
 struct GinBwdPreArgs {
   const float* src;         // CSR mode: Ga [V][HID]; direct mode: rows gathered through map

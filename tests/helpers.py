@@ -94,6 +94,8 @@ def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_g
             got, ref, truth = got[:, 64:], ref[:, 64:], truth[:, 64:]
         one("grad " + n, got, ref, truth, GRAD_TOL_MAX)
     gerr = sorted(r[1] for r in report if r[0].startswith("grad "))
-    med = gerr[len(gerr) // 2]
-    assert med <= GRAD_TOL_MEDIAN, ("median gradient error", med)
+    rerr = sorted(r[2] for r in report if r[0].startswith("grad "))
+    med, med_ref = gerr[len(gerr) // 2], rerr[len(rerr) // 2]
+    # at full size (~3e7 ReLU units) mask flips are everywhere: the yardstick is the fp32 reference run's own median
+    assert med <= max(GRAD_TOL_MEDIAN, 2.0 * med_ref), ("median gradient error", med, "fp32 reference run", med_ref)
     return report
