@@ -188,6 +188,28 @@ __device__ __forceinline__ void gemm_tn(const float* __restrict__ Xs, int ldx, c
   }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, every copy of a tile in flight at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// [TILE_M][COLS] row tile of a global [V][COLS] matrix -> smem (leading dim ld), rows >= V zero-filled
+template <int TILE_M, int COLS>
+__device__ __forceinline__ void cp_async_row_tile(float* __restrict__ dst, int ld, const float* __restrict__ src,
+                                                  int row_base, int V) {
+  constexpr int C4 = COLS / 4;
+  for (int i = threadIdx.x; i < TILE_M * C4; i += kThreads) {
+    const int r = i / C4, c = (i % C4) * 4;
+    const int v = row_base + r;
+    const bool ok = v < V;
+    cp_async16(dst + r * ld + c, src + (size_t)(ok ? v : 0) * COLS + c, ok);
+  }
+}
+
 // cooperative copy of a dense [rows][cols] fp32 matrix (global, contiguous) into smem with leading dim ld
 template <int COLS>
 __device__ __forceinline__ void load_matrix(float* __restrict__ dst, int ld, const float* __restrict__ src, int rows) {

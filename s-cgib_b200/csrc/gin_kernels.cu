@@ -357,26 +357,32 @@ gin_bwd_main_kernel(GinBwdMainArgs p) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * GT;
     __syncthreads();
-    // ---- stage g_y, r, a
-    for (int i = threadIdx.x; i < GT * (HID / 4); i += kThreads) {
-      const int r = i / (HID / 4), c = (i % (HID / 4)) * 4;
-      const int v = base + r;
-      float4 gy = make4(0.f), rr = make4(0.f);
-      if (v < p.V) {
-        const float4 go = ld4(p.g_o + (size_t)v * HID + c);
-        const float4 y = ld4(p.y + (size_t)v * HID + c);
-        const float4 mean = ldg4(p.bn + c), rstd = ldg4(p.bn + HID + c), gamma = ldg4(p.bn + 2 * HID + c);
-        const float4 c1 = ldg4(p.cvec + c), c2 = ldg4(p.cvec + HID + c);
-        gy.x = rstd.x * (gamma.x * go.x - c1.x - (y.x - mean.x) * rstd.x * c2.x);
-        gy.y = rstd.y * (gamma.y * go.y - c1.y - (y.y - mean.y) * rstd.y * c2.y);
-        gy.z = rstd.z * (gamma.z * go.z - c1.z - (y.z - mean.z) * rstd.z * c2.z);
-        gy.w = rstd.w * (gamma.w * go.w - c1.w - (y.w - mean.w) * rstd.w * c2.w);
-        rr = ld4(p.r + (size_t)v * HID + c);
+    // ---- stage g_o, y, r, a with cp.async (the whole 128 KB tile in flight at once), then g_y in place:
+    //      g_y = rstd * (gamma*g_o - c1 - yhat*c2)
+    cp_async_row_tile<GT, HID>(sm.gy, GLD, p.g_o, base, p.V);
+    cp_async_row_tile<GT, HID>(sm.gu, GLD, p.y, base, p.V);
+    cp_async_row_tile<GT, HID>(sm.r, GLD, p.r, base, p.V);
+    cp_async_row_tile<GT, KIN>(sm.a, LDA, p.a, base, p.V);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    {
+      const int c = (threadIdx.x % (HID / 4)) * 4;
+      const float4 mean = ldg4(p.bn + c), rstd = ldg4(p.bn + HID + c), gamma = ldg4(p.bn + 2 * HID + c);
+      const float4 c1 = ldg4(p.cvec + c), c2 = ldg4(p.cvec + HID + c);
+      for (int r = threadIdx.x / (HID / 4); r < GT; r += kThreads / (HID / 4)) {
+        float4 gy = make4(0.f);
+        if (base + r < p.V) {
+          const float4 go = ld4(sm.gy + r * GLD + c);
+          const float4 y = ld4(sm.gu + r * GLD + c);
+          gy.x = rstd.x * (gamma.x * go.x - c1.x - (y.x - mean.x) * rstd.x * c2.x);
+          gy.y = rstd.y * (gamma.y * go.y - c1.y - (y.y - mean.y) * rstd.y * c2.y);
+          gy.z = rstd.z * (gamma.z * go.z - c1.z - (y.z - mean.z) * rstd.z * c2.z);
+          gy.w = rstd.w * (gamma.w * go.w - c1.w - (y.w - mean.w) * rstd.w * c2.w);
+        }
+        st4(sm.gy + r * GLD + c, gy);
       }
-      st4(sm.gy + r * GLD + c, gy);
-      st4(sm.r + r * GLD + c, rr);
     }
-    load_row_tile<GT, KIN>(sm.a, LDA, p.a, base, p.V);
     __syncthreads();
     // ---- g_u = (g_y W2) * [r > 0]
     {
