@@ -24,6 +24,13 @@ bool use_tensor_cores() {
   return g_use_tc == 1;
 }
 
+// contrastive similarity blocks on tcgen05 (default on; SCGIB_CON_FFMA=1 selects the FFMA tiles)
+static int g_con_tc = -1;
+static bool use_tc_contrastive() {
+  if (g_con_tc < 0) { const char* e = getenv("SCGIB_CON_FFMA"); g_con_tc = (e && e[0] == '1') ? 0 : 1; }
+  return g_con_tc == 1;
+}
+
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers).
@@ -108,7 +115,7 @@ struct Ws {
   unsigned int* counters;
   float *H, *q, *C, *logit, *alpha, *lam, *noisy, *Z, *r_head, *readout, *core, *gstat, *cstat, *kl;
   float *rpart, *G, *edge;
-  float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout;
+  float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout, *zsplit;
   float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o, *Ga, *ga0[2];
   float* ppart;
   size_t bytes;
@@ -155,7 +162,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.gstat = take((size_t)B * 4 * HID); w.cstat = take((size_t)B * 2 * HID); w.kl = take(4);
   w.rpart = take((size_t)num_sms() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
   const int js = contrastive_jsplit(B);
-  w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID);
+  w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID); w.zsplit = take((size_t)4 * B * HID);
   w.n1 = take(B); w.n2 = take(B); w.diag = take(B); w.D = take(B);
   w.rowsum = take((size_t)js * B);
   w.g1p = take((size_t)js * B * HID); w.g2p = take((size_t)js * B * HID);
@@ -314,10 +321,13 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
   }
   const int js = contrastive_jsplit(b->B);
   {
-    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag};
+    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
     PROF("normalize", launch_normalize(a, s));
-    ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum};
-    PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
+    ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum, w.zsplit};
+    if (use_tc_contrastive())
+      PROF("contrastive_fwd_tc", launch_contrastive_fwd_tc(c, s));
+    else
+      PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
   }
   {
     LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, w.kl, w.D, losses};

@@ -185,10 +185,11 @@ struct ReconBwdArgs {
 void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s);
 
 // contrastive (models.py:606-629)
-struct NormalizeArgs { const float *core, *readout; int B; float *z1, *z2, *n1, *n2, *diag; };
+struct NormalizeArgs { const float *core, *readout; int B; float *z1, *z2, *n1, *n2, *diag; float* zsplit; };  // zsplit: optional [4][B][HID] tf32 hi/lo of z1, z2
 void launch_normalize(const NormalizeArgs& a, cudaStream_t s);
-struct ContrastiveFwdArgs { const float *z1, *z2; int B; int jsplit; float* rowsum; };  // rowsum [jsplit][B]
-void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s);
+struct ContrastiveFwdArgs { const float *z1, *z2; int B; int jsplit; float* rowsum; const float* zsplit; };  // rowsum [jsplit][B]
+void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s);        // FP32 FFMA tiles
+void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s);     // tcgen05 3xTF32 (contrastive_tc.cu)
 struct ContrastiveBwdArgs {
   const float *z1, *z2, *D; int B; int jsplit;
   float* g1p; float* g2p;                // [jsplit][B][HID] partial gradients wrt z1_hat / z2_hat

@@ -132,6 +132,12 @@ void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s) {
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 // z1 = core / max(||core||, 1e-12), z2 = readout / max(||readout||, 1e-12), diag = z1 . z2   (warp per row)
 __global__ void __launch_bounds__(kThreads)
 normalize_kernel(NormalizeArgs p) {
@@ -143,6 +149,14 @@ normalize_kernel(NormalizeArgs p) {
     const float2 za = make_float2(a.x / na, a.y / na), zb = make_float2(b.x / nb, b.y / nb);
     st2(p.z1 + (size_t)i * HID + c, za);
     st2(p.z2 + (size_t)i * HID + c, zb);
+    if (p.zsplit) {   // tf32 hi / lo parts for the tensor-core kernels: hi = rna(z), lo = rna(z - hi)
+      const size_t n = (size_t)p.B * HID, o = (size_t)i * HID + c;
+      const float2 ah = make_float2(tf32_round(za.x), tf32_round(za.y)), bh = make_float2(tf32_round(zb.x), tf32_round(zb.y));
+      st2(p.zsplit + o, ah);
+      st2(p.zsplit + n + o, make_float2(tf32_round(za.x - ah.x), tf32_round(za.y - ah.y)));
+      st2(p.zsplit + 2 * n + o, bh);
+      st2(p.zsplit + 3 * n + o, make_float2(tf32_round(zb.x - bh.x), tf32_round(zb.y - bh.y)));
+    }
     const float d = warp_sum(za.x * zb.x + za.y * zb.y);
     if (lane == 0) { p.n1[i] = na; p.n2[i] = nb; p.diag[i] = d; }
   }
