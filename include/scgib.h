@@ -195,13 +195,18 @@ SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int
 SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,
                                                   int32_t Es, const char* name);
 
-/* GIN forward implementation: 0 = FP32 FFMA register tiles (default), 1 = tcgen05 3xTF32 tensor-core kernel
- * (also selectable with the environment variable SCGIB_TC=1). */
-SCGIB_API void scgib_set_tensor_cores(int on);
+/* GIN forward implementation: 0 = FP32 FFMA register tiles (gin_kernels.cu), 1 = tcgen05 3xTF32 with 64-row tiles
+ * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu;
+ * 3 is the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
+SCGIB_API void scgib_set_tensor_cores(int mode);
 
 /* Probe of the tcgen05 tile-GEMM primitives (tests only): one 3xTF32 GEMM of fp32 tiles A [M,64], B [64 or M,64] in
  * operand-major mode 0/1/2 (umma_test.cu); out[128][64] = dump of all TMEM lanes. */
 SCGIB_API int scgib_debug_umma(const float* A, const float* B, float* out, int32_t M, int32_t mode, void* stream);
+/* Runtime-parametrised variant (tests only; umma_probe2.cu): params = 23 int32 {M, N, ksteps, split, a_fmt, b_fmt,
+ * a_mn, b_mn, a_{lbo,sbo,ltype,div,adv_lo,adv_hi}, b_{...}, RA, RB, reps}; a_fmt 2 = A operand in tensor memory;
+ * out has 128*64 + 1 floats (the last one = SM cycles of the MMA sequence issued `reps` times). */
+SCGIB_API int scgib_debug_umma2(const float* A, const float* B, float* out, const int32_t* params, void* stream);
 
 /* Per-launch timing with CUDA events recorded on the launching stream (used by bench.py for the roofline
  * numbers).  enable(1) clears the record; every later kernel launch of this library is bracketed by two events;

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "scgib_set_tensor_cores": (None, [c_int]),
     "scgib_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "scgib_debug_umma2": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_void_p]),
     "scgib_profile_enable": (None, [c_int]),
     "scgib_profile_count": (c_int, []),
     "scgib_profile_get": (c_int, [c_int, POINTER(c_char_p), POINTER(c_float)]),

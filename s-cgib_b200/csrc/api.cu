@@ -19,9 +19,15 @@ int num_sms() {
 }
 
 static int g_use_tc = -1;
-bool use_tensor_cores() {
-  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] == '1') ? 1 : 0; }   // opt-in: DESIGN.md section 3
-  return g_use_tc == 1;
+int tensor_core_mode() {
+  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }   // default: gin_tc2.cu, 16 producer warps
+  return g_use_tc;
+}
+static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
+  const int m = tensor_core_mode();
+  if (m == 0) launch_gin_fwd(a, kin, s);
+  else if (m == 1) launch_gin_fwd_tc(a, kin, s);
+  else launch_gin_fwd_tc2(a, kin, m - 1, s);
 }
 
 // contrastive similarity blocks on tcgen05 (default on; SCGIB_CON_FFMA=1 selects the FFMA tiles)
@@ -124,6 +130,8 @@ struct Ws {
 static size_t small_part_floats(int N, int Ns) {
   const int Vmax = N > Ns ? N : Ns;
   size_t a = (size_t)((Vmax + 63) / 64) * 2 * HID;                   // gin fwd tile partials (64-row tiles)
+  const size_t a2 = (size_t)num_sms() * 3 * HID * 2;                  // gin_tc2: per-CTA (n, mean, M2) in fp64
+  a = a > a2 ? a : a2;
   size_t b = (size_t)gin_bwd_pre_grid(Vmax) * 2 * HID;               // dgamma/dbeta partials
   size_t c = (size_t)2 * num_sms() * 5 * HID;                        // gate partials
   size_t d = (size_t)input_proj_bwd_grid(N, Ns) * DTR * 32;          // transfer_d partials
@@ -284,9 +292,9 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
       a.bn_out = w.bn[e][l];
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
       if (use_tensor_cores())
-        PROF(e == 0 ? "gin_fwd_tc.enc1" : "gin_fwd_tc.enc2", launch_gin_fwd_tc(a, l == 0 ? DTR : HID, s));
+        PROF(e == 0 ? "gin_fwd_tc.enc1" : "gin_fwd_tc.enc2", launch_gin_fwd_any(a, l == 0 ? DTR : HID, s));
       else
-        PROF(e == 0 ? "gin_fwd.enc1" : "gin_fwd.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
+        PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
     }
   }
   {
@@ -460,7 +468,10 @@ extern "C" SCGIB_API int scgib_input_proj_fwd_f32(const float* x, const float* W
 }
 
 extern "C" SCGIB_API size_t scgib_gin_workspace_bytes(int32_t V) {
-  return al((size_t)((V + 63) / 64) * 2 * HID * sizeof(float)) + al(HID * HID * sizeof(float)) * 2 + 256;
+  size_t part = (size_t)((V + 63) / 64) * 2 * HID * sizeof(float);
+  const size_t part2 = (size_t)num_sms() * 3 * HID * sizeof(double);
+  if (part2 > part) part = part2;
+  return al(part) + al(HID * HID * sizeof(float)) * 2 + 256;
 }
 
 extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, const int32_t* row_map, const float* bn_in,
@@ -490,7 +501,7 @@ extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, c
   a.W1t = w1t; a.b1 = b1; a.W2t = w2t; a.b2 = b2; a.W1 = W1; a.W2 = W2;
   a.gamma = nullptr; a.beta = nullptr;
   a.a_out = a_out; a.r_out = r_out; a.y_out = y_out; a.part = part; a.counter = counter; a.bn_out = bn_out; a.running = running;
-  if (use_tensor_cores()) launch_gin_fwd_tc(a, kin, s); else launch_gin_fwd(a, kin, s);
+  launch_gin_fwd_any(a, kin, s);
   return (int)cudaGetLastError();
 }
 
@@ -537,4 +548,4 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
 }
 
 // Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
-extern "C" SCGIB_API void scgib_set_tensor_cores(int on) { g_use_tc = on ? 1 : 0; }
+extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 3) ? mode : -1; }   // < 0: back to the default

@@ -28,12 +28,15 @@ struct GinFwdArgs {
   unsigned int* counter;
   float* bn_out;                      // {mean, rstd, gamma, beta}[HID]
   float* running;                     // optional {running_mean, running_var}[HID]
+  int dbg = 0;                        // gin_tc2 experiments (SCGIB_DBG bit mask): 1 no r/y stores, 2 no stats, 4 no gather loads, 8 no a store
 };
 int gin_fwd_grid(int V);
 void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
 int gin_fwd_tc_tiles(int V);
 void launch_gin_fwd_tc(const GinFwdArgs& a, int kin, cudaStream_t s);     // tcgen05 3xTF32 (gin_tc.cu)
-bool use_tensor_cores();                                                  // SCGIB_TC=1 selects the tcgen05 forward
+void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int groups, cudaStream_t s);  // warp-specialised tcgen05 (gin_tc2.cu)
+int tensor_core_mode();                                                   // SCGIB_TC: 0 FFMA, 1 gin_tc.cu, 2/3 gin_tc2.cu (1/2 producer groups)
+inline bool use_tensor_cores() { return tensor_core_mode() != 0; }
 
 struct GinBwdPreArgs {
   const float* src;         // CSR mode: Ga [V][HID]; direct mode: rows gathered through map

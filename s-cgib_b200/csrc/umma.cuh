@@ -162,5 +162,69 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
 
+// the same without the wait (issue several, then tmem_ld_wait once)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// registers -> tensor memory: thread t of the warp writes lane (lane_base + t), columns col..col+15
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+         "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+         "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+         "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+         "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A operand in tensor memory (M = 128: accumulator-style layout, row = lane, K index = column; 8 columns per K step)
+__device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// Format-S tile ([halves of 32 columns][R rows][128 B], 32-byte chunks XOR-swizzled with row % 4) read as a K-MAJOR
+// operand (MN index = tile row, K index = column): layout type SWIZZLE_128B_BASE32B, SBO = 512, LBO = half stride;
+// K step s (8 columns = 32 B) starts at half s/4, byte 32*(s%4) of the row.  Measured on B200 (tests/gpu_umma_probe2.py):
+// the same physical tile therefore serves both contractions of a backward pass (over columns and over rows).
+__device__ __forceinline__ uint64_t desc_s_kmajor(uint32_t tile, int R, int s) {
+  return desc_base(tile + (uint32_t)(s >> 2) * (uint32_t)(R * 128) + (uint32_t)(s & 3) * 32u, (uint32_t)R * 128u, 512u) | ((uint64_t)1 << 61);
+}
+// ... and as an MN-MAJOR operand (MN index = column, K index = tile row): K step s covers rows 8s..8s+7
+__device__ __forceinline__ uint64_t desc_s_mnmajor(uint32_t tile, int R, int s) {
+  return desc_base(tile + (uint32_t)s * 1024u, (uint32_t)R * 128u, 512u) | ((uint64_t)1 << 61);
+}
+// dense format-G weight tile [n rows][C cols] (128-byte cores) as the K-major B operand, K step s
+__device__ __forceinline__ uint64_t desc_g_dense(uint32_t tile, int C, int s) {
+  return desc_base(tile + (uint32_t)s * 256u, 128u, (uint32_t)(C / 4) * 128u);
+}
+
+// one elected lane of a fully converged warp (the compiler then knows the MMA issue region is single-threaded)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
 }  // namespace umma
 }  // namespace scgib

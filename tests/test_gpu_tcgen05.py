@@ -31,11 +31,14 @@ def test_umma_3xtf32_tile_gemm(M, mode):
     assert rel(out[lanes], ref) <= 3e-6          # plain TF32 would be ~1e-3
 
 
+@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (2, 300), (3, 300), (2, 6000), (3, 6000)])
 @pytest.mark.parametrize("kin", [32, 64])
-def test_gin_layer_forward_tensor_cores(kin):
+def test_gin_layer_forward_tensor_cores(kin, mode, B):
+    """mode 1: gin_tc.cu (M = 64 tiles); modes 2/3: gin_tc2.cu (warp-specialised, 1/2 producer groups).  B = 6000
+    graphs give ~90 k rows = several 128-row tiles per CTA (both pipeline stages reused)."""
     from scgib_b200 import _lib, ops
     lib = _lib.load()
-    g = synth_batch(2, 300)
+    g = synth_batch(2, B)
     tg = tgraph_from_ref(g)
     torch.manual_seed(kin)
     conv = GINConvRef(MLP(kin, 64, 64)).double()
@@ -44,13 +47,13 @@ def test_gin_layer_forward_tensor_cores(kin):
     lin1, lin2 = conv.apply_func.mlp[0], conv.apply_func.mlp[2]
     pg = product_graph(g, DEV)
     f = lambda t: t.detach().float().to(DEV)
-    lib.scgib_set_tensor_cores(1)
+    lib.scgib_set_tensor_cores(mode)
     try:
         y, bn, a, r = ops.gin_layer_fwd(f(h), pg.indptr, pg.indices, f(lin1.weight), f(lin1.bias), f(lin2.weight),
                                         f(lin2.bias), save=True)
         torch.cuda.synchronize()
     finally:
-        lib.scgib_set_tensor_cores(0)
+        lib.scgib_set_tensor_cores(-1)
     assert rel(y, y_ref) <= 5e-6
     assert rel(bn[0], y_ref.mean(0)) <= 1e-5
     assert rel(bn[1], 1.0 / torch.sqrt(y_ref.var(0, unbiased=False) + 1e-5)) <= 1e-5
