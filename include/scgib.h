@@ -199,6 +199,9 @@ SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B,
  * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu;
  * 3 is the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
 SCGIB_API void scgib_set_tensor_cores(int mode);
+/* GIN backward (BN backward + the four MLP gradient GEMMs): 1 = tcgen05 3xTF32 kernel (gin_bwd_tc.cu, default),
+ * 0 = FP32 FFMA register tiles; environment variable SCGIB_TC_BWD; on < 0 restores the default. */
+SCGIB_API void scgib_set_tensor_cores_bwd(int on);
 
 /* Probe of the tcgen05 tile-GEMM primitives (tests only): one 3xTF32 GEMM of fp32 tiles A [M,64], B [64 or M,64] in
  * operand-major mode 0/1/2 (umma_test.cu); out[128][64] = dump of all TMEM lanes. */

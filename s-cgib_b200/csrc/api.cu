@@ -23,6 +23,11 @@ int tensor_core_mode() {
   if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }   // default: gin_tc2.cu, 16 producer warps
   return g_use_tc;
 }
+static int g_bwd_tc = -1;
+int bwd_tensor_core_mode() {
+  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
+  return g_bwd_tc;
+}
 static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
   const int m = tensor_core_mode();
   if (m == 0) launch_gin_fwd(a, kin, s);
@@ -423,7 +428,10 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
       ma.V = V; ma.g_a = l == 0 ? w.ga0[e] : w.Ga; ma.part = w.ppart; ma.pstride = lo.total;
       ma.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); ma.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
       ma.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); ma.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
-      PROF(e == 0 ? "gin_bwd_main.enc1" : "gin_bwd_main.enc2", launch_gin_bwd_main(ma, kin, GP, s));
+      if (bwd_tensor_core_mode())
+        PROF(e == 0 ? "gin_bwd_main_tc.enc1" : "gin_bwd_main_tc.enc2", launch_gin_bwd_main_tc(ma, kin, GP, s));
+      else
+        PROF(e == 0 ? "gin_bwd_main_ffma.enc1" : "gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma, kin, GP, s));
     }
   }
   {
@@ -548,4 +556,5 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
 }
 
 // Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
+extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int on) { g_bwd_tc = on < 0 ? -1 : (on ? 1 : 0); }
 extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 3) ? mode : -1; }   // < 0: back to the default

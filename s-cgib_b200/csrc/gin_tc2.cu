@@ -217,7 +217,7 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
     }
   } else if (warp == kEpiWarps) {
     // =========================================================================== MMA issuer
-    if (lane == 0) {
+    {   // the whole warp runs the loop (uniform descriptors); one elected lane issues each instruction
       const uint32_t w1h = smem_u32(smem + L::off_w1_hi), w2h = smem_u32(smem + L::off_w2_hi);
       static_assert(L::off_w1_lo == L::off_w1_hi + L::W1B && L::off_w2_lo == L::off_w2_hi + L::W2B, "hi/lo weight tiles must be adjacent");
       auto gemm1 = [&](int i) {
@@ -232,11 +232,11 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
           if (p.dbg & 64) break;
           const uint64_t dah = desc_s_kmajor(ah, TM, k), dal = desc_s_kmajor(al, TM, k);
           const uint64_t dbh = desc_g_dense(w1h, KIN, k);   // hi tile; the N = 128 view continues into the lo tile
-          mma_tf32(d, dah, dbh, kIdesc2, k > 0);
-          mma_tf32(d, dal, dbh, kIdesc, true);
+          mma_tf32_w(d, dah, dbh, kIdesc2, k > 0);
+          mma_tf32_w(d, dal, dbh, kIdesc, true);
         }
-        mma_commit(&bars[B_D1 + s]);
-        mma_commit(&bars[B_EMPTY_A + s]);
+        mma_commit_w(&bars[B_D1 + s]);
+        mma_commit_w(&bars[B_EMPTY_A + s]);
       };
       auto gemm2 = [&](int i) {
         const int s = i & 1, use = i >> 1;
@@ -248,10 +248,10 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
         for (int k = 0; k < HID / 8; ++k) {
           if (p.dbg & 64) break;
           const uint64_t dbh = desc_g_dense(w2h, HID, k);
-          mma_tf32_ta(d, rh + 8 * k, dbh, kIdesc2, k > 0);
-          mma_tf32_ta(d, rl + 8 * k, dbh, kIdesc, true);
+          mma_tf32_ta_w(d, rh + 8 * k, dbh, kIdesc2, k > 0);
+          mma_tf32_ta_w(d, rl + 8 * k, dbh, kIdesc, true);
         }
-        mma_commit(&bars[B_D2 + s]);
+        mma_commit_w(&bars[B_D2 + s]);
       };
       if (my_tiles > 0) gemm1(0);
       if (my_tiles > 1) gemm1(1);

@@ -65,7 +65,9 @@ struct GinBwdMainArgs {
   int64_t pstride;
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
-void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);
+void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
+void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
+int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 tcgen05 (default)
 
 struct InputProjBwdArgs {
   const float* ga[2];       // layer-0 input gradients of the two encoders, [V][DTR]

@@ -222,6 +222,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// MMA issue from a fully converged warp: every lane computes the (warp-uniform) descriptors, so they stay in uniform
+// registers, and one elected lane issues.  Issuing from inside an `if (lane == 0)` region instead makes the compiler
+// rebuild every descriptor in vector registers and move it to the uniform file per instruction (R2UR), which costs
+// more than the ~54-cycle tcgen05.mma itself for the small N = 64, K = 8 MMAs of this path.
+__device__ __forceinline__ void mma_tf32_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if (elect_one()) mma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_tf32_ta_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if (elect_one()) mma_tf32_ta(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }

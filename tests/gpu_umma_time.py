@@ -31,16 +31,23 @@ def run(tag, reps, **kw):
     print("%-40s reps=%4d mmas=%6d cycles=%9.0f  -> %.1f cycles/mma" % (tag, reps, n, min(res), min(res) / n), flush=True)
 
 
+S_MN = dict(lbo=128 * 128, sbo=512, ltype=1, div=1, adv_lo=0, adv_hi=1024)
+mn = {}
+for side in "ab":
+    for k, v in S_MN.items():
+        mn[side + "_" + k] = v
+skw = {"a_" + k: v for k, v in S_K.items()}
 for reps in (128,):
     run("A smem G K-major, 3x", reps)
-    run("A smem G K-major, 1x", reps, split=1)
-    skw = {"a_" + k: v for k, v in S_K.items()}
     run("A smem S K-major, 3x", reps, a_fmt=1, **skw)
     run("A in TMEM, 3x", reps, a_fmt=2)
-    run("A in TMEM, 1x", reps, a_fmt=2, split=1)
-    run("N=16 A smem G", reps, N=16)
     run("N=128 A smem G (timing only)", reps, N=128)
-    run("N=256 A smem G (timing only)", reps, N=256)
     run("M=64 N=64 A smem G", reps, M=64)
     run("M=64 N=128 A smem G", reps, M=64, N=128)
-    run("M=64 N=256 A smem G", reps, M=64, N=256)
+    run("M=64 N=64 S MN-major both, 3x", reps, M=64, ksteps=16, a_fmt=1, b_fmt=1, a_mn=1, b_mn=1, RB=128, **mn)
+    run("M=64 N=64 S MN-major both, 1x", reps, M=64, ksteps=16, a_fmt=1, b_fmt=1, a_mn=1, b_mn=1, RB=128, split=1, **mn)
+    run("M=64 N=128 S MN-major both, 1x", reps, M=64, N=128, ksteps=16, a_fmt=1, b_fmt=1, a_mn=1, b_mn=1, RB=128, split=1, **mn)
+    kmn = dict(mn); kmn.update(skw)
+    run("M=128 A S K-major, B S MN-major N=64 1x", reps, M=128, a_fmt=1, b_fmt=1, a_mn=0, b_mn=1, split=1, **kmn)
+    amn = dict(mn); amn.update({"b_" + k: v for k, v in G_K.items()})
+    run("M=64 A S MN-major, B G K-major N=64 1x", reps, M=64, a_fmt=1, b_fmt=0, a_mn=1, b_mn=0, split=1, **amn)
