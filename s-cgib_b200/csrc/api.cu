@@ -373,7 +373,10 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
   const int js = contrastive_jsplit(b->B);
   {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
-    PROF("contrastive_bwd", launch_contrastive_bwd(a, s));
+    if (use_tc_contrastive())
+      PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc(a, w.zsplit, s));
+    else
+      PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, s));
     ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
     PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, s));
   }

@@ -141,12 +141,225 @@ contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward (same math as contrastive_bwd_kernel, loss_kernels.cu):
+//   blockIdx.z == 0 (rows i of z1):  g1_i = sum_{j != i} e^{z1_i.z1_j} (1/D_i + 1/D_j) z1_j + sum_j e^{z1_i.z2_j}/D_i z2_j
+//   blockIdx.z == 1 (rows j of z2):  g2_j = sum_i e^{z1_i.z2_j}/D_i z1_i
+// Per 128-row block and 64-row column block: S = Zrow Zcol^T (3xTF32, K-major operands) -> TMEM; the 256 threads turn
+// S into the weighted probabilities P (exp, 1/D weights, masks), split P into tf32 hi/lo and write it BACK to tensor
+// memory, where it is the A operand of the second GEMM  acc += P Zcol  (B = the same shared-memory column tile, now
+// read MN-major; its hi and lo copies are adjacent, so one N = 128 MMA yields P_hi Z_hi and P_hi Z_lo).  P never touches
+// shared memory and the B x B matrices never exist in HBM.  The similarity GEMMs of block t+1 are issued before the
+// epilogue of block t (double-buffered S columns), column tiles are double-buffered with cp.async.
+// ------------------------------------------------------------------------------------------------
+constexpr int ZS_BYTES = tile_s_bytes(CJ);                 // 16384: one [64][64] tile in format S
+constexpr uint32_t kIdSim = idesc_tf32(CI, CJ, false, false);
+constexpr uint32_t kIdPVa = idesc_tf32(CI, 2 * HID, false, true), kIdPVb = idesc_tf32(CI, HID, false, true);
+// TMEM: S set s at 128 s (S1 | S2), P_hi 256, P_lo 320, acc 384 (128 columns, N-stacked)
+constexpr int kColP = 256, kColAcc = 384;
+
+struct ConBwdTcLayout {
+  static constexpr int off_zi = 0;                            // hi, lo (dense cores, K-major A)
+  static constexpr int off_zj = 2 * ZI_BYTES;                 // [2 stages][z1 hi, z1 lo, z2 hi, z2 lo] format S
+  static constexpr int off_di = off_zj + 2 * 4 * ZS_BYTES;    // float [128]
+  static constexpr int off_dj = off_di + CI * 4;              // float [2][64]
+  static constexpr int off_bar = off_dj + 2 * CJ * 4;         // sim[2], pv
+  static constexpr int total = off_bar + 64;
+};
+
+template <int R>
+__device__ __forceinline__ void cp_async_tile_s(unsigned char* dst, const float* __restrict__ src, int base, int B) {
+  for (int i = threadIdx.x; i < R * 16; i += kThreads) {
+    const int r = i >> 4, c4 = i & 15;
+    const bool ok = base + r < B;
+    cp_async16(dst + tile_s_off4(R, r, c4), src + (size_t)(ok ? base + r : 0) * HID + c4 * 4, ok);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit) {
+  using L = ConBwdTcLayout;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* zi_hi = smem + L::off_zi;
+  unsigned char* zi_lo = zi_hi + ZI_BYTES;
+  unsigned char* zj = smem + L::off_zj;
+  float* s_di = reinterpret_cast<float*>(smem + L::off_di);
+  float* s_dj = reinterpret_cast<float*>(smem + L::off_dj);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::off_bar + 32);
+  const size_t n = (size_t)p.B * HID;
+  const float *z1h = zsplit, *z1l = zsplit + n, *z2h = zsplit + 2 * n, *z2l = zsplit + 3 * n;
+  const bool mode1 = (blockIdx.z == 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ibase = blockIdx.x * CI;
+  const int jblocks = (p.B + CJ - 1) / CJ;
+  const int nblk = (jblocks - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+  auto jb_of = [&](int t) { return ((int)blockIdx.y + t * (int)gridDim.y) * CJ; };
+  auto load_j = [&](int t) {
+    unsigned char* buf = zj + (t & 1) * 4 * ZS_BYTES;
+    const int jbase = jb_of(t);
+    cp_async_tile_s<CJ>(buf, z1h, jbase, p.B);
+    cp_async_tile_s<CJ>(buf + ZS_BYTES, z1l, jbase, p.B);
+    if (!mode1) {
+      cp_async_tile_s<CJ>(buf + 2 * ZS_BYTES, z2h, jbase, p.B);
+      cp_async_tile_s<CJ>(buf + 3 * ZS_BYTES, z2l, jbase, p.B);
+    }
+    if (threadIdx.x < CJ) s_dj[(t & 1) * CJ + threadIdx.x] = (jbase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + jbase + threadIdx.x) : 0.f;
+  };
+
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1); }
+  cp_async_tile_g<CI>(zi_hi, mode1 ? z2h : z1h, ibase, p.B);
+  cp_async_tile_g<CI>(zi_lo, mode1 ? z2l : z1l, ibase, p.B);
+  if (threadIdx.x < CI) s_di[threadIdx.x] = (ibase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + ibase + threadIdx.x) : 0.f;
+  if (nblk > 0) load_j(0);
+  cp_async_commit();
+  if (nblk > 1) load_j(1);
+  cp_async_commit();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t zih = smem_u32(zi_hi), zil = smem_u32(zi_lo);
+  // similarity GEMMs of block t into S set t&1 (whole warp 0 runs this; one elected lane issues)
+  auto issue_sim = [&](int t) {
+    const uint32_t buf = smem_u32(zj + (t & 1) * 4 * ZS_BYTES);
+    const uint32_t d = tmem + (t & 1) * 128;
+    const int nsim = mode1 ? 1 : 2;
+    for (int q = 0; q < nsim; ++q) {
+      const uint32_t bh = buf + q * 2 * ZS_BYTES, bl = bh + ZS_BYTES;
+#pragma unroll
+      for (int k = 0; k < HID / 8; ++k) {
+        const uint64_t ah = desc_g_dense(zih, HID, k), al = desc_g_dense(zil, HID, k);
+        const uint64_t dbh = desc_s_kmajor(bh, CJ, k), dbl = desc_s_kmajor(bl, CJ, k);
+        mma_tf32_w(d + q * 64, al, dbh, kIdSim, k > 0);
+        mma_tf32_w(d + q * 64, ah, dbl, kIdSim, true);
+        mma_tf32_w(d + q * 64, ah, dbh, kIdSim, true);
+      }
+    }
+    mma_commit_w(&s_bar[t & 1]);
+  };
+  // acc += P Zcol for source q (0: z1 tile, 1: z2 tile) of block t; P (hi | lo) is in tensor memory
+  auto issue_pv = [&](int t, int q, bool first) {
+    const uint32_t bh = smem_u32(zj + (t & 1) * 4 * ZS_BYTES) + q * 2 * ZS_BYTES;
+#pragma unroll
+    for (int k = 0; k < CJ / 8; ++k) {
+      const uint64_t b = desc_s_mnmajor(bh, CJ, k);
+      mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 8 * k, b, kIdPVa, !(first && k == 0));
+      mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 64 + 8 * k, b, kIdPVb, true);
+    }
+    mma_commit_w(&s_bar[2]);
+  };
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (warp == 0 && nblk > 0) issue_sim(0);
+
+  const int row = 32 * (warp & 3) + lane;              // TMEM lane = row of the 128-row block
+  const int hcol = (warp >> 2) * 32;                   // this thread's half of the 64 columns
+  const int gi = ibase + row;
+  const uint32_t tl = (uint32_t)(32 * (warp & 3)) << 16;
+  const float di = s_di[row];
+  int pv_issued = 0, pv_waited = 0;                    // PV GEMM groups committed / observed complete (block-uniform)
+  auto wait_pv = [&]() {                               // every committed PV GEMM has completed (P and its column tile are free)
+    while (pv_waited < pv_issued) { mbar_wait(&s_bar[2], (uint32_t)(pv_waited & 1)); ++pv_waited; }
+    fence_after_sync();
+  };
+  // one weighted-probability block: S (32 columns of this thread) -> P hi/lo in tensor memory
+  auto make_p = [&](uint32_t s_addr, int jbase, const float* dj, int kind) {   // kind 0: refl (z1 z1), 1: between, 2: mode 1
+    float v[32];
+    tmem_ld16_nowait(s_addr, *reinterpret_cast<float (*)[16]>(v));
+    tmem_ld16_nowait(s_addr + 16, *reinterpret_cast<float (*)[16]>(v + 16));
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int gj = jbase + hcol + j;
+      float w;
+      if (kind == 0) w = (gj != gi) ? di + dj[hcol + j] : 0.f;
+      else if (kind == 1) w = di;
+      else w = dj[hcol + j];
+      v[j] = (gj < p.B && gi < p.B) ? expf(v[j]) * w : 0.f;
+    }
+    wait_pv();                                         // the previous P has been consumed before it is overwritten
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { hi[j] = tf32_rna(v[16 * c + j]); lo[j] = tf32_rna(v[16 * c + j] - hi[j]); }
+      tmem_st16(tmem + tl + kColP + hcol + 16 * c, hi);
+      tmem_st16(tmem + tl + kColP + 64 + hcol + 16 * c, lo);
+    }
+    tmem_st_wait();
+  };
+  for (int t = 0; t < nblk; ++t) {
+    // A. block t+1 has landed -> its similarity GEMMs go into the other S set (consumed two iterations ago)
+    cp_async_wait_all();
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (warp == 0 && t + 1 < nblk) issue_sim(t + 1);
+    // B. similarities of block t are in tensor memory
+    mbar_wait(&s_bar[t & 1], (uint32_t)((t >> 1) & 1));
+    fence_after_sync();
+    const int jbase = jb_of(t);
+    const float* dj = s_dj + (t & 1) * CJ;
+    const uint32_t sset = tmem + tl + (t & 1) * 128 + hcol;
+    const int nsrc = mode1 ? 1 : 2;
+    for (int q = 0; q < nsrc; ++q) {
+      make_p(sset + q * 64, jbase, dj, mode1 ? 2 : q);
+      fence_before_sync();
+      __syncthreads();
+      fence_after_sync();
+      if (warp == 0) issue_pv(t, q, pv_issued == 0);
+      ++pv_issued;
+    }
+    // C. stage t&1 is free once the PV GEMMs of block t have completed: prefetch block t+2 into it
+    if (t + 2 < nblk) { wait_pv(); load_j(t + 2); }
+    cp_async_commit();
+  }
+  // ---- result rows: acc = columns 0..63 + columns 64..127
+  float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
+  if (nblk > 0) {
+    wait_pv();
+    float a0[32], a1[32];
+    tmem_ld16_nowait(tmem + tl + kColAcc + hcol, *reinterpret_cast<float (*)[16]>(a0));
+    tmem_ld16_nowait(tmem + tl + kColAcc + hcol + 16, *reinterpret_cast<float (*)[16]>(a0 + 16));
+    tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol, *reinterpret_cast<float (*)[16]>(a1));
+    tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol + 16, *reinterpret_cast<float (*)[16]>(a1 + 16));
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a0[j] += a1[j];
+    if (gi < p.B) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, a0 + 8 * j);
+    }
+  } else if (gi < p.B) {
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, z);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(contrastive_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ConTcLayout::total), true);
   (void)once;
   dim3 grid((a.B + CI - 1) / CI, a.jsplit);
   contrastive_fwd_tc_kernel<<<grid, kThreads, ConTcLayout::total, s>>>(a);
+}
+
+void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(contrastive_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ConBwdTcLayout::total), true);
+  (void)once;
+  dim3 grid((a.B + CI - 1) / CI, a.jsplit, 2);
+  contrastive_bwd_tc_kernel<<<grid, kThreads, ConBwdTcLayout::total, s>>>(a, zsplit);
 }
 
 }  // namespace scgib

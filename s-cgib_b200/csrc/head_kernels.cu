@@ -268,9 +268,15 @@ compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict_
   const int j = threadIdx.x & (2 * HID - 1);  // 0..63 mean, 64..127 var
   const int seg = threadIdx.x / (2 * HID);
   const int g0 = B > kEmaWindow ? B - kEmaWindow : 0;
+  // newest graph first: weight 0.1 * 0.9^k for age k = B-1-g, advanced by a constant factor (two pow() per thread
+  // instead of one per term: the fp64 pow dominated this kernel)
   double acc = 0.0;
-  for (int g = g0 + seg; g < B; g += kEmaSeg)
-    acc += 0.1 * pow(0.9, (double)(B - 1 - g)) * (double)cstat[(size_t)g * 2 * HID + j];
+  double w = 0.1 * pow(0.9, (double)seg);
+  const double step = pow(0.9, (double)kEmaSeg);
+  for (int g = B - 1 - seg; g >= g0; g -= kEmaSeg) {
+    acc += w * (double)cstat[(size_t)g * 2 * HID + j];
+    w *= step;
+  }
   s_part[seg][j] = acc;
   __syncthreads();
   if (seg == 0) {

@@ -199,7 +199,8 @@ struct ContrastiveBwdArgs {
   const float *z1, *z2, *D; int B; int jsplit;
   float* g1p; float* g2p;                // [jsplit][B][HID] partial gradients wrt z1_hat / z2_hat
 };
-void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s);
+void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s);                          // FP32 FFMA tiles
+void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s);   // tcgen05 (contrastive_tc.cu)
 struct ContrastiveBwdFinArgs {
   const float *g1p, *g2p, *z1, *z2, *n1, *n2; int B; int jsplit; float scale;
   float *g_core, *g_readout;

@@ -22,6 +22,10 @@ for ltype, sbo, lbo, adv in itertools.product([1, 2, 0], [1024, 512], [16, 128 *
 for ltype, sbo, lbo in itertools.product([1, 2], [1024, 512], [16, 128 * 128]):
     CASES.append(("A fmt S K-major 1 kstep ltype=%d sbo=%d lbo=%d" % (ltype, sbo, lbo), "AB8",
                   dict(a_fmt=1, a_ltype=ltype, a_sbo=sbo, a_lbo=lbo, a_div=4, a_adv_lo=32, a_adv_hi=128 * 128, ksteps=1)))
+CASES.append(("B fmt S K-major R=64 (dual use)", "AB", dict(b_fmt=1, b_ltype=1, b_sbo=512, b_lbo=64 * 128, b_div=4, b_adv_lo=32, b_adv_hi=64 * 128)))
+CASES.append(("A TMEM x B fmt S MN-major R=64", "ABn", dict(a_fmt=2, b_fmt=1, b_mn=1, b_ltype=1, b_sbo=512, b_lbo=64 * 128, b_div=1, b_adv_lo=0, b_adv_hi=1024)))
+CASES.append(("A fmt S K-major x B fmt S MN-major R=64", "ABn", dict(a_fmt=1, a_ltype=1, a_sbo=512, a_lbo=128 * 128, a_div=4, a_adv_lo=32, a_adv_hi=128 * 128,
+                                                               b_fmt=1, b_mn=1, b_ltype=1, b_sbo=512, b_lbo=64 * 128, b_div=1, b_adv_lo=0, b_adv_hi=1024)))
 kw = {}
 for side in "ab":
     for k, v in S_MN.items():
@@ -44,6 +48,8 @@ def one(idx):
         ref, lanes = A.double() @ B.double().t(), L128
     elif kind == "AB8":
         ref, lanes = A.double()[:, :8] @ B.double()[:, :8].t(), L128
+    elif kind == "ABn":
+        ref, lanes = A.double() @ B.double(), L128
     elif kind == "A64":
         A = A[:64].contiguous()
         ref, lanes = A.double() @ B.double().t(), L64
