@@ -45,45 +45,96 @@ struct Bn4 {
 };
 
 // GIN aggregation a_v = f(in[map(v)]) + sum_{u in N(v)} f(in[map(u)]) for NR rows at once per thread (lane `gl` owns
-// 4 channels).  The NR dependent chains (indptr -> indices -> [row_map] -> features) are interleaved so that NR times
-// more loads are in flight: the gather is latency-bound, not bandwidth-bound (degree ~2, 256-byte rows).
+// 4 channels).  The gather is latency-bound, not bandwidth-bound (degree ~2, 256-byte rows), so it is organised for
+// memory-level parallelism: every dependent stage (indptr -> indices -> [row_map] -> feature rows) is issued for all
+// NR rows and for TWO neighbour slots at once before anything is consumed.  Neighbours are added in CSR order.
 template <int KIN, int NR>
 __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, const int32_t* __restrict__ row_map,
                                                  const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                  int V, const int (&v)[NR], int gl, const Bn4* bn, float4 (&acc)[NR]) {
-  int e0[NR], e1[NR];
+  int e0[NR], deg[NR], sv[NR];
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
     const bool ok = v[j] < V;
     e0[j] = ok ? __ldg(indptr + v[j]) : 0;
-    e1[j] = ok ? __ldg(indptr + v[j] + 1) : 0;
+    deg[j] = ok ? __ldg(indptr + v[j] + 1) : 0;
+    sv[j] = (ok && row_map) ? __ldg(row_map + v[j]) : v[j];
+  }
+  int maxd = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) { deg[j] -= e0[j]; maxd = max(maxd, deg[j]); }
+  int u0[NR], u1[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    u0[j] = deg[j] > 0 ? __ldg(indices + e0[j]) : -1;
+    u1[j] = deg[j] > 1 ? __ldg(indices + e0[j] + 1) : -1;
+  }
+  float4 hs[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) hs[j] = v[j] < V ? ld4(in + (size_t)sv[j] * KIN + gl * 4) : make4(0.f);
+  if (row_map) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if (u0[j] >= 0) u0[j] = __ldg(row_map + u0[j]);
+      if (u1[j] >= 0) u1[j] = __ldg(row_map + u1[j]);
+    }
+  }
+  float4 h0[NR], h1[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    h0[j] = u0[j] >= 0 ? ld4(in + (size_t)u0[j] * KIN + gl * 4) : make4(0.f);
+    h1[j] = u1[j] >= 0 ? ld4(in + (size_t)u1[j] * KIN + gl * 4) : make4(0.f);
   }
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
     acc[j] = make4(0.f);
-    if (v[j] < V) {
-      const int sv = row_map ? __ldg(row_map + v[j]) : v[j];
-      const float4 h = ld4(in + (size_t)sv * KIN + gl * 4);
-      acc[j] = bn ? bn->act(h) : h;
-    }
+    if (v[j] < V) acc[j] = bn ? bn->act(hs[j]) : hs[j];
+    if (u0[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h0[j]) : h0[j]);
+    if (u1[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h1[j]) : h1[j]);
   }
-  int maxd = 0;
+  for (int d = 2; d < maxd; d += 2) {                    // rows with more than two neighbours
 #pragma unroll
-  for (int j = 0; j < NR; ++j) maxd = max(maxd, e1[j] - e0[j]);
-  for (int s = 0; s < maxd; ++s) {
-    int u[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) u[j] = (e0[j] + s < e1[j]) ? __ldg(indices + e0[j] + s) : -1;
+    for (int j = 0; j < NR; ++j) {
+      u0[j] = deg[j] > d ? __ldg(indices + e0[j] + d) : -1;
+      u1[j] = deg[j] > d + 1 ? __ldg(indices + e0[j] + d + 1) : -1;
+    }
     if (row_map) {
 #pragma unroll
-      for (int j = 0; j < NR; ++j) if (u[j] >= 0) u[j] = __ldg(row_map + u[j]);
+      for (int j = 0; j < NR; ++j) {
+        if (u0[j] >= 0) u0[j] = __ldg(row_map + u0[j]);
+        if (u1[j] >= 0) u1[j] = __ldg(row_map + u1[j]);
+      }
     }
-    float4 h[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) h[j] = (u[j] >= 0) ? ld4(in + (size_t)u[j] * KIN + gl * 4) : make4(0.f);
+    for (int j = 0; j < NR; ++j) {
+      h0[j] = u0[j] >= 0 ? ld4(in + (size_t)u0[j] * KIN + gl * 4) : make4(0.f);
+      h1[j] = u1[j] >= 0 ? ld4(in + (size_t)u1[j] * KIN + gl * 4) : make4(0.f);
+    }
 #pragma unroll
-    for (int j = 0; j < NR; ++j) if (u[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h[j]) : h[j]);
+    for (int j = 0; j < NR; ++j) {
+      if (u0[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h0[j]) : h0[j]);
+      if (u1[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h1[j]) : h1[j]);
+    }
   }
+}
+
+// Deterministic sum of `n` per-CTA partials part[b * stride] (b = start, start + step, ...) in fp64: the loads of a
+// batch are independent and issued together (one L2 latency per batch instead of one per partial), the adds keep the
+// fixed order.
+template <int BATCH>
+__device__ __forceinline__ double sum_partials(const float* part, size_t stride, int n, int start, int step) {
+  double s = 0.0;
+  for (int b0 = start; b0 < n; b0 += step * BATCH) {
+    float v[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int b = b0 + k * step;
+      v[k] = b < n ? __ldcg(part + (size_t)b * stride) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) s += (double)v[k];
+  }
+  return s;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -238,7 +238,7 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
 //   g_o = G * [gamma*yhat+beta > 0] ; dbeta = sum g_o ; dgamma = sum g_o*yhat
 // Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 gin_bwd_pre_kernel(GinBwdPreArgs p) {
   __shared__ __align__(16) float s_red[16 * 2 * HID];
   __shared__ double s_d[2 * 2 * HID];
@@ -252,6 +252,9 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
     float4 g[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) vv[j] = v0 + j * gridDim.x * 16;
+    float4 y[NR];   // issued first: independent of the gather's dependent index chain
+#pragma unroll
+    for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
     if (p.indptr) {
       gather_aggregate<HID, NR>(p.src, nullptr, p.indptr, p.indices, p.V, vv, l, nullptr, g);
     } else {
@@ -261,9 +264,6 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
         if (vv[j] < p.V) g[j] = ld4(p.src + (size_t)(p.map ? __ldg(p.map + vv[j]) : vv[j]) * HID + l * 4);
       }
     }
-    float4 y[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       if (vv[j] >= p.V) continue;
@@ -286,12 +286,10 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
     p.part[(size_t)blockIdx.x * 2 * HID + threadIdx.x] = s;
   }
   if (!last_cta_arrives(p.counter)) return;
-  // 256 threads: column j = tid & 127 (0..63 dbeta, 64..127 dgamma), 2 interleaved segments
+  // 256 threads: column j = tid & 127 (0..63 dbeta, 64..127 dgamma), 2 interleaved segments, batched loads
   {
     const int j = threadIdx.x & (2 * HID - 1), seg = threadIdx.x >> 7;
-    double s = 0.0;
-    for (int b = seg; b < (int)gridDim.x; b += 2) s += (double)__ldcg(p.part + (size_t)b * 2 * HID + j);
-    s_d[seg * 2 * HID + j] = s;
+    s_d[seg * 2 * HID + j] = sum_partials<16>(p.part + j, 2 * HID, (int)gridDim.x, seg, 2);
   }
   __syncthreads();
   if (threadIdx.x < HID) {
@@ -306,7 +304,7 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
   }
 }
 
-int gin_bwd_pre_grid(int V) { return min((V + 15) / 16, 8 * num_sms()); }
+int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, 2 * num_sms()); }   // 2 resident CTAs per SM, 64 rows per pass
 
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s) {
   gin_bwd_pre_kernel<<<gin_bwd_pre_grid(a.V), kThreads, 0, s>>>(a);
@@ -519,8 +517,7 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
   for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
   if (!last_cta_arrives(p.counter)) return;
   for (int idx = threadIdx.x; idx < DTR * FP; idx += kThreads) {
-    double s = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(p.part + (size_t)b * DTR * FP + idx);
+    const double s = sum_partials<16>(p.part + idx, DTR * FP, (int)gridDim.x, 0, 1);
     const int oo = idx / FP, f = idx % FP;
     if (f < p.F) p.d_Wt[oo * p.F + f] = (float)s;
   }
