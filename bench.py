@@ -248,8 +248,8 @@ def main():
     hbm, peak_src = peaks()
     dom = max(kernels, key=lambda k_: kernels[k_]["ms_per_step"])
     # algorithmic bytes of one launch of the dominant kernel family (per-layer figures of SURVEY.md 8d)
-    V = {"enc1": b.N, "enc2": b.Ns}.get(dom.split(".")[-1], b.N)
-    D = {"enc1": b.E, "enc2": b.Es}.get(dom.split(".")[-1], b.E)
+    V = {"enc1": b.N, "enc2": b.Ns, "enc1+2": b.N + b.Ns}.get(dom.split(".")[-1], b.N)
+    D = {"enc1": b.E, "enc2": b.Es, "enc1+2": b.E + b.Es}.get(dom.split(".")[-1], b.E)
     per_layer = [(32, 64), (64, 64), (64, 64), (64, 64)]
     if dom.startswith("gin_bwd_main"):
         abytes = sum(V * 2 * (di + d) * 4 for di, d in per_layer) / 4.0

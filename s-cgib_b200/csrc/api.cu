@@ -121,13 +121,14 @@ struct Ws {
   float* t;
   float *a[2][8], *r[2][8], *y[2][8];
   float* bn[2][8];      // {mean, rstd, gamma, beta}
-  float* cvec;
+  float* cvec[2];
   float* small_part;    // BN partials (fwd) / dgamma,dbeta partials (bwd) / gate partials / input-proj partials
+  float* small_part2;   // the same for Encoder2 when both encoders share a launch
   unsigned int* counters;
   float *H, *q, *C, *logit, *alpha, *lam, *noisy, *Z, *r_head, *readout, *core, *gstat, *cstat, *kl;
   float *rpart, *G, *edge;
   float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout, *zsplit;
-  float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o, *Ga, *ga0[2];
+  float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o[2], *Ga[2], *ga0[2];
   float* ppart;
   size_t bytes;
 };
@@ -137,7 +138,7 @@ static size_t small_part_floats(int N, int Ns) {
   size_t a = (size_t)((Vmax + 63) / 64) * 2 * HID;                   // gin fwd tile partials (64-row tiles)
   const size_t a2 = (size_t)num_sms() * 3 * HID * 2;                  // gin_tc2: per-CTA (n, mean, M2) in fp64
   a = a > a2 ? a : a2;
-  size_t b = (size_t)gin_bwd_pre_grid(Vmax) * 2 * HID;               // dgamma/dbeta partials
+  size_t b = (size_t)(gin_bwd_pre_grid(N + Ns) + 2) * 2 * HID;       // dgamma/dbeta partials (per problem of a shared launch)
   size_t c = (size_t)2 * num_sms() * 5 * HID;                        // gate partials
   size_t d = (size_t)input_proj_bwd_grid(N, Ns) * DTR * 32;          // transfer_d partials
   size_t m = a > b ? a : b;
@@ -165,8 +166,8 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
     }
   w.head_w1t = take(2 * HID * HID); w.head_w2t = take(HID * HID); w.comp_w1t = take(HID * HID);
   w.t = take((size_t)N * DTR);
-  w.cvec = take(2 * HID);
-  w.small_part = take(small_part_floats(N, Ns));
+  w.cvec[0] = take(2 * HID); w.cvec[1] = take(2 * HID);
+  w.small_part = take(small_part_floats(N, Ns)); w.small_part2 = take(small_part_floats(N, Ns));
   w.counters = (unsigned int*)take(64);
   w.H = take((size_t)N * HID); w.q = take((size_t)N * HID); w.C = take((size_t)N * HID);
   w.logit = take(N); w.alpha = take(N); w.lam = take(N);
@@ -182,7 +183,9 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.g_core = take((size_t)B * HID); w.g_readout = take((size_t)B * HID);
   w.gZ = take((size_t)N * HID); w.gI = take((size_t)N * 2 * HID); w.gp = take(N);
   w.g_q = take((size_t)N * HID); w.gH = take((size_t)N * HID); w.gC = take((size_t)N * HID);
-  w.g_o = take((size_t)Vmax * HID); w.Ga = take((size_t)Vmax * HID);
+  w.g_o[0] = take((size_t)N * HID); w.g_o[1] = take((size_t)Ns * HID);
+  w.Ga[0] = take((size_t)N * HID); w.Ga[1] = take((size_t)Ns * HID);
+  (void)Vmax;
   w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
   w.ppart = take((size_t)num_sms() * lo.total);
   w.bytes = o;
@@ -278,10 +281,11 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
     cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
   else
     PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s));
-  // the two GIN encoders (models.py:704, 707)
-  for (int e = 0; e < 2; ++e) {
-    for (int l = 0; l < L; ++l) {
-      GinFwdArgs a;
+  // the two GIN encoders (models.py:704, 707): layer l of Encoder1 and of Encoder2 are independent, so they share a launch
+  for (int l = 0; l < L; ++l) {
+    GinFwdArgs ga[2];
+    for (int e = 0; e < 2; ++e) {
+      GinFwdArgs& a = ga[e];
       a.in = l == 0 ? w.t : w.y[e][l - 1];
       a.row_map = (e == 1 && l == 0) ? b->ego_nodes : nullptr;
       a.bn_in = l == 0 ? nullptr : w.bn[e][l - 1];
@@ -293,13 +297,18 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
       a.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); a.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
       a.gamma = params + lo.enc(e, l, L, SCGIB_ENC_GAMMA); a.beta = params + lo.enc(e, l, L, SCGIB_ENC_BETA);
       a.a_out = w.a[e][l]; a.r_out = w.r[e][l]; a.y_out = w.y[e][l];
-      a.part = w.small_part; a.counter = w.counters + 0;
+      a.part = e == 0 ? w.small_part : w.small_part2; a.counter = w.counters + (e == 0 ? 0 : 8);
       a.bn_out = w.bn[e][l];
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
-      if (use_tensor_cores())
-        PROF(e == 0 ? "gin_fwd_tc.enc1" : "gin_fwd_tc.enc2", launch_gin_fwd_any(a, l == 0 ? DTR : HID, s));
-      else
-        PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(a, l == 0 ? DTR : HID, s));
+    }
+    const int kin = l == 0 ? DTR : HID, m = tensor_core_mode();
+    if (m >= 2) {
+      PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc2_pair(ga[0], ga[1], kin, m - 1, s));
+    } else {
+      for (int e = 0; e < 2; ++e) {
+        if (m == 1) PROF(e == 0 ? "gin_fwd_tc64.enc1" : "gin_fwd_tc64.enc2", launch_gin_fwd_tc(ga[e], kin, s));
+        else PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
+      }
     }
   }
   {
@@ -409,32 +418,37 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
                      lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1]};
     PROF("gate_lin_bwd", launch_gate_lin_bwd(a, GP, s));
   }
-  for (int e = 0; e < 2; ++e) {
-    const int V = e == 0 ? b->N : b->Ns;
-    const int32_t* indptr = e == 0 ? b->indptr : b->sub_indptr;
-    const int32_t* indices = e == 0 ? b->indices : b->sub_indices;
-    for (int l = L - 1; l >= 0; --l) {
-      const int kin = l == 0 ? DTR : HID;
-      GinBwdPreArgs pa;
+  const int enc_split = pair_split(GP, (b->N + 127) / 128, (b->Ns + 127) / 128);   // CTAs of Encoder1 in a shared launch
+  const bool pair_main = bwd_tensor_core_mode() != 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const int kin = l == 0 ? DTR : HID;
+    GinBwdPreArgs pa[2];
+    GinBwdMainArgs ma[2];
+    for (int e = 0; e < 2; ++e) {
+      const int V = e == 0 ? b->N : b->Ns;
+      GinBwdPreArgs& q = pa[e];
       if (l == L - 1) {
-        pa.src = e == 0 ? w.gH : w.gC; pa.indptr = nullptr; pa.indices = nullptr; pa.map = e == 0 ? nullptr : b->ego_seed;
+        q.src = e == 0 ? w.gH : w.gC; q.indptr = nullptr; q.indices = nullptr; q.map = e == 0 ? nullptr : b->ego_seed;
       } else {
-        pa.src = w.Ga; pa.indptr = indptr; pa.indices = indices; pa.map = nullptr;
+        q.src = w.Ga[e]; q.indptr = e == 0 ? b->indptr : b->sub_indptr; q.indices = e == 0 ? b->indices : b->sub_indices; q.map = nullptr;
       }
-      pa.y = w.y[e][l]; pa.bn = w.bn[e][l]; pa.V = V; pa.g_o = w.g_o; pa.part = w.small_part; pa.counter = w.counters + 2;
-      pa.d_gamma = grads + lo.enc(e, l, L, SCGIB_ENC_GAMMA); pa.d_beta = grads + lo.enc(e, l, L, SCGIB_ENC_BETA);
-      pa.cvec = w.cvec;
-      PROF(e == 0 ? "gin_bwd_pre.enc1" : "gin_bwd_pre.enc2", launch_gin_bwd_pre(pa, s));
-      GinBwdMainArgs ma;
-      ma.g_o = w.g_o; ma.y = w.y[e][l]; ma.r = w.r[e][l]; ma.a = w.a[e][l]; ma.bn = w.bn[e][l]; ma.cvec = w.cvec;
-      ma.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); ma.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
-      ma.V = V; ma.g_a = l == 0 ? w.ga0[e] : w.Ga; ma.part = w.ppart; ma.pstride = lo.total;
-      ma.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); ma.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
-      ma.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); ma.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
-      if (bwd_tensor_core_mode())
-        PROF(e == 0 ? "gin_bwd_main_tc.enc1" : "gin_bwd_main_tc.enc2", launch_gin_bwd_main_tc(ma, kin, GP, s));
-      else
-        PROF(e == 0 ? "gin_bwd_main_ffma.enc1" : "gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma, kin, GP, s));
+      q.y = w.y[e][l]; q.bn = w.bn[e][l]; q.V = V; q.g_o = w.g_o[e];
+      q.part = e == 0 ? w.small_part : w.small_part2; q.counter = w.counters + (e == 0 ? 2 : 10);
+      q.d_gamma = grads + lo.enc(e, l, L, SCGIB_ENC_GAMMA); q.d_beta = grads + lo.enc(e, l, L, SCGIB_ENC_BETA);
+      q.cvec = w.cvec[e];
+      GinBwdMainArgs& m = ma[e];
+      m.g_o = w.g_o[e]; m.y = w.y[e][l]; m.r = w.r[e][l]; m.a = w.a[e][l]; m.bn = w.bn[e][l]; m.cvec = w.cvec[e];
+      m.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); m.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
+      m.V = V; m.g_a = l == 0 ? w.ga0[e] : w.Ga[e]; m.part = w.ppart; m.pstride = lo.total;
+      m.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); m.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
+      m.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); m.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
+    }
+    PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], s));
+    if (pair_main) {
+      PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc_pair(ma[0], ma[1], kin, GP, s));
+    } else {
+      PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, GP, s));
+      PROF("gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma[1], kin, GP, s));
     }
   }
   {
@@ -449,11 +463,13 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
   {
     ReduceRanges r;
     r.n = 0;
-    auto add = [&](int64_t off, int64_t len) { r.off[r.n] = off; r.len[r.n] = len; ++r.n; };
-    add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1]);
-    add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1]);
-    for (int e = 0; e < 2; ++e)
-      for (int l = 0; l < L; ++l) add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1));
+    auto add = [&](int64_t off, int64_t len, int c0, int c1) { r.off[r.n] = off; r.len[r.n] = len; r.c0[r.n] = c0; r.c1[r.n] = c1; ++r.n; };
+    add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1], 0, GP);
+    add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1], 0, GP);
+    for (int e = 0; e < 2; ++e)        // shared launches: partial rows [0, split) belong to Encoder1, [split, GP) to Encoder2
+      for (int l = 0; l < L; ++l)
+        add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1),
+            pair_main ? (e == 0 ? 0 : enc_split) : 0, pair_main ? (e == 0 ? enc_split : GP) : GP);
     PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
   }
   return (int)cudaGetLastError();
@@ -535,7 +551,7 @@ extern "C" SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d,
       {"noisy", w.noisy}, {"Z", w.Z}, {"r_head", w.r_head}, {"readout", w.readout}, {"core", w.core}, {"gstat", w.gstat},
       {"kl", w.kl}, {"G", w.G}, {"edge", w.edge}, {"z1", w.z1}, {"z2", w.z2}, {"D", w.D}, {"diag", w.diag},
       {"g_core", w.g_core}, {"g_readout", w.g_readout}, {"gZ", w.gZ}, {"gI", w.gI}, {"gp", w.gp}, {"g_q", w.g_q},
-      {"gH", w.gH}, {"gC", w.gC}, {"ga0_1", w.ga0[0]}, {"ga0_2", w.ga0[1]}, {"cvec", w.cvec}};
+      {"gH", w.gH}, {"gC", w.gC}, {"ga0_1", w.ga0[0]}, {"ga0_2", w.ga0[1]}, {"cvec", w.cvec[0]}};
   for (auto& e : tab)
     if (!strcmp(e.n, name)) return (int64_t)((const char*)e.p - (const char*)nullptr);
   int e = 0, l = 0;

@@ -118,22 +118,13 @@ __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, c
   }
 }
 
-// Deterministic sum of `n` per-CTA partials part[b * stride] (b = start, start + step, ...) in fp64: the loads of a
-// batch are independent and issued together (one L2 latency per batch instead of one per partial), the adds keep the
-// fixed order.
-template <int BATCH>
+// Deterministic sum of `n` per-CTA partials part[b * stride] (b = start, start + step, ...) in fp64, fixed order.  The
+// loads are independent of the adds, so the unrolled loop keeps several in flight (a hand-batched variant with an
+// explicit array of loads measured slower on B200).
 __device__ __forceinline__ double sum_partials(const float* part, size_t stride, int n, int start, int step) {
   double s = 0.0;
-  for (int b0 = start; b0 < n; b0 += step * BATCH) {
-    float v[BATCH];
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      const int b = b0 + k * step;
-      v[k] = b < n ? __ldcg(part + (size_t)b * stride) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k) s += (double)v[k];
-  }
+#pragma unroll 8
+  for (int b = start; b < n; b += step) s += (double)__ldcg(part + (size_t)b * stride);
   return s;
 }
 
@@ -152,19 +143,21 @@ __device__ __forceinline__ float warp_max(float v) {
 // "last CTA finalises" pattern: every CTA publishes its partials, the last one to arrive reduces
 // them in a fixed order (deterministic, no float atomics) and resets the counter for the next launch.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool last_cta_arrives(unsigned int* counter) {
+// (`ncta` = number of CTAs working on this problem: a launch may carry two independent problems, see GinFwdPair)
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* counter, unsigned int ncta) {
   __shared__ bool is_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int prev = atomicAdd(counter, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == ncta - 1);
     if (is_last) *counter = 0u;
   }
   __syncthreads();
   if (is_last) __threadfence();
   return is_last;
 }
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* counter) { return last_cta_arrives(counter, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Register-tiled FP32 tile GEMMs out of shared memory (256 threads).

@@ -60,8 +60,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <int KIN>
 __global__ void __launch_bounds__(kThreadsTotal, 1)
-gin_bwd_tc_kernel(GinBwdMainArgs p) {
+gin_bwd_tc_kernel(GinBwdMainPair pp) {
   using L = Smem<KIN>;
+  const bool second = (int)blockIdx.x >= pp.split;
+  const GinBwdMainArgs& p = pp.a[second ? 1 : 0];
+  const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
+  const int nblk = second ? (int)gridDim.x - pp.split : pp.split;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* X = smem + L::off_x;
   unsigned char* Y = smem + L::off_y;
@@ -71,8 +75,8 @@ gin_bwd_tc_kernel(GinBwdMainArgs p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::off_bar + B_COUNT * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.V + TM - 1) / TM;
-  const int my_tiles = max(0, (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
-  auto tile_base = [&](int i) { return ((int)blockIdx.x + i * (int)gridDim.x) * TM; };
+  const int my_tiles = max(0, (n_tiles - bid + nblk - 1) / nblk);
+  auto tile_base = [&](int i) { return (bid + i * nblk) * TM; };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[B_FULL1], kLoadWarps);
@@ -363,15 +367,26 @@ gin_bwd_tc_kernel(GinBwdMainArgs p) {
 }  // namespace bwdtc
 
 template <int KIN>
-static void launch_bwd_tc(const GinBwdMainArgs& a, int grid, cudaStream_t s) {
+static void launch_bwd_tc(const GinBwdMainPair& pp, int grid, cudaStream_t s) {
   using L = bwdtc::Smem<KIN>;
   static bool once = (cudaFuncSetAttribute(bwdtc::gin_bwd_tc_kernel<KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  bwdtc::gin_bwd_tc_kernel<KIN><<<grid, bwdtc::kThreadsTotal, L::total, s>>>(a);
+  bwdtc::gin_bwd_tc_kernel<KIN><<<grid, bwdtc::kThreadsTotal, L::total, s>>>(pp);
 }
 
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s) {
-  if (kin == DTR) launch_bwd_tc<DTR>(a, grid, s); else launch_bwd_tc<HID>(a, grid, s);
+  GinBwdMainPair pp;
+  pp.a[0] = a; pp.a[1] = a;
+  pp.split = grid;
+  if (kin == DTR) launch_bwd_tc<DTR>(pp, grid, s); else launch_bwd_tc<HID>(pp, grid, s);
+}
+
+// the same layer of both encoders in one launch: CTAs [0, split) write the partial gradients of a0, [split, grid) of a1
+void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s) {
+  GinBwdMainPair pp;
+  pp.a[0] = a0; pp.a[1] = a1;
+  pp.split = pair_split(grid, (a0.V + bwdtc::TM - 1) / bwdtc::TM, (a1.V + bwdtc::TM - 1) / bwdtc::TM);
+  if (kin == DTR) launch_bwd_tc<DTR>(pp, grid, s); else launch_bwd_tc<HID>(pp, grid, s);
 }
 
 }  // namespace scgib

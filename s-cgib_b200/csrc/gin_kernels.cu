@@ -239,7 +239,11 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
 // Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 2)
-gin_bwd_pre_kernel(GinBwdPreArgs p) {
+gin_bwd_pre_kernel(GinBwdPrePair pp) {
+  const bool second = (int)blockIdx.x >= pp.split;
+  const GinBwdPreArgs& p = pp.a[second ? 1 : 0];
+  const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
+  const int nblk = second ? (int)gridDim.x - pp.split : pp.split;
   __shared__ __align__(16) float s_red[16 * 2 * HID];
   __shared__ double s_d[2 * 2 * HID];
   const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
@@ -247,11 +251,11 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
   bn.load(p.bn, l * 4);
   float4 db = make4(0.f), dg = make4(0.f);
   constexpr int NR = 4;
-  for (int v0 = blockIdx.x * 16 + hw; v0 < p.V; v0 += gridDim.x * 16 * NR) {
+  for (int v0 = bid * 16 + hw; v0 < p.V; v0 += nblk * 16 * NR) {
     int vv[NR];
     float4 g[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) vv[j] = v0 + j * gridDim.x * 16;
+    for (int j = 0; j < NR; ++j) vv[j] = v0 + j * nblk * 16;
     float4 y[NR];   // issued first: independent of the gather's dependent index chain
 #pragma unroll
     for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
@@ -283,13 +287,13 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
     float s = 0.f;
 #pragma unroll
     for (int h = 0; h < 16; ++h) s += s_red[h * 2 * HID + threadIdx.x];
-    p.part[(size_t)blockIdx.x * 2 * HID + threadIdx.x] = s;
+    p.part[(size_t)bid * 2 * HID + threadIdx.x] = s;
   }
-  if (!last_cta_arrives(p.counter)) return;
+  if (!last_cta_arrives(p.counter, (unsigned)nblk)) return;
   // 256 threads: column j = tid & 127 (0..63 dbeta, 64..127 dgamma), 2 interleaved segments, batched loads
   {
     const int j = threadIdx.x & (2 * HID - 1), seg = threadIdx.x >> 7;
-    s_d[seg * 2 * HID + j] = sum_partials<16>(p.part + j, 2 * HID, (int)gridDim.x, seg, 2);
+    s_d[seg * 2 * HID + j] = sum_partials(p.part + j, 2 * HID, nblk, seg, 2);
   }
   __syncthreads();
   if (threadIdx.x < HID) {
@@ -307,7 +311,25 @@ gin_bwd_pre_kernel(GinBwdPreArgs p) {
 int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, 2 * num_sms()); }   // 2 resident CTAs per SM, 64 rows per pass
 
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s) {
-  gin_bwd_pre_kernel<<<gin_bwd_pre_grid(a.V), kThreads, 0, s>>>(a);
+  GinBwdPrePair pp;
+  pp.a[0] = a; pp.a[1] = a;
+  const int grid = gin_bwd_pre_grid(a.V);
+  pp.split = grid;
+  gin_bwd_pre_kernel<<<grid, kThreads, 0, s>>>(pp);
+}
+
+int pair_split(int grid, int work0, int work1) {
+  if (grid < 2) return grid;
+  int s0 = (int)(((long long)grid * work0 + (work0 + work1) / 2) / (work0 + work1));
+  return max(1, min(grid - 1, s0));
+}
+
+void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, cudaStream_t s) {
+  GinBwdPrePair pp;
+  pp.a[0] = a0; pp.a[1] = a1;
+  const int grid = max(2, gin_bwd_pre_grid(a0.V + a1.V));
+  pp.split = pair_split(grid, a0.V, a1.V);
+  gin_bwd_pre_kernel<<<grid, kThreads, 0, s>>>(pp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -517,7 +539,9 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
   for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
   if (!last_cta_arrives(p.counter)) return;
   for (int idx = threadIdx.x; idx < DTR * FP; idx += kThreads) {
-    const double s = sum_partials<16>(p.part + idx, DTR * FP, (int)gridDim.x, 0, 1);
+    double s = 0.0;
+#pragma unroll 8
+    for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(p.part + (size_t)b * DTR * FP + idx);
     const int oo = idx / FP, f = idx % FP;
     if (f < p.F) p.d_Wt[oo * p.F + f] = (float)s;
   }

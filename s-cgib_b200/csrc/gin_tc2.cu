@@ -73,8 +73,12 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 template <int KIN, int PW>
 __global__ void __launch_bounds__((kEpiWarps + 1 + PW) * 32, 1)
-gin_fwd_tc2_kernel(GinFwdArgs p) {
+gin_fwd_tc2_kernel(GinFwdPair pp) {
   using L = Smem<KIN>;
+  const bool second = (int)blockIdx.x >= pp.split;
+  const GinFwdArgs& p = pp.a[second ? 1 : 0];
+  const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
+  const int nblk = second ? (int)gridDim.x - pp.split : pp.split;
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_b1 = reinterpret_cast<float*>(smem + L::off_f);
   float* s_b2 = s_b1 + HID;
@@ -84,7 +88,7 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::off_bar + B_COUNT * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.V + TM - 1) / TM;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x + i*gridDim.x
+  const int my_tiles = (n_tiles - bid + nblk - 1) / nblk;   // tiles bid + i*nblk
 
   // ---- one-time setup: barriers, TMEM, weights (natural [out][in] = K-major B operand, dense cores), biases
   if (threadIdx.x == 0) {
@@ -128,7 +132,7 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
     const bool has_bn = (p.bn_in != nullptr);
     if (has_bn) bn.load(p.bn_in, gl * 4);
     auto act = [&](float4 h) { return has_bn ? bn.act(h) : h; };
-    auto tile_base = [&](int i) { return ((int)blockIdx.x + i * (int)gridDim.x) * TM; };
+    auto tile_base = [&](int i) { return (bid + i * nblk) * TM; };
     auto prod_sync = [&]() { asm volatile("bar.sync 1, %0;" :: "n"(PT) : "memory"); };
     // indptr slice, mapped self rows and (unmapped) neighbour rows of a tile -> index buffer `buf`, asynchronously
     // (cp.async: no register staging, nothing waits until the end of the iteration)
@@ -267,7 +271,7 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
     double run_n = 0.0, run_mean[2] = {0.0, 0.0}, run_m2[2] = {0.0, 0.0};   // columns lane, 32 + lane
     auto epi1 = [&](int i) {
       const int s = i & 1, use = i >> 1;
-      const int gv = ((int)blockIdx.x + i * (int)gridDim.x) * TM + row;
+      const int gv = (bid + i * nblk) * TM + row;
       mbar_wait(&bars[B_D1 + s], (uint32_t)(use & 1));
       fence_after_sync();
       const uint32_t t0 = tmem + s * 256 + tl;
@@ -297,7 +301,7 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
     };
     auto epi2 = [&](int i) {
       const int s = i & 1, use = i >> 1;
-      const int base = ((int)blockIdx.x + i * (int)gridDim.x) * TM;
+      const int base = (bid + i * nblk) * TM;
       const int gv = base + row;
       const bool valid = gv < p.V;
       const int cnt = max(0, min(32, p.V - (base + warp * 32)));   // valid rows of this warp (warp-uniform)
@@ -377,10 +381,10 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
         n = nt;
       }
     }
-    double* part = reinterpret_cast<double*>(p.part) + (size_t)blockIdx.x * 3 * HID;
+    double* part = reinterpret_cast<double*>(p.part) + (size_t)bid * 3 * HID;
     part[c] = n; part[HID + c] = mean; part[2 * HID + c] = m2;
   }
-  if ((p.dbg & 256) || !last_cta_arrives(p.counter)) return;
+  if ((p.dbg & 256) || !last_cta_arrives(p.counter, (unsigned)nblk)) return;
   // ---- batch statistics: the last CTA combines the per-CTA partials in fp64.  Thread (c, seg) first LOADS its partials
   //      (independent loads, one L2 latency), then Chan-combines them in a fixed order; 8 segments, then a serial 8-way.
   {
@@ -390,12 +394,12 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
     double* s_comb = reinterpret_cast<double*>(smem);        // [SEGS][3][HID] (the stages are dead by now)
     if (seg < SEGS) {
       double n = 0.0, mean = 0.0, m2 = 0.0;
-      for (int b0 = seg; b0 < (int)gridDim.x; b0 += SEGS * BATCH) {
+      for (int b0 = seg; b0 < nblk; b0 += SEGS * BATCH) {
         double pn[BATCH], pm[BATCH], pq[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {                    // independent loads first ...
           const int b = b0 + k * SEGS;
-          const bool ok = b < (int)gridDim.x;
+          const bool ok = b < nblk;
           pn[k] = ok ? __ldcg(part + (size_t)b * 3 * HID + c) : 0.0;
           pm[k] = ok ? __ldcg(part + (size_t)b * 3 * HID + HID + c) : 0.0;
           pq[k] = ok ? __ldcg(part + (size_t)b * 3 * HID + 2 * HID + c) : 0.0;
@@ -438,24 +442,43 @@ gin_fwd_tc2_kernel(GinFwdArgs p) {
 }  // namespace tc2
 
 template <int KIN, int PW>
-static void launch_tc2(const GinFwdArgs& a, cudaStream_t s) {
+static void launch_tc2(const GinFwdPair& pp, int grid, cudaStream_t s) {
   using L = tc2::Smem<KIN>;
   static bool once = (cudaFuncSetAttribute(tc2::gin_fwd_tc2_kernel<KIN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  const int n_tiles = (a.V + tc2::TM - 1) / tc2::TM;
-  const int grid = min(n_tiles, num_sms());
   constexpr int threads = (tc2::kEpiWarps + 1 + PW) * 32;
-  tc2::gin_fwd_tc2_kernel<KIN, PW><<<grid, threads, L::total, s>>>(a);
+  tc2::gin_fwd_tc2_kernel<KIN, PW><<<grid, threads, L::total, s>>>(pp);
+}
+
+static int dbg_mask() {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("SCGIB_DBG"); dbg = e ? atoi(e) : 0; }
+  return dbg;
+}
+
+static void launch_tc2_any(GinFwdPair& pp, int grid, int kin, int variant, cudaStream_t s) {
+  pp.a[0].dbg = pp.a[1].dbg = dbg_mask();
+  if (kin == DTR) { if (variant == 2) launch_tc2<DTR, 16>(pp, grid, s); else launch_tc2<DTR, 8>(pp, grid, s); }
+  else { if (variant == 2) launch_tc2<HID, 16>(pp, grid, s); else launch_tc2<HID, 8>(pp, grid, s); }
 }
 
 // variant 1: 8 producer warps, variant 2: 16 producer warps
-void launch_gin_fwd_tc2(const GinFwdArgs& a_, int kin, int variant, cudaStream_t s) {
-  GinFwdArgs a = a_;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("SCGIB_DBG"); dbg = e ? atoi(e) : 0; }
-  a.dbg = dbg;
-  if (kin == DTR) { if (variant == 2) launch_tc2<DTR, 16>(a, s); else launch_tc2<DTR, 8>(a, s); }
-  else { if (variant == 2) launch_tc2<HID, 16>(a, s); else launch_tc2<HID, 8>(a, s); }
+void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s) {
+  GinFwdPair pp;
+  pp.a[0] = a; pp.a[1] = a;
+  const int grid = min((a.V + tc2::TM - 1) / tc2::TM, num_sms());
+  pp.split = grid;                                   // single problem: every CTA works on a[0]
+  launch_tc2_any(pp, grid, kin, variant, s);
+}
+
+// the same layer of both encoders in one launch (separate part / counter / bn_out buffers per problem)
+void launch_gin_fwd_tc2_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, int variant, cudaStream_t s) {
+  GinFwdPair pp;
+  pp.a[0] = a0; pp.a[1] = a1;
+  const int t0 = (a0.V + tc2::TM - 1) / tc2::TM, t1 = (a1.V + tc2::TM - 1) / tc2::TM;
+  const int grid = min(t0 + t1, num_sms());
+  pp.split = pair_split(grid, t0, t1);
+  launch_tc2_any(pp, grid, kin, variant, s);
 }
 
 }  // namespace scgib

@@ -30,11 +30,16 @@ struct GinFwdArgs {
   float* running;                     // optional {running_mean, running_var}[HID]
   int dbg = 0;                        // gin_tc2 experiments (SCGIB_DBG bit mask): 1 no r/y stores, 2 no stats, 4 no gather loads, 8 no a store
 };
+// Two independent problems of the same shape class (the same layer of Encoder1 and Encoder2) in ONE launch: CTAs
+// [0, split) work on a[0], CTAs [split, grid) on a[1]; split is chosen proportional to the tile counts, so the 148
+// persistent CTAs are balanced over both row sets and the per-launch fixed costs are paid once.
+struct GinFwdPair { GinFwdArgs a[2]; int split; };
 int gin_fwd_grid(int V);
 void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
 int gin_fwd_tc_tiles(int V);
 void launch_gin_fwd_tc(const GinFwdArgs& a, int kin, cudaStream_t s);     // tcgen05 3xTF32 (gin_tc.cu)
-void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int groups, cudaStream_t s);  // warp-specialised tcgen05 (gin_tc2.cu)
+void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s);  // warp-specialised tcgen05 (gin_tc2.cu)
+void launch_gin_fwd_tc2_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, int variant, cudaStream_t s);
 int tensor_core_mode();                                                   // SCGIB_TC: 0 FFMA, 1 gin_tc.cu, 2/3 gin_tc2.cu (1/2 producer groups)
 inline bool use_tensor_cores() { return tensor_core_mode() != 0; }
 
@@ -52,8 +57,11 @@ struct GinBwdPreArgs {
   float *d_gamma, *d_beta;  // [HID] final gradients
   float* cvec;              // {c1, c2}[HID]
 };
+struct GinBwdPrePair { GinBwdPreArgs a[2]; int split; };
 int gin_bwd_pre_grid(int V);
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s);
+void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, cudaStream_t s);   // grid = gin_bwd_pre_grid(V0 + V1)
+int pair_split(int grid, int work0, int work1);     // CTAs given to problem 0
 
 struct GinBwdMainArgs {
   const float *g_o, *y, *r, *a;
@@ -66,7 +74,9 @@ struct GinBwdMainArgs {
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
+struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; };
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
+void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 tcgen05 (default)
 
 struct InputProjBwdArgs {
@@ -218,7 +228,7 @@ struct LossFinalizeArgs {
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s);
 
 // grads[off..off+len) = sum_c part[c*pstride + off + i] for each listed range
-struct ReduceRanges { int64_t off[40]; int64_t len[40]; int n; };
+struct ReduceRanges { int64_t off[40]; int64_t len[40]; int c0[40]; int c1[40]; int n; };   // partial rows [c0, c1) hold the range
 void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
                             cudaStream_t s);
 

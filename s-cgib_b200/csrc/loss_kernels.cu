@@ -379,9 +379,11 @@ void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_fina
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_kernel(const float* __restrict__ part, int64_t pstride, int nparts, ReduceRanges r, float* __restrict__ grads) {
   const int64_t off = r.off[blockIdx.y], len = r.len[blockIdx.y];
+  const int c0 = r.c0[blockIdx.y], c1 = min(r.c1[blockIdx.y], nparts);
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (int64_t)gridDim.x * kThreads) {
     double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += (double)part[(size_t)c * pstride + off + i];
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) s += (double)part[(size_t)c * pstride + off + i];
     grads[off + i] = (float)s;
   }
 }
