@@ -111,6 +111,11 @@ def cpu_reference_run(steps, warmup, batch=128, k=1):
         data.append((tgraph_from_ref(g), x, tgraph_from_ego(e), x[en]))
     for i in range(warmup):
         oracle_train_step(model, opt, *data[i % 2])
+    if steps is None:                      # bounded sample: about 12 s of CPU work
+        t0 = time.perf_counter()
+        for i in range(3):
+            oracle_train_step(model, opt, *data[i % 2])
+        steps = max(10, min(400, int(12.0 / ((time.perf_counter() - t0) / 3))))
     t0 = time.perf_counter()
     for i in range(steps):
         oracle_train_step(model, opt, *data[i % 2])
@@ -120,7 +125,7 @@ def cpu_reference_run(steps, warmup, batch=128, k=1):
                       "recon, %.1f s wall" % (steps, batch, dt)}, dt / steps * 1e3
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     if rank != 0:
         return
     base, ms = cpu_reference_run(args.steps, args.warmup, batch=128, k=args.k)
@@ -132,7 +137,7 @@ def run_reference(args, rank):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -146,11 +151,21 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -282,14 +297,15 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes,
-                         "note": "FP32-FFMA tile GEMMs dominate this kernel; see DESIGN.md (compute roof 74.4 TFLOP/s)"},
+                         "note": "warp-specialised tcgen05 3xTF32 kernel (MLP GEMMs on the tensor pipe); bytes = SURVEY 8(d) "
+                                 "per-layer figure of both encoders' rows in the launch; see DESIGN.md section 3"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "peak": hbm, "unit": "GB/s", "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm},
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_reference_run(20, 3, batch=128, k=args.k)
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline"], _ = cpu_reference_run(None, 3, batch=128, k=args.k)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

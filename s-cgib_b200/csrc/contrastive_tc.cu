@@ -126,7 +126,7 @@ contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
         for (int j = 0; j < 16; ++j) {
           const int gj = jbase + hcol + c16 * 16 + j;
           const bool use = (gj < p.B) && (part == 1 || gj != gi);
-          rs += use ? expf(v[j]) : 0.f;
+          rs += use ? __expf(v[j]) : 0.f;   // |s| <= 1: ex2.approx is good to ~2e-7 relative
         }
       }
     }
@@ -189,160 +189,175 @@ contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::off_bar + 32);
   const size_t n = (size_t)p.B * HID;
   const float *z1h = zsplit, *z1l = zsplit + n, *z2h = zsplit + 2 * n, *z2l = zsplit + 3 * n;
-  const bool mode1 = (blockIdx.z == 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ibase = blockIdx.x * CI;
   const int jblocks = (p.B + CJ - 1) / CJ;
   const int nblk = (jblocks - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
   auto jb_of = [&](int t) { return ((int)blockIdx.y + t * (int)gridDim.y) * CJ; };
-  auto load_j = [&](int t) {
-    unsigned char* buf = zj + (t & 1) * 4 * ZS_BYTES;
-    const int jbase = jb_of(t);
-    cp_async_tile_s<CJ>(buf, z1h, jbase, p.B);
-    cp_async_tile_s<CJ>(buf + ZS_BYTES, z1l, jbase, p.B);
-    if (!mode1) {
-      cp_async_tile_s<CJ>(buf + 2 * ZS_BYTES, z2h, jbase, p.B);
-      cp_async_tile_s<CJ>(buf + 3 * ZS_BYTES, z2l, jbase, p.B);
-    }
-    if (threadIdx.x < CJ) s_dj[(t & 1) * CJ + threadIdx.x] = (jbase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + jbase + threadIdx.x) : 0.f;
-  };
 
   if (warp == 0) tmem_alloc(s_tmem, 512);
   if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1); }
-  cp_async_tile_g<CI>(zi_hi, mode1 ? z2h : z1h, ibase, p.B);
-  cp_async_tile_g<CI>(zi_lo, mode1 ? z2l : z1l, ibase, p.B);
-  if (threadIdx.x < CI) s_di[threadIdx.x] = (ibase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + ibase + threadIdx.x) : 0.f;
-  if (nblk > 0) load_j(0);
-  cp_async_commit();
-  if (nblk > 1) load_j(1);
-  cp_async_commit();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *s_tmem;
   const uint32_t zih = smem_u32(zi_hi), zil = smem_u32(zi_lo);
-  // similarity GEMMs of block t into S set t&1 (whole warp 0 runs this; one elected lane issues)
-  auto issue_sim = [&](int t) {
-    const uint32_t buf = smem_u32(zj + (t & 1) * 4 * ZS_BYTES);
-    const uint32_t d = tmem + (t & 1) * 128;
-    const int nsim = mode1 ? 1 : 2;
-    for (int q = 0; q < nsim; ++q) {
-      const uint32_t bh = buf + q * 2 * ZS_BYTES, bl = bh + ZS_BYTES;
-#pragma unroll
-      for (int k = 0; k < HID / 8; ++k) {
-        const uint64_t ah = desc_g_dense(zih, HID, k), al = desc_g_dense(zil, HID, k);
-        const uint64_t dbh = desc_s_kmajor(bh, CJ, k), dbl = desc_s_kmajor(bl, CJ, k);
-        mma_tf32_w(d + q * 64, al, dbh, kIdSim, k > 0);
-        mma_tf32_w(d + q * 64, ah, dbl, kIdSim, true);
-        mma_tf32_w(d + q * 64, ah, dbh, kIdSim, true);
-      }
-    }
-    mma_commit_w(&s_bar[t & 1]);
-  };
-  // acc += P Zcol for source q (0: z1 tile, 1: z2 tile) of block t; P (hi | lo) is in tensor memory
-  auto issue_pv = [&](int t, int q, bool first) {
-    const uint32_t bh = smem_u32(zj + (t & 1) * 4 * ZS_BYTES) + q * 2 * ZS_BYTES;
-#pragma unroll
-    for (int k = 0; k < CJ / 8; ++k) {
-      const uint64_t b = desc_s_mnmajor(bh, CJ, k);
-      mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 8 * k, b, kIdPVa, !(first && k == 0));
-      mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 64 + 8 * k, b, kIdPVb, true);
-    }
-    mma_commit_w(&s_bar[2]);
-  };
-  asm volatile("cp.async.wait_group 1;" ::: "memory");
-  fence_smem_to_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  if (warp == 0 && nblk > 0) issue_sim(0);
-
   const int row = 32 * (warp & 3) + lane;              // TMEM lane = row of the 128-row block
   const int hcol = (warp >> 2) * 32;                   // this thread's half of the 64 columns
   const int gi = ibase + row;
   const uint32_t tl = (uint32_t)(32 * (warp & 3)) << 16;
-  const float di = s_di[row];
+  int sim_n[2] = {0, 0};                               // completed waits per S set (mbarrier phase bookkeeping)
   int pv_issued = 0, pv_waited = 0;                    // PV GEMM groups committed / observed complete (block-uniform)
   auto wait_pv = [&]() {                               // every committed PV GEMM has completed (P and its column tile are free)
     while (pv_waited < pv_issued) { mbar_wait(&s_bar[2], (uint32_t)(pv_waited & 1)); ++pv_waited; }
     fence_after_sync();
   };
-  // one weighted-probability block: S (32 columns of this thread) -> P hi/lo in tensor memory
-  auto make_p = [&](uint32_t s_addr, int jbase, const float* dj, int kind) {   // kind 0: refl (z1 z1), 1: between, 2: mode 1
-    float v[32];
-    tmem_ld16_nowait(s_addr, *reinterpret_cast<float (*)[16]>(v));
-    tmem_ld16_nowait(s_addr + 16, *reinterpret_cast<float (*)[16]>(v + 16));
-    tmem_ld_wait();
+
+  // Both gradient halves in one CTA (balanced work, single wave): mode 0 = rows of z1 (g1), mode 1 = rows of z2 (g2)
+  for (int mode = 0; mode < 2; ++mode) {
+    const bool mode1 = (mode == 1);
+    auto load_j = [&](int t) {
+      unsigned char* buf = zj + (t & 1) * 4 * ZS_BYTES;
+      const int jbase = jb_of(t);
+      cp_async_tile_s<CJ>(buf, z1h, jbase, p.B);
+      cp_async_tile_s<CJ>(buf + ZS_BYTES, z1l, jbase, p.B);
+      if (!mode1) {
+        cp_async_tile_s<CJ>(buf + 2 * ZS_BYTES, z2h, jbase, p.B);
+        cp_async_tile_s<CJ>(buf + 3 * ZS_BYTES, z2l, jbase, p.B);
+      }
+      if (threadIdx.x < CJ) s_dj[(t & 1) * CJ + threadIdx.x] = (jbase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + jbase + threadIdx.x) : 0.f;
+    };
+    // similarity GEMMs of block t into S set t&1 (whole warp 0 runs this; one elected lane issues)
+    auto issue_sim = [&](int t) {
+      const uint32_t buf = smem_u32(zj + (t & 1) * 4 * ZS_BYTES);
+      const uint32_t d = tmem + (t & 1) * 128;
+      const int nsim = mode1 ? 1 : 2;
+      for (int q = 0; q < nsim; ++q) {
+        const uint32_t bh = buf + q * 2 * ZS_BYTES, bl = bh + ZS_BYTES;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int gj = jbase + hcol + j;
-      float w;
-      if (kind == 0) w = (gj != gi) ? di + dj[hcol + j] : 0.f;
-      else if (kind == 1) w = di;
-      else w = dj[hcol + j];
-      v[j] = (gj < p.B && gi < p.B) ? expf(v[j]) * w : 0.f;
-    }
-    wait_pv();                                         // the previous P has been consumed before it is overwritten
+        for (int k = 0; k < HID / 8; ++k) {
+          const uint64_t ah = desc_g_dense(zih, HID, k), al = desc_g_dense(zil, HID, k);
+          const uint64_t dbh = desc_s_kmajor(bh, CJ, k), dbl = desc_s_kmajor(bl, CJ, k);
+          mma_tf32_w(d + q * 64, al, dbh, kIdSim, k > 0);
+          mma_tf32_w(d + q * 64, ah, dbl, kIdSim, true);
+          mma_tf32_w(d + q * 64, ah, dbh, kIdSim, true);
+        }
+      }
+      mma_commit_w(&s_bar[t & 1]);
+    };
+    // acc += P Zcol for source q (0: z1 tile, 1: z2 tile) of block t; P (hi | lo) is in tensor memory
+    auto issue_pv = [&](int t, int q, bool first) {
+      const uint32_t bh = smem_u32(zj + (t & 1) * 4 * ZS_BYTES) + q * 2 * ZS_BYTES;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { hi[j] = tf32_rna(v[16 * c + j]); lo[j] = tf32_rna(v[16 * c + j] - hi[j]); }
-      tmem_st16(tmem + tl + kColP + hcol + 16 * c, hi);
-      tmem_st16(tmem + tl + kColP + 64 + hcol + 16 * c, lo);
-    }
-    tmem_st_wait();
-  };
-  for (int t = 0; t < nblk; ++t) {
-    // A. block t+1 has landed -> its similarity GEMMs go into the other S set (consumed two iterations ago)
-    cp_async_wait_all();
+      for (int k = 0; k < CJ / 8; ++k) {
+        const uint64_t b = desc_s_mnmajor(bh, CJ, k);
+        mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 8 * k, b, kIdPVa, !(first && k == 0));
+        mma_tf32_ta_w(tmem + kColAcc, tmem + kColP + 64 + 8 * k, b, kIdPVb, true);
+      }
+      mma_commit_w(&s_bar[2]);
+    };
+    // ---- prologue of the mode: row tile (all earlier MMAs have completed: see the end of the loop body) + two column blocks
+    cp_async_tile_g<CI>(zi_hi, mode1 ? z2h : z1h, ibase, p.B);
+    cp_async_tile_g<CI>(zi_lo, mode1 ? z2l : z1l, ibase, p.B);
+    if (mode == 0 && threadIdx.x < CI) s_di[threadIdx.x] = (ibase + threadIdx.x < p.B) ? 1.f / __ldg(p.D + ibase + threadIdx.x) : 0.f;
+    if (nblk > 0) load_j(0);
+    cp_async_commit();
+    if (nblk > 1) load_j(1);
+    cp_async_commit();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     fence_smem_to_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (warp == 0 && t + 1 < nblk) issue_sim(t + 1);
-    // B. similarities of block t are in tensor memory
-    mbar_wait(&s_bar[t & 1], (uint32_t)((t >> 1) & 1));
-    fence_after_sync();
-    const int jbase = jb_of(t);
-    const float* dj = s_dj + (t & 1) * CJ;
-    const uint32_t sset = tmem + tl + (t & 1) * 128 + hcol;
-    const int nsrc = mode1 ? 1 : 2;
-    for (int q = 0; q < nsrc; ++q) {
-      make_p(sset + q * 64, jbase, dj, mode1 ? 2 : q);
+    if (warp == 0 && nblk > 0) issue_sim(0);
+    const float di = s_di[row];
+    int pv_in_mode = 0;
+    // one weighted-probability block: S (32 columns of this thread) -> P hi/lo in tensor memory
+    auto make_p = [&](uint32_t s_addr, int jbase, const float* dj, int kind) {   // kind 0: refl (z1 z1), 1: between, 2: mode 1
+      float v[32];
+      tmem_ld16_nowait(s_addr, *reinterpret_cast<float (*)[16]>(v));
+      tmem_ld16_nowait(s_addr + 16, *reinterpret_cast<float (*)[16]>(v + 16));
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gj = jbase + hcol + j;
+        float w;
+        if (kind == 0) w = (gj != gi) ? di + dj[hcol + j] : 0.f;
+        else if (kind == 1) w = di;
+        else w = dj[hcol + j];
+        v[j] = (gj < p.B && gi < p.B) ? __expf(v[j]) * w : 0.f;   // |s| <= 1: ex2.approx is good to ~2e-7 relative
+      }
+      wait_pv();                                         // the previous P has been consumed before it is overwritten
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { hi[j] = tf32_rna(v[16 * c + j]); lo[j] = tf32_rna(v[16 * c + j] - hi[j]); }
+        tmem_st16(tmem + tl + kColP + hcol + 16 * c, hi);
+        tmem_st16(tmem + tl + kColP + 64 + hcol + 16 * c, lo);
+      }
+      tmem_st_wait();
+    };
+    for (int t = 0; t < nblk; ++t) {
+      // A. block t+1 has landed (its similarity GEMMs, into the other S set, are issued after the first PV GEMM below)
+      cp_async_wait_all();
+      fence_smem_to_async();
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (warp == 0) issue_pv(t, q, pv_issued == 0);
-      ++pv_issued;
+      // B. similarities of block t are in tensor memory
+      mbar_wait(&s_bar[t & 1], (uint32_t)(sim_n[t & 1] & 1));
+      ++sim_n[t & 1];
+      fence_after_sync();
+      const int jbase = jb_of(t);
+      const float* dj = s_dj + (t & 1) * CJ;
+      const uint32_t sset = tmem + tl + (t & 1) * 128 + hcol;
+      const int nsrc = mode1 ? 1 : 2;
+      for (int q = 0; q < nsrc; ++q) {
+        make_p(sset + q * 64, jbase, dj, mode1 ? 2 : q);
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (warp == 0) {
+          issue_pv(t, q, pv_in_mode == 0);
+          // the similarity GEMMs of block t+1 queue BEHIND the first PV GEMM of block t (the tensor pipe is in order):
+          // the next make_p waits for a short PV, and its exponentials overlap the long similarity GEMMs
+          if (q == 0 && t + 1 < nblk) issue_sim(t + 1);
+        }
+        ++pv_issued;
+        ++pv_in_mode;
+      }
+      // C. stage t&1 is free once the PV GEMMs of block t have completed: prefetch block t+2 into it
+      if (t + 2 < nblk) { wait_pv(); load_j(t + 2); }
+      cp_async_commit();
     }
-    // C. stage t&1 is free once the PV GEMMs of block t have completed: prefetch block t+2 into it
-    if (t + 2 < nblk) { wait_pv(); load_j(t + 2); }
-    cp_async_commit();
-  }
-  // ---- result rows: acc = columns 0..63 + columns 64..127
-  float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
-  if (nblk > 0) {
-    wait_pv();
-    float a0[32], a1[32];
-    tmem_ld16_nowait(tmem + tl + kColAcc + hcol, *reinterpret_cast<float (*)[16]>(a0));
-    tmem_ld16_nowait(tmem + tl + kColAcc + hcol + 16, *reinterpret_cast<float (*)[16]>(a0 + 16));
-    tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol, *reinterpret_cast<float (*)[16]>(a1));
-    tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol + 16, *reinterpret_cast<float (*)[16]>(a1 + 16));
-    tmem_ld_wait();
+    // ---- result rows of this mode: acc = columns 0..63 + columns 64..127
+    float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
+    if (nblk > 0) {
+      wait_pv();
+      float a0[32], a1[32];
+      tmem_ld16_nowait(tmem + tl + kColAcc + hcol, *reinterpret_cast<float (*)[16]>(a0));
+      tmem_ld16_nowait(tmem + tl + kColAcc + hcol + 16, *reinterpret_cast<float (*)[16]>(a0 + 16));
+      tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol, *reinterpret_cast<float (*)[16]>(a1));
+      tmem_ld16_nowait(tmem + tl + kColAcc + 64 + hcol + 16, *reinterpret_cast<float (*)[16]>(a1 + 16));
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a0[j] += a1[j];
-    if (gi < p.B) {
+      for (int j = 0; j < 32; ++j) a0[j] += a1[j];
+      if (gi < p.B) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, a0 + 8 * j);
+        for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, a0 + 8 * j);
+      }
+    } else if (gi < p.B) {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, z);
     }
-  } else if (gi < p.B) {
-    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) st8(out + (size_t)gi * HID + hcol + 8 * j, z);
+    // every MMA of this mode has completed (wait_pv covers the similarity GEMMs too: in-order completion) and every
+    // thread has read its accumulator rows before the next mode overwrites tiles and tensor memory
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
   }
-  fence_before_sync();
-  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -358,7 +373,7 @@ void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit,
   static bool once = (cudaFuncSetAttribute(contrastive_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ConBwdTcLayout::total), true);
   (void)once;
-  dim3 grid((a.B + CI - 1) / CI, a.jsplit, 2);
+  dim3 grid((a.B + CI - 1) / CI, a.jsplit);
   contrastive_bwd_tc_kernel<<<grid, kThreads, ConBwdTcLayout::total, s>>>(a, zsplit);
 }
 

@@ -166,9 +166,11 @@ void launch_normalize(const NormalizeArgs& a, cudaStream_t s) {
 }
 
 int contrastive_jsplit(int B) {
-  const int iblocks = (B + CT - 1) / CT;
-  int js = (2 * num_sms() + iblocks - 1) / iblocks;
-  const int jblocks = iblocks;
+  // The tcgen05 kernels (contrastive_tc.cu) run one CTA per SM on 128-row blocks: split the column range so that
+  // (row blocks) x (splits) fills the SMs in a single wave.  The FFMA kernels (64-row blocks, 2 CTAs per SM) accept the same value.
+  const int iblocks = (B + 127) / 128;
+  int js = num_sms() / iblocks;
+  const int jblocks = (B + CT - 1) / CT;
   if (js > jblocks) js = jblocks;
   if (js < 1) js = 1;
   return js;
