@@ -22,6 +22,14 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {
   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
                "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
+// streaming variants (L2 evict-first): tensors saved for the backward pass / read exactly once must not push the next
+// layer's gather source out of L2
+__device__ __forceinline__ void st8_cs(float* p, const float* v) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 ld4_cs(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 make4(float a) { return make_float4(a, a, a, a); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 relu4(float4 a) {

@@ -133,8 +133,8 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
         const bool ok = v < p.V;
         const size_t o = (size_t)(ok ? v : 0) * HID + c;
         go[j] = ok ? ld4(p.g_o + o) : make4(0.f);
-        yy[j] = ok ? ld4(p.y + o) : make4(0.f);
-        rr[j] = ok ? ld4(p.r + o) : make4(0.f);
+        yy[j] = ok ? ld4_cs(p.y + o) : make4(0.f);
+        rr[j] = ok ? ld4_cs(p.r + o) : make4(0.f);
       }
       if (i + 1 < my_tiles) {                                 // next tile -> L2: 256 lines of 128 B per [128][64] tile
         const int nb = tile_base(i + 1), line = pt & 255;
@@ -181,7 +181,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
 #pragma unroll
       for (int j = 0; j < ANR; ++j) {
         const int v = base + ar + j * ARPP;
-        aa[j] = v < p.V ? ld4(p.a + (size_t)v * KIN + al * 4) : make4(0.f);
+        aa[j] = v < p.V ? ld4_cs(p.a + (size_t)v * KIN + al * 4) : make4(0.f);
       }
       mbar_wait(&bars[B_D1], (uint32_t)(i & 1));
 #pragma unroll

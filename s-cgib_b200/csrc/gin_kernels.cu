@@ -258,7 +258,7 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
     for (int j = 0; j < NR; ++j) vv[j] = v0 + j * nblk * 16;
     float4 y[NR];   // issued first: independent of the gather's dependent index chain
 #pragma unroll
-    for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
+    for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4_cs(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
     if (p.indptr) {
       gather_aggregate<HID, NR>(p.src, nullptr, p.indptr, p.indices, p.V, vv, l, nullptr, g);
     } else {

@@ -23,6 +23,10 @@
 namespace scgib {
 using namespace umma;
 
+// per-tile role timestamps (SCGIB_DBG bit 1024; experiments only): [cta][tile < 16][event < 12] SM clock values
+__device__ long long g_tc2_trace[160 * 16 * 12];
+#define TC2_TRACE(ev, tile) do { if ((p.dbg & 1024) && (tile) < 16 && blockIdx.x < 160) g_tc2_trace[((size_t)blockIdx.x * 16 + (tile)) * 12 + (ev)] = clock64(); } while (0)
+
 namespace tc2 {
 constexpr int TM = 128;                       // rows per tile = UMMA M
 constexpr int kEpiWarps = 4;
@@ -34,8 +38,10 @@ constexpr int kStageBytes = 2 * TM * HID * 4; // hi + lo tile of one stage (form
 // is, N = 128 costs 64: measured with tests/gpu_umma_time.py.)
 constexpr uint32_t kIdesc = idesc_tf32(TM, HID, false, false);
 constexpr uint32_t kIdesc2 = idesc_tf32(TM, 2 * HID, false, false);
-// TMEM columns of stage s (base + 256 s): D (128; GEMM1 then GEMM2) | r_hi | r_lo
-constexpr int kColD1 = 0, kColD2 = 0, kColRhi = 128, kColRlo = 192;
+// TMEM columns of stage s (base + 256 s): D1 (128 columns: hi*hi | hi*lo halves) | D2 (128).  Epilogue 1 overwrites D1
+// IN PLACE with r_hi (columns 0..63) and r_lo (64..127) - every thread has read both halves of its row chunk before it
+// stores - so GEMM1 of the next user of the stage depends only on the in-order tensor pipe, not on epilogue 2.
+constexpr int kColD1 = 0, kColRhi = 0, kColRlo = 64, kColD2 = 128;
 
 template <int KIN>
 struct Smem {
@@ -158,64 +164,74 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
       const int* ip = s_ip + s * (TM + 4);
       const int* ix = s_ix + s * kIdxCap;
       const int e_begin = ip[0];
+      if (pt == 0) TC2_TRACE(0, i);
       auto nbr = [&](int e) {                                  // mapped neighbour row of tile-relative edge e
         const int u = (e < kIdxCap) ? ix[e] : __ldg(p.indices + e_begin + e);
         return p.row_map ? __ldg(p.row_map + u) : u;
       };
-      // ---- [A] self row + first two neighbour rows of every row of this thread: all loads in flight together
-      int deg[NR], eoff[NR];
-      float4 h0[NR], h1[NR], h2[NR];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int r = gr + j * RPP, v = base + r;
-        const bool ok = v < p.V && !(p.dbg & 4);
-        const int p0 = ip[r], p1 = ip[r + 1];
-        deg[j] = ok ? p1 - p0 : 0;
-        eoff[j] = p0 - e_begin;
-        const int sv = p.row_map ? s_self[s * TM + r] : v;
-        h0[j] = ok ? ld4(p.in + (size_t)sv * KIN + gl * 4) : make4(0.f);
-        h1[j] = deg[j] > 0 ? ld4(p.in + (size_t)nbr(eoff[j]) * KIN + gl * 4) : make4(0.f);
-        h2[j] = deg[j] > 1 ? ld4(p.in + (size_t)nbr(eoff[j] + 1) * KIN + gl * 4) : make4(0.f);
-      }
-      // ---- [B] stage the next tile's indices while those loads are in flight; fetch the range of the tile after it
-      if (i + 1 < my_tiles) {
-        stage_indices((i + 1) & 1, tile_base(i + 1), nb_begin, nb_end);
-        if (i + 2 < my_tiles) { const int b2 = tile_base(i + 2); nb_begin = __ldg(p.indptr + b2); nb_end = __ldg(p.indptr + min(b2 + TM, p.V)); }
-      }
-      // ---- [C] a_v = f(h_v) + sum_u f(h_u), neighbours in CSR order (same summation order as gin_fwd_kernel)
-      float4 agg[NR];
-      int maxd = 0;
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        agg[j] = (base + gr + j * RPP < p.V) ? act(h0[j]) : make4(0.f);
-        if (deg[j] > 0) agg[j] = add4(agg[j], act(h1[j]));
-        if (deg[j] > 1) agg[j] = add4(agg[j], act(h2[j]));
-        maxd = max(maxd, deg[j]);
-      }
-      for (int d = 2; d < maxd; d += 2) {                      // rows with more than two neighbours
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          h1[j] = deg[j] > d ? ld4(p.in + (size_t)nbr(eoff[j] + d) * KIN + gl * 4) : make4(0.f);
-          h2[j] = deg[j] > d + 1 ? ld4(p.in + (size_t)nbr(eoff[j] + d + 1) * KIN + gl * 4) : make4(0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          if (deg[j] > d) agg[j] = add4(agg[j], act(h1[j]));
-          if (deg[j] > d + 1) agg[j] = add4(agg[j], act(h2[j]));
-        }
-      }
-      if (use > 0) mbar_wait(&bars[B_EMPTY_A + s], (uint32_t)((use - 1) & 1));   // GEMM1 of the previous user is done
       unsigned char* hi = smem + L::off_stage + s * kStageBytes;
       unsigned char* lo = hi + TM * KIN * 4;
+      // The thread's NR rows are processed in batches of NB: registers hold 3 NB rows in flight (no spills).
+      constexpr int NB = NR > 4 ? 4 : NR;
+#pragma unroll 1
+      for (int jb = 0; jb < NR; jb += NB) {
+        // ---- [A] self row + first two neighbour rows of every row of the batch: all loads in flight together
+        int deg[NB], eoff[NB];
+        float4 h0[NB], h1[NB], h2[NB];
 #pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int r = gr + j * RPP;
-        if (p.a_out && base + r < p.V && !(p.dbg & 8)) st4(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j]);
-        if (!(p.dbg & 16)) store_split4_s(hi, lo, TM, r, gl, agg[j]);
+        for (int j = 0; j < NB; ++j) {
+          const int r = gr + (jb + j) * RPP, v = base + r;
+          const bool ok = v < p.V && !(p.dbg & 4);
+          const int p0 = ip[r], p1 = ip[r + 1];
+          deg[j] = ok ? p1 - p0 : 0;
+          eoff[j] = p0 - e_begin;
+          const int sv = p.row_map ? s_self[s * TM + r] : v;
+          h0[j] = ok ? ld4(p.in + (size_t)sv * KIN + gl * 4) : make4(0.f);
+          h1[j] = deg[j] > 0 ? ld4(p.in + (size_t)nbr(eoff[j]) * KIN + gl * 4) : make4(0.f);
+          h2[j] = deg[j] > 1 ? ld4(p.in + (size_t)nbr(eoff[j] + 1) * KIN + gl * 4) : make4(0.f);
+        }
+        if (pt == 0 && jb == 0) TC2_TRACE(1, i);
+        // ---- [B] stage the next tile's indices while those loads are in flight; fetch the range of the tile after it
+        if (jb == 0 && i + 1 < my_tiles) {
+          stage_indices((i + 1) & 1, tile_base(i + 1), nb_begin, nb_end);
+          if (i + 2 < my_tiles) { const int b2 = tile_base(i + 2); nb_begin = __ldg(p.indptr + b2); nb_end = __ldg(p.indptr + min(b2 + TM, p.V)); }
+        }
+        // ---- [C] a_v = f(h_v) + sum_u f(h_u), neighbours in CSR order (same summation order as gin_fwd_kernel)
+        float4 agg[NB];
+        int maxd = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          agg[j] = (base + gr + (jb + j) * RPP < p.V) ? act(h0[j]) : make4(0.f);
+          if (deg[j] > 0) agg[j] = add4(agg[j], act(h1[j]));
+          if (deg[j] > 1) agg[j] = add4(agg[j], act(h2[j]));
+          maxd = max(maxd, deg[j]);
+        }
+        for (int d = 2; d < maxd; d += 2) {                      // rows with more than two neighbours
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            h1[j] = deg[j] > d ? ld4(p.in + (size_t)nbr(eoff[j] + d) * KIN + gl * 4) : make4(0.f);
+            h2[j] = deg[j] > d + 1 ? ld4(p.in + (size_t)nbr(eoff[j] + d + 1) * KIN + gl * 4) : make4(0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            if (deg[j] > d) agg[j] = add4(agg[j], act(h1[j]));
+            if (deg[j] > d + 1) agg[j] = add4(agg[j], act(h2[j]));
+          }
+        }
+        if (pt == 0 && jb == 0) TC2_TRACE(2, i);
+        if (jb == 0 && use > 0) mbar_wait(&bars[B_EMPTY_A + s], (uint32_t)((use - 1) & 1));   // GEMM1 of the previous user is done
+        if (pt == 0 && jb == 0) TC2_TRACE(3, i);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int r = gr + (jb + j) * RPP;
+          if (p.a_out && base + r < p.V && !(p.dbg & 8)) st4_cs(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j]);
+          if (!(p.dbg & 16)) store_split4_s(hi, lo, TM, r, gl, agg[j]);
+        }
       }
       if (!(p.dbg & 128)) fence_smem_to_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_FULL_A + s]);
+      if (pt == 0) TC2_TRACE(4, i);
       cp_async_wait_all();
       prod_sync();   // index buffer (i+1)&1 is complete, buffer i&1 may be overwritten by the next iteration
     }
@@ -227,8 +243,8 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
       auto gemm1 = [&](int i) {
         const int s = i & 1, use = i >> 1;
         mbar_wait(&bars[B_FULL_A + s], (uint32_t)(use & 1));
-        if (use > 0) mbar_wait(&bars[B_DFREE + s], (uint32_t)((use - 1) & 1));   // epilogue 2 of the previous user has read D
         fence_after_sync();
+        if (lane == 0) TC2_TRACE(5, i);
         const uint32_t ah = smem_u32(smem + L::off_stage + s * kStageBytes), al = ah + TM * KIN * 4;
         const uint32_t d = tmem + s * 256 + kColD1;
 #pragma unroll
@@ -246,6 +262,7 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
         const int s = i & 1, use = i >> 1;
         mbar_wait(&bars[B_R + s], (uint32_t)(use & 1));
         fence_after_sync();
+        if (lane == 0) TC2_TRACE(6, i);
         const uint32_t d = tmem + s * 256 + kColD2;
         const uint32_t rh = tmem + s * 256 + kColRhi, rl = tmem + s * 256 + kColRlo;
 #pragma unroll
@@ -274,6 +291,7 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
       const int gv = (bid + i * nblk) * TM + row;
       mbar_wait(&bars[B_D1 + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) TC2_TRACE(7, i);
       const uint32_t t0 = tmem + s * 256 + tl;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -291,13 +309,14 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
         tmem_st16(t0 + kColRhi + 16 * c, hi);
         tmem_st16(t0 + kColRlo + 16 * c, lo);
         if (p.r_out && gv < p.V && !(p.dbg & 1)) {
-          st8(p.r_out + (size_t)gv * HID + 16 * c, v);
-          st8(p.r_out + (size_t)gv * HID + 16 * c + 8, v + 8);
+          st8_cs(p.r_out + (size_t)gv * HID + 16 * c, v);
+          st8_cs(p.r_out + (size_t)gv * HID + 16 * c + 8, v + 8);
         }
       }
       tmem_st_wait();
       fence_before_sync();
       mbar_arrive(&bars[B_R + s]);
+      if (threadIdx.x == 0) TC2_TRACE(8, i);
     };
     auto epi2 = [&](int i) {
       const int s = i & 1, use = i >> 1;
@@ -307,6 +326,7 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
       const int cnt = max(0, min(32, p.V - (base + warp * 32)));   // valid rows of this warp (warp-uniform)
       mbar_wait(&bars[B_D2 + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) TC2_TRACE(9, i);
       const uint32_t t0 = tmem + s * 256 + tl + kColD2;
       float mean_h[2] = {0.f, 0.f}, m2_h[2] = {0.f, 0.f};
 #pragma unroll
@@ -348,8 +368,8 @@ gin_fwd_tc2_kernel(GinFwdPair pp) {
         }
         run_n = nt;
       }
-      fence_before_sync();   // TMEM reads of this stage are complete: GEMM1 of the next user may overwrite D
-      mbar_arrive(&bars[B_DFREE + s]);
+      fence_before_sync();   // TMEM reads of this stage are complete before GEMM2 of its next user (ordered through B_R)
+      if (threadIdx.x == 0) TC2_TRACE(10, i);
     };
     if (my_tiles > 0) epi1(0);
     for (int i = 0; i < my_tiles; ++i) {
@@ -461,6 +481,12 @@ static void launch_tc2_any(GinFwdPair& pp, int grid, int kin, int variant, cudaS
   if (kin == DTR) { if (variant == 2) launch_tc2<DTR, 16>(pp, grid, s); else launch_tc2<DTR, 8>(pp, grid, s); }
   else { if (variant == 2) launch_tc2<HID, 16>(pp, grid, s); else launch_tc2<HID, 8>(pp, grid, s); }
 }
+
+}  // namespace scgib
+extern "C" __attribute__((visibility("default"))) int scgib_debug_tc2_trace(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, scgib::g_tc2_trace, (size_t)n * sizeof(long long));
+}
+namespace scgib {
 
 // variant 1: 8 producer warps, variant 2: 16 producer warps
 void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel timing of the tc2 forward under SCGIB_DBG elimination masks (experiments only)
 for d in "$@"; do
-  SCGIB_TC=3 SCGIB_DBG=$d timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+  SCGIB_DBG=$d timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 k=d['kernels']
