@@ -196,8 +196,8 @@ SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B,
                                                   int32_t Es, const char* name);
 
 /* GIN forward implementation: 0 = FP32 FFMA register tiles (gin_kernels.cu), 1 = tcgen05 3xTF32 with 64-row tiles
- * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu;
- * 3 is the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
+ * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu),
+ * 4 = the same pipeline with the gather served from a shared-memory row window (gin_tc3.cu, the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
 SCGIB_API void scgib_set_tensor_cores(int mode);
 /* GIN backward (BN backward + the four MLP gradient GEMMs): 1 = tcgen05 3xTF32 kernel (gin_bwd_tc.cu, default),
  * 0 = FP32 FFMA register tiles; environment variable SCGIB_TC_BWD; on < 0 restores the default. */

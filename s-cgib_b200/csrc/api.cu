@@ -20,7 +20,7 @@ int num_sms() {
 
 static int g_use_tc = -1;
 int tensor_core_mode() {
-  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }   // default: gin_tc2.cu, 16 producer warps
+  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 4; }   // default: gin_tc3.cu
   return g_use_tc;
 }
 static int g_bwd_tc = -1;
@@ -32,6 +32,7 @@ static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
   const int m = tensor_core_mode();
   if (m == 0) launch_gin_fwd(a, kin, s);
   else if (m == 1) launch_gin_fwd_tc(a, kin, s);
+  else if (m == 4) launch_gin_fwd_tc3(a, kin, s);
   else launch_gin_fwd_tc2(a, kin, m - 1, s);
 }
 
@@ -302,8 +303,10 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
     }
     const int kin = l == 0 ? DTR : HID, m = tensor_core_mode();
-    if (m >= 2) {
-      PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc2_pair(ga[0], ga[1], kin, m - 1, s));
+    if (m == 4) {
+      PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
+    } else if (m >= 2) {
+      PROF("gin_fwd_tc2.enc1+2", launch_gin_fwd_tc2_pair(ga[0], ga[1], kin, m - 1, s));
     } else {
       for (int e = 0; e < 2; ++e) {
         if (m == 1) PROF(e == 0 ? "gin_fwd_tc64.enc1" : "gin_fwd_tc64.enc2", launch_gin_fwd_tc(ga[e], kin, s));
@@ -576,4 +579,4 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
 
 // Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
 extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int on) { g_bwd_tc = on < 0 ? -1 : (on ? 1 : 0); }
-extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 3) ? mode : -1; }   // < 0: back to the default
+extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 4) ? mode : -1; }   // < 0: back to the default

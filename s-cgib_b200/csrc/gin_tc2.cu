@@ -24,7 +24,7 @@ namespace scgib {
 using namespace umma;
 
 // per-tile role timestamps (SCGIB_DBG bit 1024; experiments only): [cta][tile < 16][event < 12] SM clock values
-__device__ long long g_tc2_trace[160 * 16 * 12];
+__device__ long long g_tc2_trace[160 * 16 * 12];   // also written by gin_tc3.cu
 #define TC2_TRACE(ev, tile) do { if ((p.dbg & 1024) && (tile) < 16 && blockIdx.x < 160) g_tc2_trace[((size_t)blockIdx.x * 16 + (tile)) * 12 + (ev)] = clock64(); } while (0)
 
 namespace tc2 {
@@ -481,12 +481,6 @@ static void launch_tc2_any(GinFwdPair& pp, int grid, int kin, int variant, cudaS
   if (kin == DTR) { if (variant == 2) launch_tc2<DTR, 16>(pp, grid, s); else launch_tc2<DTR, 8>(pp, grid, s); }
   else { if (variant == 2) launch_tc2<HID, 16>(pp, grid, s); else launch_tc2<HID, 8>(pp, grid, s); }
 }
-
-}  // namespace scgib
-extern "C" __attribute__((visibility("default"))) int scgib_debug_tc2_trace(long long* host_out, int n) {
-  return (int)cudaMemcpyFromSymbol(host_out, scgib::g_tc2_trace, (size_t)n * sizeof(long long));
-}
-namespace scgib {
 
 // variant 1: 8 producer warps, variant 2: 16 producer warps
 void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s) {

@@ -40,7 +40,9 @@ int gin_fwd_tc_tiles(int V);
 void launch_gin_fwd_tc(const GinFwdArgs& a, int kin, cudaStream_t s);     // tcgen05 3xTF32 (gin_tc.cu)
 void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s);  // warp-specialised tcgen05 (gin_tc2.cu)
 void launch_gin_fwd_tc2_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, int variant, cudaStream_t s);
-int tensor_core_mode();                                                   // SCGIB_TC: 0 FFMA, 1 gin_tc.cu, 2/3 gin_tc2.cu (1/2 producer groups)
+void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // shared-memory window gather (gin_tc3.cu)
+void launch_gin_fwd_tc3_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, cudaStream_t s);
+int tensor_core_mode();                                                   // SCGIB_TC: 0 FFMA, 1 gin_tc.cu, 2/3 gin_tc2.cu (8/16 producer warps), 4 gin_tc3.cu
 inline bool use_tensor_cores() { return tensor_core_mode() != 0; }
 
 struct GinBwdPreArgs {

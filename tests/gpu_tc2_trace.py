@@ -18,7 +18,7 @@ n = 160 * 16 * 12
 buf = (ctypes.c_longlong * n)()
 lib.scgib_debug_tc2_trace(ctypes.cast(buf, ctypes.c_void_p), n)
 t = np.frombuffer(buf, dtype=np.int64).reshape(160, 16, 12).astype(np.float64)
-names = ["p.start", "p.issued", "p.data", "p.empty", "p.full", "m.g1", "m.g2", "e.d1", "e.r", "e.d2", "e.end"]
+names = ["p.start", "p.landed", "p.issued", "p.gathered", "p.full", "m.g1", "m.g2", "e.d1", "e.r", "e.d2", "e.end"]
 for cta in (0, 40, 100):
     t0 = t[cta, 0, 0]
     print("CTA", cta)

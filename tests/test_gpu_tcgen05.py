@@ -31,7 +31,7 @@ def test_umma_3xtf32_tile_gemm(M, mode):
     assert rel(out[lanes], ref) <= 3e-6          # plain TF32 would be ~1e-3
 
 
-@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (2, 300), (3, 300), (2, 6000), (3, 6000)])
+@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (2, 300), (3, 300), (4, 300), (2, 6000), (3, 6000), (4, 6000), (4, 20000)])
 @pytest.mark.parametrize("kin", [32, 64])
 def test_gin_layer_forward_tensor_cores(kin, mode, B):
     """mode 1: gin_tc.cu (M = 64 tiles); modes 2/3: gin_tc2.cu (warp-specialised, 1/2 producer groups).  B = 6000
