@@ -277,6 +277,11 @@ def main():
     else:
         abytes = 3 * b.N * 64 * 4
     achieved = abytes / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
+    traffic = None                       # dram__bytes_read + write per launch of that kernel, from the committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
 
     if rank == 0:
         graphs = args.batch * world * args.steps
@@ -295,7 +300,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": (nlaunch + 5) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes,
                          "note": "warp-specialised tcgen05 3xTF32 kernel (MLP GEMMs on the tensor pipe); bytes = SURVEY 8(d) "
                                  "per-layer figure of both encoders' rows in the launch; see DESIGN.md section 3"},

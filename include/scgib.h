@@ -205,6 +205,8 @@ SCGIB_API void scgib_set_tensor_cores_bwd(int on);
 /* Experiments only: per-tile role timestamps of the last gin_tc2 forward launch run with SCGIB_DBG bit 1024
  * ([cta < 160][tile < 16][event < 12] SM clocks) copied to host memory. */
 SCGIB_API int scgib_debug_tc2_trace(long long* host_out, int n);
+/* The same for the last gin_bwd_tc launch (SCGIB_DBG bit 2048). */
+SCGIB_API int scgib_debug_bwd_trace(long long* host_out, int n);
 
 /* Probe of the tcgen05 tile-GEMM primitives (tests only): one 3xTF32 GEMM of fp32 tiles A [M,64], B [64 or M,64] in
  * operand-major mode 0/1/2 (umma_test.cu); out[128][64] = dump of all TMEM lanes. */

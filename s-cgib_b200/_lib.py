@@ -56,6 +56,7 @@ _SIGNATURES = {
     "scgib_set_tensor_cores": (None, [c_int]),
     "scgib_set_tensor_cores_bwd": (None, [c_int]),
     "scgib_debug_tc2_trace": (c_int, [c_void_p, c_int]),
+    "scgib_debug_bwd_trace": (c_int, [c_void_p, c_int]),
     "scgib_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "scgib_debug_umma2": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_void_p]),
     "scgib_profile_enable": (None, [c_int]),

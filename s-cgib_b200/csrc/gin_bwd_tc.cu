@@ -14,11 +14,16 @@
 // Shared memory holds two 64 KB tile buffers: X = g_y, then g_u; Y = r, then a (loaded while G1/G3 run).
 // Roles: 16 loader warps (coalesced float4 rows -> BN backward -> hi/lo split -> shared memory; next tile prefetched
 // into L2), one MMA-issuing warp, 4 epilogue warps (thread = tile row = TMEM lane).
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "umma.cuh"
 
 namespace scgib {
 using namespace umma;
+
+// per-tile role timestamps (SCGIB_DBG bit 2048; experiments only, tests/gpu_tc2_trace.py bwd)
+__device__ long long g_bwd_trace[160 * 16 * 12];
+#define BWD_TRACE(ev, tile) do { if (trace_on && (tile) < 16 && blockIdx.x < 160) g_bwd_trace[((size_t)blockIdx.x * 16 + (tile)) * 12 + (ev)] = clock64(); } while (0)
 
 namespace bwdtc {
 constexpr int TM = 128;
@@ -66,6 +71,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
   const GinBwdMainArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
   const int nblk = second ? (int)gridDim.x - pp.split : pp.split;
+  const bool trace_on = pp.trace != 0;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* X = smem + L::off_x;
   unsigned char* Y = smem + L::off_y;
@@ -125,6 +131,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
     constexpr int ALPR = KIN / 4;                             // lanes per `a` row
     for (int i = 0; i < my_tiles; ++i) {
       const int base = tile_base(i);
+      if (pt == 0) BWD_TRACE(0, i);
       // ---- phase 1: g_o, y, r rows -> g_y, r (hi/lo) -> X, Y
       float4 go[NR], yy[NR], rr[NR];
 #pragma unroll
@@ -149,6 +156,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
         }
       }
       if (i > 0) mbar_wait(&bars[B_D2], (uint32_t)((i - 1) & 1));   // G2 / G4 of the previous tile have read X and Y
+      if (pt == 0) BWD_TRACE(1, i);
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int row = gr + j * RPP;
@@ -174,6 +182,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
       fence_smem_to_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_FULL1]);
+      if (pt == 0) BWD_TRACE(2, i);
       // ---- phase 2: a rows -> (after G1 / G3 have read Y) -> Y
       constexpr int ARPP = LT / ALPR, ANR = TM / ARPP;
       const int al = pt % ALPR, ar = pt / ALPR;
@@ -184,11 +193,13 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
         aa[j] = v < p.V ? ld4_cs(p.a + (size_t)v * KIN + al * 4) : make4(0.f);
       }
       mbar_wait(&bars[B_D1], (uint32_t)(i & 1));
+      if (pt == 0) BWD_TRACE(3, i);
 #pragma unroll
       for (int j = 0; j < ANR; ++j) store_split4_s(Y, Y + TM * KIN * 4, TM, ar + j * ARPP, al, aa[j]);
       fence_smem_to_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_FULL2]);
+      if (pt == 0) BWD_TRACE(4, i);
     }
   } else if (warp == kEpiWarps) {
     // =========================================================================== MMA issuer
@@ -205,6 +216,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
       for (int i = 0; i < my_tiles; ++i) {
         mbar_wait(&bars[B_FULL1], (uint32_t)(i & 1));
         fence_after_sync();
+        if (lane == 0) BWD_TRACE(5, i);
         // G1: g_r = g_y W2          (A = X K-major, B = [W2t_hi | W2t_lo])
 #pragma unroll
         for (int k = 0; k < HID / 8; ++k) {
@@ -223,6 +235,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
         mbar_wait(&bars[B_GU], (uint32_t)(i & 1));
         mbar_wait(&bars[B_FULL2], (uint32_t)(i & 1));
         fence_after_sync();
+        if (lane == 0) BWD_TRACE(6, i);
         // G2: g_a = g_u W1          (A = X K-major, B = [W1t_hi | W1t_lo])
 #pragma unroll
         for (int k = 0; k < HID / 8; ++k) {
@@ -250,6 +263,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
       // ---- epilogue 1: g_u = g_r * [r > 0] -> X (hi/lo), column sums for db1
       mbar_wait(&bars[B_D1], (uint32_t)(i & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) BWD_TRACE(7, i);
       const uint2 m = s_mask[row];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -274,9 +288,11 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
       fence_smem_to_async();
       fence_before_sync();
       mbar_arrive(&bars[B_GU]);
+      if (threadIdx.x == 0) BWD_TRACE(8, i);
       // ---- epilogue 2: g_a -> global
       mbar_wait(&bars[B_D2], (uint32_t)(i & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) BWD_TRACE(9, i);
 #pragma unroll
       for (int c0 = 0; c0 < KIN; c0 += 32) {
         float g[32], t2[32];
@@ -293,6 +309,7 @@ gin_bwd_tc_kernel(GinBwdMainPair pp) {
         }
       }
       fence_before_sync();
+      if (threadIdx.x == 0) BWD_TRACE(10, i);
     }
   }
   // ---- every CTA writes its partial gradients (zeros when it had no tile)
@@ -374,8 +391,20 @@ static void launch_bwd_tc(const GinBwdMainPair& pp, int grid, cudaStream_t s) {
   bwdtc::gin_bwd_tc_kernel<KIN><<<grid, bwdtc::kThreadsTotal, L::total, s>>>(pp);
 }
 
+}  // namespace scgib
+extern "C" __attribute__((visibility("default"))) int scgib_debug_bwd_trace(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, scgib::g_bwd_trace, (size_t)n * sizeof(long long));
+}
+namespace scgib {
+static int bwd_trace_flag() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_DBG"); v = (e && (atoi(e) & 2048)) ? 1 : 0; }
+  return v;
+}
+
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s) {
   GinBwdMainPair pp;
+  pp.trace = 0;
   pp.a[0] = a; pp.a[1] = a;
   pp.split = grid;
   if (kin == DTR) launch_bwd_tc<DTR>(pp, grid, s); else launch_bwd_tc<HID>(pp, grid, s);
@@ -386,6 +415,7 @@ void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs&
   GinBwdMainPair pp;
   pp.a[0] = a0; pp.a[1] = a1;
   pp.split = pair_split(grid, (a0.V + bwdtc::TM - 1) / bwdtc::TM, (a1.V + bwdtc::TM - 1) / bwdtc::TM);
+  pp.trace = bwd_trace_flag();
   if (kin == DTR) launch_bwd_tc<DTR>(pp, grid, s); else launch_bwd_tc<HID>(pp, grid, s);
 }
 

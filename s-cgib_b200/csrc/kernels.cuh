@@ -76,7 +76,7 @@ struct GinBwdMainArgs {
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
-struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; };
+struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; };
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
 void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 tcgen05 (default)
