@@ -155,6 +155,14 @@ SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const float* params
 SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* batch,
                                 const float* loss_scale, float* grads,
                                 void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the feature path only: gradients of <gZ, Z> with respect to every parameter, where Z = MLP(interaction_map)
+ * is the output of scgib_pretrain_forward_f32 (its `Z` argument) and gZ [N, hidden] is the upstream gradient of whatever
+ * head consumes Z - the fine-tuning models' Set2Set / predict head (Mainmodel_finetuning.forward, models.py:501-520;
+ * autograd through model.extract_features + self.MLP).  Same workspace / grads contract as scgib_pretrain_backward_f32;
+ * the pre-training losses contribute nothing. */
+SCGIB_API int scgib_extract_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* batch,
+                                         const float* gZ, float* grads, void* workspace, size_t workspace_bytes,
+                                         void* stream);
 
 /* Adam with L2-in-gradient weight decay over one flat buffer (torch.optim.Adam(lr, weight_decay),
  * exp_pretraining.py:86,112,323).  step = 1-based step count; grad_scale multiplies the gradient
@@ -199,9 +207,11 @@ SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B,
  * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu),
  * 4 = the same pipeline with the gather served from a shared-memory row window (gin_tc3.cu, the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
 SCGIB_API void scgib_set_tensor_cores(int mode);
-/* GIN backward (BN backward + the four MLP gradient GEMMs): 1 = tcgen05 3xTF32 kernel (gin_bwd_tc.cu, default),
- * 0 = FP32 FFMA register tiles; environment variable SCGIB_TC_BWD; on < 0 restores the default. */
-SCGIB_API void scgib_set_tensor_cores_bwd(int on);
+/* GIN backward (BN backward + the four MLP gradient GEMMs): 1 = tcgen05 3xTF32 kernel with 128-row tiles (gin_bwd_tc.cu,
+ * default), 2 = the variant with double-buffered 64-row tiles and M-stacked weight-gradient operands (gin_bwd_tc2.cu; same
+ * speed on B200, kept for comparison), 0 = FP32 FFMA register tiles; environment variable SCGIB_TC_BWD; mode < 0 restores
+ * the default. */
+SCGIB_API void scgib_set_tensor_cores_bwd(int mode);
 /* Experiments only: per-tile role timestamps of the last gin_tc2 forward launch run with SCGIB_DBG bit 1024
  * ([cta < 160][tile < 16][event < 12] SM clocks) copied to host memory. */
 SCGIB_API int scgib_debug_tc2_trace(long long* host_out, int n);

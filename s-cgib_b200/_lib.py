@@ -45,6 +45,8 @@ _SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scgib_pretrain_backward_f32": (c_int, [POINTER(Dims), c_void_p, POINTER(Batch), POINTER(c_float), c_void_p,
                                             c_void_p, c_size_t, c_void_p]),
+    "scgib_extract_backward_f32": (c_int, [POINTER(Dims), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]),
     "scgib_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p]),
     "scgib_input_proj_fwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -25,7 +25,7 @@ int tensor_core_mode() {
 }
 static int g_bwd_tc = -1;
 int bwd_tensor_core_mode() {
-  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
+  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
   return g_bwd_tc;
 }
 static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
@@ -364,9 +364,10 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
   return (int)cudaGetLastError();
 }
 
-extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* b,
-                                           const float* loss_scale, float* grads, void* workspace,
-                                           size_t workspace_bytes, void* stream_) {
+// gZ_ext == nullptr: gradients of scale . {KL, contrastive, recon};  gZ_ext != nullptr: gradients of <gZ_ext, Z> (the
+// upstream gradient of a head applied to Z = MLP(interaction_map): the fine-tuning models, models.py:501-520)
+static int backward_impl(const ScgibDims* d, const float* params, const ScgibBatch* b, const float* loss_scale,
+                         const float* gZ_ext, float* grads, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!dims_ok(d)) return SCGIB_E_SHAPE;
   if (!params || !grads || !workspace || !loss_scale) return SCGIB_E_NULL;
   int rc = check_batch(b);
@@ -383,7 +384,12 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   const int js = contrastive_jsplit(b->B);
-  {
+  if (gZ_ext) {
+    if (((uintptr_t)gZ_ext & 15u) != 0) return SCGIB_E_ALIGN;
+    cudaMemcpyAsync(w.gZ, gZ_ext, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    cudaMemsetAsync(w.g_core, 0, (size_t)b->B * HID * sizeof(float), s);
+    cudaMemsetAsync(w.g_readout, 0, (size_t)b->B * HID * sizeof(float), s);
+  } else {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
     if (use_tc_contrastive())
       PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc(a, w.zsplit, s));
@@ -391,10 +397,8 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
       PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, s));
     ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
     PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, s));
-  }
-  {
-    ReconBwdArgs a{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
-    PROF("recon_bwd", launch_recon_bwd(a, s));
+    ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+    PROF("recon_bwd", launch_recon_bwd(ra, s));
   }
   {
     HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
@@ -448,7 +452,10 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
     }
     PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], s));
     if (pair_main) {
-      PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc_pair(ma[0], ma[1], kin, GP, s));
+      if (bwd_tensor_core_mode() == 2)
+        PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
+      else
+        PROF("gin_bwd_main_tc128.enc1+2", launch_gin_bwd_main_tc_pair(ma[0], ma[1], kin, GP, s));
     } else {
       PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, GP, s));
       PROF("gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma[1], kin, GP, s));
@@ -476,6 +483,20 @@ extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const f
     PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
   }
   return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_pretrain_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* b,
+                                           const float* loss_scale, float* grads, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  return backward_impl(d, params, b, loss_scale, nullptr, grads, workspace, workspace_bytes, stream);
+}
+
+extern "C" SCGIB_API int scgib_extract_backward_f32(const ScgibDims* d, const float* params, const ScgibBatch* b,
+                                          const float* gZ, float* grads, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  if (!gZ) return SCGIB_E_NULL;
+  const float zero[3] = {0.f, 0.f, 0.f};
+  return backward_impl(d, params, b, zero, gZ, grads, workspace, workspace_bytes, stream);
 }
 
 extern "C" SCGIB_API int scgib_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
@@ -578,5 +599,5 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
 }
 
 // Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
-extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int on) { g_bwd_tc = on < 0 ? -1 : (on ? 1 : 0); }
+extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int mode) { g_bwd_tc = (mode >= 0 && mode <= 2) ? mode : -1; }
 extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 4) ? mode : -1; }   // < 0: back to the default

@@ -391,11 +391,6 @@ static void launch_bwd_tc(const GinBwdMainPair& pp, int grid, cudaStream_t s) {
   bwdtc::gin_bwd_tc_kernel<KIN><<<grid, bwdtc::kThreadsTotal, L::total, s>>>(pp);
 }
 
-}  // namespace scgib
-extern "C" __attribute__((visibility("default"))) int scgib_debug_bwd_trace(long long* host_out, int n) {
-  return (int)cudaMemcpyFromSymbol(host_out, scgib::g_bwd_trace, (size_t)n * sizeof(long long));
-}
-namespace scgib {
 static int bwd_trace_flag() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SCGIB_DBG"); v = (e && (atoi(e) & 2048)) ? 1 : 0; }

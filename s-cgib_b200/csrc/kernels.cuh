@@ -79,7 +79,9 @@ void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_
 struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; };
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
 void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
-int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 tcgen05 (default)
+void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // 64-row double-buffered tiles (gin_bwd_tc2.cu)
+void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
+int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 gin_bwd_tc.cu (default), 2 gin_bwd_tc2.cu
 
 struct InputProjBwdArgs {
   const float* ga[2];       // layer-0 input gradients of the two encoders, [V][DTR]

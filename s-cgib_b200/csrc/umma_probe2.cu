@@ -16,6 +16,7 @@ struct Probe2 {
   int b_lbo, b_sbo, b_ltype, b_div, b_adv_lo, b_adv_hi;
   int RA, RB;                         // rows of the A / B source matrices ([R][64] fp32)
   int reps;                           // timing: the whole MMA sequence is issued `reps` times; cycles -> out[128*64]
+  int a_lo_off;                       // byte offset of the A lo tile from the hi tile (0 = default 40960); adjacent tiles allow M-stacking
 };
 
 __global__ void __launch_bounds__(128) umma_probe2_kernel(const float* __restrict__ A, const float* __restrict__ B,
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(128) umma_probe2_kernel(const float* __restric
   __shared__ __align__(8) uint64_t s_bar;
   constexpr int TB = 40960;   // >= tile_bytes(128, 64) = 36864 and tile_s_bytes(128) = 32768, 1024-aligned
   unsigned char* a_hi = smem;
-  unsigned char* a_lo = a_hi + TB;
+  unsigned char* a_lo = a_hi + (p.a_lo_off > 0 ? p.a_lo_off : TB);
   unsigned char* b_hi = a_lo + TB;
   unsigned char* b_lo = b_hi + TB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) umma_probe2_kernel(const float* __restric
 extern "C" SCGIB_API int scgib_debug_umma2(const float* A, const float* B, float* out, const int32_t* params, void* stream) {
   if (!A || !B || !out || !params) return SCGIB_E_NULL;
   scgib::Probe2 p;
-  static_assert(sizeof(scgib::Probe2) == 23 * sizeof(int), "Probe2 is 23 ints");
+  static_assert(sizeof(scgib::Probe2) == 24 * sizeof(int), "Probe2 is 24 ints");
   memcpy(&p, params, sizeof(p));
   if ((p.M != 64 && p.M != 128) || p.N < 8 || p.N > 256 || (p.N > 64 && p.reps < 2) || p.RA < 1 || p.RA > 128 || p.RB < 1 || p.RB > 128 || p.a_div < 1 ||
       p.b_div < 1 || p.ksteps < 1 || p.ksteps > 16 || p.reps < 1)

@@ -282,6 +282,21 @@ class PretrainEngine:
                                                         ws.numel(), st), "pretrain_backward")
         return self.grads
 
+    def extract_backward(self, gZ: torch.Tensor, params: Optional[torch.Tensor] = None):
+        """Gradients of <gZ, Z> into the flat ``grads`` buffer (overwritten): the backward of ``extract_features`` + head
+        MLP for a downstream head that consumes Z (fine-tuning, models.py:501-520).  Call after ``forward``."""
+        b, gate_u, feat_u = self._last
+        cb = b.c_struct(gate_u, feat_u)
+        ws = self._workspace(b)
+        gZ = gZ.contiguous().float()
+        assert gZ.shape == (b.N, HID) and gZ.device == self.device
+        p = self.params if params is None else params
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_extract_backward_f32(ctypes.byref(self.dims), _lib.ptr(p), ctypes.byref(cb), _lib.ptr(gZ),
+                                                       _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), st),
+                   "extract_backward")
+        return self.grads
+
     def adam_step(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, grad_scale=1.0):
         """torch.optim.Adam(lr, weight_decay=5e-5) of exp_pretraining.py:86 over the flat buffer."""
         self.step_count += 1

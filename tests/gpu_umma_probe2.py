@@ -26,6 +26,11 @@ CASES.append(("B fmt S K-major R=64 (dual use)", "AB", dict(b_fmt=1, b_ltype=1, 
 CASES.append(("A TMEM x B fmt S MN-major R=64", "ABn", dict(a_fmt=2, b_fmt=1, b_mn=1, b_ltype=1, b_sbo=512, b_lbo=64 * 128, b_div=1, b_adv_lo=0, b_adv_hi=1024)))
 CASES.append(("A fmt S K-major x B fmt S MN-major R=64", "ABn", dict(a_fmt=1, a_ltype=1, a_sbo=512, a_lbo=128 * 128, a_div=4, a_adv_lo=32, a_adv_hi=128 * 128,
                                                                b_fmt=1, b_mn=1, b_ltype=1, b_sbo=512, b_lbo=64 * 128, b_div=1, b_adv_lo=0, b_adv_hi=1024)))
+# 64-row tiles: A K-major R=64 (M=64); M-stacked A = [hi | lo]^T (adjacent tiles, MN-major, M=128) x B MN-major, K = 64 rows
+CASES.append(("A fmt S K-major R=64 M=64", "A64", dict(M=64, a_fmt=1, a_ltype=1, a_sbo=512, a_lbo=64 * 128, a_div=4, a_adv_lo=32, a_adv_hi=64 * 128)))
+CASES.append(("M-stacked A [hi|lo]^T MN-major M=128 K=64 rows, 1x", "AtB64s", dict(M=128, ksteps=8, split=1, a_fmt=1, b_fmt=1, a_mn=1, b_mn=1, a_lo_off=16384,
+                                                                           a_lbo=64 * 128, a_sbo=512, a_ltype=1, a_div=1, a_adv_lo=0, a_adv_hi=1024,
+                                                                           b_lbo=64 * 128, b_sbo=512, b_ltype=1, b_div=1, b_adv_lo=0, b_adv_hi=1024)))
 kw = {}
 for side in "ab":
     for k, v in S_MN.items():
@@ -50,6 +55,18 @@ def one(idx):
         ref, lanes = A.double()[:, :8] @ B.double()[:, :8].t(), L128
     elif kind == "ABn":
         ref, lanes = A.double() @ B.double(), L128
+    elif kind == "AtB64s":
+        A = A[:64].contiguous()
+        B = torch.randn(64, 64, device=dev)
+        Ah = A.double()
+        import struct
+        # tf32 round-to-nearest-away of A, emulated on the host
+        a32 = A.cpu().numpy().view("uint32").astype("uint64")
+        hi = (((a32 + 0x1000) & 0xFFFFE000).astype("uint32")).view("float32")
+        hi_t = torch.from_numpy(hi.copy()).double().to(dev)
+        lo_t = Ah - hi_t
+        ref = torch.cat([hi_t.t() @ B.double(), lo_t.t() @ B.double()], 0)
+        lanes = L128
     elif kind == "A64":
         A = A[:64].contiguous()
         ref, lanes = A.double() @ B.double().t(), L64
@@ -61,13 +78,16 @@ def one(idx):
         for k, v in G_K.items():
             p[side + "_" + k] = v
     p.update(kwargs)
-    arr = (ctypes.c_int32 * (len(FIELDS) + 1))(*([int(p[f]) for f in FIELDS] + [1]))
+    arr = (ctypes.c_int32 * (len(FIELDS) + 2))(*([int(p[f]) for f in FIELDS] + [1, int(p.get("a_lo_off", 0))]))
     out = torch.full((129, 64), float("nan"), device=dev)
     rc = lib.scgib_debug_umma2(_lib.ptr(A), _lib.ptr(B), _lib.ptr(out), arr, None)
     torch.cuda.synchronize()
     got = out[lanes].double()[:, :ref.shape[1]]
     err = float((got - ref).abs().max() / ref.abs().max())
     alt = ""
+    if kind == "AtB64s":
+        lo_err = float((got[64:] - ref[64:]).abs().max() / ref[64:].abs().max())
+        alt = " (lo rows 64..127 alone: %.2e)" % lo_err
     if kind == "A64":
         got2 = out[:64].double()
         alt = " (lanes 0..63: %.2e)" % float((got2 - ref).abs().max() / ref.abs().max())

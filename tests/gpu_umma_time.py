@@ -20,7 +20,7 @@ def run(tag, reps, **kw):
         for k, v in G_K.items():
             p[side + "_" + k] = v
     p.update(kw)
-    arr = (ctypes.c_int32 * len(F2))(*[int(p[f]) for f in F2])
+    arr = (ctypes.c_int32 * (len(F2) + 1))(*([int(p[f]) for f in F2] + [0]))
     out = torch.zeros(128 * 64 + 1, device=dev)
     res = []
     for _ in range(3):

@@ -19,8 +19,8 @@ from oracle.graph_ref import (RefEgoBatch, RefGraph, batch_ref, ego_batch_ref, g
                               synth_batch)
 from oracle.scgib_oracle import (OracleMainmodel, draw_noise_like_reference, normalize_rows, tgraph_from_ego,
                                  tgraph_from_ref)
-from tests.helpers import (check_against_truth, engine_from_oracle, fp64_truth, oracle_grads, product_ego_from_ref,
-                           product_graph, rel)
+from tests.helpers import (GRAD_TOL_MAX, GRAD_TOL_MEDIAN, check_against_truth, engine_from_oracle, fp64_truth,
+                           is_zero_grad_param, oracle_grads, product_ego_from_ref, product_graph, rel)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -184,6 +184,39 @@ def test_parity_full_size_vs_vectorised_oracle_fp64(B, k):
     rep = check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
     worst = max(rep, key=lambda r: r[1])
     print("worst cuda-vs-fp64 %.3e (%s); fp32 torch oracle on the same tensor %.3e" % (worst[1], worst[0], worst[2]))
+
+
+def test_extract_backward_external_upstream_gradient():
+    """Backward of the feature path for a downstream head (fine-tuning, models.py:501-520): gradients of <G, Z> for a
+    random upstream gradient G against autograd of the fp64 oracle."""
+    g = synth_batch(21, 96)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(5)
+    m = OracleMainmodel(9)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 7)
+    G = torch.randn(g.num_nodes, 64, generator=torch.Generator().manual_seed(3))
+    m64 = OracleMainmodel(9).double()
+    m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
+    x = normalize_rows(torch.from_numpy(g.x).double())
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    out = m64.forward_vectorised(tgraph_from_ref(g), x, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())
+    (out["Z"] * G.double()).sum().backward()
+    truth = {n: p.grad.detach().clone() for n, p in m64.named_parameters() if p.grad is not None}
+    from scgib_b200.engine import DeviceBatch
+    eng = engine_from_oracle(m, DEV)
+    pg = product_graph(g, DEV)
+    b = DeviceBatch(pg, product_ego_from_ref(pg, e, 1, DEV), pg.ndata["x"])
+    _, emb = eng.forward(b, gate_u.to(DEV), feat_u.to(DEV), want=True, update_running=False)
+    assert rel(emb["Z"], out["Z"]) <= 1e-5
+    eng.extract_backward(G.to(DEV))
+    torch.cuda.synchronize()
+    errs = []
+    for n, gv in eng.grad_views().items():
+        if n not in truth or is_zero_grad_param(n):
+            continue
+        errs.append(rel(gv, truth[n]))
+    errs.sort()
+    assert errs[len(errs) // 2] <= GRAD_TOL_MEDIAN and errs[-1] <= GRAD_TOL_MAX, errs[-5:]
 
 
 def test_forward_backward_deterministic():
