@@ -28,10 +28,8 @@ __device__ long long g_tc3_trace[160 * 16 * 12];
 
 namespace tc3 {
 constexpr int TM = 128;                       // rows per tile = UMMA M
-constexpr int kEpiWarps = 8, kProdWarps = 8;
+constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads3 = (kEpiWarps + 1 + kProdWarps) * 32;
-constexpr int PT = kProdWarps * 32;           // producer threads
 constexpr int kIdxCap = 1024;                 // staged neighbour indices per tile (more edges: read from global)
 constexpr int kStageBytes = 2 * TM * HID * 4; // hi + lo tile of one stage (format S); first holds the raw row window
 constexpr int HALO = 64, WIN = TM + 2 * HALO;  // window rows (WIN * 64 floats = the whole stage)
@@ -74,10 +72,12 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int KIN>
-__global__ void __launch_bounds__(kThreads3, 1)
+template <int KIN, int PW>
+__global__ void __launch_bounds__((kEpiWarps + 1 + PW) * 32, 1)
 gin_fwd_tc3_kernel(GinFwdPair pp) {
   using L = Smem<KIN>;
+  constexpr int kThreads3 = (kEpiWarps + 1 + PW) * 32;
+  constexpr int PT = PW * 32;                                 // producer threads
   const bool second = (int)blockIdx.x >= pp.split;
   const GinFwdArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
@@ -97,7 +97,7 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
   // ---- one-time setup: barriers, TMEM, weights (natural [out][in] = K-major B operand, dense cores), biases
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[B_FULL_A + s], kProdWarps);
+      mbar_init(&bars[B_FULL_A + s], PW);
       mbar_init(&bars[B_EMPTY_A + s], 1);
       mbar_init(&bars[B_D1 + s], 1);
       mbar_init(&bars[B_R + s], kEpiWarps * 32);
@@ -124,7 +124,7 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
 
   if (warp > kMmaWarp) {
     // =========================================================================== producers
-    constexpr int LPR = KIN / 4, RPP = PT / LPR, NR = TM / RPP;   // lanes per row, rows per pass, rows per thread
+    constexpr int LPR = KIN / 4, RPP = PT / LPR, NR = (TM + RPP - 1) / RPP;   // lanes per row, rows per pass, passes (last one guarded)
     const int pt = (warp - (kMmaWarp + 1)) * 32 + lane;
     const int gl = pt % LPR, gr = pt / LPR;
     int* s_ip = reinterpret_cast<int*>(smem + L::off_ip);
@@ -203,8 +203,8 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
       int e0[NR], deg[NR], maxd = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        const int r = gr + j * RPP;
-        const bool ok = base + r < p.V;
+        const int r = min(gr + j * RPP, TM - 1);
+        const bool ok = gr + j * RPP < TM && base + r < p.V;
         e0[j] = ip[r] - e_begin;
         deg[j] = ok ? ip[r + 1] - ip[r] : 0;
         maxd = max(maxd, deg[j]);
@@ -232,8 +232,10 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int r = gr + j * RPP;
-        if (p.a_out && base + r < p.V) st4_cs(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j]);
-        store_split4_s(hi, lo, TM, r, gl, agg[j]);
+        if (r < TM) {
+          if (p.a_out && base + r < p.V) st4_cs(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j]);
+          store_split4_s(hi, lo, TM, r, gl, agg[j]);
+        }
       }
       fence_smem_to_async();
       __syncwarp();
@@ -453,12 +455,21 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
 
 }  // namespace tc3
 
+template <int KIN, int PW>
+static void launch_tc3_pw(const GinFwdPair& pp, int grid, cudaStream_t s) {
+  using L = tc3::Smem<KIN>;
+  static bool once = (cudaFuncSetAttribute(tc3::gin_fwd_tc3_kernel<KIN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
+  (void)once;
+  tc3::gin_fwd_tc3_kernel<KIN, PW><<<grid, (tc3::kEpiWarps + 1 + PW) * 32, L::total, s>>>(pp);
+}
 template <int KIN>
 static void launch_tc3(const GinFwdPair& pp, int grid, cudaStream_t s) {
-  using L = tc3::Smem<KIN>;
-  static bool once = (cudaFuncSetAttribute(tc3::gin_fwd_tc3_kernel<KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
-  (void)once;
-  tc3::gin_fwd_tc3_kernel<KIN><<<grid, tc3::kThreads3, L::total, s>>>(pp);
+  static int pw = -1;                     // producer warps: SCGIB_TC3_PW = 8 | 12 | 16 (default) | 20
+  if (pw < 0) { const char* e = getenv("SCGIB_TC3_PW"); pw = e ? atoi(e) : 16; }
+  if (pw == 20) launch_tc3_pw<KIN, 20>(pp, grid, s);
+  else if (pw == 16) launch_tc3_pw<KIN, 16>(pp, grid, s);
+  else if (pw == 12) launch_tc3_pw<KIN, 12>(pp, grid, s);
+  else launch_tc3_pw<KIN, 8>(pp, grid, s);
 }
 
 }  // namespace scgib
