@@ -25,7 +25,7 @@ int tensor_core_mode() {
 }
 static int g_bwd_tc = -1;
 int bwd_tensor_core_mode() {
-  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
   return g_bwd_tc;
 }
 static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
