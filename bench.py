@@ -184,6 +184,9 @@ def main():
     lib = _lib.load()
     eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)     # same seed on every rank: replicas start equal
     eng._noise_gen.manual_seed(1234 + rank)
+    fused_dp = world > 1 and os.environ.get("SCGIB_DP", "peer") == "peer"
+    if fused_dp:
+        eng.enable_peer_allreduce()      # gradient all-reduce fused with Adam over NVLink peer memory (no NCCL per step)
 
     n_batches = 4
     host = [synth_batch(1000 * rank + i, args.batch).pin_memory() for i in range(n_batches)]
@@ -294,6 +297,7 @@ def main():
                                    "k_transition=%d, batch %d synthetic PCQM4Mv2-shape graphs per GPU (BASELINE configs[1])" % (args.k, args.batch),
                        "graphs_per_gpu": args.batch, "nodes": b.N, "edges": b.E, "ego_rows": b.Ns, "ego_edges": b.Es,
                        "parallelism": "dp%d" % world,
+                       "grad_exchange": ("fused peer-memory all-reduce + Adam kernel" if fused_dp else "NCCL all-reduce + Adam") if world > 1 else "none",
                        "l2": "no flush: per-step working set (workspace %.2f GB, 4 rotating batches) exceeds the 126 MB L2" % (eng._ws.numel() / 1e9)},
             "clocks": clocks,
             "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,

@@ -226,6 +226,26 @@ SCGIB_API int scgib_debug_umma(const float* A, const float* B, float* out, int32
  * out has 128*64 + 1 floats (the last one = SM cycles of the MMA sequence issued `reps` times). */
 SCGIB_API int scgib_debug_umma2(const float* A, const float* B, float* out, const int32_t* params, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism: gradient all-reduce fused with Adam over NVLink peer memory (peer_kernels.cu).  Replaces
+ * loss.backward()'s gradient exchange + optimizer.step() (exp_pretraining.py:321-323) for one process per GPU.
+ *  scgib_peer_alloc  : cudaMalloc + zero a buffer and return its 64-byte CUDA IPC handle (the one place where the
+ *                      library allocates: an IPC handle must name a whole allocation);
+ *  scgib_peer_open   : map a peer process's buffer (handle exchanged by the host, e.g. torch.distributed);
+ *  scgib_allreduce_adam_f32 : peer_grads[r] / peer_flags[r] (HOST arrays of device pointers, r < world <= 16) are rank
+ *                      r's gradient buffer of this step's parity and its flag array (uint32[world], zero-initialised);
+ *                      seq = 1, 2, ... is the step number, identical on every rank; gradients are double-buffered by
+ *                      seq & 1 (see peer_kernels.cu).  Every rank applies the identical rank-ordered mean gradient.
+ * ------------------------------------------------------------------------------------------ */
+SCGIB_API int scgib_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+SCGIB_API int scgib_peer_open(const unsigned char* handle64, void** dev_ptr);
+SCGIB_API int scgib_peer_close(void* dev_ptr);
+SCGIB_API int scgib_peer_free(void* dev_ptr);
+SCGIB_API int scgib_allreduce_adam_f32(float* params, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                       const void* const* peer_grads, const void* const* peer_flags, int32_t rank,
+                                       int32_t world, uint32_t seq, int64_t step, float lr, float beta1, float beta2,
+                                       float eps, float weight_decay, void* stream);
+
 /* Per-launch timing with CUDA events recorded on the launching stream (used by bench.py for the roofline
  * numbers).  enable(1) clears the record; every later kernel launch of this library is bracketed by two events;
  * after synchronising the stream, profile_get(i) returns the static kernel-family name and the elapsed ms. */

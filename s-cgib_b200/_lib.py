@@ -49,6 +49,13 @@ _SIGNATURES = {
                                            c_size_t, c_void_p]),
     "scgib_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p]),
+    "scgib_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_char_p]),
+    "scgib_peer_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "scgib_peer_close": (c_int, [c_void_p]),
+    "scgib_peer_free": (c_int, [c_void_p]),
+    "scgib_allreduce_adam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_int32,
+                                         c_int32, ctypes.c_uint32, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                         c_void_p]),
     "scgib_input_proj_fwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "scgib_gin_workspace_bytes": (c_size_t, [c_int32]),
     "scgib_gin_layer_fwd_f32": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

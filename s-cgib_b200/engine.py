@@ -305,14 +305,31 @@ class PretrainEngine:
                                                 _lib.ptr(self.exp_avg_sq), self.total, self.step_count, lr, betas[0],
                                                 betas[1], eps, weight_decay, grad_scale, st), "adam")
 
+    def enable_peer_allreduce(self, group=None):
+        """Data parallelism without NCCL on the hot path: gradients live in NVLink-mapped peer memory and ONE fused
+        kernel per step does the rank-ordered all-reduce and Adam (dist.PeerAllreduce, csrc/peer_kernels.cu)."""
+        from .dist import PeerAllreduce
+        self._peer = PeerAllreduce(self.lib, self.total, self.device, group)
+        self.grads = self._peer.grads(1)
+        return self._peer
+
     def train_step(self, b: DeviceBatch, gate_u=None, feat_u=None, lr=1e-4, weight_decay=5e-5, world_size=1):
         """forward + backward (+ gradient all-reduce) + Adam; returns the device losses tensor (no host sync)."""
+        peer = getattr(self, "_peer", None)
         losses = self.forward(b, gate_u, feat_u)
-        self.backward()
-        if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-        self.adam_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / world_size)
+        if peer is not None and world_size > 1:
+            peer.seq += 1
+            self.grads = peer.grads(peer.seq)                 # this step's parity buffer (peers read it over NVLink)
+            self.backward()
+            self.step_count += 1
+            peer.step(self.params, self.exp_avg, self.exp_avg_sq, peer.seq, self.step_count, lr, (0.9, 0.999), 1e-8,
+                      weight_decay, torch.cuda.current_stream(self.device).cuda_stream)
+        else:
+            self.backward()
+            if world_size > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            self.adam_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / world_size)
         slot = getattr(b, "_slot", None)
         if slot is not None:                      # the slot's buffers may be overwritten once this step has run
             slot["done"] = torch.cuda.Event()
