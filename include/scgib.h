@@ -164,6 +164,45 @@ SCGIB_API int scgib_extract_backward_f32(const ScgibDims* d, const float* params
                                          const float* gZ, float* grads, void* workspace, size_t workspace_bytes,
                                          void* stream);
 
+/* Forward of the feature path only: everything scgib_pretrain_forward_f32 does up to Z = MLP(interaction_map), without
+ * the pre-training losses - what Mainmodel_finetuning.forward runs before its readout (models.py:508-513:
+ * transfer_d, model.extract_features, self.MLP).  Same workspace; pair with scgib_extract_backward_f32. */
+SCGIB_API int scgib_extract_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
+                                        const ScgibBatch* batch, float* interaction_map, float* Z, float* noisy,
+                                        float* graph_readout, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fine-tuning head (Mainmodel_finetuning.forward, models.py:515-520): dgl.nn.Set2Set(H, n_iters = T, n_layers = 1)
+ * readout of Z (models.py:365, 515; per iteration: q = LSTM(q*), e_v = z_v . q_g, alpha = softmax over the graph,
+ * r_g = sum alpha_v z_v, q* = [q || r]) -> predict = Linear(2H,H)-ReLU-Linear(H,C) (models.py:386-397) -> sigmoid
+ * (models.py:519-520; sigmoid = 0 for the regression datasets, models.py:516-517).  One kernel per direction.
+ * head_params / head_grads: one flat fp32 buffer, slots below (scgib_finetune_head_layout gives offsets, each slot
+ * padded to 4 floats).  H in {64, 128}, C <= 64, T <= 8.  The forward leaves its saved state in `workspace`
+ * (scgib_finetune_head_workspace_bytes, 256-byte aligned); the backward must get the same workspace and Z.
+ *   fwd: scores [B,C]; optional readout [B,2H] (= q* after the last iteration, the Set2Set output).
+ *   bwd: gZ [N,H] (overwritten) = d<g_scores, scores>/dZ; head_grads: every slot overwritten.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  SCGIB_FT_LSTM_WIH = 0, /* s2s.lstm.weight_ih_l0 [4H,2H]  (gate order i,f,g,o) */
+  SCGIB_FT_LSTM_WHH,     /* s2s.lstm.weight_hh_l0 [4H,H]  */
+  SCGIB_FT_LSTM_BIH,     /* s2s.lstm.bias_ih_l0 [4H]      */
+  SCGIB_FT_LSTM_BHH,     /* s2s.lstm.bias_hh_l0 [4H]      */
+  SCGIB_FT_PRED_W1,      /* predict.0.weight [H,2H]       */
+  SCGIB_FT_PRED_B1,      /* predict.0.bias [H]            */
+  SCGIB_FT_PRED_W2,      /* predict.2.weight [C,H]        */
+  SCGIB_FT_PRED_B2,      /* predict.2.bias [C]            */
+  SCGIB_FT_SLOTS
+};
+SCGIB_API int64_t scgib_finetune_head_layout(int32_t H, int32_t C, int64_t* offsets, int64_t* sizes);
+SCGIB_API size_t scgib_finetune_head_workspace_bytes(int32_t H, int32_t C, int32_t T, int32_t B, int32_t N);
+SCGIB_API int scgib_finetune_head_fwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
+                                          const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N, float* scores,
+                                          float* readout, void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
+                                          const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N,
+                                          const float* scores, const float* g_scores, float* gZ, float* head_grads,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Adam with L2-in-gradient weight decay over one flat buffer (torch.optim.Adam(lr, weight_decay),
  * exp_pretraining.py:86,112,323).  step = 1-based step count; grad_scale multiplies the gradient
  * first (1/world_size after a sum all-reduce). */

@@ -131,6 +131,7 @@ class _LSTMHolder(nn.Module):
     def __init__(self, input_dim, n_iters, n_layers):
         super().__init__()
         self.lstm = nn.LSTM(2 * input_dim, input_dim, n_layers)
+        self.lstm.reset_parameters()     # DGL's Set2Set.__init__ re-initialises the LSTM (a second RNG draw)
 
 
 class OracleMainmodel(nn.Module):
@@ -351,3 +352,80 @@ def oracle_train_step(model: OracleMainmodel, opt, g, x_norm, eg, x_subs_norm, g
     loss.backward()
     opt.step()
     return float(loss.detach())
+
+
+# --------------------------------------------------------------------------------------
+# fine-tuning head: Set2Set readout + predict MLP
+# --------------------------------------------------------------------------------------
+class Set2SetRef(nn.Module):
+    """dgl.nn.Set2Set(input_dim, n_iters, n_layers) restated from DGL 1.1.0 (dgl/nn/pytorch/glob.py; call sites
+    models.py:365, 515): zero-initialised LSTM state and q*; per iteration ``q = LSTM(q*)``,
+    ``e_v = <feat_v, q_graph(v)>``, ``alpha = softmax of e over the nodes of each graph``,
+    ``readout_g = sum_v alpha_v feat_v``, ``q* = [q || readout]``.  DGL internals: restated, unpinned."""
+
+    def __init__(self, input_dim, n_iters, n_layers):
+        super().__init__()
+        self.input_dim, self.output_dim, self.n_iters, self.n_layers = input_dim, 2 * input_dim, n_iters, n_layers
+        self.lstm = nn.LSTM(self.output_dim, self.input_dim, n_layers)
+        self.lstm.reset_parameters()
+
+    def forward(self, g: TGraph, feat):
+        nB = g.seg_ptr.numel() - 1
+        seg = g.seg_ids()
+        h = (feat.new_zeros((self.n_layers, nB, self.input_dim)), feat.new_zeros((self.n_layers, nB, self.input_dim)))
+        q_star = feat.new_zeros(nB, self.output_dim)
+        for _ in range(self.n_iters):
+            q, h = self.lstm(q_star.unsqueeze(0), h)
+            q = q.view(nB, self.input_dim)
+            e = (feat * q[seg]).sum(dim=-1)
+            mx = torch.full((nB,), -float("inf"), dtype=feat.dtype).scatter_reduce(0, seg, e, "amax")
+            ex = torch.exp(e - mx[seg])
+            alpha = ex / torch.zeros(nB, dtype=feat.dtype).index_add(0, seg, ex)[seg]
+            readout = torch.zeros(nB, self.input_dim, dtype=feat.dtype).index_add(0, seg, feat * alpha[:, None])
+            q_star = torch.cat([q, readout], dim=-1)
+        return q_star
+
+
+def finetune_trainable(name: str) -> bool:
+    """The freeze rule of Mainmodel_finetuning.__init__ for the LOADED model's parameters (models.py:424-435): the inner
+    loop's last iteration wins, so exactly the names containing "layers.2" stay trainable (with num_layers = 4 the list
+    is ["layers.4", "layers.3", "layers.2"])."""
+    return "layers.2" in name
+
+
+class OracleFinetune(nn.Module):
+    """models.py:358-520 (Mainmodel_finetuning), GIN encoder: own transfer_d / MLP / s2s / predict around the loaded
+    pre-trained model's extract_features.  Modules the forward never touches (embedding_h, reduce_d, attn_layer,
+    Encoder1/2, compressor of the OUTER module) are kept so that state-dict keys match."""
+
+    def __init__(self, inner: OracleMainmodel, in_dim, hidden_dim=64, d_transfer=32, num_classes=10,
+                 task="graph_classification", regression_dataset=False, num_gin_layers=4):
+        super().__init__()
+        self.s2s = Set2SetRef(hidden_dim, 2, 1)
+        self.transfer_d = nn.Linear(in_dim, d_transfer, bias=False)
+        self.embedding_h = nn.Linear(d_transfer, hidden_dim, bias=False)
+        self.reduce_d = nn.Linear(2 * hidden_dim, hidden_dim)
+        self.attn_layer = nn.Linear(2 * hidden_dim, 1)
+        out_dim = 1 if task == "graph_regression" else num_classes
+        self.predict = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, out_dim))
+        self.MLP = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim))
+        self.Encoder1 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.Encoder2 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.model = inner
+        for n, p in self.model.named_parameters():
+            p.requires_grad = finetune_trainable(n)
+        self.compressor = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(),
+                                        nn.Linear(hidden_dim, 1))
+        self.no_sigmoid = regression_dataset      # models.py:516-517 (dataset in self.tasks)
+
+    def forward(self, g: TGraph, x_norm, eg: TGraph, x_subs_norm, gate_u=None, feat_u=None):
+        """models.py:501-520 -> dict(scores, Z, interaction_map, readout)."""
+        batch_x = self.transfer_d(x_norm)
+        x_subs = self.transfer_d(x_subs_norm)
+        imap, _, _, _ = self.model.extract_features(g, batch_x, eg, x_subs, gate_u, feat_u)
+        Z = self.MLP(imap)
+        q_star = self.s2s(g, Z)
+        s = self.predict(q_star)
+        if not self.no_sigmoid:
+            s = torch.sigmoid(s)
+        return dict(scores=s, Z=Z, interaction_map=imap, readout=q_star)

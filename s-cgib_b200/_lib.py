@@ -28,6 +28,7 @@ ENC_W1, ENC_B1, ENC_W2, ENC_B2, ENC_GAMMA, ENC_BETA, ENC_SLOTS = range(7)
 (P_HEAD_W1, P_HEAD_B1, P_HEAD_W2, P_HEAD_B2, P_COMP_W1, P_COMP_B1, P_COMP_GAMMA, P_COMP_BETA, P_COMP_W2,
  P_COMP_B2, P_ATTN_W, P_ATTN_B, P_TRANSFER, P_ENC) = range(14)
 EGO_CAP = 128
+FT_SLOTS = 8
 
 _SIGNATURES = {
     "scgib_version": (c_int, []),
@@ -47,6 +48,14 @@ _SIGNATURES = {
                                             c_void_p, c_size_t, c_void_p]),
     "scgib_extract_backward_f32": (c_int, [POINTER(Dims), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                            c_size_t, c_void_p]),
+    "scgib_extract_forward_f32": (c_int, [POINTER(Dims), c_void_p, c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scgib_finetune_head_layout": (c_int64, [c_int32, c_int32, POINTER(c_int64), POINTER(c_int64)]),
+    "scgib_finetune_head_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "scgib_finetune_head_fwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                            c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scgib_finetune_head_bwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                            c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scgib_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p]),
     "scgib_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_char_p]),

@@ -246,12 +246,12 @@ extern "C" SCGIB_API size_t scgib_pretrain_workspace_bytes(const ScgibDims* d, i
   return carve(d, lo, B, N, E, Ns, Es, nullptr).bytes;
 }
 
-extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
-                                          const ScgibBatch* b, float* losses, float* interaction_map, float* Z,
-                                          float* noisy, float* graph_readout, void* workspace, size_t workspace_bytes,
-                                          void* stream_) {
+// features_only: stop after the head MLP (Z); the pre-training losses are not evaluated (fine-tuning forward)
+static int forward_impl(const ScgibDims* d, const float* params, float* bn_running, const ScgibBatch* b, float* losses,
+                        float* interaction_map, float* Z, float* noisy, float* graph_readout, void* workspace,
+                        size_t workspace_bytes, void* stream_, bool features_only) {
   if (!dims_ok(d)) return SCGIB_E_SHAPE;
-  if (!params || !losses || !workspace) return SCGIB_E_NULL;
+  if (!params || (!losses && !features_only) || !workspace) return SCGIB_E_NULL;
   int rc = check_batch(b);
   if (rc) return rc;
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)params & 15u) != 0) return SCGIB_E_ALIGN;
@@ -338,14 +338,14 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
                   params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.r_head, w.Z};
     PROF("head_fwd", launch_head_fwd(a, s));
   }
-  {
+  if (!features_only) {
     const int grid = num_sms();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
     PROF("recon_fwd", launch_recon_fwd(a, grid, s));
     PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, s));
   }
   const int js = contrastive_jsplit(b->B);
-  {
+  if (!features_only) {
     NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
     PROF("normalize", launch_normalize(a, s));
     ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum, w.zsplit};
@@ -354,7 +354,7 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
     else
       PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
   }
-  {
+  if (!features_only) {
     LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, w.kl, w.D, losses};
     PROF("loss_finalize", launch_loss_finalize(a, s));
   }
@@ -362,6 +362,21 @@ extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const fl
   if (noisy) cudaMemcpyAsync(noisy, w.noisy, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (graph_readout) cudaMemcpyAsync(graph_readout, w.readout, (size_t)b->B * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
   return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_pretrain_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
+                                          const ScgibBatch* b, float* losses, float* interaction_map, float* Z,
+                                          float* noisy, float* graph_readout, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  return forward_impl(d, params, bn_running, b, losses, interaction_map, Z, noisy, graph_readout, workspace,
+                      workspace_bytes, stream, false);
+}
+
+extern "C" SCGIB_API int scgib_extract_forward_f32(const ScgibDims* d, const float* params, float* bn_running,
+                                         const ScgibBatch* b, float* interaction_map, float* Z, float* noisy,
+                                         float* graph_readout, void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(d, params, bn_running, b, nullptr, interaction_map, Z, noisy, graph_readout, workspace,
+                      workspace_bytes, stream, true);
 }
 
 // gZ_ext == nullptr: gradients of scale . {KL, contrastive, recon};  gZ_ext != nullptr: gradients of <gZ_ext, Z> (the
@@ -506,6 +521,114 @@ extern "C" SCGIB_API int scgib_adam_step_f32(float* params, const float* grads, 
   if (n < 1 || step < 1) return SCGIB_E_RANGE;
   cudaStream_t s = (cudaStream_t)stream;
   PROF("adam", launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, s));
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- fine-tuning head (Set2Set + predict)
+namespace scgib {
+struct FtLayout { int64_t off[SCGIB_FT_SLOTS], size[SCGIB_FT_SLOTS], total; };
+static FtLayout ft_layout(int H, int C) {
+  FtLayout lo;
+  const int64_t sz[SCGIB_FT_SLOTS] = {(int64_t)4 * H * 2 * H, (int64_t)4 * H * H, 4 * H, 4 * H, (int64_t)H * 2 * H, H, (int64_t)C * H, C};
+  int64_t o = 0;
+  for (int i = 0; i < SCGIB_FT_SLOTS; ++i) { lo.off[i] = o; lo.size[i] = sz[i]; o += (sz[i] + 3) / 4 * 4; }
+  lo.total = o;
+  return lo;
+}
+struct FtWs { float *WlstmT, *Wp1T, *gates, *cst, *qstar, *alpha, *rp, *g_pre, *g_u, *dgates, *gp; size_t bytes; };
+static FtWs ft_carve(int H, int C, int T, int B, int N, void* base) {
+  FtWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  w.WlstmT = take((size_t)3 * H * 4 * H); w.Wp1T = take((size_t)2 * H * H);
+  w.gates = take((size_t)T * B * 4 * H); w.cst = take((size_t)T * B * H); w.qstar = take((size_t)T * B * 2 * H);
+  w.alpha = take((size_t)T * N); w.rp = take((size_t)B * H); w.g_pre = take((size_t)B * C); w.g_u = take((size_t)B * H);
+  w.dgates = take((size_t)T * B * 4 * H); w.gp = take(N);
+  w.bytes = o;
+  return w;
+}
+static bool ft_dims_ok(int H, int C, int T) { return (H == 64 || H == 128) && C >= 1 && C <= finetune_max_classes() && T >= 1 && T <= 8; }
+}  // namespace scgib
+
+extern "C" SCGIB_API int64_t scgib_finetune_head_layout(int32_t H, int32_t C, int64_t* offsets, int64_t* sizes) {
+  if (!ft_dims_ok(H, C, 1)) return SCGIB_E_SHAPE;
+  const FtLayout lo = ft_layout(H, C);
+  for (int i = 0; i < SCGIB_FT_SLOTS; ++i) {
+    if (offsets) offsets[i] = lo.off[i];
+    if (sizes) sizes[i] = lo.size[i];
+  }
+  return lo.total;
+}
+
+extern "C" SCGIB_API size_t scgib_finetune_head_workspace_bytes(int32_t H, int32_t C, int32_t T, int32_t B, int32_t N) {
+  if (!ft_dims_ok(H, C, T) || B < 1 || N < 1) return 0;
+  return ft_carve(H, C, T, B, N, nullptr).bytes;
+}
+
+extern "C" SCGIB_API int scgib_finetune_head_fwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
+                                           const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N, float* scores,
+                                           float* readout, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!ft_dims_ok(H, C, T)) return SCGIB_E_SHAPE;
+  if (!head_params || !Z || !graph_ptr || !scores || !workspace) return SCGIB_E_NULL;
+  if (B < 1 || N < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)head_params & 15u) != 0 || ((uintptr_t)Z & 15u) != 0) return SCGIB_E_ALIGN;
+  const FtLayout lo = ft_layout(H, C);
+  const FtWs w = ft_carve(H, C, T, B, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  TransposeJobs jobs;
+  jobs.n = 3;
+  jobs.job[0] = TransposeJob{head_params + lo.off[SCGIB_FT_LSTM_WIH], w.WlstmT, 4 * H, 2 * H};
+  jobs.job[1] = TransposeJob{head_params + lo.off[SCGIB_FT_LSTM_WHH], w.WlstmT + (size_t)2 * H * 4 * H, 4 * H, H};
+  jobs.job[2] = TransposeJob{head_params + lo.off[SCGIB_FT_PRED_W1], w.Wp1T, H, 2 * H};
+  PROF("ft_transpose_weights", launch_transposes(jobs, s));
+  FinetuneHeadFwdArgs a;
+  a.Z = Z; a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = H; a.C = C; a.T = T; a.sigmoid = sigmoid;
+  a.WlstmT = w.WlstmT; a.b_ih = head_params + lo.off[SCGIB_FT_LSTM_BIH]; a.b_hh = head_params + lo.off[SCGIB_FT_LSTM_BHH];
+  a.Wp1T = w.Wp1T; a.bp1 = head_params + lo.off[SCGIB_FT_PRED_B1];
+  a.Wp2 = head_params + lo.off[SCGIB_FT_PRED_W2]; a.bp2 = head_params + lo.off[SCGIB_FT_PRED_B2];
+  a.gates = w.gates; a.cst = w.cst; a.qstar = w.qstar; a.alpha = w.alpha; a.rp = w.rp; a.scores = scores;
+  PROF("finetune_head_fwd", launch_finetune_head_fwd(a, s));
+  if (readout)
+    cudaMemcpyAsync(readout, w.qstar + (size_t)(T - 1) * B * 2 * H, (size_t)B * 2 * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
+                                           const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N,
+                                           const float* scores, const float* g_scores, float* gZ, float* head_grads,
+                                           void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!ft_dims_ok(H, C, T)) return SCGIB_E_SHAPE;
+  if (!head_params || !Z || !graph_ptr || !scores || !g_scores || !gZ || !head_grads || !workspace) return SCGIB_E_NULL;
+  if (B < 1 || N < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)head_params & 15u) != 0 || ((uintptr_t)Z & 15u) != 0 ||
+      ((uintptr_t)gZ & 15u) != 0)
+    return SCGIB_E_ALIGN;
+  const FtLayout lo = ft_layout(H, C);
+  const FtWs w = ft_carve(H, C, T, B, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  FinetuneHeadBwdArgs a;
+  a.Z = Z; a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = H; a.C = C; a.T = T; a.sigmoid = sigmoid;
+  a.Wih = head_params + lo.off[SCGIB_FT_LSTM_WIH]; a.Whh = head_params + lo.off[SCGIB_FT_LSTM_WHH];
+  a.Wp1 = head_params + lo.off[SCGIB_FT_PRED_W1]; a.Wp2 = head_params + lo.off[SCGIB_FT_PRED_W2];
+  a.gates = w.gates; a.cst = w.cst; a.qstar = w.qstar; a.alpha = w.alpha; a.rp = w.rp; a.scores = scores;
+  a.g_scores = g_scores; a.g_pre = w.g_pre; a.g_u = w.g_u; a.dgates = w.dgates; a.gp = w.gp; a.gZ = gZ;
+  PROF("finetune_head_bwd", launch_finetune_head_bwd(a, s));
+  // weight gradients: fixed-order reductions over the graphs
+  float* g = head_grads;
+  if (T > 1) {   // the LSTM input of step t is q*_{t-1} (zero at t = 0)
+    PROF("ft_dWih", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WIH], 2 * H, (T - 1) * B, 4 * H, 2 * H, 0, s));
+    PROF("ft_dWhh", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WHH], H, (T - 1) * B, 4 * H, H, 0, s));
+  } else {
+    cudaMemsetAsync(g + lo.off[SCGIB_FT_LSTM_WIH], 0, (size_t)(lo.off[SCGIB_FT_LSTM_BIH] - lo.off[SCGIB_FT_LSTM_WIH]) * sizeof(float), s);
+  }
+  PROF("ft_dbias", launch_colsum(w.dgates, 4 * H, T * B, 4 * H, g + lo.off[SCGIB_FT_LSTM_BIH], g + lo.off[SCGIB_FT_LSTM_BHH], s));
+  PROF("ft_dWp1", launch_atb(w.g_u, H, w.qstar + (size_t)(T - 1) * B * 2 * H, 2 * H, g + lo.off[SCGIB_FT_PRED_W1], 2 * H, B, H, 2 * H, 0, s));
+  PROF("ft_dbp1", launch_colsum(w.g_u, H, B, H, g + lo.off[SCGIB_FT_PRED_B1], nullptr, s));
+  PROF("ft_dWp2", launch_atb(w.g_pre, C, w.rp, H, g + lo.off[SCGIB_FT_PRED_W2], H, B, C, H, 0, s));
+  PROF("ft_dbp2", launch_colsum(w.g_pre, C, B, C, g + lo.off[SCGIB_FT_PRED_B2], nullptr, s));
   return (int)cudaGetLastError();
 }
 

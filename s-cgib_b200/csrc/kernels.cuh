@@ -239,4 +239,31 @@ void launch_reduce_partials(const float* part, int64_t pstride, int nparts, cons
 void launch_adam(float* params, const float* grads, float* m, float* v, int64_t n, int64_t step, float lr, float b1,
                  float b2, float eps, float wd, float gscale, cudaStream_t s);
 
+// ---------------------------------------------------------------- finetune_kernels.cu
+// Fine-tuning head (Mainmodel_finetuning.forward, models.py:501-520): Set2Set(H, T iterations, 1 LSTM layer) -> predict MLP
+// -> optional sigmoid, one kernel per direction; per-graph state saved in the caller's workspace.
+struct FinetuneHeadFwdArgs {
+  const float* Z; const int32_t* graph_ptr; int B, N, H, C, T, sigmoid;
+  const float* WlstmT;                   // k-major [3H][4H] = [W_ih^T ; W_hh^T]
+  const float *b_ih, *b_hh;              // [4H]
+  const float* Wp1T; const float* bp1;   // k-major [2H][H], [H]
+  const float* Wp2; const float* bp2;    // natural [C][H], [C]
+  float *gates, *cst, *qstar, *alpha;    // saved: [T][B][4H] (activated i,f,g,o), [T][B][H], [T][B][2H], [T][N]
+  float *rp, *scores;                    // [B][H] predict hidden (post-ReLU), [B][C]
+};
+void launch_finetune_head_fwd(const FinetuneHeadFwdArgs& a, cudaStream_t s);
+struct FinetuneHeadBwdArgs {
+  const float* Z; const int32_t* graph_ptr; int B, N, H, C, T, sigmoid;
+  const float *Wih, *Whh, *Wp1, *Wp2;    // natural layouts
+  const float *gates, *cst, *qstar, *alpha, *rp, *scores;
+  const float* g_scores;                 // [B][C]
+  float *g_pre, *g_u, *dgates, *gp;      // [B][C], [B][H], [T][B][4H], [N] scratch
+  float* gZ;                             // [N][H]
+};
+void launch_finetune_head_bwd(const FinetuneHeadBwdArgs& a, cudaStream_t s);
+// out[m][n] (+)= sum_r A[r][m] * Bm[r][n], fixed order;  out[c] = sum_r A[r][c]
+void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, int R, int M, int Nn, int accumulate, cudaStream_t s);
+void launch_colsum(const float* A, int lda, int R, int M, float* out, float* out2, cudaStream_t s);
+int finetune_max_classes();
+
 }  // namespace scgib

@@ -282,6 +282,26 @@ class PretrainEngine:
                                                         ws.numel(), st), "pretrain_backward")
         return self.grads
 
+    def forward_features(self, b: DeviceBatch, gate_u=None, feat_u=None, want_imap=False, update_running=True,
+                         params: Optional[torch.Tensor] = None):
+        """Feature path only (transfer_d -> extract_features -> head MLP; models.py:508-513), no pre-training losses.
+        Returns Z [N,64] (and interaction_map [N,128] with ``want_imap``); ``extract_backward`` is its backward."""
+        if gate_u is None:
+            gate_u, feat_u = self.draw_noise(b.N)
+        self._last = (b, gate_u.contiguous(), feat_u.contiguous())
+        cb = b.c_struct(self._last[1], self._last[2])
+        ws = self._workspace(b)
+        Z = torch.empty(b.N, HID, device=self.device)
+        imap = torch.empty(b.N, 2 * HID, device=self.device) if want_imap else None
+        p = self.params if params is None else params
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_extract_forward_f32(
+            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if update_running else None,
+            ctypes.byref(cb), _lib.ptr(imap), _lib.ptr(Z), None, None, _lib.ptr(ws), ws.numel(), st), "extract_forward")
+        if update_running:
+            self.num_batches_tracked += 1
+        return (Z, imap) if want_imap else Z
+
     def extract_backward(self, gZ: torch.Tensor, params: Optional[torch.Tensor] = None):
         """Gradients of <gZ, Z> into the flat ``grads`` buffer (overwritten): the backward of ``extract_features`` + head
         MLP for a downstream head that consumes Z (fine-tuning, models.py:501-520).  Call after ``forward``."""
@@ -335,3 +355,77 @@ class PretrainEngine:
             slot["done"] = torch.cuda.Event()
             slot["done"].record(torch.cuda.current_stream(self.device))
         return losses
+
+
+FT_NAMES = ["s2s.lstm.weight_ih_l0", "s2s.lstm.weight_hh_l0", "s2s.lstm.bias_ih_l0", "s2s.lstm.bias_hh_l0",
+            "predict.0.weight", "predict.0.bias", "predict.2.weight", "predict.2.bias"]
+
+
+class FinetuneHead:
+    """Set2Set(hidden, n_iters, 1) readout + predict MLP (+ sigmoid) of Mainmodel_finetuning.forward
+    (models.py:515-520) on the CUDA path: one forward kernel, one backward kernel + fixed-order weight-gradient
+    reductions (csrc/finetune_kernels.cu).  Parameters / gradients live in one flat buffer (slots = FT_NAMES)."""
+
+    def __init__(self, hidden: int, num_out: int, n_iters: int = 2, sigmoid: bool = True, device="cuda:0"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FinetuneHead needs a CUDA device: the hot path has no CPU fallback")
+        self.H, self.C, self.T, self.sigmoid = int(hidden), int(num_out), int(n_iters), bool(sigmoid)
+        off = (ctypes.c_int64 * _lib.FT_SLOTS)()
+        sz = (ctypes.c_int64 * _lib.FT_SLOTS)()
+        total = int(self.lib.scgib_finetune_head_layout(self.H, self.C, off, sz))
+        if total < 0:
+            _lib.check(total, "finetune_head_layout")
+        self.total, self.offsets, self.sizes = total, list(off), list(sz)
+        H, C = self.H, self.C
+        self.shapes = [(4 * H, 2 * H), (4 * H, H), (4 * H,), (4 * H,), (H, 2 * H), (H,), (C, H), (C,)]
+        self.names = list(FT_NAMES)
+        self.params = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self._ws = None
+        self._saved = None
+
+    def views(self, grads=False):
+        buf = self.grads if grads else self.params
+        return OrderedDict((n, buf[o:o + s].view(shp)) for n, o, s, shp in zip(self.names, self.offsets, self.sizes, self.shapes))
+
+    def load_state_dict(self, sd):
+        for n, t in self.views().items():
+            t.copy_(sd[n].reshape(t.shape))
+
+    def _workspace(self, B, N):
+        need = self.lib.scgib_finetune_head_workspace_bytes(self.H, self.C, self.T, B, N)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(int(need * 1.1) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, Z: torch.Tensor, graph_ptr: torch.Tensor, want_readout=False):
+        """scores [B,C] (after the sigmoid if enabled); with ``want_readout`` also the Set2Set output q* [B,2H]."""
+        Z = Z.contiguous()
+        B, N = graph_ptr.numel() - 1, Z.shape[0]
+        assert Z.shape[1] == self.H and Z.dtype == torch.float32 and graph_ptr.dtype == torch.int32
+        ws = self._workspace(B, N)
+        scores = torch.empty(B, self.C, device=self.device)
+        readout = torch.empty(B, 2 * self.H, device=self.device) if want_readout else None
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_finetune_head_fwd_f32(_lib.ptr(self.params), self.H, self.C, self.T, int(self.sigmoid),
+                                                        _lib.ptr(Z), _lib.ptr(graph_ptr), B, N, _lib.ptr(scores),
+                                                        _lib.ptr(readout), _lib.ptr(ws), ws.numel(), st), "finetune_head_fwd")
+        self._saved = (Z, graph_ptr, scores)
+        return (scores, readout) if want_readout else scores
+
+    def backward(self, g_scores: torch.Tensor):
+        """Returns gZ [N,H]; the head's parameter gradients are written to ``self.grads`` (overwritten)."""
+        Z, graph_ptr, scores = self._saved
+        B, N = graph_ptr.numel() - 1, Z.shape[0]
+        g_scores = g_scores.contiguous().float()
+        gZ = torch.empty_like(Z)
+        ws = self._workspace(B, N)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.scgib_finetune_head_bwd_f32(_lib.ptr(self.params), self.H, self.C, self.T, int(self.sigmoid),
+                                                        _lib.ptr(Z), _lib.ptr(graph_ptr), B, N, _lib.ptr(scores),
+                                                        _lib.ptr(g_scores), _lib.ptr(gZ), _lib.ptr(self.grads),
+                                                        _lib.ptr(ws), ws.numel(), st), "finetune_head_bwd")
+        return gZ

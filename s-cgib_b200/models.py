@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .engine import HID, DeviceBatch, PretrainEngine, bn_buffer_names, param_names
+from .engine import FT_NAMES, HID, DeviceBatch, FinetuneHead, PretrainEngine, bn_buffer_names, param_names
 from .graph import BatchedGraph, EgoBatch, khop_ego_batch
 
 DEFAULT_GIN_LAYERS = 4   # reference models.py:57-58: ``num_layers = 5; range(num_layers - 1)``
@@ -84,7 +84,9 @@ class _Set2SetParams(nn.Module):
 
     def __init__(self, input_dim, n_iters, n_layers):
         super().__init__()
+        self.input_dim, self.output_dim, self.n_iters, self.n_layers = input_dim, 2 * input_dim, n_iters, n_layers
         self.lstm = nn.LSTM(2 * input_dim, input_dim, n_layers)
+        self.lstm.reset_parameters()          # DGL's Set2Set.__init__ re-initialises the LSTM (second RNG draw)
 
 
 class _PretrainFn(torch.autograd.Function):
@@ -313,3 +315,134 @@ class Mainmodel_continue(_HotPathMixin, nn.Module):
 
     __getstate__ = Mainmodel.__getstate__
     __setstate__ = Mainmodel.__setstate__
+
+
+class _FinetuneFn(torch.autograd.Function):
+    """transfer_d -> model.extract_features -> MLP -> Set2Set -> predict (-> sigmoid) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, owner, batch, gate_u, feat_u, *params):
+        eng, head = owner._bridge.engine, owner._head
+        Z = eng.forward_features(batch, gate_u, feat_u, update_running=owner.training)
+        scores = head.forward(Z, batch.g.graph_ptr)
+        ctx.owner = owner
+        return scores
+
+    @staticmethod
+    def backward(ctx, g_scores):
+        owner = ctx.owner
+        eng, head = owner._bridge.engine, owner._head
+        gZ = head.backward(g_scores)
+        eng.extract_backward(gZ)
+        gv, hv = eng.grad_views(), head.views(grads=True)
+        grads = [gv[n].clone() for n in owner._bridge.slot_names] + [hv[n].clone() for n in FT_NAMES]
+        return (None, None, None, None) + tuple(grads)
+
+
+class Mainmodel_finetuning(nn.Module):
+    """reference models.py:358-543: fine-tuning wrapper around a pickled pre-trained model.  Owns transfer_d, MLP, the
+    Set2Set readout and the predict head; the loaded ``self.model`` supplies the encoders, compressor and attention layer
+    through ``extract_features`` with only the ``layers.2`` parameters left trainable (models.py:424-435).
+    ``forward`` returns ``(scores, 0, 0, 0)`` like the reference; the loss helpers are the reference's."""
+
+    def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, num_classes, cp_filename, encoder):
+        super().__init__()
+        _check_args(args, encoder)
+        self.tau = 1.0
+        self.dataset = args.dataset
+        self.readout = args.readout_f
+        self.gin_layers = int(getattr(args, "gin_layers", DEFAULT_GIN_LAYERS))
+        self.in_dim_raw = in_dim
+        self.s2s = _Set2SetParams(hidden_dim, 2, 1)
+        self.in_dim = args.d_transfer
+        self.transfer_d = nn.Linear(in_dim, self.in_dim, bias=False)
+        self.batch_size = args.batch_size
+        self.useAtt = args.useAtt
+        self.embedding_h = nn.Linear(self.in_dim, hidden_dim, bias=False)
+        self.hidden_dim = hidden_dim
+        self.k_transition = k_transition
+        self.reduce_d = nn.Linear(2 * self.hidden_dim, self.hidden_dim)
+        self.attn_layer = nn.Linear(2 * self.hidden_dim, 1)
+        self.num_nodes = -1
+        self.device = args.device
+        self.tasks = ['ZINC', 'Peptides-struct', 'FreeSolv', 'ESOL']
+        if args.task == "graph_regression":
+            out_dim = 1
+        elif args.task == "graph_classification":
+            out_dim = num_classes
+        else:
+            raise NotImplementedError("task must be graph_regression or graph_classification (models.py:385-399)")
+        self.predict = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                     nn.Linear(self.hidden_dim, out_dim))
+        self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                 nn.Linear(self.hidden_dim, self.hidden_dim))
+        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        print("Loading pre-trained model .pt  ... ")
+        self.model = torch.load(cp_filename, map_location=args.device, weights_only=False)
+        for name, para in self.model.named_parameters():     # models.py:424-435: the last list entry decides
+            para.requires_grad = "layers.2" in name
+        self.compressor = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.BatchNorm1d(self.hidden_dim),
+                                        nn.ReLU(), nn.Linear(self.hidden_dim, 1))
+        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+        self._head = None
+
+    __getstate__ = Mainmodel.__getstate__
+
+    def __setstate__(self, st):
+        Mainmodel.__setstate__(self, st)
+        self._head = None
+
+    _device_batch = _HotPathMixin._device_batch
+    _noise = _HotPathMixin._noise
+
+    def _sync_head(self, device):
+        device = torch.device(device)
+        sigmoid = self.dataset not in self.tasks              # models.py:516-520
+        if self._head is None or self._head.device != device:
+            self._head = FinetuneHead(self.hidden_dim, self.predict[2].out_features, n_iters=self.s2s.n_iters,
+                                      sigmoid=sigmoid, device=device)
+        views = self._head.views()
+        params = []
+        for name in FT_NAMES:
+            obj = self
+            parts = name.split(".")
+            for p in parts[:-1]:
+                obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+            prm = getattr(obj, parts[-1])
+            v = views[name]
+            if prm.data_ptr() != v.data_ptr():
+                v.copy_(prm.data.to(device).reshape(v.shape))
+                prm.data = v
+            params.append(prm)
+        return params
+
+    def forward(self, batch_g, batch_x, flatten_batch_subgraphs, x_subs, current_epoch, edge_index, k_transition,
+                device, batch_size=2):
+        """reference models.py:501-520 -> (scores [B,C], 0, 0, 0)."""
+        self.batch_size = batch_size
+        self.device = device
+        params = self._bridge.sync(device) + self._sync_head(device)
+        self._bridge.training = self.training
+        b = self._device_batch(batch_g, batch_x, flatten_batch_subgraphs, device)
+        gate_u, feat_u = self._noise(b.N, b.g.device)
+        scores = _FinetuneFn.apply(self, b, gate_u, feat_u, *params)
+        if self.training:
+            _HotPathMixin._bump_batches_tracked(self, b.B)
+        return scores, 0, 0, 0
+
+    # loss helpers: reference models.py:522-543 (operate on the [B,C] scores)
+    def loss(self, scores, targets):
+        return nn.BCELoss()(scores.float(), targets.float())
+
+    def loss_CrossEntropy(self, scores, targets):
+        return nn.CrossEntropyLoss()(scores.to(torch.float32), targets.squeeze(dim=-1))
+
+    def loss_RMSE(self, scores, targets):
+        return torch.sqrt(nn.MSELoss()(scores, targets))
+
+    def BCEWithLogitsLoss(self, scores, targets):
+        return nn.BCEWithLogitsLoss()(scores, targets)
+
+    def lossMAE(self, scores, targets):
+        return nn.L1Loss()(scores, targets)

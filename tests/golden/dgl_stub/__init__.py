@@ -71,7 +71,8 @@ class GINConv(nn.Module):
 
 
 class Set2Set(nn.Module):
-    """Parameter container only (the pre-training default readout is 'sum')."""
+    """dgl.nn.pytorch.glob.Set2Set(input_dim, n_iters, n_layers), restated from DGL 1.1.0: broadcast_nodes /
+    softmax_nodes / sum_nodes are written out with segment ids."""
 
     def __init__(self, input_dim, n_iters, n_layers):
         super().__init__()
@@ -80,7 +81,21 @@ class Set2Set(nn.Module):
         self.lstm.reset_parameters()
 
     def forward(self, graph, feat):
-        raise NotImplementedError("Set2Set readout is outside the golden scope")
+        n = graph.batch_num_nodes()
+        batch_size = n.numel()
+        seg = torch.repeat_interleave(torch.arange(batch_size), n)
+        h = (feat.new_zeros((self.n_layers, batch_size, self.input_dim)),
+             feat.new_zeros((self.n_layers, batch_size, self.input_dim)))
+        q_star = feat.new_zeros(batch_size, self.output_dim)
+        for _ in range(self.n_iters):
+            q, h = self.lstm(q_star.unsqueeze(0), h)
+            q = q.view(batch_size, self.input_dim)
+            e = (feat * q[seg]).sum(dim=-1, keepdim=True)                      # feat * broadcast_nodes(graph, q)
+            alpha = torch.cat([torch.softmax(t, dim=0) for t in torch.split(e, n.tolist())])   # softmax_nodes
+            r = feat * alpha
+            readout = torch.zeros(batch_size, self.input_dim, dtype=feat.dtype).index_add(0, seg, r)   # sum_nodes
+            q_star = torch.cat([q, readout], dim=-1)
+        return q_star
 
 
 class _Dummy:

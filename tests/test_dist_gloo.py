@@ -82,8 +82,13 @@ def test_two_rank_gloo_allreduce_matches_single_process():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    g0, _ = _shard_grads(0, 6)
-    g1, _ = _shard_grads(6, 12)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)              # same summation order as the workers (ReLU masks are rounding-sensitive)
+    try:
+        g0, _ = _shard_grads(0, 6)
+        g1, _ = _shard_grads(6, 12)
+    finally:
+        torch.set_num_threads(nthreads)
     mean = ((g0 + g1) / 2).numpy()
     for rank, g, p in res:
         # workers run torch single-threaded, the check multi-threaded: fp32 summation order differs

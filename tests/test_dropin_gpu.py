@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from oracle.graph_ref import ego_batch_ref, synth_batch
 from oracle.scgib_oracle import OracleMainmodel, normalize_rows, tgraph_from_ego, tgraph_from_ref
-from tests.helpers import product_graph, rel
+from tests.helpers import fp64_truth, product_graph, rel
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -53,8 +53,18 @@ def test_mainmodel_forward_backward_matches_oracle(monkeypatch):
     refg = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
     got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
     assert set(refg) <= set(got)
-    errs = sorted(rel(got[n], refg[n]) for n in refg if float(refg[n].abs().max()) > 1e-3)
-    assert errs[len(errs) // 2] <= 5e-5 and errs[-1] <= 5e-3
+    # gradient policy of tests/helpers.py: measured against the fp64 oracle, next to the fp32 oracle's own distance
+    # from it (a ReLU unit at the kink flips its mask between two correct fp32 implementations)
+    _, truth = fp64_truth(ref, g, e, gate_u, feat_u)
+    errs = []
+    for n in refg:
+        if float(truth[n].abs().max()) <= 1e-3:
+            continue
+        e_got, e_ref = rel(got[n].cpu(), truth[n]), rel(refg[n], truth[n])
+        assert e_got <= max(5e-3, 5.0 * e_ref), (n, e_got, e_ref)
+        errs.append(e_got)
+    errs.sort()
+    assert errs[len(errs) // 2] <= 5e-5
     # BN running statistics are live module buffers
     assert rel(m.Encoder1.batch_norms[0].running_mean, ref.Encoder1.batch_norms[0].running_mean) <= 1e-5
     assert int(m.compressor[1].num_batches_tracked) == 48

@@ -99,3 +99,43 @@ def test_reference_noise_stream_is_reproduced_without_injection(path):
     torch.manual_seed(fx["meta"]["noise_seed"])
     out = m.forward_faithful(tg, x, te, x[ego_nodes])
     assert rel(out["noisy"], fx["out"]["noisy"]) <= 2e-6
+
+
+# ---------------------------------------------------------------- fine-tuning
+FT_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "finetune_*.pt")))
+
+
+def finetune_oracle_from_fixture(fx, dtype=torch.float32):
+    from oracle.scgib_oracle import OracleFinetune
+    inner = OracleMainmodel(9, 64, 32, 4)
+    m = OracleFinetune(inner, 9, 64, 32, num_classes=fx["meta"]["num_classes"])
+    missing, unexpected = m.load_state_dict(fx["state"], strict=False)
+    assert not unexpected
+    m.train()
+    return m.to(dtype)
+
+
+@pytest.mark.parametrize("path", FT_GOLD, ids=[os.path.basename(p) for p in FT_GOLD])
+def test_finetune_oracle_matches_reference(path):
+    """OracleFinetune (Set2Set restatement + freeze rule) vs the unmodified Mainmodel_finetuning: scores, loss, the 21
+    gradients of one train_pep_func step, and which parameters are trainable."""
+    fx, g, e = load_fixture(path)
+    m = finetune_oracle_from_fixture(fx)
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    x = normalize_rows(torch.from_numpy(g.x))
+    ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    out = m(tg, x, te, x[ego_nodes], gate_u, feat_u)
+    assert rel(out["scores"], fx["out"]["scores"]) <= 2e-6
+    loss = torch.nn.functional.binary_cross_entropy(out["scores"], fx["targets"]) / 2
+    assert abs(float(loss) - float(fx["out"]["loss"])) <= 2e-6 * abs(float(fx["out"]["loss"]))
+    assert sorted(n for n, p in m.named_parameters() if p.requires_grad) == fx["trainable"]
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(grads) == set(fx["grads"])
+    gmax = max(float(v.abs().max()) for v in fx["grads"].values())
+    for n, gref in fx["grads"].items():
+        if float(gref.abs().max()) <= 1e-6 * gmax:          # mathematically zero (bias in front of a BatchNorm)
+            assert float(grads[n].abs().max()) <= 1e-5 * gmax, n
+            continue
+        assert rel(grads[n], gref) <= 1e-4, (n, rel(grads[n], gref))
