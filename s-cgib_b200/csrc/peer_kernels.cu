@@ -49,7 +49,13 @@ allreduce_adam_kernel(PeerPtrs pp, int rank, int world, unsigned int seq, float*
   // 2. wait for every rank (flags only grow; a rank that is ahead has seq + 1)
   if (threadIdx.x < world) {
     const unsigned int* f = pp.flags[rank] + threadIdx.x;
-    while ((int)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
+    unsigned long long t0 = 0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) __trap();     // a peer died: fail the launch (20 s) instead of hanging the GPU
+    }
   }
   __syncthreads();
   // 3. rank-ordered sum of the peers' gradients + Adam (L2-in-gradient weight decay, torch.optim.Adam update order)
