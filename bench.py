@@ -42,6 +42,58 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlClockSampler:
+    """SM clock + throttle reasons read through NVML (nvidia_ml_py) every 5 ms from a thread while the timed region
+    runs: a 100-step timed region is ~0.25 s, too short for nvidia-smi's own start-up."""
+
+    def __init__(self, torch_index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+        try:
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+        self.sm, self.reasons, self.stop_flag = [], set(), False
+        self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+    def _loop(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml"}
+
+
+def make_clock_sampler(torch_index, smi_index):
+    try:
+        return NvmlClockSampler(torch_index)
+    except Exception:
+        return ClockSampler(smi_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -141,6 +193,133 @@ def run_reference(args, rank, emit):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Secondary workload (BASELINE configs[4]): fine-tuning step of Mainmodel_finetuning
+# ----------------------------------------------------------------------------------------------------
+def cpu_finetune_run(shape, batch, k=1, budget_s=10.0):
+    import numpy as np
+    from oracle.graph_ref import ego_batch_ref, synth_batch
+    from oracle.scgib_oracle import OracleFinetune, OracleMainmodel, normalize_rows, tgraph_from_ego, tgraph_from_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = OracleFinetune(OracleMainmodel(9), 9, num_classes=10)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    g = synth_batch(100, batch, shape)
+    e = ego_batch_ref(g, k)
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    tg, te, xs = tgraph_from_ref(g), tgraph_from_ego(e), x[en]
+    y = (torch.rand(batch, 10) < 0.1).float()
+
+    def step():
+        opt.zero_grad()
+        out = model(tg, x, te, xs)
+        (torch.nn.functional.binary_cross_entropy(out["scores"], y) / 2).backward()
+        opt.step()
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < budget_s:
+        step(); n += 1
+    dt = time.perf_counter() - t0
+    return {"value": batch * n / dt, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of B=%d %s-shape graphs, Mainmodel_finetuning fwd+bwd+Adam (per-graph loops), %.1f s wall" % (n, batch, shape, dt)}
+
+
+def run_finetune(args, emit):
+    """graphs/s of one fine-tuning step (features forward, Set2Set + predict head, BCE gradient, head backward, feature
+    backward, Adam on both flat buffers) on one GPU; hidden = 64 (the reference default --dims)."""
+    from scgib_b200 import _lib
+    from scgib_b200.engine import FinetuneHead, PretrainEngine
+    from scgib_b200.synth import synth_batch
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)
+    head = FinetuneHead(64, 10, n_iters=2, sigmoid=True, device=dev)
+    head.params.copy_((torch.rand(head.total, generator=torch.Generator().manual_seed(1)) * 0.25 - 0.125).to(dev))
+    hm, hv = torch.zeros_like(head.params), torch.zeros_like(head.params)
+    B = args.batch
+    nb = 3
+    host = [synth_batch(50 + i, B, args.shape).pin_memory() for i in range(nb)]
+    resident = [h.to(dev) for h in host]
+    targets = (torch.rand(B, 10, device=dev) < 0.1).float()
+    state = {"n": 0}
+
+    def run_steps(src, steps, read):
+        handle = eng.prefetch_batch(src[0], args.k)
+        for i in range(steps):
+            b = eng.wait_batch(handle)
+            Z = eng.forward_features(b)
+            scores = head.forward(Z, b.g.graph_ptr)
+            g_s = (scores - targets) / (scores * (1 - scores)).clamp_min(1e-12) / (2.0 * B * 10)   # d(BCE/2)/d scores
+            gZ = head.backward(g_s)
+            eng.extract_backward(gZ)
+            eng.adam_step(lr=1e-4, weight_decay=0.0)
+            state["n"] += 1
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.scgib_adam_step_f32(_lib.ptr(head.params), _lib.ptr(head.grads), _lib.ptr(hm), _lib.ptr(hv),
+                                               head.total, state["n"], 1e-4, 0.9, 0.999, 1e-8, 0.0, 1.0, st), "adam")
+            slot = getattr(b, "_slot", None)
+            if slot is not None:
+                slot["done"] = torch.cuda.Event(); slot["done"].record(torch.cuda.current_stream(dev))
+            if i + 1 < steps:
+                handle = eng.prefetch_batch(src[(i + 1) % nb], args.k)
+            if read:
+                state["scores"] = scores.cpu()
+        state["b"] = b
+
+    def timed(src, steps, read):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_steps(src, steps, read); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    run_steps(resident, max(args.warmup, 3), False)
+    sampler = make_clock_sampler(0, 0)
+    sampler.start()
+    ms = timed(resident, args.steps, False)
+    clocks = sampler.stop()
+    run_steps(host, 3, True)
+    ms_e2e = timed(host, args.steps, True)
+    prof = {}
+    lib.scgib_profile_enable(1)
+    run_steps(resident, 1, False)
+    torch.cuda.synchronize()
+    name, t = ctypes.c_char_p(), ctypes.c_float()
+    for j in range(lib.scgib_profile_count()):
+        lib.scgib_profile_get(j, ctypes.byref(name), ctypes.byref(t))
+        cur = prof.setdefault(name.value.decode(), [0.0, 0]); cur[0] += t.value; cur[1] += 1
+    nlaunch = lib.scgib_profile_count()
+    lib.scgib_profile_enable(0)
+    b = state["b"]
+    hbm, peak_src = peaks()
+    dom = max(prof, key=lambda k_: prof[k_][0])
+    V = b.N + b.Ns
+    abytes = V * 2 * (64 + 64) * 4 if dom.startswith("gin_bwd_main") else V * (64 + 64) * 4 + 4 * (V + 2 + b.E + b.Es)
+    achieved = abytes / (prof[dom][0] / prof[dom][1] * 1e-3) / 1e9
+    h2d = sum(t_.numel() * t_.element_size() for t_ in (host[0].graph_ptr, host[0].indptr, host[0].indices, host[0].ndata["x"]))
+    line = {"metric": "finetune graphs/s (%s-shape GIN-4x64 k=%d, Set2Set readout)" % (args.shape, args.k),
+            "value": B * args.steps / (ms * 1e-3), "unit": "graphs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "Mainmodel_finetuning step (ego extraction + features fwd + Set2Set/predict head + BCE + bwd + Adam), "
+                                   "GIN-4x64 (reference default --dims 64; BASELINE configs[4] names 128: open), k=%d, batch %d %s-shape graphs"
+                                   % (args.k, B, args.shape),
+                       "nodes": b.N, "edges": b.E, "ego_rows": b.Ns, "ego_edges": b.Es,
+                       "l2": "no flush: per-step working set exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": B * 10 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": (nlaunch + 8) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes},
+            "kernels": {k_: {"ms_per_step": v[0], "launches_per_step": v[1]} for k_, v in prof.items()}}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_finetune_run(args.shape, 32 if args.shape == "peptides" else 128, args.k)
+    emit(line)
+
+
+# ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +329,9 @@ def main():
     ap.add_argument("--k", type=int, default=1)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
+                    help="pretrain = the headline metric (default); finetune = Mainmodel_finetuning step (1 GPU)")
+    ap.add_argument("--shape", default="pcqm", choices=["pcqm", "peptides"], help="synthetic molecule shape (finetune workload)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -169,6 +351,12 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == "finetune":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+        if rank == 0:
+            run_finetune(args, emit)
+        return
 
     import torch.distributed as dist
     from scgib_b200 import _lib
@@ -231,14 +419,31 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    # third feed: the dataset resident in HBM, a step's input is its B molecule ids (GPU-side batch assembly)
+    from scgib_b200.graph import DeviceDataset, batch as batch_graphs
+    dataset = DeviceDataset.from_batched(batch_graphs(host), dev)
+    gen = torch.Generator().manual_seed(77 + rank)
+    id_lists = [torch.randperm(len(dataset), generator=gen)[:args.batch].to(torch.int32).pin_memory() for _ in range(8)]
+
+    def step_ids(steps):
+        handle = eng.prefetch_ids(dataset, id_lists[0], args.k)
+        for i in range(steps):
+            b = eng.wait_batch(handle)
+            losses = eng.train_step(b, world_size=world)
+            if i + 1 < steps:
+                handle = eng.prefetch_ids(dataset, id_lists[(i + 1) % len(id_lists)], args.k)
+            state["loss"] = losses.cpu()
+
     step_resident(args.warmup)
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    sampler = make_clock_sampler(local_rank, torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     if rank == 0:
         sampler.start()
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e(3)
     ms_e2e = timed(step_e2e, args.steps)
+    step_ids(3)
+    ms_ids = timed(step_ids, args.steps)
 
     # ---- per-kernel timing pass (CUDA events on the launching stream around every launch of the library)
     prof = {}
@@ -302,6 +507,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
+            "e2e_resident_dataset": {"value": graphs / (ms_ids * 1e-3), "unit": UNIT, "h2d_bytes_per_step": args.batch * 4,
+                                     "d2h_bytes_per_step": 16, "ms_per_step": ms_ids / args.steps,
+                                     "note": "dataset shard (%d molecules, %.1f MB) resident in HBM; per step only the B molecule ids "
+                                             "cross PCIe, the batch is assembled on the GPU (scgib_batch_assemble_*)"
+                                             % (len(dataset), dataset.nbytes() / 1e6)},
             "gpu_launches": (nlaunch + 5) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,

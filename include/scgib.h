@@ -129,6 +129,24 @@ SCGIB_API int scgib_ego_fill(const int32_t* indptr, const int32_t* indices, int3
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * On-device batch assembly  (replaces DataLoader + MoleculeDataset.collate + dgl.batch: molecules.py:349-362,
+ * exp_pretraining.py:283, 303-306, and the per-step H2D of the batch).  The packed dataset shard - every molecule of the
+ * dataset as ONE symmetric CSR: mol_ptr[M+1] node offsets, ds_indptr[Nt+1], ds_indices[Et] (dataset-global node ids),
+ * ds_x[Nt,F] - stays resident in HBM; a mini-batch is a device array of B molecule ids (any order, repeats allowed).
+ * dgl.batch semantics: molecules in list order, node / edge ids offset.  Two phases around one host read of (N, E):
+ *   1. count: graph_ptr[B+1], edge_ptr[B+1] (exclusive scans; graph_ptr[B] = N, edge_ptr[B] = E)
+ *   2. fill : indptr[N+1], indices[E], x[N,F] of the batch.
+ * ------------------------------------------------------------------------------------------ */
+SCGIB_API size_t scgib_batch_workspace_bytes(int32_t B);
+SCGIB_API int scgib_batch_assemble_count(const int32_t* mol_ptr, const int32_t* ds_indptr, const int32_t* ids, int32_t B,
+                                         int32_t* graph_ptr, int32_t* edge_ptr, void* workspace, size_t workspace_bytes,
+                                         void* stream);
+SCGIB_API int scgib_batch_assemble_fill(const int32_t* mol_ptr, const int32_t* ds_indptr, const int32_t* ds_indices,
+                                        const float* ds_x, int32_t F, const int32_t* ids, int32_t B,
+                                        const int32_t* graph_ptr, const int32_t* edge_ptr, int32_t* indptr,
+                                        int32_t* indices, float* x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole pre-training step (Mainmodel.forward / Mainmodel_continue.forward, models.py:662-700,
  * 1158-1195, + loss.backward(), exp_pretraining.py:315-322).
  *

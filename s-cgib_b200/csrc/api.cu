@@ -140,7 +140,7 @@ static size_t small_part_floats(int N, int Ns) {
   const size_t a2 = (size_t)num_sms() * 3 * HID * 2;                  // gin_tc2: per-CTA (n, mean, M2) in fp64
   a = a > a2 ? a : a2;
   size_t b = (size_t)(gin_bwd_pre_grid(N + Ns) + 2) * 2 * HID;       // dgamma/dbeta partials (per problem of a shared launch)
-  size_t c = (size_t)2 * num_sms() * 5 * HID;                        // gate partials
+  size_t c = (size_t)4 * num_sms() * 5 * HID;                        // gate partials
   size_t d = (size_t)input_proj_bwd_grid(N, Ns) * DTR * 32;          // transfer_d partials
   size_t m = a > b ? a : b;
   m = m > c ? m : c;
@@ -535,7 +535,7 @@ static FtLayout ft_layout(int H, int C) {
   lo.total = o;
   return lo;
 }
-struct FtWs { float *WlstmT, *Wp1T, *gates, *cst, *qstar, *alpha, *rp, *g_pre, *g_u, *dgates, *gp; size_t bytes; };
+struct FtWs { float *WlstmT, *Wp1T, *gates, *cst, *qstar, *alpha, *rp, *g_pre, *g_u, *dgates, *gp, *scratch; size_t bytes; };
 static FtWs ft_carve(int H, int C, int T, int B, int N, void* base) {
   FtWs w;
   char* p = (char*)base;
@@ -545,6 +545,7 @@ static FtWs ft_carve(int H, int C, int T, int B, int N, void* base) {
   w.gates = take((size_t)T * B * 4 * H); w.cst = take((size_t)T * B * H); w.qstar = take((size_t)T * B * 2 * H);
   w.alpha = take((size_t)T * N); w.rp = take((size_t)B * H); w.g_pre = take((size_t)B * C); w.g_u = take((size_t)B * H);
   w.dgates = take((size_t)T * B * 4 * H); w.gp = take(N);
+  w.scratch = take((size_t)atb_splits(T * B) * 4 * H * 2 * H);     // row-split partials of the weight-gradient reductions
   w.bytes = o;
   return w;
 }
@@ -619,16 +620,16 @@ extern "C" SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, i
   // weight gradients: fixed-order reductions over the graphs
   float* g = head_grads;
   if (T > 1) {   // the LSTM input of step t is q*_{t-1} (zero at t = 0)
-    PROF("ft_dWih", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WIH], 2 * H, (T - 1) * B, 4 * H, 2 * H, 0, s));
-    PROF("ft_dWhh", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WHH], H, (T - 1) * B, 4 * H, H, 0, s));
+    PROF("ft_dWih", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WIH], 2 * H, nullptr, (T - 1) * B, 4 * H, 2 * H, w.scratch, s));
+    PROF("ft_dWhh", launch_atb(w.dgates + (size_t)B * 4 * H, 4 * H, w.qstar, 2 * H, g + lo.off[SCGIB_FT_LSTM_WHH], H, nullptr, (T - 1) * B, 4 * H, H, w.scratch, s));
   } else {
     cudaMemsetAsync(g + lo.off[SCGIB_FT_LSTM_WIH], 0, (size_t)(lo.off[SCGIB_FT_LSTM_BIH] - lo.off[SCGIB_FT_LSTM_WIH]) * sizeof(float), s);
   }
-  PROF("ft_dbias", launch_colsum(w.dgates, 4 * H, T * B, 4 * H, g + lo.off[SCGIB_FT_LSTM_BIH], g + lo.off[SCGIB_FT_LSTM_BHH], s));
-  PROF("ft_dWp1", launch_atb(w.g_u, H, w.qstar + (size_t)(T - 1) * B * 2 * H, 2 * H, g + lo.off[SCGIB_FT_PRED_W1], 2 * H, B, H, 2 * H, 0, s));
-  PROF("ft_dbp1", launch_colsum(w.g_u, H, B, H, g + lo.off[SCGIB_FT_PRED_B1], nullptr, s));
-  PROF("ft_dWp2", launch_atb(w.g_pre, C, w.rp, H, g + lo.off[SCGIB_FT_PRED_W2], H, B, C, H, 0, s));
-  PROF("ft_dbp2", launch_colsum(w.g_pre, C, B, C, g + lo.off[SCGIB_FT_PRED_B2], nullptr, s));
+  PROF("ft_dbias", launch_atb(w.dgates, 4 * H, nullptr, 0, g + lo.off[SCGIB_FT_LSTM_BIH], 1, g + lo.off[SCGIB_FT_LSTM_BHH], T * B, 4 * H, 1, w.scratch, s));
+  PROF("ft_dWp1", launch_atb(w.g_u, H, w.qstar + (size_t)(T - 1) * B * 2 * H, 2 * H, g + lo.off[SCGIB_FT_PRED_W1], 2 * H, nullptr, B, H, 2 * H, w.scratch, s));
+  PROF("ft_dbp1", launch_atb(w.g_u, H, nullptr, 0, g + lo.off[SCGIB_FT_PRED_B1], 1, nullptr, B, H, 1, w.scratch, s));
+  PROF("ft_dWp2", launch_atb(w.g_pre, C, w.rp, H, g + lo.off[SCGIB_FT_PRED_W2], H, nullptr, B, C, H, w.scratch, s));
+  PROF("ft_dbp2", launch_atb(w.g_pre, C, nullptr, 0, g + lo.off[SCGIB_FT_PRED_B2], 1, nullptr, B, C, 1, w.scratch, s));
   return (int)cudaGetLastError();
 }
 

@@ -304,55 +304,49 @@ __global__ void __launch_bounds__(kThreads) finetune_head_bwd_kernel(FinetuneHea
   }
 }
 
-// out[m][n] (+)= sum_r A[r][m] * Bm[r][n]     (reduction over rows in a fixed order; 32x32 output tile per CTA)
-__global__ void __launch_bounds__(kThreads) atb_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
-                                                       int ldb, float* __restrict__ out, int ldo, int R, int M, int Nn,
-                                                       int accumulate) {
+// part[z][m][n] = sum over the rows of split z of A[r][m] * Bm[r][n]   (32x32 output tile per CTA, blockIdx.z = row split;
+// Bm == nullptr: Bm is a column of ones (column sums of A, Nn = 1)).  atb_reduce_kernel adds the splits in order:
+// out[m][n] = sum_z part[z][m][n] - a fixed order, no float atomics.
+__global__ void __launch_bounds__(kThreads) atb_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
+                                                               int ldb, float* __restrict__ part, int R, int M, int Nn,
+                                                               int rows_per_split) {
   __shared__ float sa[32][33], sb[32][33];
   const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int rbeg = blockIdx.z * rows_per_split, rend = min(R, rbeg + rows_per_split);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty in 0..7 -> 4 output rows each
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r0 = 0; r0 < R; r0 += 32) {
+  for (int r0 = rbeg; r0 < rend; r0 += 32) {
     for (int i = threadIdx.x; i < 32 * 32; i += kThreads) {
       const int rr = i >> 5, cc = i & 31;
       const int r = r0 + rr;
-      sa[rr][cc] = (r < R && m0 + cc < M) ? A[(size_t)r * lda + m0 + cc] : 0.f;
-      sb[rr][cc] = (r < R && n0 + cc < Nn) ? Bm[(size_t)r * ldb + n0 + cc] : 0.f;
+      sa[rr][cc] = (r < rend && m0 + cc < M) ? A[(size_t)r * lda + m0 + cc] : 0.f;
+      sb[rr][cc] = (r < rend && n0 + cc < Nn) ? (Bm ? Bm[(size_t)r * ldb + n0 + cc] : 1.f) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
-      const float b = sb[rr][tx];
+      const float bv = sb[rr][tx];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[rr][ty * 4 + i], b, acc[i]);
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[rr][ty * 4 + i], bv, acc[i]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i, n = n0 + tx;
-    if (m < M && n < Nn) {
-      float* o = out + (size_t)m * ldo + n;
-      *o = accumulate ? *o + acc[i] : acc[i];
-    }
+    if (m < M && n < Nn) part[((size_t)blockIdx.z * M + m) * Nn + n] = acc[i];
   }
 }
 
-// out[c] = sum_r A[r][c] (fixed order); optionally written to a second destination as well
-__global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ A, int lda, int R, int M,
-                                                          float* __restrict__ out, float* __restrict__ out2) {
-  const int c = blockIdx.x * kThreads + threadIdx.x;
-  if (c >= M) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 3 < R; r += 4) {
-    s0 += A[(size_t)r * lda + c]; s1 += A[(size_t)(r + 1) * lda + c];
-    s2 += A[(size_t)(r + 2) * lda + c]; s3 += A[(size_t)(r + 3) * lda + c];
-  }
-  for (; r < R; ++r) s0 += A[(size_t)r * lda + c];
-  const float s = (s0 + s1) + (s2 + s3);
-  out[c] = s;
-  if (out2) out2[c] = s;
+__global__ void __launch_bounds__(kThreads) atb_reduce_kernel(const float* __restrict__ part, int S, int M, int Nn,
+                                                              float* __restrict__ out, int ldo, float* __restrict__ out2) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= M * Nn) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += part[(size_t)z * M * Nn + i];
+  const int m = i / Nn, n = i % Nn;
+  out[(size_t)m * ldo + n] = s;
+  if (out2) out2[(size_t)m * ldo + n] = s;
 }
 
 }  // namespace
@@ -369,14 +363,16 @@ void launch_finetune_head_bwd(const FinetuneHeadBwdArgs& a, cudaStream_t s) {
   else finetune_head_bwd_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 
-void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, int R, int M, int Nn,
-                int accumulate, cudaStream_t s) {
-  dim3 grid((M + 31) / 32, (Nn + 31) / 32);
-  atb_kernel<<<grid, kThreads, 0, s>>>(A, lda, Bm, ldb, out, ldo, R, M, Nn, accumulate);
-}
+int atb_splits(int R) { const int sp = (R + 127) / 128; return sp < 1 ? 1 : (sp > 64 ? 64 : sp); }
 
-void launch_colsum(const float* A, int lda, int R, int M, float* out, float* out2, cudaStream_t s) {
-  colsum_kernel<<<(M + kThreads - 1) / kThreads, kThreads, 0, s>>>(A, lda, R, M, out, out2);
+// out[m][n] = sum_r A[r][m] * Bm[r][n] (Bm == nullptr: column sums of A, Nn = 1); scratch >= atb_splits(R) * M * Nn floats
+void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, float* out2, int R, int M, int Nn,
+                float* scratch, cudaStream_t s) {
+  const int S = atb_splits(R);
+  const int rows_per_split = ((R + S - 1) / S + 31) / 32 * 32;
+  dim3 grid((M + 31) / 32, (Nn + 31) / 32, S);
+  atb_partial_kernel<<<grid, kThreads, 0, s>>>(A, lda, Bm, ldb, scratch, R, M, Nn, rows_per_split);
+  atb_reduce_kernel<<<(M * Nn + kThreads - 1) / kThreads, kThreads, 0, s>>>(scratch, S, M, Nn, out, ldo, out2);
 }
 
 int finetune_max_classes() { return kMaxC; }

@@ -497,18 +497,18 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
     const int32_t* indices = p.indices[set];
     const int32_t* map = p.map[set];
     __syncthreads();
-    {  // gather gt rows: 8 lanes x float4 per row
-      const int l = threadIdx.x & 7;
-      for (int r = threadIdx.x >> 3; r < PT; r += kThreads / 8) {
-        const int v = base + r;
-        float4 g = make4(0.f);
-        if (v < V) {
-          g = ld4(ga + (size_t)v * DTR + l * 4);
-          const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
-          for (int e = e0; e < e1; ++e) g = add4(g, ld4(ga + (size_t)__ldg(indices + e) * DTR + l * 4));
-        }
-        float* d = s_g + r * (DTR + 1) + l * 4;
-        d[0] = g.x; d[1] = g.y; d[2] = g.z; d[3] = g.w;
+    {  // gather gt rows: 8 lanes x float4 per row, the thread's 4 rows in flight together (latency-bound gather)
+      const int l = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+      constexpr int NR = PT / (kThreads / 8);
+      int vv[NR];
+      float4 g[NR];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) vv[j] = base + r0 + j * (kThreads / 8);
+      gather_aggregate<DTR, NR>(ga, nullptr, indptr, indices, V, vv, l, nullptr, g);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        float* d = s_g + (r0 + j * (kThreads / 8)) * (DTR + 1) + l * 4;
+        d[0] = g[j].x; d[1] = g[j].y; d[2] = g[j].z; d[3] = g[j].w;
       }
     }
     {  // x_hat rows: one thread per (row, half) is plenty
@@ -538,12 +538,23 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
   if (!last_cta_arrives(p.counter)) return;
-  for (int idx = threadIdx.x; idx < DTR * FP; idx += kThreads) {
-    double s = 0.0;
+  // only the F real feature columns; four interleaved partial sums per output keep 32 loads in flight (the chain of
+  // ~300 dependent L2 round trips was the whole cost of this kernel); combined in a fixed order
+  for (int o2 = threadIdx.x; o2 < DTR * p.F; o2 += kThreads) {
+    const int oo = o2 / p.F, f = o2 % p.F;
+    const float* src = p.part + oo * FP + f;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int nb = (int)gridDim.x;
+    int b = 0;
 #pragma unroll 8
-    for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(p.part + (size_t)b * DTR * FP + idx);
-    const int oo = idx / FP, f = idx % FP;
-    if (f < p.F) p.d_Wt[oo * p.F + f] = (float)s;
+    for (; b + 3 < nb; b += 4) {
+      s0 += (double)__ldcg(src + (size_t)b * DTR * FP);
+      s1 += (double)__ldcg(src + (size_t)(b + 1) * DTR * FP);
+      s2 += (double)__ldcg(src + (size_t)(b + 2) * DTR * FP);
+      s3 += (double)__ldcg(src + (size_t)(b + 3) * DTR * FP);
+    }
+    for (; b < nb; ++b) s0 += (double)__ldcg(src + (size_t)b * DTR * FP);
+    p.d_Wt[oo * p.F + f] = (float)((s0 + s1) + (s2 + s3));
   }
 }
 

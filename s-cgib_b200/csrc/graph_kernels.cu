@@ -219,6 +219,45 @@ scan_apply_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// On-device batch assembly (replaces DataLoader + MoleculeDataset.collate + dgl.batch, molecules.py:349-362,
+// exp_pretraining.py:283): the packed dataset shard (all molecules as one CSR) stays resident in HBM and a batch is
+// the list of B molecule ids.  dgl.batch semantics: molecules in list order, node / edge ids offset.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+batch_count_kernel(const int32_t* __restrict__ mol_ptr, const int32_t* __restrict__ ds_indptr,
+                   const int32_t* __restrict__ ids, int B, int32_t* __restrict__ cnt_nodes, int32_t* __restrict__ cnt_edges) {
+  const int b = blockIdx.x * kThreads + threadIdx.x;
+  if (b >= B) return;
+  const int m = __ldg(ids + b);
+  const int n0 = __ldg(mol_ptr + m), n1 = __ldg(mol_ptr + m + 1);
+  cnt_nodes[b] = n1 - n0;
+  cnt_edges[b] = __ldg(ds_indptr + n1) - __ldg(ds_indptr + n0);
+}
+
+__global__ void __launch_bounds__(kThreads)
+batch_fill_kernel(const int32_t* __restrict__ mol_ptr, const int32_t* __restrict__ ds_indptr,
+                  const int32_t* __restrict__ ds_indices, const float* __restrict__ ds_x, int F,
+                  const int32_t* __restrict__ ids, int B, const int32_t* __restrict__ graph_ptr,
+                  const int32_t* __restrict__ edge_ptr, int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                  float* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (kThreads / 32);
+  for (int b = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); b < B; b += warps) {
+    const int m = __ldg(ids + b);
+    const int s0 = __ldg(mol_ptr + m), n = __ldg(mol_ptr + m + 1) - s0;     // source node range
+    const int d0 = __ldg(graph_ptr + b);                                    // destination node offset
+    const int se0 = __ldg(ds_indptr + s0), de0 = __ldg(edge_ptr + b);
+    const int ne = __ldg(ds_indptr + s0 + n) - se0;
+    for (int j = lane; j < n; j += 32) indptr[d0 + j] = __ldg(ds_indptr + s0 + j) - se0 + de0;
+    if (b == B - 1 && lane == 0) indptr[d0 + n] = de0 + ne;
+    for (int e = lane; e < ne; e += 32) indices[de0 + e] = __ldg(ds_indices + se0 + e) - s0 + d0;
+    const float* xs = ds_x + (size_t)s0 * F;
+    float* xd = x + (size_t)d0 * F;
+    for (int i = lane; i < n * F; i += 32) xd[i] = __ldg(xs + i);
+  }
+}
+
 }  // namespace scgib
 
 using namespace scgib;
@@ -260,5 +299,37 @@ extern "C" SCGIB_API int scgib_ego_fill(const int32_t* indptr, const int32_t* in
   const int grid = (N + kEgoWarps - 1) / kEgoWarps;
   ego_fill_kernel<<<grid, kEgoWarps * 32, 0, stream>>>(indptr, indices, N, k, ego_ptr, ego_eptr, ego_nodes, ego_seed,
                                                        sub_indptr, sub_indices);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API size_t scgib_batch_workspace_bytes(int32_t B) { return scgib_ego_workspace_bytes(B); }
+
+extern "C" SCGIB_API int scgib_batch_assemble_count(const int32_t* mol_ptr, const int32_t* ds_indptr, const int32_t* ids,
+                                          int32_t B, int32_t* graph_ptr, int32_t* edge_ptr, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+  if (!mol_ptr || !ds_indptr || !ids || !graph_ptr || !edge_ptr || !workspace) return SCGIB_E_NULL;
+  if (B < 1) return SCGIB_E_RANGE;
+  if (workspace_bytes < scgib_batch_workspace_bytes(B)) return SCGIB_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int32_t* cnt_nodes = (int32_t*)workspace;
+  int32_t* cnt_edges = cnt_nodes + B;
+  int2* bsum = (int2*)((char*)workspace + align_up((size_t)2 * B * sizeof(int32_t), 256));
+  batch_count_kernel<<<(B + kThreads - 1) / kThreads, kThreads, 0, stream>>>(mol_ptr, ds_indptr, ids, B, cnt_nodes, cnt_edges);
+  const int nb = (B + kScanBlock - 1) / kScanBlock;
+  scan_block_sums_kernel<<<nb, kThreads, 0, stream>>>(cnt_nodes, cnt_edges, B, bsum);
+  scan_spine_kernel<<<1, kThreads, 0, stream>>>(bsum, nb);
+  scan_apply_kernel<<<nb, kThreads, 0, stream>>>(cnt_nodes, cnt_edges, B, bsum, graph_ptr, edge_ptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_batch_assemble_fill(const int32_t* mol_ptr, const int32_t* ds_indptr, const int32_t* ds_indices,
+                                         const float* ds_x, int32_t F, const int32_t* ids, int32_t B,
+                                         const int32_t* graph_ptr, const int32_t* edge_ptr, int32_t* indptr,
+                                         int32_t* indices, float* x, void* stream_) {
+  if (!mol_ptr || !ds_indptr || !ds_x || !ids || !graph_ptr || !edge_ptr || !indptr || !x) return SCGIB_E_NULL;
+  if (B < 1 || F < 1) return SCGIB_E_RANGE;
+  const int grid = (B + kThreads / 32 - 1) / (kThreads / 32);
+  batch_fill_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(mol_ptr, ds_indptr, ds_indices, ds_x, F, ids, B, graph_ptr,
+                                                                edge_ptr, indptr, indices, x);
   return (int)cudaGetLastError();
 }

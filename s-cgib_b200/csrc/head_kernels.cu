@@ -309,6 +309,7 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
     const float2 isd = make_float2(1.f / (sd.x + kKlEps), 1.f / (sd.y + kKlEps));
     // ---- attention pass A: S = sum_v alpha_v (gT_v . C_v)
     float S = 0.f;
+#pragma unroll 4
     for (int v = v0; v < v1; ++v) {
       const float2 gT = ld2(p.gI + (size_t)v * 2 * HID + HID + c), C = ld2(p.C + (size_t)v * HID + c);
       S += __ldg(p.alpha + v) * warp_sum(gT.x * C.x + gT.y * C.y);
@@ -377,9 +378,20 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
   }
   if (!last_cta_arrives(p.counter)) return;
   for (int j = threadIdx.x; j < 4 * HID + 1; j += kThreads) {
-    double s = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(p.part + (size_t)b * 5 * HID + j);
-    const float f = (float)s;
+    // four interleaved partial sums: 32 independent loads in flight instead of a chain of ~300 L2 round trips
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int nb = (int)gridDim.x;
+    const float* src = p.part + j;
+    int b = 0;
+#pragma unroll 8
+    for (; b + 3 < nb; b += 4) {
+      s0 += (double)__ldcg(src + (size_t)b * 5 * HID);
+      s1 += (double)__ldcg(src + (size_t)(b + 1) * 5 * HID);
+      s2 += (double)__ldcg(src + (size_t)(b + 2) * 5 * HID);
+      s3 += (double)__ldcg(src + (size_t)(b + 3) * 5 * HID);
+    }
+    for (; b < nb; ++b) s0 += (double)__ldcg(src + (size_t)b * 5 * HID);
+    const float f = (float)((s0 + s1) + (s2 + s3));
     if (j < HID) p.d_gamma_c[j] = f;
     else if (j < 2 * HID) p.d_beta_c[j - HID] = f;
     else if (j < 3 * HID) p.d_wc2[j - 2 * HID] = f;
@@ -388,7 +400,7 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
   }
 }
 void launch_graph_gate_bwd(const GraphGateBwdArgs& a, cudaStream_t s) {
-  const int grid = min((a.B + 7) / 8, 2 * num_sms());
+  const int grid = min((a.B + 7) / 8, 4 * num_sms());   // latency-bound warp-per-graph loops: as many resident warps as fit
   graph_gate_bwd_kernel<<<grid, kThreads, 0, s>>>(a);
 }
 

@@ -261,9 +261,10 @@ struct FinetuneHeadBwdArgs {
   float* gZ;                             // [N][H]
 };
 void launch_finetune_head_bwd(const FinetuneHeadBwdArgs& a, cudaStream_t s);
-// out[m][n] (+)= sum_r A[r][m] * Bm[r][n], fixed order;  out[c] = sum_r A[r][c]
-void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, int R, int M, int Nn, int accumulate, cudaStream_t s);
-void launch_colsum(const float* A, int lda, int R, int M, float* out, float* out2, cudaStream_t s);
+// out[m][n] = sum_r A[r][m] * Bm[r][n] (Bm == nullptr: column sums of A, Nn = 1); row splits are reduced in a fixed order
+int atb_splits(int R);
+void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, float* out2, int R, int M, int Nn,
+                float* scratch, cudaStream_t s);
 int finetune_max_classes();
 
 }  // namespace scgib

@@ -76,8 +76,16 @@ __global__ void __launch_bounds__(kThreads)
 recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum) {
   const int j = blockIdx.x * kThreads + threadIdx.x;
   if (j > HID * HID) return;
-  double s = 0.0;
-  for (int c = 0; c < grid; ++c) s += (double)part[(size_t)c * (HID * HID + 4) + j];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // interleaved partial sums: independent loads in flight, fixed order
+  constexpr size_t ST = HID * HID + 4;
+  int c = 0;
+#pragma unroll 4
+  for (; c + 3 < grid; c += 4) {
+    s0 += (double)part[(size_t)c * ST + j]; s1 += (double)part[(size_t)(c + 1) * ST + j];
+    s2 += (double)part[(size_t)(c + 2) * ST + j]; s3 += (double)part[(size_t)(c + 3) * ST + j];
+  }
+  for (; c < grid; ++c) s0 += (double)part[(size_t)c * ST + j];
+  const double s = (s0 + s1) + (s2 + s3);
   if (j < HID * HID) G[j] = (float)s; else edge_sum[0] = (float)s;
 }
 void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, cudaStream_t s) {
@@ -380,19 +388,29 @@ void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_fina
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_kernel(const float* __restrict__ part, int64_t pstride, int nparts, ReduceRanges r, float* __restrict__ grads) {
+  // 4 consecutive lanes share one output element: each sums a contiguous quarter of the partial rows in order, the
+  // quarters are combined as (q0 + q1) + (q2 + q3) - a fixed order, with 4x the loads in flight
   const int64_t off = r.off[blockIdx.y], len = r.len[blockIdx.y];
   const int c0 = r.c0[blockIdx.y], c1 = min(r.c1[blockIdx.y], nparts);
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (int64_t)gridDim.x * kThreads) {
+  const int sub = threadIdx.x & 3;
+  const int chunk = (c1 - c0 + 3) / 4;
+  const int a = min(c0 + sub * chunk, c1), b = min(a + chunk, c1);
+  const int64_t len_pad = (len + 63) / 64 * 64;          // whole warps stay in the loop for the shuffles
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 2; i < len_pad; i += ((int64_t)gridDim.x * kThreads) >> 2) {
     double s = 0.0;
+    if (i < len) {
 #pragma unroll 8
-    for (int c = c0; c < c1; ++c) s += (double)part[(size_t)c * pstride + off + i];
-    grads[off + i] = (float)s;
+      for (int c = a; c < b; ++c) s += (double)part[(size_t)c * pstride + off + i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (sub == 0 && i < len) grads[off + i] = (float)s;
   }
 }
 void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
                             cudaStream_t s) {
   if (r.n == 0) return;
-  dim3 grid(32, r.n);   // largest range is 8192 floats = 32 CTAs x 256
+  dim3 grid(128, r.n);  // largest range is 8192 floats x 4 lanes = 128 CTAs x 256
   reduce_partials_kernel<<<grid, kThreads, 0, s>>>(part, pstride, nparts, r, grads);
 }
 

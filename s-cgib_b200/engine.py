@@ -214,6 +214,26 @@ class PretrainEngine:
             ev.record(self._side)
         return b, ev
 
+    def prefetch_ids(self, dataset, ids: torch.Tensor, k: int = 1, normalize_x: bool = True, slots: int = 3):
+        """The same pipelining for a dataset resident in HBM (graph.DeviceDataset): H2D of the B molecule ids, GPU-side
+        batch assembly and ego-net extraction of the NEXT batch on the side stream.  Pair with ``wait_batch``."""
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.device)
+            self._slots = [dict(bufs={}, done=None, dev={}) for _ in range(slots)]
+            self._slot_i = 0
+        slot = self._slots[self._slot_i % len(self._slots)]
+        self._slot_i += 1
+        with torch.cuda.stream(self._side):
+            if slot["done"] is not None:
+                self._side.wait_event(slot["done"])
+            g = dataset.assemble(ids, out=slot["dev"])
+            ego = khop_ego_batch(g, k, self.ego_ws, out=slot["bufs"])
+            b = DeviceBatch(g, ego, g.ndata["x"], normalize_x)
+            b._slot = slot
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return b, ev
+
     def wait_batch(self, handle) -> DeviceBatch:
         b, ev = handle
         torch.cuda.current_stream(self.device).wait_event(ev)

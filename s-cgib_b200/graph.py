@@ -221,3 +221,73 @@ def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, s
                                   _lib.ptr(ego_eptr), _lib.ptr(ego_nodes), _lib.ptr(ego_seed), _lib.ptr(sub_indptr),
                                   _lib.ptr(sub_indices), st), "ego_fill")
     return EgoBatch(g, k, ego_ptr[:N + 1], ego_nodes[:Ns], ego_seed[:Ns], sub_indptr[:Ns + 1], sub_indices[:Es])
+
+
+class DeviceDataset:
+    """A packed dataset shard resident in HBM (every molecule as one symmetric CSR; the format of ``pts/<name>_csr.pt``,
+    keys graph_ptr / indptr / indices / x) + GPU-side batch assembly: ``assemble(ids)`` builds the ``dgl.batch`` of the
+    listed molecules on the device (csrc/graph_kernels.cu).  Replaces DataLoader + ``MoleculeDataset.collate``
+    (molecules.py:349-362) and the per-step H2D of the batch: only the B molecule ids cross PCIe."""
+
+    def __init__(self, graph_ptr, indptr, indices, x, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceDataset needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.mol_ptr = torch.as_tensor(graph_ptr, dtype=torch.int32).to(self.device)
+        self.indptr = torch.as_tensor(indptr, dtype=torch.int32).to(self.device)
+        self.indices = torch.as_tensor(indices, dtype=torch.int32).to(self.device)
+        self.x = torch.as_tensor(x).float().contiguous().to(self.device)
+        self.F = int(self.x.shape[1])
+        self._ws = None
+        self._host = torch.empty(2, dtype=torch.int32).pin_memory()
+
+    @classmethod
+    def from_batched(cls, g: BatchedGraph, device="cuda:0"):
+        return cls(g.graph_ptr, g.indptr, g.indices, g.ndata["x"], device)
+
+    def __len__(self):
+        return self.mol_ptr.numel() - 1
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.mol_ptr, self.indptr, self.indices, self.x))
+
+    def assemble(self, ids: torch.Tensor, out=None) -> BatchedGraph:
+        """``ids``: int32 molecule ids (device, or pinned host: copied asynchronously).  One host read of (N, E) between
+        the count and the fill kernels, on the current stream.  ``out``: optional dict of reusable device buffers."""
+        dev = self.device
+        if ids.device != dev:
+            ids = ids.to(dev, non_blocking=True)
+        ids = ids.to(torch.int32).contiguous()
+        B = ids.numel()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        need = self.lib.scgib_batch_workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(int(need * 1.5), dtype=torch.uint8, device=dev)
+        out = {} if out is None else out
+
+        def buf(name, n, dtype=torch.int32):
+            t = out.get(name)
+            if t is None or t.numel() < n or t.device != dev or t.dtype != dtype:
+                t = torch.empty(int(n * 1.25) + 16, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+
+        graph_ptr, edge_ptr = buf("b_graph_ptr", B + 1), buf("b_edge_ptr", B + 1)
+        _lib.check(self.lib.scgib_batch_assemble_count(_lib.ptr(self.mol_ptr), _lib.ptr(self.indptr), _lib.ptr(ids), B,
+                                                       _lib.ptr(graph_ptr), _lib.ptr(edge_ptr), _lib.ptr(self._ws),
+                                                       self._ws.numel(), st), "batch_assemble_count")
+        self._host[0:1].copy_(graph_ptr[B:B + 1], non_blocking=True)
+        self._host[1:2].copy_(edge_ptr[B:B + 1], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        N, E = int(self._host[0]), int(self._host[1])
+        indptr, indices = buf("b_indptr", N + 1), buf("b_indices", max(E, 1))
+        x = buf("b_x", N * self.F, torch.float32)
+        _lib.check(self.lib.scgib_batch_assemble_fill(_lib.ptr(self.mol_ptr), _lib.ptr(self.indptr), _lib.ptr(self.indices),
+                                                      _lib.ptr(self.x), self.F, _lib.ptr(ids), B, _lib.ptr(graph_ptr),
+                                                      _lib.ptr(edge_ptr), _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(x),
+                                                      st), "batch_assemble_fill")
+        g = BatchedGraph.__new__(BatchedGraph)
+        g.graph_ptr, g.indptr, g.indices = graph_ptr[:B + 1], indptr[:N + 1], indices[:E]
+        g.ndata = {"x": x[:N * self.F].view(N, self.F)}
+        return g
