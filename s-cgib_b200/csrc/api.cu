@@ -130,6 +130,7 @@ struct Ws {
   float *rpart, *G, *edge;
   float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout, *zsplit;
   float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o[2], *Ga[2], *ga0[2];
+  float *aC, *head_w1a, *head_w1b, *head_bn, *head_cvec;     // tensor-core head backward (the GIN backward kernel on two K halves)
   float* ppart;
   size_t bytes;
 };
@@ -188,6 +189,8 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.Ga[0] = take((size_t)N * HID); w.Ga[1] = take((size_t)Ns * HID);
   (void)Vmax;
   w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
+  w.aC = take((size_t)N * HID); w.head_w1a = take(HID * HID); w.head_w1b = take(HID * HID);
+  w.head_bn = take(4 * HID); w.head_cvec = take(2 * HID);
   w.ppart = take((size_t)num_sms() * lo.total);
   w.bytes = o;
   (void)E; (void)Es;
@@ -335,7 +338,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
-                  params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.r_head, w.Z};
+                  params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.aC, w.r_head, w.Z};
     PROF("head_fwd", launch_head_fwd(a, s));
   }
   if (!features_only) {
@@ -415,7 +418,28 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
     PROF("recon_bwd", launch_recon_bwd(ra, s));
   }
-  {
+  // head MLP backward.  Tensor-core path: Z = W2 relu(W1a noisy + W1b (alpha C) + b1) + b2 is the GIN MLP with its first
+  // layer split over two K = 64 inputs, so its backward is the GIN backward kernel run on both halves in ONE launch
+  // (problem 0: a = noisy, W1a -> gI[:, :64], dW1a, dW2, db1, db2; problem 1: a = alpha C, W1b -> gI[:, 64:], dW1b; its
+  // duplicate dW2 / bias partials are not reduced) with an identity BatchNorm backward (g_y = gZ).
+  const bool head_tc = bwd_tensor_core_mode() != 0;
+  const int head_split = pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128);
+  if (head_tc) {
+    PROF("head_bwd_prep", launch_head_bwd_prep(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1a, w.head_w1b, w.head_bn, w.head_cvec, s));
+    GinBwdMainArgs m[2];
+    for (int h = 0; h < 2; ++h) {
+      m[h].g_o = w.gZ; m[h].y = w.Z; m[h].r = w.r_head; m[h].a = h == 0 ? w.noisy : w.aC;
+      m[h].bn = w.head_bn; m[h].cvec = w.head_cvec;
+      m[h].W1 = h == 0 ? w.head_w1a : w.head_w1b; m[h].W2 = params + lo.off[SCGIB_P_HEAD_W2];
+      m[h].V = b->N; m[h].g_a = w.gI + (size_t)h * b->N * HID; m[h].part = w.ppart; m[h].pstride = lo.total;
+      m[h].off_W1 = lo.off[SCGIB_P_HEAD_W1] + (int64_t)h * HID * HID; m[h].off_b1 = lo.off[SCGIB_P_HEAD_B1];
+      m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
+    }
+    if (bwd_tensor_core_mode() == 2)
+      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
+    else
+      PROF("head_bwd_tc128", launch_gin_bwd_main_tc_pair(m[0], m[1], HID, GP, s));
+  } else {
     HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
                   params + lo.off[SCGIB_P_HEAD_W2], w.gI, w.ppart, lo.total,
                   lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_W2], lo.off[SCGIB_P_HEAD_B2]};
@@ -427,7 +451,8 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     a.gamma_c = params + lo.off[SCGIB_P_COMP_GAMMA]; a.beta_c = params + lo.off[SCGIB_P_COMP_BETA];
     a.wc2 = params + lo.off[SCGIB_P_COMP_W2]; a.w_cand = params + lo.off[SCGIB_P_ATTN_W] + HID;
     a.feat_u = b->feat_u; a.lam = w.lam; a.alpha = w.alpha; a.gstat = w.gstat;
-    a.gI = w.gI; a.g_core = w.g_core; a.g_readout = w.g_readout; a.kl_scale = s_kl;
+    a.gI = w.gI; a.gI2 = head_tc ? w.gI + (size_t)b->N * HID : w.gI + HID; a.gI_stride = head_tc ? HID : 2 * HID;
+    a.g_core = w.g_core; a.g_readout = w.g_readout; a.kl_scale = s_kl;
     a.gp = w.gp; a.g_q = w.g_q; a.gH = w.gH; a.gC = w.gC;
     a.part = w.small_part; a.counter = w.counters + 1;
     a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
@@ -489,13 +514,20 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     ReduceRanges r;
     r.n = 0;
     auto add = [&](int64_t off, int64_t len, int c0, int c1) { r.off[r.n] = off; r.len[r.n] = len; r.c0[r.n] = c0; r.c1[r.n] = c1; ++r.n; };
-    add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1], 0, GP);
+    if (head_tc) {     // partial rows [0, head_split): problem 0 (dW1a and everything else), [head_split, GP): problem 1 (dW1b)
+      add(lo.off[SCGIB_P_HEAD_W1], (int64_t)HID * HID, 0, head_split);
+      add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, head_split, GP);
+      add(lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_B1], 0, head_split);
+    } else {
+      add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1], 0, GP);
+    }
     add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1], 0, GP);
     for (int e = 0; e < 2; ++e)        // shared launches: partial rows [0, split) belong to Encoder1, [split, GP) to Encoder2
       for (int l = 0; l < L; ++l)
         add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1),
             pair_main ? (e == 0 ? 0 : enc_split) : 0, pair_main ? (e == 0 ? enc_split : GP) : GP);
     PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
+    if (head_tc) PROF("head_dw1_interleave", launch_head_dw1_interleave(grads + lo.off[SCGIB_P_HEAD_W1], s));
   }
   return (int)cudaGetLastError();
 }

@@ -311,19 +311,19 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
     float S = 0.f;
 #pragma unroll 4
     for (int v = v0; v < v1; ++v) {
-      const float2 gT = ld2(p.gI + (size_t)v * 2 * HID + HID + c), C = ld2(p.C + (size_t)v * HID + c);
+      const float2 gT = ld2(p.gI2 + (size_t)v * p.gI_stride + c), C = ld2(p.C + (size_t)v * HID + c);
       S += __ldg(p.alpha + v) * warp_sum(gT.x * C.x + gT.y * C.y);
     }
     // ---- pass B: attention backward, gate backward (scalar part), per-graph BN sums
     float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
     for (int v = v0; v < v1; ++v) {
-      const float2 gT = ld2(p.gI + (size_t)v * 2 * HID + HID + c), C = ld2(p.C + (size_t)v * HID + c);
+      const float2 gT = ld2(p.gI2 + (size_t)v * p.gI_stride + c), C = ld2(p.C + (size_t)v * HID + c);
       const float al = __ldg(p.alpha + v);
       const float dl = al * (warp_sum(gT.x * C.x + gT.y * C.y) - S);
       st2(p.gC + (size_t)v * HID + c, make_float2(fmaf(dl, wc.x, al * gT.x), fmaf(dl, wc.y, al * gT.y)));
       a_dwc.x = fmaf(dl, C.x, a_dwc.x); a_dwc.y = fmaf(dl, C.y, a_dwc.y);
 
-      const float2 gz0 = ld2(p.gI + (size_t)v * 2 * HID + c);
+      const float2 gz0 = ld2(p.gI + (size_t)v * p.gI_stride + c);
       const float2 gz = make_float2(gz0.x + gcore.x, gz0.y + gcore.y);
       const float2 h = ld2(p.H + (size_t)v * HID + c), fu = ld2(p.feat_u + (size_t)v * HID + c);
       const float lam = __ldg(p.lam + v);
@@ -413,7 +413,8 @@ constexpr int HLD = 2 * HID + 4;
 struct HeadFwdSmem { float tile[HT * HLD]; float w1t[2 * HID * HID]; float w2t[HID * HID]; };
 
 __device__ __forceinline__ void head_load_tile(float* tile, const float* __restrict__ noisy, const float* __restrict__ C,
-                                               const float* __restrict__ alpha, int base, int N, float* imap) {
+                                               const float* __restrict__ alpha, int base, int N, float* imap,
+                                               float* aC = nullptr) {
   const int l = threadIdx.x & 31;
   for (int r = threadIdx.x >> 5; r < HT; r += kThreads / 32) {
     const int v = base + r;
@@ -425,6 +426,7 @@ __device__ __forceinline__ void head_load_tile(float* tile, const float* __restr
         const float al = __ldg(alpha + v);
         const float4 cc = ld4(C + (size_t)v * HID + (l - 16) * 4);
         val = make_float4(al * cc.x, al * cc.y, al * cc.z, al * cc.w);
+        if (aC) st4(aC + (size_t)v * HID + (l - 16) * 4, val);
       }
       if (imap) st4(imap + (size_t)v * 2 * HID + l * 4, val);
     }
@@ -445,7 +447,7 @@ head_fwd_kernel(HeadFwdArgs p) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * HT;
     __syncthreads();
-    head_load_tile(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap);
+    head_load_tile(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap, p.aC);
     __syncthreads();
     float acc[M::TM][4];
 #pragma unroll
@@ -562,6 +564,34 @@ head_bwd_kernel(HeadBwdArgs p) {
   if (threadIdx.x < HID) part[p.off_b2 + threadIdx.x] = dbias;
   else if (threadIdx.x < 2 * HID) part[p.off_b1 + threadIdx.x - HID] = dbias;
 }
+__global__ void __launch_bounds__(kThreads)
+head_bwd_prep_kernel(const float* __restrict__ W1, float* __restrict__ W1a, float* __restrict__ W1b, float* __restrict__ bn,
+                     float* __restrict__ cvec) {
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < HID * 2 * HID; i += gridDim.x * kThreads) {
+    const int o = i / (2 * HID), k = i % (2 * HID);
+    const float w = W1[i];
+    if (k < HID) W1a[o * HID + k] = w; else W1b[o * HID + k - HID] = w;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < 4 * HID; i += kThreads) bn[i] = (i >= HID && i < 3 * HID) ? 1.f : 0.f;   // mean 0, rstd 1, gamma 1, beta 0
+    for (int i = threadIdx.x; i < 2 * HID; i += kThreads) cvec[i] = 0.f;
+  }
+}
+void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, cudaStream_t s) {
+  head_bwd_prep_kernel<<<8, kThreads, 0, s>>>(W1, W1a, W1b, bn, cvec);
+}
+
+__global__ void __launch_bounds__(kThreads) head_dw1_interleave_kernel(float* __restrict__ dW1) {
+  __shared__ float s_w[2 * HID * HID];
+  for (int i = threadIdx.x; i < 2 * HID * HID; i += kThreads) s_w[i] = dW1[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * HID * HID; i += kThreads) {
+    const int o = i / (2 * HID), k = i % (2 * HID);
+    dW1[i] = k < HID ? s_w[o * HID + k] : s_w[HID * HID + o * HID + k - HID];
+  }
+}
+void launch_head_dw1_interleave(float* dW1, cudaStream_t s) { head_dw1_interleave_kernel<<<1, kThreads, 0, s>>>(dW1); }
+
 void launch_head_bwd(const HeadBwdArgs& a, int grid, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(HeadBwdSmem)), true);

@@ -154,7 +154,9 @@ struct GraphGateBwdArgs {
   const float *gamma_c, *beta_c, *wc2;
   const float* w_cand;
   const float *feat_u, *lam, *alpha, *gstat;
-  const float* gI;                       // [N][2*HID] gradient wrt interaction_map (head backward)
+  const float* gI;                       // gradient wrt the noisy half of interaction_map, row stride gI_stride
+  const float* gI2;                      // gradient wrt the alpha*C half, row stride gI_stride  (interleaved [N][2*HID]
+  int gI_stride;                         //  from the FFMA head backward: gI2 = gI + HID, stride 2*HID; dense halves: HID)
   const float* g_core;                   // [B][HID]  contrastive gradient wrt core readout
   const float* g_readout;                // [B][HID]  contrastive gradient wrt graph readout
   float kl_scale;                        // d total / d KL
@@ -173,6 +175,8 @@ struct HeadFwdArgs {
   const float *noisy, *C, *alpha; int N;
   const float *W1t, *b1, *W2t, *b2;      // W1t [2*HID][HID], W2t [HID][HID]
   float* imap;                           // optional [N][2*HID]
+  float* aC;                             // optional [N][HID]: alpha*C, the second half of interaction_map (saved for the
+                                         //  tensor-core head backward)
   float* r;                              // [N][HID] saved
   float* Z;                              // [N][HID]
 };
@@ -186,6 +190,11 @@ struct HeadBwdArgs {
   float* part; int64_t pstride; int64_t off_W1, off_b1, off_W2, off_b2;
 };
 void launch_head_bwd(const HeadBwdArgs& a, int grid, cudaStream_t s);
+// Tensor-core head backward = the GIN backward kernel run on the two K = 64 halves of the first head layer (api.cu).
+// prep: dense copies W1a = W1[:, :HID], W1b = W1[:, HID:] and the identity BatchNorm-backward constants
+// (bn = {0, 1, 1, 0}, cvec = 0: g_y = g_o).  fix: grads slot [2][HID][HID] (dW1a | dW1b) -> [HID][2*HID] in place.
+void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, cudaStream_t s);
+void launch_head_dw1_interleave(float* dW1, cudaStream_t s);
 
 // ---------------------------------------------------------------- loss_kernels.cu
 // recon: per-CTA partials of Z^T Z and of sum_{(i,j) in E} z_i . z_j     (models.py:762-768, Gram identity)
