@@ -314,55 +314,91 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
       const float2 gT = ld2(p.gI2 + (size_t)v * p.gI_stride + c), C = ld2(p.C + (size_t)v * HID + c);
       S += __ldg(p.alpha + v) * warp_sum(gT.x * C.x + gT.y * C.y);
     }
-    // ---- pass B: attention backward, gate backward (scalar part), per-graph BN sums
+    // ---- pass B: attention backward, gate backward (scalar part), per-graph BN sums.  The loop is latency-bound (one
+    //      warp per graph, two dependent shuffle reductions per row): the loads of RB rows are issued together and the
+    //      rows' shuffle chains interleave; sums are still accumulated in row order.
     float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
-    for (int v = v0; v < v1; ++v) {
-      const float2 gT = ld2(p.gI2 + (size_t)v * p.gI_stride + c), C = ld2(p.C + (size_t)v * HID + c);
-      const float al = __ldg(p.alpha + v);
-      const float dl = al * (warp_sum(gT.x * C.x + gT.y * C.y) - S);
-      st2(p.gC + (size_t)v * HID + c, make_float2(fmaf(dl, wc.x, al * gT.x), fmaf(dl, wc.y, al * gT.y)));
-      a_dwc.x = fmaf(dl, C.x, a_dwc.x); a_dwc.y = fmaf(dl, C.y, a_dwc.y);
-
-      const float2 gz0 = ld2(p.gI + (size_t)v * p.gI_stride + c);
-      const float2 gz = make_float2(gz0.x + gcore.x, gz0.y + gcore.y);
-      const float2 h = ld2(p.H + (size_t)v * HID + c), fu = ld2(p.feat_u + (size_t)v * HID + c);
-      const float lam = __ldg(p.lam + v);
-      float part = gz.x * (h.x - muH.x - fu.x * sd.x) + gz.y * (h.y - muH.y - fu.y * sd.y);
-      float2 gh = make_float2(fmaf(lam, gz.x, gread.x), fmaf(lam, gz.y, gread.y));
-      if (last) {
-        const float k = p.kl_scale / ((float)HID * n);
-        const float2 r1 = make_float2(sd.x * isd.x, sd.y * isd.y);                       // sigma/(sigma+e)
-        const float2 r2 = make_float2((h.x - muH.x) * isd.x, (h.y - muH.y) * isd.y);     // (H-mu)/(sigma+e)
-        part += k * (-(1.f - lam) * (r1.x * r1.x + r1.y * r1.y) + 2.f * n * lam * (r2.x * r2.x + r2.y * r2.y));
-        gh.x += k * 2.f * n * lam * lam * r2.x * isd.x;
-        gh.y += k * 2.f * n * lam * lam * r2.y * isd.y;
+    constexpr int RB = 4;
+    for (int vb = v0; vb < v1; vb += RB) {
+      float2 gT[RB], C[RB], gz0[RB], h[RB], fu[RB], q[RB];
+      float al[RB], lam[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = min(vb + i, v1 - 1);
+        gT[i] = ld2(p.gI2 + (size_t)v * p.gI_stride + c); C[i] = ld2(p.C + (size_t)v * HID + c);
+        gz0[i] = ld2(p.gI + (size_t)v * p.gI_stride + c); h[i] = ld2(p.H + (size_t)v * HID + c);
+        fu[i] = ld2(p.feat_u + (size_t)v * HID + c); q[i] = ld2(p.q + (size_t)v * HID + c);
+        al[i] = __ldg(p.alpha + v); lam[i] = __ldg(p.lam + v);
       }
-      st2(p.gH + (size_t)v * HID + c, gh);
-      const float glam = warp_sum(part);
-      const float gpv = glam * lam * (1.f - lam);
-      if (lane == 0) p.gp[v] = gpv;
-      a_dbc2 += gpv;
-      const float2 q = ld2(p.q + (size_t)v * HID + c);
-      const float2 qh = make_float2((q.x - muQ.x) * rstd.x, (q.y - muQ.y) * rstd.y);
-      const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
-      a_dw2.x = fmaf(gpv, fmaxf(ox, 0.f), a_dw2.x); a_dw2.y = fmaf(gpv, fmaxf(oy, 0.f), a_dw2.y);
-      const float gox = ox > 0.f ? gpv * w2.x : 0.f, goy = oy > 0.f ? gpv * w2.y : 0.f;
-      a_db.x += gox; a_db.y += goy;
-      a_dg.x = fmaf(gox, qh.x, a_dg.x); a_dg.y = fmaf(goy, qh.y, a_dg.y);
-      m1.x = fmaf(gam.x, gox, m1.x); m1.y = fmaf(gam.y, goy, m1.y);
-      m2.x = fmaf(gam.x * gox, qh.x, m2.x); m2.y = fmaf(gam.y * goy, qh.y, m2.y);
+      float dot[RB], part[RB];
+      float2 gh[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        dot[i] = gT[i].x * C[i].x + gT[i].y * C[i].y;
+        const float2 gz = make_float2(gz0[i].x + gcore.x, gz0[i].y + gcore.y);
+        part[i] = gz.x * (h[i].x - muH.x - fu[i].x * sd.x) + gz.y * (h[i].y - muH.y - fu[i].y * sd.y);
+        gh[i] = make_float2(fmaf(lam[i], gz.x, gread.x), fmaf(lam[i], gz.y, gread.y));
+        if (last) {
+          const float k = p.kl_scale / ((float)HID * n);
+          const float2 r1 = make_float2(sd.x * isd.x, sd.y * isd.y);                             // sigma/(sigma+e)
+          const float2 r2 = make_float2((h[i].x - muH.x) * isd.x, (h[i].y - muH.y) * isd.y);     // (H-mu)/(sigma+e)
+          part[i] += k * (-(1.f - lam[i]) * (r1.x * r1.x + r1.y * r1.y) + 2.f * n * lam[i] * (r2.x * r2.x + r2.y * r2.y));
+          gh[i].x += k * 2.f * n * lam[i] * lam[i] * r2.x * isd.x;
+          gh[i].y += k * 2.f * n * lam[i] * lam[i] * r2.y * isd.y;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+          part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = vb + i;
+        if (v >= v1) break;
+        const float dl = al[i] * (dot[i] - S);
+        st2(p.gC + (size_t)v * HID + c, make_float2(fmaf(dl, wc.x, al[i] * gT[i].x), fmaf(dl, wc.y, al[i] * gT[i].y)));
+        a_dwc.x = fmaf(dl, C[i].x, a_dwc.x); a_dwc.y = fmaf(dl, C[i].y, a_dwc.y);
+        st2(p.gH + (size_t)v * HID + c, gh[i]);
+        const float gpv = part[i] * lam[i] * (1.f - lam[i]);
+        if (lane == 0) p.gp[v] = gpv;
+        a_dbc2 += gpv;
+        const float2 qh = make_float2((q[i].x - muQ.x) * rstd.x, (q[i].y - muQ.y) * rstd.y);
+        const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
+        a_dw2.x = fmaf(gpv, fmaxf(ox, 0.f), a_dw2.x); a_dw2.y = fmaf(gpv, fmaxf(oy, 0.f), a_dw2.y);
+        const float gox = ox > 0.f ? gpv * w2.x : 0.f, goy = oy > 0.f ? gpv * w2.y : 0.f;
+        a_db.x += gox; a_db.y += goy;
+        a_dg.x = fmaf(gox, qh.x, a_dg.x); a_dg.y = fmaf(goy, qh.y, a_dg.y);
+        m1.x = fmaf(gam.x, gox, m1.x); m1.y = fmaf(gam.y, goy, m1.y);
+        m2.x = fmaf(gam.x * gox, qh.x, m2.x); m2.y = fmaf(gam.y * goy, qh.y, m2.y);
+        // pass C needs gpv of this row again: keep it in the q slot's x lane is not possible (per-lane data) -> re-read gp
+      }
     }
     m1.x /= n; m1.y /= n; m2.x /= n; m2.y /= n;
     __syncwarp();
     // ---- pass C: per-graph BN backward -> g_q
-    for (int v = v0; v < v1; ++v) {
-      const float gpv = __ldcg(p.gp + v);
-      const float2 q = ld2(p.q + (size_t)v * HID + c);
-      const float2 qh = make_float2((q.x - muQ.x) * rstd.x, (q.y - muQ.y) * rstd.y);
-      const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
-      const float gox = ox > 0.f ? gpv * w2.x : 0.f, goy = oy > 0.f ? gpv * w2.y : 0.f;
-      st2(p.g_q + (size_t)v * HID + c, make_float2(rstd.x * (gam.x * gox - m1.x - qh.x * m2.x),
-                                                    rstd.y * (gam.y * goy - m1.y - qh.y * m2.y)));
+    for (int vb = v0; vb < v1; vb += RB) {
+      float gpv[RB];
+      float2 q[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = min(vb + i, v1 - 1);
+        gpv[i] = __ldcg(p.gp + v);
+        q[i] = ld2(p.q + (size_t)v * HID + c);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = vb + i;
+        if (v >= v1) break;
+        const float2 qh = make_float2((q[i].x - muQ.x) * rstd.x, (q[i].y - muQ.y) * rstd.y);
+        const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
+        const float gox = ox > 0.f ? gpv[i] * w2.x : 0.f, goy = oy > 0.f ? gpv[i] * w2.y : 0.f;
+        st2(p.g_q + (size_t)v * HID + c, make_float2(rstd.x * (gam.x * gox - m1.x - qh.x * m2.x),
+                                                      rstd.y * (gam.y * goy - m1.y - qh.y * m2.y)));
+      }
     }
   }
   // ---- parameter-gradient partials: warp -> CTA -> last CTA
