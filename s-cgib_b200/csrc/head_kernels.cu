@@ -190,6 +190,7 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
     const float n = (float)(v1 - v0);
     // pass 1: means
     float2 sH = make_float2(0.f, 0.f), sQ = make_float2(0.f, 0.f);
+#pragma unroll 4
     for (int v = v0; v < v1; ++v) {
       const float2 h = ld2(p.H + (size_t)v * HID + c), q = ld2(p.q + (size_t)v * HID + c);
       sH.x += h.x; sH.y += h.y; sQ.x += q.x; sQ.y += q.y;
@@ -197,6 +198,7 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
     const float2 muH = make_float2(sH.x / n, sH.y / n), muQ = make_float2(sQ.x / n, sQ.y / n);
     // pass 2: centred second moments
     float2 vH = make_float2(0.f, 0.f), vQ = make_float2(0.f, 0.f);
+#pragma unroll 4
     for (int v = v0; v < v1; ++v) {
       const float2 h = ld2(p.H + (size_t)v * HID + c), q = ld2(p.q + (size_t)v * HID + c);
       float d;
@@ -216,26 +218,45 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
     const bool last = (g == p.B - 1);
     float2 core = make_float2(0.f, 0.f), kl1 = make_float2(0.f, 0.f), kl2 = make_float2(0.f, 0.f);
     const float2 isd = make_float2(1.f / (sd.x + kKlEps), 1.f / (sd.y + kKlEps));
-    for (int v = v0; v < v1; ++v) {
-      const float2 h = ld2(p.H + (size_t)v * HID + c), q = ld2(p.q + (size_t)v * HID + c);
-      const float ox = fmaf((q.x - muQ.x) * rstd.x, gam.x, bet.x), oy = fmaf((q.y - muQ.y) * rstd.y, gam.y, bet.y);
-      const float pv = warp_sum(fmaxf(ox, 0.f) * w2.x + fmaxf(oy, 0.f) * w2.y) + bc2;
-      const float u = __ldg(p.gate_u + v);
-      const float eps = __fadd_rn(__fmul_rn(-0.9998f, u), 0.9999f);       // (bias-(1-bias))*u + (1-bias), bias=1e-4
-      const float gi = logf(eps) - logf(1.f - eps);
-      const float lam = 1.f / (1.f + expf(-(gi + pv)));
-      const float ln = 1.f - lam;
-      const float2 fu = ld2(p.feat_u + (size_t)v * HID + c);
-      const float2 m = make_float2(lam * h.x + ln * muH.x, lam * h.y + ln * muH.y);
-      const float2 s = make_float2(ln * sd.x, ln * sd.y);
-      const float2 z = make_float2(m.x + fu.x * s.x, m.y + fu.y * s.y);
-      st2(p.noisy + (size_t)v * HID + c, z);
-      core.x += z.x; core.y += z.y;
-      if (lane == 0) p.lam[v] = lam;
-      if (last) {
-        float t;
-        t = s.x * isd.x; kl1.x = fmaf(0.5f * t, t, kl1.x); t = s.y * isd.y; kl1.y = fmaf(0.5f * t, t, kl1.y);
-        t = (m.x - muH.x) * isd.x; kl2.x = fmaf(t, t, kl2.x); t = (m.y - muH.y) * isd.y; kl2.y = fmaf(t, t, kl2.y);
+    constexpr int RB = 4;      // rows in flight per warp (latency-bound loop: loads and shuffle chains of RB rows overlap)
+    for (int vb = v0; vb < v1; vb += RB) {
+      float2 h[RB], q[RB], fu[RB];
+      float u[RB], pv[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = min(vb + i, v1 - 1);
+        h[i] = ld2(p.H + (size_t)v * HID + c); q[i] = ld2(p.q + (size_t)v * HID + c);
+        fu[i] = ld2(p.feat_u + (size_t)v * HID + c); u[i] = __ldg(p.gate_u + v);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const float ox = fmaf((q[i].x - muQ.x) * rstd.x, gam.x, bet.x), oy = fmaf((q[i].y - muQ.y) * rstd.y, gam.y, bet.y);
+        pv[i] = fmaxf(ox, 0.f) * w2.x + fmaxf(oy, 0.f) * w2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) pv[i] += __shfl_xor_sync(0xffffffffu, pv[i], o);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int v = vb + i;
+        if (v >= v1) break;
+        const float eps = __fadd_rn(__fmul_rn(-0.9998f, u[i]), 0.9999f);       // (bias-(1-bias))*u + (1-bias), bias=1e-4
+        const float gi = logf(eps) - logf(1.f - eps);
+        const float lam = 1.f / (1.f + expf(-(gi + (pv[i] + bc2))));
+        const float ln = 1.f - lam;
+        const float2 m = make_float2(lam * h[i].x + ln * muH.x, lam * h[i].y + ln * muH.y);
+        const float2 sg = make_float2(ln * sd.x, ln * sd.y);
+        const float2 z = make_float2(m.x + fu[i].x * sg.x, m.y + fu[i].y * sg.y);
+        st2(p.noisy + (size_t)v * HID + c, z);
+        core.x += z.x; core.y += z.y;
+        if (lane == 0) p.lam[v] = lam;
+        if (last) {
+          float t;
+          t = sg.x * isd.x; kl1.x = fmaf(0.5f * t, t, kl1.x); t = sg.y * isd.y; kl1.y = fmaf(0.5f * t, t, kl1.y);
+          t = (m.x - muH.x) * isd.x; kl2.x = fmaf(t, t, kl2.x); t = (m.y - muH.y) * isd.y; kl2.y = fmaf(t, t, kl2.y);
+        }
       }
     }
     st2(p.core + (size_t)g * HID + c, core);
