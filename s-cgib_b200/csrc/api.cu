@@ -43,6 +43,14 @@ static bool use_tc_contrastive() {
   return g_con_tc == 1;
 }
 
+// layers alternate the direction in which they walk the row tiles (SCGIB_FWD_ALT=0 disables): layer l+1 starts with the
+// rows layer l wrote last, which are still in L2
+static bool fwd_alternate() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_FWD_ALT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers).
@@ -304,6 +312,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       a.part = e == 0 ? w.small_part : w.small_part2; a.counter = w.counters + (e == 0 ? 0 : 8);
       a.bn_out = w.bn[e][l];
       a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
+      a.reverse = (l & 1) && fwd_alternate();
     }
     const int kin = l == 0 ? DTR : HID, m = tensor_core_mode();
     if (m == 4) {

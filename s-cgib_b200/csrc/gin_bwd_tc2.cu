@@ -82,7 +82,11 @@ gin_bwd_tc2_kernel(GinBwdMainPair pp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.V + TM - 1) / TM;
   const int my_tiles = max(0, (n_tiles - bid + nblk - 1) / nblk);
-  auto tile_base = [&](int i) { return (bid + i * nblk) * TM; };
+  // Tiles are walked in DESCENDING row order: gin_bwd_pre (the previous launch) walks ascending, so the rows it touched
+  // last (g_o just written, y just read) are still in the 126 MB L2 when this kernel starts, and the g_a rows this kernel
+  // writes last (the lowest) are the ones the next layer's gin_bwd_pre gathers first.
+  const bool rev = pp.reverse != 0;
+  auto tile_base = [&](int i) { return (bid + (rev ? my_tiles - 1 - i : i) * nblk) * TM; };
   auto Xs = [&](int s) { return smem + L::off_stage + s * kStage; };
   auto Ys = [&](int s) { return smem + L::off_stage + s * kStage + 2 * kTile; };
 
@@ -439,6 +443,7 @@ void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStr
   pp.a[0] = a; pp.a[1] = a;
   pp.split = grid;
   pp.trace = 0;
+  pp.reverse = 0;
   if (kin == DTR) launch_bwd2<DTR>(pp, grid, s); else launch_bwd2<HID>(pp, grid, s);
 }
 
@@ -449,6 +454,9 @@ void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs
   pp.a[0] = a0; pp.a[1] = a1;
   pp.split = pair_split(grid, (a0.V + 127) / 128, (a1.V + 127) / 128);
   pp.trace = bwd2_trace_flag();
+  static int rev = -1;
+  if (rev < 0) { const char* e = getenv("SCGIB_BWD_REV"); rev = (e && e[0] == '0') ? 0 : 1; }
+  pp.reverse = rev;
   if (kin == DTR) launch_bwd2<DTR>(pp, grid, s); else launch_bwd2<HID>(pp, grid, s);
 }
 

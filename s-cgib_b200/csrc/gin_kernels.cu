@@ -497,6 +497,21 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
     const int32_t* indices = p.indices[set];
     const int32_t* map = p.map[set];
     __syncthreads();
+    // x rows of the tile: issued first so that they are in flight during the gather (threads < PT own one row each)
+    float xv[9];
+    bool x_small = p.F <= 9, x_ok = false;
+    const float* xr = nullptr;
+    if (threadIdx.x < PT) {
+      const int v = base + threadIdx.x;
+      x_ok = v < V;
+      if (x_ok) {
+        xr = p.x + (size_t)(map ? __ldg(map + v) : v) * p.F;
+        if (x_small) {
+#pragma unroll
+          for (int f = 0; f < 9; ++f) xv[f] = f < p.F ? __ldg(xr + f) : 0.f;
+        }
+      }
+    }
     {  // gather gt rows: 8 lanes x float4 per row, the thread's 4 rows in flight together (latency-bound gather)
       const int l = threadIdx.x & 7, r0 = threadIdx.x >> 3;
       constexpr int NR = PT / (kThreads / 8);
@@ -511,19 +526,23 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
         d[0] = g[j].x; d[1] = g[j].y; d[2] = g[j].z; d[3] = g[j].w;
       }
     }
-    {  // x_hat rows: one thread per (row, half) is plenty
-      for (int r = threadIdx.x; r < PT; r += kThreads) {
-        const int v = base + r;
-        float* d = s_x + r * (FP + 1);
-        if (v < V) {
-          const float* xr = p.x + (size_t)(map ? __ldg(map + v) : v) * p.F;
-          float ss = 0.f;
-          for (int f = 0; f < p.F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
-          const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-          for (int f = 0; f < FP; ++f) d[f] = f < p.F ? __ldg(xr + f) * inv : 0.f;
-        } else {
-          for (int f = 0; f < FP; ++f) d[f] = 0.f;
-        }
+    if (threadIdx.x < PT) {  // x_hat rows -> shared memory
+      float* d = s_x + threadIdx.x * (FP + 1);
+      if (x_ok && x_small) {
+        float ss = 0.f;
+#pragma unroll
+        for (int f = 0; f < 9; ++f) ss = fmaf(xv[f], xv[f], ss);
+        const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+#pragma unroll
+        for (int f = 0; f < 9; ++f) d[f] = xv[f] * inv;
+        for (int f = 9; f < FP; ++f) d[f] = 0.f;
+      } else if (x_ok) {
+        float ss = 0.f;
+        for (int f = 0; f < p.F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
+        const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+        for (int f = 0; f < FP; ++f) d[f] = f < p.F ? __ldg(xr + f) * inv : 0.f;
+      } else {
+        for (int f = 0; f < FP; ++f) d[f] = 0.f;
       }
     }
     __syncthreads();

@@ -92,7 +92,8 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.V + TM - 1) / TM;
   const int my_tiles = (n_tiles - bid + nblk - 1) / nblk;     // tiles bid + i*nblk
-  auto tile_base = [&](int i) { return (bid + i * nblk) * TM; };
+  const bool rev = p.reverse != 0;
+  auto tile_base = [&](int i) { return (bid + (rev ? my_tiles - 1 - i : i) * nblk) * TM; };
 
   // ---- one-time setup: barriers, TMEM, weights (natural [out][in] = K-major B operand, dense cores), biases
   if (threadIdx.x == 0) {

@@ -28,6 +28,8 @@ struct GinFwdArgs {
   unsigned int* counter;
   float* bn_out;                      // {mean, rstd, gamma, beta}[HID]
   float* running;                     // optional {running_mean, running_var}[HID]
+  int reverse = 0;                    // gin_tc3: walk the row tiles in descending order (alternate layers: the rows the
+                                      //  previous layer wrote last are still in L2)
   int dbg = 0;                        // gin_tc2 experiments (SCGIB_DBG bit mask): 1 no r/y stores, 2 no stats, 4 no gather loads, 8 no a store
 };
 // Two independent problems of the same shape class (the same layer of Encoder1 and Encoder2) in ONE launch: CTAs
@@ -76,7 +78,7 @@ struct GinBwdMainArgs {
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
-struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; };
+struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; int reverse = 0; };
 void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
 void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
 void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // 64-row double-buffered tiles (gin_bwd_tc2.cu)

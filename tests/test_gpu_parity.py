@@ -284,3 +284,56 @@ def test_bad_arguments_raise():
         PretrainEngine(9, hidden=48, device=DEV)          # unsupported width -> SCGIB_E_SHAPE
     with pytest.raises(RuntimeError):
         PretrainEngine(9, device="cpu")                   # no CPU fallback
+
+
+def _edge_case_batch(kind):
+    if kind == "pairs":            # the smallest graphs the reference accepts (per-graph BatchNorm / unbiased std need n >= 2)
+        return batch_ref([path_graph(2, seed=i) for i in range(7)])
+    if kind == "single":           # B = 1: the contrastive loss has no negatives, the KL graph is the only graph
+        return synth_batch(21, 1)
+    if kind == "peptides":         # ~150-node graphs (BASELINE configs[4] shape): long per-graph loops, tiles spanning few graphs
+        return synth_batch(22, 6, "peptides")
+    if kind == "ragged":           # 2-node graphs next to 150-node graphs, a star (degree 12) and a 40-ring
+        star = graph_from_bonds(13, [(0, i) for i in range(1, 13)], seed=3)
+        ring = graph_from_bonds(40, [(i, (i + 1) % 40) for i in range(40)], seed=4)
+        mols = [path_graph(2, seed=1), synth_batch(23, 1, "peptides"), star, path_graph(3, seed=2), ring,
+                synth_batch(24, 1, "peptides"), path_graph(2, seed=5)]
+        return batch_ref(mols)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,k", [("pairs", 1), ("peptides", 1), ("peptides", 3), ("ragged", 2)])
+def test_parity_edge_shapes(kind, k):
+    """Ragged / extreme batches against the faithful oracle (same policy as test_parity_vs_faithful_oracle)."""
+    g = _edge_case_batch(kind)
+    e = ego_batch_ref(g, k)
+    torch.manual_seed(7)
+    m = OracleMainmodel(9)
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 300)
+    out = m.forward_faithful(tgraph_from_ref(g), x, tgraph_from_ego(e), x[en], gate_u, feat_u)
+    ref_grads = oracle_grads(m, out)
+    m.zero_grad()
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
+    truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
+    check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
+
+
+def test_single_graph_batch():
+    """B = 1: the contrastive loss is -log(e^s / e^s) = 0 (no negatives) - compared absolutely; everything else as usual."""
+    g = _edge_case_batch("single")
+    e = ego_batch_ref(g, 2)
+    torch.manual_seed(7)
+    m = OracleMainmodel(9).double()
+    x = normalize_rows(torch.from_numpy(g.x)).double()
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 300)
+    out = m.forward_faithful(tgraph_from_ref(g), x, tgraph_from_ego(e), x[en], gate_u.double(), feat_u.double())
+    eng, losses, emb = _run_engine(m.float(), g, e, 2, gate_u, feat_u)
+    assert torch.isfinite(losses).all() and torch.isfinite(eng.grads).all()
+    assert abs(float(losses[1])) <= 1e-6 and abs(float(out["contrastive"])) <= 1e-12
+    for i, name in ((0, "KL"), (2, "recon")):
+        assert abs(float(losses[i]) - float(out[name])) <= 1e-5 * abs(float(out[name])), name
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(emb[name].cpu(), out[name].detach()) <= 1e-5, name
