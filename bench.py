@@ -491,6 +491,20 @@ def main():
     except Exception:
         pass
 
+    # the HBM-bound aggregation / pooling / segment kernels (north_star: >= 60 % of HBM peak is the target): algorithmic
+    # bytes per launch (SURVEY 8d per-unit figures x this batch's sizes) / CUDA-event time per launch
+    d4 = 64 * 4
+    hbm_alg = {
+        "gin_bwd_pre.enc1+2": 3 * (b.N + b.Ns) * d4 + 4 * (b.N + b.Ns + 2 + b.E + b.Es),
+        "ego_pool_fwd": (b.Ns + b.N) * d4 + 4 * (b.N + 1) + 4 * b.N,
+        "graph_gate_fwd": 4 * b.N * d4 + 12 * b.N,
+        "recon_bwd": 2 * b.N * d4 + 4 * (b.N + 1 + b.E),
+        "input_proj_fwd": b.N * 9 * 4 + b.N * 32 * 4,
+    }
+    hbm_kernels = {k_: {"algorithmic_bytes_per_launch": v, "GB/s": v / (kernels[k_]["ms_per_launch"] * 1e-3) / 1e9,
+                        "frac": v / (kernels[k_]["ms_per_launch"] * 1e-3) / 1e9 / hbm}
+                   for k_, v in hbm_alg.items() if k_ in kernels}
+
     if rank == 0:
         graphs = args.batch * world * args.steps
         h2d = sum(t.numel() * t.element_size() for t in (host[0].graph_ptr, host[0].indptr, host[0].indices, host[0].ndata["x"]))
@@ -520,6 +534,7 @@ def main():
                                  "per-layer figure of both encoders' rows in the launch; see DESIGN.md section 3"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "peak": hbm, "unit": "GB/s", "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm},
+            "hbm_kernels": hbm_kernels,
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -48,6 +48,7 @@ ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
   for (int v = blockIdx.x * 16 + (threadIdx.x >> 4); v < p.N; v += gridDim.x * 16) {
     const int r0 = __ldg(p.ego_ptr + v), r1 = __ldg(p.ego_ptr + v + 1);
     float4 acc = make4(0.f);
+#pragma unroll 4
     for (int r = r0; r < r1; ++r) acc = add4(acc, b.act(ld4(p.y + (size_t)r * HID + l * 4)));
     st4(p.C + (size_t)v * HID + l * 4, acc);
     float d = acc.x * w.x + acc.y * w.y + acc.z * w.z + acc.w * w.w;
