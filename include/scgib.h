@@ -195,10 +195,14 @@ SCGIB_API int scgib_extract_forward_f32(const ScgibDims* d, const float* params,
  * r_g = sum alpha_v z_v, q* = [q || r]) -> predict = Linear(2H,H)-ReLU-Linear(H,C) (models.py:386-397) -> sigmoid
  * (models.py:519-520; sigmoid = 0 for the regression datasets, models.py:516-517).  One kernel per direction.
  * head_params / head_grads: one flat fp32 buffer, slots below (scgib_finetune_head_layout gives offsets, each slot
- * padded to 4 floats).  H in {64, 128}, C <= 64, T <= 8.  The forward leaves its saved state in `workspace`
+ * padded to 4 floats).  H in {32, 64, 128}, 0 <= C <= 64, T <= 8.  The forward leaves its saved state in `workspace`
  * (scgib_finetune_head_workspace_bytes, 256-byte aligned); the backward must get the same workspace and Z.
  *   fwd: scores [B,C]; optional readout [B,2H] (= q* after the last iteration, the Set2Set output).
- *   bwd: gZ [N,H] (overwritten) = d<g_scores, scores>/dZ; head_grads: every slot overwritten.
+ *   bwd: gZ [N,H] (overwritten) = d(<g_scores, scores> + <g_readout, readout>)/dZ; g_readout [B,2H] is optional;
+ *        head_grads: every slot overwritten.
+ * C = 0 is the bare Set2Set readout (no predict head; scores / g_scores unused, g_readout required): with H = 32 and
+ * zero-padded weights and features it serves Set2Set over the raw node features (Mainmodel_domainadapt.s2s_rev,
+ * models.py:114, 267 - padded hidden units have zero gates weights and stay exactly 0).
  * ------------------------------------------------------------------------------------------ */
 enum {
   SCGIB_FT_LSTM_WIH = 0, /* s2s.lstm.weight_ih_l0 [4H,2H]  (gate order i,f,g,o) */
@@ -218,8 +222,8 @@ SCGIB_API int scgib_finetune_head_fwd_f32(const float* head_params, int32_t H, i
                                           float* readout, void* workspace, size_t workspace_bytes, void* stream);
 SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
                                           const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N,
-                                          const float* scores, const float* g_scores, float* gZ, float* head_grads,
-                                          void* workspace, size_t workspace_bytes, void* stream);
+                                          const float* scores, const float* g_scores, const float* g_readout, float* gZ,
+                                          float* head_grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Adam with L2-in-gradient weight decay over one flat buffer (torch.optim.Adam(lr, weight_decay),
  * exp_pretraining.py:86,112,323).  step = 1-based step count; grad_scale multiplies the gradient

@@ -429,3 +429,40 @@ class OracleFinetune(nn.Module):
         if not self.no_sigmoid:
             s = torch.sigmoid(s)
         return dict(scores=s, Z=Z, interaction_map=imap, readout=q_star)
+
+
+class OracleDomainAdapt(nn.Module):
+    """models.py:107-355 (Mainmodel_domainadapt), GIN encoder: the feature path of the loaded model, Set2Set readout of
+    Z, ``r_transfer_d`` MLP to 2*in_dim, and a Set2Set readout of the RAW (normalised) features as the target;
+    ``X_loss = sum((r_transfer_d(s2s(Z)) - s2s_rev(x))**2)`` (models.py:254-275).  Every parameter of the loaded model
+    is trainable (models.py:176-178)."""
+
+    def __init__(self, inner: OracleMainmodel, in_dim, hidden_dim=64, d_transfer=32, num_classes=10, num_gin_layers=4):
+        super().__init__()
+        self.s2s = Set2SetRef(hidden_dim, 2, 1)
+        self.s2s_rev = Set2SetRef(in_dim, 2, 1)
+        self.transfer_d = nn.Linear(in_dim, d_transfer, bias=False)
+        self.embedding_h = nn.Linear(d_transfer, hidden_dim, bias=False)
+        self.reduce_d = nn.Linear(2 * hidden_dim, hidden_dim)
+        self.attn_layer = nn.Linear(2 * hidden_dim, 1)
+        self.r_transfer_d = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(),
+                                          nn.Linear(hidden_dim, in_dim * 2))
+        self.predict = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, num_classes))
+        self.MLP = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim))
+        self.Encoder1 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.Encoder2 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.model = inner
+        for p in self.model.parameters():
+            p.requires_grad = True
+        self.compressor = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(),
+                                        nn.Linear(hidden_dim, 1))
+        self.reconstructX = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, in_dim))
+
+    def forward(self, g: TGraph, x_norm, eg: TGraph, x_subs_norm, gate_u=None, feat_u=None):
+        batch_x = self.transfer_d(x_norm)
+        x_subs = self.transfer_d(x_subs_norm)
+        imap, _, _, _ = self.model.extract_features(g, batch_x, eg, x_subs, gate_u, feat_u)
+        Z = self.MLP(imap)
+        rec = self.r_transfer_d(self.s2s(g, Z))
+        org = self.s2s_rev(g, x_norm)
+        return dict(X_loss=torch.sum((rec - org) ** 2), rec=rec, org=org, Z=Z)

@@ -60,7 +60,8 @@ _SIGNATURES = {
     "scgib_finetune_head_fwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                             c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scgib_finetune_head_bwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
-                                            c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                            c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_void_p]),
     "scgib_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float,
                                     c_float, c_float, c_float, c_float, c_void_p]),
     "scgib_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_char_p]),

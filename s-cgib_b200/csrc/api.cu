@@ -590,7 +590,7 @@ static FtWs ft_carve(int H, int C, int T, int B, int N, void* base) {
   w.bytes = o;
   return w;
 }
-static bool ft_dims_ok(int H, int C, int T) { return (H == 64 || H == 128) && C >= 1 && C <= finetune_max_classes() && T >= 1 && T <= 8; }
+static bool ft_dims_ok(int H, int C, int T) { return (H == 32 || H == 64 || H == 128) && C >= 0 && C <= finetune_max_classes() && T >= 1 && T <= 8; }
 }  // namespace scgib
 
 extern "C" SCGIB_API int64_t scgib_finetune_head_layout(int32_t H, int32_t C, int64_t* offsets, int64_t* sizes) {
@@ -612,7 +612,7 @@ extern "C" SCGIB_API int scgib_finetune_head_fwd_f32(const float* head_params, i
                                            const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N, float* scores,
                                            float* readout, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!ft_dims_ok(H, C, T)) return SCGIB_E_SHAPE;
-  if (!head_params || !Z || !graph_ptr || !scores || !workspace) return SCGIB_E_NULL;
+  if (!head_params || !Z || !graph_ptr || (!scores && C > 0) || !workspace) return SCGIB_E_NULL;
   if (B < 1 || N < 1) return SCGIB_E_RANGE;
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)head_params & 15u) != 0 || ((uintptr_t)Z & 15u) != 0) return SCGIB_E_ALIGN;
   const FtLayout lo = ft_layout(H, C);
@@ -639,10 +639,11 @@ extern "C" SCGIB_API int scgib_finetune_head_fwd_f32(const float* head_params, i
 
 extern "C" SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, int32_t H, int32_t C, int32_t T, int32_t sigmoid,
                                            const float* Z, const int32_t* graph_ptr, int32_t B, int32_t N,
-                                           const float* scores, const float* g_scores, float* gZ, float* head_grads,
-                                           void* workspace, size_t workspace_bytes, void* stream_) {
+                                           const float* scores, const float* g_scores, const float* g_readout, float* gZ,
+                                           float* head_grads, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!ft_dims_ok(H, C, T)) return SCGIB_E_SHAPE;
-  if (!head_params || !Z || !graph_ptr || !scores || !g_scores || !gZ || !head_grads || !workspace) return SCGIB_E_NULL;
+  if (!head_params || !Z || !graph_ptr || !gZ || !head_grads || !workspace) return SCGIB_E_NULL;
+  if ((C > 0 && (!scores || !g_scores)) || (C == 0 && !g_readout)) return SCGIB_E_NULL;
   if (B < 1 || N < 1) return SCGIB_E_RANGE;
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)head_params & 15u) != 0 || ((uintptr_t)Z & 15u) != 0 ||
       ((uintptr_t)gZ & 15u) != 0)
@@ -656,7 +657,7 @@ extern "C" SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, i
   a.Wih = head_params + lo.off[SCGIB_FT_LSTM_WIH]; a.Whh = head_params + lo.off[SCGIB_FT_LSTM_WHH];
   a.Wp1 = head_params + lo.off[SCGIB_FT_PRED_W1]; a.Wp2 = head_params + lo.off[SCGIB_FT_PRED_W2];
   a.gates = w.gates; a.cst = w.cst; a.qstar = w.qstar; a.alpha = w.alpha; a.rp = w.rp; a.scores = scores;
-  a.g_scores = g_scores; a.g_pre = w.g_pre; a.g_u = w.g_u; a.dgates = w.dgates; a.gp = w.gp; a.gZ = gZ;
+  a.g_scores = g_scores; a.g_readout = g_readout; a.g_pre = w.g_pre; a.g_u = w.g_u; a.dgates = w.dgates; a.gp = w.gp; a.gZ = gZ;
   PROF("finetune_head_bwd", launch_finetune_head_bwd(a, s));
   // weight gradients: fixed-order reductions over the graphs
   float* g = head_grads;
@@ -667,6 +668,10 @@ extern "C" SCGIB_API int scgib_finetune_head_bwd_f32(const float* head_params, i
     cudaMemsetAsync(g + lo.off[SCGIB_FT_LSTM_WIH], 0, (size_t)(lo.off[SCGIB_FT_LSTM_BIH] - lo.off[SCGIB_FT_LSTM_WIH]) * sizeof(float), s);
   }
   PROF("ft_dbias", launch_atb(w.dgates, 4 * H, nullptr, 0, g + lo.off[SCGIB_FT_LSTM_BIH], 1, g + lo.off[SCGIB_FT_LSTM_BHH], T * B, 4 * H, 1, w.scratch, s));
+  if (C == 0) {     // readout only: the predict slots get zero gradients
+    cudaMemsetAsync(g + lo.off[SCGIB_FT_PRED_W1], 0, (size_t)(lo.total - lo.off[SCGIB_FT_PRED_W1]) * sizeof(float), s);
+    return (int)cudaGetLastError();
+  }
   PROF("ft_dWp1", launch_atb(w.g_u, H, w.qstar + (size_t)(T - 1) * B * 2 * H, 2 * H, g + lo.off[SCGIB_FT_PRED_W1], 2 * H, nullptr, B, H, 2 * H, w.scratch, s));
   PROF("ft_dbp1", launch_atb(w.g_u, H, nullptr, 0, g + lo.off[SCGIB_FT_PRED_B1], 1, nullptr, B, H, 1, w.scratch, s));
   PROF("ft_dWp2", launch_atb(w.g_pre, C, w.rp, H, g + lo.off[SCGIB_FT_PRED_W2], H, nullptr, B, C, H, w.scratch, s));

@@ -39,6 +39,12 @@ __device__ __forceinline__ void matvec_kmajor(const float* __restrict__ WT, int 
 
 // per-lane channel slice of a row: H/32 consecutive floats
 template <int H> struct Lane;
+template <> struct Lane<32> {   // small feature widths (Set2Set over raw features, zero-padded to 32 channels)
+  float v[1];
+  __device__ __forceinline__ void load(const float* row, int lane) { v[0] = row[lane]; }
+  __device__ __forceinline__ void store(float* row, int lane) const { row[lane] = v[0]; }
+  static constexpr int W = 1;
+};
 template <> struct Lane<64> {
   float v[2];
   __device__ __forceinline__ void load(const float* row, int lane) { const float2 t = *reinterpret_cast<const float2*>(row + lane * 2); v[0] = t.x; v[1] = t.y; }
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(kThreads) finetune_head_fwd_kernel(FinetuneHea
     }
     __syncthreads();
   }
+  if (p.C == 0) return;                 // readout only (Set2Set without a predict head)
   // ---- predict: u = relu(Wp1 q* + bp1), s = Wp2 u + bp2, optional sigmoid
   {
     const float* b1 = p.bp1;
@@ -199,33 +206,44 @@ __global__ void __launch_bounds__(kThreads) finetune_head_bwd_kernel(FinetuneHea
   const int g0 = blockIdx.x * FG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B = p.B, T = p.T, C = p.C;
-  // ---- predict backward
-  for (int i = threadIdx.x; i < FG * C; i += kThreads) {
-    const int g = i / C, c = i % C;
-    float v = 0.f;
-    if (g0 + g < B) {
-      v = p.g_scores[(size_t)(g0 + g) * C + c];
-      if (p.sigmoid) { const float s = p.scores[(size_t)(g0 + g) * C + c]; v *= s * (1.f - s); }
-      p.g_pre[(size_t)(g0 + g) * C + c] = v;
-    }
-    s_gpre[g][c] = v;
-  }
   for (int i = threadIdx.x; i < FG * H; i += kThreads) { (&sm.gh[0][0])[i] = 0.f; (&sm.gc[0][0])[i] = 0.f; }
-  __syncthreads();
-  matvec_natural(p.Wp2, C, H, &s_gpre[0][0], kMaxC, &sm.tmp[0][0], H);       // g_u (before the ReLU mask)
-  __syncthreads();
-  for (int i = threadIdx.x; i < FG * H; i += kThreads) {
-    const int g = i / H, c = i % H;
-    float v = 0.f;
-    if (g0 + g < B) {
-      v = p.rp[(size_t)(g0 + g) * H + c] > 0.f ? sm.tmp[g][c] : 0.f;
-      p.g_u[(size_t)(g0 + g) * H + c] = v;
+  if (C > 0) {
+    // ---- predict backward
+    for (int i = threadIdx.x; i < FG * C; i += kThreads) {
+      const int g = i / C, c = i % C;
+      float v = 0.f;
+      if (g0 + g < B) {
+        v = p.g_scores[(size_t)(g0 + g) * C + c];
+        if (p.sigmoid) { const float s = p.scores[(size_t)(g0 + g) * C + c]; v *= s * (1.f - s); }
+        p.g_pre[(size_t)(g0 + g) * C + c] = v;
+      }
+      s_gpre[g][c] = v;
     }
-    sm.tmp[g][c] = v;
+    __syncthreads();
+    matvec_natural(p.Wp2, C, H, &s_gpre[0][0], kMaxC, &sm.tmp[0][0], H);       // g_u (before the ReLU mask)
+    __syncthreads();
+    for (int i = threadIdx.x; i < FG * H; i += kThreads) {
+      const int g = i / H, c = i % H;
+      float v = 0.f;
+      if (g0 + g < B) {
+        v = p.rp[(size_t)(g0 + g) * H + c] > 0.f ? sm.tmp[g][c] : 0.f;
+        p.g_u[(size_t)(g0 + g) * H + c] = v;
+      }
+      sm.tmp[g][c] = v;
+    }
+    __syncthreads();
+    matvec_natural(p.Wp1, H, 2 * H, &sm.tmp[0][0], H, &sm.gq[0][0], 2 * H);    // g wrt q*_{T-1}
+  } else {
+    for (int i = threadIdx.x; i < FG * 2 * H; i += kThreads) (&sm.gq[0][0])[i] = 0.f;
   }
   __syncthreads();
-  matvec_natural(p.Wp1, H, 2 * H, &sm.tmp[0][0], H, &sm.gq[0][0], 2 * H);    // g wrt q*_{T-1}
-  __syncthreads();
+  if (p.g_readout) {                      // upstream gradient given directly at the Set2Set output q*_{T-1}
+    for (int i = threadIdx.x; i < FG * 2 * H; i += kThreads) {
+      const int g = i / (2 * H), c = i % (2 * H);
+      if (g0 + g < B) sm.gq[g][c] += p.g_readout[(size_t)(g0 + g) * 2 * H + c];
+    }
+    __syncthreads();
+  }
   for (int t = T - 1; t >= 0; --t) {
     // ---- attention backward of graph g0 + warp; adds the attention path to the q half of gq
     const int g = g0 + warp;
@@ -353,13 +371,15 @@ __global__ void __launch_bounds__(kThreads) atb_reduce_kernel(const float* __res
 
 void launch_finetune_head_fwd(const FinetuneHeadFwdArgs& a, cudaStream_t s) {
   const int grid = (a.B + FG - 1) / FG;
-  if (a.H == 64) finetune_head_fwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
+  if (a.H == 32) finetune_head_fwd_kernel<32><<<grid, kThreads, 0, s>>>(a);
+  else if (a.H == 64) finetune_head_fwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
   else finetune_head_fwd_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 
 void launch_finetune_head_bwd(const FinetuneHeadBwdArgs& a, cudaStream_t s) {
   const int grid = (a.B + FG - 1) / FG;
-  if (a.H == 64) finetune_head_bwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
+  if (a.H == 32) finetune_head_bwd_kernel<32><<<grid, kThreads, 0, s>>>(a);
+  else if (a.H == 64) finetune_head_bwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
   else finetune_head_bwd_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 

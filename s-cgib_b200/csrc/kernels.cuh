@@ -267,7 +267,8 @@ struct FinetuneHeadBwdArgs {
   const float* Z; const int32_t* graph_ptr; int B, N, H, C, T, sigmoid;
   const float *Wih, *Whh, *Wp1, *Wp2;    // natural layouts
   const float *gates, *cst, *qstar, *alpha, *rp, *scores;
-  const float* g_scores;                 // [B][C]
+  const float* g_scores;                 // [B][C]  (unused when C == 0)
+  const float* g_readout;                // optional [B][2H]: upstream gradient at the Set2Set output itself
   float *g_pre, *g_u, *dgates, *gp;      // [B][C], [B][H], [T][B][4H], [N] scratch
   float* gZ;                             // [N][H]
 };

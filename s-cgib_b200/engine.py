@@ -400,6 +400,8 @@ class FinetuneHead:
         self.total, self.offsets, self.sizes = total, list(off), list(sz)
         H, C = self.H, self.C
         self.shapes = [(4 * H, 2 * H), (4 * H, H), (4 * H,), (4 * H,), (H, 2 * H), (H,), (C, H), (C,)]
+        if C == 0:
+            self.shapes[6], self.shapes[7] = (0, H), (0,)
         self.names = list(FT_NAMES)
         self.params = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros_like(self.params)
@@ -412,7 +414,8 @@ class FinetuneHead:
 
     def load_state_dict(self, sd):
         for n, t in self.views().items():
-            t.copy_(sd[n].reshape(t.shape))
+            if t.numel():
+                t.copy_(sd[n].reshape(t.shape))
 
     def _workspace(self, B, N):
         need = self.lib.scgib_finetune_head_workspace_bytes(self.H, self.C, self.T, B, N)
@@ -427,25 +430,76 @@ class FinetuneHead:
         B, N = graph_ptr.numel() - 1, Z.shape[0]
         assert Z.shape[1] == self.H and Z.dtype == torch.float32 and graph_ptr.dtype == torch.int32
         ws = self._workspace(B, N)
-        scores = torch.empty(B, self.C, device=self.device)
-        readout = torch.empty(B, 2 * self.H, device=self.device) if want_readout else None
+        scores = torch.empty(B, max(self.C, 1), device=self.device)
+        readout = torch.empty(B, 2 * self.H, device=self.device) if (want_readout or self.C == 0) else None
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_finetune_head_fwd_f32(_lib.ptr(self.params), self.H, self.C, self.T, int(self.sigmoid),
                                                         _lib.ptr(Z), _lib.ptr(graph_ptr), B, N, _lib.ptr(scores),
                                                         _lib.ptr(readout), _lib.ptr(ws), ws.numel(), st), "finetune_head_fwd")
         self._saved = (Z, graph_ptr, scores)
+        if self.C == 0:
+            return readout
         return (scores, readout) if want_readout else scores
 
-    def backward(self, g_scores: torch.Tensor):
-        """Returns gZ [N,H]; the head's parameter gradients are written to ``self.grads`` (overwritten)."""
+    def backward(self, g_scores: Optional[torch.Tensor] = None, g_readout: Optional[torch.Tensor] = None):
+        """Returns gZ [N,H]; the head's parameter gradients are written to ``self.grads`` (overwritten).  ``g_readout``
+        [B,2H]: optional upstream gradient at the Set2Set output (required when the head has no predict MLP, C = 0)."""
         Z, graph_ptr, scores = self._saved
         B, N = graph_ptr.numel() - 1, Z.shape[0]
-        g_scores = g_scores.contiguous().float()
+        g_scores = None if g_scores is None else g_scores.contiguous().float()
+        g_readout = None if g_readout is None else g_readout.contiguous().float()
         gZ = torch.empty_like(Z)
         ws = self._workspace(B, N)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_finetune_head_bwd_f32(_lib.ptr(self.params), self.H, self.C, self.T, int(self.sigmoid),
                                                         _lib.ptr(Z), _lib.ptr(graph_ptr), B, N, _lib.ptr(scores),
-                                                        _lib.ptr(g_scores), _lib.ptr(gZ), _lib.ptr(self.grads),
+                                                        _lib.ptr(g_scores), _lib.ptr(g_readout), _lib.ptr(gZ), _lib.ptr(self.grads),
                                                         _lib.ptr(ws), ws.numel(), st), "finetune_head_bwd")
         return gZ
+
+
+class PaddedSet2Set:
+    """``dgl.nn.Set2Set(h, n_iters, 1)`` for a small feature width h <= 32 (Mainmodel_domainadapt.s2s_rev over the raw
+    node features, models.py:114, 267) on the H = 32 instance of the head kernels: weights and features are zero-padded
+    to 32 channels.  A padded hidden unit has zero gate pre-activations (i = f = o = 1/2, g = 0), so its cell and
+    hidden state stay exactly 0 and the real channels are untouched.  The scatter / gather between the module's
+    real-shaped LSTM parameters and the padded flat buffer is index plumbing on four small tensors."""
+
+    P = 32
+
+    def __init__(self, h: int, n_iters: int = 2, device="cuda:0"):
+        if not 1 <= h <= self.P:
+            raise NotImplementedError("PaddedSet2Set: feature width must be <= 32")
+        self.h, self.device = int(h), torch.device(device)
+        self.head = FinetuneHead(self.P, 0, n_iters=n_iters, sigmoid=False, device=device)
+        P, dev = self.P, self.device
+        gate_rows = torch.cat([g * P + torch.arange(h) for g in range(4)]).to(dev)                 # [4h] rows of the padded gates
+        in_cols = torch.cat([torch.arange(h), P + torch.arange(h)]).to(dev)                        # [2h] q half | readout half
+        self.idx = dict(rows=gate_rows, in_cols=in_cols, hid_cols=torch.arange(h, device=dev),
+                        out_cols=in_cols)
+
+    def set_params(self, w_ih, w_hh, b_ih, b_hh):
+        v = self.head.views()
+        self.head.params.zero_()
+        ix = self.idx
+        v["s2s.lstm.weight_ih_l0"][ix["rows"][:, None], ix["in_cols"][None, :]] = w_ih.detach().float()
+        v["s2s.lstm.weight_hh_l0"][ix["rows"][:, None], ix["hid_cols"][None, :]] = w_hh.detach().float()
+        v["s2s.lstm.bias_ih_l0"][ix["rows"]] = b_ih.detach().float()
+        v["s2s.lstm.bias_hh_l0"][ix["rows"]] = b_hh.detach().float()
+
+    def forward(self, x: torch.Tensor, graph_ptr: torch.Tensor):
+        """x [N, h] -> Set2Set output [B, 2h]."""
+        xp = torch.zeros(x.shape[0], self.P, device=self.device)
+        xp[:, :self.h] = x
+        ro = self.head.forward(xp, graph_ptr)
+        return ro[:, self.idx["out_cols"]]
+
+    def backward(self, g_out: torch.Tensor):
+        """g_out [B, 2h] -> gradients of the four LSTM tensors in their real shapes."""
+        gp = torch.zeros(g_out.shape[0], 2 * self.P, device=self.device)
+        gp[:, self.idx["out_cols"]] = g_out.float()
+        self.head.backward(None, gp)
+        gv, ix = self.head.views(grads=True), self.idx
+        return (gv["s2s.lstm.weight_ih_l0"][ix["rows"][:, None], ix["in_cols"][None, :]].clone(),
+                gv["s2s.lstm.weight_hh_l0"][ix["rows"][:, None], ix["hid_cols"][None, :]].clone(),
+                gv["s2s.lstm.bias_ih_l0"][ix["rows"]].clone(), gv["s2s.lstm.bias_hh_l0"][ix["rows"]].clone())

@@ -14,7 +14,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .engine import FT_NAMES, HID, DeviceBatch, FinetuneHead, PretrainEngine, bn_buffer_names, param_names
+from .engine import (FT_NAMES, HID, DeviceBatch, FinetuneHead, PaddedSet2Set, PretrainEngine, bn_buffer_names,
+                     param_names)
 from .graph import BatchedGraph, EgoBatch, khop_ego_batch
 
 DEFAULT_GIN_LAYERS = 4   # reference models.py:57-58: ``num_layers = 5; range(num_layers - 1)``
@@ -446,3 +447,131 @@ class Mainmodel_finetuning(nn.Module):
 
     def lossMAE(self, scores, targets):
         return nn.L1Loss()(scores, targets)
+
+
+DA_NAMES = ["s2s.lstm.weight_ih_l0", "s2s.lstm.weight_hh_l0", "s2s.lstm.bias_ih_l0", "s2s.lstm.bias_hh_l0",
+            "r_transfer_d.0.weight", "r_transfer_d.0.bias", "r_transfer_d.2.weight", "r_transfer_d.2.bias"]
+REV_NAMES = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+
+
+class _DomainAdaptFn(torch.autograd.Function):
+    """-> (r_transfer_d(s2s(MLP(extract_features))) [B, 2 in_dim], s2s_rev(x) [B, 2 in_dim])."""
+
+    @staticmethod
+    def forward(ctx, owner, batch, gate_u, feat_u, x_norm, *params):
+        eng, head, rev = owner._bridge.engine, owner._head, owner._rev
+        Z = eng.forward_features(batch, gate_u, feat_u, update_running=owner.training)
+        rec = head.forward(Z, batch.g.graph_ptr)
+        org = rev.forward(x_norm, batch.g.graph_ptr)
+        ctx.owner = owner
+        return rec, org
+
+    @staticmethod
+    def backward(ctx, g_rec, g_org):
+        owner = ctx.owner
+        eng, head, rev = owner._bridge.engine, owner._head, owner._rev
+        gZ = head.backward(g_rec)
+        eng.extract_backward(gZ)
+        gv, hv = eng.grad_views(), head.views(grads=True)
+        grads = [gv[n].clone() for n in owner._bridge.slot_names] + [hv[n].clone() for n in FT_NAMES]
+        grads += list(rev.backward(g_org))
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class Mainmodel_domainadapt(nn.Module):
+    """reference models.py:107-355: domain adaptation of a pre-trained model to a new dataset's feature space.
+    ``forward(...) -> X_loss = sum((r_transfer_d(s2s(MLP(extract_features))) - s2s_rev(batch_x))**2)`` (models.py:254-275);
+    every parameter of the loaded model is trainable (models.py:176-178).  Both Set2Set readouts and the r_transfer_d
+    MLP run in the fine-tuning head kernels (csrc/finetune_kernels.cu); the squared-error sum over the [B, 2 in_dim]
+    outputs is the reference's one-liner."""
+
+    def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, num_classes, cp_filename, encoder):
+        super().__init__()
+        _check_args(args, encoder)
+        self.tau = 1.0
+        self.readout = args.readout_f
+        self.gin_layers = int(getattr(args, "gin_layers", DEFAULT_GIN_LAYERS))
+        self.in_dim_raw = in_dim
+        self.s2s = _Set2SetParams(hidden_dim, 2, 1)
+        self.s2s_rev = _Set2SetParams(in_dim, 2, 1)
+        self.in_dim = args.d_transfer
+        self.transfer_d = nn.Linear(in_dim, self.in_dim, bias=False)
+        self.batch_size = args.batch_size
+        self.useAtt = args.useAtt
+        self.embedding_h = nn.Linear(self.in_dim, hidden_dim, bias=False)
+        self.hidden_dim = hidden_dim
+        self.k_transition = k_transition
+        self.reduce_d = nn.Linear(2 * self.hidden_dim, self.hidden_dim)
+        self.attn_layer = nn.Linear(2 * self.hidden_dim, 1)
+        self.num_nodes = -1
+        self.device = args.device
+        self.r_transfer_d = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                          nn.Linear(self.hidden_dim, in_dim * 2))
+        out_dim = 1 if getattr(args, "task", "graph_classification") == "graph_regression" else num_classes
+        self.predict = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                     nn.Linear(self.hidden_dim, out_dim))
+        self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                 nn.Linear(self.hidden_dim, self.hidden_dim))
+        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        print("Loading pre-trained model .pt  ... ")
+        self.model = torch.load(cp_filename, map_location=args.device, weights_only=False)
+        for p in self.model.parameters():
+            p.requires_grad = True
+        self.compressor = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.BatchNorm1d(self.hidden_dim),
+                                        nn.ReLU(), nn.Linear(self.hidden_dim, 1))
+        self.reconstructX = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.ReLU(),
+                                          nn.Linear(self.hidden_dim, in_dim))
+        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+        self._head = None
+        self._rev = None
+
+    __getstate__ = Mainmodel.__getstate__
+
+    def __setstate__(self, st):
+        Mainmodel.__setstate__(self, st)
+        self._head = None
+        self._rev = None
+
+    _device_batch = _HotPathMixin._device_batch
+    _noise = _HotPathMixin._noise
+
+    def _sync_heads(self, device):
+        device = torch.device(device)
+        if self._head is None or self._head.device != device:
+            self._head = FinetuneHead(self.hidden_dim, 2 * self.in_dim_raw, n_iters=self.s2s.n_iters, sigmoid=False,
+                                      device=device)
+            self._rev = PaddedSet2Set(self.in_dim_raw, n_iters=self.s2s_rev.n_iters, device=device)
+        views = self._head.views()
+        params = []
+        for name, slot in zip(DA_NAMES, FT_NAMES):          # r_transfer_d sits in the head's predict slots
+            obj = self
+            parts = name.split(".")
+            for p in parts[:-1]:
+                obj = obj[int(p)] if p.isdigit() else getattr(obj, p)
+            prm = getattr(obj, parts[-1])
+            v = views[slot]
+            if prm.data_ptr() != v.data_ptr():
+                v.copy_(prm.data.to(device).reshape(v.shape))
+                prm.data = v
+            params.append(prm)
+        rev_params = [getattr(self.s2s_rev.lstm, n) for n in REV_NAMES]
+        self._rev.set_params(*[p.data.to(device) for p in rev_params])
+        return params + rev_params
+
+    def forward(self, batch_g, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, current_epoch, edge_index,
+                k_transition, device, batch_size=16):
+        """reference models.py:254-269 -> X_loss (scalar)."""
+        self.batch_size = batch_size
+        self.device = device
+        params = self._bridge.sync(device) + self._sync_heads(device)
+        self._bridge.training = self.training
+        b = self._device_batch(batch_g, batch_x, flatten_batch_subgraphs, device)
+        gate_u, feat_u = self._noise(b.N, b.g.device)
+        rec, org = _DomainAdaptFn.apply(self, b, gate_u, feat_u, b.x, *params)
+        if self.training:
+            _HotPathMixin._bump_batches_tracked(self, b.B)
+        return self.loss_X(org, rec)
+
+    def loss_X(self, batch_x_org, interaction_map):
+        return torch.sum((interaction_map - batch_x_org) ** 2)

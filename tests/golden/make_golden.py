@@ -149,6 +149,58 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
           "trainable:", len(trainable))
 
 
+def make_domainadapt(seed, B, k, ref_models, dgl_stub, out_path):
+    """Mainmodel_domainadapt (models.py:107-355) around a pickled pre-trained Mainmodel: X_loss + backward, one step of
+    train_pep_func.train_epoch_domainadaptation (train_pep_func.py:91-124)."""
+    import functools
+    import tempfile
+    g = synth_batch(seed, B)
+    e = ego_batch_ref(g, k)
+    s, d = g.edges()
+    bg = dgl_stub.StubGraph(g.graph_ptr, s, d, g.num_nodes)
+    bg.ndata["x"] = torch.from_numpy(g.x)
+    es_dst = np.repeat(np.arange(e.num_rows), np.diff(e.sub_indptr))
+    eg = dgl_stub.StubGraph(e.ego_ptr, e.sub_indices, es_dst, e.num_rows)
+    eg.ndata["x"] = torch.from_numpy(g.x[e.ego_nodes])
+    pre_args = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
+    torch.manual_seed(seed)
+    pre = ref_models.Mainmodel(pre_args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    ckpt = os.path.join(tempfile.mkdtemp(), "pre_training_synth_GIN_64_4_%d.pt" % k)
+    torch.save(pre, ckpt)
+    args = types.SimpleNamespace(dataset="Peptides-func", readout_f="sum", d_transfer=32, batch_size=B, useAtt=1,
+                                 device="cpu", task="graph_classification")
+    real_load = torch.load
+    torch.load = functools.partial(real_load, weights_only=False)
+    try:
+        torch.manual_seed(seed + 7)
+        model = ref_models.Mainmodel_domainadapt(args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k,
+                                                 num_classes=10, cp_filename=ckpt, encoder="GIN")
+    finally:
+        torch.load = real_load
+    model.train()
+    state0 = {n: t.detach().clone() for n, t in model.state_dict().items()}
+    batch_x = F.normalize(bg.ndata["x"].float())
+    x_subs = F.normalize(eg.ndata["x"].float())
+    noise_seed = 1000 + seed
+    torch.manual_seed(noise_seed)
+    loss = model.forward(bg, batch_x, eg, None, x_subs, 1, bg.edges(), 2, "cpu", B)
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    state1 = {n: t.detach().clone() for n, t in model.state_dict().items() if "running" in n or "num_batches" in n}
+    used = set(grads) | {n for n in state0 if n.startswith("model.") and
+                         n.split(".")[1] in ("Encoder1", "Encoder2", "compressor", "attn_layer")}
+    fx = dict(
+        meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed,
+                  reference="models.py Mainmodel_domainadapt (unmodified) on dgl_stub", torch=torch.__version__),
+        graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
+        ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
+        state={n: t for n, t in state0.items() if n in used}, state_after={n: t for n, t in state1.items() if n in used},
+        out=dict(X_loss=loss.detach()), grads=grads,
+    )
+    torch.save(fx, out_path)
+    print(out_path, os.path.getsize(out_path), "bytes", "X_loss %.6f" % float(loss), "grads:", len(grads))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -159,3 +211,4 @@ if __name__ == "__main__":
     make(2, 3, 3, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k3_b3.pt"))
     make_finetune(3, 5, 1, ref_models, dgl_stub, os.path.join(HERE, "finetune_k1_b5.pt"))
     make_finetune(4, 11, 2, ref_models, dgl_stub, os.path.join(HERE, "finetune_k2_b11.pt"))
+    make_domainadapt(5, 7, 1, ref_models, dgl_stub, os.path.join(HERE, "domainadapt_k1_b7.pt"))

@@ -168,3 +168,76 @@ def test_mainmodel_finetuning_b256_vs_fp64_oracle(tmp_path, monkeypatch):
     assert set(refg) == set(got)
     errs = sorted((rel(got[n], refg[n]), n) for n in refg if float(refg[n].abs().max()) > 1e-6)
     assert errs[len(errs) // 2][0] <= 5e-5 and errs[-1][0] <= 5e-3, errs[-3:]
+
+
+DA_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "domainadapt_*.pt")))
+
+
+@pytest.mark.parametrize("h,T,B", [(9, 2, 23), (11, 3, 40), (32, 2, 9), (1, 1, 5)])
+def test_padded_set2set_small_width(h, T, B):
+    """Set2Set over narrow features (width h <= 32) on the zero-padded H = 32 kernels: output and LSTM gradients."""
+    from scgib_b200.engine import PaddedSet2Set
+    rng = np.random.default_rng(h + T + B)
+    sizes = rng.integers(1, 30, size=B)
+    tg = _seg_graph(sizes)
+    N = int(sizes.sum())
+    torch.manual_seed(h)
+    ref = Set2SetRef(h, T, 1).double()
+    x = torch.randn(N, h, dtype=torch.float64)
+    out = ref(tg, x)
+    g_out = torch.randn(B, 2 * h, dtype=torch.float64)
+    (out * g_out).sum().backward()
+    s2s = PaddedSet2Set(h, n_iters=T, device=DEV)
+    lstm = ref.lstm
+    s2s.set_params(lstm.weight_ih_l0.to(DEV), lstm.weight_hh_l0.to(DEV), lstm.bias_ih_l0.to(DEV), lstm.bias_hh_l0.to(DEV))
+    gp = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)).to(DEV)
+    got = s2s.forward(x.float().to(DEV), gp)
+    assert rel(got.cpu(), out.detach()) <= 1e-5
+    grads = s2s.backward(g_out.float().to(DEV))
+    for gg, name in zip(grads, ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")):
+        r = getattr(lstm, name).grad
+        if float(r.abs().max()) == 0.0:
+            assert float(gg.abs().max()) == 0.0
+        else:
+            assert rel(gg.cpu(), r) <= 2e-5, (name, rel(gg.cpu(), r))
+
+
+@pytest.mark.parametrize("path", DA_GOLD, ids=[os.path.basename(p) for p in DA_GOLD])
+def test_mainmodel_domainadapt_matches_reference_golden(path, tmp_path, monkeypatch):
+    """models.Mainmodel_domainadapt (CUDA path) vs the golden run of the unmodified reference class: X_loss to 1e-5 and
+    the 73 gradients of one train_epoch_domainadaptation step."""
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    fx = torch.load(path, weights_only=False)
+    g, e = RefGraph(**fx["graph"]), RefEgoBatch(**fx["ego"])
+    k = fx["meta"]["k"]
+    pre = models.Mainmodel(_args(), 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    ckpt = str(tmp_path / "pre.pt")
+    torch.save(pre, ckpt)
+    m = models.Mainmodel_domainadapt(_args(), 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, num_classes=10,
+                                     cp_filename=ckpt, encoder="GIN")
+    missing, unexpected = m.load_state_dict(fx["state"], strict=False)
+    assert not unexpected
+    m = m.to(DEV).train()
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, k)
+    x = F.normalize(pg.ndata["x"].float())
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    monkeypatch.setattr(m, "_noise", lambda N, dev: (gate_u.to(dev), feat_u.to(dev)))
+    loss = m.forward(pg, x, ego, None, None, 1, None, 2, DEV, g.num_graphs)
+    assert abs(float(loss) - float(fx["out"]["X_loss"])) <= 1e-5 * abs(float(fx["out"]["X_loss"]))
+    loss.backward()
+    got = {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(fx["grads"])
+    gmax = max(float(v.abs().max()) for v in fx["grads"].values())
+    errs = []
+    for n, gref in fx["grads"].items():
+        if float(gref.abs().max()) <= 1e-6 * gmax:
+            assert float(got[n].abs().max()) <= 1e-4 * gmax, n
+            continue
+        gg = got[n]
+        if n == "model.attn_layer.weight":
+            gg, gref = gg[:, 64:], gref[:, 64:]
+        errs.append((rel(gg, gref), n))
+    errs.sort()
+    assert errs[len(errs) // 2][0] <= 5e-5 and errs[-1][0] <= 5e-3, errs[-3:]

@@ -139,3 +139,37 @@ def test_finetune_oracle_matches_reference(path):
             assert float(grads[n].abs().max()) <= 1e-5 * gmax, n
             continue
         assert rel(grads[n], gref) <= 1e-4, (n, rel(grads[n], gref))
+
+
+# ---------------------------------------------------------------- domain adaptation
+DA_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "domainadapt_*.pt")))
+
+
+@pytest.mark.parametrize("path", DA_GOLD, ids=[os.path.basename(p) for p in DA_GOLD])
+def test_domainadapt_oracle_matches_reference(path):
+    """OracleDomainAdapt (two Set2Set restatements + X loss) vs the unmodified Mainmodel_domainadapt: loss and all 73
+    gradients of one train_epoch_domainadaptation step."""
+    from oracle.scgib_oracle import OracleDomainAdapt
+    fx, g, e = load_fixture(path)
+    m = OracleDomainAdapt(OracleMainmodel(9, 64, 32, 4), 9)
+    missing, unexpected = m.load_state_dict(fx["state"], strict=False)
+    assert not unexpected
+    m.train()
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    x = normalize_rows(torch.from_numpy(g.x))
+    ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    out = m(tg, x, te, x[ego_nodes], gate_u, feat_u)
+    assert abs(float(out["X_loss"]) - float(fx["out"]["X_loss"])) <= 2e-6 * abs(float(fx["out"]["X_loss"]))
+    out["X_loss"].backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(grads) == set(fx["grads"])
+    gmax = max(float(v.abs().max()) for v in fx["grads"].values())
+    for n, gref in fx["grads"].items():
+        if float(gref.abs().max()) <= 1e-6 * gmax:
+            assert float(grads[n].abs().max()) <= 1e-5 * gmax, n
+            continue
+        if n == "model.attn_layer.weight":                  # core half: mathematically zero (SURVEY F14)
+            assert rel(grads[n][:, 64:], gref[:, 64:]) <= 1e-4
+            continue
+        assert rel(grads[n], gref) <= 1e-4, (n, rel(grads[n], gref))
