@@ -445,6 +445,39 @@ def main():
     step_ids(3)
     ms_ids = timed(step_ids, args.steps)
 
+    # ---- the reference-facing drop-in surface: exp_pretraining.train_epoch_pre_training's loop body (reference
+    #      exp_pretraining.py:300-324) on models.Mainmodel with torch.optim.Adam over the module parameters, host batches,
+    #      one .item() per step - what a user of the reference gets by swapping the imports (rank 0 timing, N = 1 only)
+    ms_dropin = None
+    if world == 1:
+        import types
+        import torch.nn.functional as F
+        import models as dropin_models
+        from scgib_b200.graph import khop_ego_batch
+        ns = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device=str(dev),
+                                   batch_size=args.batch, k_transition=args.k)
+        torch.manual_seed(0)
+        dm = dropin_models.Mainmodel(ns, 9, 64, 4, 4, args.k, "GIN").to(dev)
+        dm.train()
+        from exp_pretraining import make_optimizer
+        dopt = make_optimizer(dm.parameters(), 1e-4)          # torch.optim.Adam(lr, weight_decay=5e-5), as the reference
+
+        def step_dropin(steps):
+            for i in range(steps):
+                bg = host[i % n_batches].to(dev, non_blocking=True)
+                bx = bg.ndata["x"].float()
+                dopt.zero_grad()
+                ego = khop_ego_batch(bg, args.k)
+                bx = F.normalize(bx)
+                _, kl, con, rec = dm.forward(bg, bx, ego, None, None, 1, None, 2, dev, args.batch)
+                loss = kl + rec + con
+                loss.backward()
+                dopt.step()
+                state["loss_item"] = loss.detach().item()
+
+        step_dropin(3)
+        ms_dropin = timed(step_dropin, args.steps)
+
     # ---- per-kernel timing pass (CUDA events on the launching stream around every launch of the library)
     prof = {}
     nlaunch = 0
@@ -526,6 +559,11 @@ def main():
                                      "note": "dataset shard (%d molecules, %.1f MB) resident in HBM; per step only the B molecule ids "
                                              "cross PCIe, the batch is assembled on the GPU (scgib_batch_assemble_*)"
                                              % (len(dataset), dataset.nbytes() / 1e6)},
+            "e2e_dropin_module": None if ms_dropin is None else {
+                "value": graphs / (ms_dropin * 1e-3), "unit": UNIT, "ms_per_step": ms_dropin / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "note": "models.Mainmodel.forward + loss.backward() + torch.optim.Adam.step() + loss.item() per step, no "
+                        "prefetch: the reference's own training loop (exp_pretraining.py:300-324) on the drop-in classes"},
             "gpu_launches": (nlaunch + 5) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,

@@ -25,6 +25,13 @@ from scgib_b200.graph import BatchedGraph, khop_ego_batch
 from scgib_b200.synth import synth_batch
 
 
+def make_optimizer(params, lr):
+    """reference exp_pretraining.py:86,112: Adam(lr, weight_decay=5e-5) over the module parameters (views of the
+    engine's flat buffer).  torch's fused=True variant was measured slower here (2.94 vs 2.65 ms per step at B = 4096);
+    PretrainEngine.adam_step is the one-kernel alternative for loops written against the engine API."""
+    return torch.optim.Adam(list(params), lr=lr, weight_decay=5e-5)
+
+
 def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
     best_epoch, best_model, best_loss = 0, model, 100000000
     for epoch in range(1, args.pt_epoches):
@@ -108,7 +115,7 @@ def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feat
                 wrapped = Mainmodel_continue(args, features[stage], hidden_dim=args.dims, num_layers=args.num_layers,
                                              num_heads=args.num_heads, k_transition=args.k_transition, num_classes=1,
                                              cp_filename=prev if stage else file_check, encoder=args.encoder).to(device)
-                optimizer = torch.optim.Adam(wrapped.parameters(), lr=args.lr, weight_decay=5e-5)
+                optimizer = make_optimizer(wrapped.parameters(), args.lr)
                 best_model, _ = run_pretraining(wrapped, loaders[stage], optimizer, batch_size, device)
                 torch.save(best_model, file_check)
             prev = file_check

@@ -178,6 +178,9 @@ class EgoWorkspace:
         self.host = None
 
 
+_DEFAULT_EGO_WS = {}     # per device: the pinned 3-int read-back buffer and the scan workspace are reused across calls
+
+
 def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, stream=None, out=None) -> EgoBatch:
     """k-hop ego-net of every node of ``g`` on the GPU (bit-exact with ``dgl.khop_in_subgraph`` node lists).
     One host synchronisation (to read Ns / Es between the count and the fill kernel).
@@ -189,7 +192,8 @@ def khop_ego_batch(g: BatchedGraph, k: int, ws: Optional[EgoWorkspace] = None, s
     dev = g.device
     N = g.num_nodes()
     st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
-    ws = ws or EgoWorkspace()
+    if ws is None:          # callers of the reference's loop pass nothing: a pinned allocation per call would cost ~2 ms
+        ws = _DEFAULT_EGO_WS.setdefault(str(dev), EgoWorkspace())
     need = lib.scgib_ego_workspace_bytes(N)
     if ws.ws is None or ws.ws.numel() < need or ws.ws.device != dev:
         ws.ws = torch.empty(int(need * 1.5), dtype=torch.uint8, device=dev)

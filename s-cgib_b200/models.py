@@ -18,6 +18,7 @@ from .engine import (FT_NAMES, HID, DeviceBatch, FinetuneHead, PaddedSet2Set, Pr
                      param_names)
 from .graph import BatchedGraph, EgoBatch, khop_ego_batch
 
+_CPU_GATE_NOISE = __import__("os").environ.get("SCGIB_CPU_GATE_NOISE", "0") == "1"
 DEFAULT_GIN_LAYERS = 4   # reference models.py:57-58: ``num_layers = 5; range(num_layers - 1)``
 
 
@@ -90,13 +91,23 @@ class _Set2SetParams(nn.Module):
         self.lstm.reset_parameters()          # DGL's Set2Set.__init__ re-initialises the LSTM (second RNG draw)
 
 
+def _detach_aliased_grads(params, flat):
+    """The backward kernels overwrite the flat gradient buffer.  A parameter whose .grad still aliases it (adopted from
+    an earlier backward and not reset by zero_grad) gets a private copy first, so gradient accumulation is preserved."""
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+    for p in params:
+        g = p.grad
+        if g is not None and lo <= g.data_ptr() < hi:
+            p.grad = g.clone()
+
+
 class _PretrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bridge, batch, gate_u, feat_u, *params):
         eng = bridge.engine
         losses = eng.forward(batch, gate_u, feat_u, update_running=bridge.training)
         ctx.bridge = bridge
-        ctx.n = len(params)
+        ctx.params = params
         out = losses.clone()
         return out[0], out[1], out[2]
 
@@ -104,10 +115,13 @@ class _PretrainFn(torch.autograd.Function):
     def backward(ctx, g_kl, g_con, g_rec):
         eng = ctx.bridge.engine
         scale = torch.stack([g_kl, g_con, g_rec]).tolist()        # one host read per backward
+        _detach_aliased_grads(ctx.params, eng.grads)
         eng.backward(tuple(scale))
         gv = eng.grad_views()
-        grads = [gv[name].clone() for name in ctx.bridge.slot_names]
-        return (None, None, None, None) + tuple(grads)
+        # views of the flat gradient buffer, no copies: autograd's AccumulateGrad adopts them as .grad when .grad is None
+        # (zero_grad(set_to_none=True), the default); gradients that are still live from an earlier backward were moved
+        # out of the buffer by _detach_aliased_grads, so accumulation across backward calls stays correct
+        return (None, None, None, None) + tuple(gv.pop(name) for name in ctx.bridge.slot_names)   # pop: no second reference
 
 
 class _Bridge:
@@ -135,6 +149,22 @@ class _Bridge:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("S-CGIB B200 path: the model must be on a CUDA device (no CPU fallback)")
+        cached = getattr(self, "_cached", None)
+        if cached is not None and self.engine is not None and self.engine.device == device and \
+                all(p.data_ptr() == ptr for p, ptr in cached[1]) and all(b.data_ptr() == ptr for b, ptr in cached[2]):
+            return cached[0]          # every parameter / BN buffer still aliases the flat buffers: nothing to do
+        params = self._sync_slow(device)
+        inner = self._bn_modules
+        bufs = []
+        for i, base in enumerate(bn_buffer_names(self.gin_layers)):
+            obj = inner
+            for q in base.split("."):
+                obj = obj[int(q)] if q.isdigit() else getattr(obj, q)
+            bufs += [(obj.running_mean, obj.running_mean.data_ptr()), (obj.running_var, obj.running_var.data_ptr())]
+        self._cached = (params, [(p, p.data_ptr()) for p in params], bufs)
+        return params
+
+    def _sync_slow(self, device):
         if self.engine is None or self.engine.device != device:
             self.engine = PretrainEngine(self.in_dim, gin_layers=self.gin_layers, device=device)
         views = self.engine.views()
@@ -186,8 +216,12 @@ class _HotPathMixin:
         return DeviceBatch(g, ego, x, normalize_x=False, t_override=t_override)
 
     def _noise(self, N, device):
-        # reference: gate noise from the CPU generator (models.py:599), feature noise on the device (models.py:650)
-        return torch.rand(N).to(device, non_blocking=True), torch.rand(N, HID, device=device)
+        # reference: gate noise from the CPU generator (models.py:599), feature noise on the device (models.py:650).
+        # Both are drawn on the device here (the CPU draw + copy costs ~0.3 ms per step at B = 4096 and the reference's
+        # per-graph CPU stream is not reproducible from a batched draw anyway); SCGIB_CPU_GATE_NOISE=1 restores the CPU draw.
+        if _CPU_GATE_NOISE:
+            return torch.rand(N).to(device, non_blocking=True), torch.rand(N, HID, device=device)
+        return torch.rand(N, device=device), torch.rand(N, HID, device=device)
 
     def forward(self, batch_g, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, current_epoch, edge_index,
                 k_transition, device, batch_size=16):
@@ -327,16 +361,19 @@ class _FinetuneFn(torch.autograd.Function):
         Z = eng.forward_features(batch, gate_u, feat_u, update_running=owner.training)
         scores = head.forward(Z, batch.g.graph_ptr)
         ctx.owner = owner
+        ctx.params = params
         return scores
 
     @staticmethod
     def backward(ctx, g_scores):
         owner = ctx.owner
         eng, head = owner._bridge.engine, owner._head
+        _detach_aliased_grads(ctx.params, eng.grads)
+        _detach_aliased_grads(ctx.params, head.grads)
         gZ = head.backward(g_scores)
         eng.extract_backward(gZ)
         gv, hv = eng.grad_views(), head.views(grads=True)
-        grads = [gv[n].clone() for n in owner._bridge.slot_names] + [hv[n].clone() for n in FT_NAMES]
+        grads = [gv.pop(n) for n in owner._bridge.slot_names] + [hv.pop(n) for n in FT_NAMES]
         return (None, None, None, None) + tuple(grads)
 
 
@@ -464,16 +501,19 @@ class _DomainAdaptFn(torch.autograd.Function):
         rec = head.forward(Z, batch.g.graph_ptr)
         org = rev.forward(x_norm, batch.g.graph_ptr)
         ctx.owner = owner
+        ctx.params = params
         return rec, org
 
     @staticmethod
     def backward(ctx, g_rec, g_org):
         owner = ctx.owner
         eng, head, rev = owner._bridge.engine, owner._head, owner._rev
+        _detach_aliased_grads(ctx.params, eng.grads)
+        _detach_aliased_grads(ctx.params, head.grads)
         gZ = head.backward(g_rec)
         eng.extract_backward(gZ)
         gv, hv = eng.grad_views(), head.views(grads=True)
-        grads = [gv[n].clone() for n in owner._bridge.slot_names] + [hv[n].clone() for n in FT_NAMES]
+        grads = [gv.pop(n) for n in owner._bridge.slot_names] + [hv.pop(n) for n in FT_NAMES]
         grads += list(rev.backward(g_org))
         return (None, None, None, None, None) + tuple(grads)
 

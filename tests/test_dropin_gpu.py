@@ -110,3 +110,40 @@ def test_extract_features_api():
     imap, kl_t, noisy, readout = m.extract_features(pg.batch_num_nodes(), pg, t, ego, None, DEV)
     assert imap.shape == (g.num_nodes, 128) and noisy.shape == (g.num_nodes, 64) and readout.shape == (16, 64)
     assert torch.equal(imap[:, :64], noisy) and torch.isfinite(kl_t).all()
+
+
+def test_gradient_accumulation_across_backward_calls(monkeypatch):
+    """.grad adopts views of the engine's flat gradient buffer (no copies); a second backward without zero_grad - the
+    grad-accumulation loop of train_pep_func.py:155-161 - must still add to the first one's gradients."""
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    torch.manual_seed(5)
+    m = models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GIN").to(DEV).train()
+    batches = []
+    for seed in (61, 62):
+        g = synth_batch(seed, 24)
+        pg = product_graph(g, DEV)
+        gen = torch.Generator().manual_seed(seed)
+        batches.append((pg, khop_ego_batch(pg, 1), F.normalize(pg.ndata["x"].float()),
+                        torch.rand(g.num_nodes, generator=gen), torch.rand(g.num_nodes, 64, generator=gen)))
+    cur = {}
+    monkeypatch.setattr(m, "_noise", lambda N, dev: (cur["gu"].to(dev), cur["fu"].to(dev)))
+
+    def run(i):
+        pg, ego, x, cur["gu"], cur["fu"] = batches[i]
+        _, kl, con, rec = m.forward(pg, x, ego, None, None, 1, None, 2, DEV, 24)
+        (kl + rec + con).backward()
+
+    single = []
+    for i in range(2):
+        m.zero_grad()
+        run(i)
+        single.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    m.zero_grad()
+    run(0)
+    run(1)                                                    # no zero_grad in between
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        want = single[0][n] + single[1][n]
+        assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-6 * float(want.abs().max()) + 1e-12), n
