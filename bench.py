@@ -460,7 +460,7 @@ def main():
         dm = dropin_models.Mainmodel(ns, 9, 64, 4, 4, args.k, "GIN").to(dev)
         dm.train()
         from exp_pretraining import make_optimizer
-        dopt = make_optimizer(dm.parameters(), 1e-4)          # torch.optim.Adam(lr, weight_decay=5e-5), as the reference
+        dopt = make_optimizer(dm, 1e-4)          # what the drop-in exp_pretraining.py builds: Adam(lr, wd 5e-5) as one flat kernel
 
         def step_dropin(steps):
             for i in range(steps):
@@ -562,7 +562,7 @@ def main():
             "e2e_dropin_module": None if ms_dropin is None else {
                 "value": graphs / (ms_dropin * 1e-3), "unit": UNIT, "ms_per_step": ms_dropin / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "note": "models.Mainmodel.forward + loss.backward() + torch.optim.Adam.step() + loss.item() per step, no "
+                "note": "models.Mainmodel.forward + loss.backward() + optimizer.step() (scgib_b200.optim.FlatAdam, as the drop-in exp_pretraining.py builds it) + loss.item() per step, no "
                         "prefetch: the reference's own training loop (exp_pretraining.py:300-324) on the drop-in classes"},
             "gpu_launches": (nlaunch + 5) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",

@@ -25,11 +25,14 @@ from scgib_b200.graph import BatchedGraph, khop_ego_batch
 from scgib_b200.synth import synth_batch
 
 
-def make_optimizer(params, lr):
-    """reference exp_pretraining.py:86,112: Adam(lr, weight_decay=5e-5) over the module parameters (views of the
-    engine's flat buffer).  torch's fused=True variant was measured slower here (2.94 vs 2.65 ms per step at B = 4096);
-    PretrainEngine.adam_step is the one-kernel alternative for loops written against the engine API."""
-    return torch.optim.Adam(list(params), lr=lr, weight_decay=5e-5)
+def make_optimizer(model, lr):
+    """reference exp_pretraining.py:86,112: Adam(lr, weight_decay=5e-5) over the model's parameters.  For the drop-in
+    modules this is scgib_b200.optim.FlatAdam: the same update as ONE kernel over the flat parameter buffer (same
+    zero_grad() / step() surface); SCGIB_TORCH_ADAM=1 keeps torch.optim.Adam on the parameter views."""
+    if hasattr(model, "_bridge") and os.environ.get("SCGIB_TORCH_ADAM", "0") != "1":
+        from scgib_b200.optim import FlatAdam
+        return FlatAdam(model, lr=lr, weight_decay=5e-5)
+    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=5e-5)
 
 
 def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
@@ -115,7 +118,7 @@ def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feat
                 wrapped = Mainmodel_continue(args, features[stage], hidden_dim=args.dims, num_layers=args.num_layers,
                                              num_heads=args.num_heads, k_transition=args.k_transition, num_classes=1,
                                              cp_filename=prev if stage else file_check, encoder=args.encoder).to(device)
-                optimizer = make_optimizer(wrapped.parameters(), args.lr)
+                optimizer = make_optimizer(wrapped, args.lr)
                 best_model, _ = run_pretraining(wrapped, loaders[stage], optimizer, batch_size, device)
                 torch.save(best_model, file_check)
             prev = file_check

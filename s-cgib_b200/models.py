@@ -114,9 +114,15 @@ class _PretrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_kl, g_con, g_rec):
         eng = ctx.bridge.engine
-        scale = torch.stack([g_kl, g_con, g_rec]).tolist()        # one host read per backward
         _detach_aliased_grads(ctx.params, eng.grads)
-        eng.backward(tuple(scale))
+        if g_kl.data_ptr() == g_con.data_ptr() == g_rec.data_ptr() and g_kl.numel() == 1:
+            # loss = KL + recon + contrastive (exp_pretraining.py:320): the three upstream gradients are one tensor.  Run the
+            # backward at scale 1 and multiply the flat gradient buffer by it on the device - no host read, no sync.
+            eng.backward((1.0, 1.0, 1.0))
+            eng.grads.mul_(g_kl.reshape(()).to(eng.grads.dtype))
+        else:
+            scale = torch.stack([g_kl, g_con, g_rec]).tolist()    # individually weighted losses: one host read
+            eng.backward(tuple(scale))
         gv = eng.grad_views()
         # views of the flat gradient buffer, no copies: autograd's AccumulateGrad adopts them as .grad when .grad is None
         # (zero_grad(set_to_none=True), the default); gradients that are still live from an earlier backward were moved

@@ -19,7 +19,8 @@ B, k = 4096, 1
 host = [synth_batch(i, B).pin_memory() for i in range(3)]
 ns = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device=str(dev), batch_size=B, k_transition=k)
 m = models.Mainmodel(ns, 9, 64, 4, 4, k, "GIN").to(dev).train()
-opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=5e-5)
+from exp_pretraining import make_optimizer
+opt = make_optimizer(m, 1e-4)
 acc = {}
 
 
@@ -53,3 +54,19 @@ for it in range(steps + 5):
     v = loss.detach().item()
     t = mark("item", t)
 print({k_: round(v_ / steps * 1e3, 3) for k_, v_ in acc.items()}, "ms per step; total", round(sum(acc.values()) / steps * 1e3, 3))
+# the same loop without the per-phase synchronisations
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for it in range(steps):
+    bg = host[it % 3].to(dev, non_blocking=True)
+    bx = bg.ndata["x"].float()
+    opt.zero_grad()
+    ego = khop_ego_batch(bg, k)
+    bx = F.normalize(bx)
+    _, kl, con, rec = m.forward(bg, bx, ego, None, None, 1, None, 2, dev, B)
+    loss = kl + rec + con
+    loss.backward()
+    opt.step()
+    v = loss.detach().item()
+torch.cuda.synchronize()
+print("unsynchronised loop: %.3f ms per step" % ((time.perf_counter() - t0) / steps * 1e3))

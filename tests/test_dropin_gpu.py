@@ -147,3 +147,36 @@ def test_gradient_accumulation_across_backward_calls(monkeypatch):
             continue
         want = single[0][n] + single[1][n]
         assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-6 * float(want.abs().max()) + 1e-12), n
+
+
+def test_flat_adam_matches_torch_adam(monkeypatch):
+    """scgib_b200.optim.FlatAdam (one kernel over the flat buffer) against torch.optim.Adam(lr, weight_decay=5e-5) on the
+    same module and the SAME gradients: one backward (two accumulated passes), then three optimiser steps without
+    recomputing the gradients (recomputing would compare two chaotic trajectories: Adam turns the rounding-noise
+    gradients of dead ReLU units into +-lr steps)."""
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    from scgib_b200.optim import FlatAdam
+    g = synth_batch(71, 32)
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, 1)
+    x = F.normalize(pg.ndata["x"].float())
+    gen = torch.Generator().manual_seed(71)
+    gu, fu = torch.rand(g.num_nodes, generator=gen), torch.rand(g.num_nodes, 64, generator=gen)
+    finals = []
+    for kind in ("torch", "flat"):
+        torch.manual_seed(9)
+        m = models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GIN").to(DEV).train()
+        monkeypatch.setattr(m, "_noise", lambda N, dev: (gu.to(dev), fu.to(dev)))
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=5e-5) if kind == "torch" else \
+            FlatAdam(m, lr=1e-3, weight_decay=5e-5)
+        opt.zero_grad()
+        for _rep in range(2):                                   # accumulated gradient (private copies, see FlatAdam.step)
+            _, kl, con, rec = m.forward(pg, x, ego, None, None, 1, None, 2, DEV, 32)
+            (kl + rec + con).backward()
+        for _step in range(3):
+            opt.step()
+        finals.append({n: p.detach().clone() for n, p in m.named_parameters()})
+    for n in finals[0]:
+        d = (finals[1][n] - finals[0][n]).abs()
+        assert float(d.max()) <= 2e-6, (n, float(d.max()))       # 0.2 % of one step (lr = 1e-3), three steps taken
