@@ -331,6 +331,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
                     help="pretrain = the headline metric (default); finetune = Mainmodel_finetuning step (1 GPU)")
+    ap.add_argument("--recons_type", default="adj", choices=["adj", "logM"],
+                    help="adj = the reference default (the headline); logM = k-step log transition matrices (models.py:770-782)")
     ap.add_argument("--shape", default="pcqm", choices=["pcqm", "peptides"], help="synthetic molecule shape (finetune workload)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
@@ -372,6 +374,8 @@ def main():
     lib = _lib.load()
     eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)     # same seed on every rank: replicas start equal
     eng._noise_gen.manual_seed(1234 + rank)
+    if args.recons_type == "logM":
+        eng.recon_logm_steps = args.k
     fused_dp = world > 1 and os.environ.get("SCGIB_DP", "peer") == "peer"
     if fused_dp:
         eng.enable_peer_allreduce()      # gradient all-reduce fused with Adam over NVLink peer memory (no NCCL per step)
@@ -454,7 +458,7 @@ def main():
         import torch.nn.functional as F
         import models as dropin_models
         from scgib_b200.graph import khop_ego_batch
-        ns = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device=str(dev),
+        ns = types.SimpleNamespace(recons_type=args.recons_type, useAtt=1, readout_f="sum", d_transfer=32, device=str(dev),
                                    batch_size=args.batch, k_transition=args.k)
         torch.manual_seed(0)
         dm = dropin_models.Mainmodel(ns, 9, 64, 4, 4, args.k, "GIN").to(dev)
@@ -548,7 +552,7 @@ def main():
             "config": {"workload": "S-CGIB pre-training step (ego extraction + fwd + bwd + grad all-reduce + Adam), GIN-4x64, "
                                    "k_transition=%d, batch %d synthetic PCQM4Mv2-shape graphs per GPU (BASELINE configs[1])" % (args.k, args.batch),
                        "graphs_per_gpu": args.batch, "nodes": b.N, "edges": b.E, "ego_rows": b.Ns, "ego_edges": b.Es,
-                       "parallelism": "dp%d" % world,
+                       "parallelism": "dp%d" % world, "recons_type": args.recons_type,
                        "grad_exchange": ("fused peer-memory all-reduce + Adam kernel" if fused_dp else "NCCL all-reduce + Adam") if world > 1 else "none",
                        "l2": "no flush: per-step working set (workspace %.2f GB, 4 rotating batches) exceeds the 126 MB L2" % (eng._ws.numel() / 1e9)},
             "clocks": clocks,

@@ -246,7 +246,7 @@ class OracleMainmodel(nn.Module):
         return interaction_map, KL_tensor, noisy, graph_features_readout
 
     def forward_faithful(self, g: TGraph, x_norm, eg: TGraph, x_subs_norm, gate_u=None, feat_u=None,
-                         batch_size=None):
+                         batch_size=None, recon_logm_steps=0):
         """models.py:662-700 / 1158-1195.  x_norm / x_subs_norm are the F.normalize'd raw features
         (exp_pretraining.py:312-314).  Returns dict with the three losses and the embeddings."""
         batch_x = self.transfer_d(x_norm)
@@ -257,7 +257,7 @@ class OracleMainmodel(nn.Module):
         noisy2 = sum_nodes(g, noisy)
         bs = batch_size if batch_size is not None else noisy2.shape[0]
         con = self.batched_semi_loss(noisy2, g_readout, bs)
-        rec = self.loss_recon_adj(Z, g)
+        rec = loss_recon_logm(Z, g, recon_logm_steps) if recon_logm_steps else self.loss_recon_adj(Z, g)
         return dict(KL=KL_loss, contrastive=con, recon=rec, interaction_map=imap, Z=Z, noisy=noisy,
                     graph_readout=g_readout, core_readout=noisy2)
 
@@ -466,3 +466,46 @@ class OracleDomainAdapt(nn.Module):
         rec = self.r_transfer_d(self.s2s(g, Z))
         org = self.s2s_rev(g, x_norm)
         return dict(X_loss=torch.sum((rec - org) ** 2), rec=rec, org=org, Z=Z)
+
+
+# --------------------------------------------------------------------------------------
+# --recons_type logM
+# --------------------------------------------------------------------------------------
+def get_prob_tran_mat(Ak: np.ndarray) -> np.ndarray:
+    """util.py:60-71 (GetProbTranMat): log(Ak / colsum) - log(1/n), negatives / -inf / nan -> 0."""
+    n = Ak.shape[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        col = np.repeat(np.sum(Ak, axis=0).reshape(1, -1), n, axis=0)
+        m = np.log(np.divide(Ak, col)) - np.log(1.0 / n)
+    m[m < 0] = 0
+    m[np.isnan(m)] = 0
+    return m
+
+
+def get_logm(dense_adj: np.ndarray, kstep: int):
+    """util.py:74-91 (getM_logM): Ak = Adj^i for i = 1..kstep (fp64), logM_i = GetProbTranMat(Ak)."""
+    n = dense_adj.shape[0]
+    Ak = np.identity(n)
+    out = []
+    for _ in range(kstep):
+        Ak = Ak @ dense_adj.astype(np.float64)
+        out.append(get_prob_tran_mat(Ak.copy()))
+    return out
+
+
+def loss_recon_logm(Z: torch.Tensor, g: TGraph, k: int) -> torch.Tensor:
+    """models.py:770-782 (loss_recon): per graph h = Z_g Z_g^T, sum_i sum((h - logM_i)^2) / n^2, all divided by k.
+    The logM matrices are what exp_pretraining.py:260-264 stores offline (float32 tensors)."""
+    ptr = g.seg_ptr.tolist()
+    loss = 0
+    for b in range(len(ptr) - 1):
+        v0, v1 = ptr[b], ptr[b + 1]
+        n = v1 - v0
+        A = np.zeros((n, n))
+        sel = (g.dst >= v0) & (g.dst < v1)
+        A[(g.src[sel] - v0).numpy(), (g.dst[sel] - v0).numpy()] = 1.0
+        logm = [torch.from_numpy(np.asarray(m)).float().to(Z.dtype) for m in get_logm(A, k)]
+        h = Z[v0:v1] @ Z[v0:v1].t()
+        for i in range(k):
+            loss = loss + torch.sum((h - logm[i]) ** 2) / (n * n)
+    return loss / k

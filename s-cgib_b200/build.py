@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libscgib.so")
-SOURCES = ["api.cu", "graph_kernels.cu", "gin_kernels.cu", "head_kernels.cu", "loss_kernels.cu", "finetune_kernels.cu", "peer_kernels.cu", "umma_test.cu", "gin_tc.cu", "gin_tc2.cu", "gin_tc3.cu", "gin_bwd_tc.cu", "gin_bwd_tc2.cu", "contrastive_tc.cu", "umma_probe2.cu"]
+SOURCES = ["api.cu", "graph_kernels.cu", "gin_kernels.cu", "head_kernels.cu", "loss_kernels.cu", "finetune_kernels.cu", "logm_kernels.cu", "peer_kernels.cu", "umma_test.cu", "gin_tc.cu", "gin_tc2.cu", "gin_tc3.cu", "gin_bwd_tc.cu", "gin_bwd_tc2.cu", "contrastive_tc.cu", "umma_probe2.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "umma.cuh", os.path.join("..", "..", "include", "scgib.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

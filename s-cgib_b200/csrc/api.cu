@@ -138,6 +138,7 @@ struct Ws {
   float *rpart, *G, *edge;
   float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout, *zsplit;
   float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o[2], *Ga[2], *ga0[2];
+  float *logm_walks, *logm_gram, *logm_pair, *logm_loss;     // --recons_type logM (logm_kernels.cu)
   float *aC, *head_w1a, *head_w1b, *head_bn, *head_cvec;     // tensor-core head backward (the GIN backward kernel on two K halves)
   float* ppart;
   size_t bytes;
@@ -197,6 +198,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.Ga[0] = take((size_t)N * HID); w.Ga[1] = take((size_t)Ns * HID);
   (void)Vmax;
   w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
+  w.logm_walks = take((size_t)logm_max_steps() * N); w.logm_gram = take(B); w.logm_pair = take(N); w.logm_loss = take(4);
   w.aC = take((size_t)N * HID); w.head_w1a = take(HID * HID); w.head_w1b = take(HID * HID);
   w.head_bn = take(4 * HID); w.head_cvec = take(2 * HID);
   w.ppart = take((size_t)num_sms() * lo.total);
@@ -213,6 +215,7 @@ static int check_batch(const ScgibBatch* b) {
     return SCGIB_E_NULL;
   if ((b->E > 0 && !b->indices) || (b->Es > 0 && !b->sub_indices)) return SCGIB_E_NULL;
   if (((uintptr_t)b->feat_u & 15u) != 0) return SCGIB_E_ALIGN;
+  if (b->recon_logm_steps < 0 || b->recon_logm_steps > logm_max_steps()) return SCGIB_E_RANGE;
   return SCGIB_OK;
 }
 
@@ -350,7 +353,11 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
                   params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.aC, w.r_head, w.Z};
     PROF("head_fwd", launch_head_fwd(a, s));
   }
-  if (!features_only) {
+  const int logm = b->recon_logm_steps;
+  if (!features_only && logm > 0) {
+    PROF("logm_fwd", launch_logm_fwd(w.Z, b->graph_ptr, b->indptr, b->indices, b->B, b->N, logm, w.logm_walks, w.logm_gram,
+                                     w.logm_pair, w.logm_loss, (int32_t*)(w.counters + 32), s));
+  } else if (!features_only) {
     const int grid = num_sms();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
     PROF("recon_fwd", launch_recon_fwd(a, grid, s));
@@ -367,7 +374,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
   }
   if (!features_only) {
-    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, w.kl, w.D, losses};
+    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses};
     PROF("loss_finalize", launch_loss_finalize(a, s));
   }
   if (Z) cudaMemcpyAsync(Z, w.Z, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -424,8 +431,13 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, s));
     ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
     PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, s));
-    ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
-    PROF("recon_bwd", launch_recon_bwd(ra, s));
+    if (b->recon_logm_steps > 0) {
+      PROF("logm_bwd", launch_logm_bwd(w.Z, b->graph_ptr, b->indptr, b->indices, b->B, b->N, b->recon_logm_steps, w.logm_walks,
+                                       s_rec, w.gZ, (int32_t*)(w.counters + 32), s));
+    } else {
+      ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+      PROF("recon_bwd", launch_recon_bwd(ra, s));
+    }
   }
   // head MLP backward.  Tensor-core path: Z = W2 relu(W1a noisy + W1b (alpha C) + b1) + b2 is the GIN MLP with its first
   // layer split over two K = 64 inputs, so its backward is the GIN backward kernel run on both halves in ONE launch

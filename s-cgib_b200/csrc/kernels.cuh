@@ -235,7 +235,8 @@ int contrastive_jsplit(int B);
 
 struct LossFinalizeArgs {
   const float* rowsum; int jsplit; const float* diag; int B;   // contrastive
-  const float* G; const float* edge_sum; int N; int E;          // recon
+  const float* G; const float* edge_sum; int N; int E;          // recon (adjacency)
+  const float* recon_override;                                  // non-null: the recon loss was computed elsewhere (logM)
   const float* kl;
   float* D;                                                      // [B] contrastive denominators (saved)
   float* losses;                                                 // {KL, contrastive, recon, total}
@@ -278,5 +279,14 @@ int atb_splits(int R);
 void launch_atb(const float* A, int lda, const float* Bm, int ldb, float* out, int ldo, float* out2, int R, int M, int Nn,
                 float* scratch, cudaStream_t s);
 int finetune_max_classes();
+
+// ---------------------------------------------------------------- logm_kernels.cu
+// `--recons_type logM` (models.py:770-782 with util.py:60-91): per-graph Gram term + sparse k-hop pair term, no dense n x n.
+// walks [k][N], gram [B], pair [N] are workspace; loss_out[0] = the loss; bwd OVERWRITES gZ with scale * d loss / d Z.
+int logm_max_steps();
+void launch_logm_fwd(const float* Z, const int32_t* graph_ptr, const int32_t* indptr, const int32_t* indices, int B, int N,
+                     int k, float* walks, float* gram, float* pair, float* loss_out, int32_t* status, cudaStream_t s);
+void launch_logm_bwd(const float* Z, const int32_t* graph_ptr, const int32_t* indptr, const int32_t* indices, int B, int N,
+                     int k, const float* walks, float scale, float* gZ, int32_t* status, cudaStream_t s);
 
 }  // namespace scgib

@@ -367,7 +367,8 @@ loss_finalize_kernel(LossFinalizeArgs p) {
     p.D[i] = d;
     con += (double)(logf(d) - p.diag[i]);      // -log(exp(s_b(i,i)) / D_i)
   }
-  for (int j = threadIdx.x; j < HID * HID; j += kThreads) { const double g = (double)p.G[j]; fro += g * g; }
+  if (!p.recon_override)
+    for (int j = threadIdx.x; j < HID * HID; j += kThreads) { const double g = (double)p.G[j]; fro += g * g; }
   s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
   __syncthreads();
   for (int o = kThreads / 2; o > 0; o >>= 1) {
@@ -377,7 +378,8 @@ loss_finalize_kernel(LossFinalizeArgs p) {
   if (threadIdx.x == 0) {
     const float kl = p.kl[0];
     const float c = (float)(s_a[0] / (double)p.B);
-    const float r = (float)((s_b[0] - 2.0 * (double)p.edge_sum[0] + (double)p.E) / (double)p.N);
+    const float r = p.recon_override ? p.recon_override[0]
+                                     : (float)((s_b[0] - 2.0 * (double)p.edge_sum[0] + (double)p.E) / (double)p.N);
     p.losses[0] = kl; p.losses[1] = c; p.losses[2] = r; p.losses[3] = kl + r + c;
   }
 }

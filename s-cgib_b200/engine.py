@@ -59,6 +59,7 @@ class DeviceBatch:
     def __init__(self, g: BatchedGraph, ego: EgoBatch, x: torch.Tensor, normalize_x: bool = True, t_override=None):
         self.g, self.ego, self.x, self.normalize_x = g, ego, (None if x is None else x.contiguous()), normalize_x
         self.t_override = None if t_override is None else t_override.contiguous().float()
+        self.recon_logm_steps = 0        # k >= 1: --recons_type logM with k-step matrices (models.py:770-782)
         self.B, self.N, self.E = g.batch_size, g.num_nodes(), g.num_edges()
         self.Ns, self.Es = ego.num_nodes(), ego.num_edges()
 
@@ -72,6 +73,7 @@ class DeviceBatch:
         b.x, b.normalize_x = (self.x.data_ptr() if self.x is not None else None), int(self.normalize_x)
         b.t_override = None if self.t_override is None else self.t_override.data_ptr()
         b.gate_u, b.feat_u = gate_u.data_ptr(), feat_u.data_ptr()
+        b.recon_logm_steps = int(self.recon_logm_steps)
         return b
 
     def algorithmic_bytes(self, gin_layers=4, F=9, s=4):
@@ -120,6 +122,7 @@ class PretrainEngine:
         self._ws = None
         self._loss_scale = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
         self.ego_ws = EgoWorkspace()
+        self.recon_logm_steps = 0        # k >= 1: batches made by this engine use --recons_type logM with k-step matrices
         self._noise_gen = torch.Generator(device=self.device)
         if seed is not None:
             self._noise_gen.manual_seed(seed)
@@ -177,7 +180,9 @@ class PretrainEngine:
         if g.device != self.device:
             g = g.to(self.device, non_blocking=True)
         ego = khop_ego_batch(g, k, self.ego_ws)
-        return DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+        b = DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+        b.recon_logm_steps = self.recon_logm_steps
+        return b
 
     def prefetch_batch(self, g: BatchedGraph, k: int = 1, normalize_x: bool = True, slots: int = 3):
         """Data-loader style pipelining: H2D (if ``g`` is a pinned host batch) and k-hop ego-net extraction of the
@@ -209,6 +214,7 @@ class PretrainEngine:
                 g = gd
             ego = khop_ego_batch(g, k, self.ego_ws, out=slot["bufs"])
             b = DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+            b.recon_logm_steps = self.recon_logm_steps
             b._slot = slot
             ev = torch.cuda.Event()
             ev.record(self._side)
@@ -229,6 +235,7 @@ class PretrainEngine:
             g = dataset.assemble(ids, out=slot["dev"])
             ego = khop_ego_batch(g, k, self.ego_ws, out=slot["bufs"])
             b = DeviceBatch(g, ego, g.ndata["x"], normalize_x)
+            b.recon_logm_steps = self.recon_logm_steps
             b._slot = slot
             ev = torch.cuda.Event()
             ev.record(self._side)

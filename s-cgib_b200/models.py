@@ -202,9 +202,9 @@ def _check_args(args, encoder):
     if encoder != "GIN":
         print("scgib_b200: only --encoder GIN is implemented on the B200 path (reference models.py:573-587)")
         raise SystemExit()
-    if getattr(args, "readout_f", "sum") != "sum" or getattr(args, "recons_type", "adj") != "adj" or \
+    if getattr(args, "readout_f", "sum") != "sum" or getattr(args, "recons_type", "adj") not in ("adj", "logM") or \
             not getattr(args, "useAtt", 1):
-        raise NotImplementedError("B200 path covers the reference defaults: --readout_f sum --recons_type adj --useAtt 1")
+        raise NotImplementedError("B200 path covers --readout_f sum --recons_type adj|logM --useAtt 1")
 
 
 class _HotPathMixin:
@@ -219,7 +219,10 @@ class _HotPathMixin:
             ego = ego.to(g.device)
         x = None if batch_x is None else batch_x.to(g.device).float()
         # exp_pretraining.py:312 already applied F.normalize to batch_x: use it as given
-        return DeviceBatch(g, ego, x, normalize_x=False, t_override=t_override)
+        b = DeviceBatch(g, ego, x, normalize_x=False, t_override=t_override)
+        if getattr(self, "recons_type", "adj") == "logM":      # models.py:693-694; the k-step matrices are computed on the GPU
+            b.recon_logm_steps = int(self.k_transition)
+        return b
 
     def _noise(self, N, device):
         # reference: gate noise from the CPU generator (models.py:599), feature noise on the device (models.py:650).

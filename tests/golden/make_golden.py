@@ -30,7 +30,7 @@ def load_reference_models(ref_root="/root/reference"):
     return importlib.import_module("models"), dgl_stub
 
 
-def make(seed, B, k, ref_models, dgl_stub, out_path):
+def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj"):
     g = synth_batch(seed, B)
     e = ego_batch_ref(g, k)
     s, d = g.edges()
@@ -41,18 +41,29 @@ def make(seed, B, k, ref_models, dgl_stub, out_path):
     eg = dgl_stub.StubGraph(e.ego_ptr, e.sub_indices, es_dst, e.num_rows)
     eg.ndata["x"] = torch.from_numpy(g.x[e.ego_nodes])
 
-    args = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
+    args = types.SimpleNamespace(recons_type=recons_type, useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
     torch.manual_seed(seed)
     model = ref_models.Mainmodel(args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
     model.train()
     state0 = {n: t.detach().clone() for n, t in model.state_dict().items()}
+    batch_logMs = None
+    if recons_type == "logM":
+        # exp_pretraining.py:260-264, 353-356: per graph, the reference's own util.getM_logM on the (stub) DGL graph
+        import util as ref_util
+        batch_logMs = []
+        for b in range(g.num_graphs):
+            v0, v1 = int(g.graph_ptr[b]), int(g.graph_ptr[b + 1])
+            sel = (d >= v0) & (d < v1)
+            one = dgl_stub.StubGraph(np.asarray([0, v1 - v0]), s[sel] - v0, d[sel] - v0, v1 - v0)
+            _, logM = ref_util.getM_logM(one, kstep=k)
+            batch_logMs.append(torch.from_numpy(np.array(logM)).float())
 
     # exp_pretraining.py:300-322
     batch_x = F.normalize(bg.ndata["x"].float())
     x_subs = F.normalize(eg.ndata["x"].float())
     noise_seed = 1000 + seed
     torch.manual_seed(noise_seed)
-    _, KL, con, rec = model.forward(bg, batch_x, eg, None, x_subs, 1, bg.edges(), 2, "cpu", B)
+    _, KL, con, rec = model.forward(bg, batch_x, eg, batch_logMs, x_subs, 1, bg.edges(), 2, "cpu", B)
     # re-run the two pieces the forward does not return (deterministic given the same RNG state)
     torch.manual_seed(noise_seed)
     imap, KLt, noisy, readout = model.extract_features(bg.batch_num_nodes(), bg,
@@ -63,7 +74,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path):
     model.load_state_dict(state0)
     model.zero_grad()
     torch.manual_seed(noise_seed)
-    _, KL2, con2, rec2 = model.forward(bg, batch_x, eg, None, x_subs, 1, bg.edges(), 2, "cpu", B)
+    _, KL2, con2, rec2 = model.forward(bg, batch_x, eg, batch_logMs, x_subs, 1, bg.edges(), 2, "cpu", B)
     assert torch.equal(KL, KL2) and torch.equal(con, con2) and torch.equal(rec, rec2)
     loss = KL2 + rec2 + con2
     loss.backward()
@@ -73,7 +84,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path):
     used = set(grads) | {n for n in state0 if "running" in n or "num_batches" in n or n.endswith(".eps")}
     fx = dict(
         meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, reference="models.py Mainmodel (unmodified) on dgl_stub",
-                  torch=torch.__version__),
+                  torch=torch.__version__, recons_type=recons_type),
         graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
         ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
         state={n: t for n, t in state0.items() if n in used},
@@ -209,6 +220,8 @@ if __name__ == "__main__":
     make(0, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k1_b6.pt"))
     make(1, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k2_b4.pt"))
     make(2, 3, 3, ref_models, dgl_stub, os.path.join(HERE, "pretrain_k3_b3.pt"))
+    make(6, 5, 2, ref_models, dgl_stub, os.path.join(HERE, "logm_k2_b5.pt"), recons_type="logM")
+    make(7, 4, 3, ref_models, dgl_stub, os.path.join(HERE, "logm_k3_b4.pt"), recons_type="logM")
     make_finetune(3, 5, 1, ref_models, dgl_stub, os.path.join(HERE, "finetune_k1_b5.pt"))
     make_finetune(4, 11, 2, ref_models, dgl_stub, os.path.join(HERE, "finetune_k2_b11.pt"))
     make_domainadapt(5, 7, 1, ref_models, dgl_stub, os.path.join(HERE, "domainadapt_k1_b7.pt"))

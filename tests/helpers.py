@@ -41,14 +41,18 @@ def oracle_grads(m, out):
     return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
 
 
-def fp64_truth(m, g, e, gate_u, feat_u):
+def fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=0):
     """fp64 vectorised oracle (forward + all parameter gradients) with the weights of ``m``: the ground truth
     both the fp32 reference run and the fp32 CUDA path are measured against."""
     m64 = OracleMainmodel(m.transfer_d.in_features, 64, 32, len(m.Encoder1.ginlayers)).double()
     m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
     x = normalize_rows(torch.from_numpy(g.x).double())
     en = torch.from_numpy(e.ego_nodes.astype(np.int64))
-    out = m64.forward_vectorised(tgraph_from_ref(g), x, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())
+    if recon_logm_steps:      # --recons_type logM: only the faithful flavour restates it
+        out = m64.forward_faithful(tgraph_from_ref(g), x, tgraph_from_ego(e), x[en], gate_u.double(), feat_u.double(),
+                                   recon_logm_steps=recon_logm_steps)
+    else:
+        out = m64.forward_vectorised(tgraph_from_ref(g), x, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())
     return out, oracle_grads(m64, out)
 
 

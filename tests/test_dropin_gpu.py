@@ -180,3 +180,28 @@ def test_flat_adam_matches_torch_adam(monkeypatch):
     for n in finals[0]:
         d = (finals[1][n] - finals[0][n]).abs()
         assert float(d.max()) <= 2e-6, (n, float(d.max()))       # 0.2 % of one step (lr = 1e-3), three steps taken
+
+
+def test_mainmodel_recons_type_logm(monkeypatch):
+    """--recons_type logM through the drop-in class: reconstruction_loss = loss_recon with k = k_transition step matrices
+    computed on the GPU (the reference reads them from pts/*_M_khop_k.pt)."""
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    k = 2
+    g = synth_batch(81, 40)
+    e = ego_batch_ref(g, k)
+    torch.manual_seed(81)
+    ref = OracleMainmodel(9)
+    torch.manual_seed(81)
+    m = models.Mainmodel(_args(recons_type="logM", k_transition=k), 9, 64, 4, 4, k, "GIN").to(DEV).train()
+    pg = product_graph(g, DEV)
+    ego = khop_ego_batch(pg, k)
+    x = F.normalize(pg.ndata["x"].float())
+    gate_u, feat_u = torch.rand(g.num_nodes), torch.rand(g.num_nodes, 64)
+    monkeypatch.setattr(m, "_noise", lambda N, dev: (gate_u.to(dev), feat_u.to(dev)))
+    _, kl, con, rec = m.forward(pg, x, ego, None, None, 1, None, 2, DEV, 40)
+    xr = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    out = ref.forward_faithful(tgraph_from_ref(g), xr, tgraph_from_ego(e), xr[en], gate_u, feat_u, recon_logm_steps=k)
+    for name, got in (("KL", kl), ("contrastive", con), ("recon", rec)):
+        assert abs(float(got) - float(out[name])) <= 1e-5 * abs(float(out[name])), name

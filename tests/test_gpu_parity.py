@@ -24,7 +24,8 @@ from tests.helpers import (GRAD_TOL_MAX, GRAD_TOL_MEDIAN, check_against_truth, e
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pretrain_*.pt")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pretrain_*.pt")) +
+              glob.glob(os.path.join(os.path.dirname(__file__), "golden", "logm_*.pt")))     # logm_*: --recons_type logM
 FWD_TOL = 1e-5
 
 
@@ -110,13 +111,14 @@ def test_gin_layer_forward(kin):
     assert rel(a, h + neigh) <= 2e-6
 
 
-def _run_engine(m, g, e, k, gate_u, feat_u, from_gpu_ego=True):
+def _run_engine(m, g, e, k, gate_u, feat_u, from_gpu_ego=True, recon_logm_steps=0):
     from scgib_b200.engine import DeviceBatch
     from scgib_b200.graph import khop_ego_batch
     eng = engine_from_oracle(m, DEV)
     pg = product_graph(g, DEV)
     ego = khop_ego_batch(pg, k) if from_gpu_ego else product_ego_from_ref(pg, e, k, DEV)
     b = DeviceBatch(pg, ego, pg.ndata["x"], normalize_x=True)
+    b.recon_logm_steps = recon_logm_steps
     losses, emb = eng.forward(b, gate_u.to(DEV), feat_u.to(DEV), want=True)
     eng.backward()
     torch.cuda.synchronize()
@@ -133,8 +135,9 @@ def test_golden_reference_parity(path):
     m = OracleMainmodel(9, 64, 32, 4)
     m.load_state_dict(fx["state"], strict=False)
     gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
-    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
-    truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
+    logm = k if fx["meta"].get("recons_type", "adj") == "logM" else 0
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u, recon_logm_steps=logm)
+    truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=logm)
     check_against_truth(eng, losses, emb, fx["out"], fx["grads"], truth_out, truth_grads)
     # direct comparison with the recorded reference numbers as well (these batches are tiny: fp32 noise is small)
     for i, name in enumerate(("KL", "contrastive", "recon")):
@@ -337,3 +340,22 @@ def test_single_graph_batch():
         assert abs(float(losses[i]) - float(out[name])) <= 1e-5 * abs(float(out[name])), name
     for name in ("interaction_map", "Z", "noisy", "graph_readout"):
         assert rel(emb[name].cpu(), out[name].detach()) <= 1e-5, name
+
+
+@pytest.mark.parametrize("seed,B,k,shape", [(41, 96, 1, "pcqm"), (42, 64, 2, "pcqm"), (43, 48, 3, "pcqm"), (44, 4, 2, "peptides")])
+def test_logm_reconstruction_vs_faithful_oracle(seed, B, k, shape):
+    """--recons_type logM (models.py:770-782 + util.py:60-91): the sparse Gram/pair formulation on the GPU against the
+    dense per-graph loop of the oracle, forward and gradients."""
+    g = synth_batch(seed, B, shape)
+    e = ego_batch_ref(g, k)
+    torch.manual_seed(seed)
+    m = OracleMainmodel(9)
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, seed + 100)
+    out = m.forward_faithful(tgraph_from_ref(g), x, tgraph_from_ego(e), x[en], gate_u, feat_u, recon_logm_steps=k)
+    ref_grads = oracle_grads(m, out)
+    m.zero_grad()
+    eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u, recon_logm_steps=k)
+    truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=k)
+    check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
