@@ -106,6 +106,9 @@ typedef struct ScgibBatch {
   const float* feat_u;         /* [N,H] U[0,1) feature noise    (rand_like,   models.py:650)    */
   const float* t_override;     /* optional [N,DT]: already-transferred features (the batch_x argument of
                                   extract_features, models.py:702); x / transfer_d are then not used (forward only) */
+  int32_t eval_mode;           /* 1: model.eval() - every BatchNorm (GIN layers, compressor) normalises with the running
+                                  statistics in `bn_running` (required, not updated); forward only (evaluate_network,
+                                  train_pep_func.py:187-230).  0: training mode (batch statistics) */
   int32_t recon_logm_steps;    /* 0: recons_type 'adj' (models.py:762-768, the default).  k >= 1: recons_type 'logM'
                                   (models.py:770-782) with the k-step log transition matrices of util.py:60-91 computed
                                   on the fly from the CSR (k = --k_transition, <= 8); no pts/*_M_khop_k.pt files */

@@ -20,7 +20,7 @@ class Batch(ctypes.Structure):
                 ("ego_ptr", c_void_p), ("ego_nodes", c_void_p), ("ego_seed", c_void_p),
                 ("sub_indptr", c_void_p), ("sub_indices", c_void_p),
                 ("x", c_void_p), ("normalize_x", c_int32), ("gate_u", c_void_p), ("feat_u", c_void_p),
-                ("t_override", c_void_p), ("recon_logm_steps", c_int32)]
+                ("t_override", c_void_p), ("eval_mode", c_int32), ("recon_logm_steps", c_int32)]
 
 
 # slot enums of include/scgib.h

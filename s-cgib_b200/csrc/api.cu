@@ -274,6 +274,8 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
   const int L = d->gin_layers;
+  const bool eval = b->eval_mode != 0;       // model.eval(): BatchNorm layers use (and do not update) their running statistics
+  if (eval && !bn_running) return SCGIB_E_NULL;
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   // k-major weight copies for the forward GEMMs
@@ -314,7 +316,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       a.a_out = w.a[e][l]; a.r_out = w.r[e][l]; a.y_out = w.y[e][l];
       a.part = e == 0 ? w.small_part : w.small_part2; a.counter = w.counters + (e == 0 ? 0 : 8);
       a.bn_out = w.bn[e][l];
-      a.running = bn_running ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
+      a.running = (bn_running && !eval) ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
       a.reverse = (l & 1) && fwd_alternate();
     }
     const int kin = l == 0 ? DTR : HID, m = tensor_core_mode();
@@ -328,6 +330,10 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
         else PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
       }
     }
+    if (eval)
+      for (int e = 0; e < 2; ++e)
+        launch_bn_from_running(bn_running + (size_t)(e * L + l) * 2 * HID, params + lo.enc(e, l, L, SCGIB_ENC_GAMMA),
+                               params + lo.enc(e, l, L, SCGIB_ENC_BETA), w.bn[e][l], s);
   }
   {
     GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q};
@@ -344,9 +350,10 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     a.wc2 = params + lo.off[SCGIB_P_COMP_W2]; a.bc2 = params + lo.off[SCGIB_P_COMP_B2];
     a.gate_u = b->gate_u; a.feat_u = b->feat_u; a.logit = w.logit;
     a.noisy = w.noisy; a.lam = w.lam; a.alpha = w.alpha; a.readout = w.readout; a.core = w.core;
-    a.gstat = w.gstat; a.cstat = bn_running ? w.cstat : nullptr; a.kl = w.kl;
+    a.gstat = w.gstat; a.cstat = (bn_running && !eval) ? w.cstat : nullptr; a.kl = w.kl;
+    a.eval_running = eval ? bn_running + (size_t)2 * L * 2 * HID : nullptr;
     PROF("graph_gate_fwd", launch_graph_gate_fwd(a, s));
-    if (bn_running) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s));
+    if (bn_running && !eval) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s));
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
@@ -407,6 +414,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->t_override) return SCGIB_E_NULL;   // forward-only mode: no gradient path to transfer_d
+  if (b->eval_mode) return SCGIB_E_RANGE;   // the BatchNorm backward is the training-mode one (batch statistics)
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)params & 15u) != 0 || ((uintptr_t)grads & 15u) != 0) return SCGIB_E_ALIGN;
   const Layout lo = make_layout(d);
   const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);

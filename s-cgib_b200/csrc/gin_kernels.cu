@@ -47,6 +47,19 @@ void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int no
   input_proj_fwd_kernel<<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
 }
 
+__global__ void bn_from_running_kernel(const float* __restrict__ running, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ bn) {
+  const int c = threadIdx.x;
+  if (c >= HID) return;
+  bn[c] = running[c];
+  bn[HID + c] = 1.f / sqrtf(running[HID + c] + kBnEps);
+  bn[2 * HID + c] = gamma[c];
+  bn[3 * HID + c] = beta[c];
+}
+void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, cudaStream_t s) {
+  bn_from_running_kernel<<<1, HID, 0, s>>>(running, gamma, beta, bn);
+}
+
 // ------------------------------------------------------------------------------------------------
 // batched transposes of small weight matrices (forward kernels want k-major copies)
 // ------------------------------------------------------------------------------------------------

@@ -207,10 +207,16 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
       d = q.x - muQ.x; vQ.x = fmaf(d, d, vQ.x); d = q.y - muQ.y; vQ.y = fmaf(d, d, vQ.y);
     }
     const float2 sd = make_float2(sqrtf(vH.x / (n - 1.f)), sqrtf(vH.y / (n - 1.f)));         // torch.std_mean: unbiased
-    const float2 rstd = make_float2(1.f / sqrtf(vQ.x / n + kBnEps), 1.f / sqrtf(vQ.y / n + kBnEps));  // BN: biased
+    float2 rstd = make_float2(1.f / sqrtf(vQ.x / n + kBnEps), 1.f / sqrtf(vQ.y / n + kBnEps));  // BN: biased
+    float2 muQe = muQ;
+    if (p.eval_running) {       // model.eval(): nn.BatchNorm1d normalises with its running statistics
+      const float2 rm = ld2(p.eval_running + c), rv = ld2(p.eval_running + HID + c);
+      muQe = rm;
+      rstd = make_float2(1.f / sqrtf(rv.x + kBnEps), 1.f / sqrtf(rv.y + kBnEps));
+    }
     st2(p.readout + (size_t)g * HID + c, sH);
     float* gs = p.gstat + (size_t)g * 4 * HID;
-    st2(gs + c, muH); st2(gs + HID + c, sd); st2(gs + 2 * HID + c, muQ); st2(gs + 3 * HID + c, rstd);
+    st2(gs + c, muH); st2(gs + HID + c, sd); st2(gs + 2 * HID + c, muQe); st2(gs + 3 * HID + c, rstd);
     if (p.cstat) {
       st2(p.cstat + (size_t)g * 2 * HID + c, muQ);
       st2(p.cstat + (size_t)g * 2 * HID + HID + c, make_float2(vQ.x / (n - 1.f), vQ.y / (n - 1.f)));
@@ -231,7 +237,7 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const float ox = fmaf((q[i].x - muQ.x) * rstd.x, gam.x, bet.x), oy = fmaf((q[i].y - muQ.y) * rstd.y, gam.y, bet.y);
+        const float ox = fmaf((q[i].x - muQe.x) * rstd.x, gam.x, bet.x), oy = fmaf((q[i].y - muQe.y) * rstd.y, gam.y, bet.y);
         pv[i] = fmaxf(ox, 0.f) * w2.x + fmaxf(oy, 0.f) * w2.y;
       }
 #pragma unroll

@@ -11,6 +11,9 @@ struct TransposeJob { const float* src; float* dst; int rows, cols; };  // dst[c
 struct TransposeJobs { TransposeJob job[24]; int n; };
 void launch_transposes(const TransposeJobs& jobs, cudaStream_t s);
 
+// eval mode (model.eval()): bn = {running_mean, 1/sqrt(running_var + eps), gamma, beta} replaces the batch statistics a
+// GIN forward kernel has just written, before the next layer / the pooling kernels read them
+void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, cudaStream_t s);
 void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s);
 
 struct GinFwdArgs {
@@ -142,6 +145,8 @@ struct GraphGateFwdArgs {
   float* readout;                        // [B][HID]  R_g   (graph_features_readout)
   float* core;                           // [B][HID]  sum_v Z^c_v
   float* gstat;                          // [B][4][HID] mu_g, sigma_g, mu^c_g, rstd^c_g (saved)
+  const float* eval_running;             // optional {running_mean, running_var}[HID] of the compressor BatchNorm: eval mode
+                                         //  (normalise with the running statistics instead of the per-graph ones)
   float* cstat;                          // optional [B][2][HID] compressor-BN batch mean / unbiased var per graph
   float* kl;                             // [1] KL loss (last graph)
 };

@@ -60,6 +60,7 @@ class DeviceBatch:
         self.g, self.ego, self.x, self.normalize_x = g, ego, (None if x is None else x.contiguous()), normalize_x
         self.t_override = None if t_override is None else t_override.contiguous().float()
         self.recon_logm_steps = 0        # k >= 1: --recons_type logM with k-step matrices (models.py:770-782)
+        self.eval_mode = False           # model.eval(): BatchNorm layers use their running statistics (forward only)
         self.B, self.N, self.E = g.batch_size, g.num_nodes(), g.num_edges()
         self.Ns, self.Es = ego.num_nodes(), ego.num_edges()
 
@@ -74,6 +75,7 @@ class DeviceBatch:
         b.t_override = None if self.t_override is None else self.t_override.data_ptr()
         b.gate_u, b.feat_u = gate_u.data_ptr(), feat_u.data_ptr()
         b.recon_logm_steps = int(self.recon_logm_steps)
+        b.eval_mode = int(bool(self.eval_mode))
         return b
 
     def algorithmic_bytes(self, gin_layers=4, F=9, s=4):
@@ -287,12 +289,12 @@ class PretrainEngine:
         p = self.params if params is None else params
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_pretrain_forward_f32(
-            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if update_running else None,
+            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if (update_running or b.eval_mode) else None,
             ctypes.byref(cb), _lib.ptr(self.losses),
             _lib.ptr(emb["interaction_map"]) if want else None, _lib.ptr(emb["Z"]) if want else None,
             _lib.ptr(emb["noisy"]) if want else None, _lib.ptr(emb["graph_readout"]) if want else None,
             _lib.ptr(ws), ws.numel(), st), "pretrain_forward")
-        if update_running:
+        if update_running and not b.eval_mode:
             self.num_batches_tracked += 1
         return (self.losses, emb) if want else self.losses
 
@@ -323,9 +325,9 @@ class PretrainEngine:
         p = self.params if params is None else params
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_extract_forward_f32(
-            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if update_running else None,
+            ctypes.byref(self.dims), _lib.ptr(p), _lib.ptr(self.bn_running) if (update_running or b.eval_mode) else None,
             ctypes.byref(cb), _lib.ptr(imap), _lib.ptr(Z), None, None, _lib.ptr(ws), ws.numel(), st), "extract_forward")
-        if update_running:
+        if update_running and not b.eval_mode:
             self.num_batches_tracked += 1
         return (Z, imap) if want_imap else Z
 

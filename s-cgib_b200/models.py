@@ -220,6 +220,7 @@ class _HotPathMixin:
         x = None if batch_x is None else batch_x.to(g.device).float()
         # exp_pretraining.py:312 already applied F.normalize to batch_x: use it as given
         b = DeviceBatch(g, ego, x, normalize_x=False, t_override=t_override)
+        b.eval_mode = not self.training              # model.eval(): running statistics in every BatchNorm (forward only)
         if getattr(self, "recons_type", "adj") == "logM":      # models.py:693-694; the k-step matrices are computed on the GPU
             b.recon_logm_steps = int(self.k_transition)
         return b

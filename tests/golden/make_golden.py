@@ -141,6 +141,12 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     state1 = {n: t.detach().clone() for n, t in model.state_dict().items() if "running" in n or "num_batches" in n}
+    # evaluate_network (train_pep_func.py:187-230): model.eval() forward with the running statistics just updated
+    model.eval()
+    torch.manual_seed(noise_seed + 1)
+    with torch.no_grad():
+        scores_eval, _, _, _ = model.forward(bg, batch_x, eg, x_subs, 1, bg.edges(), 2, "cpu", B)
+    model.train()
     # tensors the forward reads: the outer transfer_d / MLP / s2s / predict and the loaded model's encoders, compressor
     # and attention layer (models.py:508-518); everything else is dead weight in the state dict
     used = set(grads) | {n for n in state0 if n.startswith("model.") and
@@ -152,7 +158,7 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
         ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
         state={n: t for n, t in state0.items() if n in used}, state_after={n: t for n, t in state1.items() if n in used},
         trainable=trainable, targets=targets,
-        out=dict(scores=scores.detach(), loss=loss.detach()),
+        out=dict(scores=scores.detach(), loss=loss.detach(), scores_eval=scores_eval.detach()),
         grads=grads,
     )
     torch.save(fx, out_path)

@@ -123,6 +123,14 @@ def test_mainmodel_finetuning_matches_reference_golden(path, tmp_path, monkeypat
         errs.append((rel(got[n], gref), n))
     errs.sort()
     assert errs[len(errs) // 2][0] <= 5e-5 and errs[-1][0] <= 5e-3, errs[-3:]
+    # evaluate_network (train_pep_func.py:187-230): model.eval() -> every BatchNorm uses its running statistics
+    m.eval()
+    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"] + 1)
+    monkeypatch.setattr(m, "_noise", lambda N, dev: (gu2.to(dev), fu2.to(dev)))
+    with torch.no_grad():
+        scores_eval, _, _, _ = m.forward(pg, x, ego, None, 1, None, 2, DEV, g.num_graphs)
+    assert rel(scores_eval.cpu(), fx["out"]["scores_eval"]) <= 1e-5
+    m.train()
     # BN running statistics of the loaded model are live buffers updated by the forward
     sd = m.state_dict()
     for n, t in fx["state_after"].items():

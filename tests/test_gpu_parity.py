@@ -359,3 +359,40 @@ def test_logm_reconstruction_vs_faithful_oracle(seed, B, k, shape):
     eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u, recon_logm_steps=k)
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=k)
     check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
+
+
+def test_eval_mode_uses_running_statistics():
+    """model.eval(): GIN BatchNorms and the compressor BatchNorm normalise with their running statistics.  Two training
+    forwards (to move the running statistics away from their initial values), then an eval forward, against the torch
+    oracle driven the same way."""
+    g = synth_batch(91, 80)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(91)
+    m = OracleMainmodel(9)
+    x = normalize_rows(torch.from_numpy(g.x))
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
+    from scgib_b200.engine import DeviceBatch
+    from scgib_b200.graph import khop_ego_batch
+    eng = engine_from_oracle(m, DEV)
+    pg = product_graph(g, DEV)
+    b = DeviceBatch(pg, khop_ego_batch(pg, 1), pg.ndata["x"], normalize_x=True)
+    m.train()
+    for step in range(2):
+        gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 500 + step)
+        m.forward_faithful(tg, x, te, x[en], gate_u, feat_u)
+        eng.forward(b, gate_u.to(DEV), feat_u.to(DEV))
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, 600)
+    m.eval()
+    with torch.no_grad():
+        out = m.forward_faithful(tg, x, te, x[en], gate_u, feat_u)
+    b.eval_mode = True
+    before = eng.bn_running.clone()
+    losses, emb = eng.forward(b, gate_u.to(DEV), feat_u.to(DEV), want=True, update_running=False)
+    assert torch.equal(before, eng.bn_running)                      # eval never updates the running statistics
+    for i, name in enumerate(("KL", "contrastive", "recon")):
+        assert abs(float(losses[i]) - float(out[name])) <= 2e-5 * abs(float(out[name])), (name, float(losses[i]), float(out[name]))
+    for name in ("interaction_map", "Z", "noisy", "graph_readout"):
+        assert rel(emb[name].cpu(), out[name]) <= 2e-5, (name, rel(emb[name].cpu(), out[name]))
+    with pytest.raises(RuntimeError):
+        eng.backward()                                              # the backward is the training-mode one

@@ -135,6 +135,13 @@ def test_finetune_oracle_matches_reference(path):
     assert abs(float(loss) - float(fx["out"]["loss"])) <= 2e-6 * abs(float(fx["out"]["loss"]))
     assert sorted(n for n, p in m.named_parameters() if p.requires_grad) == fx["trainable"]
     loss.backward()
+    # evaluate_network: model.eval() forward right after the training forward (running statistics updated once)
+    m.eval()
+    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"] + 1)
+    with torch.no_grad():
+        ev = m(tg, x, te, x[ego_nodes], gu2, fu2)
+    assert rel(ev["scores"], fx["out"]["scores_eval"]) <= 2e-6
+    m.train()
     grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
     assert set(grads) == set(fx["grads"])
     gmax = max(float(v.abs().max()) for v in fx["grads"].values())
