@@ -435,7 +435,10 @@ class Mainmodel_finetuning(nn.Module):
         self._bridge = _Bridge(self, in_dim, self.gin_layers)
         self._head = None
 
-    __getstate__ = Mainmodel.__getstate__
+    def __getstate__(self):
+        st = Mainmodel.__getstate__(self)
+        st["_head"] = None                      # engine objects (ctypes handles, device buffers) are rebuilt on demand
+        return st
 
     def __setstate__(self, st):
         Mainmodel.__setstate__(self, st)
@@ -576,7 +579,11 @@ class Mainmodel_domainadapt(nn.Module):
         self._head = None
         self._rev = None
 
-    __getstate__ = Mainmodel.__getstate__
+    def __getstate__(self):
+        st = Mainmodel.__getstate__(self)
+        st["_head"] = None
+        st["_rev"] = None
+        return st
 
     def __setstate__(self, st):
         Mainmodel.__setstate__(self, st)

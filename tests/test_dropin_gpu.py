@@ -205,3 +205,22 @@ def test_mainmodel_recons_type_logm(monkeypatch):
     out = ref.forward_faithful(tgraph_from_ref(g), xr, tgraph_from_ego(e), xr[en], gate_u, feat_u, recon_logm_steps=k)
     for name, got in (("KL", kl), ("contrastive", con), ("recon", rec)):
         assert abs(float(got) - float(out[name])) <= 1e-5 * abs(float(out[name])), name
+
+
+def test_exp_pep_func_cli_pretrain_adapt_finetune(tmp_path, monkeypatch):
+    """The fine-tuning CLI surface end to end (reference exp_pep_func_5.py): pre-train, domain-adapt, fine-tune with
+    evaluation (model.eval()) on synthetic Peptides-shape molecules; checkpoints use the reference's naming scheme."""
+    import exp_pep_func_5 as ep
+    monkeypatch.chdir(tmp_path)
+    out = str(tmp_path) + "/outputs/"
+    common = ["--device", DEV, "--batch_size", "16", "--synthetic", "48", "--output_path", out, "--num_layers", "4"]
+    ep.args = ep.build_parser().parse_args(common + ["--pretrained_mode", "1", "--pt_epoches", "2"])
+    ep.device = torch.device(DEV)
+    with pytest.raises(SystemExit):                               # the reference quits after the pre-training stage
+        ep.main()
+    assert os.listdir(tmp_path / "outputs") == ["Peptides-func_GIN_64_4_1.pt"]
+    ep.args = ep.build_parser().parse_args(common + ["--pretrained_ds", "Peptides-func", "--domain_adapt", "1",
+                                                     "--adapt_epoches", "2", "--ft_epoches", "3"])
+    metric = ep.main()
+    assert sorted(os.listdir(tmp_path / "outputs")) == ["Peptides-func_GIN_64_4_1.pt", "Peptides-func_GIN_64_4_1_Peptides-func.pt"]
+    assert metric == metric and 0.0 < metric < 10.0             # finite BCE-with-logits metric of the test split
