@@ -21,7 +21,7 @@ from torch.utils.data import DataLoader
 
 from molecules import MoleculeDataset
 from models import Mainmodel, Mainmodel_continue
-from scgib_b200.graph import BatchedGraph, khop_ego_batch
+from scgib_b200.graph import BatchedGraph, khop_ego_batch, load_shard
 from scgib_b200.synth import synth_batch
 
 
@@ -79,8 +79,7 @@ def load_graphdataset(dataset_name):
     path = "pts/%s_csr.pt" % dataset_name
     samples_all = []
     if os.path.exists(path):
-        shard = torch.load(path)
-        big = BatchedGraph(shard["graph_ptr"], shard["indptr"], shard["indices"], shard["x"])
+        big, _ = load_shard(path)             # written by scgib_b200.graph.pack_shard from PyG-style (edge_index, x, y)
     else:
         print("[I] %s not found: generating %d synthetic molecules of the %s shape" % (path, args.synthetic, dataset_name))
         big = synth_batch(hash(dataset_name) % 1000, args.synthetic)

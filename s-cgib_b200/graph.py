@@ -295,3 +295,30 @@ class DeviceDataset:
         g.graph_ptr, g.indptr, g.indices = graph_ptr[:B + 1], indptr[:N + 1], indices[:E]
         g.ndata = {"x": x[:N * self.F].view(N, self.F)}
         return g
+
+
+# --------------------------------------------------------------------------------------------------
+# On-disk format: one packed CSR shard per dataset (replaces pts/<name>.bin + pts/<name>_subgraphs_khop_<k>.pt +
+# pts/<name>_M_khop_<k>.pt of the reference, exp_pretraining.py:171-206, 285: ego-nets and log-transition matrices are
+# computed on the GPU per batch and never stored)
+# --------------------------------------------------------------------------------------------------
+def pack_shard(molecules, path: Optional[str] = None):
+    """``molecules``: iterable of (edge_index [2,E] as in a PyG ``Data``, x [n,F], y) triples.  Each molecule goes through
+    ``graph`` (= ``util.load_dgl_fromPyG``, util.py:277-325: dgl.graph + to_bidirected) and all of them are concatenated
+    like ``dgl.batch``.  Returns (and optionally ``torch.save``s) the dict that ``pts/<name>_csr.pt`` holds."""
+    gs, ys = [], []
+    for edge_index, x, y in molecules:
+        edge_index = np.asarray(edge_index)
+        x = torch.as_tensor(np.asarray(x)).float()
+        gs.append(graph((edge_index[0], edge_index[1]), num_nodes=x.shape[0], x=x))
+        ys.append(torch.as_tensor(np.asarray(y)).float().reshape(-1))
+    big = batch(gs)
+    shard = dict(graph_ptr=big.graph_ptr, indptr=big.indptr, indices=big.indices, x=big.ndata["x"], y=torch.stack(ys))
+    if path is not None:
+        torch.save(shard, path)
+    return shard
+
+
+def load_shard(path: str) -> "tuple[BatchedGraph, torch.Tensor]":
+    shard = torch.load(path)
+    return BatchedGraph(shard["graph_ptr"], shard["indptr"], shard["indices"], shard["x"]), shard.get("y")
