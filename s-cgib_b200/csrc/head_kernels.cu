@@ -113,7 +113,7 @@ void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s) {
 }
 
 // gH += g_q Wc1 ; dWc1 += g_q^T H ; dbc1 += sum g_q
-struct GateLinBwdSmem { float gq[GT * GLD]; float h[GT * GLD]; float w[HID * HID]; };
+struct GateLinBwdSmem { float gq[2][GT * GLD]; float h[2][GT * GLD]; float w[HID * HID]; };   // two tile buffers: cp.async prefetch
 
 __global__ void __launch_bounds__(kThreads, 1)
 gate_lin_bwd_kernel(GateLinBwdArgs p) {
@@ -129,16 +129,28 @@ gate_lin_bwd_kernel(GateLinBwdArgs p) {
     for (int j = 0; j < T::TJ; ++j) dW[i][j] = 0.f;
   float dbias = 0.f;
   const int n_tiles = (p.N + GT - 1) / GT;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // the next tile's g_q / H rows are copied (cp.async, no register staging) while this tile's GEMMs run
+  if ((int)blockIdx.x < n_tiles) {
+    cp_async_row_tile<GT, HID>(sm.gq[0], GLD, p.g_q, blockIdx.x * GT, p.N);
+    cp_async_row_tile<GT, HID>(sm.h[0], GLD, p.H, blockIdx.x * GT, p.N);
+  }
+  cp_async_commit();
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int base = tile * GT;
-    __syncthreads();
-    load_row_tile<GT, HID>(sm.gq, GLD, p.g_q, base, p.N);
-    load_row_tile<GT, HID>(sm.h, GLD, p.H, base, p.N);
-    __syncthreads();
+    const float* gq = sm.gq[it & 1];
+    const float* hh = sm.h[it & 1];
+    cp_async_wait_all();
+    __syncthreads();                      // tile `it` has landed; every thread is done with the other buffer (tile it-1)
+    if (tile + (int)gridDim.x < n_tiles) {
+      cp_async_row_tile<GT, HID>(sm.gq[(it + 1) & 1], GLD, p.g_q, (tile + gridDim.x) * GT, p.N);
+      cp_async_row_tile<GT, HID>(sm.h[(it + 1) & 1], GLD, p.H, (tile + gridDim.x) * GT, p.N);
+    }
+    cp_async_commit();
     float acc[M::TM][4];
 #pragma unroll
     for (int m = 0; m < M::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-    gemm_nn<GT, HID, HID>(sm.gq, GLD, sm.w, HID, acc);
+    gemm_nn<GT, HID, HID>(gq, GLD, sm.w, HID, acc);
     const int c0 = M::col0(), r0 = M::row0();
 #pragma unroll
     for (int m = 0; m < M::TM; ++m) {
@@ -149,14 +161,15 @@ gate_lin_bwd_kernel(GateLinBwdArgs p) {
         st4(dst, make_float4(old.x + acc[m][0], old.y + acc[m][1], old.z + acc[m][2], old.w + acc[m][3]));
       }
     }
-    gemm_tn<HID, HID>(sm.gq, GLD, sm.h, GLD, GT, dW);
+    gemm_tn<HID, HID>(gq, GLD, hh, GLD, GT, dW);
     if (threadIdx.x < HID) {
       float s = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < GT; ++r) s += sm.gq[r * GLD + threadIdx.x];
+      for (int r = 0; r < GT; ++r) s += gq[r * GLD + threadIdx.x];
       dbias += s;
     }
   }
+  cp_async_wait_all();
   float* part = p.part + (size_t)blockIdx.x * p.pstride;
 #pragma unroll
   for (int i = 0; i < T::TO; ++i)

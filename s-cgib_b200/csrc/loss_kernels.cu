@@ -357,21 +357,22 @@ void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, cudaStream_
 // ------------------------------------------------------------------------------------------------
 // losses = {KL, contrastive, recon, total}; also the contrastive denominators D_i (saved for backward)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+constexpr int kFin = 1024;     // one CTA; latency-bound (B rows x jsplit dependent loads each): as many threads as a CTA allows
+__global__ void __launch_bounds__(kFin)
 loss_finalize_kernel(LossFinalizeArgs p) {
-  __shared__ double s_a[kThreads], s_b[kThreads];
+  __shared__ double s_a[kFin], s_b[kFin];
   double con = 0.0, fro = 0.0;
-  for (int i = threadIdx.x; i < p.B; i += kThreads) {
+  for (int i = threadIdx.x; i < p.B; i += kFin) {
     float d = 0.f;
     for (int js = 0; js < p.jsplit; ++js) d += p.rowsum[(size_t)js * p.B + i];
     p.D[i] = d;
     con += (double)(logf(d) - p.diag[i]);      // -log(exp(s_b(i,i)) / D_i)
   }
   if (!p.recon_override)
-    for (int j = threadIdx.x; j < HID * HID; j += kThreads) { const double g = (double)p.G[j]; fro += g * g; }
+    for (int j = threadIdx.x; j < HID * HID; j += kFin) { const double g = (double)p.G[j]; fro += g * g; }
   s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
   __syncthreads();
-  for (int o = kThreads / 2; o > 0; o >>= 1) {
+  for (int o = kFin / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
     __syncthreads();
   }
@@ -383,7 +384,7 @@ loss_finalize_kernel(LossFinalizeArgs p) {
     p.losses[0] = kl; p.losses[1] = c; p.losses[2] = r; p.losses[3] = kl + r + c;
   }
 }
-void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_finalize_kernel<<<1, kThreads, 0, s>>>(a); }
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_finalize_kernel<<<1, kFin, 0, s>>>(a); }
 
 // ------------------------------------------------------------------------------------------------
 // grads[off+i] = sum_c part[c*pstride + off + i]   (fixed order => run-to-run bit-stable)
