@@ -389,15 +389,33 @@ def main():
     # (engine.prefetch_batch); every step still extracts the ego-nets of its own batch on the GPU.
     state = {}
 
+    # D2H of every step's {KL, contrastive, recon, total}: an async copy into pinned memory right behind the step, read on
+    # the host one step later (after the next step has been launched), so the GPU never drains for the read
+    loss_host = torch.empty(2, 4).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def read_loss_async(i, losses):
+        loss_host[i & 1].copy_(losses, non_blocking=True)
+        loss_ev[i & 1].record()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            state["loss"] = loss_host[(i - 1) & 1].clone()
+
+    def read_loss_last(steps):
+        loss_ev[(steps - 1) & 1].synchronize()
+        state["loss"] = loss_host[(steps - 1) & 1].clone()
+
     def run_steps(src, steps, read_loss):
         handle = eng.prefetch_batch(src[0], args.k)
         for i in range(steps):
             b = eng.wait_batch(handle)
             losses = eng.train_step(b, world_size=world)
+            if read_loss:
+                read_loss_async(i, losses)
             if i + 1 < steps:
                 handle = eng.prefetch_batch(src[(i + 1) % n_batches], args.k)
-            if read_loss:
-                state["loss"] = losses.cpu()                      # D2H of {KL, contrastive, recon, total}
+        if read_loss:
+            read_loss_last(steps)
         state["last"] = b
 
     def step_resident(steps):
@@ -434,9 +452,10 @@ def main():
         for i in range(steps):
             b = eng.wait_batch(handle)
             losses = eng.train_step(b, world_size=world)
+            read_loss_async(i, losses)
             if i + 1 < steps:
                 handle = eng.prefetch_ids(dataset, id_lists[(i + 1) % len(id_lists)], args.k)
-            state["loss"] = losses.cpu()
+        read_loss_last(steps)
 
     step_resident(args.warmup)
     sampler = make_clock_sampler(local_rank, torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
