@@ -152,6 +152,15 @@ SCGIB_API int scgib_batch_assemble_fill(const int32_t* mol_ptr, const int32_t* d
                                         const int32_t* graph_ptr, const int32_t* edge_ptr, int32_t* indptr,
                                         int32_t* indices, float* x, void* stream);
 
+/* Input validation on the device (failure detection; the reference's preprocessing swallows errors with bare `except:`,
+ * exp_pretraining.py:276-278, and a 1-node graph surfaces as a BatchNorm ValueError / NaN std, models.py:642-647).
+ * status[0] (device int32[2]) = 0 if the batch is well formed, else the smallest violated condition: 1 graph_ptr does not
+ * cover [0,N); 2 indptr does not cover [0,E); 3 a graph with < 2 nodes; 4 indptr not monotone; 5 a neighbour outside the
+ * node's own graph; 6 neighbours not strictly ascending (to_bidirected order, duplicate edges); 7 a self loop.
+ * status[1] = an offending graph / node id. */
+SCGIB_API int scgib_batch_validate(const int32_t* graph_ptr, const int32_t* indptr, const int32_t* indices, int32_t B,
+                                   int32_t N, int32_t E, int32_t* status, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole pre-training step (Mainmodel.forward / Mainmodel_continue.forward, models.py:662-700,
  * 1158-1195, + loss.backward(), exp_pretraining.py:315-322).

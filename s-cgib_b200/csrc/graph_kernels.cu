@@ -258,6 +258,43 @@ batch_fill_kernel(const int32_t* __restrict__ mol_ptr, const int32_t* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Input validation (failure detection before a step is launched): the conditions the kernels rely on.
+// status[0] = 0 ok, else the smallest violated code; status[1] = an offending node / graph id.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+batch_validate_kernel(const int32_t* __restrict__ graph_ptr, const int32_t* __restrict__ indptr,
+                      const int32_t* __restrict__ indices, int B, int N, int E, int32_t* status) {
+  auto fail = [&](int code, int where) {
+    const int old = atomicCAS(status, 0, code);
+    if (old == 0 || code < old) { atomicMin(status, code); status[1] = where; }
+  };
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i == 0) {
+    if (graph_ptr[0] != 0 || graph_ptr[B] != N) fail(1, 0);            // graph_ptr does not cover [0, N)
+    if (indptr[0] != 0 || indptr[N] != E) fail(2, 0);                  // indptr does not cover [0, E)
+  }
+  if (i < B) {
+    const int n = graph_ptr[i + 1] - graph_ptr[i];
+    if (n < 2) fail(3, i);                                              // per-graph BatchNorm / unbiased std need n >= 2 (models.py:642-647)
+  }
+  if (i < N) {
+    const int e0 = indptr[i], e1 = indptr[i + 1];
+    if (e1 < e0 || e0 < 0 || e1 > E) { fail(4, i); return; }            // indptr not monotone
+    int lo = 0, hi = B;                                                 // the graph of node i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (graph_ptr[mid] <= i) lo = mid; else hi = mid; }
+    const int g0 = graph_ptr[lo], g1 = graph_ptr[lo + 1];
+    int prev = -1;
+    for (int e = e0; e < e1; ++e) {
+      const int u = indices[e];
+      if (u < g0 || u >= g1) { fail(5, i); break; }                     // neighbour outside the node's own graph
+      if (u <= prev) { fail(6, i); break; }                             // neighbours not strictly ascending (to_bidirected order)
+      if (u == i) { fail(7, i); break; }                                // self loop
+      prev = u;
+    }
+  }
+}
+
 }  // namespace scgib
 
 using namespace scgib;
@@ -331,5 +368,16 @@ extern "C" SCGIB_API int scgib_batch_assemble_fill(const int32_t* mol_ptr, const
   const int grid = (B + kThreads / 32 - 1) / (kThreads / 32);
   batch_fill_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(mol_ptr, ds_indptr, ds_indices, ds_x, F, ids, B, graph_ptr,
                                                                 edge_ptr, indptr, indices, x);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_batch_validate(const int32_t* graph_ptr, const int32_t* indptr, const int32_t* indices, int32_t B,
+                                    int32_t N, int32_t E, int32_t* status, void* stream_) {
+  if (!graph_ptr || !indptr || !status || (E > 0 && !indices)) return SCGIB_E_NULL;
+  if (B < 1 || N < 1 || E < 0) return SCGIB_E_RANGE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), stream);
+  const int n = N > B ? N : B;
+  batch_validate_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(graph_ptr, indptr, indices, B, N, E, status);
   return (int)cudaGetLastError();
 }

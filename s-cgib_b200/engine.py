@@ -19,6 +19,7 @@ from . import _lib
 from .graph import BatchedGraph, EgoBatch, EgoWorkspace, khop_ego_batch
 
 HID, DTR = 64, 32
+_VALIDATE = __import__("os").environ.get("SCGIB_VALIDATE", "0") == "1"     # per-batch input validation (one extra host read)
 
 
 def param_names(gin_layers: int):
@@ -176,11 +177,33 @@ class PretrainEngine:
             sd[base + ".running_var"] = self.bn_running[i, 1].clone()
         return sd
 
+    def checkpoint(self):
+        """Everything needed to resume training bit-identically: parameters, BN running statistics, Adam moments and step,
+        the noise generator state (the reference checkpoints by pickling the whole module, exp_pretraining.py:103-132,
+        and loses the optimiser state; this keeps it)."""
+        return dict(params=self.params.detach().clone(), bn_running=self.bn_running.detach().clone(),
+                    exp_avg=self.exp_avg.detach().clone(), exp_avg_sq=self.exp_avg_sq.detach().clone(),
+                    step_count=self.step_count, num_batches_tracked=self.num_batches_tracked,
+                    noise_state=self._noise_gen.get_state(), gin_layers=int(self.dims.gin_layers),
+                    in_dim=int(self.dims.in_dim))
+
+    def restore(self, ck):
+        if int(ck["gin_layers"]) != int(self.dims.gin_layers) or int(ck["in_dim"]) != int(self.dims.in_dim):
+            raise ValueError("checkpoint was written for different model dimensions")
+        self.params.copy_(ck["params"])
+        self.bn_running.copy_(ck["bn_running"])
+        self.exp_avg.copy_(ck["exp_avg"])
+        self.exp_avg_sq.copy_(ck["exp_avg_sq"])
+        self.step_count, self.num_batches_tracked = int(ck["step_count"]), int(ck["num_batches_tracked"])
+        self._noise_gen.set_state(ck["noise_state"].cpu())
+
     # ---------------------------------------------------------------- data
     def make_batch(self, g: BatchedGraph, k: int = 1, normalize_x: bool = True) -> DeviceBatch:
         """H2D of a host batch (if needed) + on-GPU k-hop ego-net extraction."""
         if g.device != self.device:
             g = g.to(self.device, non_blocking=True)
+        if _VALIDATE:
+            g.validate()
         ego = khop_ego_batch(g, k, self.ego_ws)
         b = DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
         b.recon_logm_steps = self.recon_logm_steps

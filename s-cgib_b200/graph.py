@@ -82,7 +82,25 @@ class BatchedGraph:
         g.ndata = {k: v.pin_memory() for k, v in self.ndata.items()}
         return g
 
+    VALIDATE_ERRORS = {1: "graph_ptr does not cover [0, N)", 2: "indptr does not cover [0, E)",
+                       3: "a graph has fewer than 2 nodes (per-graph BatchNorm / unbiased std, models.py:642-647)",
+                       4: "indptr is not monotone", 5: "an edge leaves its graph", 6: "neighbours are not strictly ascending "
+                       "(duplicate edge or unsorted row; build graphs with graph() / to_bidirected)", 7: "self loop"}
+
     def validate(self):
+        """Checks what the kernels rely on; on a CUDA device with one kernel (scgib_batch_validate) and one host read.
+        Raises ValueError naming the violated condition.  The engine calls it per batch when SCGIB_VALIDATE=1."""
+        if self.device.type == "cuda":
+            lib = _lib.load()
+            status = torch.zeros(2, dtype=torch.int32, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.scgib_batch_validate(_lib.ptr(self.graph_ptr), _lib.ptr(self.indptr), _lib.ptr(self.indices),
+                                                self.batch_size, self.num_nodes(), self.num_edges(), _lib.ptr(status), st),
+                       "batch_validate")
+            code, where = status.tolist()
+            if code:
+                raise ValueError("invalid batch: %s (at graph / node %d)" % (self.VALIDATE_ERRORS.get(code, code), where))
+            return self
         n = self.batch_num_nodes()
         if int(n.min()) < 2:
             raise ValueError("every graph needs >= 2 nodes (per-graph BatchNorm / unbiased std, models.py:642-647)")

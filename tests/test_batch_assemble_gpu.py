@@ -64,3 +64,26 @@ def test_train_step_from_ids_equals_step_from_host_batch():
         grads = eng.backward().clone()
         res.append((losses, grads))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_batch_validate_names_the_violation():
+    """scgib_batch_validate: well-formed batches pass; each malformed one is rejected with its own message."""
+    from scgib_b200.graph import BatchedGraph
+    mols, big = _dataset(12, 3)
+    def make(gp=None, ip=None, idx=None):
+        return BatchedGraph(torch.from_numpy(big.graph_ptr if gp is None else gp), torch.from_numpy(big.indptr if ip is None else ip),
+                            torch.from_numpy(big.indices if idx is None else idx), torch.from_numpy(big.x)).to(DEV)
+    make().validate()
+    gp = big.graph_ptr.copy(); gp[1] = gp[0] + 1                      # first graph: one node
+    with pytest.raises(ValueError, match="fewer than 2 nodes"):
+        make(gp=gp).validate()
+    idx = big.indices.copy(); idx[0] = big.num_nodes - 1              # first node points into the last graph
+    with pytest.raises(ValueError, match="leaves its graph"):
+        make(idx=idx).validate()
+    idx = big.indices.copy()
+    v = int(np.argmax(np.diff(big.indptr) >= 2)); e = int(big.indptr[v]); idx[e + 1] = idx[e]     # duplicate neighbour
+    with pytest.raises(ValueError, match="strictly ascending"):
+        make(idx=idx).validate()
+    ip = big.indptr.copy(); ip[5] = ip[6] + 1
+    with pytest.raises(ValueError, match="monotone|leaves|ascending"):
+        make(ip=ip).validate()

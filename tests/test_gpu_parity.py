@@ -396,3 +396,31 @@ def test_eval_mode_uses_running_statistics():
         assert rel(emb[name].cpu(), out[name]) <= 2e-5, (name, rel(emb[name].cpu(), out[name]))
     with pytest.raises(RuntimeError):
         eng.backward()                                              # the backward is the training-mode one
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """PretrainEngine.checkpoint / restore: 4 training steps == 2 steps + save + load into a fresh engine + 2 steps, bit for
+    bit (parameters, Adam moments, BN running statistics, noise stream)."""
+    from scgib_b200.engine import PretrainEngine
+    from scgib_b200.synth import synth_batch as product_synth
+    batches = [product_synth(100 + i, 64).to(DEV) for i in range(4)]
+
+    def steps(eng, lo, hi):
+        out = []
+        for i in range(lo, hi):
+            b = eng.make_batch(batches[i], 1)
+            out.append(eng.train_step(b).clone())
+        return out
+
+    a = PretrainEngine(9, gin_layers=4, device=DEV, seed=11)
+    la = steps(a, 0, 4)
+    b1 = PretrainEngine(9, gin_layers=4, device=DEV, seed=11)
+    lb = steps(b1, 0, 2)
+    torch.save(b1.checkpoint(), tmp_path / "ck.pt")
+    b2 = PretrainEngine(9, gin_layers=4, device=DEV, seed=999)          # different init: everything must come from the file
+    b2.restore(torch.load(tmp_path / "ck.pt", weights_only=False))
+    lb += steps(b2, 2, 4)
+    for x, y in zip(la, lb):
+        assert torch.equal(x, y)
+    assert torch.equal(a.params, b2.params) and torch.equal(a.exp_avg_sq, b2.exp_avg_sq)
+    assert torch.equal(a.bn_running, b2.bn_running) and a.step_count == b2.step_count == 4
