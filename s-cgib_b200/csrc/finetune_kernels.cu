@@ -115,23 +115,54 @@ __global__ void __launch_bounds__(kThreads) finetune_head_fwd_kernel(FinetuneHea
       q.load(&sm.in[warp][0], lane);
       float* al = p.alpha + (size_t)t * p.N;
       float mx = -INFINITY;
-      for (int v = v0; v < v1; ++v) {
-        Lane<H> z; z.load(p.Z + (size_t)v * H, lane);
-        const float e = lane_dot<H>(z, q);
-        if (lane == 0) al[v] = e;
-        mx = fmaxf(mx, e);
+      constexpr int RB = 4;               // rows in flight: the loads and the shuffle reductions of RB rows overlap
+      for (int vb = v0; vb < v1; vb += RB) {
+        Lane<H> z[RB];
+        float e[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) z[r].load(p.Z + (size_t)min(vb + r, v1 - 1) * H, lane);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          e[r] = 0.f;
+#pragma unroll
+          for (int i = 0; i < Lane<H>::W; ++i) e[r] = fmaf(z[r].v[i], q.v[i], e[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < RB; ++r) e[r] += __shfl_xor_sync(0xffffffffu, e[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (vb + r < v1) {
+            if (lane == 0) al[vb + r] = e[r];
+            mx = fmaxf(mx, e[r]);
+          }
+        }
       }
       __syncwarp();
       Lane<H> acc;
 #pragma unroll
       for (int i = 0; i < Lane<H>::W; ++i) acc.v[i] = 0.f;
       float den = 0.f;
-      for (int v = v0; v < v1; ++v) {
-        Lane<H> z; z.load(p.Z + (size_t)v * H, lane);
-        const float ex = expf(al[v] - mx);
-        den += ex;
+      for (int vb = v0; vb < v1; vb += RB) {
+        Lane<H> z[RB];
+        float ex[RB];
 #pragma unroll
-        for (int i = 0; i < Lane<H>::W; ++i) acc.v[i] = fmaf(ex, z.v[i], acc.v[i]);
+        for (int r = 0; r < RB; ++r) {
+          const int v = min(vb + r, v1 - 1);
+          z[r].load(p.Z + (size_t)v * H, lane);
+          ex[r] = al[v];
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (vb + r < v1) {
+            const float x = expf(ex[r] - mx);
+            den += x;
+#pragma unroll
+            for (int i = 0; i < Lane<H>::W; ++i) acc.v[i] = fmaf(x, z[r].v[i], acc.v[i]);
+          }
+        }
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
       __syncwarp();
@@ -255,33 +286,67 @@ __global__ void __launch_bounds__(kThreads) finetune_head_bwd_kernel(FinetuneHea
       q.load(qs, lane);
       gr.load(&sm.gq[warp][H], lane);
       float S = 0.f;
-      for (int v = v0; v < v1; ++v) {
-        Lane<H> z; z.load(p.Z + (size_t)v * H, lane);
-        const float ga = lane_dot<H>(z, gr);
-        if (lane == 0) p.gp[v] = ga;
-        S = fmaf(__ldg(al + v), ga, S);
+      constexpr int RB = 4;
+      for (int vb = v0; vb < v1; vb += RB) {
+        Lane<H> z[RB];
+        float ga[RB], av[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int v = min(vb + r, v1 - 1);
+          z[r].load(p.Z + (size_t)v * H, lane);
+          av[r] = __ldg(al + v);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          ga[r] = 0.f;
+#pragma unroll
+          for (int i = 0; i < Lane<H>::W; ++i) ga[r] = fmaf(z[r].v[i], gr.v[i], ga[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < RB; ++r) ga[r] += __shfl_xor_sync(0xffffffffu, ga[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (vb + r < v1) {
+            if (lane == 0) p.gp[vb + r] = ga[r];
+            S = fmaf(av[r], ga[r], S);
+          }
+        }
       }
       __syncwarp();
       Lane<H> accq;
 #pragma unroll
       for (int i = 0; i < Lane<H>::W; ++i) accq.v[i] = 0.f;
-      for (int v = v0; v < v1; ++v) {
-        Lane<H> z; z.load(p.Z + (size_t)v * H, lane);
-        const float a = __ldg(al + v);
-        const float ge = a * (p.gp[v] - S);
-        Lane<H> gz;
-        if (t == T - 1) {
+      for (int vb = v0; vb < v1; vb += RB) {
+        Lane<H> z[RB], gz[RB];
+        float a[RB], gpv[RB];
 #pragma unroll
-          for (int i = 0; i < Lane<H>::W; ++i) gz.v[i] = 0.f;
-        } else {
-          gz.load(p.gZ + (size_t)v * H, lane);
+        for (int r = 0; r < RB; ++r) {
+          const int v = min(vb + r, v1 - 1);
+          z[r].load(p.Z + (size_t)v * H, lane);
+          a[r] = __ldg(al + v);
+          gpv[r] = p.gp[v];
+          if (t == T - 1) {
+#pragma unroll
+            for (int i = 0; i < Lane<H>::W; ++i) gz[r].v[i] = 0.f;
+          } else {
+            gz[r].load(p.gZ + (size_t)v * H, lane);
+          }
         }
 #pragma unroll
-        for (int i = 0; i < Lane<H>::W; ++i) {
-          gz.v[i] += fmaf(a, gr.v[i], ge * q.v[i]);
-          accq.v[i] = fmaf(ge, z.v[i], accq.v[i]);
+        for (int r = 0; r < RB; ++r) {
+          if (vb + r < v1) {
+            const float ge = a[r] * (gpv[r] - S);
+#pragma unroll
+            for (int i = 0; i < Lane<H>::W; ++i) {
+              gz[r].v[i] += fmaf(a[r], gr.v[i], ge * q.v[i]);
+              accq.v[i] = fmaf(ge, z[r].v[i], accq.v[i]);
+            }
+            gz[r].store(p.gZ + (size_t)(vb + r) * H, lane);
+          }
         }
-        gz.store(p.gZ + (size_t)v * H, lane);
       }
       Lane<H> gqv;
       gqv.load(&sm.gq[warp][0], lane);

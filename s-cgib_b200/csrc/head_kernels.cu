@@ -192,6 +192,7 @@ __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<floa
 
 constexpr float kKlEps = 0.0000001f;   // models.py:632
 
+template <int RB>      // rows in flight per warp in the gate pass (4 for molecule-sized graphs, 8 for ~150-node graphs)
 __global__ void __launch_bounds__(kThreads)
 graph_gate_fwd_kernel(GraphGateFwdArgs p) {
   const int lane = threadIdx.x & 31;
@@ -238,7 +239,7 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
     const bool last = (g == p.B - 1);
     float2 core = make_float2(0.f, 0.f), kl1 = make_float2(0.f, 0.f), kl2 = make_float2(0.f, 0.f);
     const float2 isd = make_float2(1.f / (sd.x + kKlEps), 1.f / (sd.y + kKlEps));
-    constexpr int RB = 4;      // rows in flight per warp (latency-bound loop: loads and shuffle chains of RB rows overlap)
+    // latency-bound loop: the loads and shuffle chains of RB rows overlap
     for (int vb = v0; vb < v1; vb += RB) {
       float2 h[RB], q[RB], fu[RB];
       float u[RB], pv[RB];
@@ -296,7 +297,8 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
 }
 void launch_graph_gate_fwd(const GraphGateFwdArgs& a, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 8 * num_sms());
-  graph_gate_fwd_kernel<<<grid, kThreads, 0, s>>>(a);
+  if (a.N / max(a.B, 1) >= 48) graph_gate_fwd_kernel<8><<<grid, kThreads, 0, s>>>(a);
+  else graph_gate_fwd_kernel<4><<<grid, kThreads, 0, s>>>(a);
 }
 
 // running stats of the compressor BN after B sequential per-graph updates (closed form, fixed order)
