@@ -269,6 +269,22 @@ SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, const int32_
                             float* a_out, float* r_out, float* y_out, float* bn_out, float* running,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of one GINConv + BatchNorm(train) + ReLU layer (autograd through models.py:66-72), the per-layer unit of
+ * scgib_pretrain_backward_f32:
+ *   g_next : indptr == NULL: [V,H] gradient wrt the layer OUTPUT h' = relu(BN(y));
+ *            indptr != NULL: [V,H] gradient wrt the NEXT layer's aggregated input, gathered here through the symmetric
+ *            CSR (G_v = g_next[v] + sum_{u in N(v)} g_next[u]: the transpose of the GIN aggregation, no atomics);
+ *   y, r, a: what scgib_gin_layer_fwd_f32 saved (pre-BN output, hidden relu(W1 a + b1), aggregated input);
+ *   bn     : {mean, rstd, gamma, beta}[H] of this layer;
+ *   outputs: g_a [V,kin] (gradient wrt the aggregated input a), dW1 [H,kin], db1 [H], dW2 [H,H], db2 [H], dgamma [H],
+ *            dbeta [H] - all overwritten. */
+SCGIB_API size_t scgib_gin_layer_bwd_workspace_bytes(int32_t V, int32_t kin);
+SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int32_t* indptr, const int32_t* indices, int32_t V,
+                                      int32_t kin, const float* y, const float* r, const float* a, const float* bn,
+                                      const float* W1, const float* W2, float* g_a, float* dW1, float* db1, float* dW2,
+                                      float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* out[s] = sum_{rows in segment s} f(in[row])  (dgl.sum_nodes, models.py:716,725,733,684);
  * f = relu(BN(.)) when bn = {mean,rstd,gamma,beta} is given, identity otherwise. */
 SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn,

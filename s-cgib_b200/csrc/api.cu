@@ -746,6 +746,69 @@ extern "C" SCGIB_API int scgib_gin_layer_fwd_f32(const float* in, int32_t kin, c
   return (int)cudaGetLastError();
 }
 
+// One GINConv + BatchNorm + ReLU layer backward (the three kernels the whole-step backward uses per layer)
+namespace scgib {
+struct GinBwdOpWs { float *g_o, *cvec, *part2, *ppart; unsigned int* counter; int64_t off[4], pstride; size_t bytes; };
+static GinBwdOpWs gin_bwd_op_carve(int V, int kin, void* base) {
+  GinBwdOpWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  w.g_o = take((size_t)V * HID); w.cvec = take(2 * HID);
+  w.part2 = take((size_t)(gin_bwd_pre_grid(V) + 2) * 2 * HID);
+  w.counter = (unsigned int*)take(64);
+  w.off[0] = 0; w.off[1] = (int64_t)HID * kin; w.off[2] = w.off[1] + HID; w.off[3] = w.off[2] + (int64_t)HID * HID;   // W1 b1 W2 b2
+  w.pstride = w.off[3] + HID;
+  w.ppart = take((size_t)num_sms() * w.pstride);
+  w.bytes = o;
+  return w;
+}
+}  // namespace scgib
+
+extern "C" SCGIB_API size_t scgib_gin_layer_bwd_workspace_bytes(int32_t V, int32_t kin) {
+  if (V < 1 || (kin != DTR && kin != HID)) return 0;
+  return gin_bwd_op_carve(V, kin, nullptr).bytes;
+}
+
+extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int32_t* indptr, const int32_t* indices, int32_t V,
+                                       int32_t kin, const float* y, const float* r, const float* a, const float* bn,
+                                       const float* W1, const float* W2, float* g_a, float* dW1, float* db1, float* dW2,
+                                       float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
+  if (!g_next || !y || !r || !a || !bn || !W1 || !W2 || !g_a || !dW1 || !db1 || !dW2 || !db2 || !dgamma || !dbeta || !workspace)
+    return SCGIB_E_NULL;
+  if (indptr && !indices) return SCGIB_E_NULL;
+  if (kin != DTR && kin != HID) return SCGIB_E_SHAPE;
+  if (V < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0) return SCGIB_E_ALIGN;
+  const GinBwdOpWs w = gin_bwd_op_carve(V, kin, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int GP = num_sms();
+  cudaMemsetAsync(w.counter, 0, 256, s);
+  GinBwdPreArgs q;
+  q.src = g_next; q.indptr = indptr; q.indices = indptr ? indices : nullptr; q.map = nullptr;
+  q.y = y; q.bn = bn; q.V = V; q.g_o = w.g_o; q.part = w.part2; q.counter = w.counter;
+  q.d_gamma = dgamma; q.d_beta = dbeta; q.cvec = w.cvec;
+  launch_gin_bwd_pre(q, s);
+  GinBwdMainArgs m;
+  m.g_o = w.g_o; m.y = y; m.r = r; m.a = a; m.bn = bn; m.cvec = w.cvec; m.W1 = W1; m.W2 = W2; m.V = V; m.g_a = g_a;
+  m.part = w.ppart; m.pstride = w.pstride; m.off_W1 = w.off[0]; m.off_b1 = w.off[1]; m.off_W2 = w.off[2]; m.off_b2 = w.off[3];
+  const int mode = bwd_tensor_core_mode();
+  if (mode == 2) launch_gin_bwd_main_tc2(m, kin, GP, s);
+  else if (mode == 1) launch_gin_bwd_main_tc(m, kin, GP, s);
+  else launch_gin_bwd_main(m, kin, GP, s);
+  // per-CTA partials -> the four gradient tensors (fixed order)
+  float* outs[4] = {dW1, db1, dW2, db2};
+  const int64_t lens[4] = {(int64_t)HID * kin, HID, (int64_t)HID * HID, HID};
+  for (int i = 0; i < 4; ++i) {
+    ReduceRanges rr;
+    rr.n = 1; rr.off[0] = w.off[i]; rr.len[0] = lens[i]; rr.c0[0] = 0; rr.c1[0] = GP;
+    launch_reduce_partials(w.ppart, w.pstride, GP, rr, outs[i] - w.off[i], s);
+  }
+  return (int)cudaGetLastError();
+}
+
 extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn, float* out, void* stream) {
   if (!in || !seg_ptr || !out) return SCGIB_E_NULL;
   if (S < 1) return SCGIB_E_RANGE;

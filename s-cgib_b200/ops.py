@@ -56,3 +56,24 @@ def segment_sum(h, seg_ptr, bn=None):
     _lib.check(_lib.load().scgib_segment_sum_f32(_lib.ptr(h.contiguous()), _lib.ptr(seg_ptr), S, _lib.ptr(bn),
                                                  _lib.ptr(out), _stream(h)), "segment_sum")
     return out
+
+
+def gin_layer_bwd(g_next, y, r, a, bn, W1, W2, indptr=None, indices=None):
+    """Backward of one GINConv + BatchNorm(train) + ReLU layer.  ``g_next``: gradient wrt the layer output (``indptr`` None)
+    or wrt the next layer's aggregated input (gathered through the CSR).  ``bn`` = [4,64] {mean, rstd, gamma, beta}.
+    Returns (g_a, dW1, db1, dW2, db2, dgamma, dbeta)."""
+    _cuda(g_next, y, r, a, bn, W1, W2)
+    lib = _lib.load()
+    V, kin, dev = y.shape[0], a.shape[1], y.device
+    g_a = torch.empty(V, kin, device=dev)
+    dW1, db1 = torch.empty(HID, kin, device=dev), torch.empty(HID, device=dev)
+    dW2, db2 = torch.empty(HID, HID, device=dev), torch.empty(HID, device=dev)
+    dgamma, dbeta = torch.empty(HID, device=dev), torch.empty(HID, device=dev)
+    ws = torch.empty(lib.scgib_gin_layer_bwd_workspace_bytes(V, kin) + 256, dtype=torch.uint8, device=dev)
+    _lib.check(lib.scgib_gin_layer_bwd_f32(_lib.ptr(g_next.contiguous()), _lib.ptr(indptr), _lib.ptr(indices), V, kin,
+                                           _lib.ptr(y.contiguous()), _lib.ptr(r.contiguous()), _lib.ptr(a.contiguous()),
+                                           _lib.ptr(bn.contiguous()), _lib.ptr(W1.contiguous()), _lib.ptr(W2.contiguous()),
+                                           _lib.ptr(g_a), _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2),
+                                           _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws), ws.numel(), _stream(y)),
+               "gin_layer_bwd")
+    return g_a, dW1, db1, dW2, db2, dgamma, dbeta

@@ -424,3 +424,44 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
         assert torch.equal(x, y)
     assert torch.equal(a.params, b2.params) and torch.equal(a.exp_avg_sq, b2.exp_avg_sq)
     assert torch.equal(a.bn_running, b2.bn_running) and a.step_count == b2.step_count == 4
+
+
+@pytest.mark.parametrize("kin,csr", [(64, False), (32, False), (64, True)])
+def test_gin_layer_backward_op(kin, csr):
+    """scgib_gin_layer_bwd_f32 (the per-layer unit of the backward) against torch autograd through GINConv -> BatchNorm
+    (train) -> ReLU, with the upstream gradient given at the layer output or gathered through the CSR."""
+    from scgib_b200 import ops
+    from oracle.scgib_oracle import GINConvRef, MLP
+    g = synth_batch(5, 400)
+    tg = tgraph_from_ref(g)
+    V = g.num_nodes
+    torch.manual_seed(kin + int(csr))
+    conv = GINConvRef(MLP(kin, 64, 64)).double()
+    bnm = torch.nn.BatchNorm1d(64).double().train()
+    with torch.no_grad():
+        bnm.weight.uniform_(0.5, 1.5); bnm.bias.uniform_(-0.3, 0.3)
+    h = torch.randn(V, kin, dtype=torch.float64)
+    neigh = torch.zeros_like(h).index_add(0, tg.dst, h[tg.src])
+    a_ref = (h + neigh).requires_grad_(True)
+    lin1, lin2 = conv.apply_func.mlp[0], conv.apply_func.mlp[2]
+    r_ref = torch.relu(lin1(a_ref))
+    y_ref = lin2(r_ref)
+    out = torch.relu(bnm(y_ref))
+    g_up = torch.randn(V, 64, dtype=torch.float64)
+    G = g_up + torch.zeros_like(g_up).index_add(0, tg.dst, g_up[tg.src]) if csr else g_up   # transpose of the aggregation
+    (out * G).sum().backward()
+    mean, var = y_ref.mean(0), y_ref.var(0, unbiased=False)
+    bn = torch.stack([mean, 1.0 / torch.sqrt(var + 1e-5), bnm.weight, bnm.bias]).detach().float().to(DEV)
+    pg = product_graph(g, DEV)
+    res = ops.gin_layer_bwd(g_up.float().to(DEV), y_ref.detach().float().to(DEV), r_ref.detach().float().to(DEV),
+                            a_ref.detach().float().to(DEV), bn, lin1.weight.detach().float().to(DEV),
+                            lin2.weight.detach().float().to(DEV), indptr=pg.indptr if csr else None,
+                            indices=pg.indices if csr else None)
+    want = (a_ref.grad, lin1.weight.grad, lin1.bias.grad, lin2.weight.grad, lin2.bias.grad, bnm.weight.grad, bnm.bias.grad)
+    names = ("g_a", "dW1", "db1", "dW2", "db2", "dgamma", "dbeta")
+    gmax = max(float(w.abs().max()) for w in want)
+    for name, got, w in zip(names, res, want):
+        if name == "db2":        # a bias in front of a BatchNorm: mathematically zero
+            assert float(got.abs().max()) <= 1e-5 * gmax
+            continue
+        assert rel(got.cpu(), w) <= 5e-5, (name, rel(got.cpu(), w))
