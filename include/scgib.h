@@ -285,6 +285,19 @@ SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int32_t* indptr
                                       float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                                       void* stream);
 
+/* Loss operators: value and gradient in one call (the units of the whole-step functions).  workspace >=
+ * scgib_loss_workspace_bytes(B) (B = 1 for the reconstruction loss), 256-byte aligned; loss = device float[1].
+ *  scgib_recon_adj_f32  : loss_recon_adj (models.py:762-768) = sum_{ij} (z_i . z_j - A_ij)^2 / N over the WHOLE batch
+ *                         (cross-graph pairs included, as the reference does) through the Gram identity
+ *                         ||Z^T Z||_F^2 - 2 sum_E z_i . z_j + E; gZ (optional) = scale * d loss / d Z = scale 4/N (Z G - A Z).
+ *  scgib_contrastive_f32: batched_semi_loss (models.py:606-629, tau = 1, one chunk) of z1 = core readout, z2 = graph
+ *                         readout ([B,H], un-normalised); g_core / g_readout (optional, both or none) = scale * gradients. */
+SCGIB_API size_t scgib_loss_workspace_bytes(int32_t B);
+SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
+                                  float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int32_t B, float scale, float* loss,
+                                    float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream);
+
 /* out[s] = sum_{rows in segment s} f(in[row])  (dgl.sum_nodes, models.py:716,725,733,684);
  * f = relu(BN(.)) when bn = {mean,rstd,gamma,beta} is given, identity otherwise. */
 SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn,

@@ -81,6 +81,11 @@ _SIGNATURES = {
     "scgib_gin_layer_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),
+    "scgib_loss_workspace_bytes": (c_size_t, [c_int32]),
+    "scgib_recon_adj_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "scgib_contrastive_f32": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "scgib_set_tensor_cores": (None, [c_int]),
     "scgib_set_tensor_cores_bwd": (None, [c_int]),

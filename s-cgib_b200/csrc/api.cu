@@ -809,6 +809,80 @@ extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int3
   return (int)cudaGetLastError();
 }
 
+// ---- loss operators (forward + gradient in one call; the units of the whole-step functions)
+namespace scgib {
+struct LossOpWs { float *rpart, *G, *edge, *z1, *z2, *zsplit, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *kl, *losses; size_t bytes; };
+static LossOpWs loss_op_carve(int B, void* base) {
+  LossOpWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  const int js = contrastive_jsplit(B > 0 ? B : 1);
+  w.rpart = take((size_t)num_sms() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
+  w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID); w.zsplit = take((size_t)4 * B * HID);
+  w.n1 = take(B); w.n2 = take(B); w.diag = take(B); w.D = take(B); w.rowsum = take((size_t)js * B);
+  w.g1p = take((size_t)js * B * HID); w.g2p = take((size_t)js * B * HID); w.kl = take(4); w.losses = take(4);
+  w.bytes = o;
+  return w;
+}
+}  // namespace scgib
+
+extern "C" SCGIB_API size_t scgib_loss_workspace_bytes(int32_t B) { return B < 0 ? 0 : loss_op_carve(B, nullptr).bytes; }
+
+extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
+                                   float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!Z || !indptr || !loss || !workspace || (E > 0 && !indices)) return SCGIB_E_NULL;
+  if (N < 1 || E < 0) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)Z & 15u) != 0 || ((uintptr_t)gZ & 15u) != 0) return SCGIB_E_ALIGN;
+  const LossOpWs w = loss_op_carve(1, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int grid = num_sms();
+  ReconFwdArgs a{Z, indptr, indices, N, w.rpart};
+  launch_recon_fwd(a, grid, s);
+  launch_recon_reduce(w.rpart, grid, w.G, w.edge, s);
+  cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
+  cudaMemsetAsync(w.rowsum, 0, sizeof(float), s);
+  cudaMemsetAsync(w.diag, 0, sizeof(float), s);
+  LossFinalizeArgs f{w.rowsum, 1, w.diag, 0, w.G, w.edge, N, E, nullptr, w.kl, w.D, w.losses};   // B = 0: only the recon term
+  launch_loss_finalize(f, s);
+  cudaMemcpyAsync(loss, w.losses + 2, sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (gZ) {
+    ReconBwdArgs ra{Z, w.G, indptr, indices, N, scale, gZ};
+    launch_recon_bwd(ra, s);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int32_t B, float scale, float* loss,
+                                     float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!core || !readout || !loss || !workspace) return SCGIB_E_NULL;
+  if ((g_core == nullptr) != (g_readout == nullptr)) return SCGIB_E_NULL;
+  if (B < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)core & 15u) != 0 || ((uintptr_t)readout & 15u) != 0) return SCGIB_E_ALIGN;
+  const LossOpWs w = loss_op_carve(B, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int js = contrastive_jsplit(B);
+  NormalizeArgs na{core, readout, B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
+  launch_normalize(na, s);
+  ContrastiveFwdArgs c{w.z1, w.z2, B, js, w.rowsum, w.zsplit};
+  if (use_tc_contrastive()) launch_contrastive_fwd_tc(c, s); else launch_contrastive_fwd(c, s);
+  cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
+  cudaMemsetAsync(w.G, 0, HID * HID * sizeof(float), s);
+  cudaMemsetAsync(w.edge, 0, 4 * sizeof(float), s);
+  LossFinalizeArgs f{w.rowsum, js, w.diag, B, w.G, w.edge, 1, 0, nullptr, w.kl, w.D, w.losses};
+  launch_loss_finalize(f, s);
+  cudaMemcpyAsync(loss, w.losses + 1, sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (g_core) {
+    ContrastiveBwdArgs a{w.z1, w.z2, w.D, B, js, w.g1p, w.g2p};
+    if (use_tc_contrastive()) launch_contrastive_bwd_tc(a, w.zsplit, s); else launch_contrastive_bwd(a, s);
+    ContrastiveBwdFinArgs fa{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, B, js, scale, g_core, g_readout};
+    launch_contrastive_bwd_finalize(fa, s);
+  }
+  return (int)cudaGetLastError();
+}
+
 extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn, float* out, void* stream) {
   if (!in || !seg_ptr || !out) return SCGIB_E_NULL;
   if (S < 1) return SCGIB_E_RANGE;

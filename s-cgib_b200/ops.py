@@ -77,3 +77,32 @@ def gin_layer_bwd(g_next, y, r, a, bn, W1, W2, indptr=None, indices=None):
                                            _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws), ws.numel(), _stream(y)),
                "gin_layer_bwd")
     return g_a, dW1, db1, dW2, db2, dgamma, dbeta
+
+
+def recon_adj(Z, indptr, indices, scale=1.0, want_grad=True):
+    """loss_recon_adj (models.py:762-768) and scale * d loss / d Z; returns (loss[1], gZ or None)."""
+    _cuda(Z, indptr)
+    lib = _lib.load()
+    Z = Z.contiguous().float()
+    N, E = Z.shape[0], indices.numel()
+    loss = torch.empty(1, device=Z.device)
+    gZ = torch.empty_like(Z) if want_grad else None
+    ws = torch.empty(lib.scgib_loss_workspace_bytes(1) + 256, dtype=torch.uint8, device=Z.device)
+    _lib.check(lib.scgib_recon_adj_f32(_lib.ptr(Z), _lib.ptr(indptr), _lib.ptr(indices), N, E, float(scale), _lib.ptr(loss),
+                                       _lib.ptr(gZ), _lib.ptr(ws), ws.numel(), _stream(Z)), "recon_adj")
+    return loss, gZ
+
+
+def contrastive(core, readout, scale=1.0, want_grad=True):
+    """batched_semi_loss (models.py:606-629) of the core / graph readouts and its gradients; returns (loss[1], g_core, g_readout)."""
+    _cuda(core, readout)
+    lib = _lib.load()
+    core, readout = core.contiguous().float(), readout.contiguous().float()
+    B = core.shape[0]
+    loss = torch.empty(1, device=core.device)
+    g1 = torch.empty_like(core) if want_grad else None
+    g2 = torch.empty_like(core) if want_grad else None
+    ws = torch.empty(lib.scgib_loss_workspace_bytes(B) + 256, dtype=torch.uint8, device=core.device)
+    _lib.check(lib.scgib_contrastive_f32(_lib.ptr(core), _lib.ptr(readout), B, float(scale), _lib.ptr(loss), _lib.ptr(g1),
+                                         _lib.ptr(g2), _lib.ptr(ws), ws.numel(), _stream(core)), "contrastive")
+    return loss, g1, g2

@@ -465,3 +465,30 @@ def test_gin_layer_backward_op(kin, csr):
             assert float(got.abs().max()) <= 1e-5 * gmax
             continue
         assert rel(got.cpu(), w) <= 5e-5, (name, rel(got.cpu(), w))
+
+
+def test_loss_operators_recon_and_contrastive():
+    """scgib_recon_adj_f32 / scgib_contrastive_f32 (value + gradient) against the oracle's dense formulas in fp64."""
+    from scgib_b200 import ops
+    g = synth_batch(8, 200)
+    tg = tgraph_from_ref(g)
+    torch.manual_seed(8)
+    m = OracleMainmodel(9).double()
+    Z = (torch.randn(g.num_nodes, 64, dtype=torch.float64) * 0.3).requires_grad_(True)
+    rec = m.loss_recon_adj(Z, tg)
+    rec.backward()
+    pg = product_graph(g, DEV)
+    loss, gZ = ops.recon_adj(Z.detach().float().to(DEV), pg.indptr, pg.indices, scale=0.5)
+    assert abs(float(loss) - float(rec)) <= 1e-5 * abs(float(rec))
+    assert rel(gZ.cpu(), 0.5 * Z.grad) <= 2e-5
+    for B in (1, 7, 300, 1100):
+        core = (torch.randn(B, 64, dtype=torch.float64) * 2).requires_grad_(True)
+        ro = (torch.randn(B, 64, dtype=torch.float64) * 3).requires_grad_(True)
+        con = m.batched_semi_loss(core, ro, B)
+        con.backward()
+        loss, g1, g2 = ops.contrastive(core.detach().float().to(DEV), ro.detach().float().to(DEV), scale=2.0)
+        if B == 1:
+            assert abs(float(loss)) <= 1e-6
+            continue
+        assert abs(float(loss) - float(con)) <= 1e-5 * abs(float(con)), B
+        assert rel(g1.cpu(), 2.0 * core.grad) <= 5e-5 and rel(g2.cpu(), 2.0 * ro.grad) <= 5e-5, B
