@@ -249,3 +249,50 @@ def test_mainmodel_domainadapt_matches_reference_golden(path, tmp_path, monkeypa
         errs.append((rel(gg, gref), n))
     errs.sort()
     assert errs[len(errs) // 2][0] <= 5e-5 and errs[-1][0] <= 5e-3, errs[-3:]
+
+
+def test_finetune_forward_full_size_vs_fp64_oracle():
+    """B = 4096 PCQM4Mv2-shape graphs (the bench size): features-only forward + Set2Set/predict head on the GPU against the
+    fp64 vectorised oracle of the feature path followed by the fp64 Set2Set restatement; gradients of the head at scale."""
+    from scgib_b200.engine import DeviceBatch, FinetuneHead
+    from scgib_b200.graph import khop_ego_batch
+    from tests.helpers import engine_from_oracle
+    B = 4096
+    g = synth_batch(123, B) if B <= 512 else __import__("oracle.graph_ref", fromlist=["synth_batch_fast"]).synth_batch_fast(123, B)
+    e = ego_batch_ref(g, 1)
+    torch.manual_seed(123)
+    m = OracleMainmodel(9)
+    s2s = Set2SetRef(64, 2, 1)
+    predict = nn.Sequential(nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 10))
+    gen = torch.Generator().manual_seed(5)
+    gate_u, feat_u = torch.rand(g.num_nodes, generator=gen), torch.rand(g.num_nodes, 64, generator=gen)
+    eng = engine_from_oracle(m, DEV)
+    pg = product_graph(g, DEV)
+    b = DeviceBatch(pg, khop_ego_batch(pg, 1), pg.ndata["x"], normalize_x=True)
+    Z = eng.forward_features(b, gate_u.to(DEV), feat_u.to(DEV))
+    head = FinetuneHead(64, 10, n_iters=2, sigmoid=True, device=DEV)
+    sd = {"s2s." + n: p for n, p in s2s.state_dict().items()}
+    sd.update({"predict." + n: p for n, p in predict.state_dict().items()})
+    head.load_state_dict({n: t.float() for n, t in sd.items()})
+    scores = head.forward(Z, pg.graph_ptr)
+    # fp64 truth
+    m64 = OracleMainmodel(9).double()
+    m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
+    xr = normalize_rows(torch.from_numpy(g.x).double())
+    en = torch.from_numpy(e.ego_nodes.astype(np.int64))
+    tg = tgraph_from_ref(g)
+    with torch.no_grad():
+        Zt = m64.forward_vectorised(tg, xr, tgraph_from_ego(e), en, gate_u.double(), feat_u.double())["Z"]
+    assert rel(Z.cpu(), Zt) <= 2e-5
+    s2s64, pred64 = s2s.double(), predict.double()
+    Zr = Zt.clone().requires_grad_(True)
+    st = torch.sigmoid(pred64(s2s64(tg, Zr)))
+    assert rel(scores.cpu(), st.detach()) <= 2e-5
+    g_s = torch.randn(B, 10, dtype=torch.float64, generator=torch.Generator().manual_seed(6)) / B
+    (st * g_s).sum().backward()
+    gZ = head.backward(g_s.float().to(DEV))
+    assert rel(gZ.cpu(), Zr.grad) <= 1e-4
+    ref = {"s2s." + n: p.grad for n, p in s2s64.named_parameters()}
+    ref.update({"predict." + n: p.grad for n, p in pred64.named_parameters()})
+    for n, got in head.views(grads=True).items():
+        assert rel(got.cpu(), ref[n]) <= 1e-4, (n, rel(got.cpu(), ref[n]))
