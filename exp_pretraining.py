@@ -13,6 +13,7 @@ import logging
 import os
 import random
 import time
+import zlib
 from pathlib import Path
 
 import torch
@@ -37,9 +38,21 @@ def make_optimizer(model, lr):
 
 def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
     best_epoch, best_model, best_loss = 0, model, 100000000
+    rank, world = _rank_world()
     for epoch in range(1, args.pt_epoches):
+        if hasattr(pre_train_loader1.sampler, "set_epoch"):
+            pre_train_loader1.sampler.set_epoch(epoch)
+        t0 = time.time()
         epoch_train_loss, KL_Loss, contrastive_loss, reconstruction_loss = train_epoch_pre_training(
             model, args, optimizer, device, pre_train_loader1, epoch, 1, batch_size)
+        if world > 1:        # every rank must take the same early-stopping decision: use the mean loss over the ranks
+            import torch.distributed as dist
+            t = torch.tensor([epoch_train_loss], device=device, dtype=torch.float64)
+            dist.all_reduce(t)
+            epoch_train_loss = float(t) / world
+        if rank == 0:
+            n_graphs = len(pre_train_loader1) * batch_size * world
+            print('{"epoch": %d, "graphs_per_s": %.0f, "world": %d}' % (epoch, n_graphs / max(time.time() - t0, 1e-9), world))
         if best_loss >= epoch_train_loss:
             best_model, best_epoch, best_loss = model, epoch, epoch_train_loss
         if epoch - best_epoch > 50:
@@ -82,7 +95,7 @@ def load_graphdataset(dataset_name):
         big, _ = load_shard(path)             # written by scgib_b200.graph.pack_shard from PyG-style (edge_index, x, y)
     else:
         print("[I] %s not found: generating %d synthetic molecules of the %s shape" % (path, args.synthetic, dataset_name))
-        big = synth_batch(hash(dataset_name) % 1000, args.synthetic)
+        big = synth_batch(zlib.crc32(dataset_name.encode()) % 1000, args.synthetic)     # the same molecules in every process
         if args.num_features != big.ndata["x"].shape[1]:
             big.ndata["x"] = torch.cat([big.ndata["x"], torch.rand(big.num_nodes(), args.num_features - 9)], 1)
     gp, ip = big.graph_ptr.tolist(), big.indptr
@@ -91,17 +104,39 @@ def load_graphdataset(dataset_name):
         e0, e1 = int(ip[n0]), int(ip[n1])
         g = BatchedGraph([0, n1 - n0], ip[n0:n1 + 1] - e0, big.indices[e0:e1] - n0, big.ndata["x"][n0:n1])
         samples_all.append((g, torch.zeros(1), None, None))
-    random.shuffle(samples_all)
+    random.Random(0).shuffle(samples_all) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else random.shuffle(samples_all)
     return MoleculeDataset(samples_all, 'pre_training'), args.num_features
+
+
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
 
 
 def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feature3):
     """Three-stage sequential pre-training, reference exp_pretraining.py:81-145."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.manual_seed(2024)                            # identical initial weights on every rank
     model = Mainmodel(args, feature1, hidden_dim=args.dims, num_layers=args.num_layers, num_heads=args.num_heads,
                       k_transition=args.k_transition, encoder=args.encoder).to(device)
     batch_size = args.batch_size
-    loaders = [DataLoader(d.data_all, batch_size=batch_size, shuffle=True, collate_fn=d.collate)
-               for d in (dataset_full1, dataset_full2, dataset_full3)]
+    rank, world = _rank_world()
+    if world > 1:      # data parallelism (torchrun): every rank takes its shard of each epoch; FlatAdam all-reduces the gradients
+        from torch.utils.data.distributed import DistributedSampler
+        loaders = [DataLoader(d.data_all, batch_size=batch_size, collate_fn=d.collate,
+                              sampler=DistributedSampler(d.data_all, num_replicas=world, rank=rank, shuffle=True, drop_last=True))
+                   for d in (dataset_full1, dataset_full2, dataset_full3)]
+    else:
+        loaders = [DataLoader(d.data_all, batch_size=batch_size, shuffle=True, collate_fn=d.collate)
+                   for d in (dataset_full1, dataset_full2, dataset_full3)]
     features = [feature1, feature2, feature3]
     Path(args.output_path).mkdir(parents=True, exist_ok=True)
     if args.pretrained_mode == 1:
@@ -111,15 +146,30 @@ def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feat
         for stage in range(len(args.dataset_list)):
             name = "_".join(args.dataset_list[:stage + 1])
             file_check = args.output_path + f'pre_training_{name}_{tag}'
-            if not os.path.exists(file_check):
+            todo = not os.path.exists(file_check)
+            if world > 1:                                  # every rank takes the same branch (rank 0 writes the files)
+                import torch.distributed as dist
+                flag = torch.tensor([int(todo)], device=device)
+                dist.broadcast(flag, 0)
+                todo = bool(flag.item())
+            if todo:
                 if stage == 0:
-                    torch.save(model, file_check)
+                    if rank == 0:
+                        torch.save(model, file_check)
+                    _barrier(world)
+                if world > 1:
+                    torch.manual_seed(20240 + stage)       # identical initialisation of the new transfer_d / MLP on every rank
                 wrapped = Mainmodel_continue(args, features[stage], hidden_dim=args.dims, num_layers=args.num_layers,
                                              num_heads=args.num_heads, k_transition=args.k_transition, num_classes=1,
                                              cp_filename=prev if stage else file_check, encoder=args.encoder).to(device)
                 optimizer = make_optimizer(wrapped, args.lr)
                 best_model, _ = run_pretraining(wrapped, loaders[stage], optimizer, batch_size, device)
-                torch.save(best_model, file_check)
+                if world > 1:
+                    chk = float(sum(p.detach().double().sum() for p in best_model.parameters()))
+                    print("rank %d stage %d parameter checksum %.10f" % (rank, stage + 1, chk))
+                if rank == 0:
+                    torch.save(best_model, file_check)
+                _barrier(world)
             prev = file_check
             print(f"Finished pre-trained model step {stage + 1}...")
     print(f"\nFinished pretraining models on {str(args.dataset_list)} ...")
@@ -177,6 +227,14 @@ def build_parser():
 
 if __name__ == '__main__':
     args = build_parser().parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:         # torchrun: one process per GPU, --device is replaced by the local rank's GPU
+        from scgib_b200.dist import init_from_env
+        _rank, _local, _world = init_from_env("nccl")
+        args.device = "cuda:%d" % _local
     print(args)
     device = torch.device(args.device)
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()

@@ -1,7 +1,8 @@
 """Optimiser for the drop-in modules: ``torch.optim.Adam(lr, weight_decay)`` (reference exp_pretraining.py:86,112) as
 ONE kernel over the engine's flat parameter / gradient / moment buffers (``scgib_adam_step_f32``) instead of ~10 foreach
 launches over the 61 parameter tensors (0.67 ms -> 0.01 ms per step).  Same ``zero_grad()`` / ``step()`` surface, so the
-reference's training loop is unchanged."""
+reference's training loop is unchanged.  Under ``torch.distributed`` (torchrun, one process per GPU) ``step()`` first
+sum-all-reduces the flat gradient buffer, so the same loop trains data-parallel."""
 from __future__ import annotations
 
 import torch
@@ -52,7 +53,12 @@ class FlatAdam:
             if p.grad is not None:
                 raise RuntimeError("a parameter outside the engine's flat buffer received a gradient; use torch.optim.Adam")
         g = self.param_groups[0]
-        eng.adam_step(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:          # data parallelism: ONE sum all-reduce of the flat gradient buffer, mean applied in the kernel
+                torch.distributed.all_reduce(eng.grads, op=torch.distributed.ReduceOp.SUM)
+        eng.adam_step(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], grad_scale=1.0 / world)
 
     def state_dict(self):
         eng = self.model._bridge.engine
