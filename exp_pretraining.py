@@ -22,7 +22,7 @@ from torch.utils.data import DataLoader
 
 from molecules import MoleculeDataset
 from models import Mainmodel, Mainmodel_continue
-from scgib_b200.graph import BatchedGraph, khop_ego_batch, load_shard
+from scgib_b200.graph import BatchedGraph, DeviceDataset, DeviceLoader, batch as _batch, khop_ego_batch, load_shard
 from scgib_b200.synth import synth_batch
 
 
@@ -129,7 +129,12 @@ def run(i, dataset_full1, feature1, dataset_full2, feature2, dataset_full3, feat
                       k_transition=args.k_transition, encoder=args.encoder).to(device)
     batch_size = args.batch_size
     rank, world = _rank_world()
-    if world > 1:      # data parallelism (torchrun): every rank takes its shard of each epoch; FlatAdam all-reduces the gradients
+    if args.device_loader and device.type == "cuda":
+        # the datasets stay resident in HBM and every mini-batch is assembled on the GPU from its molecule ids (no Python
+        # object per molecule, no collate, no H2D of graph data): the host-side DataLoader tops out far below the kernels
+        loaders = [DeviceLoader(DeviceDataset.from_batched(_batch([smp[0] for smp in d.data_all]), device), batch_size,
+                                shuffle=True, drop_last=world > 1, rank=rank, world=world) for d in (dataset_full1, dataset_full2, dataset_full3)]
+    elif world > 1:    # data parallelism (torchrun): every rank takes its shard of each epoch; FlatAdam all-reduces the gradients
         from torch.utils.data.distributed import DistributedSampler
         loaders = [DataLoader(d.data_all, batch_size=batch_size, collate_fn=d.collate,
                               sampler=DistributedSampler(d.data_all, num_replicas=world, rank=rank, shuffle=True, drop_last=True))
@@ -221,6 +226,7 @@ def build_parser():
     parser.add_argument("--file_name", default="outputs_excels.xlsx", help="file_name dataset")
     # additions of the B200 port (not in the reference)
     parser.add_argument("--gin_layers", type=int, default=4, help="GINConv per encoder (4 in the published models.py; 5 = paper / shipped checkpoint)")
+    parser.add_argument("--device_loader", type=int, default=1, help="1: datasets resident in HBM + GPU-side batch assembly (DeviceLoader); 0: torch DataLoader + collate as in the reference")
     parser.add_argument("--synthetic", type=int, default=2048, help="synthetic molecules per dataset when pts/<name>_csr.pt is absent")
     return parser
 

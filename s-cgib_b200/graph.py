@@ -340,3 +340,48 @@ def pack_shard(molecules, path: Optional[str] = None):
 def load_shard(path: str) -> "tuple[BatchedGraph, torch.Tensor]":
     shard = torch.load(path)
     return BatchedGraph(shard["graph_ptr"], shard["indptr"], shard["indices"], shard["x"]), shard.get("y")
+
+
+class DeviceLoader:
+    """Drop-in for ``DataLoader(dataset, batch_size, shuffle=True, collate_fn=dataset.collate)`` (exp_pretraining.py:283) over
+    a ``DeviceDataset``: iterating yields the reference's 4-tuples ``(batched_graph, labels, subgraphs, logMs)`` with the
+    batch assembled on the GPU from B molecule ids (no Python object per molecule, no collate, no H2D of graph data).
+    ``rank`` / ``world`` shard every epoch's permutation like a ``DistributedSampler(drop_last=True)``."""
+
+    def __init__(self, dataset: DeviceDataset, batch_size: int, shuffle: bool = True, drop_last: bool = False,
+                 labels: Optional[torch.Tensor] = None, rank: int = 0, world: int = 1, seed: int = 0):
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.labels = None if labels is None else labels.to(dataset.device)
+        self.rank, self.world, self.seed, self.epoch = rank, world, seed, 0
+        self.sampler = self                      # ``loader.sampler.set_epoch(e)`` works as with a DistributedSampler
+        self._bufs = [{}, {}]                    # two sets of reusable device buffers (consecutive batches never share one)
+
+    def set_epoch(self, epoch: int):
+        self.epoch = int(epoch)
+
+    def _per_rank(self):
+        n = len(self.dataset)
+        return n // self.world if self.world > 1 else n
+
+    def __len__(self):
+        n = self._per_rank()
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        if self.shuffle:
+            gen = torch.Generator().manual_seed(self.seed + self.epoch)
+            perm = torch.randperm(n, generator=gen)
+        else:
+            perm = torch.arange(n)
+        if self.world > 1:
+            per = n // self.world
+            perm = perm[self.rank * per:(self.rank + 1) * per]
+        ids_dev = perm.to(torch.int32).to(self.dataset.device)
+        for i in range(len(self)):
+            ids = ids_dev[i * self.batch_size:(i + 1) * self.batch_size]
+            if ids.numel() == 0:
+                break
+            g = self.dataset.assemble(ids, out=self._bufs[i & 1])
+            labels = self.labels[ids.long()] if self.labels is not None else torch.zeros(ids.numel(), 1, device=self.dataset.device)
+            yield g, labels, None, None
