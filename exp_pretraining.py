@@ -43,7 +43,9 @@ def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
         if hasattr(pre_train_loader1.sampler, "set_epoch"):
             pre_train_loader1.sampler.set_epoch(epoch)
         t0 = time.time()
-        epoch_train_loss, KL_Loss, contrastive_loss, reconstruction_loss = train_epoch_pre_training(
+        fast = getattr(args, "engine_loop", 0) and isinstance(pre_train_loader1, DeviceLoader) and type(optimizer).__name__ == "FlatAdam"
+        epoch_fn = train_epoch_pre_training_engine if fast else train_epoch_pre_training
+        epoch_train_loss, KL_Loss, contrastive_loss, reconstruction_loss = epoch_fn(
             model, args, optimizer, device, pre_train_loader1, epoch, 1, batch_size)
         if world > 1:        # every rank must take the same early-stopping decision: use the mean loss over the ranks
             import torch.distributed as dist
@@ -59,6 +61,41 @@ def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):
             break
         print("Epoch:%d	|Best_epoch:%d	|Train_loss:%0.4f" % (epoch, best_epoch, epoch_train_loss))
     return best_model, best_epoch
+
+
+def train_epoch_pre_training_engine(model, args, optimizer, device, data_loader, epoch, k_transition, batch_size=16):
+    """The same epoch as ``train_epoch_pre_training`` driven through the engine API (``--engine_loop 1``, the default when
+    the data comes from a ``DeviceLoader`` and the optimiser is ``FlatAdam``): the next batch (ids -> GPU batch assembly ->
+    ego-nets) is prepared on a side stream while the current step runs, forward / backward / Adam are three library calls
+    on the shared flat buffers, and the per-step ``loss.item()`` of the reference loop (exp_pretraining.py:324) is replaced
+    by ONE device-to-host read per epoch.  Same parameters, BatchNorm buffers, Adam state and return values."""
+    model.train()
+    bridge = model._bridge
+    bridge.sync(device)
+    eng = bridge.engine
+    eng.recon_logm_steps = int(model.k_transition) if getattr(model, "recons_type", "adj") == "logM" else 0
+    g = optimizer.param_groups[0]
+    rank, world = _rank_world()
+    acc = torch.zeros(4, device=device, dtype=torch.float64)
+    steps = n_graphs = 0
+    it = data_loader.id_batches()
+    ids = next(it, None)
+    handle = None if ids is None else eng.prefetch_ids(data_loader.dataset, ids, args.k_transition, normalize_x=True)
+    while handle is not None:
+        b = eng.wait_batch(handle)
+        losses = eng.train_step(b, lr=g["lr"], weight_decay=g["weight_decay"], world_size=world)
+        acc += losses.double()
+        steps += 1
+        n_graphs += b.B
+        ids = next(it, None)
+        handle = None if ids is None else eng.prefetch_ids(data_loader.dataset, ids, args.k_transition, normalize_x=True)
+    inner = bridge._bn_modules                                   # nn.BatchNorm1d bookkeeping of the module view
+    for enc in (inner.Encoder1, inner.Encoder2):
+        for bn in enc.batch_norms:
+            bn.num_batches_tracked += steps
+    inner.compressor[1].num_batches_tracked += n_graphs          # one BatchNorm call per graph (models.py:642)
+    kl, con, rec, tot = (acc / max(steps, 1)).tolist()            # the epoch's one host read
+    return tot, torch.tensor(kl), torch.tensor(con), torch.tensor(rec)
 
 
 def train_epoch_pre_training(model, args, optimizer, device, data_loader, epoch, k_transition, batch_size=16):
@@ -226,6 +263,7 @@ def build_parser():
     parser.add_argument("--file_name", default="outputs_excels.xlsx", help="file_name dataset")
     # additions of the B200 port (not in the reference)
     parser.add_argument("--gin_layers", type=int, default=4, help="GINConv per encoder (4 in the published models.py; 5 = paper / shipped checkpoint)")
+    parser.add_argument("--engine_loop", type=int, default=1, help="1: drive the epoch through the engine API (prefetch stream, one host read per epoch); 0: the reference's loop body")
     parser.add_argument("--device_loader", type=int, default=1, help="1: datasets resident in HBM + GPU-side batch assembly (DeviceLoader); 0: torch DataLoader + collate as in the reference")
     parser.add_argument("--synthetic", type=int, default=2048, help="synthetic molecules per dataset when pts/<name>_csr.pt is absent")
     return parser

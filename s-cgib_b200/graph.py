@@ -367,6 +367,25 @@ class DeviceLoader:
         n = self._per_rank()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
+    def id_batches(self):
+        """The epoch's mini-batches as device tensors of molecule ids (what ``__iter__`` assembles one by one)."""
+        ids_dev = self._epoch_ids()
+        for i in range(len(self)):
+            ids = ids_dev[i * self.batch_size:(i + 1) * self.batch_size]
+            if ids.numel():
+                yield ids
+
+    def _epoch_ids(self):
+        n = len(self.dataset)
+        if self.shuffle:
+            perm = torch.randperm(n, generator=torch.Generator().manual_seed(self.seed + self.epoch))
+        else:
+            perm = torch.arange(n)
+        if self.world > 1:
+            per = n // self.world
+            perm = perm[self.rank * per:(self.rank + 1) * per]
+        return perm.to(torch.int32).to(self.dataset.device)
+
     def __iter__(self):
         n = len(self.dataset)
         if self.shuffle:
