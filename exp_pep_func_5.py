@@ -20,7 +20,7 @@ from torch.utils.data import DataLoader
 import exp_pretraining as pre
 from models import Mainmodel, Mainmodel_domainadapt, Mainmodel_finetuning
 from molecules import MoleculeDataset
-from scgib_b200.graph import BatchedGraph
+from scgib_b200.graph import BatchedGraph, DeviceDataset, DeviceLoader, batch as _batch
 from scgib_b200.synth import synth_batch
 from train_pep_func import evaluate_network, train_epoch_domainadaptation, train_epoch_graph_classification
 
@@ -93,10 +93,18 @@ def run(i, dataset_full, num_features, num_classes):
     """reference exp_pep_func_5.py:96-160."""
     batch_size = args.batch_size
     collate = dataset_full.collate
-    train_loader = DataLoader(dataset_full.train, batch_size=batch_size, shuffle=True, collate_fn=collate)
-    val_loader = DataLoader(dataset_full.val, batch_size=batch_size, shuffle=False, collate_fn=collate)
-    test_loader = DataLoader(dataset_full.test, batch_size=batch_size, shuffle=False, collate_fn=collate)
-    pre_train_loader = DataLoader(dataset_full.data_all, batch_size=batch_size, shuffle=True, collate_fn=collate)
+    if args.device_loader and device.type == "cuda":
+        # every split resident in HBM, mini-batches assembled on the GPU from molecule ids (scgib_b200.graph.DeviceLoader)
+        def dev_loader(samples, shuffle):
+            ds = DeviceDataset.from_batched(_batch([smp[0] for smp in samples]), device)
+            return DeviceLoader(ds, batch_size, shuffle=shuffle, labels=torch.stack([torch.as_tensor(smp[1]) for smp in samples]))
+        train_loader, val_loader, test_loader = dev_loader(dataset_full.train, True), dev_loader(dataset_full.val, False), dev_loader(dataset_full.test, False)
+        pre_train_loader = dev_loader(dataset_full.data_all, True)
+    else:
+        train_loader = DataLoader(dataset_full.train, batch_size=batch_size, shuffle=True, collate_fn=collate)
+        val_loader = DataLoader(dataset_full.val, batch_size=batch_size, shuffle=False, collate_fn=collate)
+        test_loader = DataLoader(dataset_full.test, batch_size=batch_size, shuffle=False, collate_fn=collate)
+        pre_train_loader = DataLoader(dataset_full.data_all, batch_size=batch_size, shuffle=True, collate_fn=collate)
     tag = f'{args.encoder}_{args.dims}_{args.num_layers}_{args.k_transition}'
     file_name_cpt = args.output_path + f'{args.dataset}_{tag}.pt'
     os.makedirs(args.output_path, exist_ok=True)
@@ -172,6 +180,8 @@ def build_parser():
     parser.add_argument("--file_name", default="outputs_excels.xlsx", help="file_name dataset")
     # additions of the B200 port (not in the reference)
     parser.add_argument("--gin_layers", type=int, default=4, help="GINConv per encoder (4 in the published models.py)")
+    parser.add_argument("--device_loader", type=int, default=1, help="1: splits resident in HBM + GPU-side batch assembly; 0: torch DataLoader + collate")
+    parser.add_argument("--engine_loop", type=int, default=1, help="pre-training stage: epoch through the engine API (see exp_pretraining.py)")
     parser.add_argument("--synthetic", type=int, default=512, help="synthetic molecules when pts/<dataset>_csr.pt is absent")
     return parser
 
