@@ -177,6 +177,55 @@ def cpu_reference_run(steps, warmup, batch=128, k=1):
                       "recon, %.1f s wall" % (steps, batch, dt)}, dt / steps * 1e3
 
 
+def torch_gpu_reference_run(dev, k=1):
+    """The "reference torch path on the same GPU" (north_star): the oracle's restatement of the reference run with plain
+    torch on the B200 - `faithful` = what the reference really executes (per-graph Python loops, dense N x N recon) at its
+    default batch 128; `vectorised` = a strong torch baseline the reference does not have (segment ops + Gram identity)
+    at B = 4096.  Forward + backward + torch.optim.Adam, CUDA events, ego-nets prepared outside the timed region (the
+    reference loads them from disk)."""
+    import numpy as np
+    from oracle.graph_ref import ego_batch_ref, synth_batch_fast
+    from oracle.scgib_oracle import OracleMainmodel, normalize_rows, tgraph_from_ego, tgraph_from_ref
+    out = {}
+    for name, B, steps in (("faithful_b128", 128, 10), ("vectorised_b4096", 4096, 20)):
+        torch.manual_seed(0)
+        model = OracleMainmodel(9).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-5)
+        g = synth_batch_fast(100, B)
+        e = ego_batch_ref(g, k)
+        x = normalize_rows(torch.from_numpy(g.x)).to(dev)
+        en = torch.from_numpy(e.ego_nodes.astype(np.int64)).to(dev)
+        tg, te = tgraph_from_ref(g).to(dev), tgraph_from_ego(e).to(dev)
+        xs = x[en]
+
+        def step():
+            opt.zero_grad()
+            if name.startswith("faithful"):
+                o = model.forward_faithful(tg, x, te, xs)
+            else:
+                o = model.forward_vectorised(tg, x, te, en, torch.rand(x.shape[0], device=dev), torch.rand(x.shape[0], 64, device=dev))
+            loss = o["KL"] + o["recon"] + o["contrastive"]
+            loss.backward()
+            opt.step()
+            return loss.detach().item()          # the reference reads the loss every step (exp_pretraining.py:324)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps}
+        del model, opt
+        torch.cuda.empty_cache()
+    out["note"] = ("plain PyTorch (the oracle's restatement of the reference's math; DGL itself is not installable here) on the "
+                   "same B200: the north_star's 'reference torch path on the same GPU'")
+    return out
+
+
 def run_reference(args, rank, emit):
     if rank != 0:
         return
@@ -599,6 +648,9 @@ def main():
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
+            del eng, dm, dopt
+            torch.cuda.empty_cache()
+            line["torch_gpu_baseline"] = torch_gpu_reference_run(dev, k=args.k)
             line["cpu_baseline"], _ = cpu_reference_run(None, 3, batch=128, k=args.k)
         emit(line)
     if world > 1:

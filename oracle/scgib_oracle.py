@@ -51,7 +51,11 @@ class TGraph:
 
     def seg_ids(self):
         n = self.batch_num_nodes()
-        return torch.repeat_interleave(torch.arange(n.numel()), n)
+        return torch.repeat_interleave(torch.arange(n.numel(), device=n.device), n)
+
+    def to(self, device):
+        """The same graph on another device (bench.py times the restatement with torch on the GPU as well)."""
+        return TGraph(*[t.to(device) for t in (self.seg_ptr, self.indptr, self.indices, self.src, self.dst)])
 
 
 def tgraph_from_ref(g: RefGraph) -> TGraph:
@@ -70,7 +74,7 @@ def tgraph_from_ego(e: RefEgoBatch) -> TGraph:
 
 def sum_nodes(g: TGraph, h: torch.Tensor) -> torch.Tensor:
     """dgl.sum_nodes: segment sum by batch_num_nodes (models.py:716, 725, 733, 684)."""
-    out = torch.zeros(g.seg_ptr.numel() - 1, h.shape[1], dtype=h.dtype)
+    out = torch.zeros(g.seg_ptr.numel() - 1, h.shape[1], dtype=h.dtype, device=h.device)
     return out.index_add(0, g.seg_ids(), h)
 
 
@@ -161,9 +165,9 @@ class OracleMainmodel(nn.Module):
         """models.py:595-604.  ``gate_u`` [n,1] replaces torch.rand(p.size())."""
         p = self.compressor(graph_features)
         bias = 0.0 + 0.0001
-        u = torch.rand(p.size()) if gate_u is None else gate_u.reshape(p.size()).to(p.dtype)
+        u = torch.rand(p.size()) if gate_u is None else gate_u.reshape(p.size()).to(p.dtype)     # CPU draw, as models.py:599
         eps = (bias - (1 - bias)) * u + (1 - bias)
-        gate_inputs = (torch.log(eps) - torch.log(1 - eps)).to(p.dtype)
+        gate_inputs = (torch.log(eps) - torch.log(1 - eps)).to(p.dtype).to(p.device)             # models.py:601
         gate_inputs = (gate_inputs + p) / 1.0
         gate_inputs = torch.sigmoid(gate_inputs).squeeze()
         return gate_inputs, p
@@ -171,9 +175,9 @@ class OracleMainmodel(nn.Module):
     def compression(self, graph_features, nodes_list, gate_u=None, feat_u=None):
         """models.py:631-660, loop-for-loop (incl. the KL overwrite of models.py:659)."""
         epsilon = 0.0000001
-        noisy_all = torch.tensor((), dtype=graph_features.dtype)
-        p_all = torch.tensor((), dtype=graph_features.dtype)
-        KL_all = torch.tensor((), dtype=graph_features.dtype)
+        noisy_all = torch.tensor((), dtype=graph_features.dtype, device=graph_features.device)
+        p_all = torch.tensor((), dtype=graph_features.dtype, device=graph_features.device)
+        KL_all = torch.tensor((), dtype=graph_features.dtype, device=graph_features.device)
         split = torch.split(graph_features, tuple(nodes_list))
         off = 0
         for i in range(len(nodes_list)):
@@ -187,7 +191,7 @@ class OracleMainmodel(nn.Module):
             std, mean = torch.std_mean(static, dim=0)
             noisy_mean = lambda_pos * features + lambda_neg * mean
             noisy_std = lambda_neg * std
-            fu = torch.rand_like(noisy_mean) if feat_u is None else feat_u[off:off + n].to(noisy_mean.dtype)
+            fu = torch.rand_like(noisy_mean) if feat_u is None else feat_u[off:off + n].to(noisy_mean.dtype).to(noisy_mean.device)
             noisy = noisy_mean + fu * noisy_std
             noisy_all = torch.cat((noisy_all, noisy), 0)
             p_all = torch.cat((p_all, p), 0)
@@ -206,7 +210,7 @@ class OracleMainmodel(nn.Module):
         num_nodes = z1.size(0)
         num_batches = (num_nodes - 1) // batch_size + 1
         f = lambda x: torch.exp(x / 1)
-        indices = torch.arange(0, num_nodes)
+        indices = torch.arange(0, num_nodes, device=z1.device)
         losses = []
         for i in range(num_batches):
             mask = indices[i * batch_size:(i + 1) * batch_size]
@@ -220,7 +224,7 @@ class OracleMainmodel(nn.Module):
     def loss_recon_adj(self, interaction_map, g: TGraph):
         """models.py:762-768: dense N x N over the whole batched graph."""
         row_num = interaction_map.shape[0]
-        adj = torch.zeros(row_num, row_num, dtype=interaction_map.dtype)
+        adj = torch.zeros(row_num, row_num, dtype=interaction_map.dtype, device=interaction_map.device)
         adj[g.src, g.dst] = 1.0
         recon = torch.mm(interaction_map, interaction_map.t())
         return torch.sum((recon - adj) ** 2) / row_num
@@ -234,7 +238,7 @@ class OracleMainmodel(nn.Module):
         noisy, p, KL_tensor = self.compression(graph_features, nodes_list, gate_u, feat_u)
         sub_readout = sum_nodes(eg, subgraphs_features)
         noisy_readout = sum_nodes(g, noisy)
-        subgs_att = torch.tensor((), dtype=noisy.dtype)
+        subgs_att = torch.tensor((), dtype=noisy.dtype, device=noisy.device)
         split = torch.split(sub_readout, tuple(nodes_list))
         for i in range(len(split)):
             cp = noisy_readout[i].repeat(nodes_list[i], 1)
@@ -276,14 +280,15 @@ class OracleMainmodel(nn.Module):
         # compressor with per-graph BatchNorm (models.py:589-596 applied per split, :642)
         lin1, bn, _, lin2 = self.compressor
         q = lin1(H)
-        qm = torch.zeros(nB, q.shape[1], dtype=dt).index_add(0, seg, q) / n[:, None]
+        dv = x_norm.device
+        qm = torch.zeros(nB, q.shape[1], dtype=dt, device=dv).index_add(0, seg, q) / n[:, None]
         qc = q - qm[seg]
-        qv = torch.zeros(nB, q.shape[1], dtype=dt).index_add(0, seg, qc * qc) / n[:, None]
+        qv = torch.zeros(nB, q.shape[1], dtype=dt, device=dv).index_add(0, seg, qc * qc) / n[:, None]
         qh = qc / torch.sqrt(qv[seg] + bn.eps)
         if self.training:
             # B sequential EMA updates (one per graph, graph order) in closed form: r <- 0.9 r + 0.1 stat_i
             with torch.no_grad():
-                w = 0.1 * 0.9 ** torch.arange(nB - 1, -1, -1, dtype=dt)
+                w = 0.1 * 0.9 ** torch.arange(nB - 1, -1, -1, dtype=dt, device=dv)
                 bn.running_mean.mul_(0.9 ** nB).add_((w[:, None] * qm).sum(0))
                 bn.running_var.mul_(0.9 ** nB).add_((w[:, None] * qv * (n / (n - 1))[:, None]).sum(0))
                 bn.num_batches_tracked += nB
@@ -291,8 +296,8 @@ class OracleMainmodel(nn.Module):
         eps = (0.0001 - (1 - 0.0001)) * gate_u.to(dt) + (1 - 0.0001)
         lam = torch.sigmoid((torch.log(eps) - torch.log(1 - eps)).to(dt)[:, None] + p)
         Hd = H.detach()
-        mu = torch.zeros(nB, H.shape[1], dtype=dt).index_add(0, seg, Hd) / n[:, None]
-        var = torch.zeros(nB, H.shape[1], dtype=dt).index_add(0, seg, (Hd - mu[seg]) ** 2) / (n[:, None] - 1)
+        mu = torch.zeros(nB, H.shape[1], dtype=dt, device=dv).index_add(0, seg, Hd) / n[:, None]
+        var = torch.zeros(nB, H.shape[1], dtype=dt, device=dv).index_add(0, seg, (Hd - mu[seg]) ** 2) / (n[:, None] - 1)
         sd = torch.sqrt(var)
         m = lam * H + (1 - lam) * mu[seg]
         s = (1 - lam) * sd[seg]
@@ -306,9 +311,9 @@ class OracleMainmodel(nn.Module):
         C = sum_nodes(eg, S)
         core = sum_nodes(g, noisy)
         logit = self.attn_layer(torch.cat((core[seg], C), -1)).squeeze(-1)
-        mx = torch.full((nB,), -float("inf"), dtype=dt).scatter_reduce(0, seg, logit, "amax")
+        mx = torch.full((nB,), -float("inf"), dtype=dt, device=dv).scatter_reduce(0, seg, logit, "amax")
         ex = torch.exp(logit - mx[seg])
-        den = torch.zeros(nB, dtype=dt).index_add(0, seg, ex)
+        den = torch.zeros(nB, dtype=dt, device=dv).index_add(0, seg, ex)
         alpha = ex / den[seg]
         imap = torch.cat((noisy, C * alpha[:, None]), -1)
         Z = self.MLP(imap)
