@@ -37,10 +37,11 @@ extern "C" {
 enum {
   SCGIB_OK = 0,
   SCGIB_E_NULL = -1,      /* required pointer is NULL */
-  SCGIB_E_SHAPE = -2,     /* unsupported dimension (hidden must be 64, d_transfer 32, 1 <= L <= 8, F <= 32) */
+  SCGIB_E_SHAPE = -2,     /* unsupported dimension (hidden must be 64 or 128, d_transfer 32, 1 <= L <= 8, F <= 32) */
   SCGIB_E_ALIGN = -3,     /* pointer not 16-byte aligned */
   SCGIB_E_WORKSPACE = -4, /* workspace too small */
   SCGIB_E_RANGE = -5,     /* size out of range (e.g. k < 1, graph with < 2 nodes) */
+  SCGIB_E_ABI = -6,       /* ScgibBatch.struct_size != sizeof(ScgibBatch): caller built against another header */
 };
 
 SCGIB_API int scgib_version(void);
@@ -56,9 +57,14 @@ SCGIB_API int scgib_num_sms(void);
 typedef struct ScgibDims {
   int32_t in_dim;     /* F: raw feature width (9 PCQM4Mv2 / mol-PCBA, 11 QM9)  exp_pretraining.py:219 */
   int32_t d_transfer; /* 32                                                      exp_pretraining.py:378 */
-  int32_t hidden;     /* 64                                                      exp_pretraining.py:390 */
+  int32_t hidden;     /* 64 or 128 (--dims)                                      exp_pretraining.py:390 */
   int32_t gin_layers; /* L: GINConv per encoder (4 in models.py:57-58)                               */
+  int32_t act_dtype;  /* SCGIB_ACT_F32 (reference precision, 1e-5) or SCGIB_ACT_BF16: the GIN encoders keep their
+                         activations (t, a, r, y and the layer gradients) in bf16 and run their MLPs as single-pass
+                         bf16 tensor-core GEMMs with fp32 accumulation and fp32 / fp64 statistics (2e-2 tolerance);
+                         parameters, gradients, optimiser state and everything the caller sees stay fp32 */
 } ScgibDims;
+enum { SCGIB_ACT_F32 = 0, SCGIB_ACT_BF16 = 1 };
 
 /* Slots of the flat parameter buffer, in layout order.  Per-encoder/per-layer slots are
  * addressed as SCGIB_P_ENC + (enc * L + layer) * SCGIB_ENC_SLOTS + {W1,B1,W2,B2,GAMMA,BETA}. */
@@ -90,6 +96,7 @@ SCGIB_API int32_t scgib_param_slots(const ScgibDims* d);
 /* One mini-batch: the batched parent graph (dgl.batch, molecules.py:359) and the flattened
  * batch of one k-hop ego-net per node (exp_pretraining.py:308-309), both as symmetric CSR. */
 typedef struct ScgibBatch {
+  int32_t struct_size;         /* = sizeof(ScgibBatch) (scgib_batch_abi_size()); checked on entry: SCGIB_E_ABI      */
   int32_t B, N, E;             /* graphs, nodes, directed edges of the parent batch            */
   int32_t Ns, Es;              /* rows / directed edges of the ego batch                        */
   const int32_t* graph_ptr;    /* [B+1] node offset of each graph   (batch_num_nodes)           */
@@ -113,6 +120,9 @@ typedef struct ScgibBatch {
                                   (models.py:770-782) with the k-step log transition matrices of util.py:60-91 computed
                                   on the fly from the CSR (k = --k_transition, <= 8); no pts/*_M_khop_k.pt files */
 } ScgibBatch;
+
+/* sizeof(ScgibBatch) of the library build: a binding fills ScgibBatch.struct_size with its own idea of the size. */
+SCGIB_API int32_t scgib_batch_abi_size(void);
 
 /* ------------------------------------------------------------------------------------------
  * k-hop ego-network extraction  (replaces dgl.khop_in_subgraph per node + dgl.batch:
@@ -307,29 +317,6 @@ SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int
  * "alpha", "lam", "y<enc>_<layer>", "gH", ...), -1 if unknown.  Tests compare intermediates with the oracle. */
 SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,
                                                   int32_t Es, const char* name);
-
-/* GIN forward implementation: 0 = FP32 FFMA register tiles (gin_kernels.cu), 1 = tcgen05 3xTF32 with 64-row tiles
- * (gin_tc.cu), 2 / 3 = warp-specialised persistent tcgen05 3xTF32 kernel with 8 / 16 producer warps (gin_tc2.cu),
- * 4 = the same pipeline with the gather served from a shared-memory row window (gin_tc3.cu, the default).  Also selectable with the environment variable SCGIB_TC; mode < 0 restores the default. */
-SCGIB_API void scgib_set_tensor_cores(int mode);
-/* GIN backward (BN backward + the four MLP gradient GEMMs): 1 = tcgen05 3xTF32 kernel with 128-row tiles (gin_bwd_tc.cu,
- * default), 2 = the variant with double-buffered 64-row tiles and M-stacked weight-gradient operands (gin_bwd_tc2.cu; same
- * speed on B200, kept for comparison), 0 = FP32 FFMA register tiles; environment variable SCGIB_TC_BWD; mode < 0 restores
- * the default. */
-SCGIB_API void scgib_set_tensor_cores_bwd(int mode);
-/* Experiments only: per-tile role timestamps of the last gin_tc2 forward launch run with SCGIB_DBG bit 1024
- * ([cta < 160][tile < 16][event < 12] SM clocks) copied to host memory. */
-SCGIB_API int scgib_debug_tc2_trace(long long* host_out, int n);
-/* The same for the last gin_bwd_tc launch (SCGIB_DBG bit 2048). */
-SCGIB_API int scgib_debug_bwd_trace(long long* host_out, int n);
-
-/* Probe of the tcgen05 tile-GEMM primitives (tests only): one 3xTF32 GEMM of fp32 tiles A [M,64], B [64 or M,64] in
- * operand-major mode 0/1/2 (umma_test.cu); out[128][64] = dump of all TMEM lanes. */
-SCGIB_API int scgib_debug_umma(const float* A, const float* B, float* out, int32_t M, int32_t mode, void* stream);
-/* Runtime-parametrised variant (tests only; umma_probe2.cu): params = 23 int32 {M, N, ksteps, split, a_fmt, b_fmt,
- * a_mn, b_mn, a_{lbo,sbo,ltype,div,adv_lo,adv_hi}, b_{...}, RA, RB, reps}; a_fmt 2 = A operand in tensor memory;
- * out has 128*64 + 1 floats (the last one = SM cycles of the MMA sequence issued `reps` times). */
-SCGIB_API int scgib_debug_umma2(const float* A, const float* B, float* out, const int32_t* params, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data parallelism: gradient all-reduce fused with Adam over NVLink peer memory (peer_kernels.cu).  Replaces

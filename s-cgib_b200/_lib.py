@@ -11,11 +11,12 @@ LIB_PATH = os.path.join(_HERE, "lib", "libscgib.so")
 
 
 class Dims(ctypes.Structure):
-    _fields_ = [("in_dim", c_int32), ("d_transfer", c_int32), ("hidden", c_int32), ("gin_layers", c_int32)]
+    _fields_ = [("in_dim", c_int32), ("d_transfer", c_int32), ("hidden", c_int32), ("gin_layers", c_int32),
+                ("act_dtype", c_int32)]          # ACT_F32 / ACT_BF16
 
 
 class Batch(ctypes.Structure):
-    _fields_ = [("B", c_int32), ("N", c_int32), ("E", c_int32), ("Ns", c_int32), ("Es", c_int32),
+    _fields_ = [("struct_size", c_int32), ("B", c_int32), ("N", c_int32), ("E", c_int32), ("Ns", c_int32), ("Es", c_int32),
                 ("graph_ptr", c_void_p), ("indptr", c_void_p), ("indices", c_void_p),
                 ("ego_ptr", c_void_p), ("ego_nodes", c_void_p), ("ego_seed", c_void_p),
                 ("sub_indptr", c_void_p), ("sub_indices", c_void_p),
@@ -23,6 +24,7 @@ class Batch(ctypes.Structure):
                 ("t_override", c_void_p), ("eval_mode", c_int32), ("recon_logm_steps", c_int32)]
 
 
+ACT_F32, ACT_BF16 = 0, 1
 # slot enums of include/scgib.h
 ENC_W1, ENC_B1, ENC_W2, ENC_B2, ENC_GAMMA, ENC_BETA, ENC_SLOTS = range(7)
 (P_HEAD_W1, P_HEAD_B1, P_HEAD_W2, P_HEAD_B2, P_COMP_W1, P_COMP_B1, P_COMP_GAMMA, P_COMP_BETA, P_COMP_W2,
@@ -34,6 +36,7 @@ _SIGNATURES = {
     "scgib_version": (c_int, []),
     "scgib_error_string": (c_char_p, [c_int]),
     "scgib_num_sms": (c_int, []),
+    "scgib_batch_abi_size": (c_int32, []),
     "scgib_param_layout": (c_int64, [POINTER(Dims), POINTER(c_int64), POINTER(c_int64)]),
     "scgib_param_slots": (c_int32, [POINTER(Dims)]),
     "scgib_ego_workspace_bytes": (c_size_t, [c_int32]),
@@ -87,18 +90,19 @@ _SIGNATURES = {
     "scgib_contrastive_f32": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
-    "scgib_set_tensor_cores": (None, [c_int]),
-    "scgib_set_tensor_cores_bwd": (None, [c_int]),
-    "scgib_debug_tc2_trace": (c_int, [c_void_p, c_int]),
-    "scgib_debug_bwd_trace": (c_int, [c_void_p, c_int]),
-    "scgib_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
-    "scgib_debug_umma2": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_void_p]),
     "scgib_profile_enable": (None, [c_int]),
     "scgib_profile_count": (c_int, []),
     "scgib_profile_get": (c_int, [c_int, POINTER(c_char_p), POINTER(c_float)]),
     "scgib_pretrain_workspace_offset": (c_int64, [POINTER(Dims), c_int32, c_int32, c_int32, c_int32, c_int32, c_char_p]),
 }
-EXPORTS = tuple(_SIGNATURES)
+EXPORTS = tuple(_SIGNATURES)          # exactly the entry points include/scgib.h declares (tests/test_abi.py)
+# csrc/scgib_private.h: implementation selection / role-timeline dumps (tests and experiments only)
+_PRIVATE_SIGNATURES = {
+    "scgib_set_tensor_cores": (None, [c_int]),
+    "scgib_set_tensor_cores_bwd": (None, [c_int]),
+    "scgib_debug_tc2_trace": (c_int, [c_void_p, c_int]),
+    "scgib_debug_bwd_trace": (c_int, [c_void_p, c_int]),
+}
 
 _lib = None
 
@@ -113,7 +117,7 @@ def load():
             "libscgib.so not found at %s - build it with `python s-cgib_b200/build.py` "
             "(or __graft_entry__.build()).  scgib_b200 has no CPU/PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in _SIGNATURES.items():
+    for name, (res, args) in list(_SIGNATURES.items()) + list(_PRIVATE_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

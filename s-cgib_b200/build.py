@@ -13,8 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libscgib.so")
-SOURCES = ["api.cu", "graph_kernels.cu", "gin_kernels.cu", "head_kernels.cu", "loss_kernels.cu", "finetune_kernels.cu", "logm_kernels.cu", "peer_kernels.cu", "umma_test.cu", "gin_tc.cu", "gin_tc2.cu", "gin_tc3.cu", "gin_bwd_tc.cu", "gin_bwd_tc2.cu", "contrastive_tc.cu", "umma_probe2.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "umma.cuh", os.path.join("..", "..", "include", "scgib.h")]
+SOURCES = ["api.cu", "graph_kernels.cu", "gin_kernels.cu", "head_kernels.cu", "loss_kernels.cu", "finetune_kernels.cu",
+           "logm_kernels.cu", "peer_kernels.cu", "gin_tc3.cu", "gin_bwd_tc2.cu", "contrastive_tc.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "umma.cuh", "scgib_private.h", os.path.join("..", "..", "include", "scgib.h")]
+# hardware probes of the tcgen05 operand formats: test infrastructure, NOT linked into the product library
+PROBE_DIR = os.path.join(os.path.dirname(HERE), "tests", "csrc")
+PROBE_LIB = os.path.join(PROBE_DIR, "libscgib_probe.so")
+PROBE_SOURCES = ["umma_test.cu", "umma_probe2.cu", "umma_probe_bf16.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -57,5 +62,23 @@ def build(verbose=False, force=False):
     return LIB
 
 
+def build_probes(force=False):
+    """tests/csrc/libscgib_probe.so (sm_100a); returns its path."""
+    srcs = [os.path.join(PROBE_DIR, f) for f in PROBE_SOURCES if os.path.exists(os.path.join(PROBE_DIR, f))]
+    h = hashlib.sha256()
+    for f in srcs + [os.path.join(CSRC, "umma.cuh")]:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    stamp = os.path.join(PROBE_DIR, "libscgib_probe.stamp")
+    if not force and os.path.exists(PROBE_LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return PROBE_LIB
+    cmd = [NVCC] + FLAGS + ["-I", CSRC, "-I", os.path.join(os.path.dirname(HERE), "include"), "-shared", "-o", PROBE_LIB] + srcs + ["-lcudart"]
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as fh:
+        fh.write(h.hexdigest())
+    return PROBE_LIB
+
+
 if __name__ == "__main__":
     print(build(verbose="--verbose" in sys.argv, force=True))
+    print(build_probes(force=True))

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include "kernels.cuh"
 #include "../../include/scgib.h"
+#include "scgib_private.h"
 
 namespace scgib {
 
@@ -18,22 +19,21 @@ int num_sms() {
   return n;
 }
 
+// SCGIB_TC / SCGIB_TC_BWD: 1 (default) = the tcgen05 kernels (gin_tc3.cu / gin_bwd_tc2.cu), 0 = the FP32 FFMA
+// register-tile kernels of gin_kernels.cu (the cross-check implementation)
 static int g_use_tc = -1;
 int tensor_core_mode() {
-  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 4; }   // default: gin_tc3.cu
+  if (g_use_tc < 0) { const char* e = getenv("SCGIB_TC"); g_use_tc = (e && e[0] == '0') ? 0 : 1; }
   return g_use_tc;
 }
 static int g_bwd_tc = -1;
 int bwd_tensor_core_mode() {
-  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+  if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
   return g_bwd_tc;
 }
 static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
-  const int m = tensor_core_mode();
-  if (m == 0) launch_gin_fwd(a, kin, s);
-  else if (m == 1) launch_gin_fwd_tc(a, kin, s);
-  else if (m == 4) launch_gin_fwd_tc3(a, kin, s);
-  else launch_gin_fwd_tc2(a, kin, m - 1, s);
+  if (tensor_core_mode() == 0) launch_gin_fwd(a, kin, s);
+  else launch_gin_fwd_tc3(a, kin, s);
 }
 
 // contrastive similarity blocks on tcgen05 (default on; SCGIB_CON_FFMA=1 selects the FFMA tiles)
@@ -209,6 +209,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
 
 static int check_batch(const ScgibBatch* b) {
   if (!b) return SCGIB_E_NULL;
+  if (b->struct_size != (int32_t)sizeof(ScgibBatch)) return SCGIB_E_ABI;
   if (b->B < 1 || b->N < 2 || b->Ns < b->N || b->E < 0 || b->Es < 0) return SCGIB_E_RANGE;
   if (!b->graph_ptr || !b->indptr || !b->ego_ptr || !b->ego_nodes || !b->ego_seed || !b->sub_indptr ||
       (!b->x && !b->t_override) || !b->gate_u || !b->feat_u)
@@ -233,11 +234,13 @@ extern "C" SCGIB_API const char* scgib_error_string(int code) {
     case SCGIB_E_ALIGN: return "pointer not 16-byte aligned";
     case SCGIB_E_WORKSPACE: return "workspace too small";
     case SCGIB_E_RANGE: return "size out of range";
+    case SCGIB_E_ABI: return "ScgibBatch.struct_size does not match this library (binding built against another scgib.h)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown scgib error";
   }
 }
 
 extern "C" SCGIB_API int scgib_num_sms(void) { return num_sms(); }
+extern "C" SCGIB_API int32_t scgib_batch_abi_size(void) { return (int32_t)sizeof(ScgibBatch); }
 
 extern "C" SCGIB_API int32_t scgib_param_slots(const ScgibDims* d) {
   if (!dims_ok(d)) return SCGIB_E_SHAPE;
@@ -319,16 +322,11 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       a.running = (bn_running && !eval) ? bn_running + (size_t)(e * L + l) * 2 * HID : nullptr;
       a.reverse = (l & 1) && fwd_alternate();
     }
-    const int kin = l == 0 ? DTR : HID, m = tensor_core_mode();
-    if (m == 4) {
+    const int kin = l == 0 ? DTR : HID;
+    if (tensor_core_mode() != 0) {
       PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
-    } else if (m >= 2) {
-      PROF("gin_fwd_tc2.enc1+2", launch_gin_fwd_tc2_pair(ga[0], ga[1], kin, m - 1, s));
     } else {
-      for (int e = 0; e < 2; ++e) {
-        if (m == 1) PROF(e == 0 ? "gin_fwd_tc64.enc1" : "gin_fwd_tc64.enc2", launch_gin_fwd_tc(ga[e], kin, s));
-        else PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
-      }
+      for (int e = 0; e < 2; ++e) PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
     }
     if (eval)
       for (int e = 0; e < 2; ++e)
@@ -464,10 +462,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m[h].off_W1 = lo.off[SCGIB_P_HEAD_W1] + (int64_t)h * HID * HID; m[h].off_b1 = lo.off[SCGIB_P_HEAD_B1];
       m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
     }
-    if (bwd_tensor_core_mode() == 2)
-      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
-    else
-      PROF("head_bwd_tc128", launch_gin_bwd_main_tc_pair(m[0], m[1], HID, GP, s));
+    PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
   } else {
     HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
                   params + lo.off[SCGIB_P_HEAD_W2], w.gI, w.ppart, lo.total,
@@ -521,10 +516,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     }
     PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], s));
     if (pair_main) {
-      if (bwd_tensor_core_mode() == 2)
-        PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
-      else
-        PROF("gin_bwd_main_tc128.enc1+2", launch_gin_bwd_main_tc_pair(ma[0], ma[1], kin, GP, s));
+      PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
     } else {
       PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, GP, s));
       PROF("gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma[1], kin, GP, s));
@@ -794,9 +786,7 @@ extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int3
   GinBwdMainArgs m;
   m.g_o = w.g_o; m.y = y; m.r = r; m.a = a; m.bn = bn; m.cvec = w.cvec; m.W1 = W1; m.W2 = W2; m.V = V; m.g_a = g_a;
   m.part = w.ppart; m.pstride = w.pstride; m.off_W1 = w.off[0]; m.off_b1 = w.off[1]; m.off_W2 = w.off[2]; m.off_b2 = w.off[3];
-  const int mode = bwd_tensor_core_mode();
-  if (mode == 2) launch_gin_bwd_main_tc2(m, kin, GP, s);
-  else if (mode == 1) launch_gin_bwd_main_tc(m, kin, GP, s);
+  if (bwd_tensor_core_mode() != 0) launch_gin_bwd_main_tc2(m, kin, GP, s);
   else launch_gin_bwd_main(m, kin, GP, s);
   // per-CTA partials -> the four gradient tensors (fixed order)
   float* outs[4] = {dW1, db1, dW2, db2};
@@ -925,6 +915,6 @@ extern "C" SCGIB_API int scgib_profile_get(int i, const char** name, float* ms) 
   return (int)cudaEventElapsedTime(ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]);
 }
 
-// Select the GIN forward implementation: 1 = tcgen05 3xTF32 tensor-core kernel (gin_tc.cu), 0 = FP32 FFMA kernel.
-extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int mode) { g_bwd_tc = (mode >= 0 && mode <= 2) ? mode : -1; }
-extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode >= 0 && mode <= 4) ? mode : -1; }   // < 0: back to the default
+// scgib_private.h: select the GIN implementation (1 = tcgen05, 0 = FP32 FFMA cross-check; < 0: back to the default)
+extern "C" SCGIB_API void scgib_set_tensor_cores_bwd(int mode) { g_bwd_tc = (mode == 0 || mode == 1) ? mode : -1; }
+extern "C" SCGIB_API void scgib_set_tensor_cores(int mode) { g_use_tc = (mode == 0 || mode == 1) ? mode : -1; }

@@ -41,13 +41,9 @@ struct GinFwdArgs {
 struct GinFwdPair { GinFwdArgs a[2]; int split; };
 int gin_fwd_grid(int V);
 void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
-int gin_fwd_tc_tiles(int V);
-void launch_gin_fwd_tc(const GinFwdArgs& a, int kin, cudaStream_t s);     // tcgen05 3xTF32 (gin_tc.cu)
-void launch_gin_fwd_tc2(const GinFwdArgs& a, int kin, int variant, cudaStream_t s);  // warp-specialised tcgen05 (gin_tc2.cu)
-void launch_gin_fwd_tc2_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, int variant, cudaStream_t s);
-void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // shared-memory window gather (gin_tc3.cu)
+void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // tcgen05 3xTF32, shared-memory window gather (gin_tc3.cu)
 void launch_gin_fwd_tc3_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, cudaStream_t s);
-int tensor_core_mode();                                                   // SCGIB_TC: 0 FFMA, 1 gin_tc.cu, 2/3 gin_tc2.cu (8/16 producer warps), 4 gin_tc3.cu
+int tensor_core_mode();                                                   // SCGIB_TC: 1 gin_tc3.cu (default), 0 FFMA cross-check
 inline bool use_tensor_cores() { return tensor_core_mode() != 0; }
 
 struct GinBwdPreArgs {
@@ -82,11 +78,9 @@ struct GinBwdMainArgs {
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
 struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; int reverse = 0; };
-void launch_gin_bwd_main_tc(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);   // tcgen05 3xTF32 (gin_bwd_tc.cu)
-void launch_gin_bwd_main_tc_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
-void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // 64-row double-buffered tiles (gin_bwd_tc2.cu)
+void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // tcgen05 3xTF32, 64-row double-buffered tiles (gin_bwd_tc2.cu)
 void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
-int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 0 FFMA, 1 gin_bwd_tc.cu (default), 2 gin_bwd_tc2.cu
+int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
 
 struct InputProjBwdArgs {
   const float* ga[2];       // layer-0 input gradients of the two encoders, [V][DTR]

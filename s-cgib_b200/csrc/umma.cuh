@@ -249,5 +249,51 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 operands (kind::f16, fp32 accumulation; K = 16 per instruction).  Tile format "B": a [R rows][64 bf16] block is
+// R dense 128-byte rows whose 16-byte chunks are XOR-swizzled with (row % 8) (SWIZZLE_128B; block base 1024-byte
+// aligned); wider tiles are column blocks of 64.  The same physical block is read
+//   K-major  (MN index = row, K = column): SBO = 1024 (8-row groups), K step s starts 32*s bytes into the row;
+//   MN-major (MN index = column, K = row): SBO = 1024 (8-row K groups), LBO = block stride (next 64 MN columns),
+//                                          K step s (16 rows) starts at byte 2048*s.
+// Pinned on B200 by tests/csrc/umma_probe_bf16.cu (tests/gpu_umma_probe_bf16.py).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if (elect_one()) mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+constexpr uint64_t kSw128 = (uint64_t)2 << 61;
+// byte offset of the 16-byte chunk c8 (8 bf16) of `row` inside a format-B block
+__device__ __forceinline__ int tile_b_off(int row, int c8) { return row * 128 + ((c8 ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint64_t desc_b_kmajor(uint32_t block, int s) {          // K step s of one 64-column block
+  return desc_base(block + (uint32_t)s * 32u, 16u, 1024u) | kSw128;
+}
+__device__ __forceinline__ uint64_t desc_b_mnmajor(uint32_t block, uint32_t block_stride, int s) {   // K step s = rows 16s..16s+15
+  return desc_base(block + (uint32_t)s * 2048u, block_stride, 1024u) | kSw128;
+}
+// two fp32 -> packed bf16x2 (round to nearest even): lo half = a, hi half = b
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
 }  // namespace umma
 }  // namespace scgib

@@ -67,6 +67,7 @@ class DeviceBatch:
 
     def c_struct(self, gate_u, feat_u):
         b = _lib.Batch()
+        b.struct_size = ctypes.sizeof(_lib.Batch)
         b.B, b.N, b.E, b.Ns, b.Es = self.B, self.N, self.E, self.Ns, self.Es
         g, e = self.g, self.ego
         b.graph_ptr, b.indptr, b.indices = g.graph_ptr.data_ptr(), g.indptr.data_ptr(), g.indices.data_ptr()
@@ -126,10 +127,15 @@ class PretrainEngine:
         self._loss_scale = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
         self.ego_ws = EgoWorkspace()
         self.recon_logm_steps = 0        # k >= 1: batches made by this engine use --recons_type logM with k-step matrices
+        self.fwd_serial = 0              # bumped by every forward: an autograd node of an older forward must not run backward
         self._noise_gen = torch.Generator(device=self.device)
         if seed is not None:
             self._noise_gen.manual_seed(seed)
             self.reset_parameters(seed)
+        else:
+            # unseeded: follow torch's global seed (torch.manual_seed) and decorrelate data-parallel ranks
+            rank = int(__import__("os").environ.get("RANK", "0"))
+            self._noise_gen.manual_seed((torch.initial_seed() + 7919 * rank) % (2 ** 63))
 
     # ---------------------------------------------------------------- parameters
     def views(self) -> "OrderedDict[str, torch.Tensor]":
@@ -221,6 +227,7 @@ class PretrainEngine:
             self._slot_i = 0
         slot = self._slots[self._slot_i % len(self._slots)]
         self._slot_i += 1
+        train_stream = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._side):
             if slot["done"] is not None:
                 self._side.wait_event(slot["done"])
@@ -238,7 +245,11 @@ class PretrainEngine:
                 gd.ndata = {"x": put("x", g.ndata["x"])}
                 g = gd
             ego = khop_ego_batch(g, k, self.ego_ws, out=slot["bufs"])
-            b = DeviceBatch(g, ego, g.ndata["x"].float(), normalize_x)
+            x = g.ndata["x"]
+            if x.dtype != torch.float32:                     # the fp32 copy is allocated on the side stream but read by
+                x = x.float()                                # the training stream: keep its block out of the side pool
+                x.record_stream(train_stream)                # until that work has run
+            b = DeviceBatch(g, ego, x, normalize_x)
             b.recon_logm_steps = self.recon_logm_steps
             b._slot = slot
             ev = torch.cuda.Event()
@@ -302,6 +313,7 @@ class PretrainEngine:
         if gate_u is None:
             gate_u, feat_u = self.draw_noise(b.N)
         self._last = (b, gate_u.contiguous(), feat_u.contiguous())
+        self.fwd_serial += 1
         cb = b.c_struct(self._last[1], self._last[2])
         ws = self._workspace(b)
         emb = None
@@ -332,6 +344,7 @@ class PretrainEngine:
         _lib.check(self.lib.scgib_pretrain_backward_f32(ctypes.byref(self.dims), _lib.ptr(p), ctypes.byref(cb),
                                                         self._loss_scale, _lib.ptr(self.grads), _lib.ptr(ws),
                                                         ws.numel(), st), "pretrain_backward")
+        self._release_slot(b)
         return self.grads
 
     def forward_features(self, b: DeviceBatch, gate_u=None, feat_u=None, want_imap=False, update_running=True,
@@ -341,6 +354,7 @@ class PretrainEngine:
         if gate_u is None:
             gate_u, feat_u = self.draw_noise(b.N)
         self._last = (b, gate_u.contiguous(), feat_u.contiguous())
+        self.fwd_serial += 1
         cb = b.c_struct(self._last[1], self._last[2])
         ws = self._workspace(b)
         Z = torch.empty(b.N, HID, device=self.device)
@@ -367,6 +381,7 @@ class PretrainEngine:
         _lib.check(self.lib.scgib_extract_backward_f32(ctypes.byref(self.dims), _lib.ptr(p), ctypes.byref(cb), _lib.ptr(gZ),
                                                        _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), st),
                    "extract_backward")
+        self._release_slot(b)
         return self.grads
 
     def adam_step(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, grad_scale=1.0):
@@ -402,11 +417,15 @@ class PretrainEngine:
                 import torch.distributed as dist
                 dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
             self.adam_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / world_size)
+        self._release_slot(b)
+        return losses
+
+    def _release_slot(self, b):
+        """A prefetch slot's buffers may be overwritten once the work queued so far on the training stream has run."""
         slot = getattr(b, "_slot", None)
-        if slot is not None:                      # the slot's buffers may be overwritten once this step has run
+        if slot is not None:
             slot["done"] = torch.cuda.Event()
             slot["done"].record(torch.cuda.current_stream(self.device))
-        return losses
 
 
 FT_NAMES = ["s2s.lstm.weight_ih_l0", "s2s.lstm.weight_hh_l0", "s2s.lstm.bias_ih_l0", "s2s.lstm.bias_hh_l0",
@@ -439,6 +458,7 @@ class FinetuneHead:
         self.grads = torch.zeros_like(self.params)
         self._ws = None
         self._saved = None
+        self.fwd_serial = 0
 
     def views(self, grads=False):
         buf = self.grads if grads else self.params
@@ -469,6 +489,7 @@ class FinetuneHead:
                                                         _lib.ptr(Z), _lib.ptr(graph_ptr), B, N, _lib.ptr(scores),
                                                         _lib.ptr(readout), _lib.ptr(ws), ws.numel(), st), "finetune_head_fwd")
         self._saved = (Z, graph_ptr, scores)
+        self.fwd_serial += 1
         if self.C == 0:
             return readout
         return (scores, readout) if want_readout else scores

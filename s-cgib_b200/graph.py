@@ -376,9 +376,12 @@ class DeviceLoader:
                 yield ids
 
     def _epoch_ids(self):
+        """Permutation of this pass, then advance the epoch: like ``DataLoader(shuffle=True)`` every pass reshuffles
+        without anybody calling ``set_epoch`` (which stays as the data-parallel override: all ranks must agree)."""
         n = len(self.dataset)
         if self.shuffle:
             perm = torch.randperm(n, generator=torch.Generator().manual_seed(self.seed + self.epoch))
+            self.epoch += 1
         else:
             perm = torch.arange(n)
         if self.world > 1:
@@ -387,16 +390,7 @@ class DeviceLoader:
         return perm.to(torch.int32).to(self.dataset.device)
 
     def __iter__(self):
-        n = len(self.dataset)
-        if self.shuffle:
-            gen = torch.Generator().manual_seed(self.seed + self.epoch)
-            perm = torch.randperm(n, generator=gen)
-        else:
-            perm = torch.arange(n)
-        if self.world > 1:
-            per = n // self.world
-            perm = perm[self.rank * per:(self.rank + 1) * per]
-        ids_dev = perm.to(torch.int32).to(self.dataset.device)
+        ids_dev = self._epoch_ids()
         for i in range(len(self)):
             ids = ids_dev[i * self.batch_size:(i + 1) * self.batch_size]
             if ids.numel() == 0:

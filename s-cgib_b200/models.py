@@ -91,6 +91,13 @@ class _Set2SetParams(nn.Module):
         self.lstm.reset_parameters()          # DGL's Set2Set.__init__ re-initialises the LSTM (second RNG draw)
 
 
+def _check_serial(what, obj, serial):
+    """The engine keeps ONE workspace of saved activations: backward must belong to the most recent forward."""
+    if obj.fwd_serial != serial:
+        raise RuntimeError("scgib_b200: %s.backward() after another forward on the same model - the saved activations of "
+                           "this forward were overwritten (one forward, then its backward; see INTEGRATION.md)" % what)
+
+
 def _detach_aliased_grads(params, flat):
     """The backward kernels overwrite the flat gradient buffer.  A parameter whose .grad still aliases it (adopted from
     an earlier backward and not reset by zero_grad) gets a private copy first, so gradient accumulation is preserved."""
@@ -108,12 +115,14 @@ class _PretrainFn(torch.autograd.Function):
         losses = eng.forward(batch, gate_u, feat_u, update_running=bridge.training)
         ctx.bridge = bridge
         ctx.params = params
+        ctx.serial = eng.fwd_serial
         out = losses.clone()
         return out[0], out[1], out[2]
 
     @staticmethod
     def backward(ctx, g_kl, g_con, g_rec):
         eng = ctx.bridge.engine
+        _check_serial("Mainmodel", eng, ctx.serial)
         _detach_aliased_grads(ctx.params, eng.grads)
         if g_kl.data_ptr() == g_con.data_ptr() == g_rec.data_ptr() and g_kl.numel() == 1:
             # loss = KL + recon + contrastive (exp_pretraining.py:320): the three upstream gradients are one tensor.  Run the
@@ -372,12 +381,15 @@ class _FinetuneFn(torch.autograd.Function):
         scores = head.forward(Z, batch.g.graph_ptr)
         ctx.owner = owner
         ctx.params = params
+        ctx.serial = (eng.fwd_serial, head.fwd_serial)
         return scores
 
     @staticmethod
     def backward(ctx, g_scores):
         owner = ctx.owner
         eng, head = owner._bridge.engine, owner._head
+        _check_serial("Mainmodel_finetuning", eng, ctx.serial[0])
+        _check_serial("Mainmodel_finetuning (head)", head, ctx.serial[1])
         _detach_aliased_grads(ctx.params, eng.grads)
         _detach_aliased_grads(ctx.params, head.grads)
         gZ = head.backward(g_scores)
@@ -515,12 +527,16 @@ class _DomainAdaptFn(torch.autograd.Function):
         org = rev.forward(x_norm, batch.g.graph_ptr)
         ctx.owner = owner
         ctx.params = params
+        ctx.serial = (eng.fwd_serial, head.fwd_serial, rev.head.fwd_serial)
         return rec, org
 
     @staticmethod
     def backward(ctx, g_rec, g_org):
         owner = ctx.owner
         eng, head, rev = owner._bridge.engine, owner._head, owner._rev
+        _check_serial("Mainmodel_domainadapt", eng, ctx.serial[0])
+        _check_serial("Mainmodel_domainadapt (head)", head, ctx.serial[1])
+        _check_serial("Mainmodel_domainadapt (s2s_rev)", rev.head, ctx.serial[2])
         _detach_aliased_grads(ctx.params, eng.grads)
         _detach_aliased_grads(ctx.params, head.grads)
         gZ = head.backward(g_rec)

@@ -3,7 +3,7 @@
 // with this probe on a B200 (tests/gpu_umma_probe2.py).
 #include <string.h>
 #include "umma.cuh"
-#include "../../include/scgib.h"
+#include "scgib.h"
 
 namespace scgib {
 using namespace umma;

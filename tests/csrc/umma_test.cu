@@ -2,7 +2,7 @@
 // GEMM in each operand-major mode and dumps all 128 TMEM lanes, so the tests can verify descriptors, the format-F
 // swizzle and the TMEM row mapping for M = 64 and M = 128 against torch.
 #include "umma.cuh"
-#include "../../include/scgib.h"
+#include "scgib.h"
 
 namespace scgib {
 using namespace umma;

@@ -41,7 +41,8 @@ CASES.append(("fmt S MN-major both M=64 K=128", "AtB2", dict(M=64, ksteps=16, a_
 def one(idx):
     import torch
     from scgib_b200 import _lib
-    lib = _lib.load()
+    from tests import probe_lib
+    lib = probe_lib.load()
     dev = "cuda:0"
     tag, kind, kwargs = CASES[idx]
     torch.manual_seed(0)

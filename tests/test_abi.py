@@ -74,6 +74,29 @@ def test_argument_validation_without_gpu():
     assert b"NULL" in lib.scgib_error_string(-1)
 
 
+def test_batch_struct_matches_header_and_integration_doc():
+    """The ctypes mirror of ScgibBatch (s-cgib_b200/_lib.py) and the binding INTEGRATION.md shows a maintainer have the
+    library's struct size, and a struct of another size is refused (SCGIB_E_ABI) before anything is dereferenced."""
+    L = _lib()
+    lib = L.load()
+    assert ctypes.sizeof(L.Batch) == lib.scgib_batch_abi_size()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class Dims\(ctypes.Structure\).*?\[\(\"eval_mode\".*?\)\]\n", doc, re.S)
+    assert m, "INTEGRATION.md no longer shows the ctypes structs"
+    ns = {"ctypes": ctypes}
+    exec(m.group(0), ns)
+    assert ctypes.sizeof(ns["Batch"]) == lib.scgib_batch_abi_size()
+    assert [f[0] for f in ns["Batch"]._fields_] == [f[0] for f in L.Batch._fields_]
+    assert [f[0] for f in ns["Dims"]._fields_] == [f[0] for f in L.Dims._fields_]
+    good = L.Dims(9, 32, 64, 4)
+    b = L.Batch()
+    b.struct_size = ctypes.sizeof(L.Batch) - 8          # e.g. a binding without eval_mode / recon_logm_steps (round 1 doc)
+    one = ctypes.c_float(0)
+    rc = lib.scgib_pretrain_forward_f32(ctypes.byref(good), ctypes.byref(one), None, ctypes.byref(b), ctypes.byref(one), None, None,
+                                        None, None, ctypes.byref(one), 0, None)
+    assert rc == -6 and b"struct_size" in lib.scgib_error_string(-6)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     L = _lib()
     monkeypatch.setattr(L, "_lib", None)

@@ -17,7 +17,8 @@ def test_umma_3xtf32_tile_gemm(M, mode):
     """mode 0: A K-major, B K-major; mode 1: B MN-major (natural weights); mode 2: both MN-major (reduction over the
     tile rows).  fp32-level accuracy (3xTF32) and the documented TMEM lane of every accumulator row."""
     from scgib_b200 import _lib
-    lib = _lib.load()
+    from tests import probe_lib
+    lib = probe_lib.load()
     torch.manual_seed(M + mode)
     A = torch.randn(M, 64, device=DEV)
     B = torch.randn(M if mode == 2 else 64, 64, device=DEV)
@@ -31,11 +32,11 @@ def test_umma_3xtf32_tile_gemm(M, mode):
     assert rel(out[lanes], ref) <= 3e-6          # plain TF32 would be ~1e-3
 
 
-@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (2, 300), (3, 300), (4, 300), (2, 6000), (3, 6000), (4, 6000), (4, 20000)])
+@pytest.mark.parametrize("mode,B", [(0, 300), (1, 300), (1, 6000), (1, 20000)])
 @pytest.mark.parametrize("kin", [32, 64])
 def test_gin_layer_forward_tensor_cores(kin, mode, B):
-    """mode 1: gin_tc.cu (M = 64 tiles); modes 2/3: gin_tc2.cu (warp-specialised, 1/2 producer groups).  B = 6000
-    graphs give ~90 k rows = several 128-row tiles per CTA (both pipeline stages reused)."""
+    """mode 1: gin_tc3.cu (warp-specialised tcgen05 kernel), mode 0: the FFMA cross-check.  B = 6000 graphs give
+    ~90 k rows = several 128-row tiles per CTA (both pipeline stages reused)."""
     from scgib_b200 import _lib, ops
     lib = _lib.load()
     g = synth_batch(2, B)
