@@ -383,6 +383,8 @@ def main():
     ap.add_argument("--recons_type", default="adj", choices=["adj", "logM"],
                     help="adj = the reference default (the headline); logM = k-step log transition matrices (models.py:770-782)")
     ap.add_argument("--shape", default="pcqm", choices=["pcqm", "peptides"], help="synthetic molecule shape (finetune workload)")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32 = the headline (reference precision); bf16 = bf16 activations + single-pass bf16 tensor-core MLPs in the GIN encoders")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -421,7 +423,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)     # same seed on every rank: replicas start equal
+    bf16 = args.dtype == "bf16"
+    eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0, dtype=args.dtype)     # same seed on every rank: replicas start equal
     eng._noise_gen.manual_seed(1234 + rank)
     if args.recons_type == "logM":
         eng.recon_logm_steps = args.k
@@ -527,7 +530,7 @@ def main():
         import models as dropin_models
         from scgib_b200.graph import khop_ego_batch
         ns = types.SimpleNamespace(recons_type=args.recons_type, useAtt=1, readout_f="sum", d_transfer=32, device=str(dev),
-                                   batch_size=args.batch, k_transition=args.k)
+                                   batch_size=args.batch, k_transition=args.k, dtype=args.dtype)
         torch.manual_seed(0)
         dm = dropin_models.Mainmodel(ns, 9, 64, 4, 4, args.k, "GIN").to(dev)
         dm.train()
@@ -572,27 +575,36 @@ def main():
     kernels = {k_: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] // psteps,
                     "ms_per_launch": v[0] / v[1]} for k_, v in prof.items()}
     b = eng.make_batch(resident[0], args.k)
-    step_bytes = b.algorithmic_bytes(gin_layers=4)
+    es = 2 if bf16 else 4                 # bytes per activation element of the GIN encoders
+    step_bytes = b.algorithmic_bytes(gin_layers=4, s=es)
     hbm, peak_src = peaks()
-    dom = max(kernels, key=lambda k_: kernels[k_]["ms_per_step"])
-    # algorithmic bytes of one launch of the dominant kernel family (per-layer figures of SURVEY.md 8d)
-    V = {"enc1": b.N, "enc2": b.Ns, "enc1+2": b.N + b.Ns}.get(dom.split(".")[-1], b.N)
-    D = {"enc1": b.E, "enc2": b.Es, "enc1+2": b.E + b.Es}.get(dom.split(".")[-1], b.E)
+    # A GIN layer's backward is TWO launches here (gin_bwd_pre + gin_bwd_main): they are one roofline unit, so that the
+    # SURVEY 8(d) layer-backward budget (2 x the layer's forward bytes) is counted ONCE
+    fam = {}
+    for k_, v in kernels.items():
+        f = "gin_bwd (pre + main)" if k_.startswith(("gin_bwd_pre", "gin_bwd_main")) else k_
+        cur = fam.setdefault(f, {"ms_per_step": 0.0, "members": []})
+        cur["ms_per_step"] += v["ms_per_step"]
+        cur["members"].append(k_)
+    dom = max(fam, key=lambda k_: fam[k_]["ms_per_step"])
+    # algorithmic bytes of one layer of the dominant family (SURVEY.md 8d per-layer figures, both encoders' rows, averaged
+    # over the 4 layers), and the time of that layer = the family's time per step / 4 layers
+    V, D = b.N + b.Ns, b.E + b.Es
     per_layer = [(32, 64), (64, 64), (64, 64), (64, 64)]
-    if dom.startswith("gin_bwd_main"):
-        abytes = sum(V * 2 * (di + d) * 4 for di, d in per_layer) / 4.0
+    fwd_layer = sum(V * (di + d) * es + 4 * (V + 1 + D) for di, d in per_layer) / 4.0
+    if dom.startswith("gin_bwd"):
+        abytes, unit_ms = 2.0 * fwd_layer, fam[dom]["ms_per_step"] / 4.0
     elif dom.startswith("gin_fwd"):
-        abytes = sum(V * (di + d) * 4 + 4 * (V + 1 + D) for di, d in per_layer) / 4.0
-    elif dom.startswith("gin_bwd_pre"):
-        abytes = (V * 3 * 64 * 4 + 4 * (V + 1 + D))
+        abytes, unit_ms = fwd_layer, fam[dom]["ms_per_step"] / 4.0
     elif dom.startswith("contrastive"):
-        abytes = 4 * b.B * 64 * 4
+        abytes, unit_ms = 4 * b.B * 64 * 4, kernels[dom]["ms_per_launch"]
     else:
-        abytes = 3 * b.N * 64 * 4
-    achieved = abytes / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
-    traffic = None                       # dram__bytes_read + write per launch of that kernel, from the committed ncu capture
+        abytes, unit_ms = 3 * b.N * 64 * 4, kernels[dom]["ms_per_launch"]
+    achieved = abytes / (unit_ms * 1e-3) / 1e9
+    traffic = None                       # dram__bytes_read + write per unit, from the ncu capture of THIS build (profiles/)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        traffic = tj.get(args.dtype, {}).get(dom, {}).get("dram_bytes_per_unit")
     except Exception:
         pass
 
@@ -600,7 +612,7 @@ def main():
     # bytes per launch (SURVEY 8d per-unit figures x this batch's sizes) / CUDA-event time per launch
     d4 = 64 * 4
     hbm_alg = {
-        "gin_bwd_pre.enc1+2": 3 * (b.N + b.Ns) * d4 + 4 * (b.N + b.Ns + 2 + b.E + b.Es),
+        ("gin_bwd_pre_bf16.enc1+2" if bf16 else "gin_bwd_pre.enc1+2"): 3 * (b.N + b.Ns) * 64 * es + 4 * (b.N + b.Ns + 2 + b.E + b.Es),
         "ego_pool_fwd": (b.Ns + b.N) * d4 + 4 * (b.N + 1) + 4 * b.N,
         "graph_gate_fwd": 4 * b.N * d4 + 12 * b.N,
         "recon_bwd": 2 * b.N * d4 + 4 * (b.N + 1 + b.E),
@@ -616,9 +628,11 @@ def main():
         line = {
             "metric": METRIC, "value": graphs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "S-CGIB pre-training step (ego extraction + fwd + bwd + grad all-reduce + Adam), GIN-4x64, "
-                                   "k_transition=%d, batch %d synthetic PCQM4Mv2-shape graphs per GPU (BASELINE configs[1])" % (args.k, args.batch),
+            "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
+            "config": {"workload": "S-CGIB pre-training step (ego extraction + fwd + bwd + grad all-reduce + Adam), GIN-4x64 "
+                                   "(= BASELINE's 'GIN-5x64': the published code's 5-layer GIN has 4 GINConv, SURVEY F4), "
+                                   "k_transition=%d, batch %d synthetic PCQM4Mv2-shape graphs per GPU (BASELINE configs[1]%s)"
+                                   % (args.k, args.batch, ", bf16 half: bf16 activations in the GIN encoders" if bf16 else ""),
                        "graphs_per_gpu": args.batch, "nodes": b.N, "edges": b.E, "ego_rows": b.Ns, "ego_edges": b.Es,
                        "parallelism": "dp%d" % world, "recons_type": args.recons_type,
                        "grad_exchange": ("fused peer-memory all-reduce + Adam kernel" if fused_dp else "NCCL all-reduce + Adam") if world > 1 else "none",
@@ -639,9 +653,10 @@ def main():
             "gpu_launches": (nlaunch + 5) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": abytes,
-                         "note": "warp-specialised tcgen05 3xTF32 kernel (MLP GEMMs on the tensor pipe); bytes = SURVEY 8(d) "
-                                 "per-layer figure of both encoders' rows in the launch; see DESIGN.md section 3"},
+                         "algorithmic_bytes_per_unit": abytes, "unit_ms": unit_ms, "members": fam[dom]["members"],
+                         "note": "unit = ONE GIN layer of both encoders (layer average): forward = 1 launch, backward = "
+                                 "gin_bwd_pre + gin_bwd_main (the SURVEY 8(d) layer-backward budget, 2 x forward bytes, is "
+                                 "counted once over both launches); warp-specialised tcgen05 kernels, see DESIGN.md section 3"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "peak": hbm, "unit": "GB/s", "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm},
             "hbm_kernels": hbm_kernels,

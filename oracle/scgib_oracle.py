@@ -121,11 +121,37 @@ class GIN(nn.Module):
             self.batch_norms.append(nn.BatchNorm1d(hidden_dim))
 
     def forward(self, g, h):
+        if getattr(self, "emulate_bf16", False):
+            return self.forward_bf16_emulated(g, h)
         for i, layer in enumerate(self.ginlayers):
             h = layer(g, h)
             h = self.batch_norms[i](h)
             h = F.relu(h)
         return h
+
+    def forward_bf16_emulated(self, g, h):
+        """The same layers with the rounding points of the product's bf16 mode (csrc/gin_bf16.cu), everything else in the
+        module's own precision (fp64 in the tests): the layer input t, the aggregated input a, the hidden activation r, the
+        pre-BN output y and both weight matrices are rounded to bf16 (round-to-nearest-even); accumulation, biases, the
+        BatchNorm statistics (of the ROUNDED y) and BN + ReLU are exact.  Training-mode statistics only.  The casts are
+        straight-through for autograd.  Test infrastructure: separates "the kernel computes the bf16 algorithm correctly"
+        from "how far the bf16 algorithm is from the reference"."""
+        bf = lambda x: x + (x.detach().float().bfloat16().to(x.dtype) - x.detach())
+        h = bf(h)
+        act = lambda z: z
+        for i, layer in enumerate(self.ginlayers):
+            hin = act(h)
+            a = bf(hin + torch.zeros_like(hin).index_add(0, g.dst, hin[g.src]))
+            l1, l2 = layer.apply_func.mlp[0], layer.apply_func.mlp[2]
+            r = bf(F.relu(a @ bf(l1.weight).t() + l1.bias))
+            y = bf(r @ bf(l2.weight).t() + l2.bias)
+            bn = self.batch_norms[i]
+            mu, var = y.mean(0), y.var(0, unbiased=False)
+            sc = bn.weight / torch.sqrt(var + bn.eps)
+            sh = bn.bias - mu * sc
+            act = (lambda sc, sh: (lambda z: F.relu(z * sc + sh)))(sc, sh)
+            h = y
+        return act(h)
 
 
 class _LSTMHolder(nn.Module):

@@ -90,7 +90,7 @@ static inline void debug_check(const char* name, cudaStream_t s) {
 
 static bool dims_ok(const ScgibDims* d) {
   return d && d->hidden == HID && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&
-         d->in_dim <= 32;
+         d->in_dim <= 32 && (d->act_dtype == SCGIB_ACT_F32 || d->act_dtype == SCGIB_ACT_BF16);
 }
 
 struct Layout {
@@ -162,6 +162,9 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   char* p = (char*)base;
   size_t o = 0;
   auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  // activations of the GIN encoders (t, a, r, y, the layer gradients g_o / Ga): fp32, or bf16 in bf16 mode - carved by bytes
+  const size_t es = d->act_dtype == SCGIB_ACT_BF16 ? 2 : 4;
+  auto take_act = [&](size_t nelems) { float* r = (float*)(p + o); o += al(nelems * es); return r; };
   const int L = d->gin_layers;
   const int V[2] = {N, Ns};
   const int Vmax = N > Ns ? N : Ns;
@@ -170,13 +173,13 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
       const int kin = l == 0 ? DTR : HID;
       w.enc_w1t[e][l] = take((size_t)kin * HID);
       w.enc_w2t[e][l] = take((size_t)HID * HID);
-      w.a[e][l] = take((size_t)V[e] * kin);
-      w.r[e][l] = take((size_t)V[e] * HID);
-      w.y[e][l] = take((size_t)V[e] * HID);
+      w.a[e][l] = take_act((size_t)V[e] * kin);
+      w.r[e][l] = take_act((size_t)V[e] * HID);
+      w.y[e][l] = take_act((size_t)V[e] * HID);
       w.bn[e][l] = take(4 * HID);
     }
   w.head_w1t = take(2 * HID * HID); w.head_w2t = take(HID * HID); w.comp_w1t = take(HID * HID);
-  w.t = take((size_t)N * DTR);
+  w.t = take_act((size_t)N * DTR);
   w.cvec[0] = take(2 * HID); w.cvec[1] = take(2 * HID);
   w.small_part = take(small_part_floats(N, Ns)); w.small_part2 = take(small_part_floats(N, Ns));
   w.counters = (unsigned int*)take(64);
@@ -194,8 +197,8 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.g_core = take((size_t)B * HID); w.g_readout = take((size_t)B * HID);
   w.gZ = take((size_t)N * HID); w.gI = take((size_t)N * 2 * HID); w.gp = take(N);
   w.g_q = take((size_t)N * HID); w.gH = take((size_t)N * HID); w.gC = take((size_t)N * HID);
-  w.g_o[0] = take((size_t)N * HID); w.g_o[1] = take((size_t)Ns * HID);
-  w.Ga[0] = take((size_t)N * HID); w.Ga[1] = take((size_t)Ns * HID);
+  w.g_o[0] = take_act((size_t)N * HID); w.g_o[1] = take_act((size_t)Ns * HID);
+  w.Ga[0] = take_act((size_t)N * HID); w.Ga[1] = take_act((size_t)Ns * HID);
   (void)Vmax;
   w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
   w.logm_walks = take((size_t)logm_max_steps() * N); w.logm_gram = take(B); w.logm_pair = take(N); w.logm_loss = take(4);
@@ -279,6 +282,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   const int L = d->gin_layers;
   const bool eval = b->eval_mode != 0;       // model.eval(): BatchNorm layers use (and do not update) their running statistics
   if (eval && !bn_running) return SCGIB_E_NULL;
+  const bool bf = d->act_dtype == SCGIB_ACT_BF16;   // bf16 mode: GIN activations in bf16, single-pass bf16 tensor-core MLPs
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   // k-major weight copies for the forward GEMMs
@@ -297,10 +301,12 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     add(params + lo.off[SCGIB_P_COMP_W1], w.comp_w1t, HID, HID);
     PROF("transpose_weights", launch_transposes(jobs, s));
   }
-  if (b->t_override)
+  if (b->t_override && bf)
+    launch_f32_to_bf16(b->t_override, w.t, (size_t)b->N * DTR, s);
+  else if (b->t_override)
     cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
   else
-    PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s));
+    PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s, bf));
   // the two GIN encoders (models.py:704, 707): layer l of Encoder1 and of Encoder2 are independent, so they share a launch
   for (int l = 0; l < L; ++l) {
     GinFwdArgs ga[2];
@@ -323,7 +329,9 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       a.reverse = (l & 1) && fwd_alternate();
     }
     const int kin = l == 0 ? DTR : HID;
-    if (tensor_core_mode() != 0) {
+    if (bf) {
+      PROF("gin_fwd_bf16.enc1+2", launch_gin_fwd_bf16(ga[0], &ga[1], kin, HID, s));
+    } else if (tensor_core_mode() != 0) {
       PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
     } else {
       for (int e = 0; e < 2; ++e) PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
@@ -334,11 +342,11 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
                                params + lo.enc(e, l, L, SCGIB_ENC_BETA), w.bn[e][l], s);
   }
   {
-    GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q};
+    GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q, bf};
     PROF("gate_lin_fwd", launch_gate_lin_fwd(a, s));
   }
   {
-    EgoPoolFwdArgs a{w.y[1][L - 1], w.bn[1][L - 1], b->ego_ptr, b->N, params + lo.off[SCGIB_P_ATTN_W] + HID, w.C, w.logit};
+    EgoPoolFwdArgs a{w.y[1][L - 1], w.bn[1][L - 1], b->ego_ptr, b->N, params + lo.off[SCGIB_P_ATTN_W] + HID, w.C, w.logit, bf};
     PROF("ego_pool_fwd", launch_ego_pool_fwd(a, s));
   }
   {
@@ -421,6 +429,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   const int L = d->gin_layers;
   const int GP = num_sms();
   const float s_kl = loss_scale[0], s_con = loss_scale[1], s_rec = loss_scale[2];
+  const bool bf = d->act_dtype == SCGIB_ACT_BF16;
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   const int js = contrastive_jsplit(b->B);
@@ -490,7 +499,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     PROF("gate_lin_bwd", launch_gate_lin_bwd(a, GP, s));
   }
   const int enc_split = pair_split(GP, (b->N + 127) / 128, (b->Ns + 127) / 128);   // CTAs of Encoder1 in a shared launch
-  const bool pair_main = bwd_tensor_core_mode() != 0;
+  const bool pair_main = bf || bwd_tensor_core_mode() != 0;
   for (int l = L - 1; l >= 0; --l) {
     const int kin = l == 0 ? DTR : HID;
     GinBwdPreArgs pa[2];
@@ -513,6 +522,11 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m.V = V; m.g_a = l == 0 ? w.ga0[e] : w.Ga[e]; m.part = w.ppart; m.pstride = lo.total;
       m.off_W1 = lo.enc(e, l, L, SCGIB_ENC_W1); m.off_b1 = lo.enc(e, l, L, SCGIB_ENC_B1);
       m.off_W2 = lo.enc(e, l, L, SCGIB_ENC_W2); m.off_b2 = lo.enc(e, l, L, SCGIB_ENC_B2);
+    }
+    if (bf) {
+      PROF("gin_bwd_pre_bf16.enc1+2", launch_gin_bwd_pre_bf16(pa[0], &pa[1], HID, s));
+      PROF("gin_bwd_main_bf16.enc1+2", launch_gin_bwd_main_bf16(ma[0], &ma[1], kin, HID, GP, s));
+      continue;
     }
     PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], s));
     if (pair_main) {

@@ -9,6 +9,7 @@ constexpr int HID = 64;        // hidden width (exp_pretraining.py:390)
 constexpr int DTR = 32;        // d_transfer   (exp_pretraining.py:378)
 constexpr int kThreads = 256;  // CTA size of every tile kernel
 constexpr float kBnEps = 1e-5f;
+typedef uint16_t bf16_t;       // raw bfloat16 storage (bf16 mode: activations of the GIN encoders)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -30,6 +31,27 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
 }
 __device__ __forceinline__ void st4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ float4 ld4_cs(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+// 4 consecutive channels of an activation row stored as fp32 or (bf16 mode) bf16: `p` is the tensor base, idx the element index
+template <bool BF>
+__device__ __forceinline__ float4 ld4a(const float* p, size_t idx) {
+  if (BF) {
+    const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16_t*>(p) + idx);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+  }
+  return *reinterpret_cast<const float4*>(p + idx);
+}
+template <bool BF>
+__device__ __forceinline__ void st4a(float* p, size_t idx, float4 v) {
+  if (BF) {
+    uint2 w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v.w), "f"(v.z));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16_t*>(p) + idx) = w;
+  } else {
+    *reinterpret_cast<float4*>(p + idx) = v;
+  }
+}
 __device__ __forceinline__ float4 make4(float a) { return make_float4(a, a, a, a); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 relu4(float4 a) {

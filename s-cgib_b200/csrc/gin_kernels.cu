@@ -17,6 +17,7 @@ namespace scgib {
 // ------------------------------------------------------------------------------------------------
 // x_hat = x / max(||x||_2, 1e-12);  t = x_hat Wt^T          (Wt [DTR][F])
 // ------------------------------------------------------------------------------------------------
+template <bool OUT_BF16>
 __global__ void __launch_bounds__(kThreads)
 input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt, int N, int F, int normalize,
                       float* __restrict__ t) {
@@ -38,13 +39,25 @@ input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
       const float4 w = ld4(s_w + f * DTR + q * 4);
       acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
     }
-    st4(t + (size_t)v * DTR + q * 4, acc);
+    st4a<OUT_BF16>(t, (size_t)v * DTR + q * 4, acc);
   }
 }
 
-void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s) {
+// out_bf16: t is bf16 storage (bf16 mode: the layer-0 input of the GIN encoders)
+void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s, bool out_bf16) {
   const int grid = min((N + 31) / 32, 148 * 8);
-  input_proj_fwd_kernel<<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
+  if (out_bf16) input_proj_fwd_kernel<true><<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
+  else input_proj_fwd_kernel<false><<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
+}
+
+__global__ void __launch_bounds__(kThreads) f32_to_bf16_kernel(const float* __restrict__ in, bf16_t* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads)
+    st4a<true>(reinterpret_cast<float*>(out), 4 * i, ld4(in + 4 * i));
+}
+void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) {   // n multiple of 4
+  const size_t n4 = n / 4;
+  const int grid = (int)min((size_t)(4 * num_sms()), (n4 + kThreads - 1) / kThreads);
+  if (n4 > 0) f32_to_bf16_kernel<<<grid, kThreads, 0, s>>>(in, reinterpret_cast<bf16_t*>(out), n4);
 }
 
 __global__ void bn_from_running_kernel(const float* __restrict__ running, const float* __restrict__ gamma,

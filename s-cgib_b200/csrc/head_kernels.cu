@@ -39,6 +39,7 @@ void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const fl
 }
 
 // C_v = sum over the ego-net of v of relu(BN(y)) ; logit_v = w_cand . C_v
+template <bool BF>
 __global__ void __launch_bounds__(kThreads)
 ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
   const int l = threadIdx.x & 15;
@@ -49,7 +50,7 @@ ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
     const int r0 = __ldg(p.ego_ptr + v), r1 = __ldg(p.ego_ptr + v + 1);
     float4 acc = make4(0.f);
 #pragma unroll 4
-    for (int r = r0; r < r1; ++r) acc = add4(acc, b.act(ld4(p.y + (size_t)r * HID + l * 4)));
+    for (int r = r0; r < r1; ++r) acc = add4(acc, b.act(ld4a<BF>(p.y, (size_t)r * HID + l * 4)));
     st4(p.C + (size_t)v * HID + l * 4, acc);
     float d = acc.x * w.x + acc.y * w.y + acc.z * w.z + acc.w * w.w;
     const unsigned hmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;   // the two half-warps may diverge at the tail
@@ -60,7 +61,8 @@ ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
 }
 void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s) {
   const int grid = min((a.N + 15) / 16, 16 * num_sms());
-  ego_pool_fwd_kernel<<<grid, kThreads, 0, s>>>(a);
+  if (a.y_bf16) ego_pool_fwd_kernel<true><<<grid, kThreads, 0, s>>>(a);
+  else ego_pool_fwd_kernel<false><<<grid, kThreads, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -68,6 +70,7 @@ void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 struct GateLinFwdSmem { float tile[GT * GLD]; float w[HID * HID]; };
 
+template <bool BF>
 __global__ void __launch_bounds__(kThreads, 2)
 gate_lin_fwd_kernel(GateLinFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -85,7 +88,7 @@ gate_lin_fwd_kernel(GateLinFwdArgs p) {
       if (v < p.N) {
         Bn4 b;
         b.load(p.bn, c);
-        h = b.act(ld4(p.y + (size_t)v * HID + c));
+        h = b.act(ld4a<BF>(p.y, (size_t)v * HID + c));
         st4(p.H + (size_t)v * HID + c, h);
       }
       st4(sm.tile + r * GLD + c, h);
@@ -105,11 +108,12 @@ gate_lin_fwd_kernel(GateLinFwdArgs p) {
   }
 }
 void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(gate_lin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(GateLinFwdSmem)), true);
+  static bool once = (cudaFuncSetAttribute(gate_lin_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem)),
+                      cudaFuncSetAttribute(gate_lin_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem)), true);
   (void)once;
   const int grid = min((a.N + GT - 1) / GT, 2 * num_sms());
-  gate_lin_fwd_kernel<<<grid, kThreads, sizeof(GateLinFwdSmem), s>>>(a);
+  if (a.y_bf16) gate_lin_fwd_kernel<true><<<grid, kThreads, sizeof(GateLinFwdSmem), s>>>(a);
+  else gate_lin_fwd_kernel<false><<<grid, kThreads, sizeof(GateLinFwdSmem), s>>>(a);
 }
 
 // gH += g_q Wc1 ; dWc1 += g_q^T H ; dbc1 += sum g_q

@@ -14,7 +14,8 @@ void launch_transposes(const TransposeJobs& jobs, cudaStream_t s);
 // eval mode (model.eval()): bn = {running_mean, 1/sqrt(running_var + eps), gamma, beta} replaces the batch statistics a
 // GIN forward kernel has just written, before the next layer / the pooling kernels read them
 void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, cudaStream_t s);
-void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s);
+void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s, bool out_bf16 = false);
+void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
 
 struct GinFwdArgs {
   const float* in;          // [*, KIN]  t (layer 0) or the previous layer's pre-BN output y
@@ -43,6 +44,9 @@ int gin_fwd_grid(int V);
 void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
 void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // tcgen05 3xTF32, shared-memory window gather (gin_tc3.cu)
 void launch_gin_fwd_tc3_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, cudaStream_t s);
+// bf16 mode (gin_bf16.cu, gin_bwd_bf16.cu): the float* activation fields of the argument blocks point to bf16 data
+size_t gin_fwd_bf16_part_floats(int hidden);
+void launch_gin_fwd_bf16(const GinFwdArgs& a0, const GinFwdArgs* a1, int kin, int hidden, cudaStream_t s);
 int tensor_core_mode();                                                   // SCGIB_TC: 1 gin_tc3.cu (default), 0 FFMA cross-check
 inline bool use_tensor_cores() { return tensor_core_mode() != 0; }
 
@@ -80,6 +84,9 @@ void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_
 struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; int reverse = 0; };
 void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // tcgen05 3xTF32, 64-row double-buffered tiles (gin_bwd_tc2.cu)
 void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
+int gin_bwd_pre_bf16_grid(int V, int hidden);
+void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, int hidden, cudaStream_t s);
+void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s);
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
 
 struct InputProjBwdArgs {
@@ -101,9 +108,10 @@ void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s);
 // ---------------------------------------------------------------- head_kernels.cu
 // H = relu(BN(y_last)) materialised; q = H Wc1^T + bc1   (compressor.0, models.py:590)
 struct GateLinFwdArgs {
-  const float* y; const float* bn; int N;
+  const float* y; const float* bn; int N;   // y: fp32, or bf16 storage when y_bf16
   const float* Wc1t; const float* bc1;   // Wc1t [HID][HID] k-major
   float* H; float* q;
+  bool y_bf16 = false;
 };
 void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s);
 
@@ -121,6 +129,7 @@ struct EgoPoolFwdArgs {
   const float* y; const float* bn; const int32_t* ego_ptr; int N;
   const float* w_cand;                   // attn_layer.weight[0, HID:2*HID]
   float* C; float* logit;
+  bool y_bf16 = false;                   // y is bf16 storage (bf16 mode)
 };
 void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s);
 

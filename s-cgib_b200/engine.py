@@ -80,7 +80,7 @@ class DeviceBatch:
         b.eval_mode = int(bool(self.eval_mode))
         return b
 
-    def algorithmic_bytes(self, gin_layers=4, F=9, s=4):
+    def algorithmic_bytes(self, gin_layers=4, F=9, s=4):   # s = bytes per activation element (2 in bf16 mode)
         """SURVEY.md §8(d) 'algorithmic bytes per training step' evaluated on this batch's actual sizes."""
         N, E, Ns, Es, d = self.N, self.E, self.Ns, self.Es, HID
 
@@ -98,12 +98,18 @@ class DeviceBatch:
 
 class PretrainEngine:
     def __init__(self, in_dim: int, gin_layers: int = 4, hidden: int = 64, d_transfer: int = 32,
-                 device="cuda:0", seed: Optional[int] = None):
+                 device="cuda:0", seed: Optional[int] = None, dtype: str = "fp32"):
+        """``dtype``: "fp32" (reference precision, 1e-5) or "bf16" (the GIN encoders keep their activations in bf16 and run
+        single-pass bf16 tensor-core MLPs; parameters, gradients, optimiser state and all outputs stay fp32; 2e-2)."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("PretrainEngine needs a CUDA device: the hot path has no CPU fallback")
-        self.dims = _lib.Dims(int(in_dim), int(d_transfer), int(hidden), int(gin_layers))
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError("dtype must be 'fp32' or 'bf16'")
+        self.dtype = dtype
+        self.dims = _lib.Dims(int(in_dim), int(d_transfer), int(hidden), int(gin_layers),
+                              _lib.ACT_BF16 if dtype == "bf16" else _lib.ACT_F32)
         n = self.lib.scgib_param_slots(ctypes.byref(self.dims))
         if n < 0:
             _lib.check(n, "param_slots")
