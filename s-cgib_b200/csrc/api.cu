@@ -31,8 +31,8 @@ int bwd_tensor_core_mode() {
   if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
   return g_bwd_tc;
 }
-static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {
-  if (tensor_core_mode() == 0) launch_gin_fwd(a, kin, s);
+static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {      // op-level entry: hidden 64
+  if (tensor_core_mode() == 0) launch_gin_fwd(a, kin, HID, s);
   else launch_gin_fwd_tc3(a, kin, s);
 }
 
@@ -89,7 +89,7 @@ static inline void debug_check(const char* name, cudaStream_t s) {
 #define PROF(name, stmt) do { prof_begin(name, s); stmt; prof_end(s); debug_check(name, s); } while (0)
 
 static bool dims_ok(const ScgibDims* d) {
-  return d && d->hidden == HID && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&
+  return d && (d->hidden == 64 || d->hidden == 128) && d->d_transfer == DTR && d->gin_layers >= 1 && d->gin_layers <= 8 && d->in_dim >= 1 &&
          d->in_dim <= 32 && (d->act_dtype == SCGIB_ACT_F32 || d->act_dtype == SCGIB_ACT_BF16);
 }
 
@@ -103,7 +103,7 @@ struct Layout {
 
 static Layout make_layout(const ScgibDims* d) {
   Layout lo;
-  const int L = d->gin_layers;
+  const int L = d->gin_layers, HID = d->hidden;
   int64_t sizes[SCGIB_P_ENC] = {
       (int64_t)HID * 2 * HID, HID, (int64_t)HID * HID, HID,      // head
       (int64_t)HID * HID, HID, HID, HID, HID, 1,                  // compressor
@@ -144,7 +144,7 @@ struct Ws {
   size_t bytes;
 };
 
-static size_t small_part_floats(int N, int Ns) {
+static size_t small_part_floats(int N, int Ns, int HID) {
   const int Vmax = N > Ns ? N : Ns;
   size_t a = (size_t)((Vmax + 63) / 64) * 2 * HID;                   // gin fwd tile partials (64-row tiles)
   const size_t a2 = (size_t)num_sms() * 3 * HID * 2;                  // gin_tc2: per-CTA (n, mean, M2) in fp64
@@ -165,7 +165,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   // activations of the GIN encoders (t, a, r, y, the layer gradients g_o / Ga): fp32, or bf16 in bf16 mode - carved by bytes
   const size_t es = d->act_dtype == SCGIB_ACT_BF16 ? 2 : 4;
   auto take_act = [&](size_t nelems) { float* r = (float*)(p + o); o += al(nelems * es); return r; };
-  const int L = d->gin_layers;
+  const int L = d->gin_layers, HID = d->hidden;
   const int V[2] = {N, Ns};
   const int Vmax = N > Ns ? N : Ns;
   for (int e = 0; e < 2; ++e)
@@ -181,7 +181,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.head_w1t = take(2 * HID * HID); w.head_w2t = take(HID * HID); w.comp_w1t = take(HID * HID);
   w.t = take_act((size_t)N * DTR);
   w.cvec[0] = take(2 * HID); w.cvec[1] = take(2 * HID);
-  w.small_part = take(small_part_floats(N, Ns)); w.small_part2 = take(small_part_floats(N, Ns));
+  w.small_part = take(small_part_floats(N, Ns, HID)); w.small_part2 = take(small_part_floats(N, Ns, HID));
   w.counters = (unsigned int*)take(64);
   w.H = take((size_t)N * HID); w.q = take((size_t)N * HID); w.C = take((size_t)N * HID);
   w.logit = take(N); w.alpha = take(N); w.lam = take(N);
@@ -233,7 +233,7 @@ extern "C" SCGIB_API const char* scgib_error_string(int code) {
   switch (code) {
     case SCGIB_OK: return "ok";
     case SCGIB_E_NULL: return "required pointer is NULL";
-    case SCGIB_E_SHAPE: return "unsupported dimensions (hidden must be 64, d_transfer 32, 1 <= gin_layers <= 8, in_dim <= 32)";
+    case SCGIB_E_SHAPE: return "unsupported dimensions (hidden must be 64 or 128, d_transfer 32, 1 <= gin_layers <= 8, in_dim <= 32; --recons_type logM and the op-level entries: hidden 64)";
     case SCGIB_E_ALIGN: return "pointer not 16-byte aligned";
     case SCGIB_E_WORKSPACE: return "workspace too small";
     case SCGIB_E_RANGE: return "size out of range";
@@ -279,10 +279,12 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
-  const int L = d->gin_layers;
+  const int L = d->gin_layers, HID = d->hidden;
   const bool eval = b->eval_mode != 0;       // model.eval(): BatchNorm layers use (and do not update) their running statistics
   if (eval && !bn_running) return SCGIB_E_NULL;
   const bool bf = d->act_dtype == SCGIB_ACT_BF16;   // bf16 mode: GIN activations in bf16, single-pass bf16 tensor-core MLPs
+  const bool tc64 = HID == 64;                      // the 3xTF32 tcgen05 kernels (fp32 data) exist for hidden = 64; 128: FFMA tiles
+  if (b->recon_logm_steps > 0 && HID != 64 && !features_only) return SCGIB_E_SHAPE;   // --recons_type logM: hidden 64 only
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   // k-major weight copies for the forward GEMMs
@@ -331,23 +333,23 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     const int kin = l == 0 ? DTR : HID;
     if (bf) {
       PROF("gin_fwd_bf16.enc1+2", launch_gin_fwd_bf16(ga[0], &ga[1], kin, HID, s));
-    } else if (tensor_core_mode() != 0) {
+    } else if (tc64 && tensor_core_mode() != 0) {
       PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
     } else {
-      for (int e = 0; e < 2; ++e) PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, s));
+      for (int e = 0; e < 2; ++e) PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, HID, s));
     }
     if (eval)
       for (int e = 0; e < 2; ++e)
         launch_bn_from_running(bn_running + (size_t)(e * L + l) * 2 * HID, params + lo.enc(e, l, L, SCGIB_ENC_GAMMA),
-                               params + lo.enc(e, l, L, SCGIB_ENC_BETA), w.bn[e][l], s);
+                               params + lo.enc(e, l, L, SCGIB_ENC_BETA), w.bn[e][l], HID, s);
   }
   {
     GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q, bf};
-    PROF("gate_lin_fwd", launch_gate_lin_fwd(a, s));
+    PROF("gate_lin_fwd", launch_gate_lin_fwd(a, HID, s));
   }
   {
     EgoPoolFwdArgs a{w.y[1][L - 1], w.bn[1][L - 1], b->ego_ptr, b->N, params + lo.off[SCGIB_P_ATTN_W] + HID, w.C, w.logit, bf};
-    PROF("ego_pool_fwd", launch_ego_pool_fwd(a, s));
+    PROF("ego_pool_fwd", launch_ego_pool_fwd(a, HID, s));
   }
   {
     GraphGateFwdArgs a;
@@ -358,13 +360,13 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     a.noisy = w.noisy; a.lam = w.lam; a.alpha = w.alpha; a.readout = w.readout; a.core = w.core;
     a.gstat = w.gstat; a.cstat = (bn_running && !eval) ? w.cstat : nullptr; a.kl = w.kl;
     a.eval_running = eval ? bn_running + (size_t)2 * L * 2 * HID : nullptr;
-    PROF("graph_gate_fwd", launch_graph_gate_fwd(a, s));
-    if (bn_running && !eval) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, s));
+    PROF("graph_gate_fwd", launch_graph_gate_fwd(a, HID, s));
+    if (bn_running && !eval) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, HID, s));
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
                   params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.aC, w.r_head, w.Z};
-    PROF("head_fwd", launch_head_fwd(a, s));
+    PROF("head_fwd", launch_head_fwd(a, HID, s));
   }
   const int logm = b->recon_logm_steps;
   if (!features_only && logm > 0) {
@@ -373,21 +375,21 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   } else if (!features_only) {
     const int grid = num_sms();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
-    PROF("recon_fwd", launch_recon_fwd(a, grid, s));
-    PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, s));
+    PROF("recon_fwd", launch_recon_fwd(a, HID, grid, s));
+    PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, HID, s));
   }
   const int js = contrastive_jsplit(b->B);
   if (!features_only) {
-    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
-    PROF("normalize", launch_normalize(a, s));
+    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag, tc64 ? w.zsplit : nullptr};
+    PROF("normalize", launch_normalize(a, HID, s));
     ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum, w.zsplit};
-    if (use_tc_contrastive())
+    if (tc64 && use_tc_contrastive())
       PROF("contrastive_fwd_tc", launch_contrastive_fwd_tc(c, s));
     else
-      PROF("contrastive_fwd", launch_contrastive_fwd(c, s));
+      PROF("contrastive_fwd", launch_contrastive_fwd(c, HID, s));
   }
   if (!features_only) {
-    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses};
+    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses, HID};
     PROF("loss_finalize", launch_loss_finalize(a, s));
   }
   if (Z) cudaMemcpyAsync(Z, w.Z, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -426,10 +428,12 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   const Ws w = carve(d, lo, b->B, b->N, b->E, b->Ns, b->Es, workspace);
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
-  const int L = d->gin_layers;
+  const int L = d->gin_layers, HID = d->hidden;
   const int GP = num_sms();
   const float s_kl = loss_scale[0], s_con = loss_scale[1], s_rec = loss_scale[2];
   const bool bf = d->act_dtype == SCGIB_ACT_BF16;
+  const bool tc_bwd = HID == 64 && bwd_tensor_core_mode() != 0;    // 3xTF32 tcgen05 backward (fp32 data): hidden 64; else FFMA tiles
+  if (b->recon_logm_steps > 0 && HID != 64 && !gZ_ext) return SCGIB_E_SHAPE;
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
   const int js = contrastive_jsplit(b->B);
@@ -440,28 +444,27 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     cudaMemsetAsync(w.g_readout, 0, (size_t)b->B * HID * sizeof(float), s);
   } else {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
-    if (use_tc_contrastive())
+    if (HID == 64 && use_tc_contrastive())
       PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc(a, w.zsplit, s));
     else
-      PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, s));
+      PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, HID, s));
     ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
-    PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, s));
+    PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, HID, s));
     if (b->recon_logm_steps > 0) {
       PROF("logm_bwd", launch_logm_bwd(w.Z, b->graph_ptr, b->indptr, b->indices, b->B, b->N, b->recon_logm_steps, w.logm_walks,
                                        s_rec, w.gZ, (int32_t*)(w.counters + 32), s));
     } else {
       ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
-      PROF("recon_bwd", launch_recon_bwd(ra, s));
+      PROF("recon_bwd", launch_recon_bwd(ra, HID, s));
     }
   }
-  // head MLP backward.  Tensor-core path: Z = W2 relu(W1a noisy + W1b (alpha C) + b1) + b2 is the GIN MLP with its first
-  // layer split over two K = 64 inputs, so its backward is the GIN backward kernel run on both halves in ONE launch
-  // (problem 0: a = noisy, W1a -> gI[:, :64], dW1a, dW2, db1, db2; problem 1: a = alpha C, W1b -> gI[:, 64:], dW1b; its
-  // duplicate dW2 / bias partials are not reduced) with an identity BatchNorm backward (g_y = gZ).
-  const bool head_tc = bwd_tensor_core_mode() != 0;
-  const int head_split = pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128);
-  if (head_tc) {
-    PROF("head_bwd_prep", launch_head_bwd_prep(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1a, w.head_w1b, w.head_bn, w.head_cvec, s));
+  // head MLP backward: Z = W2 relu(W1a noisy + W1b (alpha C) + b1) + b2 is the GIN MLP with its first layer split over two
+  // K = H inputs, so its backward is the GIN backward kernel run on both halves (problem 0: a = noisy, W1a -> gI[:, :H], dW1a,
+  // dW2, db1, db2; problem 1: a = alpha C, W1b -> gI[:, H:], dW1b; its duplicate dW2 / bias partials are not reduced) with an
+  // identity BatchNorm backward (g_y = gZ).  tcgen05 kernel: both problems in ONE launch (CTAs split); FFMA tiles: two launches.
+  const int head_split = tc_bwd ? pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128) : GP;
+  {
+    PROF("head_bwd_prep", launch_head_bwd_prep(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1a, w.head_w1b, w.head_bn, w.head_cvec, HID, s));
     GinBwdMainArgs m[2];
     for (int h = 0; h < 2; ++h) {
       m[h].g_o = w.gZ; m[h].y = w.Z; m[h].r = w.r_head; m[h].a = h == 0 ? w.noisy : w.aC;
@@ -471,12 +474,12 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m[h].off_W1 = lo.off[SCGIB_P_HEAD_W1] + (int64_t)h * HID * HID; m[h].off_b1 = lo.off[SCGIB_P_HEAD_B1];
       m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
     }
-    PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
-  } else {
-    HeadBwdArgs a{w.gZ, w.noisy, w.C, w.alpha, w.r_head, b->N, params + lo.off[SCGIB_P_HEAD_W1],
-                  params + lo.off[SCGIB_P_HEAD_W2], w.gI, w.ppart, lo.total,
-                  lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_W2], lo.off[SCGIB_P_HEAD_B2]};
-    PROF("head_bwd", launch_head_bwd(a, GP, s));
+    if (tc_bwd) {
+      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
+    } else {
+      PROF("head_bwd_ffma.a", launch_gin_bwd_main(m[0], HID, HID, GP, s));
+      PROF("head_bwd_ffma.b", launch_gin_bwd_main(m[1], HID, HID, GP, s));   // rewrites the (identical) dW2 / bias partials of .a
+    }
   }
   {
     GraphGateBwdArgs a;
@@ -484,22 +487,22 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     a.gamma_c = params + lo.off[SCGIB_P_COMP_GAMMA]; a.beta_c = params + lo.off[SCGIB_P_COMP_BETA];
     a.wc2 = params + lo.off[SCGIB_P_COMP_W2]; a.w_cand = params + lo.off[SCGIB_P_ATTN_W] + HID;
     a.feat_u = b->feat_u; a.lam = w.lam; a.alpha = w.alpha; a.gstat = w.gstat;
-    a.gI = w.gI; a.gI2 = head_tc ? w.gI + (size_t)b->N * HID : w.gI + HID; a.gI_stride = head_tc ? HID : 2 * HID;
+    a.gI = w.gI; a.gI2 = w.gI + (size_t)b->N * HID; a.gI_stride = HID;      // dense halves [N][H] | [N][H]
     a.g_core = w.g_core; a.g_readout = w.g_readout; a.kl_scale = s_kl;
     a.gp = w.gp; a.g_q = w.g_q; a.gH = w.gH; a.gC = w.gC;
     a.part = w.small_part; a.counter = w.counters + 1;
     a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
     a.d_wc2 = grads + lo.off[SCGIB_P_COMP_W2]; a.d_bc2 = grads + lo.off[SCGIB_P_COMP_B2];
     a.d_attn_w = grads + lo.off[SCGIB_P_ATTN_W]; a.d_attn_b = grads + lo.off[SCGIB_P_ATTN_B];
-    PROF("graph_gate_bwd", launch_graph_gate_bwd(a, s));
+    PROF("graph_gate_bwd", launch_graph_gate_bwd(a, HID, s));
   }
   {
     GateLinBwdArgs a{w.g_q, w.H, b->N, params + lo.off[SCGIB_P_COMP_W1], w.gH, w.ppart, lo.total,
                      lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1]};
-    PROF("gate_lin_bwd", launch_gate_lin_bwd(a, GP, s));
+    PROF("gate_lin_bwd", launch_gate_lin_bwd(a, HID, GP, s));
   }
   const int enc_split = pair_split(GP, (b->N + 127) / 128, (b->Ns + 127) / 128);   // CTAs of Encoder1 in a shared launch
-  const bool pair_main = bf || bwd_tensor_core_mode() != 0;
+  const bool pair_main = bf || tc_bwd;
   for (int l = L - 1; l >= 0; --l) {
     const int kin = l == 0 ? DTR : HID;
     GinBwdPreArgs pa[2];
@@ -528,12 +531,12 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       PROF("gin_bwd_main_bf16.enc1+2", launch_gin_bwd_main_bf16(ma[0], &ma[1], kin, HID, GP, s));
       continue;
     }
-    PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], s));
+    PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], HID, s));
     if (pair_main) {
       PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
     } else {
-      PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, GP, s));
-      PROF("gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma[1], kin, GP, s));
+      PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, HID, GP, s));
+      PROF("gin_bwd_main_ffma.enc2", launch_gin_bwd_main(ma[1], kin, HID, GP, s));
     }
   }
   {
@@ -549,20 +552,18 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     ReduceRanges r;
     r.n = 0;
     auto add = [&](int64_t off, int64_t len, int c0, int c1) { r.off[r.n] = off; r.len[r.n] = len; r.c0[r.n] = c0; r.c1[r.n] = c1; ++r.n; };
-    if (head_tc) {     // partial rows [0, head_split): problem 0 (dW1a and everything else), [head_split, GP): problem 1 (dW1b)
-      add(lo.off[SCGIB_P_HEAD_W1], (int64_t)HID * HID, 0, head_split);
-      add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, head_split, GP);
-      add(lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_B1], 0, head_split);
-    } else {
-      add(lo.off[SCGIB_P_HEAD_W1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_W1], 0, GP);
-    }
+    // shared tcgen05 launch: partial rows [0, head_split) = problem 0 (dW1a and everything else), [head_split, GP) = problem 1
+    // (dW1b); FFMA: two launches, every partial row holds both
+    add(lo.off[SCGIB_P_HEAD_W1], (int64_t)HID * HID, 0, head_split);
+    add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, tc_bwd ? head_split : 0, GP);
+    add(lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_B1], 0, head_split);
     add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1], 0, GP);
     for (int e = 0; e < 2; ++e)        // shared launches: partial rows [0, split) belong to Encoder1, [split, GP) to Encoder2
       for (int l = 0; l < L; ++l)
         add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1),
             pair_main ? (e == 0 ? 0 : enc_split) : 0, pair_main ? (e == 0 ? enc_split : GP) : GP);
     PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
-    if (head_tc) PROF("head_dw1_interleave", launch_head_dw1_interleave(grads + lo.off[SCGIB_P_HEAD_W1], s));
+    PROF("head_dw1_interleave", launch_head_dw1_interleave(grads + lo.off[SCGIB_P_HEAD_W1], HID, s));
   }
   return (int)cudaGetLastError();
 }
@@ -796,12 +797,12 @@ extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int3
   q.src = g_next; q.indptr = indptr; q.indices = indptr ? indices : nullptr; q.map = nullptr;
   q.y = y; q.bn = bn; q.V = V; q.g_o = w.g_o; q.part = w.part2; q.counter = w.counter;
   q.d_gamma = dgamma; q.d_beta = dbeta; q.cvec = w.cvec;
-  launch_gin_bwd_pre(q, s);
+  launch_gin_bwd_pre(q, HID, s);
   GinBwdMainArgs m;
   m.g_o = w.g_o; m.y = y; m.r = r; m.a = a; m.bn = bn; m.cvec = w.cvec; m.W1 = W1; m.W2 = W2; m.V = V; m.g_a = g_a;
   m.part = w.ppart; m.pstride = w.pstride; m.off_W1 = w.off[0]; m.off_b1 = w.off[1]; m.off_W2 = w.off[2]; m.off_b2 = w.off[3];
   if (bwd_tensor_core_mode() != 0) launch_gin_bwd_main_tc2(m, kin, GP, s);
-  else launch_gin_bwd_main(m, kin, GP, s);
+  else launch_gin_bwd_main(m, kin, HID, GP, s);
   // per-CTA partials -> the four gradient tensors (fixed order)
   float* outs[4] = {dW1, db1, dW2, db2};
   const int64_t lens[4] = {(int64_t)HID * kin, HID, (int64_t)HID * HID, HID};
@@ -843,8 +844,8 @@ extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indp
   cudaStream_t s = (cudaStream_t)stream_;
   const int grid = num_sms();
   ReconFwdArgs a{Z, indptr, indices, N, w.rpart};
-  launch_recon_fwd(a, grid, s);
-  launch_recon_reduce(w.rpart, grid, w.G, w.edge, s);
+  launch_recon_fwd(a, HID, grid, s);
+  launch_recon_reduce(w.rpart, grid, w.G, w.edge, HID, s);
   cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
   cudaMemsetAsync(w.rowsum, 0, sizeof(float), s);
   cudaMemsetAsync(w.diag, 0, sizeof(float), s);
@@ -853,7 +854,7 @@ extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indp
   cudaMemcpyAsync(loss, w.losses + 2, sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (gZ) {
     ReconBwdArgs ra{Z, w.G, indptr, indices, N, scale, gZ};
-    launch_recon_bwd(ra, s);
+    launch_recon_bwd(ra, HID, s);
   }
   return (int)cudaGetLastError();
 }
@@ -869,9 +870,9 @@ extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* r
   cudaStream_t s = (cudaStream_t)stream_;
   const int js = contrastive_jsplit(B);
   NormalizeArgs na{core, readout, B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
-  launch_normalize(na, s);
+  launch_normalize(na, HID, s);
   ContrastiveFwdArgs c{w.z1, w.z2, B, js, w.rowsum, w.zsplit};
-  if (use_tc_contrastive()) launch_contrastive_fwd_tc(c, s); else launch_contrastive_fwd(c, s);
+  if (use_tc_contrastive()) launch_contrastive_fwd_tc(c, s); else launch_contrastive_fwd(c, HID, s);
   cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
   cudaMemsetAsync(w.G, 0, HID * HID * sizeof(float), s);
   cudaMemsetAsync(w.edge, 0, 4 * sizeof(float), s);
@@ -880,9 +881,9 @@ extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* r
   cudaMemcpyAsync(loss, w.losses + 1, sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (g_core) {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, B, js, w.g1p, w.g2p};
-    if (use_tc_contrastive()) launch_contrastive_bwd_tc(a, w.zsplit, s); else launch_contrastive_bwd(a, s);
+    if (use_tc_contrastive()) launch_contrastive_bwd_tc(a, w.zsplit, s); else launch_contrastive_bwd(a, HID, s);
     ContrastiveBwdFinArgs fa{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, B, js, scale, g_core, g_readout};
-    launch_contrastive_bwd_finalize(fa, s);
+    launch_contrastive_bwd_finalize(fa, HID, s);
   }
   return (int)cudaGetLastError();
 }
@@ -890,7 +891,7 @@ extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* r
 extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn, float* out, void* stream) {
   if (!in || !seg_ptr || !out) return SCGIB_E_NULL;
   if (S < 1) return SCGIB_E_RANGE;
-  launch_segment_sum(in, seg_ptr, S, bn, out, (cudaStream_t)stream);
+  launch_segment_sum(in, seg_ptr, S, bn, out, HID, (cudaStream_t)stream);
   return (int)cudaGetLastError();
 }
 

@@ -61,8 +61,8 @@ __device__ __forceinline__ float4 relu4(float4 a) {
 // relu(BN(y)) for 4 consecutive channels: ((y - mean) * rstd) * gamma + beta
 struct Bn4 {
   float4 mean, rstd, gamma, beta;
-  __device__ __forceinline__ void load(const float* bn, int c) {  // bn = {mean[H], rstd[H], gamma[H], beta[H]}
-    mean = ldg4(bn + c); rstd = ldg4(bn + HID + c); gamma = ldg4(bn + 2 * HID + c); beta = ldg4(bn + 3 * HID + c);
+  __device__ __forceinline__ void load(const float* bn, int c, int H = HID) {  // bn = {mean[H], rstd[H], gamma[H], beta[H]}
+    mean = ldg4(bn + c); rstd = ldg4(bn + H + c); gamma = ldg4(bn + 2 * H + c); beta = ldg4(bn + 3 * H + c);
   }
   __device__ __forceinline__ float4 xhat(float4 y) const {
     return make_float4((y.x - mean.x) * rstd.x, (y.y - mean.y) * rstd.y, (y.z - mean.z) * rstd.z, (y.w - mean.w) * rstd.w);

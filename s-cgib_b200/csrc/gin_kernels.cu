@@ -61,7 +61,7 @@ void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) { 
 }
 
 __global__ void bn_from_running_kernel(const float* __restrict__ running, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ bn) {
+                                       const float* __restrict__ beta, float* __restrict__ bn, int HID) {
   const int c = threadIdx.x;
   if (c >= HID) return;
   bn[c] = running[c];
@@ -69,8 +69,8 @@ __global__ void bn_from_running_kernel(const float* __restrict__ running, const 
   bn[2 * HID + c] = gamma[c];
   bn[3 * HID + c] = beta[c];
 }
-void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, cudaStream_t s) {
-  bn_from_running_kernel<<<1, HID, 0, s>>>(running, gamma, beta, bn);
+void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, int hidden, cudaStream_t s) {
+  bn_from_running_kernel<<<1, hidden, 0, s>>>(running, gamma, beta, bn, hidden);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -91,10 +91,10 @@ void launch_transposes(const TransposeJobs& jobs, cudaStream_t s) {
 // GIN layer forward
 // ------------------------------------------------------------------------------------------------
 constexpr int GT = 128;        // rows per tile
-constexpr int GLD = HID + 4;   // smem leading dim (row-major tiles)
 
-template <int KIN>
+template <int KIN, int HID>
 struct GinFwdSmem {
+  static constexpr int GLD = HID + 4;   // smem leading dim (row-major tiles)
   float tile[GT * GLD];        // A tile [GT][KIN+4] then R tile [GT][HID+4]
   float w1t[KIN * HID];
   float w2t[HID * HID];
@@ -103,11 +103,12 @@ struct GinFwdSmem {
   double dred[4 * HID];
 };
 
-template <int KIN>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int KIN, int HID>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 gin_fwd_kernel(GinFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GinFwdSmem<KIN>& sm = *reinterpret_cast<GinFwdSmem<KIN>*>(smem_raw);
+  GinFwdSmem<KIN, HID>& sm = *reinterpret_cast<GinFwdSmem<KIN, HID>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   constexpr int LDA = KIN + 4;
   constexpr int LPR = KIN / 4;             // lanes per row in the gather
   constexpr int RPP = kThreads / LPR;      // rows per pass
@@ -121,23 +122,26 @@ gin_fwd_kernel(GinFwdArgs p) {
   const int gl = threadIdx.x % LPR, gr = threadIdx.x / LPR;
   Bn4 bn;
   const bool has_bn = (p.bn_in != nullptr);
-  if (has_bn) bn.load(p.bn_in, gl * 4);   // KIN == HID whenever a BN precedes the layer
+  if (has_bn) bn.load(p.bn_in, gl * 4, HID);   // KIN == HID whenever a BN precedes the layer
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * GT;
     __syncthreads();  // previous tile's readers of sm.tile are done (also covers the weight loads)
     // ---- gather-aggregate: a_v = f(in[map(v)]) + sum_u f(in[map(u)])   (all row passes of the thread interleaved)
     {
-      constexpr int NR = GT / RPP;
-      int vv[NR];
-      float4 agg[NR];
+      constexpr int NRT = GT / RPP, NR = NRT < 8 ? NRT : 8;    // row passes of the thread, at most 8 in flight together
+#pragma unroll 1
+      for (int j0 = 0; j0 < NRT; j0 += NR) {
+        int vv[NR];
+        float4 agg[NR];
 #pragma unroll
-      for (int j = 0; j < NR; ++j) vv[j] = base + gr + j * RPP;
-      gather_aggregate<KIN, NR>(p.in, p.row_map, p.indptr, p.indices, p.V, vv, gl, has_bn ? &bn : nullptr, agg);
+        for (int j = 0; j < NR; ++j) vv[j] = base + gr + (j0 + j) * RPP;
+        gather_aggregate<KIN, NR>(p.in, p.row_map, p.indptr, p.indices, p.V, vv, gl, has_bn ? &bn : nullptr, agg);
 #pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        if (p.a_out && vv[j] < p.V) st4(p.a_out + (size_t)vv[j] * KIN + gl * 4, agg[j]);
-        st4(sm.tile + (gr + j * RPP) * LDA + gl * 4, agg[j]);
+        for (int j = 0; j < NR; ++j) {
+          if (p.a_out && vv[j] < p.V) st4(p.a_out + (size_t)vv[j] * KIN + gl * 4, agg[j]);
+          st4(sm.tile + (gr + (j0 + j) * RPP) * LDA + gl * 4, agg[j]);
+        }
       }
     }
     __syncthreads();
@@ -206,18 +210,22 @@ gin_fwd_kernel(GinFwdArgs p) {
   }
   // ---- batch statistics: last CTA combines the per-tile (n, mean, M2) in fp64, fixed order
   if (!last_cta_arrives(p.counter)) return;
-  const int c = threadIdx.x & (HID - 1), seg = threadIdx.x >> 6;
+  constexpr int NSEG = kThreads / HID;     // interleaved segments per column (4 at HID = 64, 2 at HID = 128)
+  const int c = threadIdx.x % HID, seg = threadIdx.x / HID;
   double s = 0.0;
-  for (int t = seg; t < n_tiles; t += 4) {
+  for (int t = seg; t < n_tiles; t += NSEG) {
     const double n = (double)min(GT, p.V - t * GT);
     s += n * (double)__ldcg(p.part + (size_t)t * 2 * HID + c);
   }
   sm.dred[seg * HID + c] = s;
   __syncthreads();
-  const double mean = (sm.dred[c] + sm.dred[HID + c] + sm.dred[2 * HID + c] + sm.dred[3 * HID + c]) / (double)p.V;
+  double msum = 0.0;
+#pragma unroll
+  for (int g = 0; g < NSEG; ++g) msum += sm.dred[g * HID + c];
+  const double mean = msum / (double)p.V;
   __syncthreads();
   double q = 0.0;
-  for (int t = seg; t < n_tiles; t += 4) {
+  for (int t = seg; t < n_tiles; t += NSEG) {
     const double n = (double)min(GT, p.V - t * GT);
     const double d = (double)__ldcg(p.part + (size_t)t * 2 * HID + c) - mean;
     q += (double)__ldcg(p.part + (size_t)t * 2 * HID + HID + c) + n * d * d;
@@ -225,7 +233,10 @@ gin_fwd_kernel(GinFwdArgs p) {
   sm.dred[seg * HID + c] = q;
   __syncthreads();
   if (threadIdx.x < HID) {
-    const double var = (sm.dred[c] + sm.dred[HID + c] + sm.dred[2 * HID + c] + sm.dred[3 * HID + c]) / (double)p.V;
+    double qsum = 0.0;
+#pragma unroll
+    for (int g = 0; g < NSEG; ++g) qsum += sm.dred[g * HID + c];
+    const double var = qsum / (double)p.V;
     p.bn_out[c] = (float)mean;
     p.bn_out[HID + c] = (float)(1.0 / sqrt(var + (double)kBnEps));
     if (p.gamma) { p.bn_out[2 * HID + c] = p.gamma[c]; p.bn_out[3 * HID + c] = p.beta[c]; }
@@ -242,19 +253,18 @@ int gin_fwd_grid(int V) {
   return min(n_tiles, 2 * num_sms());
 }
 
-void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
-  const int grid = gin_fwd_grid(a.V);
-  if (kin == DTR) {
-    static bool once = (cudaFuncSetAttribute(gin_fwd_kernel<DTR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(GinFwdSmem<DTR>)), true);
-    (void)once;
-    gin_fwd_kernel<DTR><<<grid, kThreads, sizeof(GinFwdSmem<DTR>), s>>>(a);
-  } else {
-    static bool once = (cudaFuncSetAttribute(gin_fwd_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(GinFwdSmem<HID>)), true);
-    (void)once;
-    gin_fwd_kernel<HID><<<grid, kThreads, sizeof(GinFwdSmem<HID>), s>>>(a);
-  }
+template <int KIN, int H>
+static void launch_gin_fwd_t(const GinFwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(gin_fwd_kernel<KIN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(GinFwdSmem<KIN, H>)), true);
+  (void)once;
+  const int n_tiles = (a.V + GT - 1) / GT;
+  const int grid = min(n_tiles, (H == 64 ? 2 : 1) * num_sms());
+  gin_fwd_kernel<KIN, H><<<grid, kThreads, sizeof(GinFwdSmem<KIN, H>), s>>>(a);
+}
+void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s) {
+  if (hidden == 64) { if (kin == DTR) launch_gin_fwd_t<DTR, 64>(a, s); else launch_gin_fwd_t<64, 64>(a, s); }
+  else { if (kin == DTR) launch_gin_fwd_t<DTR, 128>(a, s); else launch_gin_fwd_t<128, 128>(a, s); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,24 +274,26 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s) {
 //   g_o = G * [gamma*yhat+beta > 0] ; dbeta = sum g_o ; dgamma = sum g_o*yhat
 // Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
 // ------------------------------------------------------------------------------------------------
+template <int HID>
 __global__ void __launch_bounds__(kThreads, 2)
 gin_bwd_pre_kernel(GinBwdPrePair pp) {
   const bool second = (int)blockIdx.x >= pp.split;
   const GinBwdPreArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
   const int nblk = second ? (int)gridDim.x - pp.split : pp.split;
-  __shared__ __align__(16) float s_red[16 * 2 * HID];
-  __shared__ double s_d[2 * 2 * HID];
-  const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  constexpr int LPR = HID / 4, RPC = kThreads / LPR;       // lanes per row (4 channels each), rows per CTA pass
+  __shared__ __align__(16) float s_red[RPC * 2 * HID];
+  __shared__ double s_d[kThreads];
+  const int l = threadIdx.x % LPR, hw = threadIdx.x / LPR;
   Bn4 bn;
-  bn.load(p.bn, l * 4);
+  bn.load(p.bn, l * 4, HID);
   float4 db = make4(0.f), dg = make4(0.f);
   constexpr int NR = 4;
-  for (int v0 = bid * 16 + hw; v0 < p.V; v0 += nblk * 16 * NR) {
+  for (int v0 = bid * RPC + hw; v0 < p.V; v0 += nblk * RPC * NR) {
     int vv[NR];
     float4 g[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) vv[j] = v0 + j * nblk * 16;
+    for (int j = 0; j < NR; ++j) vv[j] = v0 + j * nblk * RPC;
     float4 y[NR];   // issued first: independent of the gather's dependent index chain
 #pragma unroll
     for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4_cs(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
@@ -312,20 +324,22 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
   if (threadIdx.x < 2 * HID) {
     float s = 0.f;
 #pragma unroll
-    for (int h = 0; h < 16; ++h) s += s_red[h * 2 * HID + threadIdx.x];
+    for (int h = 0; h < RPC; ++h) s += s_red[h * 2 * HID + threadIdx.x];
     p.part[(size_t)bid * 2 * HID + threadIdx.x] = s;
   }
   if (!last_cta_arrives(p.counter, (unsigned)nblk)) return;
-  // 256 threads: column j = tid & 127 (0..63 dbeta, 64..127 dgamma), 2 interleaved segments, batched loads
+  // 256 threads: column j (0..H-1 dbeta, H..2H-1 dgamma), NSEG interleaved segments, batched loads
+  constexpr int NSEG = kThreads / (2 * HID);
   {
-    const int j = threadIdx.x & (2 * HID - 1), seg = threadIdx.x >> 7;
-    s_d[seg * 2 * HID + j] = sum_partials(p.part + j, 2 * HID, nblk, seg, 2);
+    const int j = threadIdx.x % (2 * HID), seg = threadIdx.x / (2 * HID);
+    s_d[seg * 2 * HID + j] = sum_partials(p.part + j, 2 * HID, nblk, seg, NSEG);
   }
   __syncthreads();
   if (threadIdx.x < HID) {
     const int c = threadIdx.x;
-    const double dbeta = s_d[c] + s_d[2 * HID + c];
-    const double dgamma = s_d[HID + c] + s_d[2 * HID + HID + c];
+    double dbeta = 0.0, dgamma = 0.0;
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg) { dbeta += s_d[sg * 2 * HID + c]; dgamma += s_d[sg * 2 * HID + HID + c]; }
     p.d_beta[c] = (float)dbeta;
     p.d_gamma[c] = (float)dgamma;
     const double gamma = (double)p.bn[2 * HID + c];
@@ -336,12 +350,13 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
 
 int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, 2 * num_sms()); }   // 2 resident CTAs per SM, 64 rows per pass
 
-void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s) {
+void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s) {
   GinBwdPrePair pp;
   pp.a[0] = a; pp.a[1] = a;
   const int grid = gin_bwd_pre_grid(a.V);
   pp.split = grid;
-  gin_bwd_pre_kernel<<<grid, kThreads, 0, s>>>(pp);
+  if (hidden == 64) gin_bwd_pre_kernel<64><<<grid, kThreads, 0, s>>>(pp);
+  else gin_bwd_pre_kernel<128><<<grid, kThreads, 0, s>>>(pp);
 }
 
 int pair_split(int grid, int work0, int work1) {
@@ -350,12 +365,13 @@ int pair_split(int grid, int work0, int work1) {
   return max(1, min(grid - 1, s0));
 }
 
-void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, cudaStream_t s) {
+void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, int hidden, cudaStream_t s) {
   GinBwdPrePair pp;
   pp.a[0] = a0; pp.a[1] = a1;
   const int grid = max(2, gin_bwd_pre_grid(a0.V + a1.V));
   pp.split = pair_split(grid, a0.V, a1.V);
-  gin_bwd_pre_kernel<<<grid, kThreads, 0, s>>>(pp);
+  if (hidden == 64) gin_bwd_pre_kernel<64><<<grid, kThreads, 0, s>>>(pp);
+  else gin_bwd_pre_kernel<128><<<grid, kThreads, 0, s>>>(pp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,8 +380,9 @@ void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, c
 //   g_u = (g_y W2) * [r > 0] ; g_a = g_u W1 -> Ga
 //   dW2 += g_y^T r ; db2 += sum g_y ; dW1 += g_u^T a ; db1 += sum g_u     (per-CTA partials)
 // ------------------------------------------------------------------------------------------------
-template <int KIN>
+template <int KIN, int HID, int GT>
 struct GinBwdSmem {
+  static constexpr int GLD = HID + 4;
   float gy[GT * GLD];
   float gu[GT * GLD];
   float r[GT * GLD];
@@ -374,11 +391,13 @@ struct GinBwdSmem {
   float w1[HID * KIN];     // natural [out][in]  = k-major for g_u W1
 };
 
-template <int KIN>
+// GT = rows per tile (128 at HID = 64; 32 at HID = 128: three [GT][HID] tiles + both weight matrices must fit 227 KB)
+template <int KIN, int HID, int GT>
 __global__ void __launch_bounds__(kThreads, 1)
 gin_bwd_main_kernel(GinBwdMainArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GinBwdSmem<KIN>& sm = *reinterpret_cast<GinBwdSmem<KIN>*>(smem_raw);
+  GinBwdSmem<KIN, HID, GT>& sm = *reinterpret_cast<GinBwdSmem<KIN, HID, GT>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   constexpr int LDA = KIN + 4;
   using M2 = NNMap<GT, HID>;   // g_r tile
   using M1 = NNMap<GT, KIN>;   // g_a tile
@@ -485,18 +504,16 @@ gin_bwd_main_kernel(GinBwdMainArgs p) {
   else if (threadIdx.x < 2 * HID) part[p.off_b1 + threadIdx.x - HID] = dbias;
 }
 
-void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s) {
-  if (kin == DTR) {
-    static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<DTR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(GinBwdSmem<DTR>)), true);
-    (void)once;
-    gin_bwd_main_kernel<DTR><<<grid, kThreads, sizeof(GinBwdSmem<DTR>), s>>>(a);
-  } else {
-    static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(GinBwdSmem<HID>)), true);
-    (void)once;
-    gin_bwd_main_kernel<HID><<<grid, kThreads, sizeof(GinBwdSmem<HID>), s>>>(a);
-  }
+template <int KIN, int H, int GTB>
+static void launch_gin_bwd_main_t(const GinBwdMainArgs& a, int grid, cudaStream_t s) {
+  using S = GinBwdSmem<KIN, H, GTB>;
+  static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<KIN, H, GTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
+  (void)once;
+  gin_bwd_main_kernel<KIN, H, GTB><<<grid, kThreads, sizeof(S), s>>>(a);
+}
+void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s) {
+  if (hidden == 64) { if (kin == DTR) launch_gin_bwd_main_t<DTR, 64, 128>(a, grid, s); else launch_gin_bwd_main_t<64, 64, 128>(a, grid, s); }
+  else { if (kin == DTR) launch_gin_bwd_main_t<DTR, 128, 32>(a, grid, s); else launch_gin_bwd_main_t<128, 128, 32>(a, grid, s); }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,18 +12,19 @@
 namespace scgib {
 
 constexpr int GT = 128;
-constexpr int GLD = HID + 4;
 
 // ------------------------------------------------------------------------------------------------
 // segment sums (half-warp per segment, float4 lanes)
 // ------------------------------------------------------------------------------------------------
+template <int HID>
 __global__ void __launch_bounds__(kThreads)
 segment_sum_kernel(const float* __restrict__ in, const int32_t* __restrict__ seg_ptr, int S, const float* __restrict__ bn,
                    float* __restrict__ out) {
-  const int l = threadIdx.x & 15;
+  constexpr int LPR = HID / 4, SPC = kThreads / LPR;      // lanes per segment (4 channels each), segments per CTA pass
+  const int l = threadIdx.x % LPR;
   Bn4 b;
-  if (bn) b.load(bn, l * 4);
-  for (int s = blockIdx.x * 16 + (threadIdx.x >> 4); s < S; s += gridDim.x * 16) {
+  if (bn) b.load(bn, l * 4, HID);
+  for (int s = blockIdx.x * SPC + (threadIdx.x / LPR); s < S; s += gridDim.x * SPC) {
     const int r0 = __ldg(seg_ptr + s), r1 = __ldg(seg_ptr + s + 1);
     float4 acc = make4(0.f);
     for (int r = r0; r < r1; ++r) {
@@ -33,48 +34,58 @@ segment_sum_kernel(const float* __restrict__ in, const int32_t* __restrict__ seg
     st4(out + (size_t)s * HID + l * 4, acc);
   }
 }
-void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, cudaStream_t s) {
-  const int grid = min((S + 15) / 16, 16 * num_sms());
-  segment_sum_kernel<<<grid, kThreads, 0, s>>>(in, seg_ptr, S, bn, out);
+void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, int hidden, cudaStream_t s) {
+  const int spc = kThreads / (hidden / 4);
+  const int grid = min((S + spc - 1) / spc, 16 * num_sms());
+  if (hidden == 64) segment_sum_kernel<64><<<grid, kThreads, 0, s>>>(in, seg_ptr, S, bn, out);
+  else segment_sum_kernel<128><<<grid, kThreads, 0, s>>>(in, seg_ptr, S, bn, out);
 }
 
 // C_v = sum over the ego-net of v of relu(BN(y)) ; logit_v = w_cand . C_v
-template <bool BF>
+template <bool BF, int HID>
 __global__ void __launch_bounds__(kThreads)
 ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
-  const int l = threadIdx.x & 15;
+  constexpr int LPR = HID / 4, SPC = kThreads / LPR;      // 16 lanes (half-warp) per seed at HID = 64, a full warp at 128
+  const int l = threadIdx.x % LPR;
   Bn4 b;
-  b.load(p.bn, l * 4);
+  b.load(p.bn, l * 4, HID);
   const float4 w = ldg4(p.w_cand + l * 4);
-  for (int v = blockIdx.x * 16 + (threadIdx.x >> 4); v < p.N; v += gridDim.x * 16) {
+  for (int v = blockIdx.x * SPC + (threadIdx.x / LPR); v < p.N; v += gridDim.x * SPC) {
     const int r0 = __ldg(p.ego_ptr + v), r1 = __ldg(p.ego_ptr + v + 1);
     float4 acc = make4(0.f);
 #pragma unroll 4
     for (int r = r0; r < r1; ++r) acc = add4(acc, b.act(ld4a<BF>(p.y, (size_t)r * HID + l * 4)));
     st4(p.C + (size_t)v * HID + l * 4, acc);
     float d = acc.x * w.x + acc.y * w.y + acc.z * w.z + acc.w * w.w;
-    const unsigned hmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;   // the two half-warps may diverge at the tail
+    const unsigned hmask = LPR == 32 ? 0xffffffffu : ((threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu);   // half-warps may diverge at the tail
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
     if (l == 0) p.logit[v] = d;
   }
 }
-void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s) {
-  const int grid = min((a.N + 15) / 16, 16 * num_sms());
-  if (a.y_bf16) ego_pool_fwd_kernel<true><<<grid, kThreads, 0, s>>>(a);
-  else ego_pool_fwd_kernel<false><<<grid, kThreads, 0, s>>>(a);
+void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, int hidden, cudaStream_t s) {
+  const int spc = kThreads / (hidden / 4);
+  const int grid = min((a.N + spc - 1) / spc, 16 * num_sms());
+  if (hidden == 64) {
+    if (a.y_bf16) ego_pool_fwd_kernel<true, 64><<<grid, kThreads, 0, s>>>(a);
+    else ego_pool_fwd_kernel<false, 64><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.y_bf16) ego_pool_fwd_kernel<true, 128><<<grid, kThreads, 0, s>>>(a);
+    else ego_pool_fwd_kernel<false, 128><<<grid, kThreads, 0, s>>>(a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // H = relu(BN(y_last)) ; q = H Wc1^T + bc1
 // ------------------------------------------------------------------------------------------------
-struct GateLinFwdSmem { float tile[GT * GLD]; float w[HID * HID]; };
+template <int HID> struct GateLinFwdSmem { float tile[GT * (HID + 4)]; float w[HID * HID]; };
 
-template <bool BF>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool BF, int HID>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 gate_lin_fwd_kernel(GateLinFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GateLinFwdSmem& sm = *reinterpret_cast<GateLinFwdSmem*>(smem_raw);
+  GateLinFwdSmem<HID>& sm = *reinterpret_cast<GateLinFwdSmem<HID>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   using M = NNMap<GT, HID>;
   load_matrix<HID>(sm.w, HID, p.Wc1t, HID);
   const int n_tiles = (p.N + GT - 1) / GT;
@@ -87,7 +98,7 @@ gate_lin_fwd_kernel(GateLinFwdArgs p) {
       float4 h = make4(0.f);
       if (v < p.N) {
         Bn4 b;
-        b.load(p.bn, c);
+        b.load(p.bn, c, HID);
         h = b.act(ld4a<BF>(p.y, (size_t)v * HID + c));
         st4(p.H + (size_t)v * HID + c, h);
       }
@@ -107,22 +118,27 @@ gate_lin_fwd_kernel(GateLinFwdArgs p) {
     }
   }
 }
-void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(gate_lin_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem)),
-                      cudaFuncSetAttribute(gate_lin_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem)), true);
+template <bool BF, int H>
+static void launch_gate_lin_fwd_t(const GateLinFwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(gate_lin_fwd_kernel<BF, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem<H>)), true);
   (void)once;
-  const int grid = min((a.N + GT - 1) / GT, 2 * num_sms());
-  if (a.y_bf16) gate_lin_fwd_kernel<true><<<grid, kThreads, sizeof(GateLinFwdSmem), s>>>(a);
-  else gate_lin_fwd_kernel<false><<<grid, kThreads, sizeof(GateLinFwdSmem), s>>>(a);
+  const int grid = min((a.N + GT - 1) / GT, (H == 64 ? 2 : 1) * num_sms());
+  gate_lin_fwd_kernel<BF, H><<<grid, kThreads, sizeof(GateLinFwdSmem<H>), s>>>(a);
+}
+void launch_gate_lin_fwd(const GateLinFwdArgs& a, int hidden, cudaStream_t s) {
+  if (hidden == 64) { if (a.y_bf16) launch_gate_lin_fwd_t<true, 64>(a, s); else launch_gate_lin_fwd_t<false, 64>(a, s); }
+  else { if (a.y_bf16) launch_gate_lin_fwd_t<true, 128>(a, s); else launch_gate_lin_fwd_t<false, 128>(a, s); }
 }
 
 // gH += g_q Wc1 ; dWc1 += g_q^T H ; dbc1 += sum g_q
-struct GateLinBwdSmem { float gq[2][GT * GLD]; float h[2][GT * GLD]; float w[HID * HID]; };   // two tile buffers: cp.async prefetch
+template <int HID, int GT> struct GateLinBwdSmem { float gq[2][GT * (HID + 4)]; float h[2][GT * (HID + 4)]; float w[HID * HID]; };   // two tile buffers: cp.async prefetch
 
+template <int HID, int GT>       // GT rows per tile: 128 at HID = 64, 32 at HID = 128 (four tiles + the weights in 227 KB)
 __global__ void __launch_bounds__(kThreads, 1)
 gate_lin_bwd_kernel(GateLinBwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GateLinBwdSmem& sm = *reinterpret_cast<GateLinBwdSmem*>(smem_raw);
+  GateLinBwdSmem<HID, GT>& sm = *reinterpret_cast<GateLinBwdSmem<HID, GT>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   using M = NNMap<GT, HID>;
   using T = TNMap<HID, HID>;
   load_matrix<HID>(sm.w, HID, p.Wc1, HID);
@@ -181,82 +197,123 @@ gate_lin_bwd_kernel(GateLinBwdArgs p) {
     for (int j = 0; j < T::TJ; ++j) part[p.off_W + (T::o0() + i) * HID + T::j0() + j] = dW[i][j];
   if (threadIdx.x < HID) part[p.off_b + threadIdx.x] = dbias;
 }
-void launch_gate_lin_bwd(const GateLinBwdArgs& a, int grid, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(gate_lin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(GateLinBwdSmem)), true);
+template <int H, int GTB>
+static void launch_gate_lin_bwd_t(const GateLinBwdArgs& a, int grid, cudaStream_t s) {
+  using S = GateLinBwdSmem<H, GTB>;
+  static bool once = (cudaFuncSetAttribute(gate_lin_bwd_kernel<H, GTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
   (void)once;
-  gate_lin_bwd_kernel<<<grid, kThreads, sizeof(GateLinBwdSmem), s>>>(a);
+  gate_lin_bwd_kernel<H, GTB><<<grid, kThreads, sizeof(S), s>>>(a);
+}
+void launch_gate_lin_bwd(const GateLinBwdArgs& a, int hidden, int grid, cudaStream_t s) {
+  if (hidden == 64) launch_gate_lin_bwd_t<64, 128>(a, grid, s); else launch_gate_lin_bwd_t<128, 32>(a, grid, s);
 }
 
 // ------------------------------------------------------------------------------------------------
 // per-graph gate (warp per graph, lane owns channels 2l, 2l+1)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+// A lane owns CPL = HID / 32 consecutive channels (2 at HID = 64, 4 at HID = 128): vector loads / stores of CPL floats
+template <int CPL> struct LaneVec { float v[CPL]; };
+template <int CPL>
+__device__ __forceinline__ LaneVec<CPL> ldv(const float* p) {
+  LaneVec<CPL> r;
+  if (CPL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
+  else { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[CPL - 2] = t.z; r.v[CPL - 1] = t.w; }
+  return r;
+}
+template <int CPL>
+__device__ __forceinline__ void stv(float* p, const LaneVec<CPL>& a) {
+  if (CPL == 2) *reinterpret_cast<float2*>(p) = make_float2(a.v[0], a.v[1]);
+  else *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[CPL - 2], a.v[CPL - 1]);
+}
+template <int CPL>
+__device__ __forceinline__ LaneVec<CPL> zerov() {
+  LaneVec<CPL> r;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) r.v[k] = 0.f;
+  return r;
+}
 
 constexpr float kKlEps = 0.0000001f;   // models.py:632
 
-template <int RB>      // rows in flight per warp in the gate pass (4 for molecule-sized graphs, 8 for ~150-node graphs)
+template <int HID, int RB>      // RB rows in flight per warp in the gate pass (4 for molecule-sized graphs, 8 for ~150-node graphs)
 __global__ void __launch_bounds__(kThreads)
 graph_gate_fwd_kernel(GraphGateFwdArgs p) {
+  constexpr int CPL = HID / 32;
+  using V = LaneVec<CPL>;
   const int lane = threadIdx.x & 31;
-  const int c = 2 * lane;
-  const float2 gam = ld2(p.gamma_c + c), bet = ld2(p.beta_c + c), w2 = ld2(p.wc2 + c);
+  const int c = CPL * lane;
+  const V gam = ldv<CPL>(p.gamma_c + c), bet = ldv<CPL>(p.beta_c + c), w2 = ldv<CPL>(p.wc2 + c);
   const float bc2 = __ldg(p.bc2);
   const int warps = gridDim.x * (kThreads / 32);
   for (int g = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < p.B; g += warps) {
     const int v0 = __ldg(p.graph_ptr + g), v1 = __ldg(p.graph_ptr + g + 1);
     const float n = (float)(v1 - v0);
     // pass 1: means
-    float2 sH = make_float2(0.f, 0.f), sQ = make_float2(0.f, 0.f);
+    V sH = zerov<CPL>(), sQ = zerov<CPL>();
 #pragma unroll 4
     for (int v = v0; v < v1; ++v) {
-      const float2 h = ld2(p.H + (size_t)v * HID + c), q = ld2(p.q + (size_t)v * HID + c);
-      sH.x += h.x; sH.y += h.y; sQ.x += q.x; sQ.y += q.y;
+      const V h = ldv<CPL>(p.H + (size_t)v * HID + c), q = ldv<CPL>(p.q + (size_t)v * HID + c);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { sH.v[k] += h.v[k]; sQ.v[k] += q.v[k]; }
     }
-    const float2 muH = make_float2(sH.x / n, sH.y / n), muQ = make_float2(sQ.x / n, sQ.y / n);
+    V muH, muQ;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { muH.v[k] = sH.v[k] / n; muQ.v[k] = sQ.v[k] / n; }
     // pass 2: centred second moments
-    float2 vH = make_float2(0.f, 0.f), vQ = make_float2(0.f, 0.f);
+    V vH = zerov<CPL>(), vQ = zerov<CPL>();
 #pragma unroll 4
     for (int v = v0; v < v1; ++v) {
-      const float2 h = ld2(p.H + (size_t)v * HID + c), q = ld2(p.q + (size_t)v * HID + c);
-      float d;
-      d = h.x - muH.x; vH.x = fmaf(d, d, vH.x); d = h.y - muH.y; vH.y = fmaf(d, d, vH.y);
-      d = q.x - muQ.x; vQ.x = fmaf(d, d, vQ.x); d = q.y - muQ.y; vQ.y = fmaf(d, d, vQ.y);
+      const V h = ldv<CPL>(p.H + (size_t)v * HID + c), q = ldv<CPL>(p.q + (size_t)v * HID + c);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        float d = h.v[k] - muH.v[k]; vH.v[k] = fmaf(d, d, vH.v[k]);
+        d = q.v[k] - muQ.v[k]; vQ.v[k] = fmaf(d, d, vQ.v[k]);
+      }
     }
-    const float2 sd = make_float2(sqrtf(vH.x / (n - 1.f)), sqrtf(vH.y / (n - 1.f)));         // torch.std_mean: unbiased
-    float2 rstd = make_float2(1.f / sqrtf(vQ.x / n + kBnEps), 1.f / sqrtf(vQ.y / n + kBnEps));  // BN: biased
-    float2 muQe = muQ;
+    V sd, rstd, muQe = muQ, uvar;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      sd.v[k] = sqrtf(vH.v[k] / (n - 1.f));                       // torch.std_mean: unbiased
+      rstd.v[k] = 1.f / sqrtf(vQ.v[k] / n + kBnEps);              // BN: biased
+      uvar.v[k] = vQ.v[k] / (n - 1.f);
+    }
     if (p.eval_running) {       // model.eval(): nn.BatchNorm1d normalises with its running statistics
-      const float2 rm = ld2(p.eval_running + c), rv = ld2(p.eval_running + HID + c);
+      const V rm = ldv<CPL>(p.eval_running + c), rv = ldv<CPL>(p.eval_running + HID + c);
       muQe = rm;
-      rstd = make_float2(1.f / sqrtf(rv.x + kBnEps), 1.f / sqrtf(rv.y + kBnEps));
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) rstd.v[k] = 1.f / sqrtf(rv.v[k] + kBnEps);
     }
-    st2(p.readout + (size_t)g * HID + c, sH);
+    stv<CPL>(p.readout + (size_t)g * HID + c, sH);
     float* gs = p.gstat + (size_t)g * 4 * HID;
-    st2(gs + c, muH); st2(gs + HID + c, sd); st2(gs + 2 * HID + c, muQe); st2(gs + 3 * HID + c, rstd);
+    stv<CPL>(gs + c, muH); stv<CPL>(gs + HID + c, sd); stv<CPL>(gs + 2 * HID + c, muQe); stv<CPL>(gs + 3 * HID + c, rstd);
     if (p.cstat) {
-      st2(p.cstat + (size_t)g * 2 * HID + c, muQ);
-      st2(p.cstat + (size_t)g * 2 * HID + HID + c, make_float2(vQ.x / (n - 1.f), vQ.y / (n - 1.f)));
+      stv<CPL>(p.cstat + (size_t)g * 2 * HID + c, muQ);
+      stv<CPL>(p.cstat + (size_t)g * 2 * HID + HID + c, uvar);
     }
     // pass 3: gate, noisy features, core readout, KL of the last graph
     const bool last = (g == p.B - 1);
-    float2 core = make_float2(0.f, 0.f), kl1 = make_float2(0.f, 0.f), kl2 = make_float2(0.f, 0.f);
-    const float2 isd = make_float2(1.f / (sd.x + kKlEps), 1.f / (sd.y + kKlEps));
+    V core = zerov<CPL>(), kl1 = zerov<CPL>(), kl2 = zerov<CPL>(), isd;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) isd.v[k] = 1.f / (sd.v[k] + kKlEps);
     // latency-bound loop: the loads and shuffle chains of RB rows overlap
     for (int vb = v0; vb < v1; vb += RB) {
-      float2 h[RB], q[RB], fu[RB];
+      V h[RB], q[RB], fu[RB];
       float u[RB], pv[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int v = min(vb + i, v1 - 1);
-        h[i] = ld2(p.H + (size_t)v * HID + c); q[i] = ld2(p.q + (size_t)v * HID + c);
-        fu[i] = ld2(p.feat_u + (size_t)v * HID + c); u[i] = __ldg(p.gate_u + v);
+        h[i] = ldv<CPL>(p.H + (size_t)v * HID + c); q[i] = ldv<CPL>(p.q + (size_t)v * HID + c);
+        fu[i] = ldv<CPL>(p.feat_u + (size_t)v * HID + c); u[i] = __ldg(p.gate_u + v);
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const float ox = fmaf((q[i].x - muQe.x) * rstd.x, gam.x, bet.x), oy = fmaf((q[i].y - muQe.y) * rstd.y, gam.y, bet.y);
-        pv[i] = fmaxf(ox, 0.f) * w2.x + fmaxf(oy, 0.f) * w2.y;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float o = fmaf((q[i].v[k] - muQe.v[k]) * rstd.v[k], gam.v[k], bet.v[k]);
+          acc = k == 0 ? fmaxf(o, 0.f) * w2.v[k] : acc + fmaxf(o, 0.f) * w2.v[k];
+        }
+        pv[i] = acc;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -271,22 +328,28 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
         const float gi = logf(eps) - logf(1.f - eps);
         const float lam = 1.f / (1.f + expf(-(gi + (pv[i] + bc2))));
         const float ln = 1.f - lam;
-        const float2 m = make_float2(lam * h[i].x + ln * muH.x, lam * h[i].y + ln * muH.y);
-        const float2 sg = make_float2(ln * sd.x, ln * sd.y);
-        const float2 z = make_float2(m.x + fu[i].x * sg.x, m.y + fu[i].y * sg.y);
-        st2(p.noisy + (size_t)v * HID + c, z);
-        core.x += z.x; core.y += z.y;
-        if (lane == 0) p.lam[v] = lam;
-        if (last) {
-          float t;
-          t = sg.x * isd.x; kl1.x = fmaf(0.5f * t, t, kl1.x); t = sg.y * isd.y; kl1.y = fmaf(0.5f * t, t, kl1.y);
-          t = (m.x - muH.x) * isd.x; kl2.x = fmaf(t, t, kl2.x); t = (m.y - muH.y) * isd.y; kl2.y = fmaf(t, t, kl2.y);
+        V z;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float m = lam * h[i].v[k] + ln * muH.v[k];
+          const float sg = ln * sd.v[k];
+          z.v[k] = m + fu[i].v[k] * sg;
+          core.v[k] += z.v[k];
+          if (last) {
+            float t = sg * isd.v[k]; kl1.v[k] = fmaf(0.5f * t, t, kl1.v[k]);
+            t = (m - muH.v[k]) * isd.v[k]; kl2.v[k] = fmaf(t, t, kl2.v[k]);
+          }
         }
+        stv<CPL>(p.noisy + (size_t)v * HID + c, z);
+        if (lane == 0) p.lam[v] = lam;
       }
     }
-    st2(p.core + (size_t)g * HID + c, core);
+    stv<CPL>(p.core + (size_t)g * HID + c, core);
     if (last) {
-      const float tot = warp_sum(kl1.x + kl1.y + n * (kl2.x + kl2.y));
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { a1 = k == 0 ? kl1.v[k] : a1 + kl1.v[k]; a2 = k == 0 ? kl2.v[k] : a2 + kl2.v[k]; }
+      const float tot = warp_sum(a1 + n * a2);
       if (lane == 0) p.kl[0] = tot / ((float)HID * n);
     }
     // attention softmax over the graph's nodes (core half and bias cancel: SURVEY F14)
@@ -299,20 +362,27 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
     for (int v = v0 + lane; v < v1; v += 32) p.alpha[v] = expf(__ldg(p.logit + v) - mx) / se;
   }
 }
-void launch_graph_gate_fwd(const GraphGateFwdArgs& a, cudaStream_t s) {
+void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 8 * num_sms());
-  if (a.N / max(a.B, 1) >= 48) graph_gate_fwd_kernel<8><<<grid, kThreads, 0, s>>>(a);
-  else graph_gate_fwd_kernel<4><<<grid, kThreads, 0, s>>>(a);
+  const bool big = a.N / max(a.B, 1) >= 48;
+  if (hidden == 64) {
+    if (big) graph_gate_fwd_kernel<64, 8><<<grid, kThreads, 0, s>>>(a);
+    else graph_gate_fwd_kernel<64, 4><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (big) graph_gate_fwd_kernel<128, 8><<<grid, kThreads, 0, s>>>(a);
+    else graph_gate_fwd_kernel<128, 4><<<grid, kThreads, 0, s>>>(a);
+  }
 }
 
 // running stats of the compressor BN after B sequential per-graph updates (closed form, fixed order)
 // r_B = 0.9^B r_0 + sum_g 0.1 * 0.9^(B-1-g) stat_g ; graphs older than kEmaWindow contribute < 0.9^768 ~ 1e-35.
 constexpr int kEmaWindow = 768;
-constexpr int kEmaSeg = 8;
-__global__ void __launch_bounds__(2 * HID * kEmaSeg)
+template <int HID>
+__global__ void __launch_bounds__(1024)
 compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict__ running) {
+  constexpr int kEmaSeg = 1024 / (2 * HID);     // 8 segments at HID = 64, 4 at HID = 128
   __shared__ double s_part[kEmaSeg][2 * HID];
-  const int j = threadIdx.x & (2 * HID - 1);  // 0..63 mean, 64..127 var
+  const int j = threadIdx.x % (2 * HID);  // 0..H-1 mean, H..2H-1 var
   const int seg = threadIdx.x / (2 * HID);
   const int g0 = B > kEmaWindow ? B - kEmaWindow : 0;
   // newest graph first: weight 0.1 * 0.9^k for age k = B-1-g, advanced by a constant factor (two pow() per thread
@@ -333,72 +403,90 @@ compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict_
     running[j] = (float)r;
   }
 }
-void launch_compressor_ema(const float* cstat, int B, float* running, cudaStream_t s) {
-  compressor_ema_kernel<<<1, 2 * HID * kEmaSeg, 0, s>>>(cstat, B, running);
+void launch_compressor_ema(const float* cstat, int B, float* running, int hidden, cudaStream_t s) {
+  if (hidden == 64) compressor_ema_kernel<64><<<1, 1024, 0, s>>>(cstat, B, running);
+  else compressor_ema_kernel<128><<<1, 1024, 0, s>>>(cstat, B, running);
 }
 
+template <int HID>
 __global__ void __launch_bounds__(kThreads)
 graph_gate_bwd_kernel(GraphGateBwdArgs p) {
+  constexpr int CPL = HID / 32;
+  using V = LaneVec<CPL>;
   __shared__ __align__(16) float s_red[(kThreads / 32) * 5 * HID];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = 2 * lane;
-  const float2 gam = ld2(p.gamma_c + c), bet = ld2(p.beta_c + c), w2 = ld2(p.wc2 + c), wc = ld2(p.w_cand + c);
-  float2 a_dg = make_float2(0.f, 0.f), a_db = a_dg, a_dw2 = a_dg, a_dwc = a_dg;
+  const int c = CPL * lane;
+  const V gam = ldv<CPL>(p.gamma_c + c), bet = ldv<CPL>(p.beta_c + c), w2 = ldv<CPL>(p.wc2 + c), wc = ldv<CPL>(p.w_cand + c);
+  V a_dg = zerov<CPL>(), a_db = zerov<CPL>(), a_dw2 = zerov<CPL>(), a_dwc = zerov<CPL>();
   float a_dbc2 = 0.f;
   const int warps = gridDim.x * (kThreads / 32);
+  auto dot = [](const V& a, const V& b) {
+    float r = a.v[0] * b.v[0];
+#pragma unroll
+    for (int k = 1; k < CPL; ++k) r += a.v[k] * b.v[k];
+    return r;
+  };
   for (int g = blockIdx.x * (kThreads / 32) + warp; g < p.B; g += warps) {
     const int v0 = __ldg(p.graph_ptr + g), v1 = __ldg(p.graph_ptr + g + 1);
     const float n = (float)(v1 - v0);
     const float* gs = p.gstat + (size_t)g * 4 * HID;
-    const float2 muH = ld2(gs + c), sd = ld2(gs + HID + c), muQ = ld2(gs + 2 * HID + c), rstd = ld2(gs + 3 * HID + c);
-    const float2 gcore = ld2(p.g_core + (size_t)g * HID + c), gread = ld2(p.g_readout + (size_t)g * HID + c);
+    const V muH = ldv<CPL>(gs + c), sd = ldv<CPL>(gs + HID + c), muQ = ldv<CPL>(gs + 2 * HID + c), rstd = ldv<CPL>(gs + 3 * HID + c);
+    const V gcore = ldv<CPL>(p.g_core + (size_t)g * HID + c), gread = ldv<CPL>(p.g_readout + (size_t)g * HID + c);
     const bool last = (g == p.B - 1) && (p.kl_scale != 0.f);
-    const float2 isd = make_float2(1.f / (sd.x + kKlEps), 1.f / (sd.y + kKlEps));
+    V isd;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) isd.v[k] = 1.f / (sd.v[k] + kKlEps);
     // ---- attention pass A: S = sum_v alpha_v (gT_v . C_v)
     float S = 0.f;
 #pragma unroll 4
     for (int v = v0; v < v1; ++v) {
-      const float2 gT = ld2(p.gI2 + (size_t)v * p.gI_stride + c), C = ld2(p.C + (size_t)v * HID + c);
-      S += __ldg(p.alpha + v) * warp_sum(gT.x * C.x + gT.y * C.y);
+      const V gT = ldv<CPL>(p.gI2 + (size_t)v * p.gI_stride + c), C = ldv<CPL>(p.C + (size_t)v * HID + c);
+      S += __ldg(p.alpha + v) * warp_sum(dot(gT, C));
     }
     // ---- pass B: attention backward, gate backward (scalar part), per-graph BN sums.  The loop is latency-bound (one
     //      warp per graph, two dependent shuffle reductions per row): the loads of RB rows are issued together and the
     //      rows' shuffle chains interleave; sums are still accumulated in row order.
-    float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
+    V m1 = zerov<CPL>(), m2 = zerov<CPL>();
     constexpr int RB = 4;
     for (int vb = v0; vb < v1; vb += RB) {
-      float2 gT[RB], C[RB], gz0[RB], h[RB], fu[RB], q[RB];
+      V gT[RB], C[RB], gz0[RB], h[RB], fu[RB], q[RB];
       float al[RB], lam[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int v = min(vb + i, v1 - 1);
-        gT[i] = ld2(p.gI2 + (size_t)v * p.gI_stride + c); C[i] = ld2(p.C + (size_t)v * HID + c);
-        gz0[i] = ld2(p.gI + (size_t)v * p.gI_stride + c); h[i] = ld2(p.H + (size_t)v * HID + c);
-        fu[i] = ld2(p.feat_u + (size_t)v * HID + c); q[i] = ld2(p.q + (size_t)v * HID + c);
+        gT[i] = ldv<CPL>(p.gI2 + (size_t)v * p.gI_stride + c); C[i] = ldv<CPL>(p.C + (size_t)v * HID + c);
+        gz0[i] = ldv<CPL>(p.gI + (size_t)v * p.gI_stride + c); h[i] = ldv<CPL>(p.H + (size_t)v * HID + c);
+        fu[i] = ldv<CPL>(p.feat_u + (size_t)v * HID + c); q[i] = ldv<CPL>(p.q + (size_t)v * HID + c);
         al[i] = __ldg(p.alpha + v); lam[i] = __ldg(p.lam + v);
       }
-      float dot[RB], part[RB];
-      float2 gh[RB];
+      float dt[RB], part[RB];
+      V gh[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        dot[i] = gT[i].x * C[i].x + gT[i].y * C[i].y;
-        const float2 gz = make_float2(gz0[i].x + gcore.x, gz0[i].y + gcore.y);
-        part[i] = gz.x * (h[i].x - muH.x - fu[i].x * sd.x) + gz.y * (h[i].y - muH.y - fu[i].y * sd.y);
-        gh[i] = make_float2(fmaf(lam[i], gz.x, gread.x), fmaf(lam[i], gz.y, gread.y));
-        if (last) {
-          const float k = p.kl_scale / ((float)HID * n);
-          const float2 r1 = make_float2(sd.x * isd.x, sd.y * isd.y);                             // sigma/(sigma+e)
-          const float2 r2 = make_float2((h[i].x - muH.x) * isd.x, (h[i].y - muH.y) * isd.y);     // (H-mu)/(sigma+e)
-          part[i] += k * (-(1.f - lam[i]) * (r1.x * r1.x + r1.y * r1.y) + 2.f * n * lam[i] * (r2.x * r2.x + r2.y * r2.y));
-          gh[i].x += k * 2.f * n * lam[i] * lam[i] * r2.x * isd.x;
-          gh[i].y += k * 2.f * n * lam[i] * lam[i] * r2.y * isd.y;
+        dt[i] = dot(gT[i], C[i]);
+        float pa = 0.f, kr1 = 0.f, kr2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float gz = gz0[i].v[k] + gcore.v[k];
+          const float t = gz * (h[i].v[k] - muH.v[k] - fu[i].v[k] * sd.v[k]);
+          pa = k == 0 ? t : pa + t;
+          gh[i].v[k] = fmaf(lam[i], gz, gread.v[k]);
+          if (last) {
+            const float r1 = sd.v[k] * isd.v[k];                              // sigma/(sigma+e)
+            const float r2 = (h[i].v[k] - muH.v[k]) * isd.v[k];               // (H-mu)/(sigma+e)
+            kr1 = k == 0 ? r1 * r1 : kr1 + r1 * r1;
+            kr2 = k == 0 ? r2 * r2 : kr2 + r2 * r2;
+            gh[i].v[k] += (p.kl_scale / ((float)HID * n)) * 2.f * n * lam[i] * lam[i] * r2 * isd.v[k];
+          }
         }
+        if (last) pa += (p.kl_scale / ((float)HID * n)) * (-(1.f - lam[i]) * kr1 + 2.f * n * lam[i] * kr2);
+        part[i] = pa;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-          dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+          dt[i] += __shfl_xor_sync(0xffffffffu, dt[i], o);
           part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
         }
       }
@@ -406,51 +494,60 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
       for (int i = 0; i < RB; ++i) {
         const int v = vb + i;
         if (v >= v1) break;
-        const float dl = al[i] * (dot[i] - S);
-        st2(p.gC + (size_t)v * HID + c, make_float2(fmaf(dl, wc.x, al[i] * gT[i].x), fmaf(dl, wc.y, al[i] * gT[i].y)));
-        a_dwc.x = fmaf(dl, C[i].x, a_dwc.x); a_dwc.y = fmaf(dl, C[i].y, a_dwc.y);
-        st2(p.gH + (size_t)v * HID + c, gh[i]);
+        const float dl = al[i] * (dt[i] - S);
         const float gpv = part[i] * lam[i] * (1.f - lam[i]);
+        V gc;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          gc.v[k] = fmaf(dl, wc.v[k], al[i] * gT[i].v[k]);
+          a_dwc.v[k] = fmaf(dl, C[i].v[k], a_dwc.v[k]);
+          const float qh = (q[i].v[k] - muQ.v[k]) * rstd.v[k];
+          const float o = fmaf(qh, gam.v[k], bet.v[k]);
+          a_dw2.v[k] = fmaf(gpv, fmaxf(o, 0.f), a_dw2.v[k]);
+          const float go = o > 0.f ? gpv * w2.v[k] : 0.f;
+          a_db.v[k] += go;
+          a_dg.v[k] = fmaf(go, qh, a_dg.v[k]);
+          m1.v[k] = fmaf(gam.v[k], go, m1.v[k]);
+          m2.v[k] = fmaf(gam.v[k] * go, qh, m2.v[k]);
+        }
+        stv<CPL>(p.gC + (size_t)v * HID + c, gc);
+        stv<CPL>(p.gH + (size_t)v * HID + c, gh[i]);
         if (lane == 0) p.gp[v] = gpv;
         a_dbc2 += gpv;
-        const float2 qh = make_float2((q[i].x - muQ.x) * rstd.x, (q[i].y - muQ.y) * rstd.y);
-        const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
-        a_dw2.x = fmaf(gpv, fmaxf(ox, 0.f), a_dw2.x); a_dw2.y = fmaf(gpv, fmaxf(oy, 0.f), a_dw2.y);
-        const float gox = ox > 0.f ? gpv * w2.x : 0.f, goy = oy > 0.f ? gpv * w2.y : 0.f;
-        a_db.x += gox; a_db.y += goy;
-        a_dg.x = fmaf(gox, qh.x, a_dg.x); a_dg.y = fmaf(goy, qh.y, a_dg.y);
-        m1.x = fmaf(gam.x, gox, m1.x); m1.y = fmaf(gam.y, goy, m1.y);
-        m2.x = fmaf(gam.x * gox, qh.x, m2.x); m2.y = fmaf(gam.y * goy, qh.y, m2.y);
-        // pass C needs gpv of this row again: keep it in the q slot's x lane is not possible (per-lane data) -> re-read gp
       }
     }
-    m1.x /= n; m1.y /= n; m2.x /= n; m2.y /= n;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { m1.v[k] /= n; m2.v[k] /= n; }
     __syncwarp();
     // ---- pass C: per-graph BN backward -> g_q
     for (int vb = v0; vb < v1; vb += RB) {
       float gpv[RB];
-      float2 q[RB];
+      V q[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int v = min(vb + i, v1 - 1);
         gpv[i] = __ldcg(p.gp + v);
-        q[i] = ld2(p.q + (size_t)v * HID + c);
+        q[i] = ldv<CPL>(p.q + (size_t)v * HID + c);
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int v = vb + i;
         if (v >= v1) break;
-        const float2 qh = make_float2((q[i].x - muQ.x) * rstd.x, (q[i].y - muQ.y) * rstd.y);
-        const float ox = fmaf(qh.x, gam.x, bet.x), oy = fmaf(qh.y, gam.y, bet.y);
-        const float gox = ox > 0.f ? gpv[i] * w2.x : 0.f, goy = oy > 0.f ? gpv[i] * w2.y : 0.f;
-        st2(p.g_q + (size_t)v * HID + c, make_float2(rstd.x * (gam.x * gox - m1.x - qh.x * m2.x),
-                                                      rstd.y * (gam.y * goy - m1.y - qh.y * m2.y)));
+        V gq;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float qh = (q[i].v[k] - muQ.v[k]) * rstd.v[k];
+          const float o = fmaf(qh, gam.v[k], bet.v[k]);
+          const float go = o > 0.f ? gpv[i] * w2.v[k] : 0.f;
+          gq.v[k] = rstd.v[k] * (gam.v[k] * go - m1.v[k] - qh * m2.v[k]);
+        }
+        stv<CPL>(p.g_q + (size_t)v * HID + c, gq);
       }
     }
   }
   // ---- parameter-gradient partials: warp -> CTA -> last CTA
   float* r = s_red + warp * 5 * HID;
-  st2(r + c, a_dg); st2(r + HID + c, a_db); st2(r + 2 * HID + c, a_dw2); st2(r + 3 * HID + c, a_dwc);
+  stv<CPL>(r + c, a_dg); stv<CPL>(r + HID + c, a_db); stv<CPL>(r + 2 * HID + c, a_dw2); stv<CPL>(r + 3 * HID + c, a_dwc);
   if (lane == 0) r[4 * HID] = a_dbc2;
   __syncthreads();
   for (int j = threadIdx.x; j < 4 * HID + 1; j += kThreads) {
@@ -482,34 +579,34 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
     else { p.d_bc2[0] = f; p.d_attn_b[0] = 0.f; }
   }
 }
-void launch_graph_gate_bwd(const GraphGateBwdArgs& a, cudaStream_t s) {
+void launch_graph_gate_bwd(const GraphGateBwdArgs& a, int hidden, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 4 * num_sms());   // latency-bound warp-per-graph loops: as many resident warps as fit
-  graph_gate_bwd_kernel<<<grid, kThreads, 0, s>>>(a);
+  if (hidden == 64) graph_gate_bwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
+  else graph_gate_bwd_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
 // head MLP forward: Z = Wm2 relu(Wm1 [noisy || alpha*C] + bm1) + bm2
 // ------------------------------------------------------------------------------------------------
-constexpr int HT = 64;                 // rows per tile
-constexpr int HLD = 2 * HID + 4;
+// HT rows per tile: 64 at HID = 64; 32 at HID = 128 (tile [HT][2H] + W1t [2H][H] + W2t [H][H] = 225 KB)
+template <int HID, int HT> struct HeadFwdSmem { float tile[HT * (2 * HID + 4)]; float w1t[2 * HID * HID]; float w2t[HID * HID]; };
 
-struct HeadFwdSmem { float tile[HT * HLD]; float w1t[2 * HID * HID]; float w2t[HID * HID]; };
-
+template <int HID, int HT>
 __device__ __forceinline__ void head_load_tile(float* tile, const float* __restrict__ noisy, const float* __restrict__ C,
-                                               const float* __restrict__ alpha, int base, int N, float* imap,
-                                               float* aC = nullptr) {
-  const int l = threadIdx.x & 31;
-  for (int r = threadIdx.x >> 5; r < HT; r += kThreads / 32) {
+                                               const float* __restrict__ alpha, int base, int N, float* imap, float* aC) {
+  constexpr int HLD = 2 * HID + 4, LPR = 2 * HID / 4;      // lanes per row of the [noisy || alpha C] tile (4 channels each)
+  for (int i = threadIdx.x; i < HT * LPR; i += kThreads) {
+    const int r = i / LPR, l = i % LPR;
     const int v = base + r;
     float4 val = make4(0.f);
     if (v < N) {
-      if (l < 16) {
+      if (l < LPR / 2) {
         val = ld4(noisy + (size_t)v * HID + l * 4);
       } else {
         const float al = __ldg(alpha + v);
-        const float4 cc = ld4(C + (size_t)v * HID + (l - 16) * 4);
+        const float4 cc = ld4(C + (size_t)v * HID + (l - LPR / 2) * 4);
         val = make_float4(al * cc.x, al * cc.y, al * cc.z, al * cc.w);
-        if (aC) st4(aC + (size_t)v * HID + (l - 16) * 4, val);
+        if (aC) st4(aC + (size_t)v * HID + (l - LPR / 2) * 4, val);
       }
       if (imap) st4(imap + (size_t)v * 2 * HID + l * 4, val);
     }
@@ -517,10 +614,12 @@ __device__ __forceinline__ void head_load_tile(float* tile, const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HID, int HT>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 head_fwd_kernel(HeadFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  HeadFwdSmem& sm = *reinterpret_cast<HeadFwdSmem*>(smem_raw);
+  HeadFwdSmem<HID, HT>& sm = *reinterpret_cast<HeadFwdSmem<HID, HT>*>(smem_raw);
+  constexpr int GLD = HID + 4, HLD = 2 * HID + 4;
   using M = NNMap<HT, HID>;
   load_matrix<HID>(sm.w1t, HID, p.W1t, 2 * HID);
   load_matrix<HID>(sm.w2t, HID, p.W2t, HID);
@@ -530,7 +629,7 @@ head_fwd_kernel(HeadFwdArgs p) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * HT;
     __syncthreads();
-    head_load_tile(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap, p.aC);
+    head_load_tile<HID, HT>(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap, p.aC);
     __syncthreads();
     float acc[M::TM][4];
 #pragma unroll
@@ -555,101 +654,24 @@ head_fwd_kernel(HeadFwdArgs p) {
     }
   }
 }
-void launch_head_fwd(const HeadFwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(HeadFwdSmem)), true);
+template <int H, int HT>
+static void launch_head_fwd_t(const HeadFwdArgs& a, cudaStream_t s) {
+  using S = HeadFwdSmem<H, HT>;
+  static bool once = (cudaFuncSetAttribute(head_fwd_kernel<H, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
   (void)once;
-  const int grid = min((a.N + HT - 1) / HT, 2 * num_sms());
-  head_fwd_kernel<<<grid, kThreads, sizeof(HeadFwdSmem), s>>>(a);
+  const int grid = min((a.N + HT - 1) / HT, (H == 64 ? 2 : 1) * num_sms());
+  head_fwd_kernel<H, HT><<<grid, kThreads, sizeof(S), s>>>(a);
+}
+void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s) {
+  if (hidden == 64) launch_head_fwd_t<64, 64>(a, s); else launch_head_fwd_t<128, 32>(a, s);
 }
 
-// head MLP backward (persistent): gI = ((gZ W2) * [r>0]) W1 ; dW2 += gZ^T r ; dW1 += g_u^T I ; biases
-struct HeadBwdSmem {
-  float gy[HT * GLD]; float gu[HT * GLD]; float r[HT * GLD]; float a[HT * HLD];
-  float w2[HID * HID]; float w1[HID * 2 * HID];
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-head_bwd_kernel(HeadBwdArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  HeadBwdSmem& sm = *reinterpret_cast<HeadBwdSmem*>(smem_raw);
-  using M2 = NNMap<HT, HID>;
-  using M1 = NNMap<HT, 2 * HID>;
-  using T2 = TNMap<HID, HID>;
-  using T1 = TNMap<HID, 2 * HID>;
-  load_matrix<HID>(sm.w2, HID, p.W2, HID);
-  load_matrix<2 * HID>(sm.w1, 2 * HID, p.W1, HID);
-  float dW2[T2::TO][T2::TJ], dW1[T1::TO][T1::TJ];
-#pragma unroll
-  for (int i = 0; i < T2::TO; ++i)
-#pragma unroll
-    for (int j = 0; j < T2::TJ; ++j) dW2[i][j] = 0.f;
-#pragma unroll
-  for (int i = 0; i < T1::TO; ++i)
-#pragma unroll
-    for (int j = 0; j < T1::TJ; ++j) dW1[i][j] = 0.f;
-  float dbias = 0.f;
-  const int n_tiles = (p.N + HT - 1) / HT;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int base = tile * HT;
-    __syncthreads();
-    load_row_tile<HT, HID>(sm.gy, GLD, p.gZ, base, p.N);
-    load_row_tile<HT, HID>(sm.r, GLD, p.r, base, p.N);
-    head_load_tile(sm.a, p.noisy, p.C, p.alpha, base, p.N, nullptr);
-    __syncthreads();
-    {
-      float acc[M2::TM][4];
-#pragma unroll
-      for (int m = 0; m < M2::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-      gemm_nn<HT, HID, HID>(sm.gy, GLD, sm.w2, HID, acc);
-      const int c0 = M2::col0(), r0 = M2::row0();
-#pragma unroll
-      for (int m = 0; m < M2::TM; ++m) {
-        const float4 rr = ld4(sm.r + (r0 + m) * GLD + c0);
-        st4(sm.gu + (r0 + m) * GLD + c0,
-            make_float4(rr.x > 0.f ? acc[m][0] : 0.f, rr.y > 0.f ? acc[m][1] : 0.f,
-                        rr.z > 0.f ? acc[m][2] : 0.f, rr.w > 0.f ? acc[m][3] : 0.f));
-      }
-    }
-    __syncthreads();
-    {
-      float acc[M1::TM][4];
-#pragma unroll
-      for (int m = 0; m < M1::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-      gemm_nn<HT, HID, 2 * HID>(sm.gu, GLD, sm.w1, 2 * HID, acc);
-      const int c0 = M1::col0(), r0 = M1::row0();
-#pragma unroll
-      for (int m = 0; m < M1::TM; ++m) {
-        const int v = base + r0 + m;
-        if (v < p.N) st4(p.gI + (size_t)v * 2 * HID + c0, make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
-      }
-    }
-    gemm_tn<HID, HID>(sm.gy, GLD, sm.r, GLD, HT, dW2);
-    gemm_tn<HID, 2 * HID>(sm.gu, GLD, sm.a, HLD, HT, dW1);
-    if (threadIdx.x < 2 * HID) {
-      const float* src = (threadIdx.x < HID) ? sm.gy : sm.gu;
-      const int c = threadIdx.x & (HID - 1);
-      float s = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < HT; ++r) s += src[r * GLD + c];
-      dbias += s;
-    }
-  }
-  float* part = p.part + (size_t)blockIdx.x * p.pstride;
-#pragma unroll
-  for (int i = 0; i < T2::TO; ++i)
-#pragma unroll
-    for (int j = 0; j < T2::TJ; ++j) part[p.off_W2 + (T2::o0() + i) * HID + T2::j0() + j] = dW2[i][j];
-#pragma unroll
-  for (int i = 0; i < T1::TO; ++i)
-#pragma unroll
-    for (int j = 0; j < T1::TJ; ++j) part[p.off_W1 + (T1::o0() + i) * 2 * HID + T1::j0() + j] = dW1[i][j];
-  if (threadIdx.x < HID) part[p.off_b2 + threadIdx.x] = dbias;
-  else if (threadIdx.x < 2 * HID) part[p.off_b1 + threadIdx.x - HID] = dbias;
-}
+// The head MLP backward is the GIN layer backward kernel run on the two K = H halves of the first head layer (api.cu).
+// prep: dense copies W1a = W1[:, :H], W1b = W1[:, H:] and the identity BatchNorm-backward constants
+// (bn = {0, 1, 1, 0}, cvec = 0: g_y = g_o).  interleave: grads slot [2][H][H] (dW1a | dW1b) -> [H][2H] in place.
 __global__ void __launch_bounds__(kThreads)
 head_bwd_prep_kernel(const float* __restrict__ W1, float* __restrict__ W1a, float* __restrict__ W1b, float* __restrict__ bn,
-                     float* __restrict__ cvec) {
+                     float* __restrict__ cvec, int HID) {
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < HID * 2 * HID; i += gridDim.x * kThreads) {
     const int o = i / (2 * HID), k = i % (2 * HID);
     const float w = W1[i];
@@ -660,12 +682,12 @@ head_bwd_prep_kernel(const float* __restrict__ W1, float* __restrict__ W1a, floa
     for (int i = threadIdx.x; i < 2 * HID; i += kThreads) cvec[i] = 0.f;
   }
 }
-void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, cudaStream_t s) {
-  head_bwd_prep_kernel<<<8, kThreads, 0, s>>>(W1, W1a, W1b, bn, cvec);
+void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, int hidden, cudaStream_t s) {
+  head_bwd_prep_kernel<<<8, kThreads, 0, s>>>(W1, W1a, W1b, bn, cvec, hidden);
 }
 
-__global__ void __launch_bounds__(kThreads) head_dw1_interleave_kernel(float* __restrict__ dW1) {
-  __shared__ float s_w[2 * HID * HID];
+__global__ void __launch_bounds__(kThreads) head_dw1_interleave_kernel(float* __restrict__ dW1, int HID) {
+  extern __shared__ __align__(16) float s_w[];            // [2 * HID * HID]
   for (int i = threadIdx.x; i < 2 * HID * HID; i += kThreads) s_w[i] = dW1[i];
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * HID * HID; i += kThreads) {
@@ -673,13 +695,11 @@ __global__ void __launch_bounds__(kThreads) head_dw1_interleave_kernel(float* __
     dW1[i] = k < HID ? s_w[o * HID + k] : s_w[HID * HID + o * HID + k - HID];
   }
 }
-void launch_head_dw1_interleave(float* dW1, cudaStream_t s) { head_dw1_interleave_kernel<<<1, kThreads, 0, s>>>(dW1); }
-
-void launch_head_bwd(const HeadBwdArgs& a, int grid, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(HeadBwdSmem)), true);
+void launch_head_dw1_interleave(float* dW1, int hidden, cudaStream_t s) {
+  const int bytes = 2 * hidden * hidden * (int)sizeof(float);
+  static bool once = (cudaFuncSetAttribute(head_dw1_interleave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4), true);
   (void)once;
-  head_bwd_kernel<<<grid, kThreads, sizeof(HeadBwdSmem), s>>>(a);
+  head_dw1_interleave_kernel<<<1, kThreads, bytes, s>>>(dW1, hidden);
 }
 
 }  // namespace scgib

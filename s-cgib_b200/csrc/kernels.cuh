@@ -13,7 +13,7 @@ void launch_transposes(const TransposeJobs& jobs, cudaStream_t s);
 
 // eval mode (model.eval()): bn = {running_mean, 1/sqrt(running_var + eps), gamma, beta} replaces the batch statistics a
 // GIN forward kernel has just written, before the next layer / the pooling kernels read them
-void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, cudaStream_t s);
+void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, int hidden, cudaStream_t s);
 void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s, bool out_bf16 = false);
 void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
 
@@ -41,7 +41,7 @@ struct GinFwdArgs {
 // persistent CTAs are balanced over both row sets and the per-launch fixed costs are paid once.
 struct GinFwdPair { GinFwdArgs a[2]; int split; };
 int gin_fwd_grid(int V);
-void launch_gin_fwd(const GinFwdArgs& a, int kin, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu)
+void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu), hidden 64 / 128
 void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // tcgen05 3xTF32, shared-memory window gather (gin_tc3.cu)
 void launch_gin_fwd_tc3_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, cudaStream_t s);
 // bf16 mode (gin_bf16.cu, gin_bwd_bf16.cu): the float* activation fields of the argument blocks point to bf16 data
@@ -66,8 +66,8 @@ struct GinBwdPreArgs {
 };
 struct GinBwdPrePair { GinBwdPreArgs a[2]; int split; };
 int gin_bwd_pre_grid(int V);
-void launch_gin_bwd_pre(const GinBwdPreArgs& a, cudaStream_t s);
-void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, cudaStream_t s);   // grid = gin_bwd_pre_grid(V0 + V1)
+void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s);
+void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, int hidden, cudaStream_t s);   // grid = gin_bwd_pre_grid(V0 + V1)
 int pair_split(int grid, int work0, int work1);     // CTAs given to problem 0
 
 struct GinBwdMainArgs {
@@ -80,7 +80,7 @@ struct GinBwdMainArgs {
   int64_t pstride;
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
-void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);      // FP32 FFMA tiles
+void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s);      // FP32 FFMA tiles, hidden 64 / 128
 struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; int reverse = 0; };
 void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // tcgen05 3xTF32, 64-row double-buffered tiles (gin_bwd_tc2.cu)
 void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
@@ -113,7 +113,7 @@ struct GateLinFwdArgs {
   float* H; float* q;
   bool y_bf16 = false;
 };
-void launch_gate_lin_fwd(const GateLinFwdArgs& a, cudaStream_t s);
+void launch_gate_lin_fwd(const GateLinFwdArgs& a, int hidden, cudaStream_t s);
 
 // gH += g_q Wc1 ; dWc1 = g_q^T H ; dbc1 = sum g_q     (persistent, per-CTA partials)
 struct GateLinBwdArgs {
@@ -122,7 +122,7 @@ struct GateLinBwdArgs {
   float* gH;                             // in/out [N][HID]
   float* part; int64_t pstride; int64_t off_W, off_b;
 };
-void launch_gate_lin_bwd(const GateLinBwdArgs& a, int grid, cudaStream_t s);
+void launch_gate_lin_bwd(const GateLinBwdArgs& a, int hidden, int grid, cudaStream_t s);
 
 // C_v = sum_{j in ego(v)} relu(BN(y2_last_j)) ; logit_v = w_cand . C_v
 struct EgoPoolFwdArgs {
@@ -131,9 +131,9 @@ struct EgoPoolFwdArgs {
   float* C; float* logit;
   bool y_bf16 = false;                   // y is bf16 storage (bf16 mode)
 };
-void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, cudaStream_t s);
+void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, int hidden, cudaStream_t s);
 
-void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, cudaStream_t s);
+void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, int hidden, cudaStream_t s);
 
 // Per-graph gate + attention softmax (warp per graph): models.py:595-604, 631-660, 738-748
 struct GraphGateFwdArgs {
@@ -153,10 +153,10 @@ struct GraphGateFwdArgs {
   float* cstat;                          // optional [B][2][HID] compressor-BN batch mean / unbiased var per graph
   float* kl;                             // [1] KL loss (last graph)
 };
-void launch_graph_gate_fwd(const GraphGateFwdArgs& a, cudaStream_t s);
+void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s);
 
 // compressor BatchNorm running stats: B sequential EMA updates in closed form (models.py:642 per graph)
-void launch_compressor_ema(const float* cstat, int B, float* running, cudaStream_t s);
+void launch_compressor_ema(const float* cstat, int B, float* running, int hidden, cudaStream_t s);
 
 struct GraphGateBwdArgs {
   const int32_t* graph_ptr; int B; int N;
@@ -178,7 +178,7 @@ struct GraphGateBwdArgs {
   unsigned int* counter;
   float *d_gamma_c, *d_beta_c, *d_wc2, *d_bc2, *d_attn_w, *d_attn_b;   // final gradients
 };
-void launch_graph_gate_bwd(const GraphGateBwdArgs& a, cudaStream_t s);
+void launch_graph_gate_bwd(const GraphGateBwdArgs& a, int hidden, cudaStream_t s);
 
 // Z = Wm2 relu(Wm1 [noisy || alpha*C] + bm1) + bm2       (models.py:676, 749)
 struct HeadFwdArgs {
@@ -190,21 +190,13 @@ struct HeadFwdArgs {
   float* r;                              // [N][HID] saved
   float* Z;                              // [N][HID]
 };
-void launch_head_fwd(const HeadFwdArgs& a, cudaStream_t s);
+void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s);
 
-struct HeadBwdArgs {
-  const float* gZ;                       // [N][HID]
-  const float *noisy, *C, *alpha, *r; int N;
-  const float *W1, *W2;                  // natural: W1 [HID][2*HID], W2 [HID][HID]
-  float* gI;                             // [N][2*HID]
-  float* part; int64_t pstride; int64_t off_W1, off_b1, off_W2, off_b2;
-};
-void launch_head_bwd(const HeadBwdArgs& a, int grid, cudaStream_t s);
-// Tensor-core head backward = the GIN backward kernel run on the two K = 64 halves of the first head layer (api.cu).
+// Head backward = the GIN backward kernel run on the two K = H halves of the first head layer (api.cu).
 // prep: dense copies W1a = W1[:, :HID], W1b = W1[:, HID:] and the identity BatchNorm-backward constants
 // (bn = {0, 1, 1, 0}, cvec = 0: g_y = g_o).  fix: grads slot [2][HID][HID] (dW1a | dW1b) -> [HID][2*HID] in place.
-void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, cudaStream_t s);
-void launch_head_dw1_interleave(float* dW1, cudaStream_t s);
+void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, int hidden, cudaStream_t s);
+void launch_head_dw1_interleave(float* dW1, int hidden, cudaStream_t s);
 
 // ---------------------------------------------------------------- loss_kernels.cu
 // recon: per-CTA partials of Z^T Z and of sum_{(i,j) in E} z_i . z_j     (models.py:762-768, Gram identity)
@@ -212,33 +204,33 @@ struct ReconFwdArgs {
   const float* Z; const int32_t* indptr; const int32_t* indices; int N;
   float* part;                           // [grid][HID*HID + 4]
 };
-void launch_recon_fwd(const ReconFwdArgs& a, int grid, cudaStream_t s);
+void launch_recon_fwd(const ReconFwdArgs& a, int hidden, int grid, cudaStream_t s);
 // G = sum of partials; edge = sum; one small kernel
-void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, cudaStream_t s);
+void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, int hidden, cudaStream_t s);
 // gZ = scale * (4/N) * (Z G - A Z)
 struct ReconBwdArgs {
   const float* Z; const float* G; const int32_t* indptr; const int32_t* indices; int N;
   float scale; float* gZ;
 };
-void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s);
+void launch_recon_bwd(const ReconBwdArgs& a, int hidden, cudaStream_t s);
 
 // contrastive (models.py:606-629)
 struct NormalizeArgs { const float *core, *readout; int B; float *z1, *z2, *n1, *n2, *diag; float* zsplit; };  // zsplit: optional [4][B][HID] tf32 hi/lo of z1, z2
-void launch_normalize(const NormalizeArgs& a, cudaStream_t s);
+void launch_normalize(const NormalizeArgs& a, int hidden, cudaStream_t s);
 struct ContrastiveFwdArgs { const float *z1, *z2; int B; int jsplit; float* rowsum; const float* zsplit; };  // rowsum [jsplit][B]
-void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s);        // FP32 FFMA tiles
+void launch_contrastive_fwd(const ContrastiveFwdArgs& a, int hidden, cudaStream_t s);        // FP32 FFMA tiles (hidden 64 / 128)
 void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s);     // tcgen05 3xTF32 (contrastive_tc.cu)
 struct ContrastiveBwdArgs {
   const float *z1, *z2, *D; int B; int jsplit;
   float* g1p; float* g2p;                // [jsplit][B][HID] partial gradients wrt z1_hat / z2_hat
 };
-void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s);                          // FP32 FFMA tiles
+void launch_contrastive_bwd(const ContrastiveBwdArgs& a, int hidden, cudaStream_t s);                          // FP32 FFMA tiles (hidden 64 / 128)
 void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s);   // tcgen05 (contrastive_tc.cu)
 struct ContrastiveBwdFinArgs {
   const float *g1p, *g2p, *z1, *z2, *n1, *n2; int B; int jsplit; float scale;
   float *g_core, *g_readout;
 };
-void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, cudaStream_t s);
+void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, int hidden, cudaStream_t s);
 int contrastive_jsplit(int B);
 
 struct LossFinalizeArgs {
@@ -248,6 +240,7 @@ struct LossFinalizeArgs {
   const float* kl;
   float* D;                                                      // [B] contrastive denominators (saved)
   float* losses;                                                 // {KL, contrastive, recon, total}
+  int hidden = HID;                                              // G is [hidden][hidden]
 };
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s);
 

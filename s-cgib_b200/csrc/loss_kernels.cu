@@ -13,18 +13,19 @@
 namespace scgib {
 
 constexpr int GT = 128;
-constexpr int GLD = HID + 4;
 constexpr int CT = 64;   // contrastive tile
 
 // ------------------------------------------------------------------------------------------------
 // recon forward: per-CTA partial Gram matrix + partial edge-dot sum
 // ------------------------------------------------------------------------------------------------
-struct ReconFwdSmem { float z[GT * GLD]; float red[kThreads / 32]; };
+template <int HID> struct ReconFwdSmem { float z[GT * (HID + 4)]; float red[kThreads / 32]; };
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HID>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 recon_fwd_kernel(ReconFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ReconFwdSmem& sm = *reinterpret_cast<ReconFwdSmem*>(smem_raw);
+  ReconFwdSmem<HID>& sm = *reinterpret_cast<ReconFwdSmem<HID>*>(smem_raw);
+  constexpr int GLD = HID + 4, LPR = HID / 4, RPP = kThreads / LPR;
   using T = TNMap<HID, HID>;
   float G[T::TO][T::TJ];
 #pragma unroll
@@ -32,7 +33,7 @@ recon_fwd_kernel(ReconFwdArgs p) {
 #pragma unroll
     for (int j = 0; j < T::TJ; ++j) G[i][j] = 0.f;
   float ed = 0.f;
-  const int l = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  const int l = threadIdx.x % LPR, hw = threadIdx.x / LPR;
   const int n_tiles = (p.N + GT - 1) / GT;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * GT;
@@ -40,7 +41,7 @@ recon_fwd_kernel(ReconFwdArgs p) {
     load_row_tile<GT, HID>(sm.z, GLD, p.Z, base, p.N);
     __syncthreads();
     gemm_tn<HID, HID>(sm.z, GLD, sm.z, GLD, GT, G);
-    for (int r = hw; r < GT; r += 16) {
+    for (int r = hw; r < GT; r += RPP) {
       const int v = base + r;
       if (v < p.N) {
         float4 nb = make4(0.f);
@@ -65,19 +66,22 @@ recon_fwd_kernel(ReconFwdArgs p) {
     part[HID * HID] = s;
   }
 }
-void launch_recon_fwd(const ReconFwdArgs& a, int grid, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(recon_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(ReconFwdSmem)), true);
+template <int H>
+static void launch_recon_fwd_t(const ReconFwdArgs& a, int grid, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(recon_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconFwdSmem<H>)), true);
   (void)once;
-  recon_fwd_kernel<<<grid, kThreads, sizeof(ReconFwdSmem), s>>>(a);
+  recon_fwd_kernel<H><<<grid, kThreads, sizeof(ReconFwdSmem<H>), s>>>(a);
+}
+void launch_recon_fwd(const ReconFwdArgs& a, int hidden, int grid, cudaStream_t s) {
+  if (hidden == 64) launch_recon_fwd_t<64>(a, grid, s); else launch_recon_fwd_t<128>(a, grid, s);
 }
 
 __global__ void __launch_bounds__(kThreads)
-recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum) {
+recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum, int HID) {
   const int j = blockIdx.x * kThreads + threadIdx.x;
   if (j > HID * HID) return;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // interleaved partial sums: independent loads in flight, fixed order
-  constexpr size_t ST = HID * HID + 4;
+  const size_t ST = (size_t)HID * HID + 4;
   int c = 0;
 #pragma unroll 4
   for (; c + 3 < grid; c += 4) {
@@ -88,17 +92,19 @@ recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict_
   const double s = (s0 + s1) + (s2 + s3);
   if (j < HID * HID) G[j] = (float)s; else edge_sum[0] = (float)s;
 }
-void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, cudaStream_t s) {
-  recon_reduce_kernel<<<(HID * HID + 1 + kThreads - 1) / kThreads, kThreads, 0, s>>>(part, grid, G, edge_sum);
+void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, int hidden, cudaStream_t s) {
+  recon_reduce_kernel<<<(hidden * hidden + 1 + kThreads - 1) / kThreads, kThreads, 0, s>>>(part, grid, G, edge_sum, hidden);
 }
 
 // recon backward: gZ = scale * (4/N) * (Z G - A Z)
-struct ReconBwdSmem { float z[GT * GLD]; float g[HID * HID]; };
+template <int HID> struct ReconBwdSmem { float z[GT * (HID + 4)]; float g[HID * HID]; };
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HID>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 recon_bwd_kernel(ReconBwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ReconBwdSmem& sm = *reinterpret_cast<ReconBwdSmem*>(smem_raw);
+  ReconBwdSmem<HID>& sm = *reinterpret_cast<ReconBwdSmem<HID>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   using M = NNMap<GT, HID>;
   load_matrix<HID>(sm.g, HID, p.G, HID);
   const float k = p.scale * 4.f / (float)p.N;
@@ -126,12 +132,15 @@ recon_bwd_kernel(ReconBwdArgs p) {
     }
   }
 }
-void launch_recon_bwd(const ReconBwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(recon_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(ReconBwdSmem)), true);
+template <int H>
+static void launch_recon_bwd_t(const ReconBwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(recon_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconBwdSmem<H>)), true);
   (void)once;
-  const int grid = min((a.N + GT - 1) / GT, 2 * num_sms());
-  recon_bwd_kernel<<<grid, kThreads, sizeof(ReconBwdSmem), s>>>(a);
+  const int grid = min((a.N + GT - 1) / GT, (H == 64 ? 2 : 1) * num_sms());
+  recon_bwd_kernel<H><<<grid, kThreads, sizeof(ReconBwdSmem<H>), s>>>(a);
+}
+void launch_recon_bwd(const ReconBwdArgs& a, int hidden, cudaStream_t s) {
+  if (hidden == 64) launch_recon_bwd_t<64>(a, s); else launch_recon_bwd_t<128>(a, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,9 +156,26 @@ __device__ __forceinline__ float tf32_round(float v) {
 }
 
 // z1 = core / max(||core||, 1e-12), z2 = readout / max(||readout||, 1e-12), diag = z1 . z2   (warp per row)
+// (HID = 128: the same kernel run on channel pairs 2*lane and 64 + 2*lane; norms and the diagonal sum both halves)
+template <int HID>
 __global__ void __launch_bounds__(kThreads)
 normalize_kernel(NormalizeArgs p) {
   const int lane = threadIdx.x & 31, c = 2 * lane;
+  if (HID == 128) {
+    for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
+      const float2 a0 = ld2(p.core + (size_t)i * HID + c), a1 = ld2(p.core + (size_t)i * HID + 64 + c);
+      const float2 b0 = ld2(p.readout + (size_t)i * HID + c), b1 = ld2(p.readout + (size_t)i * HID + 64 + c);
+      const float na = fmaxf(sqrtf(warp_sum((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y))), 1e-12f);
+      const float nb = fmaxf(sqrtf(warp_sum((b0.x * b0.x + b0.y * b0.y) + (b1.x * b1.x + b1.y * b1.y))), 1e-12f);
+      const float2 za0 = make_float2(a0.x / na, a0.y / na), za1 = make_float2(a1.x / na, a1.y / na);
+      const float2 zb0 = make_float2(b0.x / nb, b0.y / nb), zb1 = make_float2(b1.x / nb, b1.y / nb);
+      st2(p.z1 + (size_t)i * HID + c, za0); st2(p.z1 + (size_t)i * HID + 64 + c, za1);
+      st2(p.z2 + (size_t)i * HID + c, zb0); st2(p.z2 + (size_t)i * HID + 64 + c, zb1);
+      const float d = warp_sum((za0.x * zb0.x + za0.y * zb0.y) + (za1.x * zb1.x + za1.y * zb1.y));
+      if (lane == 0) { p.n1[i] = na; p.n2[i] = nb; p.diag[i] = d; }
+    }
+    return;
+  }
   for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
     const float2 a = ld2(p.core + (size_t)i * HID + c), b = ld2(p.readout + (size_t)i * HID + c);
     const float na = fmaxf(sqrtf(warp_sum(a.x * a.x + a.y * a.y)), 1e-12f);
@@ -169,8 +195,10 @@ normalize_kernel(NormalizeArgs p) {
     if (lane == 0) { p.n1[i] = na; p.n2[i] = nb; p.diag[i] = d; }
   }
 }
-void launch_normalize(const NormalizeArgs& a, cudaStream_t s) {
-  normalize_kernel<<<min((a.B + 7) / 8, 8 * num_sms()), kThreads, 0, s>>>(a);
+void launch_normalize(const NormalizeArgs& a, int hidden, cudaStream_t s) {
+  const int grid = min((a.B + 7) / 8, 8 * num_sms());
+  if (hidden == 64) normalize_kernel<64><<<grid, kThreads, 0, s>>>(a);
+  else normalize_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 
 int contrastive_jsplit(int B) {
@@ -185,7 +213,9 @@ int contrastive_jsplit(int B) {
 }
 
 // S[i][j] = a_i . b_j for a 64x64 tile pair; thread (ti,tj): rows ti*4+ii, columns tj+16*jj (conflict-free float4 reads)
+template <int HID>
 __device__ __forceinline__ void sim_tile(const float* __restrict__ As, const float* __restrict__ Bs, float (&s)[4][4]) {
+  constexpr int GLD = HID + 4;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -206,12 +236,14 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ As, const flo
   }
 }
 
-struct ConFwdSmem { float zi[CT * GLD]; float zj1[CT * GLD]; float zj2[CT * GLD]; };
+template <int HID> struct ConFwdSmem { float zi[CT * (HID + 4)]; float zj1[CT * (HID + 4)]; float zj2[CT * (HID + 4)]; };
 
+template <int HID>
 __global__ void __launch_bounds__(kThreads, 2)
 contrastive_fwd_kernel(ContrastiveFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ConFwdSmem& sm = *reinterpret_cast<ConFwdSmem*>(smem_raw);
+  ConFwdSmem<HID>& sm = *reinterpret_cast<ConFwdSmem<HID>*>(smem_raw);
+  constexpr int GLD = HID + 4;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
   const int ibase = blockIdx.x * CT;
   const int jblocks = (p.B + CT - 1) / CT;
@@ -224,7 +256,7 @@ contrastive_fwd_kernel(ContrastiveFwdArgs p) {
     load_row_tile<CT, HID>(sm.zj2, GLD, p.z2, jbase, p.B);
     __syncthreads();
     float s[4][4];
-    sim_tile(sm.zi, sm.zj1, s);
+    sim_tile<HID>(sm.zi, sm.zj1, s);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -232,7 +264,7 @@ contrastive_fwd_kernel(ContrastiveFwdArgs p) {
         const int gi = ibase + ti * 4 + i, gj = jbase + tj + 16 * j;
         if (gj < p.B && gj != gi) rs[i] += expf(s[i][j]);       // refl_sim.sum(1) - refl_sim.diag()
       }
-    sim_tile(sm.zi, sm.zj2, s);
+    sim_tile<HID>(sm.zi, sm.zj2, s);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -250,24 +282,29 @@ contrastive_fwd_kernel(ContrastiveFwdArgs p) {
     if (tj == 0 && gi < p.B) p.rowsum[(size_t)blockIdx.y * p.B + gi] = v;
   }
 }
-void launch_contrastive_fwd(const ContrastiveFwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(contrastive_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(ConFwdSmem)), true);
+template <int H>
+static void launch_contrastive_fwd_t(const ContrastiveFwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(contrastive_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConFwdSmem<H>)), true);
   (void)once;
   dim3 grid((a.B + CT - 1) / CT, a.jsplit);
-  contrastive_fwd_kernel<<<grid, kThreads, sizeof(ConFwdSmem), s>>>(a);
+  contrastive_fwd_kernel<H><<<grid, kThreads, sizeof(ConFwdSmem<H>), s>>>(a);
+}
+void launch_contrastive_fwd(const ContrastiveFwdArgs& a, int hidden, cudaStream_t s) {
+  if (hidden == 64) launch_contrastive_fwd_t<64>(a, s); else launch_contrastive_fwd_t<128>(a, s);
 }
 
 // backward.  blockIdx.z == 0: rows of z1 (g1);  blockIdx.z == 1: rows of z2 (g2).
 //   g1_i = sum_{j!=i} e^{s_r(i,j)} (1/D_i + 1/D_j) z1_j + sum_j e^{s_b(i,j)}/D_i z2_j
 //   g2_j = sum_i e^{s_b(i,j)}/D_i z1_i
 // (the 1/B factor and the -z2_i / -z1_j terms are applied in the finalise kernel)
-struct ConBwdSmem { float zi[CT * GLD]; float zj1[CT * GLD]; float zj2[CT * GLD]; float P[CT * GLD]; float Di[CT]; float Dj[CT]; };
+template <int HID> struct ConBwdSmem { float zi[CT * (HID + 4)]; float zj1[CT * (HID + 4)]; float zj2[CT * (HID + 4)]; float P[CT * (CT + 4)]; float Di[CT]; float Dj[CT]; };
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HID>
+__global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 contrastive_bwd_kernel(ContrastiveBwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ConBwdSmem& sm = *reinterpret_cast<ConBwdSmem*>(smem_raw);
+  ConBwdSmem<HID>& sm = *reinterpret_cast<ConBwdSmem<HID>*>(smem_raw);
+  constexpr int GLD = HID + 4, PLD = CT + 4;
   using M = NNMap<CT, HID>;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
   const bool mode1 = (blockIdx.z == 1);
@@ -286,7 +323,7 @@ contrastive_bwd_kernel(ContrastiveBwdArgs p) {
     if (threadIdx.x < CT) sm.Dj[threadIdx.x] = (jbase + threadIdx.x < p.B) ? 1.f / p.D[jbase + threadIdx.x] : 0.f;
     __syncthreads();
     float s[4][4];
-    sim_tile(sm.zi, sm.zj1, s);
+    sim_tile<HID>(sm.zi, sm.zj1, s);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -296,22 +333,22 @@ contrastive_bwd_kernel(ContrastiveBwdArgs p) {
         float w;
         if (mode1) w = sm.Dj[lj];                                   // rows are z2_j', columns z1_i: weight 1/D_i of the column
         else w = (gj != gi) ? sm.Di[li] + sm.Dj[lj] : 0.f;
-        sm.P[li * GLD + lj] = (gj < p.B && gi < p.B) ? expf(s[i][j]) * w : 0.f;
+        sm.P[li * PLD + lj] = (gj < p.B && gi < p.B) ? expf(s[i][j]) * w : 0.f;
       }
     __syncthreads();
-    gemm_nn<CT, CT, HID>(sm.P, GLD, sm.zj1, GLD, acc);
+    gemm_nn<CT, CT, HID>(sm.P, PLD, sm.zj1, GLD, acc);
     if (!mode1) {
-      sim_tile(sm.zi, sm.zj2, s);
+      sim_tile<HID>(sm.zi, sm.zj2, s);
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int li = ti * 4 + i, lj = tj + 16 * j;
-          sm.P[li * GLD + lj] = (jbase + lj < p.B && ibase + li < p.B) ? expf(s[i][j]) * sm.Di[li] : 0.f;
+          sm.P[li * PLD + lj] = (jbase + lj < p.B && ibase + li < p.B) ? expf(s[i][j]) * sm.Di[li] : 0.f;
         }
       __syncthreads();
-      gemm_nn<CT, CT, HID>(sm.P, GLD, sm.zj2, GLD, acc);
+      gemm_nn<CT, CT, HID>(sm.P, PLD, sm.zj2, GLD, acc);
     }
   }
   float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
@@ -322,36 +359,53 @@ contrastive_bwd_kernel(ContrastiveBwdArgs p) {
     if (gi < p.B) st4(out + (size_t)gi * HID + c0, make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
   }
 }
-void launch_contrastive_bwd(const ContrastiveBwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(contrastive_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(ConBwdSmem)), true);
+template <int H>
+static void launch_contrastive_bwd_t(const ContrastiveBwdArgs& a, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(contrastive_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConBwdSmem<H>)), true);
   (void)once;
   dim3 grid((a.B + CT - 1) / CT, a.jsplit, 2);
-  contrastive_bwd_kernel<<<grid, kThreads, sizeof(ConBwdSmem), s>>>(a);
+  contrastive_bwd_kernel<H><<<grid, kThreads, sizeof(ConBwdSmem<H>), s>>>(a);
+}
+void launch_contrastive_bwd(const ContrastiveBwdArgs& a, int hidden, cudaStream_t s) {
+  if (hidden == 64) launch_contrastive_bwd_t<64>(a, s); else launch_contrastive_bwd_t<128>(a, s);
 }
 
 // g wrt the un-normalised readouts: (g - z_hat (z_hat . g)) / max(||z||, 1e-12)     (warp per row)
+template <int HID>
 __global__ void __launch_bounds__(kThreads)
 contrastive_bwd_finalize_kernel(ContrastiveBwdFinArgs p) {
+  constexpr int NH = HID / 64;                  // a lane owns channel pairs 2*lane + 64*h
   const int lane = threadIdx.x & 31, c = 2 * lane;
   const float k = p.scale / (float)p.B;
   for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
-    float2 g1 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f);
-    for (int js = 0; js < p.jsplit; ++js) {
-      const float2 a = ld2(p.g1p + ((size_t)js * p.B + i) * HID + c), b = ld2(p.g2p + ((size_t)js * p.B + i) * HID + c);
-      g1.x += a.x; g1.y += a.y; g2.x += b.x; g2.y += b.y;
+    float2 g1[NH], g2[NH], z1[NH], z2[NH];
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      g1[h] = make_float2(0.f, 0.f); g2[h] = make_float2(0.f, 0.f);
+      for (int js = 0; js < p.jsplit; ++js) {
+        const float2 a = ld2(p.g1p + ((size_t)js * p.B + i) * HID + 64 * h + c), b = ld2(p.g2p + ((size_t)js * p.B + i) * HID + 64 * h + c);
+        g1[h].x += a.x; g1[h].y += a.y; g2[h].x += b.x; g2[h].y += b.y;
+      }
+      z1[h] = ld2(p.z1 + (size_t)i * HID + 64 * h + c); z2[h] = ld2(p.z2 + (size_t)i * HID + 64 * h + c);
+      g1[h].x = k * (g1[h].x - z2[h].x); g1[h].y = k * (g1[h].y - z2[h].y);
+      g2[h].x = k * (g2[h].x - z1[h].x); g2[h].y = k * (g2[h].y - z1[h].y);
+      const float p1 = z1[h].x * g1[h].x + z1[h].y * g1[h].y, p2 = z2[h].x * g2[h].x + z2[h].y * g2[h].y;
+      t1 = h == 0 ? p1 : t1 + p1; t2 = h == 0 ? p2 : t2 + p2;
     }
-    const float2 z1 = ld2(p.z1 + (size_t)i * HID + c), z2 = ld2(p.z2 + (size_t)i * HID + c);
-    g1.x = k * (g1.x - z2.x); g1.y = k * (g1.y - z2.y);
-    g2.x = k * (g2.x - z1.x); g2.y = k * (g2.y - z1.y);
-    const float d1 = warp_sum(z1.x * g1.x + z1.y * g1.y), d2 = warp_sum(z2.x * g2.x + z2.y * g2.y);
+    const float d1 = warp_sum(t1), d2 = warp_sum(t2);
     const float n1 = p.n1[i], n2 = p.n2[i];
-    st2(p.g_core + (size_t)i * HID + c, make_float2((g1.x - z1.x * d1) / n1, (g1.y - z1.y * d1) / n1));
-    st2(p.g_readout + (size_t)i * HID + c, make_float2((g2.x - z2.x * d2) / n2, (g2.y - z2.y * d2) / n2));
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      st2(p.g_core + (size_t)i * HID + 64 * h + c, make_float2((g1[h].x - z1[h].x * d1) / n1, (g1[h].y - z1[h].y * d1) / n1));
+      st2(p.g_readout + (size_t)i * HID + 64 * h + c, make_float2((g2[h].x - z2[h].x * d2) / n2, (g2[h].y - z2[h].y * d2) / n2));
+    }
   }
 }
-void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, cudaStream_t s) {
-  contrastive_bwd_finalize_kernel<<<min((a.B + 7) / 8, 8 * num_sms()), kThreads, 0, s>>>(a);
+void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, int hidden, cudaStream_t s) {
+  const int grid = min((a.B + 7) / 8, 8 * num_sms());
+  if (hidden == 64) contrastive_bwd_finalize_kernel<64><<<grid, kThreads, 0, s>>>(a);
+  else contrastive_bwd_finalize_kernel<128><<<grid, kThreads, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,7 +423,7 @@ loss_finalize_kernel(LossFinalizeArgs p) {
     con += (double)(logf(d) - p.diag[i]);      // -log(exp(s_b(i,i)) / D_i)
   }
   if (!p.recon_override)
-    for (int j = threadIdx.x; j < HID * HID; j += kFin) { const double g = (double)p.G[j]; fro += g * g; }
+    for (int j = threadIdx.x; j < p.hidden * p.hidden; j += kFin) { const double g = (double)p.G[j]; fro += g * g; }
   s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
   __syncthreads();
   for (int o = kFin / 2; o > 0; o >>= 1) {

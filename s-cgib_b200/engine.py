@@ -36,12 +36,13 @@ def param_names(gin_layers: int):
     return names
 
 
-def param_shapes(in_dim: int, gin_layers: int):
-    shapes = [(HID, 2 * HID), (HID,), (HID, HID), (HID,), (HID, HID), (HID,), (HID,), (HID,), (1, HID), (1,),
-              (1, 2 * HID), (1,), (DTR, in_dim)]
+def param_shapes(in_dim: int, gin_layers: int, hidden: int = HID):
+    H = hidden
+    shapes = [(H, 2 * H), (H,), (H, H), (H,), (H, H), (H,), (H,), (H,), (1, H), (1,),
+              (1, 2 * H), (1,), (DTR, in_dim)]
     for _e in range(2):
         for l in range(gin_layers):
-            shapes += [(HID, DTR if l == 0 else HID), (HID,), (HID, HID), (HID,), (HID,), (HID,)]
+            shapes += [(H, DTR if l == 0 else H), (H,), (H, H), (H,), (H,), (H,)]
     return shapes
 
 
@@ -80,9 +81,9 @@ class DeviceBatch:
         b.eval_mode = int(bool(self.eval_mode))
         return b
 
-    def algorithmic_bytes(self, gin_layers=4, F=9, s=4):   # s = bytes per activation element (2 in bf16 mode)
+    def algorithmic_bytes(self, gin_layers=4, F=9, s=4, hidden=HID):   # s = bytes per activation element (2 in bf16 mode)
         """SURVEY.md §8(d) 'algorithmic bytes per training step' evaluated on this batch's actual sizes."""
-        N, E, Ns, Es, d = self.N, self.E, self.Ns, self.Es, HID
+        N, E, Ns, Es, d = self.N, self.E, self.Ns, self.Es, hidden
 
         def enc(V, D):
             tot = 0
@@ -108,6 +109,7 @@ class PretrainEngine:
         if dtype not in ("fp32", "bf16"):
             raise ValueError("dtype must be 'fp32' or 'bf16'")
         self.dtype = dtype
+        self.hidden = int(hidden)
         self.dims = _lib.Dims(int(in_dim), int(d_transfer), int(hidden), int(gin_layers),
                               _lib.ACT_BF16 if dtype == "bf16" else _lib.ACT_F32)
         n = self.lib.scgib_param_slots(ctypes.byref(self.dims))
@@ -118,7 +120,7 @@ class PretrainEngine:
         self.total = int(self.lib.scgib_param_layout(ctypes.byref(self.dims), off, sz))
         self.offsets, self.sizes = list(off), list(sz)
         self.names = param_names(gin_layers)
-        self.shapes = param_shapes(in_dim, gin_layers)
+        self.shapes = param_shapes(in_dim, gin_layers, self.hidden)
         assert len(self.names) == n == len(self.shapes)
         self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros_like(self.params)
@@ -197,10 +199,11 @@ class PretrainEngine:
                     exp_avg=self.exp_avg.detach().clone(), exp_avg_sq=self.exp_avg_sq.detach().clone(),
                     step_count=self.step_count, num_batches_tracked=self.num_batches_tracked,
                     noise_state=self._noise_gen.get_state(), gin_layers=int(self.dims.gin_layers),
-                    in_dim=int(self.dims.in_dim))
+                    in_dim=int(self.dims.in_dim), hidden=self.hidden)
 
     def restore(self, ck):
-        if int(ck["gin_layers"]) != int(self.dims.gin_layers) or int(ck["in_dim"]) != int(self.dims.in_dim):
+        if int(ck["gin_layers"]) != int(self.dims.gin_layers) or int(ck["in_dim"]) != int(self.dims.in_dim) or \
+                int(ck.get("hidden", HID)) != self.hidden:
             raise ValueError("checkpoint was written for different model dimensions")
         self.params.copy_(ck["params"])
         self.bn_running.copy_(ck["bn_running"])
@@ -291,7 +294,7 @@ class PretrainEngine:
     def draw_noise(self, N):
         """U[0,1) gate / feature noise (reference: CPU torch.rand per graph, device rand_like: models.py:599, 650)."""
         return (torch.rand(N, device=self.device, generator=self._noise_gen),
-                torch.rand(N, HID, device=self.device, generator=self._noise_gen))
+                torch.rand(N, self.hidden, device=self.device, generator=self._noise_gen))
 
     def _workspace(self, b: DeviceBatch):
         need = self.lib.scgib_pretrain_workspace_bytes(ctypes.byref(self.dims), b.B, b.N, b.E, b.Ns, b.Es)
@@ -324,9 +327,10 @@ class PretrainEngine:
         ws = self._workspace(b)
         emb = None
         if want:
-            emb = dict(interaction_map=torch.empty(b.N, 2 * HID, device=self.device),
-                       Z=torch.empty(b.N, HID, device=self.device), noisy=torch.empty(b.N, HID, device=self.device),
-                       graph_readout=torch.empty(b.B, HID, device=self.device))
+            H = self.hidden
+            emb = dict(interaction_map=torch.empty(b.N, 2 * H, device=self.device),
+                       Z=torch.empty(b.N, H, device=self.device), noisy=torch.empty(b.N, H, device=self.device),
+                       graph_readout=torch.empty(b.B, H, device=self.device))
         p = self.params if params is None else params
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_pretrain_forward_f32(
@@ -363,8 +367,8 @@ class PretrainEngine:
         self.fwd_serial += 1
         cb = b.c_struct(self._last[1], self._last[2])
         ws = self._workspace(b)
-        Z = torch.empty(b.N, HID, device=self.device)
-        imap = torch.empty(b.N, 2 * HID, device=self.device) if want_imap else None
+        Z = torch.empty(b.N, self.hidden, device=self.device)
+        imap = torch.empty(b.N, 2 * self.hidden, device=self.device) if want_imap else None
         p = self.params if params is None else params
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_extract_forward_f32(
@@ -381,7 +385,7 @@ class PretrainEngine:
         cb = b.c_struct(gate_u, feat_u)
         ws = self._workspace(b)
         gZ = gZ.contiguous().float()
-        assert gZ.shape == (b.N, HID) and gZ.device == self.device
+        assert gZ.shape == (b.N, self.hidden) and gZ.device == self.device
         p = self.params if params is None else params
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.scgib_extract_backward_f32(ctypes.byref(self.dims), _lib.ptr(p), ctypes.byref(cb), _lib.ptr(gZ),

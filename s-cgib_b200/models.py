@@ -50,8 +50,9 @@ class GIN(nn.Module):
 
     def __init__(self, input_dim, hidden_dim=64, num_gin_layers=DEFAULT_GIN_LAYERS):
         super().__init__()
-        if hidden_dim != HID:
-            raise NotImplementedError("libscgib is built for hidden_dim=64 (exp_pretraining.py:390)")
+        if hidden_dim not in (64, 128):
+            raise NotImplementedError("libscgib is built for hidden_dim 64 or 128 (--dims, exp_pretraining.py:390)")
+        self.hidden_dim = hidden_dim
         self.ginlayers = nn.ModuleList()
         self.batch_norms = nn.ModuleList()
         for layer in range(num_gin_layers):
@@ -62,6 +63,9 @@ class GIN(nn.Module):
     @torch.no_grad()
     def forward(self, g, h):
         from . import ops
+        if self.hidden_dim != HID:
+            raise NotImplementedError("the stand-alone GIN.forward (op-level entry) is built for hidden_dim=64; the models run 128 "
+                                      "through Mainmodel.forward")
         indptr, indices = (g.sub_indptr, g.sub_indices) if isinstance(g, EgoBatch) else (g.indptr, g.indices)
         bn_in = None
         for i, layer in enumerate(self.ginlayers):
@@ -239,9 +243,10 @@ class _HotPathMixin:
         # reference: gate noise from the CPU generator (models.py:599), feature noise on the device (models.py:650).
         # Both are drawn on the device here (the CPU draw + copy costs ~0.3 ms per step at B = 4096 and the reference's
         # per-graph CPU stream is not reproducible from a batched draw anyway); SCGIB_CPU_GATE_NOISE=1 restores the CPU draw.
+        H = int(self.hidden_dim)
         if _CPU_GATE_NOISE:
-            return torch.rand(N).to(device, non_blocking=True), torch.rand(N, HID, device=device)
-        return torch.rand(N, device=device), torch.rand(N, HID, device=device)
+            return torch.rand(N).to(device, non_blocking=True), torch.rand(N, H, device=device)
+        return torch.rand(N, device=device), torch.rand(N, H, device=device)
 
     def forward(self, batch_g, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, current_epoch, edge_index,
                 k_transition, device, batch_size=16):

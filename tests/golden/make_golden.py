@@ -30,7 +30,7 @@ def load_reference_models(ref_root="/root/reference"):
     return importlib.import_module("models"), dgl_stub
 
 
-def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj"):
+def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj", hidden=64):
     g = synth_batch(seed, B)
     e = ego_batch_ref(g, k)
     s, d = g.edges()
@@ -43,7 +43,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj"):
 
     args = types.SimpleNamespace(recons_type=recons_type, useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
     torch.manual_seed(seed)
-    model = ref_models.Mainmodel(args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    model = ref_models.Mainmodel(args, 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
     model.train()
     state0 = {n: t.detach().clone() for n, t in model.state_dict().items()}
     batch_logMs = None
@@ -84,7 +84,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj"):
     used = set(grads) | {n for n in state0 if "running" in n or "num_batches" in n or n.endswith(".eps")}
     fx = dict(
         meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, reference="models.py Mainmodel (unmodified) on dgl_stub",
-                  torch=torch.__version__, recons_type=recons_type),
+                  torch=torch.__version__, recons_type=recons_type, hidden=hidden),
         graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
         ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
         state={n: t for n, t in state0.items() if n in used},
@@ -98,7 +98,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj"):
           "grads:", len(grads))
 
 
-def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
+def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10, hidden=64):
     """Mainmodel_finetuning (models.py:358-543) around a pickled pre-trained Mainmodel, one training step of
     train_pep_func.train_epoch_graph_classification (train_pep_func.py:137-157): BCE(sigmoid scores, targets) / 2."""
     import functools
@@ -114,8 +114,8 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
 
     pre_args = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
     torch.manual_seed(seed)
-    pre = ref_models.Mainmodel(pre_args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
-    ckpt = os.path.join(tempfile.mkdtemp(), "pre_training_synth_GIN_64_4_%d.pt" % k)
+    pre = ref_models.Mainmodel(pre_args, 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    ckpt = os.path.join(tempfile.mkdtemp(), "pre_training_synth_GIN_%d_4_%d.pt" % (hidden, k))
     torch.save(pre, ckpt)                                       # exp_pretraining.py:107 saves the whole module
     args = types.SimpleNamespace(dataset="Peptides-func", readout_f="sum", d_transfer=32, batch_size=B, useAtt=1,
                                  device="cpu", task="graph_classification")
@@ -123,7 +123,7 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
     torch.load = functools.partial(real_load, weights_only=False)   # torch >= 2.6 default; the reference targets 2.0.1
     try:
         torch.manual_seed(seed + 7)
-        model = ref_models.Mainmodel_finetuning(args, 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k,
+        model = ref_models.Mainmodel_finetuning(args, 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k,
                                                 num_classes=num_classes, cp_filename=ckpt, encoder="GIN")
     finally:
         torch.load = real_load
@@ -152,7 +152,7 @@ def make_finetune(seed, B, k, ref_models, dgl_stub, out_path, num_classes=10):
     used = set(grads) | {n for n in state0 if n.startswith("model.") and
                          n.split(".")[1] in ("Encoder1", "Encoder2", "compressor", "attn_layer")}
     fx = dict(
-        meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, num_classes=num_classes,
+        meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, num_classes=num_classes, hidden=hidden,
                   reference="models.py Mainmodel_finetuning (unmodified) on dgl_stub", torch=torch.__version__),
         graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
         ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
@@ -231,3 +231,7 @@ if __name__ == "__main__":
     make_finetune(3, 5, 1, ref_models, dgl_stub, os.path.join(HERE, "finetune_k1_b5.pt"))
     make_finetune(4, 11, 2, ref_models, dgl_stub, os.path.join(HERE, "finetune_k2_b11.pt"))
     make_domainadapt(5, 7, 1, ref_models, dgl_stub, os.path.join(HERE, "domainadapt_k1_b7.pt"))
+    # hidden_dim = 128 (--dims 128; BASELINE configs[4] GIN-5x128): the same unmodified reference classes at the wider width
+    make(8, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "pretrain_h128_k1_b6.pt"), hidden=128)
+    make(9, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "pretrain_h128_k2_b4.pt"), hidden=128)
+    make_finetune(10, 5, 1, ref_models, dgl_stub, os.path.join(HERE, "finetune_h128_k1_b5.pt"), hidden=128)

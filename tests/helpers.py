@@ -29,9 +29,13 @@ def product_ego_from_ref(pg, e: RefEgoBatch, k, device):
     return EgoBatch(pg, k, t(e.ego_ptr), t(e.ego_nodes), t(seed), t(e.sub_indptr), t(e.sub_indices))
 
 
-def engine_from_oracle(m: OracleMainmodel, device, gin_layers=4, in_dim=9):
+def hidden_of(m) -> int:
+    return m.attn_layer.in_features // 2
+
+
+def engine_from_oracle(m: OracleMainmodel, device, gin_layers=4, in_dim=9, dtype="fp32"):
     from scgib_b200.engine import PretrainEngine
-    eng = PretrainEngine(in_dim, gin_layers=gin_layers, device=device)
+    eng = PretrainEngine(in_dim, gin_layers=gin_layers, hidden=hidden_of(m), device=device, dtype=dtype)
     eng.load_state_dict({k: v.detach().float().to(device) for k, v in m.state_dict().items()}, strict=False)
     return eng
 
@@ -44,7 +48,7 @@ def oracle_grads(m, out):
 def fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=0):
     """fp64 vectorised oracle (forward + all parameter gradients) with the weights of ``m``: the ground truth
     both the fp32 reference run and the fp32 CUDA path are measured against."""
-    m64 = OracleMainmodel(m.transfer_d.in_features, 64, 32, len(m.Encoder1.ginlayers)).double()
+    m64 = OracleMainmodel(m.transfer_d.in_features, hidden_of(m), 32, len(m.Encoder1.ginlayers)).double()
     m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
     x = normalize_rows(torch.from_numpy(g.x).double())
     en = torch.from_numpy(e.ego_nodes.astype(np.int64))
@@ -94,8 +98,9 @@ def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_g
             assert float(got.abs().max()) <= 1e-5 * gmax, n
             continue
         if n == "attn_layer.weight":
-            assert float(got[:, :64].abs().max()) == 0.0          # core half: exactly zero
-            got, ref, truth = got[:, 64:], ref[:, 64:], truth[:, 64:]
+            H = got.shape[1] // 2
+            assert float(got[:, :H].abs().max()) == 0.0          # core half: exactly zero
+            got, ref, truth = got[:, H:], ref[:, H:], truth[:, H:]
         one("grad " + n, got, ref, truth, GRAD_TOL_MAX)
     gerr = sorted(r[1] for r in report if r[0].startswith("grad "))
     rerr = sorted(r[2] for r in report if r[0].startswith("grad "))

@@ -77,12 +77,12 @@ def _args(**kw):
     return a
 
 
-def _dropin_from_state(tmp_path, state, k, num_classes):
+def _dropin_from_state(tmp_path, state, k, num_classes, hidden=64):
     import models
-    pre = models.Mainmodel(_args(), 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
-    ckpt = str(tmp_path / ("pre_training_synth_GIN_64_4_%d.pt" % k))
+    pre = models.Mainmodel(_args(), 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    ckpt = str(tmp_path / ("pre_training_synth_GIN_%d_4_%d.pt" % (hidden, k)))
     torch.save(pre, ckpt)
-    m = models.Mainmodel_finetuning(_args(), 9, hidden_dim=64, num_layers=4, num_heads=4, k_transition=k,
+    m = models.Mainmodel_finetuning(_args(), 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k,
                                     num_classes=num_classes, cp_filename=ckpt, encoder="GIN")
     missing, unexpected = m.load_state_dict(state, strict=False)
     assert not unexpected
@@ -96,14 +96,14 @@ def test_mainmodel_finetuning_matches_reference_golden(path, tmp_path, monkeypat
     from scgib_b200.graph import khop_ego_batch
     fx = torch.load(path, weights_only=False)
     g, e = RefGraph(**fx["graph"]), RefEgoBatch(**fx["ego"])
-    k, C = fx["meta"]["k"], fx["meta"]["num_classes"]
-    m = _dropin_from_state(tmp_path, fx["state"], k, C)
+    k, C, H = fx["meta"]["k"], fx["meta"]["num_classes"], int(fx["meta"].get("hidden", 64))
+    m = _dropin_from_state(tmp_path, fx["state"], k, C, H)
     assert sorted(n for n, p in m.named_parameters() if p.requires_grad) == fx["trainable"]
     pg = product_graph(g, DEV)
     ego = khop_ego_batch(pg, k)
     assert np.array_equal(ego.ego_nodes.cpu().numpy(), e.ego_nodes)
     x = F.normalize(pg.ndata["x"].float())
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), H, fx["meta"]["noise_seed"])
     monkeypatch.setattr(m, "_noise", lambda N, dev: (gate_u.to(dev), feat_u.to(dev)))
     m.train()
     scores, z1, z2, z3 = m.forward(pg, x, ego, None, 1, None, 2, DEV, g.num_graphs)
@@ -125,7 +125,7 @@ def test_mainmodel_finetuning_matches_reference_golden(path, tmp_path, monkeypat
     assert errs[len(errs) // 2][0] <= 5e-5 and errs[-1][0] <= 5e-3, errs[-3:]
     # evaluate_network (train_pep_func.py:187-230): model.eval() -> every BatchNorm uses its running statistics
     m.eval()
-    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"] + 1)
+    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), H, fx["meta"]["noise_seed"] + 1)
     monkeypatch.setattr(m, "_noise", lambda N, dev: (gu2.to(dev), fu2.to(dev)))
     with torch.no_grad():
         scores_eval, _, _, _ = m.forward(pg, x, ego, None, 1, None, 2, DEV, g.num_graphs)

@@ -35,9 +35,10 @@ TOL_LOSS, TOL_EMUL = 2e-2, 2e-2
 GRAD_MEDIAN = 4e-2
 
 
-def _engine(m, L=4, hidden=64, dtype="bf16"):
+def _engine(m, L=4, dtype="bf16"):
     from scgib_b200.engine import PretrainEngine
-    eng = PretrainEngine(9, gin_layers=L, hidden=hidden, device=DEV, dtype=dtype)
+    from tests.helpers import hidden_of
+    eng = PretrainEngine(9, gin_layers=L, hidden=hidden_of(m), device=DEV, dtype=dtype)
     eng.load_state_dict({k: v.detach().float().to(DEV) for k, v in m.state_dict().items()}, strict=False)
     return eng
 
@@ -47,8 +48,8 @@ def _emulated(m, g, e, gate_u, feat_u):
     straight-through, so they see the forward's rounded activations and masks but not the backward kernels' own bf16
     rounding of the layer gradients)."""
     from oracle.scgib_oracle import normalize_rows, tgraph_from_ego, tgraph_from_ref
-    from tests.helpers import oracle_grads
-    m64 = OracleMainmodel(9, 64, 32, len(m.Encoder1.ginlayers)).double()
+    from tests.helpers import hidden_of, oracle_grads
+    m64 = OracleMainmodel(9, hidden_of(m), 32, len(m.Encoder1.ginlayers)).double()
     m64.load_state_dict({n: (v.double() if v.dtype.is_floating_point else v) for n, v in m.state_dict().items()})
     m64.Encoder1.emulate_bf16 = m64.Encoder2.emulate_bf16 = True
     x = normalize_rows(torch.from_numpy(g.x).double())
@@ -57,14 +58,14 @@ def _emulated(m, g, e, gate_u, feat_u):
     return out, oracle_grads(m64, out)
 
 
-def _check(seed, B, k, report=None):
+def _check(seed, B, k, report=None, hidden=64, shape="pcqm"):
     from scgib_b200.engine import DeviceBatch
     from scgib_b200.graph import khop_ego_batch
-    g = synth_batch(seed, B)
+    g = synth_batch(seed, B, shape)
     e = ego_batch_ref(g, k)
     torch.manual_seed(seed)
-    m = OracleMainmodel(9)
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, seed + 100)
+    m = OracleMainmodel(9, hidden)
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), hidden, seed + 100)
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
     emul_out, emul_grads = _emulated(m, g, e, gate_u, feat_u)
     eng = _engine(m)
@@ -90,12 +91,12 @@ def _check(seed, B, k, report=None):
             continue
         truth, emul = truth_grads[n].reshape(got.shape), emul_grads[n].reshape(got.shape)
         if n == "attn_layer.weight":
-            got, truth, emul = got[:, 64:], truth[:, 64:], emul[:, 64:]
+            got, truth, emul = got[:, hidden:], truth[:, hidden:], emul[:, hidden:]
         gerr[n], gerr_emul[n], ginh[n] = rel(got, truth), rel(got, emul), rel(emul, truth)
     median = lambda d: sorted(d.values())[len(d) // 2]
     med, med_emul, med_inh = median(gerr), median(gerr_emul), median(ginh)
     worst, worst_emul = max(gerr, key=gerr.get), max(gerr_emul, key=gerr_emul.get)
-    rep = dict(B=B, k=k, seed=seed, cuda_vs_fp64=errs, cuda_vs_bf16_emulation=errs_emul, bf16_emulation_vs_fp64=inherent,
+    rep = dict(B=B, k=k, seed=seed, hidden=hidden, shape=shape, cuda_vs_fp64=errs, cuda_vs_bf16_emulation=errs_emul, bf16_emulation_vs_fp64=inherent,
                grad_median_vs_fp64=med, grad_max_vs_fp64=gerr[worst], grad_worst=worst,
                grad_median_vs_bf16_emulation=med_emul, grad_max_vs_bf16_emulation=gerr_emul[worst_emul], grad_worst_vs_emulation=worst_emul,
                grad_median_bf16_emulation_vs_fp64=med_inh, grad_max_bf16_emulation_vs_fp64=max(ginh.values()))
@@ -103,7 +104,7 @@ def _check(seed, B, k, report=None):
         report.update(rep)
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_bf16")
     os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "b%d_k%d_s%d.json" % (B, k, seed)), "w") as fh:
+    with open(os.path.join(out, "h%d_%s_b%d_k%d_s%d.json" % (hidden, shape, B, k, seed)), "w") as fh:
         json.dump(rep, fh, indent=1)
     assert torch.isfinite(eng.grads).all()
     for name in errs:
@@ -129,6 +130,13 @@ def test_bf16_parity_small(seed, B, k):
 def test_bf16_parity_full_size(k):
     """B = 4096 (configs[1]); k = 2, 3 are configs[3]."""
     _check(20 + k, 4096, k)
+
+
+@pytest.mark.parametrize("seed,B,k,shape", [(31, 128, 1, "pcqm"), (32, 300, 2, "pcqm"), (33, 64, 1, "peptides"), (34, 1024, 1, "pcqm")])
+def test_bf16_parity_hidden128(seed, B, k, shape):
+    """--dims 128 (BASELINE configs[4] GIN-5x128) in bf16 mode: the same kernels instantiated at H = 128 (K = 128 GEMMs over two
+    64-column operand blocks, 128-column accumulators)."""
+    _check(seed, B, k, hidden=128, shape=shape)
 
 
 def test_bf16_deterministic_and_trains():

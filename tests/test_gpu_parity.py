@@ -131,10 +131,10 @@ def test_golden_reference_parity(path):
     BN running statistics."""
     fx = torch.load(path, weights_only=False)
     g, e = RefGraph(**fx["graph"]), RefEgoBatch(**fx["ego"])
-    k = fx["meta"]["k"]
-    m = OracleMainmodel(9, 64, 32, 4)
+    k, H = fx["meta"]["k"], int(fx["meta"].get("hidden", 64))
+    m = OracleMainmodel(9, H, 32, 4)
     m.load_state_dict(fx["state"], strict=False)
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), H, fx["meta"]["noise_seed"])
     logm = k if fx["meta"].get("recons_type", "adj") == "logM" else 0
     eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u, recon_logm_steps=logm)
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=logm)

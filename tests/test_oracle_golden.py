@@ -21,8 +21,12 @@ def load_fixture(path):
     return fx, g, e
 
 
+def hidden_of_fixture(fx):
+    return int(fx["meta"].get("hidden", 64))
+
+
 def oracle_from_fixture(fx, dtype=torch.float32):
-    m = OracleMainmodel(9, 64, 32, 4)
+    m = OracleMainmodel(9, hidden_of_fixture(fx), 32, 4)
     missing, unexpected = m.load_state_dict(fx["state"], strict=False)
     assert not unexpected
     m.train()
@@ -53,7 +57,7 @@ def test_oracle_forward_backward_matches_reference(path, flavour):
     tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
     x = normalize_rows(torch.from_numpy(g.x))
     ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), hidden_of_fixture(fx), fx["meta"]["noise_seed"])
     logm = fx["meta"]["k"] if fx["meta"].get("recons_type", "adj") == "logM" else 0
     if logm and flavour == "vectorised":
         pytest.skip("the vectorised flavour restates the adjacency reconstruction only")
@@ -79,8 +83,9 @@ def test_oracle_forward_backward_matches_reference(path, flavour):
             assert float(got.abs().max()) <= 1e-5 * gmax and float(gref.abs().max()) <= 1e-5 * gmax, n
             continue
         if n == "attn_layer.weight":
-            assert float(got[:, :64].abs().max()) <= 1e-5 * gmax and float(gref[:, :64].abs().max()) <= 1e-5 * gmax
-            got, gref = got[:, 64:], gref[:, 64:]
+            H = got.shape[1] // 2
+            assert float(got[:, :H].abs().max()) <= 1e-5 * gmax and float(gref[:, :H].abs().max()) <= 1e-5 * gmax
+            got, gref = got[:, H:], gref[:, H:]
         assert rel(got, gref) <= 50 * tol, (n, rel(got, gref))
     # BN running statistics after one training forward
     sd = m.state_dict()
@@ -111,8 +116,9 @@ FT_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fi
 
 def finetune_oracle_from_fixture(fx, dtype=torch.float32):
     from oracle.scgib_oracle import OracleFinetune
-    inner = OracleMainmodel(9, 64, 32, 4)
-    m = OracleFinetune(inner, 9, 64, 32, num_classes=fx["meta"]["num_classes"])
+    H = hidden_of_fixture(fx)
+    inner = OracleMainmodel(9, H, 32, 4)
+    m = OracleFinetune(inner, 9, H, 32, num_classes=fx["meta"]["num_classes"])
     missing, unexpected = m.load_state_dict(fx["state"], strict=False)
     assert not unexpected
     m.train()
@@ -128,7 +134,7 @@ def test_finetune_oracle_matches_reference(path):
     tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
     x = normalize_rows(torch.from_numpy(g.x))
     ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), hidden_of_fixture(fx), fx["meta"]["noise_seed"])
     out = m(tg, x, te, x[ego_nodes], gate_u, feat_u)
     assert rel(out["scores"], fx["out"]["scores"]) <= 2e-6
     loss = torch.nn.functional.binary_cross_entropy(out["scores"], fx["targets"]) / 2
@@ -137,7 +143,7 @@ def test_finetune_oracle_matches_reference(path):
     loss.backward()
     # evaluate_network: model.eval() forward right after the training forward (running statistics updated once)
     m.eval()
-    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"] + 1)
+    gu2, fu2 = draw_noise_like_reference(g.batch_num_nodes().tolist(), hidden_of_fixture(fx), fx["meta"]["noise_seed"] + 1)
     with torch.no_grad():
         ev = m(tg, x, te, x[ego_nodes], gu2, fu2)
     assert rel(ev["scores"], fx["out"]["scores_eval"]) <= 2e-6
@@ -169,7 +175,7 @@ def test_domainadapt_oracle_matches_reference(path):
     tg, te = tgraph_from_ref(g), tgraph_from_ego(e)
     x = normalize_rows(torch.from_numpy(g.x))
     ego_nodes = torch.from_numpy(e.ego_nodes.astype(np.int64))
-    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), 64, fx["meta"]["noise_seed"])
+    gate_u, feat_u = draw_noise_like_reference(g.batch_num_nodes().tolist(), hidden_of_fixture(fx), fx["meta"]["noise_seed"])
     out = m(tg, x, te, x[ego_nodes], gate_u, feat_u)
     assert abs(float(out["X_loss"]) - float(fx["out"]["X_loss"])) <= 2e-6 * abs(float(fx["out"]["X_loss"]))
     out["X_loss"].backward()
