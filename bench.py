@@ -145,14 +145,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's path restated loop-for-loop (oracle), forward + backward + Adam
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, batch=128, k=1):
+def cpu_reference_run(steps, warmup, batch=128, k=1, hidden=64):
     import numpy as np
     from oracle.graph_ref import ego_batch_ref, synth_batch
     from oracle.scgib_oracle import OracleMainmodel, normalize_rows, oracle_train_step, tgraph_from_ego, tgraph_from_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = OracleMainmodel(9)
+    model = OracleMainmodel(9, hidden)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-5)
     data = []
     for s in range(2):
@@ -177,7 +177,7 @@ def cpu_reference_run(steps, warmup, batch=128, k=1):
                       "recon, %.1f s wall" % (steps, batch, dt)}, dt / steps * 1e3
 
 
-def torch_gpu_reference_run(dev, k=1):
+def torch_gpu_reference_run(dev, k=1, hidden=64):
     """The "reference torch path on the same GPU" (north_star): the oracle's restatement of the reference run with plain
     torch on the B200 - `faithful` = what the reference really executes (per-graph Python loops, dense N x N recon) at its
     default batch 128; `vectorised` = a strong torch baseline the reference does not have (segment ops + Gram identity)
@@ -189,7 +189,7 @@ def torch_gpu_reference_run(dev, k=1):
     out = {}
     for name, B, steps in (("faithful_b128", 128, 10), ("vectorised_b4096", 4096, 20)):
         torch.manual_seed(0)
-        model = OracleMainmodel(9).to(dev)
+        model = OracleMainmodel(9, hidden).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-5)
         g = synth_batch_fast(100, B)
         e = ego_batch_ref(g, k)
@@ -203,7 +203,7 @@ def torch_gpu_reference_run(dev, k=1):
             if name.startswith("faithful"):
                 o = model.forward_faithful(tg, x, te, xs)
             else:
-                o = model.forward_vectorised(tg, x, te, en, torch.rand(x.shape[0], device=dev), torch.rand(x.shape[0], 64, device=dev))
+                o = model.forward_vectorised(tg, x, te, en, torch.rand(x.shape[0], device=dev), torch.rand(x.shape[0], hidden, device=dev))
             loss = o["KL"] + o["recon"] + o["contrastive"]
             loss.backward()
             opt.step()
@@ -229,7 +229,7 @@ def torch_gpu_reference_run(dev, k=1):
 def run_reference(args, rank, emit):
     if rank != 0:
         return
-    base, ms = cpu_reference_run(args.steps, args.warmup, batch=128, k=args.k)
+    base, ms = cpu_reference_run(args.steps, args.warmup, batch=128, k=args.k, hidden=args.dims)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -244,13 +244,13 @@ def run_reference(args, rank, emit):
 # ----------------------------------------------------------------------------------------------------
 # Secondary workload (BASELINE configs[4]): fine-tuning step of Mainmodel_finetuning
 # ----------------------------------------------------------------------------------------------------
-def cpu_finetune_run(shape, batch, k=1, budget_s=10.0):
+def cpu_finetune_run(shape, batch, k=1, budget_s=10.0, hidden=64):
     import numpy as np
     from oracle.graph_ref import ego_batch_ref, synth_batch
     from oracle.scgib_oracle import OracleFinetune, OracleMainmodel, normalize_rows, tgraph_from_ego, tgraph_from_ref
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    model = OracleFinetune(OracleMainmodel(9), 9, num_classes=10)
+    model = OracleFinetune(OracleMainmodel(9, hidden), 9, hidden, num_classes=10)
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     g = synth_batch(100, batch, shape)
     e = ego_batch_ref(g, k)
@@ -282,8 +282,9 @@ def run_finetune(args, emit):
     from scgib_b200.synth import synth_batch
     dev = torch.device("cuda", 0)
     lib = _lib.load()
-    eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)
-    head = FinetuneHead(64, 10, n_iters=2, sigmoid=True, device=dev)
+    H, es = args.dims, (2 if args.dtype == "bf16" else 4)
+    eng = PretrainEngine(9, gin_layers=4, hidden=H, device=dev, seed=0, dtype=args.dtype)
+    head = FinetuneHead(H, 10, n_iters=2, sigmoid=True, device=dev)
     head.params.copy_((torch.rand(head.total, generator=torch.Generator().manual_seed(1)) * 0.25 - 0.125).to(dev))
     hm, hv = torch.zeros_like(head.params), torch.zeros_like(head.params)
     B = args.batch
@@ -342,18 +343,30 @@ def run_finetune(args, emit):
     lib.scgib_profile_enable(0)
     b = state["b"]
     hbm, peak_src = peaks()
-    dom = max(prof, key=lambda k_: prof[k_][0])
-    V = b.N + b.Ns
-    abytes = V * 2 * (64 + 64) * 4 if dom.startswith("gin_bwd_main") else V * (64 + 64) * 4 + 4 * (V + 2 + b.E + b.Es)
-    achieved = abytes / (prof[dom][0] / prof[dom][1] * 1e-3) / 1e9
+    # roofline unit = ONE GIN layer of both encoders (layer average); a layer's backward = gin_bwd_pre + gin_bwd_main
+    fam = {}
+    for k_, v in prof.items():
+        f = "gin_bwd (pre + main)" if k_.startswith(("gin_bwd_pre", "gin_bwd_main")) else k_
+        cur = fam.setdefault(f, [0.0, []]); cur[0] += v[0]; cur[1].append(k_)
+    dom = max(fam, key=lambda k_: fam[k_][0])
+    V, D = b.N + b.Ns, b.E + b.Es
+    fwd_layer = sum(V * (di + H) * es + 4 * (V + 1 + D) for di in (32, H, H, H)) / 4.0
+    if dom.startswith("gin_bwd"):
+        abytes, unit_ms = 2.0 * fwd_layer, fam[dom][0] / 4.0
+    elif dom.startswith("gin_fwd"):
+        abytes, unit_ms = fwd_layer, fam[dom][0] / 4.0
+    else:
+        abytes, unit_ms = 3 * b.N * H * 4, prof[dom][0] / prof[dom][1]
+    achieved = abytes / (unit_ms * 1e-3) / 1e9
+    step_bytes = b.algorithmic_bytes(gin_layers=4, s=es, hidden=H) - 3 * (b.N * H * es + 4 * (b.N + 1 + b.E))   # no recon / contrastive in fine-tuning
     h2d = sum(t_.numel() * t_.element_size() for t_ in (host[0].graph_ptr, host[0].indptr, host[0].indices, host[0].ndata["x"]))
-    line = {"metric": "finetune graphs/s (%s-shape GIN-4x64 k=%d, Set2Set readout)" % (args.shape, args.k),
+    line = {"metric": "finetune graphs/s (%s-shape GIN-4x%d k=%d, Set2Set readout)" % (args.shape, H, args.k),
             "value": B * args.steps / (ms * 1e-3), "unit": "graphs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "Mainmodel_finetuning step (ego extraction + features fwd + Set2Set/predict head + BCE + bwd + Adam), "
-                                   "GIN-4x64 (reference default --dims 64; BASELINE configs[4] names 128: open), k=%d, batch %d %s-shape graphs"
-                                   % (args.k, B, args.shape),
+                                   "GIN-4x%d (--dims %d; BASELINE configs[4] = GIN-5x128 in the paper's layer count), k=%d, batch %d %s-shape graphs"
+                                   % (H, H, args.k, B, args.shape),
                        "nodes": b.N, "edges": b.E, "ego_rows": b.Ns, "ego_edges": b.Es,
                        "l2": "no flush: per-step working set exceeds the 126 MB L2"},
             "clocks": clocks,
@@ -361,10 +374,13 @@ def run_finetune(args, emit):
                     "d2h_bytes_per_step": B * 10 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": (nlaunch + 8) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes},
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_unit": abytes, "unit_ms": unit_ms,
+                         "members": fam[dom][1], "note": "unit = one GIN layer of both encoders (layer average); backward = pre + main"},
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                              "peak": hbm, "unit": "GB/s", "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm},
             "kernels": {k_: {"ms_per_step": v[0], "launches_per_step": v[1]} for k_, v in prof.items()}}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_finetune_run(args.shape, 32 if args.shape == "peptides" else 128, args.k)
+        line["cpu_baseline"] = cpu_finetune_run(args.shape, 32 if args.shape == "peptides" else 128, args.k, hidden=H)
     emit(line)
 
 
@@ -383,6 +399,7 @@ def main():
     ap.add_argument("--recons_type", default="adj", choices=["adj", "logM"],
                     help="adj = the reference default (the headline); logM = k-step log transition matrices (models.py:770-782)")
     ap.add_argument("--shape", default="pcqm", choices=["pcqm", "peptides"], help="synthetic molecule shape (finetune workload)")
+    ap.add_argument("--dims", type=int, default=64, choices=[64, 128], help="hidden width (--dims of the reference CLI); 128 = BASELINE configs[4]")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
                     help="fp32 = the headline (reference precision); bf16 = bf16 activations + single-pass bf16 tensor-core MLPs in the GIN encoders")
     args = ap.parse_args()
@@ -424,7 +441,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     bf16 = args.dtype == "bf16"
-    eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0, dtype=args.dtype)     # same seed on every rank: replicas start equal
+    H = args.dims
+    eng = PretrainEngine(9, gin_layers=4, hidden=H, device=dev, seed=0, dtype=args.dtype)     # same seed on every rank: replicas start equal
     eng._noise_gen.manual_seed(1234 + rank)
     if args.recons_type == "logM":
         eng.recon_logm_steps = args.k
@@ -532,7 +550,7 @@ def main():
         ns = types.SimpleNamespace(recons_type=args.recons_type, useAtt=1, readout_f="sum", d_transfer=32, device=str(dev),
                                    batch_size=args.batch, k_transition=args.k, dtype=args.dtype)
         torch.manual_seed(0)
-        dm = dropin_models.Mainmodel(ns, 9, 64, 4, 4, args.k, "GIN").to(dev)
+        dm = dropin_models.Mainmodel(ns, 9, H, 4, 4, args.k, "GIN").to(dev)
         dm.train()
         from exp_pretraining import make_optimizer
         dopt = make_optimizer(dm, 1e-4)          # what the drop-in exp_pretraining.py builds: Adam(lr, wd 5e-5) as one flat kernel
@@ -576,7 +594,7 @@ def main():
                     "ms_per_launch": v[0] / v[1]} for k_, v in prof.items()}
     b = eng.make_batch(resident[0], args.k)
     es = 2 if bf16 else 4                 # bytes per activation element of the GIN encoders
-    step_bytes = b.algorithmic_bytes(gin_layers=4, s=es)
+    step_bytes = b.algorithmic_bytes(gin_layers=4, s=es, hidden=H)
     hbm, peak_src = peaks()
     # A GIN layer's backward is TWO launches here (gin_bwd_pre + gin_bwd_main): they are one roofline unit, so that the
     # SURVEY 8(d) layer-backward budget (2 x the layer's forward bytes) is counted ONCE
@@ -590,16 +608,16 @@ def main():
     # algorithmic bytes of one layer of the dominant family (SURVEY.md 8d per-layer figures, both encoders' rows, averaged
     # over the 4 layers), and the time of that layer = the family's time per step / 4 layers
     V, D = b.N + b.Ns, b.E + b.Es
-    per_layer = [(32, 64), (64, 64), (64, 64), (64, 64)]
+    per_layer = [(32, H), (H, H), (H, H), (H, H)]
     fwd_layer = sum(V * (di + d) * es + 4 * (V + 1 + D) for di, d in per_layer) / 4.0
     if dom.startswith("gin_bwd"):
         abytes, unit_ms = 2.0 * fwd_layer, fam[dom]["ms_per_step"] / 4.0
     elif dom.startswith("gin_fwd"):
         abytes, unit_ms = fwd_layer, fam[dom]["ms_per_step"] / 4.0
     elif dom.startswith("contrastive"):
-        abytes, unit_ms = 4 * b.B * 64 * 4, kernels[dom]["ms_per_launch"]
+        abytes, unit_ms = 4 * b.B * H * 4, kernels[dom]["ms_per_launch"]
     else:
-        abytes, unit_ms = 3 * b.N * 64 * 4, kernels[dom]["ms_per_launch"]
+        abytes, unit_ms = 3 * b.N * H * 4, kernels[dom]["ms_per_launch"]
     achieved = abytes / (unit_ms * 1e-3) / 1e9
     traffic = None                       # dram__bytes_read + write per unit, from the ncu capture of THIS build (profiles/)
     try:
@@ -610,9 +628,9 @@ def main():
 
     # the HBM-bound aggregation / pooling / segment kernels (north_star: >= 60 % of HBM peak is the target): algorithmic
     # bytes per launch (SURVEY 8d per-unit figures x this batch's sizes) / CUDA-event time per launch
-    d4 = 64 * 4
+    d4 = H * 4
     hbm_alg = {
-        ("gin_bwd_pre_bf16.enc1+2" if bf16 else "gin_bwd_pre.enc1+2"): 3 * (b.N + b.Ns) * 64 * es + 4 * (b.N + b.Ns + 2 + b.E + b.Es),
+        ("gin_bwd_pre_bf16.enc1+2" if bf16 else "gin_bwd_pre.enc1+2"): 3 * (b.N + b.Ns) * H * es + 4 * (b.N + b.Ns + 2 + b.E + b.Es),
         "ego_pool_fwd": (b.Ns + b.N) * d4 + 4 * (b.N + 1) + 4 * b.N,
         "graph_gate_fwd": 4 * b.N * d4 + 12 * b.N,
         "recon_bwd": 2 * b.N * d4 + 4 * (b.N + 1 + b.E),
@@ -629,7 +647,7 @@ def main():
             "metric": METRIC, "value": graphs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
-            "config": {"workload": "S-CGIB pre-training step (ego extraction + fwd + bwd + grad all-reduce + Adam), GIN-4x64 "
+            "config": {"workload": "S-CGIB pre-training step (ego extraction + fwd + bwd + grad all-reduce + Adam), GIN-4x" + str(H) + " "
                                    "(= BASELINE's 'GIN-5x64': the published code's 5-layer GIN has 4 GINConv, SURVEY F4), "
                                    "k_transition=%d, batch %d synthetic PCQM4Mv2-shape graphs per GPU (BASELINE configs[1]%s)"
                                    % (args.k, args.batch, ", bf16 half: bf16 activations in the GIN encoders" if bf16 else ""),
@@ -665,8 +683,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             del eng, dm, dopt
             torch.cuda.empty_cache()
-            line["torch_gpu_baseline"] = torch_gpu_reference_run(dev, k=args.k)
-            line["cpu_baseline"], _ = cpu_reference_run(None, 3, batch=128, k=args.k)
+            line["torch_gpu_baseline"] = torch_gpu_reference_run(dev, k=args.k, hidden=H)
+            line["cpu_baseline"], _ = cpu_reference_run(None, 3, batch=128, k=args.k, hidden=H)
         emit(line)
     if world > 1:
         dist.barrier()

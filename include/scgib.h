@@ -313,6 +313,49 @@ SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int
 SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn,
                           float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-graph core gate, core-candidate attention, head MLP and the sum_nodes broadcast as individual operators:
+ * the units scgib_extract_forward/backward_f32 run fused.  hidden in {64, 128}.
+ *
+ *  scgib_core_gate_fwd/bwd_f32 : compress + compression (models.py:595-604, 631-660) on Hfeat = graph_features [N,H]
+ *      (the Encoder1 output): q = compressor.0(H), per-graph BatchNorm (compressor.1, training mode), p = compressor.3(relu),
+ *      lambda = sigmoid(logit(eps(gate_u)) + p), noisy = lambda H + (1 - lambda) mu_g + feat_u (1 - lambda) sigma_g,
+ *      graph_readout = sum_nodes(H), core_readout = sum_nodes(noisy), kl = KL of the LAST graph (models.py:657-659).
+ *      bwd: gradients of <g_noisy, noisy> + <g_core, core_readout> + <g_readout, graph_readout> + kl_scale * kl; call after
+ *      the forward with the same workspace (scgib_core_gate_workspace_bytes, 256-byte aligned).
+ *  scgib_core_cand_attn_fwd/bwd_f32 : the attention loop (models.py:738-748): alpha = per-graph softmax of
+ *      attn_layer([core || C_v]); the core half and the bias cancel in the softmax, so only w_cand = attn_layer.weight[0, H:]
+ *      enters (their gradients are exactly zero).  T = alpha C (optional).  bwd workspace: (N + B*hidden) floats + 256 bytes.
+ *  scgib_head_mlp_fwd/bwd_f32 : self.MLP(interaction_map) (models.py:569-572, 676) with interaction_map = [noisy || alpha C];
+ *      bwd returns gI as TWO dense halves [2][N][H] (gradient wrt noisy, then wrt alpha C) and the four parameter gradients.
+ *  scgib_segment_sum_bwd_f32 : backward of dgl.sum_nodes: g_in[row] = g_out[segment(row)].
+ * ------------------------------------------------------------------------------------------ */
+SCGIB_API size_t scgib_core_gate_workspace_bytes(int32_t hidden, int32_t B, int32_t N);
+SCGIB_API int scgib_core_gate_fwd_f32(const float* Hfeat, const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden,
+                                      const float* Wc1, const float* bc1, const float* gamma_c, const float* beta_c,
+                                      const float* wc2, const float* bc2, const float* gate_u, const float* feat_u,
+                                      float* noisy, float* lam, float* graph_readout, float* core_readout, float* kl,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_core_gate_bwd_f32(const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden, const float* Wc1,
+                                      const float* gamma_c, const float* beta_c, const float* wc2, const float* feat_u,
+                                      const float* g_noisy, const float* g_core, const float* g_readout, float kl_scale,
+                                      float* gH, float* dWc1, float* dbc1, float* dgamma_c, float* dbeta_c, float* dwc2,
+                                      float* dbc2, void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_core_cand_attn_fwd_f32(const float* C, const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden,
+                                           const float* w_cand, float* alpha, float* T, void* stream);
+SCGIB_API int scgib_core_cand_attn_bwd_f32(const float* C, const float* alpha, const float* gT, const int32_t* graph_ptr,
+                                           int32_t B, int32_t N, int32_t hidden, const float* w_cand, float* gC,
+                                           float* dw_cand, void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API size_t scgib_head_mlp_workspace_bytes(int32_t hidden, int32_t N);
+SCGIB_API int scgib_head_mlp_fwd_f32(const float* noisy, const float* C, const float* alpha, int32_t N, int32_t hidden,
+                                     const float* W1, const float* b1, const float* W2, const float* b2,
+                                     float* interaction_map, float* Z, void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_head_mlp_bwd_f32(const float* gZ, const float* noisy, int32_t N, int32_t hidden, const float* W1,
+                                     const float* W2, float* gI, float* dW1, float* db1, float* dW2, float* db2,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+SCGIB_API int scgib_segment_sum_bwd_f32(const float* g_out, const int32_t* seg_ptr, int32_t S, int32_t hidden, float* g_in,
+                                        void* stream);
+
 /* Debugging aid: byte offset of a named intermediate inside the pre-training workspace ("t", "H", "q", "C",
  * "alpha", "lam", "y<enc>_<layer>", "gH", ...), -1 if unknown.  Tests compare intermediates with the oracle. */
 SCGIB_API int64_t scgib_pretrain_workspace_offset(const ScgibDims* d, int32_t B, int32_t N, int32_t E, int32_t Ns,

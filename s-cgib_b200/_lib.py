@@ -90,6 +90,17 @@ _SIGNATURES = {
     "scgib_contrastive_f32": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "scgib_core_gate_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "scgib_core_gate_fwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32] + [c_void_p] * 13 + [c_void_p, c_size_t, c_void_p]),
+    "scgib_core_gate_bwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32] + [c_void_p] * 8 + [c_float] + [c_void_p] * 7 +
+                                [c_void_p, c_size_t, c_void_p]),
+    "scgib_core_cand_attn_fwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scgib_core_cand_attn_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scgib_head_mlp_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "scgib_head_mlp_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "scgib_head_mlp_bwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32] + [c_void_p] * 7 + [c_void_p, c_size_t, c_void_p]),
+    "scgib_segment_sum_bwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "scgib_profile_enable": (None, [c_int]),
     "scgib_profile_count": (c_int, []),
     "scgib_profile_get": (c_int, [c_int, POINTER(c_char_p), POINTER(c_float)]),
@@ -102,6 +113,7 @@ _PRIVATE_SIGNATURES = {
     "scgib_set_tensor_cores_bwd": (None, [c_int]),
     "scgib_debug_tc2_trace": (c_int, [c_void_p, c_int]),
     "scgib_debug_bwd_trace": (c_int, [c_void_p, c_int]),
+    "scgib_debug_bf16_trace": (c_int, [c_void_p, c_int]),
 }
 
 _lib = None

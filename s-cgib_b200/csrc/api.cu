@@ -51,6 +51,12 @@ static bool fwd_alternate() {
   return v == 1;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers).
@@ -475,7 +481,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
     }
     if (tc_bwd) {
-      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
+      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s, true));   // W1a / W1b come from head_bwd_prep
     } else {
       PROF("head_bwd_ffma.a", launch_gin_bwd_main(m[0], HID, HID, GP, s));
       PROF("head_bwd_ffma.b", launch_gin_bwd_main(m[1], HID, HID, GP, s));   // rewrites the (identical) dW2 / bias partials of .a
@@ -892,6 +898,241 @@ extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* s
   if (!in || !seg_ptr || !out) return SCGIB_E_NULL;
   if (S < 1) return SCGIB_E_RANGE;
   launch_segment_sum(in, seg_ptr, S, bn, out, HID, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- op-level entries: core gate, attention, head MLP
+namespace scgib {
+struct GateOpWs {
+  float *Hc, *q, *gstat, *lam, *alpha0, *logit0, *zeros, *gp, *g_q, *gC, *w1t, *bnid, *part, *ppart, *kl;
+  unsigned int* counters;
+  int64_t pstride;
+  size_t bytes;
+};
+static GateOpWs gate_op_carve(int H, int B, int N, void* base) {
+  GateOpWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  w.Hc = take((size_t)N * H); w.q = take((size_t)N * H); w.gstat = take((size_t)B * 4 * H); w.lam = take(N);
+  w.alpha0 = take(N); w.logit0 = take(N); w.zeros = take((size_t)N * H); w.gp = take(N); w.g_q = take((size_t)N * H);
+  w.gC = take((size_t)N * H); w.w1t = take((size_t)H * H); w.bnid = take(4 * H);
+  w.part = take((size_t)4 * num_sms() * 5 * H);
+  w.pstride = (int64_t)H * H + H;
+  w.ppart = take((size_t)num_sms() * w.pstride);
+  w.kl = take(4);
+  w.counters = (unsigned int*)take(64);
+  w.bytes = o;
+  return w;
+}
+static bool hidden_ok(int H) { return H == 64 || H == 128; }
+}  // namespace scgib
+
+extern "C" SCGIB_API size_t scgib_core_gate_workspace_bytes(int32_t hidden, int32_t B, int32_t N) {
+  if (!hidden_ok(hidden) || B < 1 || N < 2) return 0;
+  return gate_op_carve(hidden, B, N, nullptr).bytes;
+}
+
+extern "C" SCGIB_API int scgib_core_gate_fwd_f32(const float* Hfeat, const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden,
+                                       const float* Wc1, const float* bc1, const float* gamma_c, const float* beta_c,
+                                       const float* wc2, const float* bc2, const float* gate_u, const float* feat_u, float* noisy,
+                                       float* lam, float* graph_readout, float* core_readout, float* kl, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  if (!Hfeat || !graph_ptr || !Wc1 || !bc1 || !gamma_c || !beta_c || !wc2 || !bc2 || !gate_u || !feat_u || !noisy || !graph_readout ||
+      !core_readout || !workspace)
+    return SCGIB_E_NULL;
+  if (!hidden_ok(hidden)) return SCGIB_E_SHAPE;
+  if (B < 1 || N < 2) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) || ((uintptr_t)Hfeat & 15u) || ((uintptr_t)feat_u & 15u) || ((uintptr_t)noisy & 15u)) return SCGIB_E_ALIGN;
+  const GateOpWs w = gate_op_carve(hidden, B, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int H = hidden;
+  TransposeJobs jobs;
+  jobs.n = 1;
+  jobs.job[0] = TransposeJob{Wc1, w.w1t, H, H};
+  launch_transposes(jobs, s);
+  // identity BatchNorm in front of the linear layer: Hfeat is already relu(BN(y)) >= 0, so relu(1 * (H - 0) * 1 + 0) = H
+  launch_identity_bn(w.bnid, H, s);
+  cudaMemsetAsync(w.logit0, 0, (size_t)N * sizeof(float), s);
+  GateLinFwdArgs g{Hfeat, w.bnid, N, w.w1t, bc1, w.Hc, w.q, false};
+  launch_gate_lin_fwd(g, H, s);
+  GraphGateFwdArgs a;
+  a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = w.Hc; a.q = w.q;
+  a.gamma_c = gamma_c; a.beta_c = beta_c; a.wc2 = wc2; a.bc2 = bc2; a.gate_u = gate_u; a.feat_u = feat_u; a.logit = w.logit0;
+  a.noisy = noisy; a.lam = w.lam; a.alpha = w.alpha0; a.readout = graph_readout; a.core = core_readout; a.gstat = w.gstat;
+  a.eval_running = nullptr; a.cstat = nullptr; a.kl = w.kl;
+  launch_graph_gate_fwd(a, H, s);
+  if (lam) cudaMemcpyAsync(lam, w.lam, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (kl) cudaMemcpyAsync(kl, w.kl, sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_core_gate_bwd_f32(const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden, const float* Wc1,
+                                       const float* gamma_c, const float* beta_c, const float* wc2, const float* feat_u,
+                                       const float* g_noisy, const float* g_core, const float* g_readout, float kl_scale,
+                                       float* gH, float* dWc1, float* dbc1, float* dgamma_c, float* dbeta_c, float* dwc2, float* dbc2,
+                                       void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!graph_ptr || !Wc1 || !gamma_c || !beta_c || !wc2 || !feat_u || !g_noisy || !g_core || !g_readout || !gH || !dWc1 || !dbc1 ||
+      !dgamma_c || !dbeta_c || !dwc2 || !dbc2 || !workspace)
+    return SCGIB_E_NULL;
+  if (!hidden_ok(hidden)) return SCGIB_E_SHAPE;
+  if (B < 1 || N < 2) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) || ((uintptr_t)g_noisy & 15u) || ((uintptr_t)gH & 15u)) return SCGIB_E_ALIGN;
+  const GateOpWs w = gate_op_carve(hidden, B, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int H = hidden, GP = num_sms();
+  cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
+  cudaMemsetAsync(w.zeros, 0, (size_t)N * H * sizeof(float), s);
+  cudaMemsetAsync(w.alpha0, 0, (size_t)N * sizeof(float), s);
+  GraphGateBwdArgs a;
+  a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = w.Hc; a.q = w.q; a.C = w.zeros;
+  a.gamma_c = gamma_c; a.beta_c = beta_c; a.wc2 = wc2; a.w_cand = w.zeros;     // no attention branch: zero candidates / weights
+  a.feat_u = feat_u; a.lam = w.lam; a.alpha = w.alpha0; a.gstat = w.gstat;
+  a.gI = g_noisy; a.gI2 = w.zeros; a.gI_stride = H; a.g_core = g_core; a.g_readout = g_readout; a.kl_scale = kl_scale;
+  a.gp = w.gp; a.g_q = w.g_q; a.gH = gH; a.gC = w.gC; a.part = w.part; a.counter = w.counters + 1;
+  a.d_gamma_c = dgamma_c; a.d_beta_c = dbeta_c; a.d_wc2 = dwc2; a.d_bc2 = dbc2;
+  a.d_attn_w = w.bnid; a.d_attn_b = w.kl + 1;                                   // discarded (the attention weights are not part of this op)
+  launch_graph_gate_bwd(a, H, s);
+  GateLinBwdArgs g{w.g_q, w.Hc, N, Wc1, gH, w.ppart, w.pstride, 0, (int64_t)H * H};
+  launch_gate_lin_bwd(g, H, GP, s);
+  float* outs[2] = {dWc1, dbc1};
+  const int64_t offs[2] = {0, (int64_t)H * H}, lens[2] = {(int64_t)H * H, H};
+  for (int i = 0; i < 2; ++i) {
+    ReduceRanges rr;
+    rr.n = 1; rr.off[0] = offs[i]; rr.len[0] = lens[i]; rr.c0[0] = 0; rr.c1[0] = GP;
+    launch_reduce_partials(w.ppart, w.pstride, GP, rr, outs[i] - offs[i], s);
+  }
+  return (int)cudaGetLastError();
+}
+
+// core-candidate attention (models.py:738-748): alpha = softmax_g(w_cand . C_v), T = alpha C.  The core half of attn_layer
+// and its bias cancel in the per-graph softmax (their gradients are exactly zero), so only w_cand = attn_layer.weight[0, H:] enters.
+extern "C" SCGIB_API int scgib_core_cand_attn_fwd_f32(const float* C, const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden,
+                                            const float* w_cand, float* alpha, float* T, void* stream) {
+  if (!C || !graph_ptr || !w_cand || !alpha) return SCGIB_E_NULL;
+  if (hidden < 1 || (hidden & 3)) return SCGIB_E_SHAPE;
+  if (B < 1 || N < 1) return SCGIB_E_RANGE;
+  launch_attn_fwd(C, graph_ptr, B, hidden, w_cand, alpha, T, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+// workspace: (N + B * hidden) floats, 256-byte aligned
+extern "C" SCGIB_API int scgib_core_cand_attn_bwd_f32(const float* C, const float* alpha, const float* gT, const int32_t* graph_ptr, int32_t B,
+                                            int32_t N, int32_t hidden, const float* w_cand, float* gC, float* dw_cand, void* workspace,
+                                            size_t workspace_bytes, void* stream_) {
+  if (!C || !alpha || !gT || !graph_ptr || !w_cand || !gC || !dw_cand || !workspace) return SCGIB_E_NULL;
+  if (hidden < 1 || (hidden & 3)) return SCGIB_E_SHAPE;
+  if (B < 1 || N < 1) return SCGIB_E_RANGE;
+  if (workspace_bytes < ((size_t)N + (size_t)B * hidden) * sizeof(float) + 256) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  float* scratch = (float*)workspace;
+  float* dwp = (float*)((char*)workspace + al((size_t)N * sizeof(float)));
+  launch_attn_bwd(C, alpha, gT, graph_ptr, B, hidden, w_cand, gC, dwp, scratch, s);
+  launch_colsum_rows(dwp, B, hidden, dw_cand, s);
+  return (int)cudaGetLastError();
+}
+
+extern "C" SCGIB_API int scgib_segment_sum_bwd_f32(const float* g_out, const int32_t* seg_ptr, int32_t S, int32_t hidden, float* g_in,
+                                         void* stream) {
+  if (!g_out || !seg_ptr || !g_in) return SCGIB_E_NULL;
+  if (hidden < 4 || (hidden & 3)) return SCGIB_E_SHAPE;
+  if (S < 1) return SCGIB_E_RANGE;
+  launch_segment_sum_bwd(g_out, seg_ptr, S, hidden, g_in, (cudaStream_t)stream);
+  return (int)cudaGetLastError();
+}
+
+// head MLP (models.py:569-572, 676): Z = W2 relu(W1 [noisy || alpha C] + b1) + b2
+namespace scgib {
+struct HeadOpWs { float *w1t, *w2t, *aC, *r, *Zc, *w1a, *w1b, *bnid, *cvec, *ppart; int64_t off[4], pstride; size_t bytes; };
+static HeadOpWs head_op_carve(int H, int N, void* base) {
+  HeadOpWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
+  w.w1t = take((size_t)2 * H * H); w.w2t = take((size_t)H * H); w.aC = take((size_t)N * H); w.r = take((size_t)N * H);
+  w.Zc = take((size_t)N * H); w.w1a = take((size_t)H * H); w.w1b = take((size_t)H * H); w.bnid = take(4 * H); w.cvec = take(2 * H);
+  w.off[0] = 0; w.off[1] = (int64_t)2 * H * H; w.off[2] = w.off[1] + H; w.off[3] = w.off[2] + (int64_t)H * H;   // W1 b1 W2 b2
+  w.pstride = w.off[3] + H;
+  w.ppart = take((size_t)num_sms() * w.pstride);
+  w.bytes = o;
+  return w;
+}
+}  // namespace scgib
+
+extern "C" SCGIB_API size_t scgib_head_mlp_workspace_bytes(int32_t hidden, int32_t N) {
+  if (!hidden_ok(hidden) || N < 1) return 0;
+  return head_op_carve(hidden, N, nullptr).bytes;
+}
+
+extern "C" SCGIB_API int scgib_head_mlp_fwd_f32(const float* noisy, const float* C, const float* alpha, int32_t N, int32_t hidden,
+                                      const float* W1, const float* b1, const float* W2, const float* b2, float* interaction_map,
+                                      float* Z, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!noisy || !C || !alpha || !W1 || !b1 || !W2 || !b2 || !Z || !workspace) return SCGIB_E_NULL;
+  if (!hidden_ok(hidden)) return SCGIB_E_SHAPE;
+  if (N < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) || ((uintptr_t)noisy & 15u) || ((uintptr_t)C & 15u) || ((uintptr_t)Z & 15u)) return SCGIB_E_ALIGN;
+  const HeadOpWs w = head_op_carve(hidden, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int H = hidden;
+  TransposeJobs jobs;
+  jobs.n = 2;
+  jobs.job[0] = TransposeJob{W1, w.w1t, H, 2 * H};
+  jobs.job[1] = TransposeJob{W2, w.w2t, H, H};
+  launch_transposes(jobs, s);
+  HeadFwdArgs a{noisy, C, alpha, N, w.w1t, b1, w.w2t, b2, interaction_map, w.aC, w.r, w.Zc};
+  launch_head_fwd(a, H, s);
+  cudaMemcpyAsync(Z, w.Zc, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return (int)cudaGetLastError();
+}
+
+// gI [N, 2H] = d<gZ, Z>/d interaction_map (first half: noisy, second half: alpha C); call after the forward with the same workspace
+extern "C" SCGIB_API int scgib_head_mlp_bwd_f32(const float* gZ, const float* noisy, int32_t N, int32_t hidden, const float* W1,
+                                      const float* W2, float* gI, float* dW1, float* db1, float* dW2, float* db2, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
+  if (!gZ || !noisy || !W1 || !W2 || !gI || !dW1 || !db1 || !dW2 || !db2 || !workspace) return SCGIB_E_NULL;
+  if (!hidden_ok(hidden)) return SCGIB_E_SHAPE;
+  if (N < 1) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) || ((uintptr_t)gZ & 15u) || ((uintptr_t)gI & 15u)) return SCGIB_E_ALIGN;
+  const HeadOpWs w = head_op_carve(hidden, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int H = hidden, GP = num_sms();
+  const bool tc = H == 64 && bwd_tensor_core_mode() != 0;
+  launch_head_bwd_prep(W1, w.w1a, w.w1b, w.bnid, w.cvec, H, s);
+  // the GIN backward kernel on the two K = H halves of the first layer (identity BatchNorm backward: g_y = gZ; its `y` operand
+  // only enters multiplied by zero).  gI is returned as two dense halves [2][N][H]: gradient wrt noisy, then wrt alpha C.
+  GinBwdMainArgs m[2];
+  for (int h = 0; h < 2; ++h) {
+    m[h].g_o = gZ; m[h].y = gZ; m[h].r = w.r; m[h].a = h == 0 ? noisy : w.aC;
+    m[h].bn = w.bnid; m[h].cvec = w.cvec; m[h].W1 = h == 0 ? w.w1a : w.w1b; m[h].W2 = W2; m[h].V = N;
+    m[h].g_a = gI + (size_t)h * N * H;
+    m[h].part = w.ppart; m[h].pstride = w.pstride;
+    m[h].off_W1 = w.off[0] + (int64_t)h * H * H; m[h].off_b1 = w.off[1]; m[h].off_W2 = w.off[2]; m[h].off_b2 = w.off[3];
+  }
+  int split = GP;
+  if (tc) {
+    launch_gin_bwd_main_tc2_pair(m[0], m[1], H, GP, s, true);
+    split = pair_split(GP, (N + 127) / 128, (N + 127) / 128);
+  } else {
+    launch_gin_bwd_main(m[0], H, H, GP, s);
+    launch_gin_bwd_main(m[1], H, H, GP, s);
+  }
+  ReduceRanges rr;
+  rr.n = 0;
+  auto add = [&](int64_t off, int64_t len, int c0, int c1) { rr.off[rr.n] = off; rr.len[rr.n] = len; rr.c0[rr.n] = c0; rr.c1[rr.n] = c1; ++rr.n; };
+  add(w.off[0], (int64_t)H * H, 0, split);
+  add(w.off[0] + (int64_t)H * H, (int64_t)H * H, tc ? split : 0, GP);
+  launch_reduce_partials(w.ppart, w.pstride, GP, rr, dW1 - w.off[0], s);
+  launch_head_dw1_interleave(dW1, H, s);
+  float* outs[3] = {db1, dW2, db2};
+  const int64_t lens[3] = {H, (int64_t)H * H, H};
+  for (int i = 0; i < 3; ++i) {
+    ReduceRanges r1;
+    r1.n = 1; r1.off[0] = w.off[i + 1]; r1.len[0] = lens[i]; r1.c0[0] = 0; r1.c1[0] = split;
+    launch_reduce_partials(w.ppart, w.pstride, GP, r1, outs[i] - w.off[i + 1], s);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -11,6 +11,15 @@ constexpr int kThreads = 256;  // CTA size of every tile kernel
 constexpr float kBnEps = 1e-5f;
 typedef uint16_t bf16_t;       // raw bfloat16 storage (bf16 mode: activations of the GIN encoders)
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_k() below may be scheduled while its predecessor in
+// the stream is still running; it must not touch anything the predecessor writes before pdl_wait() returns (the
+// predecessor grid has then completed and its memory is visible).  pdl_trigger() lets the NEXT kernel in the stream be
+// scheduled; it is always issued after this kernel's own pdl_wait(), so a kernel's pre-wait section only ever overlaps its
+// immediate predecessor.  Without a programmatic dependency both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -328,6 +337,19 @@ __device__ __forceinline__ void load_row_tile(float* __restrict__ dst, int ld, c
     if (v < V) val = ld4(src + (size_t)v * COLS + c);
     st4(dst + r * ld + c, val);
   }
+}
+
+// Host side: launch with the programmatic-stream-serialization attribute (SCGIB_PDL=0 disables: plain stream order)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 }  // namespace scgib

@@ -39,6 +39,7 @@ __device__ __forceinline__ void cp_async_tile_g(unsigned char* dst, const float*
 
 __global__ void __launch_bounds__(kThreads, 1)
 contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* zi_hi = smem + ConTcLayout::off_zi;
   unsigned char* zi_lo = zi_hi + ZI_BYTES;
@@ -178,6 +179,7 @@ __device__ __forceinline__ void cp_async_tile_s(unsigned char* dst, const float*
 
 __global__ void __launch_bounds__(kThreads, 1)
 contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit) {
+  pdl_sync();
   using L = ConBwdTcLayout;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* zi_hi = smem + L::off_zi;
@@ -366,7 +368,7 @@ void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s) {
                                            ConTcLayout::total), true);
   (void)once;
   dim3 grid((a.B + CI - 1) / CI, a.jsplit);
-  contrastive_fwd_tc_kernel<<<grid, kThreads, ConTcLayout::total, s>>>(a);
+  launch_k((contrastive_fwd_tc_kernel), dim3(grid), dim3(kThreads), ConTcLayout::total, s, a);
 }
 
 void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s) {
@@ -374,7 +376,7 @@ void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit,
                                            ConBwdTcLayout::total), true);
   (void)once;
   dim3 grid((a.B + CI - 1) / CI, a.jsplit);
-  contrastive_bwd_tc_kernel<<<grid, kThreads, ConBwdTcLayout::total, s>>>(a, zsplit);
+  launch_k((contrastive_bwd_tc_kernel), dim3(grid), dim3(kThreads), ConBwdTcLayout::total, s, a, zsplit);
 }
 
 }  // namespace scgib

@@ -20,6 +20,10 @@
 namespace scgib {
 using namespace umma;
 
+// per-tile role timestamps (SCGIB_DBG bit 1024; experiments only, tests/gpu_tc2_trace.py)
+__device__ long long g_bf16_trace[160 * 16 * 12];
+#define BF_TRACE(ev, tile) do { if ((p.dbg & 1024) && (tile) < 16 && blockIdx.x < 160) g_bf16_trace[((size_t)blockIdx.x * 16 + (tile)) * 12 + (ev)] = clock64(); } while (0)
+
 namespace bf {
 constexpr int TM = 128;                       // rows per tile = UMMA M
 constexpr int kEpiWarps = 8;
@@ -146,6 +150,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 4 * H);
   stage_weight<H, KIN>(smem + L::off_w1, p.W1, threadIdx.x, kThreadsF);
   stage_weight<H, H>(smem + L::off_w2, p.W2, threadIdx.x, kThreadsF);
+  pdl_sync();      // everything above reads parameters only; from here on: the previous kernel's outputs (bn_in, activations)
   if (threadIdx.x < H) {
     const int c = threadIdx.x;
     s_b1[c] = p.b1[c]; s_b2[c] = p.b2[c];
@@ -219,10 +224,12 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
     for (int i = 0; i < my_tiles; ++i) {
       const int s = i & 1, use = i >> 1, buf = i % kIdxBufs;
       const int base = tile_base(i), ws = win_start(i);
+      if (pt == 0) BF_TRACE(0, i);
       // [1] indices of tile i+1 and the window of tile i have landed
       cp_async_wait_all();
       mbar_wait(&bars[B_RAW + s], (uint32_t)(use & 1));
       prod_sync();
+      if (pt == 0) BF_TRACE(1, i);
       // [2] one tile ahead: window of tile i+1 (its stage is free once GEMM1 of tile i-1 has read it), indices of tile i+2
       if (i + 1 < my_tiles) {
         if (i >= 1) mbar_wait(&bars[B_EMPTY_A + (s ^ 1)], (uint32_t)(((i - 1) >> 1) & 1));
@@ -231,6 +238,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       if (i + 2 < my_tiles) stage_indices(i + 2, nb_begin, nb_end);
       cp_async_commit();
       if (i + 3 < my_tiles) bounds(i + 3, nb_begin, nb_end);
+      if (pt == 0) BF_TRACE(2, i);
       // [3] a_v = f(h_v) + sum_u f(h_u), neighbours in CSR order, out of the raw window (fp32 accumulation)
       const int* ip = s_ip + buf * (TM + 4);
       const int* ix = s_ix + buf * L::kIdxCap;
@@ -268,6 +276,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       }
       // [4] every producer has finished reading the raw window: overwrite the stage with the bf16 operand tile
       prod_sync();
+      if (pt == 0) BF_TRACE(3, i);
       unsigned char* At = smem + L::off_stage + s * L::kStage;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
@@ -282,6 +291,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       fence_smem_to_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_FULL_A + s]);
+      if (pt == 0) BF_TRACE(4, i);
     }
     cp_async_wait_all();
   } else if (warp == kMmaWarp) {
@@ -291,6 +301,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       const int s = i & 1, use = i >> 1;
       mbar_wait(&bars[B_FULL_A + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (lane == 0) BF_TRACE(5, i);
       const uint32_t at = smem_u32(smem + L::off_stage + s * L::kStage);
       const uint32_t d = tmem + s * 2 * H;
 #pragma unroll
@@ -303,6 +314,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       const int s = i & 1, use = i >> 1;
       mbar_wait(&bars[B_R + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (lane == 0) BF_TRACE(6, i);
       const uint32_t d = tmem + s * 2 * H + H;
       const uint32_t rb = tmem + s * 2 * H;
 #pragma unroll
@@ -328,6 +340,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       const int gv = tile_base(i) + row;
       mbar_wait(&bars[B_D1 + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) BF_TRACE(7, i);
       const uint32_t t0 = tmem + s * 2 * H + tl;
       uint32_t pk[CH][16];
 #pragma unroll
@@ -354,6 +367,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       tmem_st_wait();
       fence_before_sync();
       mbar_arrive(&bars[B_R + s]);
+      if (threadIdx.x == 0) BF_TRACE(8, i);
     };
     auto epi2 = [&](int i) {
       const int s = i & 1, use = i >> 1;
@@ -363,6 +377,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       const int cnt = max(0, min(32, p.V - (base + q * 32)));
       mbar_wait(&bars[B_D2 + s], (uint32_t)(use & 1));
       fence_after_sync();
+      if (threadIdx.x == 0) BF_TRACE(9, i);
       double nt = run_n;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -401,6 +416,7 @@ gin_fwd_bf16_kernel(GinFwdPair pp) {
       }
       run_n = nt;
       fence_before_sync();
+      if (threadIdx.x == 0) BF_TRACE(10, i);
     };
     if (my_tiles > 0) epi1(0);
     for (int i = 0; i < my_tiles; ++i) {
@@ -501,8 +517,14 @@ static void launch_fwd_bf16(const GinFwdPair& pp, int grid, cudaStream_t s) {
   constexpr int PW = 16;
   static bool once = (cudaFuncSetAttribute(bf::gin_fwd_bf16_kernel<KIN, H, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  bf::gin_fwd_bf16_kernel<KIN, H, PW><<<grid, (bf::kEpiWarps + 1 + PW) * 32, L::total, s>>>(pp);
+  launch_k((bf::gin_fwd_bf16_kernel<KIN, H, PW>), dim3(grid), dim3((bf::kEpiWarps + 1 + PW) * 32), L::total, s, pp);
 }
+
+}  // namespace scgib
+extern "C" __attribute__((visibility("default"))) int scgib_debug_bf16_trace(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, scgib::g_bf16_trace, (size_t)n * sizeof(long long));
+}
+namespace scgib {
 
 size_t gin_fwd_bf16_part_floats(int hidden) { return (size_t)num_sms() * 3 * hidden * 2; }   // per-CTA (n, mean, M2) in fp64
 
@@ -513,6 +535,9 @@ void launch_gin_fwd_bf16(const GinFwdArgs& a0, const GinFwdArgs* a1, int kin, in
   const int t0 = (a0.V + bf::TM - 1) / bf::TM, t1 = a1 ? (a1->V + bf::TM - 1) / bf::TM : 0;
   const int grid = min(t0 + t1, num_sms());
   pp.split = a1 ? pair_split(grid, t0, t1) : grid;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("SCGIB_DBG"); dbg = e ? atoi(e) : 0; }
+  pp.a[0].dbg = pp.a[1].dbg = dbg;
   if (hidden == 64) {
     if (kin == DTR) launch_fwd_bf16<DTR, 64>(pp, grid, s); else launch_fwd_bf16<64, 64>(pp, grid, s);
   } else {

@@ -36,6 +36,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 template <int H>
 __global__ void __launch_bounds__(kThreads, 2)
 gin_bwd_pre_bf16_kernel(GinBwdPrePair pp) {
+  pdl_sync();
   const bool second = (int)blockIdx.x >= pp.split;
   const GinBwdPreArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;
@@ -265,6 +266,7 @@ gin_bwd_bf16_kernel(GinBwdMainPair pp) {
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
   stage_weight<H, H, H>(smem + L::off_w2, p.W2, threadIdx.x, kThreadsB);
   stage_weight<H, KIN, KP>(smem + L::off_w1, p.W1, threadIdx.x, kThreadsB);
+  pdl_sync();      // the weights above are parameters; bn / cvec / g_o / y / r / a below come from the previous kernels
   fence_smem_to_async();
   fence_before_sync();
   __syncthreads();
@@ -541,8 +543,8 @@ void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, i
   pp.a[0] = a0; pp.a[1] = a1 ? *a1 : a0;
   const int grid = max(a1 ? 2 : 1, gin_bwd_pre_bf16_grid(a0.V + (a1 ? a1->V : 0), hidden));
   pp.split = a1 ? pair_split(grid, a0.V, a1->V) : grid;
-  if (hidden == 64) bfb::gin_bwd_pre_bf16_kernel<64><<<grid, kThreads, 0, s>>>(pp);
-  else bfb::gin_bwd_pre_bf16_kernel<128><<<grid, kThreads, 0, s>>>(pp);
+  if (hidden == 64) launch_k((bfb::gin_bwd_pre_bf16_kernel<64>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else launch_k((bfb::gin_bwd_pre_bf16_kernel<128>), dim3(grid), dim3(kThreads), 0, s, pp);
 }
 
 template <int KIN, int H, bool GA_F32>
@@ -550,7 +552,7 @@ static void launch_bwd_bf16_t(const GinBwdMainPair& pp, int grid, cudaStream_t s
   using L = bfb::BwdSmem<KIN, H>;
   static bool once = (cudaFuncSetAttribute(bfb::gin_bwd_bf16_kernel<KIN, H, GA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  bfb::gin_bwd_bf16_kernel<KIN, H, GA_F32><<<grid, bfb::kThreadsB, L::total, s>>>(pp);
+  launch_k((bfb::gin_bwd_bf16_kernel<KIN, H, GA_F32>), dim3(grid), dim3(bfb::kThreadsB), L::total, s, pp);
 }
 
 // CTAs [0, split) write the partial gradients of a0, [split, grid) of a1 (a1 == nullptr: one problem).  g_o / y / r / a are

@@ -101,6 +101,7 @@ gin_bwd_tc2_kernel(GinBwdMainPair pp) {
     mbar_init(&bars[B_E2], kEpiWarps * 32);
   }
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
+  if (pp.wait_first) pdl_sync();
   // transposed weights, hi/lo split: W2t[in][out] = W2[out][in], W1t[kin][out] = W1[out][kin]  (K-major B operands)
   for (int i = threadIdx.x; i < HID * HID; i += kThreadsB) {
     const int o = i / HID, c = i % HID;                       // coalesced read of W2[o][c]
@@ -116,6 +117,7 @@ gin_bwd_tc2_kernel(GinBwdMainPair pp) {
     *reinterpret_cast<float*>(smem + L::off_w1 + off) = hi;
     *reinterpret_cast<float*>(smem + L::off_w1 + L::W1B + off) = lo;
   }
+  if (!pp.wait_first) pdl_sync();   // the weights above are parameters; bn / cvec / g_o / y / r / a below come from the previous kernels
   fence_smem_to_async();
   fence_before_sync();
   __syncthreads();
@@ -424,7 +426,7 @@ static void launch_bwd2(const GinBwdMainPair& pp, int grid, cudaStream_t s) {
   using L = bwd2::Smem<KIN>;
   static bool once = (cudaFuncSetAttribute(bwd2::gin_bwd_tc2_kernel<KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  bwd2::gin_bwd_tc2_kernel<KIN><<<grid, bwd2::kThreadsB, L::total, s>>>(pp);
+  launch_k((bwd2::gin_bwd_tc2_kernel<KIN>), dim3(grid), dim3(bwd2::kThreadsB), L::total, s, pp);
 }
 
 }  // namespace scgib
@@ -449,9 +451,11 @@ void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStr
 
 // the same layer of both encoders in one launch: CTAs [0, split) write the partial gradients of a0, [split, grid) of a1
 // (split as computed by pair_split on 128-row tile counts: api.cu uses the same rule for the partial-sum ranges)
-void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s) {
+void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s,
+                                  bool weights_from_prev_kernel) {
   GinBwdMainPair pp;
   pp.a[0] = a0; pp.a[1] = a1;
+  pp.wait_first = weights_from_prev_kernel ? 1 : 0;
   pp.split = pair_split(grid, (a0.V + 127) / 128, (a1.V + 127) / 128);
   pp.trace = bwd2_trace_flag();
   static int rev = -1;

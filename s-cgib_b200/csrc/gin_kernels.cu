@@ -21,6 +21,7 @@ template <bool OUT_BF16>
 __global__ void __launch_bounds__(kThreads)
 input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt, int N, int F, int normalize,
                       float* __restrict__ t) {
+  pdl_sync();
   __shared__ __align__(16) float s_w[32 * DTR];  // [f][o]
   for (int i = threadIdx.x; i < F * DTR; i += kThreads) {
     const int o = i / F, f = i % F;
@@ -46,22 +47,24 @@ input_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
 // out_bf16: t is bf16 storage (bf16 mode: the layer-0 input of the GIN encoders)
 void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s, bool out_bf16) {
   const int grid = min((N + 31) / 32, 148 * 8);
-  if (out_bf16) input_proj_fwd_kernel<true><<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
-  else input_proj_fwd_kernel<false><<<grid, kThreads, 0, s>>>(x, Wt, N, F, normalize, t);
+  if (out_bf16) launch_k((input_proj_fwd_kernel<true>), dim3(grid), dim3(kThreads), 0, s, x, Wt, N, F, normalize, t);
+  else launch_k((input_proj_fwd_kernel<false>), dim3(grid), dim3(kThreads), 0, s, x, Wt, N, F, normalize, t);
 }
 
 __global__ void __launch_bounds__(kThreads) f32_to_bf16_kernel(const float* __restrict__ in, bf16_t* __restrict__ out, size_t n4) {
+  pdl_sync();
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads)
     st4a<true>(reinterpret_cast<float*>(out), 4 * i, ld4(in + 4 * i));
 }
 void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) {   // n multiple of 4
   const size_t n4 = n / 4;
   const int grid = (int)min((size_t)(4 * num_sms()), (n4 + kThreads - 1) / kThreads);
-  if (n4 > 0) f32_to_bf16_kernel<<<grid, kThreads, 0, s>>>(in, reinterpret_cast<bf16_t*>(out), n4);
+  if (n4 > 0) launch_k((f32_to_bf16_kernel), dim3(grid), dim3(kThreads), 0, s, in, reinterpret_cast<bf16_t*>(out), n4);
 }
 
 __global__ void bn_from_running_kernel(const float* __restrict__ running, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float* __restrict__ bn, int HID) {
+  pdl_sync();
   const int c = threadIdx.x;
   if (c >= HID) return;
   bn[c] = running[c];
@@ -70,13 +73,14 @@ __global__ void bn_from_running_kernel(const float* __restrict__ running, const 
   bn[3 * HID + c] = beta[c];
 }
 void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, int hidden, cudaStream_t s) {
-  bn_from_running_kernel<<<1, hidden, 0, s>>>(running, gamma, beta, bn, hidden);
+  launch_k((bn_from_running_kernel), dim3(1), dim3(hidden), 0, s, running, gamma, beta, bn, hidden);
 }
 
 // ------------------------------------------------------------------------------------------------
 // batched transposes of small weight matrices (forward kernels want k-major copies)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) transpose_many_kernel(TransposeJobs jobs) {
+  pdl_sync();
   const TransposeJob j = jobs.job[blockIdx.x];
   for (int i = threadIdx.x; i < j.rows * j.cols; i += kThreads) {
     const int c = i / j.rows, r = i % j.rows;   // consecutive threads write consecutive dst elements
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) transpose_many_kernel(TransposeJobs 
   }
 }
 void launch_transposes(const TransposeJobs& jobs, cudaStream_t s) {
-  if (jobs.n > 0) transpose_many_kernel<<<jobs.n, kThreads, 0, s>>>(jobs);
+  if (jobs.n > 0) launch_k((transpose_many_kernel), dim3(jobs.n), dim3(kThreads), 0, s, jobs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -106,6 +110,7 @@ struct GinFwdSmem {
 template <int KIN, int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 gin_fwd_kernel(GinFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GinFwdSmem<KIN, HID>& sm = *reinterpret_cast<GinFwdSmem<KIN, HID>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -260,7 +265,7 @@ static void launch_gin_fwd_t(const GinFwdArgs& a, cudaStream_t s) {
   (void)once;
   const int n_tiles = (a.V + GT - 1) / GT;
   const int grid = min(n_tiles, (H == 64 ? 2 : 1) * num_sms());
-  gin_fwd_kernel<KIN, H><<<grid, kThreads, sizeof(GinFwdSmem<KIN, H>), s>>>(a);
+  launch_k((gin_fwd_kernel<KIN, H>), dim3(grid), dim3(kThreads), sizeof(GinFwdSmem<KIN, H>), s, a);
 }
 void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s) {
   if (hidden == 64) { if (kin == DTR) launch_gin_fwd_t<DTR, 64>(a, s); else launch_gin_fwd_t<64, 64>(a, s); }
@@ -277,6 +282,7 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s) {
 template <int HID>
 __global__ void __launch_bounds__(kThreads, 2)
 gin_bwd_pre_kernel(GinBwdPrePair pp) {
+  pdl_sync();
   const bool second = (int)blockIdx.x >= pp.split;
   const GinBwdPreArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
@@ -355,8 +361,8 @@ void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s) {
   pp.a[0] = a; pp.a[1] = a;
   const int grid = gin_bwd_pre_grid(a.V);
   pp.split = grid;
-  if (hidden == 64) gin_bwd_pre_kernel<64><<<grid, kThreads, 0, s>>>(pp);
-  else gin_bwd_pre_kernel<128><<<grid, kThreads, 0, s>>>(pp);
+  if (hidden == 64) launch_k((gin_bwd_pre_kernel<64>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else launch_k((gin_bwd_pre_kernel<128>), dim3(grid), dim3(kThreads), 0, s, pp);
 }
 
 int pair_split(int grid, int work0, int work1) {
@@ -370,8 +376,8 @@ void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, i
   pp.a[0] = a0; pp.a[1] = a1;
   const int grid = max(2, gin_bwd_pre_grid(a0.V + a1.V));
   pp.split = pair_split(grid, a0.V, a1.V);
-  if (hidden == 64) gin_bwd_pre_kernel<64><<<grid, kThreads, 0, s>>>(pp);
-  else gin_bwd_pre_kernel<128><<<grid, kThreads, 0, s>>>(pp);
+  if (hidden == 64) launch_k((gin_bwd_pre_kernel<64>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else launch_k((gin_bwd_pre_kernel<128>), dim3(grid), dim3(kThreads), 0, s, pp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,6 +401,7 @@ struct GinBwdSmem {
 template <int KIN, int HID, int GT>
 __global__ void __launch_bounds__(kThreads, 1)
 gin_bwd_main_kernel(GinBwdMainArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GinBwdSmem<KIN, HID, GT>& sm = *reinterpret_cast<GinBwdSmem<KIN, HID, GT>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -509,7 +516,7 @@ static void launch_gin_bwd_main_t(const GinBwdMainArgs& a, int grid, cudaStream_
   using S = GinBwdSmem<KIN, H, GTB>;
   static bool once = (cudaFuncSetAttribute(gin_bwd_main_kernel<KIN, H, GTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
   (void)once;
-  gin_bwd_main_kernel<KIN, H, GTB><<<grid, kThreads, sizeof(S), s>>>(a);
+  launch_k((gin_bwd_main_kernel<KIN, H, GTB>), dim3(grid), dim3(kThreads), sizeof(S), s, a);
 }
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s) {
   if (hidden == 64) { if (kin == DTR) launch_gin_bwd_main_t<DTR, 64, 128>(a, grid, s); else launch_gin_bwd_main_t<64, 64, 128>(a, grid, s); }
@@ -526,6 +533,7 @@ constexpr int FP = 32;    // padded feature width
 
 __global__ void __launch_bounds__(kThreads)
 input_proj_bwd_kernel(InputProjBwdArgs p) {
+  pdl_sync();
   __shared__ float s_g[PT * (DTR + 1)];
   __shared__ float s_x[PT * (FP + 1)];
   const int o = threadIdx.x & 31, fg = threadIdx.x >> 5;  // thread owns dWt[o][fg*4 .. fg*4+3]
@@ -624,7 +632,7 @@ int input_proj_bwd_grid(int V0, int V1) {
   return min((V0 + PT - 1) / PT + (V1 + PT - 1) / PT, 2 * num_sms());
 }
 void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s) {
-  input_proj_bwd_kernel<<<input_proj_bwd_grid(a.V[0], a.V[1]), kThreads, 0, s>>>(a);
+  launch_k((input_proj_bwd_kernel), dim3(input_proj_bwd_grid(a.V[0], a.V[1])), dim3(kThreads), 0, s, a);
 }
 
 }  // namespace scgib

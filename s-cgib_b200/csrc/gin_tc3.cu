@@ -116,6 +116,7 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
     store_split4(smem + L::off_w2_hi, smem + L::off_w2_lo, HID, o, c4, ldg4(p.W2 + (size_t)o * HID + c4 * 4), 128);
   }
   if (threadIdx.x < HID) { s_b1[threadIdx.x] = p.b1[threadIdx.x]; s_b2[threadIdx.x] = p.b2[threadIdx.x]; }
+  pdl_sync();      // everything above reads parameters only; from here on: the previous kernel's outputs (bn_in, activations)
   if (p.bn_in && threadIdx.x < 4 * HID) s_bn[threadIdx.x] = p.bn_in[threadIdx.x];
   fence_smem_to_async();
   fence_before_sync();
@@ -461,7 +462,7 @@ static void launch_tc3_pw(const GinFwdPair& pp, int grid, cudaStream_t s) {
   using L = tc3::Smem<KIN>;
   static bool once = (cudaFuncSetAttribute(tc3::gin_fwd_tc3_kernel<KIN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total), true);
   (void)once;
-  tc3::gin_fwd_tc3_kernel<KIN, PW><<<grid, (tc3::kEpiWarps + 1 + PW) * 32, L::total, s>>>(pp);
+  launch_k((tc3::gin_fwd_tc3_kernel<KIN, PW>), dim3(grid), dim3((tc3::kEpiWarps + 1 + PW) * 32), L::total, s, pp);
 }
 template <int KIN>
 static void launch_tc3(const GinFwdPair& pp, int grid, cudaStream_t s) {

@@ -20,6 +20,7 @@ template <int HID>
 __global__ void __launch_bounds__(kThreads)
 segment_sum_kernel(const float* __restrict__ in, const int32_t* __restrict__ seg_ptr, int S, const float* __restrict__ bn,
                    float* __restrict__ out) {
+  pdl_sync();
   constexpr int LPR = HID / 4, SPC = kThreads / LPR;      // lanes per segment (4 channels each), segments per CTA pass
   const int l = threadIdx.x % LPR;
   Bn4 b;
@@ -37,14 +38,15 @@ segment_sum_kernel(const float* __restrict__ in, const int32_t* __restrict__ seg
 void launch_segment_sum(const float* in, const int32_t* seg_ptr, int S, const float* bn, float* out, int hidden, cudaStream_t s) {
   const int spc = kThreads / (hidden / 4);
   const int grid = min((S + spc - 1) / spc, 16 * num_sms());
-  if (hidden == 64) segment_sum_kernel<64><<<grid, kThreads, 0, s>>>(in, seg_ptr, S, bn, out);
-  else segment_sum_kernel<128><<<grid, kThreads, 0, s>>>(in, seg_ptr, S, bn, out);
+  if (hidden == 64) launch_k((segment_sum_kernel<64>), dim3(grid), dim3(kThreads), 0, s, in, seg_ptr, S, bn, out);
+  else launch_k((segment_sum_kernel<128>), dim3(grid), dim3(kThreads), 0, s, in, seg_ptr, S, bn, out);
 }
 
 // C_v = sum over the ego-net of v of relu(BN(y)) ; logit_v = w_cand . C_v
 template <bool BF, int HID>
 __global__ void __launch_bounds__(kThreads)
 ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
+  pdl_sync();
   constexpr int LPR = HID / 4, SPC = kThreads / LPR;      // 16 lanes (half-warp) per seed at HID = 64, a full warp at 128
   const int l = threadIdx.x % LPR;
   Bn4 b;
@@ -67,11 +69,11 @@ void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, int hidden, cudaStream_t s) {
   const int spc = kThreads / (hidden / 4);
   const int grid = min((a.N + spc - 1) / spc, 16 * num_sms());
   if (hidden == 64) {
-    if (a.y_bf16) ego_pool_fwd_kernel<true, 64><<<grid, kThreads, 0, s>>>(a);
-    else ego_pool_fwd_kernel<false, 64><<<grid, kThreads, 0, s>>>(a);
+    if (a.y_bf16) launch_k((ego_pool_fwd_kernel<true, 64>), dim3(grid), dim3(kThreads), 0, s, a);
+    else launch_k((ego_pool_fwd_kernel<false, 64>), dim3(grid), dim3(kThreads), 0, s, a);
   } else {
-    if (a.y_bf16) ego_pool_fwd_kernel<true, 128><<<grid, kThreads, 0, s>>>(a);
-    else ego_pool_fwd_kernel<false, 128><<<grid, kThreads, 0, s>>>(a);
+    if (a.y_bf16) launch_k((ego_pool_fwd_kernel<true, 128>), dim3(grid), dim3(kThreads), 0, s, a);
+    else launch_k((ego_pool_fwd_kernel<false, 128>), dim3(grid), dim3(kThreads), 0, s, a);
   }
 }
 
@@ -83,6 +85,7 @@ template <int HID> struct GateLinFwdSmem { float tile[GT * (HID + 4)]; float w[H
 template <bool BF, int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 gate_lin_fwd_kernel(GateLinFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateLinFwdSmem<HID>& sm = *reinterpret_cast<GateLinFwdSmem<HID>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -123,7 +126,7 @@ static void launch_gate_lin_fwd_t(const GateLinFwdArgs& a, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(gate_lin_fwd_kernel<BF, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateLinFwdSmem<H>)), true);
   (void)once;
   const int grid = min((a.N + GT - 1) / GT, (H == 64 ? 2 : 1) * num_sms());
-  gate_lin_fwd_kernel<BF, H><<<grid, kThreads, sizeof(GateLinFwdSmem<H>), s>>>(a);
+  launch_k((gate_lin_fwd_kernel<BF, H>), dim3(grid), dim3(kThreads), sizeof(GateLinFwdSmem<H>), s, a);
 }
 void launch_gate_lin_fwd(const GateLinFwdArgs& a, int hidden, cudaStream_t s) {
   if (hidden == 64) { if (a.y_bf16) launch_gate_lin_fwd_t<true, 64>(a, s); else launch_gate_lin_fwd_t<false, 64>(a, s); }
@@ -136,6 +139,7 @@ template <int HID, int GT> struct GateLinBwdSmem { float gq[2][GT * (HID + 4)]; 
 template <int HID, int GT>       // GT rows per tile: 128 at HID = 64, 32 at HID = 128 (four tiles + the weights in 227 KB)
 __global__ void __launch_bounds__(kThreads, 1)
 gate_lin_bwd_kernel(GateLinBwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateLinBwdSmem<HID, GT>& sm = *reinterpret_cast<GateLinBwdSmem<HID, GT>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -202,7 +206,7 @@ static void launch_gate_lin_bwd_t(const GateLinBwdArgs& a, int grid, cudaStream_
   using S = GateLinBwdSmem<H, GTB>;
   static bool once = (cudaFuncSetAttribute(gate_lin_bwd_kernel<H, GTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
   (void)once;
-  gate_lin_bwd_kernel<H, GTB><<<grid, kThreads, sizeof(S), s>>>(a);
+  launch_k((gate_lin_bwd_kernel<H, GTB>), dim3(grid), dim3(kThreads), sizeof(S), s, a);
 }
 void launch_gate_lin_bwd(const GateLinBwdArgs& a, int hidden, int grid, cudaStream_t s) {
   if (hidden == 64) launch_gate_lin_bwd_t<64, 128>(a, grid, s); else launch_gate_lin_bwd_t<128, 32>(a, grid, s);
@@ -238,6 +242,7 @@ constexpr float kKlEps = 0.0000001f;   // models.py:632
 template <int HID, int RB>      // RB rows in flight per warp in the gate pass (4 for molecule-sized graphs, 8 for ~150-node graphs)
 __global__ void __launch_bounds__(kThreads)
 graph_gate_fwd_kernel(GraphGateFwdArgs p) {
+  pdl_sync();
   constexpr int CPL = HID / 32;
   using V = LaneVec<CPL>;
   const int lane = threadIdx.x & 31;
@@ -366,11 +371,11 @@ void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s
   const int grid = min((a.B + 7) / 8, 8 * num_sms());
   const bool big = a.N / max(a.B, 1) >= 48;
   if (hidden == 64) {
-    if (big) graph_gate_fwd_kernel<64, 8><<<grid, kThreads, 0, s>>>(a);
-    else graph_gate_fwd_kernel<64, 4><<<grid, kThreads, 0, s>>>(a);
+    if (big) launch_k((graph_gate_fwd_kernel<64, 8>), dim3(grid), dim3(kThreads), 0, s, a);
+    else launch_k((graph_gate_fwd_kernel<64, 4>), dim3(grid), dim3(kThreads), 0, s, a);
   } else {
-    if (big) graph_gate_fwd_kernel<128, 8><<<grid, kThreads, 0, s>>>(a);
-    else graph_gate_fwd_kernel<128, 4><<<grid, kThreads, 0, s>>>(a);
+    if (big) launch_k((graph_gate_fwd_kernel<128, 8>), dim3(grid), dim3(kThreads), 0, s, a);
+    else launch_k((graph_gate_fwd_kernel<128, 4>), dim3(grid), dim3(kThreads), 0, s, a);
   }
 }
 
@@ -380,6 +385,7 @@ constexpr int kEmaWindow = 768;
 template <int HID>
 __global__ void __launch_bounds__(1024)
 compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict__ running) {
+  pdl_sync();
   constexpr int kEmaSeg = 1024 / (2 * HID);     // 8 segments at HID = 64, 4 at HID = 128
   __shared__ double s_part[kEmaSeg][2 * HID];
   const int j = threadIdx.x % (2 * HID);  // 0..H-1 mean, H..2H-1 var
@@ -404,13 +410,14 @@ compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict_
   }
 }
 void launch_compressor_ema(const float* cstat, int B, float* running, int hidden, cudaStream_t s) {
-  if (hidden == 64) compressor_ema_kernel<64><<<1, 1024, 0, s>>>(cstat, B, running);
-  else compressor_ema_kernel<128><<<1, 1024, 0, s>>>(cstat, B, running);
+  if (hidden == 64) launch_k((compressor_ema_kernel<64>), dim3(1), dim3(1024), 0, s, cstat, B, running);
+  else launch_k((compressor_ema_kernel<128>), dim3(1), dim3(1024), 0, s, cstat, B, running);
 }
 
 template <int HID>
 __global__ void __launch_bounds__(kThreads)
 graph_gate_bwd_kernel(GraphGateBwdArgs p) {
+  pdl_sync();
   constexpr int CPL = HID / 32;
   using V = LaneVec<CPL>;
   __shared__ __align__(16) float s_red[(kThreads / 32) * 5 * HID];
@@ -581,8 +588,8 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
 }
 void launch_graph_gate_bwd(const GraphGateBwdArgs& a, int hidden, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 4 * num_sms());   // latency-bound warp-per-graph loops: as many resident warps as fit
-  if (hidden == 64) graph_gate_bwd_kernel<64><<<grid, kThreads, 0, s>>>(a);
-  else graph_gate_bwd_kernel<128><<<grid, kThreads, 0, s>>>(a);
+  if (hidden == 64) launch_k((graph_gate_bwd_kernel<64>), dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k((graph_gate_bwd_kernel<128>), dim3(grid), dim3(kThreads), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -617,6 +624,7 @@ __device__ __forceinline__ void head_load_tile(float* tile, const float* __restr
 template <int HID, int HT>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 head_fwd_kernel(HeadFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HeadFwdSmem<HID, HT>& sm = *reinterpret_cast<HeadFwdSmem<HID, HT>*>(smem_raw);
   constexpr int GLD = HID + 4, HLD = 2 * HID + 4;
@@ -660,7 +668,7 @@ static void launch_head_fwd_t(const HeadFwdArgs& a, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(head_fwd_kernel<H, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)), true);
   (void)once;
   const int grid = min((a.N + HT - 1) / HT, (H == 64 ? 2 : 1) * num_sms());
-  head_fwd_kernel<H, HT><<<grid, kThreads, sizeof(S), s>>>(a);
+  launch_k((head_fwd_kernel<H, HT>), dim3(grid), dim3(kThreads), sizeof(S), s, a);
 }
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s) {
   if (hidden == 64) launch_head_fwd_t<64, 64>(a, s); else launch_head_fwd_t<128, 32>(a, s);
@@ -672,6 +680,7 @@ void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s) {
 __global__ void __launch_bounds__(kThreads)
 head_bwd_prep_kernel(const float* __restrict__ W1, float* __restrict__ W1a, float* __restrict__ W1b, float* __restrict__ bn,
                      float* __restrict__ cvec, int HID) {
+  pdl_sync();
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < HID * 2 * HID; i += gridDim.x * kThreads) {
     const int o = i / (2 * HID), k = i % (2 * HID);
     const float w = W1[i];
@@ -682,11 +691,17 @@ head_bwd_prep_kernel(const float* __restrict__ W1, float* __restrict__ W1a, floa
     for (int i = threadIdx.x; i < 2 * HID; i += kThreads) cvec[i] = 0.f;
   }
 }
+__global__ void identity_bn_kernel(float* __restrict__ bn, int HID) {
+  pdl_sync();
+  for (int i = threadIdx.x; i < 4 * HID; i += blockDim.x) bn[i] = (i >= HID && i < 3 * HID) ? 1.f : 0.f;
+}
+void launch_identity_bn(float* bn, int hidden, cudaStream_t s) { identity_bn_kernel<<<1, 128, 0, s>>>(bn, hidden); }
 void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, int hidden, cudaStream_t s) {
-  head_bwd_prep_kernel<<<8, kThreads, 0, s>>>(W1, W1a, W1b, bn, cvec, hidden);
+  launch_k((head_bwd_prep_kernel), dim3(8), dim3(kThreads), 0, s, W1, W1a, W1b, bn, cvec, hidden);
 }
 
 __global__ void __launch_bounds__(kThreads) head_dw1_interleave_kernel(float* __restrict__ dW1, int HID) {
+  pdl_sync();
   extern __shared__ __align__(16) float s_w[];            // [2 * HID * HID]
   for (int i = threadIdx.x; i < 2 * HID * HID; i += kThreads) s_w[i] = dW1[i];
   __syncthreads();
@@ -699,7 +714,122 @@ void launch_head_dw1_interleave(float* dW1, int hidden, cudaStream_t s) {
   const int bytes = 2 * hidden * hidden * (int)sizeof(float);
   static bool once = (cudaFuncSetAttribute(head_dw1_interleave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4), true);
   (void)once;
-  head_dw1_interleave_kernel<<<1, kThreads, bytes, s>>>(dW1, hidden);
+  launch_k((head_dw1_interleave_kernel), dim3(1), dim3(kThreads), bytes, s, dW1, hidden);
+}
+
+}  // namespace scgib
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone operators behind the op-level C ABI (scgib_core_cand_attn_*_f32, scgib_segment_sum_bwd_f32): the whole-step
+// functions run the same math fused into ego_pool_fwd / graph_gate_fwd / graph_gate_bwd.
+// ------------------------------------------------------------------------------------------------
+namespace scgib {
+
+// attention over the candidates of each graph (models.py:738-748; the core half of attn_layer and its bias cancel in the
+// softmax): logit_v = w_cand . C_v, alpha = softmax over the graph's nodes, T_v = alpha_v C_v.  Warp per graph.
+__global__ void __launch_bounds__(kThreads)
+attn_fwd_kernel(const float* __restrict__ C, const int32_t* __restrict__ graph_ptr, int B, int H, const float* __restrict__ w_cand,
+                float* __restrict__ alpha, float* __restrict__ T) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  for (int g = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < B; g += gridDim.x * (kThreads / 32)) {
+    const int v0 = __ldg(graph_ptr + g), v1 = __ldg(graph_ptr + g + 1);
+    float mx = -INFINITY;
+    for (int v = v0; v < v1; ++v) {
+      float d = 0.f;
+      for (int c = lane; c < H; c += 32) d = fmaf(__ldg(w_cand + c), C[(size_t)v * H + c], d);
+      d = warp_sum(d);
+      if (lane == 0) alpha[v] = d;                 // logits first
+      mx = fmaxf(mx, d);
+    }
+    __syncwarp();
+    float se = 0.f;
+    for (int v = v0 + lane; v < v1; v += 32) se += expf(alpha[v] - mx);
+    se = warp_sum(se);
+    __syncwarp();
+    for (int v = v0 + lane; v < v1; v += 32) alpha[v] = expf(alpha[v] - mx) / se;
+    __syncwarp();
+    if (T)
+      for (int v = v0; v < v1; ++v) {
+        const float a = alpha[v];
+        for (int c = lane; c < H; c += 32) T[(size_t)v * H + c] = a * C[(size_t)v * H + c];
+      }
+  }
+}
+void launch_attn_fwd(const float* C, const int32_t* graph_ptr, int B, int H, const float* w_cand, float* alpha, float* T, cudaStream_t s) {
+  launch_k((attn_fwd_kernel), dim3(min((B + 7) / 8, 8 * num_sms())), dim3(kThreads), 0, s, C, graph_ptr, B, H, w_cand, alpha, T);
+}
+
+// backward: d alpha_v = gT_v . C_v;  d logit_v = alpha_v (d alpha_v - sum_u alpha_u d alpha_u);  gC_v = alpha_v gT_v + d logit_v w_cand;
+// d w_cand = sum_v d logit_v C_v  (per-graph partials dwp [B][H], summed by the caller's reduction in graph order)
+__global__ void __launch_bounds__(kThreads)
+attn_bwd_kernel(const float* __restrict__ C, const float* __restrict__ alpha, const float* __restrict__ gT,
+                const int32_t* __restrict__ graph_ptr, int B, int H, const float* __restrict__ w_cand, float* __restrict__ gC,
+                float* __restrict__ dwp, float* __restrict__ scratch) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  for (int g = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < B; g += gridDim.x * (kThreads / 32)) {
+    const int v0 = __ldg(graph_ptr + g), v1 = __ldg(graph_ptr + g + 1);
+    float S = 0.f;
+    for (int v = v0; v < v1; ++v) {
+      float d = 0.f;
+      for (int c = lane; c < H; c += 32) d = fmaf(gT[(size_t)v * H + c], C[(size_t)v * H + c], d);
+      d = warp_sum(d);
+      if (lane == 0) scratch[v] = d;
+      S = fmaf(alpha[v], d, S);
+    }
+    __syncwarp();
+    for (int c = lane; c < H; c += 32) {
+      const float w = __ldg(w_cand + c);
+      float dw = 0.f;
+      for (int v = v0; v < v1; ++v) {
+        const float a = alpha[v], dl = a * (scratch[v] - S);
+        gC[(size_t)v * H + c] = fmaf(dl, w, a * gT[(size_t)v * H + c]);
+        dw = fmaf(dl, C[(size_t)v * H + c], dw);
+      }
+      dwp[(size_t)g * H + c] = dw;
+    }
+  }
+}
+void launch_attn_bwd(const float* C, const float* alpha, const float* gT, const int32_t* graph_ptr, int B, int H, const float* w_cand,
+                     float* gC, float* dwp, float* scratch, cudaStream_t s) {
+  launch_k((attn_bwd_kernel), dim3(min((B + 7) / 8, 8 * num_sms())), dim3(kThreads), 0, s, C, alpha, gT, graph_ptr, B, H, w_cand, gC, dwp, scratch);
+}
+
+// backward of dgl.sum_nodes: g_in[row] = g_out[segment of row]
+__global__ void __launch_bounds__(kThreads)
+segment_sum_bwd_kernel(const float* __restrict__ g_out, const int32_t* __restrict__ seg_ptr, int S, int H, float* __restrict__ g_in) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  for (int sgm = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); sgm < S; sgm += gridDim.x * (kThreads / 32)) {
+    const int r0 = __ldg(seg_ptr + sgm), r1 = __ldg(seg_ptr + sgm + 1);
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 g = ld4(g_out + (size_t)sgm * H + c);
+      for (int r = r0; r < r1; ++r) st4(g_in + (size_t)r * H + c, g);
+    }
+  }
+}
+void launch_segment_sum_bwd(const float* g_out, const int32_t* seg_ptr, int S, int H, float* g_in, cudaStream_t s) {
+  launch_k((segment_sum_bwd_kernel), dim3(min((S + 7) / 8, 16 * num_sms())), dim3(kThreads), 0, s, g_out, seg_ptr, S, H, g_in);
+}
+
+// out[c] = sum_g part[g][c] in graph order (fp64 accumulate): fixed-order column sums of per-graph partials
+__global__ void __launch_bounds__(kThreads)
+colsum_rows_kernel(const float* __restrict__ part, int R, int H, float* __restrict__ out) {
+  pdl_sync();
+  for (int c = blockIdx.x * kThreads + threadIdx.x; c < H; c += gridDim.x * kThreads) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = 0;
+    for (; r + 3 < R; r += 4) {
+      s0 += (double)part[(size_t)r * H + c]; s1 += (double)part[(size_t)(r + 1) * H + c];
+      s2 += (double)part[(size_t)(r + 2) * H + c]; s3 += (double)part[(size_t)(r + 3) * H + c];
+    }
+    for (; r < R; ++r) s0 += (double)part[(size_t)r * H + c];
+    out[c] = (float)((s0 + s1) + (s2 + s3));
+  }
+}
+void launch_colsum_rows(const float* part, int R, int H, float* out, cudaStream_t s) {
+  launch_k((colsum_rows_kernel), dim3(1), dim3(kThreads), 0, s, part, R, H, out);
 }
 
 }  // namespace scgib

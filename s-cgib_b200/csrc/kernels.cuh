@@ -81,9 +81,14 @@ struct GinBwdMainArgs {
   int64_t off_W1, off_b1, off_W2, off_b2;
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s);      // FP32 FFMA tiles, hidden 64 / 128
-struct GinBwdMainPair { GinBwdMainArgs a[2]; int split; int trace; int reverse = 0; };
+struct GinBwdMainPair {
+  GinBwdMainArgs a[2]; int split; int trace; int reverse = 0;
+  int wait_first = 0;       // PDL: W1 / W2 are written by the kernel launched right before this one (the head backward's de-interleaved
+                            //  W1 halves): wait for it before staging the weights instead of after
+};
 void launch_gin_bwd_main_tc2(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s);  // tcgen05 3xTF32, 64-row double-buffered tiles (gin_bwd_tc2.cu)
-void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s);
+void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s,
+                                  bool weights_from_prev_kernel = false);
 int gin_bwd_pre_bf16_grid(int V, int hidden);
 void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, int hidden, cudaStream_t s);
 void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s);
@@ -197,6 +202,14 @@ void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s);
 // (bn = {0, 1, 1, 0}, cvec = 0: g_y = g_o).  fix: grads slot [2][HID][HID] (dW1a | dW1b) -> [HID][2*HID] in place.
 void launch_head_bwd_prep(const float* W1, float* W1a, float* W1b, float* bn, float* cvec, int hidden, cudaStream_t s);
 void launch_head_dw1_interleave(float* dW1, int hidden, cudaStream_t s);
+void launch_identity_bn(float* bn, int hidden, cudaStream_t s);        // bn = {mean 0, rstd 1, gamma 1, beta 0}
+
+// stand-alone attention / segment-broadcast operators (op-level C ABI)
+void launch_attn_fwd(const float* C, const int32_t* graph_ptr, int B, int H, const float* w_cand, float* alpha, float* T, cudaStream_t s);
+void launch_attn_bwd(const float* C, const float* alpha, const float* gT, const int32_t* graph_ptr, int B, int H, const float* w_cand,
+                     float* gC, float* dwp, float* scratch, cudaStream_t s);
+void launch_segment_sum_bwd(const float* g_out, const int32_t* seg_ptr, int S, int H, float* g_in, cudaStream_t s);
+void launch_colsum_rows(const float* part, int R, int H, float* out, cudaStream_t s);
 
 // ---------------------------------------------------------------- loss_kernels.cu
 // recon: per-CTA partials of Z^T Z and of sum_{(i,j) in E} z_i . z_j     (models.py:762-768, Gram identity)

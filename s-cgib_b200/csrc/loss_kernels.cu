@@ -23,6 +23,7 @@ template <int HID> struct ReconFwdSmem { float z[GT * (HID + 4)]; float red[kThr
 template <int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 recon_fwd_kernel(ReconFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ReconFwdSmem<HID>& sm = *reinterpret_cast<ReconFwdSmem<HID>*>(smem_raw);
   constexpr int GLD = HID + 4, LPR = HID / 4, RPP = kThreads / LPR;
@@ -70,7 +71,7 @@ template <int H>
 static void launch_recon_fwd_t(const ReconFwdArgs& a, int grid, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(recon_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconFwdSmem<H>)), true);
   (void)once;
-  recon_fwd_kernel<H><<<grid, kThreads, sizeof(ReconFwdSmem<H>), s>>>(a);
+  launch_k((recon_fwd_kernel<H>), dim3(grid), dim3(kThreads), sizeof(ReconFwdSmem<H>), s, a);
 }
 void launch_recon_fwd(const ReconFwdArgs& a, int hidden, int grid, cudaStream_t s) {
   if (hidden == 64) launch_recon_fwd_t<64>(a, grid, s); else launch_recon_fwd_t<128>(a, grid, s);
@@ -78,6 +79,7 @@ void launch_recon_fwd(const ReconFwdArgs& a, int hidden, int grid, cudaStream_t 
 
 __global__ void __launch_bounds__(kThreads)
 recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum, int HID) {
+  pdl_sync();
   const int j = blockIdx.x * kThreads + threadIdx.x;
   if (j > HID * HID) return;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // interleaved partial sums: independent loads in flight, fixed order
@@ -93,7 +95,7 @@ recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict_
   if (j < HID * HID) G[j] = (float)s; else edge_sum[0] = (float)s;
 }
 void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, int hidden, cudaStream_t s) {
-  recon_reduce_kernel<<<(hidden * hidden + 1 + kThreads - 1) / kThreads, kThreads, 0, s>>>(part, grid, G, edge_sum, hidden);
+  launch_k((recon_reduce_kernel), dim3((hidden * hidden + 1 + kThreads - 1) / kThreads), dim3(kThreads), 0, s, part, grid, G, edge_sum, hidden);
 }
 
 // recon backward: gZ = scale * (4/N) * (Z G - A Z)
@@ -102,6 +104,7 @@ template <int HID> struct ReconBwdSmem { float z[GT * (HID + 4)]; float g[HID * 
 template <int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 recon_bwd_kernel(ReconBwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ReconBwdSmem<HID>& sm = *reinterpret_cast<ReconBwdSmem<HID>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -137,7 +140,7 @@ static void launch_recon_bwd_t(const ReconBwdArgs& a, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(recon_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconBwdSmem<H>)), true);
   (void)once;
   const int grid = min((a.N + GT - 1) / GT, (H == 64 ? 2 : 1) * num_sms());
-  recon_bwd_kernel<H><<<grid, kThreads, sizeof(ReconBwdSmem<H>), s>>>(a);
+  launch_k((recon_bwd_kernel<H>), dim3(grid), dim3(kThreads), sizeof(ReconBwdSmem<H>), s, a);
 }
 void launch_recon_bwd(const ReconBwdArgs& a, int hidden, cudaStream_t s) {
   if (hidden == 64) launch_recon_bwd_t<64>(a, s); else launch_recon_bwd_t<128>(a, s);
@@ -160,6 +163,7 @@ __device__ __forceinline__ float tf32_round(float v) {
 template <int HID>
 __global__ void __launch_bounds__(kThreads)
 normalize_kernel(NormalizeArgs p) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, c = 2 * lane;
   if (HID == 128) {
     for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < p.B; i += gridDim.x * (kThreads / 32)) {
@@ -197,8 +201,8 @@ normalize_kernel(NormalizeArgs p) {
 }
 void launch_normalize(const NormalizeArgs& a, int hidden, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 8 * num_sms());
-  if (hidden == 64) normalize_kernel<64><<<grid, kThreads, 0, s>>>(a);
-  else normalize_kernel<128><<<grid, kThreads, 0, s>>>(a);
+  if (hidden == 64) launch_k((normalize_kernel<64>), dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k((normalize_kernel<128>), dim3(grid), dim3(kThreads), 0, s, a);
 }
 
 int contrastive_jsplit(int B) {
@@ -241,6 +245,7 @@ template <int HID> struct ConFwdSmem { float zi[CT * (HID + 4)]; float zj1[CT * 
 template <int HID>
 __global__ void __launch_bounds__(kThreads, 2)
 contrastive_fwd_kernel(ContrastiveFwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ConFwdSmem<HID>& sm = *reinterpret_cast<ConFwdSmem<HID>*>(smem_raw);
   constexpr int GLD = HID + 4;
@@ -287,7 +292,7 @@ static void launch_contrastive_fwd_t(const ContrastiveFwdArgs& a, cudaStream_t s
   static bool once = (cudaFuncSetAttribute(contrastive_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConFwdSmem<H>)), true);
   (void)once;
   dim3 grid((a.B + CT - 1) / CT, a.jsplit);
-  contrastive_fwd_kernel<H><<<grid, kThreads, sizeof(ConFwdSmem<H>), s>>>(a);
+  launch_k((contrastive_fwd_kernel<H>), dim3(grid), dim3(kThreads), sizeof(ConFwdSmem<H>), s, a);
 }
 void launch_contrastive_fwd(const ContrastiveFwdArgs& a, int hidden, cudaStream_t s) {
   if (hidden == 64) launch_contrastive_fwd_t<64>(a, s); else launch_contrastive_fwd_t<128>(a, s);
@@ -302,6 +307,7 @@ template <int HID> struct ConBwdSmem { float zi[CT * (HID + 4)]; float zj1[CT * 
 template <int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 contrastive_bwd_kernel(ContrastiveBwdArgs p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ConBwdSmem<HID>& sm = *reinterpret_cast<ConBwdSmem<HID>*>(smem_raw);
   constexpr int GLD = HID + 4, PLD = CT + 4;
@@ -364,7 +370,7 @@ static void launch_contrastive_bwd_t(const ContrastiveBwdArgs& a, cudaStream_t s
   static bool once = (cudaFuncSetAttribute(contrastive_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConBwdSmem<H>)), true);
   (void)once;
   dim3 grid((a.B + CT - 1) / CT, a.jsplit, 2);
-  contrastive_bwd_kernel<H><<<grid, kThreads, sizeof(ConBwdSmem<H>), s>>>(a);
+  launch_k((contrastive_bwd_kernel<H>), dim3(grid), dim3(kThreads), sizeof(ConBwdSmem<H>), s, a);
 }
 void launch_contrastive_bwd(const ContrastiveBwdArgs& a, int hidden, cudaStream_t s) {
   if (hidden == 64) launch_contrastive_bwd_t<64>(a, s); else launch_contrastive_bwd_t<128>(a, s);
@@ -374,6 +380,7 @@ void launch_contrastive_bwd(const ContrastiveBwdArgs& a, int hidden, cudaStream_
 template <int HID>
 __global__ void __launch_bounds__(kThreads)
 contrastive_bwd_finalize_kernel(ContrastiveBwdFinArgs p) {
+  pdl_sync();
   constexpr int NH = HID / 64;                  // a lane owns channel pairs 2*lane + 64*h
   const int lane = threadIdx.x & 31, c = 2 * lane;
   const float k = p.scale / (float)p.B;
@@ -404,8 +411,8 @@ contrastive_bwd_finalize_kernel(ContrastiveBwdFinArgs p) {
 }
 void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, int hidden, cudaStream_t s) {
   const int grid = min((a.B + 7) / 8, 8 * num_sms());
-  if (hidden == 64) contrastive_bwd_finalize_kernel<64><<<grid, kThreads, 0, s>>>(a);
-  else contrastive_bwd_finalize_kernel<128><<<grid, kThreads, 0, s>>>(a);
+  if (hidden == 64) launch_k((contrastive_bwd_finalize_kernel<64>), dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k((contrastive_bwd_finalize_kernel<128>), dim3(grid), dim3(kThreads), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,6 +421,7 @@ void launch_contrastive_bwd_finalize(const ContrastiveBwdFinArgs& a, int hidden,
 constexpr int kFin = 1024;     // one CTA; latency-bound (B rows x jsplit dependent loads each): as many threads as a CTA allows
 __global__ void __launch_bounds__(kFin)
 loss_finalize_kernel(LossFinalizeArgs p) {
+  pdl_sync();
   __shared__ double s_a[kFin], s_b[kFin];
   double con = 0.0, fro = 0.0;
   for (int i = threadIdx.x; i < p.B; i += kFin) {
@@ -438,13 +446,14 @@ loss_finalize_kernel(LossFinalizeArgs p) {
     p.losses[0] = kl; p.losses[1] = c; p.losses[2] = r; p.losses[3] = kl + r + c;
   }
 }
-void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { loss_finalize_kernel<<<1, kFin, 0, s>>>(a); }
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { launch_k((loss_finalize_kernel), dim3(1), dim3(kFin), 0, s, a); }
 
 // ------------------------------------------------------------------------------------------------
 // grads[off+i] = sum_c part[c*pstride + off + i]   (fixed order => run-to-run bit-stable)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_kernel(const float* __restrict__ part, int64_t pstride, int nparts, ReduceRanges r, float* __restrict__ grads) {
+  pdl_sync();
   // 4 consecutive lanes share one output element: each sums a contiguous quarter of the partial rows in order, the
   // quarters are combined as (q0 + q1) + (q2 + q3) - a fixed order, with 4x the loads in flight
   const int64_t off = r.off[blockIdx.y], len = r.len[blockIdx.y];
@@ -468,7 +477,7 @@ void launch_reduce_partials(const float* part, int64_t pstride, int nparts, cons
                             cudaStream_t s) {
   if (r.n == 0) return;
   dim3 grid(128, r.n);  // largest range is 8192 floats x 4 lanes = 128 CTAs x 256
-  reduce_partials_kernel<<<grid, kThreads, 0, s>>>(part, pstride, nparts, r, grads);
+  launch_k((reduce_partials_kernel), dim3(grid), dim3(kThreads), 0, s, part, pstride, nparts, r, grads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -477,6 +486,7 @@ void launch_reduce_partials(const float* part, int64_t pstride, int nparts, cons
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
             float lr, float b1, float b2, float eps, float wd, float gscale, float step_size, float bc2_sqrt) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const float pi = p[i];
     const float gi = fmaf(wd, pi, g[i] * gscale);

@@ -18,6 +18,7 @@ SCGIB_API void scgib_set_tensor_cores_bwd(int mode);
  * ([cta < 160][tile < 16][event < 12] SM clocks) copied to host memory; bit 2048: the same for gin_bwd_tc2. */
 SCGIB_API int scgib_debug_tc2_trace(long long* host_out, int n);
 SCGIB_API int scgib_debug_bwd_trace(long long* host_out, int n);
+SCGIB_API int scgib_debug_bf16_trace(long long* host_out, int n);     /* gin_fwd_bf16 (bf16 mode), same layout */
 #ifdef __cplusplus
 }
 #endif

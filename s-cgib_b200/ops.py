@@ -106,3 +106,110 @@ def contrastive(core, readout, scale=1.0, want_grad=True):
     _lib.check(lib.scgib_contrastive_f32(_lib.ptr(core), _lib.ptr(readout), B, float(scale), _lib.ptr(loss), _lib.ptr(g1),
                                          _lib.ptr(g2), _lib.ptr(ws), ws.numel(), _stream(core)), "contrastive")
     return loss, g1, g2
+
+
+def _ws(nbytes, dev):
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+
+
+class CoreGate:
+    """compress + compression (models.py:595-604, 631-660) as one operator pair; ``forward`` keeps its saved state in a
+    workspace that ``backward`` reuses (one forward, then its backward)."""
+
+    def __init__(self, hidden, Wc1, bc1, gamma_c, beta_c, wc2, bc2):
+        self.H = int(hidden)
+        self.p = [t.contiguous().float() for t in (Wc1, bc1, gamma_c, beta_c, wc2, bc2)]
+
+    def forward(self, Hfeat, graph_ptr, gate_u, feat_u):
+        _cuda(Hfeat, graph_ptr, gate_u, feat_u)
+        lib, H, dev = _lib.load(), self.H, Hfeat.device
+        N, B = Hfeat.shape[0], graph_ptr.numel() - 1
+        self.ws = _ws(lib.scgib_core_gate_workspace_bytes(H, B, N), dev)
+        self.saved = (graph_ptr, B, N, feat_u.contiguous())
+        noisy, lam = torch.empty(N, H, device=dev), torch.empty(N, device=dev)
+        readout, core, kl = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev), torch.empty(1, device=dev)
+        W, b, g, be, w2, b2 = self.p
+        _lib.check(lib.scgib_core_gate_fwd_f32(_lib.ptr(Hfeat.contiguous()), _lib.ptr(graph_ptr), B, N, H, _lib.ptr(W), _lib.ptr(b),
+                                               _lib.ptr(g), _lib.ptr(be), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(gate_u.contiguous()),
+                                               _lib.ptr(self.saved[3]), _lib.ptr(noisy), _lib.ptr(lam), _lib.ptr(readout), _lib.ptr(core),
+                                               _lib.ptr(kl), _lib.ptr(self.ws), self.ws.numel(), _stream(Hfeat)), "core_gate_fwd")
+        return noisy, lam, readout, core, kl
+
+    def backward(self, g_noisy, g_core, g_readout, kl_scale=1.0):
+        lib, H = _lib.load(), self.H
+        graph_ptr, B, N, feat_u = self.saved
+        dev = feat_u.device
+        W, b, g, be, w2, b2 = self.p
+        gH = torch.empty(N, H, device=dev)
+        out = [torch.empty(H, H, device=dev), torch.empty(H, device=dev), torch.empty(H, device=dev), torch.empty(H, device=dev),
+               torch.empty(H, device=dev), torch.empty(1, device=dev)]
+        _lib.check(lib.scgib_core_gate_bwd_f32(_lib.ptr(graph_ptr), B, N, H, _lib.ptr(W), _lib.ptr(g), _lib.ptr(be), _lib.ptr(w2),
+                                               _lib.ptr(feat_u), _lib.ptr(g_noisy.contiguous()), _lib.ptr(g_core.contiguous()),
+                                               _lib.ptr(g_readout.contiguous()), float(kl_scale), _lib.ptr(gH), *[_lib.ptr(t) for t in out],
+                                               _lib.ptr(self.ws), self.ws.numel(), _stream(gH)), "core_gate_bwd")
+        return (gH, *out)
+
+
+def core_cand_attn_fwd(C, graph_ptr, w_cand):
+    """attention loop of models.py:738-748 -> (alpha [N], T = alpha C [N,H])."""
+    _cuda(C, graph_ptr, w_cand)
+    N, H = C.shape
+    alpha, T = torch.empty(N, device=C.device), torch.empty_like(C)
+    _lib.check(_lib.load().scgib_core_cand_attn_fwd_f32(_lib.ptr(C.contiguous()), _lib.ptr(graph_ptr), graph_ptr.numel() - 1, N, H,
+                                                        _lib.ptr(w_cand.contiguous()), _lib.ptr(alpha), _lib.ptr(T), _stream(C)), "attn_fwd")
+    return alpha, T
+
+
+def core_cand_attn_bwd(C, alpha, gT, graph_ptr, w_cand):
+    _cuda(C, alpha, gT, graph_ptr, w_cand)
+    N, H = C.shape
+    B = graph_ptr.numel() - 1
+    gC, dw = torch.empty_like(C), torch.empty(H, device=C.device)
+    ws = _ws((N + B * H) * 4 + 512, C.device)
+    _lib.check(_lib.load().scgib_core_cand_attn_bwd_f32(_lib.ptr(C.contiguous()), _lib.ptr(alpha), _lib.ptr(gT.contiguous()), _lib.ptr(graph_ptr),
+                                                        B, N, H, _lib.ptr(w_cand.contiguous()), _lib.ptr(gC), _lib.ptr(dw), _lib.ptr(ws),
+                                                        ws.numel(), _stream(C)), "attn_bwd")
+    return gC, dw
+
+
+class HeadMLP:
+    """self.MLP(interaction_map), interaction_map = [noisy || alpha C] (models.py:569-572, 676, 749)."""
+
+    def __init__(self, hidden, W1, b1, W2, b2):
+        self.H = int(hidden)
+        self.p = [t.contiguous().float() for t in (W1, b1, W2, b2)]
+
+    def forward(self, noisy, C, alpha):
+        _cuda(noisy, C, alpha)
+        lib, H, dev = _lib.load(), self.H, noisy.device
+        N = noisy.shape[0]
+        self.ws = _ws(lib.scgib_head_mlp_workspace_bytes(H, N), dev)
+        self.saved = (noisy.contiguous(), N)
+        imap, Z = torch.empty(N, 2 * H, device=dev), torch.empty(N, H, device=dev)
+        W1, b1, W2, b2 = self.p
+        _lib.check(lib.scgib_head_mlp_fwd_f32(_lib.ptr(self.saved[0]), _lib.ptr(C.contiguous()), _lib.ptr(alpha.contiguous()), N, H, _lib.ptr(W1),
+                                              _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(imap), _lib.ptr(Z), _lib.ptr(self.ws),
+                                              self.ws.numel(), _stream(noisy)), "head_mlp_fwd")
+        return Z, imap
+
+    def backward(self, gZ):
+        lib, H = _lib.load(), self.H
+        noisy, N = self.saved
+        dev = noisy.device
+        W1, b1, W2, b2 = self.p
+        gI = torch.empty(2, N, H, device=dev)
+        dW1, db1, dW2, db2 = torch.empty(H, 2 * H, device=dev), torch.empty(H, device=dev), torch.empty(H, H, device=dev), torch.empty(H, device=dev)
+        _lib.check(lib.scgib_head_mlp_bwd_f32(_lib.ptr(gZ.contiguous()), _lib.ptr(noisy), N, H, _lib.ptr(W1), _lib.ptr(W2), _lib.ptr(gI),
+                                              _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2), _lib.ptr(self.ws), self.ws.numel(),
+                                              _stream(noisy)), "head_mlp_bwd")
+        return gI, dW1, db1, dW2, db2
+
+
+def segment_sum_bwd(g_out, seg_ptr, rows):
+    """backward of dgl.sum_nodes: g_in[row] = g_out[segment(row)]."""
+    _cuda(g_out, seg_ptr)
+    S, H = g_out.shape
+    g_in = torch.empty(rows, H, device=g_out.device)
+    _lib.check(_lib.load().scgib_segment_sum_bwd_f32(_lib.ptr(g_out.contiguous()), _lib.ptr(seg_ptr), S, H, _lib.ptr(g_in), _stream(g_out)),
+               "segment_sum_bwd")
+    return g_in

@@ -8,7 +8,8 @@ from scgib_b200.synth import synth_batch
 
 lib = _lib.load()
 dev = torch.device("cuda:0")
-eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0)
+import os
+eng = PretrainEngine(9, gin_layers=4, device=dev, seed=0, dtype=os.environ.get("SCGIB_TRACE_DTYPE", "fp32"))
 g = synth_batch(1, 4096).to(dev)
 b = eng.make_batch(g, 1)
 import sys
@@ -20,7 +21,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 n = 160 * 16 * 12
 buf = (ctypes.c_longlong * n)()
-(lib.scgib_debug_bwd_trace if BWD else lib.scgib_debug_tc2_trace)(ctypes.cast(buf, ctypes.c_void_p), n)
+BF = os.environ.get("SCGIB_TRACE_DTYPE", "fp32") == "bf16"
+(lib.scgib_debug_bwd_trace if BWD else (lib.scgib_debug_bf16_trace if BF else lib.scgib_debug_tc2_trace))(ctypes.cast(buf, ctypes.c_void_p), n)
 t = np.frombuffer(buf, dtype=np.int64).reshape(160, 16, 12).astype(np.float64)
 names = (["l.start", "l.d2prev", "l.full1", "l.d1", "l.full2", "m.g13", "m.g24", "e.d1", "e.gu", "e.d2", "e.end"] if BWD else
          ["p.start", "p.landed", "p.issued", "p.gathered", "p.full", "m.g1", "m.g2", "e.d1", "e.r", "e.d2", "e.end"])
