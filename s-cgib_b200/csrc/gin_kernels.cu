@@ -10,6 +10,7 @@
 //   statistics (Chan combine in fp64, fixed order) and the running-stat EMA.
 // Backward per layer: `gin_bwd_pre` (gather of the upstream gradient, ReLU/BN mask, d gamma / d beta with an
 // in-kernel deterministic finalise) then `gin_bwd_main` (BN backward, 4 tile GEMMs: g_r, g_a, dW2, dW1).
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace scgib {
@@ -279,8 +280,8 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s) {
 //   g_o = G * [gamma*yhat+beta > 0] ; dbeta = sum g_o ; dgamma = sum g_o*yhat
 // Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
 // ------------------------------------------------------------------------------------------------
-template <int HID>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int HID, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 gin_bwd_pre_kernel(GinBwdPrePair pp) {
   pdl_sync();
   const bool second = (int)blockIdx.x >= pp.split;
@@ -354,15 +355,28 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
   }
 }
 
-int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, 2 * num_sms()); }   // 2 resident CTAs per SM, 64 rows per pass
+// resident CTAs per SM of the gather kernels: SCGIB_PRE_OCC = 2 (default) | 3 | 4.  Measured on B200 (B = 4096): 52 / 58 / 59 us
+// per launch in fp32 and 42 / 63 / 68 us in bf16 - the register cap of the higher occupancies spills the rows in flight
+int gin_bwd_pre_occ() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_PRE_OCC"); v = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 2; }
+  return v;
+}
+int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, gin_bwd_pre_occ() * num_sms()); }
+template <int H>
+static void launch_pre_t(const GinBwdPrePair& pp, int grid, cudaStream_t s) {
+  const int occ = gin_bwd_pre_occ();
+  if (occ == 2) launch_k((gin_bwd_pre_kernel<H, 2>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else if (occ == 3) launch_k((gin_bwd_pre_kernel<H, 3>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else launch_k((gin_bwd_pre_kernel<H, 4>), dim3(grid), dim3(kThreads), 0, s, pp);
+}
 
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s) {
   GinBwdPrePair pp;
   pp.a[0] = a; pp.a[1] = a;
   const int grid = gin_bwd_pre_grid(a.V);
   pp.split = grid;
-  if (hidden == 64) launch_k((gin_bwd_pre_kernel<64>), dim3(grid), dim3(kThreads), 0, s, pp);
-  else launch_k((gin_bwd_pre_kernel<128>), dim3(grid), dim3(kThreads), 0, s, pp);
+  if (hidden == 64) launch_pre_t<64>(pp, grid, s); else launch_pre_t<128>(pp, grid, s);
 }
 
 int pair_split(int grid, int work0, int work1) {
@@ -376,8 +390,7 @@ void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, i
   pp.a[0] = a0; pp.a[1] = a1;
   const int grid = max(2, gin_bwd_pre_grid(a0.V + a1.V));
   pp.split = pair_split(grid, a0.V, a1.V);
-  if (hidden == 64) launch_k((gin_bwd_pre_kernel<64>), dim3(grid), dim3(kThreads), 0, s, pp);
-  else launch_k((gin_bwd_pre_kernel<128>), dim3(grid), dim3(kThreads), 0, s, pp);
+  if (hidden == 64) launch_pre_t<64>(pp, grid, s); else launch_pre_t<128>(pp, grid, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ struct GinBwdPreArgs {
 };
 struct GinBwdPrePair { GinBwdPreArgs a[2]; int split; };
 int gin_bwd_pre_grid(int V);
+int gin_bwd_pre_occ();          // resident CTAs per SM of the gather kernels (SCGIB_PRE_OCC)
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s);
 void launch_gin_bwd_pre_pair(const GinBwdPreArgs& a0, const GinBwdPreArgs& a1, int hidden, cudaStream_t s);   // grid = gin_bwd_pre_grid(V0 + V1)
 int pair_split(int grid, int work0, int work1);     // CTAs given to problem 0

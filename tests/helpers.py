@@ -63,7 +63,22 @@ def fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=0):
 GRAD_TOL_MEDIAN, GRAD_TOL_MAX = 5e-5, 5e-3
 
 
-def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_grads, fwd_tol=1e-5, slack=5.0):
+def dump_parity(tag, report):
+    """Measured errors of a parity case -> gpurun_out/parity_fp32/<tag>.json (kept in profiles/parity_r02.json)."""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_fp32")
+    os.makedirs(out, exist_ok=True)
+    fwd = {r[0]: dict(cuda_vs_fp64=r[1], fp32_torch_vs_fp64=r[2], bound=r[3]) for r in report if not r[0].startswith("grad ")}
+    g = sorted(r[1] for r in report if r[0].startswith("grad "))
+    gr = sorted(r[2] for r in report if r[0].startswith("grad "))
+    worst = max((r for r in report if r[0].startswith("grad ")), key=lambda r: r[1])
+    with open(os.path.join(out, tag + ".json"), "w") as fh:
+        json.dump(dict(case=tag, forward=fwd, grad_median_cuda_vs_fp64=g[len(g) // 2], grad_max_cuda_vs_fp64=g[-1],
+                       grad_worst=worst[0], grad_median_fp32_torch_vs_fp64=gr[len(gr) // 2], grad_max_fp32_torch_vs_fp64=gr[-1]), fh, indent=1)
+
+
+def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_grads, fwd_tol=1e-5, slack=5.0, tag=None):
     """The CUDA fp32 result is measured against the fp64 oracle ("truth"), next to the reference-precision (fp32
     torch) run of the same math.
 
@@ -105,6 +120,8 @@ def check_against_truth(eng, losses, emb, ref_out, ref_grads, truth_out, truth_g
     gerr = sorted(r[1] for r in report if r[0].startswith("grad "))
     rerr = sorted(r[2] for r in report if r[0].startswith("grad "))
     med, med_ref = gerr[len(gerr) // 2], rerr[len(rerr) // 2]
+    if tag is not None:
+        dump_parity(tag, report)
     # at full size (~3e7 ReLU units) mask flips are everywhere: the yardstick is the fp32 reference run's own median
     assert med <= max(GRAD_TOL_MEDIAN, 2.0 * med_ref), ("median gradient error", med, "fp32 reference run", med_ref)
     return report

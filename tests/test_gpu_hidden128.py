@@ -60,7 +60,7 @@ def _fp32_case(seed, B, k, shape):
     eng.backward()
     torch.cuda.synchronize()
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
-    check_against_truth(eng, losses.cpu(), emb, out, ref_grads, truth_out, truth_grads)
+    check_against_truth(eng, losses.cpu(), emb, out, ref_grads, truth_out, truth_grads, tag="h128_faithful_%s_b%d_k%d_s%d" % (shape, B, k, seed))
     # bit-identical rerun
     l2 = eng.forward(b, gate_u.to(DEV), feat_u.to(DEV), update_running=False).clone()
     g1 = eng.grads.clone()
@@ -90,7 +90,7 @@ def test_full_size_hidden128_finite_and_matches_vectorised_oracle():
     eng.backward()
     torch.cuda.synchronize()
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
-    check_against_truth(eng, losses.cpu(), emb, out, ref_grads, truth_out, truth_grads)
+    check_against_truth(eng, losses.cpu(), emb, out, ref_grads, truth_out, truth_grads, tag="h128_vectorised_b1024_k1")
 
 
 def _args(**kw):

@@ -138,7 +138,7 @@ def test_golden_reference_parity(path):
     logm = k if fx["meta"].get("recons_type", "adj") == "logM" else 0
     eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u, recon_logm_steps=logm)
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u, recon_logm_steps=logm)
-    check_against_truth(eng, losses, emb, fx["out"], fx["grads"], truth_out, truth_grads)
+    check_against_truth(eng, losses, emb, fx["out"], fx["grads"], truth_out, truth_grads, tag="golden_" + os.path.basename(path)[:-3])
     # direct comparison with the recorded reference numbers as well (these batches are tiny: fp32 noise is small)
     for i, name in enumerate(("KL", "contrastive", "recon")):
         assert abs(float(losses[i]) - float(fx["out"][name])) <= FWD_TOL * abs(float(fx["out"][name])), name
@@ -165,7 +165,7 @@ def test_parity_vs_faithful_oracle(seed, B, k):
     m.zero_grad()
     eng, losses, emb = _run_engine(m, g, e, k, gate_u, feat_u)
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
-    check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
+    check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads, tag="h64_faithful_b%d_k%d" % (B, k))
 
 
 @pytest.mark.parametrize("B,k", [(4096, 1)])
@@ -184,7 +184,7 @@ def test_parity_full_size_vs_vectorised_oracle_fp64(B, k):
     ref_grads = oracle_grads(m, out)
     m.zero_grad()
     truth_out, truth_grads = fp64_truth(m, g, e, gate_u, feat_u)
-    rep = check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads)
+    rep = check_against_truth(eng, losses, emb, out, ref_grads, truth_out, truth_grads, tag="h64_vectorised_b%d_k%d" % (B, k))
     worst = max(rep, key=lambda r: r[1])
     print("worst cuda-vs-fp64 %.3e (%s); fp32 torch oracle on the same tensor %.3e" % (worst[1], worst[0], worst[2]))
 
