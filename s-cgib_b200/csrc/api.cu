@@ -146,6 +146,7 @@ struct Ws {
   float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o[2], *Ga[2], *ga0[2];
   float *logm_walks, *logm_gram, *logm_pair, *logm_loss;     // --recons_type logM (logm_kernels.cu)
   float *aC, *head_w1a, *head_w1b, *head_bn, *head_cvec;     // tensor-core head backward (the GIN backward kernel on two K halves)
+  bf16_t *noisy_bf, *aC_bf, *r_head_bf, *gZ_bf;              // bf16 mode: its operands in bf16 (the bf16 GIN backward kernel)
   float* ppart;
   size_t bytes;
 };
@@ -210,6 +211,12 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.logm_walks = take((size_t)logm_max_steps() * N); w.logm_gram = take(B); w.logm_pair = take(N); w.logm_loss = take(4);
   w.aC = take((size_t)N * HID); w.head_w1a = take(HID * HID); w.head_w1b = take(HID * HID);
   w.head_bn = take(4 * HID); w.head_cvec = take(2 * HID);
+  if (d->act_dtype == SCGIB_ACT_BF16) {
+    w.noisy_bf = (bf16_t*)take_act((size_t)N * HID); w.aC_bf = (bf16_t*)take_act((size_t)N * HID);
+    w.r_head_bf = (bf16_t*)take_act((size_t)N * HID); w.gZ_bf = (bf16_t*)take_act((size_t)N * HID);
+  } else {
+    w.noisy_bf = w.aC_bf = w.r_head_bf = w.gZ_bf = nullptr;
+  }
   w.ppart = take((size_t)num_sms() * lo.total);
   w.bytes = o;
   (void)E; (void)Es;
@@ -366,12 +373,14 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     a.noisy = w.noisy; a.lam = w.lam; a.alpha = w.alpha; a.readout = w.readout; a.core = w.core;
     a.gstat = w.gstat; a.cstat = (bn_running && !eval) ? w.cstat : nullptr; a.kl = w.kl;
     a.eval_running = eval ? bn_running + (size_t)2 * L * 2 * HID : nullptr;
+    a.noisy_bf = w.noisy_bf;
     PROF("graph_gate_fwd", launch_graph_gate_fwd(a, HID, s));
     if (bn_running && !eval) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, HID, s));
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
-                  params + lo.off[SCGIB_P_HEAD_B2], interaction_map, w.aC, w.r_head, w.Z};
+                  params + lo.off[SCGIB_P_HEAD_B2], interaction_map, bf ? nullptr : w.aC, bf ? nullptr : w.r_head, w.Z,
+                  w.r_head_bf, w.aC_bf};       // bf16 mode: the backward's operands are kept in bf16 only
     PROF("head_fwd", launch_head_fwd(a, HID, s));
   }
   const int logm = b->recon_logm_steps;
@@ -468,9 +477,11 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   // K = H inputs, so its backward is the GIN backward kernel run on both halves (problem 0: a = noisy, W1a -> gI[:, :H], dW1a,
   // dW2, db1, db2; problem 1: a = alpha C, W1b -> gI[:, H:], dW1b; its duplicate dW2 / bias partials are not reduced) with an
   // identity BatchNorm backward (g_y = gZ).  tcgen05 kernel: both problems in ONE launch (CTAs split); FFMA tiles: two launches.
-  const int head_split = tc_bwd ? pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128) : GP;
+  const bool head_pair = tc_bwd || bf;         // one shared launch (CTAs split between the two K halves)
+  const int head_split = head_pair ? pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128) : GP;
   {
     PROF("head_bwd_prep", launch_head_bwd_prep(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1a, w.head_w1b, w.head_bn, w.head_cvec, HID, s));
+    if (bf) PROF("head_gz_bf16", launch_f32_to_bf16(w.gZ, w.gZ_bf, (size_t)b->N * HID, s));
     GinBwdMainArgs m[2];
     for (int h = 0; h < 2; ++h) {
       m[h].g_o = w.gZ; m[h].y = w.Z; m[h].r = w.r_head; m[h].a = h == 0 ? w.noisy : w.aC;
@@ -480,7 +491,15 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m[h].off_W1 = lo.off[SCGIB_P_HEAD_W1] + (int64_t)h * HID * HID; m[h].off_b1 = lo.off[SCGIB_P_HEAD_B1];
       m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
     }
-    if (tc_bwd) {
+    if (bf) {
+      // bf16 mode: the bf16 GIN backward kernel (single-pass bf16 MMAs) on bf16 copies of gZ / r / noisy / alpha C; gI stays fp32.
+      // Its weight staging precedes its PDL wait: W1a / W1b come from head_bwd_prep, TWO launches upstream (complete by then).
+      for (int h = 0; h < 2; ++h) {
+        m[h].g_o = (const float*)w.gZ_bf; m[h].y = (const float*)w.gZ_bf; m[h].r = (const float*)w.r_head_bf;
+        m[h].a = (const float*)(h == 0 ? w.noisy_bf : w.aC_bf);
+      }
+      PROF("head_bwd_bf16", launch_gin_bwd_main_bf16(m[0], &m[1], HID, HID, GP, s, true));
+    } else if (tc_bwd) {
       PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s, true));   // W1a / W1b come from head_bwd_prep
     } else {
       PROF("head_bwd_ffma.a", launch_gin_bwd_main(m[0], HID, HID, GP, s));
@@ -561,7 +580,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     // shared tcgen05 launch: partial rows [0, head_split) = problem 0 (dW1a and everything else), [head_split, GP) = problem 1
     // (dW1b); FFMA: two launches, every partial row holds both
     add(lo.off[SCGIB_P_HEAD_W1], (int64_t)HID * HID, 0, head_split);
-    add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, tc_bwd ? head_split : 0, GP);
+    add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, head_pair ? head_split : 0, GP);
     add(lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_B1], 0, head_split);
     add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1], 0, GP);
     for (int e = 0; e < 2; ++e)        // shared launches: partial rows [0, split) belong to Encoder1, [split, GP) to Encoder2

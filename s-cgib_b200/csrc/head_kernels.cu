@@ -230,6 +230,14 @@ __device__ __forceinline__ void stv(float* p, const LaneVec<CPL>& a) {
   else *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[CPL - 2], a.v[CPL - 1]);
 }
 template <int CPL>
+__device__ __forceinline__ void stv_bf16(bf16_t* p, const LaneVec<CPL>& a) {      // round-to-nearest-even bf16 copy
+  uint32_t w0, w1;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(a.v[1]), "f"(a.v[0]));
+  if (CPL == 2) { *reinterpret_cast<uint32_t*>(p) = w0; return; }
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(a.v[CPL - 1]), "f"(a.v[CPL - 2]));
+  *reinterpret_cast<uint2*>(p) = make_uint2(w0, w1);
+}
+template <int CPL>
 __device__ __forceinline__ LaneVec<CPL> zerov() {
   LaneVec<CPL> r;
 #pragma unroll
@@ -346,6 +354,7 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
           }
         }
         stv<CPL>(p.noisy + (size_t)v * HID + c, z);
+        if (p.noisy_bf) stv_bf16<CPL>(p.noisy_bf + (size_t)v * HID + c, z);
         if (lane == 0) p.lam[v] = lam;
       }
     }
@@ -600,7 +609,8 @@ template <int HID, int HT> struct HeadFwdSmem { float tile[HT * (2 * HID + 4)]; 
 
 template <int HID, int HT>
 __device__ __forceinline__ void head_load_tile(float* tile, const float* __restrict__ noisy, const float* __restrict__ C,
-                                               const float* __restrict__ alpha, int base, int N, float* imap, float* aC) {
+                                               const float* __restrict__ alpha, int base, int N, float* imap, float* aC,
+                                               bf16_t* aC_bf) {
   constexpr int HLD = 2 * HID + 4, LPR = 2 * HID / 4;      // lanes per row of the [noisy || alpha C] tile (4 channels each)
   for (int i = threadIdx.x; i < HT * LPR; i += kThreads) {
     const int r = i / LPR, l = i % LPR;
@@ -614,6 +624,7 @@ __device__ __forceinline__ void head_load_tile(float* tile, const float* __restr
         const float4 cc = ld4(C + (size_t)v * HID + (l - LPR / 2) * 4);
         val = make_float4(al * cc.x, al * cc.y, al * cc.z, al * cc.w);
         if (aC) st4(aC + (size_t)v * HID + (l - LPR / 2) * 4, val);
+        if (aC_bf) st4a<true>(reinterpret_cast<float*>(aC_bf), (size_t)v * HID + (l - LPR / 2) * 4, val);
       }
       if (imap) st4(imap + (size_t)v * 2 * HID + l * 4, val);
     }
@@ -637,7 +648,7 @@ head_fwd_kernel(HeadFwdArgs p) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * HT;
     __syncthreads();
-    head_load_tile<HID, HT>(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap, p.aC);
+    head_load_tile<HID, HT>(sm.tile, p.noisy, p.C, p.alpha, base, p.N, p.imap, p.aC, p.aC_bf);
     __syncthreads();
     float acc[M::TM][4];
 #pragma unroll
@@ -649,7 +660,10 @@ head_fwd_kernel(HeadFwdArgs p) {
       const float4 rv = relu4(make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]));
       st4(sm.tile + (r0 + m) * GLD + c0, rv);
       const int v = base + r0 + m;
-      if (v < p.N) st4(p.r + (size_t)v * HID + c0, rv);
+      if (v < p.N) {
+        if (p.r) st4(p.r + (size_t)v * HID + c0, rv);
+        if (p.r_bf) st4a<true>(reinterpret_cast<float*>(p.r_bf), (size_t)v * HID + c0, rv);
+      }
     }
     __syncthreads();
 #pragma unroll

@@ -92,7 +92,8 @@ void launch_gin_bwd_main_tc2_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs
                                   bool weights_from_prev_kernel = false);
 int gin_bwd_pre_bf16_grid(int V, int hidden);
 void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, int hidden, cudaStream_t s);
-void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s);
+void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s,
+                              bool ga_f32 = false);      // ga_f32: g_a is written as fp32 also for kin == hidden (head backward)
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
 
 struct InputProjBwdArgs {
@@ -158,6 +159,7 @@ struct GraphGateFwdArgs {
                                          //  (normalise with the running statistics instead of the per-graph ones)
   float* cstat;                          // optional [B][2][HID] compressor-BN batch mean / unbiased var per graph
   float* kl;                             // [1] KL loss (last graph)
+  bf16_t* noisy_bf = nullptr;            // optional bf16 copy of noisy (bf16 mode: `a` operand of the head backward)
 };
 void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s);
 
@@ -193,8 +195,10 @@ struct HeadFwdArgs {
   float* imap;                           // optional [N][2*HID]
   float* aC;                             // optional [N][HID]: alpha*C, the second half of interaction_map (saved for the
                                          //  tensor-core head backward)
-  float* r;                              // [N][HID] saved
+  float* r;                              // [N][HID] saved (optional)
   float* Z;                              // [N][HID]
+  bf16_t* r_bf = nullptr;                // optional bf16 copies of r and alpha*C (bf16 mode: operands of the head backward)
+  bf16_t* aC_bf = nullptr;
 };
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s);
 
