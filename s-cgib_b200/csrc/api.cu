@@ -300,28 +300,36 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   if (b->recon_logm_steps > 0 && HID != 64 && !features_only) return SCGIB_E_SHAPE;   // --recons_type logM: hidden 64 only
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
-  // k-major weight copies for the forward GEMMs
+  // Parameter-only prologue, ONE launch: k-major weight copies for the FFMA forward GEMMs (the tensor-core GIN kernels read
+  // the natural layout: their copies are skipped), the head backward's operands (W1 halves, identity BN constants: the
+  // backward pass of the same step finds them in the workspace) and the input projection.
   {
-    TransposeJobs jobs;
+    FwdPrepArgs pa;
+    TransposeJobs& jobs = pa.jobs;
     jobs.n = 0;
     auto add = [&](const float* src, float* dst, int rows, int cols) { jobs.job[jobs.n++] = TransposeJob{src, dst, rows, cols}; };
-    for (int e = 0; e < 2; ++e)
-      for (int l = 0; l < L; ++l) {
-        add(params + lo.enc(e, l, L, SCGIB_ENC_W1), w.enc_w1t[e][l], HID, l == 0 ? DTR : HID);
-        add(params + lo.enc(e, l, L, SCGIB_ENC_W2), w.enc_w2t[e][l], HID, HID);
-        if (jobs.n >= 22) { launch_transposes(jobs, s); jobs.n = 0; }
-      }
+    const bool enc_ffma = !bf && !(tc64 && tensor_core_mode() != 0);
+    if (enc_ffma)
+      for (int e = 0; e < 2; ++e)
+        for (int l = 0; l < L; ++l) {
+          add(params + lo.enc(e, l, L, SCGIB_ENC_W1), w.enc_w1t[e][l], HID, l == 0 ? DTR : HID);
+          add(params + lo.enc(e, l, L, SCGIB_ENC_W2), w.enc_w2t[e][l], HID, HID);
+          if (jobs.n >= 20) { launch_transposes(jobs, s); jobs.n = 0; }
+        }
     add(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1t, HID, 2 * HID);
     add(params + lo.off[SCGIB_P_HEAD_W2], w.head_w2t, HID, HID);
     add(params + lo.off[SCGIB_P_COMP_W1], w.comp_w1t, HID, HID);
-    PROF("transpose_weights", launch_transposes(jobs, s));
+    pa.headW1 = params + lo.off[SCGIB_P_HEAD_W1]; pa.W1a = w.head_w1a; pa.W1b = w.head_w1b; pa.bn = w.head_bn; pa.cvec = w.head_cvec;
+    pa.hid = HID;
+    if (b->t_override && bf)
+      launch_f32_to_bf16(b->t_override, w.t, (size_t)b->N * DTR, s);
+    else if (b->t_override)
+      cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    else {
+      pa.x = b->x; pa.Wt = params + lo.off[SCGIB_P_TRANSFER]; pa.N = b->N; pa.F = d->in_dim; pa.normalize = b->normalize_x; pa.t = w.t;
+    }
+    PROF("fwd_prep", launch_fwd_prep(pa, s, bf));
   }
-  if (b->t_override && bf)
-    launch_f32_to_bf16(b->t_override, w.t, (size_t)b->N * DTR, s);
-  else if (b->t_override)
-    cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  else
-    PROF("input_proj_fwd", launch_input_proj_fwd(b->x, params + lo.off[SCGIB_P_TRANSFER], b->N, d->in_dim, b->normalize_x, w.t, s, bf));
   // the two GIN encoders (models.py:704, 707): layer l of Encoder1 and of Encoder2 are independent, so they share a launch
   for (int l = 0; l < L; ++l) {
     GinFwdArgs ga[2];
@@ -356,6 +364,8 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
         launch_bn_from_running(bn_running + (size_t)(e * L + l) * 2 * HID, params + lo.enc(e, l, L, SCGIB_ENC_GAMMA),
                                params + lo.enc(e, l, L, SCGIB_ENC_BETA), w.bn[e][l], HID, s);
   }
+  // forward tail on the tcgen05 contrastive launch: recon_reduce + compressor_ema as side CTAs, loss_finalize by its last CTA
+  const bool fuse_tail = !features_only && tc64 && use_tc_contrastive();
   {
     GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q, bf};
     PROF("gate_lin_fwd", launch_gate_lin_fwd(a, HID, s));
@@ -374,8 +384,12 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     a.gstat = w.gstat; a.cstat = (bn_running && !eval) ? w.cstat : nullptr; a.kl = w.kl;
     a.eval_running = eval ? bn_running + (size_t)2 * L * 2 * HID : nullptr;
     a.noisy_bf = w.noisy_bf;
+    if (!features_only) {      // the contrastive loss' row normalisation rides in the per-graph warps
+      a.z1 = w.z1; a.z2 = w.z2; a.n1 = w.n1; a.n2 = w.n2; a.diag = w.diag; a.zsplit = tc64 ? w.zsplit : nullptr;
+    }
     PROF("graph_gate_fwd", launch_graph_gate_fwd(a, HID, s));
-    if (bn_running && !eval) PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, HID, s));
+    if (bn_running && !eval && !fuse_tail)
+      PROF("compressor_ema", launch_compressor_ema(w.cstat, b->B, bn_running + (size_t)2 * L * 2 * HID, HID, s));
   }
   {
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
@@ -391,21 +405,22 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     const int grid = num_sms();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
     PROF("recon_fwd", launch_recon_fwd(a, HID, grid, s));
-    PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, HID, s));
+    if (!fuse_tail) PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, HID, s));
   }
   const int js = contrastive_jsplit(b->B);
   if (!features_only) {
-    NormalizeArgs a{w.core, w.readout, b->B, w.z1, w.z2, w.n1, w.n2, w.diag, tc64 ? w.zsplit : nullptr};
-    PROF("normalize", launch_normalize(a, HID, s));
     ContrastiveFwdArgs c{w.z1, w.z2, b->B, js, w.rowsum, w.zsplit};
-    if (tc64 && use_tc_contrastive())
-      PROF("contrastive_fwd_tc", launch_contrastive_fwd_tc(c, s));
-    else
+    LossFinalizeArgs fin{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses, HID};
+    if (fuse_tail) {
+      ConFwdSides sd;
+      if (logm <= 0) { sd.rpart = w.rpart; sd.rgrid = num_sms(); sd.G = w.G; sd.edge = w.edge; sd.n_reduce = 8; }
+      if (bn_running && !eval) { sd.cstat = w.cstat; sd.running = bn_running + (size_t)2 * L * 2 * HID; sd.n_ema = 1; }
+      sd.finalize = 1; sd.fin = fin; sd.counter = w.counters + 4;
+      PROF("contrastive_fwd_tc", launch_contrastive_fwd_tc_sides(c, sd, s));
+    } else {
       PROF("contrastive_fwd", launch_contrastive_fwd(c, HID, s));
-  }
-  if (!features_only) {
-    LossFinalizeArgs a{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses, HID};
-    PROF("loss_finalize", launch_loss_finalize(a, s));
+      PROF("loss_finalize", launch_loss_finalize(fin, s));
+    }
   }
   if (Z) cudaMemcpyAsync(Z, w.Z, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (noisy) cudaMemcpyAsync(noisy, w.noisy, (size_t)b->N * HID * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -458,18 +473,23 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     cudaMemsetAsync(w.g_core, 0, (size_t)b->B * HID * sizeof(float), s);
     cudaMemsetAsync(w.g_readout, 0, (size_t)b->B * HID * sizeof(float), s);
   } else {
+    // contrastive backward; its normalisation backward (contrastive_bwd_finalize) is fused into graph_gate_bwd below.  On the
+    // tcgen05 launch the adjacency-reconstruction backward rides along as side CTAs on the SMs the 128-row blocks leave idle.
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, b->B, js, w.g1p, w.g2p};
-    if (HID == 64 && use_tc_contrastive())
-      PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc(a, w.zsplit, s));
-    else
+    const bool con_tc = HID == 64 && use_tc_contrastive();
+    const bool logm = b->recon_logm_steps > 0;
+    ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+    if (con_tc) {
+      ConBwdSides sd;
+      if (!logm) { sd.recon = ra; sd.n_recon = max(1, num_sms() - ((b->B + 127) / 128) * js); }
+      PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc_sides(a, w.zsplit, sd, s));
+    } else {
       PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, HID, s));
-    ContrastiveBwdFinArgs f{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, b->B, js, s_con, w.g_core, w.g_readout};
-    PROF("contrastive_bwd_finalize", launch_contrastive_bwd_finalize(f, HID, s));
-    if (b->recon_logm_steps > 0) {
+    }
+    if (logm) {
       PROF("logm_bwd", launch_logm_bwd(w.Z, b->graph_ptr, b->indptr, b->indices, b->B, b->N, b->recon_logm_steps, w.logm_walks,
                                        s_rec, w.gZ, (int32_t*)(w.counters + 32), s));
-    } else {
-      ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+    } else if (!con_tc) {
       PROF("recon_bwd", launch_recon_bwd(ra, HID, s));
     }
   }
@@ -480,7 +500,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   const bool head_pair = tc_bwd || bf;         // one shared launch (CTAs split between the two K halves)
   const int head_split = head_pair ? pair_split(GP, (b->N + 127) / 128, (b->N + 127) / 128) : GP;
   {
-    PROF("head_bwd_prep", launch_head_bwd_prep(params + lo.off[SCGIB_P_HEAD_W1], w.head_w1a, w.head_w1b, w.head_bn, w.head_cvec, HID, s));
+    // (W1a / W1b / head_bn / head_cvec were prepared by the forward pass of this step: fwd_prep)
     if (bf) PROF("head_gz_bf16", launch_f32_to_bf16(w.gZ, w.gZ_bf, (size_t)b->N * HID, s));
     GinBwdMainArgs m[2];
     for (int h = 0; h < 2; ++h) {
@@ -500,7 +520,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       }
       PROF("head_bwd_bf16", launch_gin_bwd_main_bf16(m[0], &m[1], HID, HID, GP, s, true));
     } else if (tc_bwd) {
-      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s, true));   // W1a / W1b come from head_bwd_prep
+      PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
     } else {
       PROF("head_bwd_ffma.a", launch_gin_bwd_main(m[0], HID, HID, GP, s));
       PROF("head_bwd_ffma.b", launch_gin_bwd_main(m[1], HID, HID, GP, s));   // rewrites the (identical) dW2 / bias partials of .a
@@ -514,6 +534,10 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     a.feat_u = b->feat_u; a.lam = w.lam; a.alpha = w.alpha; a.gstat = w.gstat;
     a.gI = w.gI; a.gI2 = w.gI + (size_t)b->N * HID; a.gI_stride = HID;      // dense halves [N][H] | [N][H]
     a.g_core = w.g_core; a.g_readout = w.g_readout; a.kl_scale = s_kl;
+    if (!gZ_ext) {
+      a.con_g1p = w.g1p; a.con_g2p = w.g2p; a.con_z1 = w.z1; a.con_z2 = w.z2; a.con_n1 = w.n1; a.con_n2 = w.n2;
+      a.con_jsplit = js; a.con_scale = s_con;
+    }
     a.gp = w.gp; a.g_q = w.g_q; a.gH = w.gH; a.gC = w.gC;
     a.part = w.small_part; a.counter = w.counters + 1;
     a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
@@ -578,9 +602,12 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     r.n = 0;
     auto add = [&](int64_t off, int64_t len, int c0, int c1) { r.off[r.n] = off; r.len[r.n] = len; r.c0[r.n] = c0; r.c1[r.n] = c1; ++r.n; };
     // shared tcgen05 launch: partial rows [0, head_split) = problem 0 (dW1a and everything else), [head_split, GP) = problem 1
-    // (dW1b); FFMA: two launches, every partial row holds both
+    // (dW1b); FFMA: two launches, every partial row holds both.  The partial slot holds [dW1a | dW1b] ([2][H][H]); the
+    // reduction writes them interleaved as the parameter's [H][2H] layout.
     add(lo.off[SCGIB_P_HEAD_W1], (int64_t)HID * HID, 0, head_split);
+    r.dst[r.n - 1] = lo.off[SCGIB_P_HEAD_W1]; r.ilv[r.n - 1] = HID;
     add(lo.off[SCGIB_P_HEAD_W1] + (int64_t)HID * HID, (int64_t)HID * HID, head_pair ? head_split : 0, GP);
+    r.dst[r.n - 1] = lo.off[SCGIB_P_HEAD_W1] + HID; r.ilv[r.n - 1] = HID;
     add(lo.off[SCGIB_P_HEAD_B1], lo.off[SCGIB_P_HEAD_B2] + HID - lo.off[SCGIB_P_HEAD_B1], 0, head_split);
     add(lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1] + HID - lo.off[SCGIB_P_COMP_W1], 0, GP);
     for (int e = 0; e < 2; ++e)        // shared launches: partial rows [0, split) belong to Encoder1, [split, GP) to Encoder2
@@ -588,7 +615,6 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
         add(lo.enc(e, l, L, SCGIB_ENC_W1), lo.enc(e, l, L, SCGIB_ENC_B2) + HID - lo.enc(e, l, L, SCGIB_ENC_W1),
             pair_main ? (e == 0 ? 0 : enc_split) : 0, pair_main ? (e == 0 ? enc_split : GP) : GP);
     PROF("reduce_partials", launch_reduce_partials(w.ppart, lo.total, GP, r, grads, s));
-    PROF("head_dw1_interleave", launch_head_dw1_interleave(grads + lo.off[SCGIB_P_HEAD_W1], HID, s));
   }
   return (int)cudaGetLastError();
 }

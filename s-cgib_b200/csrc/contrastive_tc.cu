@@ -8,6 +8,7 @@
 // exp / row-sum epilogue of block t (tcgen05.ld) overlap.
 #include "kernels.cuh"
 #include "umma.cuh"
+#include "side_jobs.cuh"
 
 namespace scgib {
 using namespace umma;
@@ -37,10 +38,28 @@ __device__ __forceinline__ void cp_async_tile_g(unsigned char* dst, const float*
   }
 }
 
+// Grid: CTAs [0, iblocks * jsplit) are the similarity CTAs (row block b % iblocks, column split b / iblocks); the CTAs
+// after them run the side jobs of ConFwdSides (recon_reduce, then compressor_ema); the CTA that finishes last runs
+// loss_finalize when sd.finalize is set.
+__device__ __forceinline__ void con_fwd_finish(const ConFwdSides& sd) {
+  if (!sd.finalize) return;
+  if (!last_cta_arrives(sd.counter)) return;
+  loss_finalize_body<kThreads>(sd.fin);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
+contrastive_fwd_tc_kernel(ContrastiveFwdArgs p, ConFwdSides sd, int iblocks) {
   pdl_sync();
   extern __shared__ __align__(1024) unsigned char smem[];
+  const int nmain = iblocks * p.jsplit;
+  if ((int)blockIdx.x >= nmain) {
+    const int side = (int)blockIdx.x - nmain;
+    if (side < sd.n_reduce) recon_reduce_body(sd.rpart, sd.rgrid, sd.G, sd.edge, HID, side, sd.n_reduce);
+    else compressor_ema_body<HID, kThreads>(sd.cstat, p.B, sd.running);
+    con_fwd_finish(sd);
+    return;
+  }
+  const int bx = (int)blockIdx.x % iblocks, by = (int)blockIdx.x / iblocks, gy = p.jsplit;
   unsigned char* zi_hi = smem + ConTcLayout::off_zi;
   unsigned char* zi_lo = zi_hi + ZI_BYTES;
   unsigned char* zj = smem + ConTcLayout::off_zj;
@@ -52,10 +71,10 @@ contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
   const float* z2h = z1l + (size_t)p.B * HID;
   const float* z2l = z2h + (size_t)p.B * HID;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ibase = blockIdx.x * CI;
+  const int ibase = bx * CI;
   const int jblocks = (p.B + CJ - 1) / CJ;
-  const int nblk = (jblocks - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;   // blocks of this CTA
-  auto jb_of = [&](int t) { return (int)blockIdx.y + t * (int)gridDim.y; };
+  const int nblk = (jblocks - by + gy - 1) / gy;   // blocks of this CTA
+  auto jb_of = [&](int t) { return by + t * gy; };
   auto load_j = [&](int t) {
     unsigned char* buf = zj + (t & 1) * 4 * ZJ_BYTES;
     const int jbase = jb_of(t) * CJ;
@@ -136,10 +155,11 @@ contrastive_fwd_tc_kernel(ContrastiveFwdArgs p) {
   s_rs[(warp >> 2) * CI + row] = rs;
   __syncthreads();
   if (threadIdx.x < CI && ibase + threadIdx.x < p.B)
-    p.rowsum[(size_t)blockIdx.y * p.B + ibase + threadIdx.x] = s_rs[threadIdx.x] + s_rs[CI + threadIdx.x];
+    p.rowsum[(size_t)by * p.B + ibase + threadIdx.x] = s_rs[threadIdx.x] + s_rs[CI + threadIdx.x];
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
+  con_fwd_finish(sd);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,10 +198,16 @@ __device__ __forceinline__ void cp_async_tile_s(unsigned char* dst, const float*
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit) {
+contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit, ConBwdSides sd, int iblocks) {
   pdl_sync();
   using L = ConBwdTcLayout;
   extern __shared__ __align__(1024) unsigned char smem[];
+  const int nmain = iblocks * p.jsplit;
+  if ((int)blockIdx.x >= nmain) {          // side CTAs: the adjacency-reconstruction backward (independent of this kernel's work)
+    recon_bwd_body<HID>(sd.recon, smem, (int)blockIdx.x - nmain, sd.n_recon);
+    return;
+  }
+  const int bx = (int)blockIdx.x % iblocks, by = (int)blockIdx.x / iblocks, gy = p.jsplit;
   unsigned char* zi_hi = smem + L::off_zi;
   unsigned char* zi_lo = zi_hi + ZI_BYTES;
   unsigned char* zj = smem + L::off_zj;
@@ -192,10 +218,10 @@ contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit
   const size_t n = (size_t)p.B * HID;
   const float *z1h = zsplit, *z1l = zsplit + n, *z2h = zsplit + 2 * n, *z2l = zsplit + 3 * n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ibase = blockIdx.x * CI;
+  const int ibase = bx * CI;
   const int jblocks = (p.B + CJ - 1) / CJ;
-  const int nblk = (jblocks - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
-  auto jb_of = [&](int t) { return ((int)blockIdx.y + t * (int)gridDim.y) * CJ; };
+  const int nblk = (jblocks - by + gy - 1) / gy;
+  auto jb_of = [&](int t) { return (by + t * gy) * CJ; };
 
   if (warp == 0) tmem_alloc(s_tmem, 512);
   if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1); }
@@ -334,7 +360,7 @@ contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit
       cp_async_commit();
     }
     // ---- result rows of this mode: acc = columns 0..63 + columns 64..127
-    float* out = (mode1 ? p.g2p : p.g1p) + (size_t)blockIdx.y * p.B * HID;
+    float* out = (mode1 ? p.g2p : p.g1p) + (size_t)by * p.B * HID;
     if (nblk > 0) {
       wait_pv();
       float a0[32], a1[32];
@@ -363,20 +389,28 @@ contrastive_bwd_tc_kernel(ContrastiveBwdArgs p, const float* __restrict__ zsplit
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s) {
+static_assert(ConBwdTcLayout::total >= (int)sizeof(ReconBwdSmem<HID>), "recon_bwd side CTAs use the contrastive kernel's shared memory");
+
+void launch_contrastive_fwd_tc_sides(const ContrastiveFwdArgs& a, const ConFwdSides& sides, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(contrastive_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ConTcLayout::total), true);
   (void)once;
-  dim3 grid((a.B + CI - 1) / CI, a.jsplit);
-  launch_k((contrastive_fwd_tc_kernel), dim3(grid), dim3(kThreads), ConTcLayout::total, s, a);
+  const int iblocks = (a.B + CI - 1) / CI;
+  const int grid = iblocks * a.jsplit + sides.n_reduce + sides.n_ema;
+  launch_k((contrastive_fwd_tc_kernel), dim3(grid), dim3(kThreads), ConTcLayout::total, s, a, sides, iblocks);
 }
+void launch_contrastive_fwd_tc(const ContrastiveFwdArgs& a, cudaStream_t s) { launch_contrastive_fwd_tc_sides(a, ConFwdSides{}, s); }
 
-void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s) {
+void launch_contrastive_bwd_tc_sides(const ContrastiveBwdArgs& a, const float* zsplit, const ConBwdSides& sides, cudaStream_t s) {
   static bool once = (cudaFuncSetAttribute(contrastive_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ConBwdTcLayout::total), true);
   (void)once;
-  dim3 grid((a.B + CI - 1) / CI, a.jsplit);
-  launch_k((contrastive_bwd_tc_kernel), dim3(grid), dim3(kThreads), ConBwdTcLayout::total, s, a, zsplit);
+  const int iblocks = (a.B + CI - 1) / CI;
+  const int grid = iblocks * a.jsplit + sides.n_recon;
+  launch_k((contrastive_bwd_tc_kernel), dim3(grid), dim3(kThreads), ConBwdTcLayout::total, s, a, zsplit, sides, iblocks);
+}
+void launch_contrastive_bwd_tc(const ContrastiveBwdArgs& a, const float* zsplit, cudaStream_t s) {
+  launch_contrastive_bwd_tc_sides(a, zsplit, ConBwdSides{}, s);
 }
 
 }  // namespace scgib

@@ -52,6 +52,66 @@ void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int no
   else launch_k((input_proj_fwd_kernel<false>), dim3(grid), dim3(kThreads), 0, s, x, Wt, N, F, normalize, t);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The parameter-only prologue of a step in ONE launch (three independent jobs, CTA ranges): input projection
+// (CTAs [0, nproj)), the k-major weight copies of the FFMA kernels (one CTA per job) and the head backward's operand
+// preparation (8 CTAs: W1a = W1[:, :H], W1b = W1[:, H:], identity BatchNorm-backward constants).
+// ------------------------------------------------------------------------------------------------
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(kThreads) fwd_prep_kernel(FwdPrepArgs p) {
+  pdl_sync();
+  __shared__ __align__(16) float s_w[32 * DTR];  // [f][o]
+  const int b = (int)blockIdx.x;
+  if (b < p.nproj) {
+    const int F = p.F;
+    for (int i = threadIdx.x; i < F * DTR; i += kThreads) {
+      const int o = i / F, f = i % F;
+      s_w[f * DTR + o] = p.Wt[i];
+    }
+    __syncthreads();
+    const int q = threadIdx.x & 7;  // output quad
+    for (int v = b * (kThreads / 8) + (threadIdx.x >> 3); v < p.N; v += p.nproj * (kThreads / 8)) {
+      const float* xr = p.x + (size_t)v * F;
+      float ss = 0.f;
+      for (int f = 0; f < F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
+      const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+      float4 acc = make4(0.f);
+      for (int f = 0; f < F; ++f) {
+        const float a = __ldg(xr + f) * inv;
+        const float4 w = ld4(s_w + f * DTR + q * 4);
+        acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
+      }
+      st4a<OUT_BF16>(p.t, (size_t)v * DTR + q * 4, acc);
+    }
+    return;
+  }
+  if (b < p.nproj + p.jobs.n) {
+    const TransposeJob j = p.jobs.job[b - p.nproj];
+    for (int i = threadIdx.x; i < j.rows * j.cols; i += kThreads) {
+      const int c = i / j.rows, r = i % j.rows;   // consecutive threads write consecutive dst elements
+      j.dst[(size_t)c * j.rows + r] = __ldg(j.src + (size_t)r * j.cols + c);
+    }
+    return;
+  }
+  const int hb = b - p.nproj - p.jobs.n, H = p.hid;      // head backward prep, 8 CTAs
+  for (int i = hb * kThreads + threadIdx.x; i < H * 2 * H; i += 8 * kThreads) {
+    const int o = i / (2 * H), k = i % (2 * H);
+    const float w = __ldg(p.headW1 + i);
+    if (k < H) p.W1a[o * H + k] = w; else p.W1b[o * H + k - H] = w;
+  }
+  if (hb == 0) {
+    for (int i = threadIdx.x; i < 4 * H; i += kThreads) p.bn[i] = (i >= H && i < 3 * H) ? 1.f : 0.f;   // mean 0, rstd 1, gamma 1, beta 0
+    for (int i = threadIdx.x; i < 2 * H; i += kThreads) p.cvec[i] = 0.f;
+  }
+}
+void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16) {
+  a.nproj = a.x ? min((a.N + 31) / 32, 148 * 8) : 0;
+  const int grid = a.nproj + a.jobs.n + (a.headW1 ? 8 : 0);
+  if (grid == 0) return;
+  if (out_bf16) launch_k((fwd_prep_kernel<true>), dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k((fwd_prep_kernel<false>), dim3(grid), dim3(kThreads), 0, s, a);
+}
+
 __global__ void __launch_bounds__(kThreads) f32_to_bf16_kernel(const float* __restrict__ in, bf16_t* __restrict__ out, size_t n4) {
   pdl_sync();
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads)

@@ -8,6 +8,7 @@
 //   attention (Python loop)               models.py:738-749
 //   self.MLP(interaction_map)             models.py:569-572, 676
 #include "kernels.cuh"
+#include "side_jobs.cuh"
 
 namespace scgib {
 
@@ -246,6 +247,11 @@ __device__ __forceinline__ LaneVec<CPL> zerov() {
 }
 
 constexpr float kKlEps = 0.0000001f;   // models.py:632
+__device__ __forceinline__ float tf32_rna_f(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 
 template <int HID, int RB>      // RB rows in flight per warp in the gate pass (4 for molecule-sized graphs, 8 for ~150-node graphs)
 __global__ void __launch_bounds__(kThreads)
@@ -359,6 +365,32 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
       }
     }
     stv<CPL>(p.core + (size_t)g * HID + c, core);
+    if (p.z1) {
+      // the contrastive loss' row normalisation (models.py:606-610, F.normalize) of this graph's two readouts, fused here:
+      // z1 = core / max(||core||, 1e-12), z2 = readout / max(||readout||, 1e-12), diag = z1 . z2, tf32 hi / lo copies
+      float qa = 0.f, qb = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { qa = fmaf(core.v[k], core.v[k], qa); qb = fmaf(sH.v[k], sH.v[k], qb); }
+      const float na = fmaxf(sqrtf(warp_sum(qa)), 1e-12f), nb = fmaxf(sqrtf(warp_sum(qb)), 1e-12f);
+      V za, zb;
+      float dd = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { za.v[k] = core.v[k] / na; zb.v[k] = sH.v[k] / nb; dd = fmaf(za.v[k], zb.v[k], dd); }
+      const size_t o = (size_t)g * HID + c;
+      stv<CPL>(p.z1 + o, za); stv<CPL>(p.z2 + o, zb);
+      if (p.zsplit) {
+        const size_t nn = (size_t)p.B * HID;
+        V ah, al, bh, bl;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          ah.v[k] = tf32_rna_f(za.v[k]); al.v[k] = tf32_rna_f(za.v[k] - ah.v[k]);
+          bh.v[k] = tf32_rna_f(zb.v[k]); bl.v[k] = tf32_rna_f(zb.v[k] - bh.v[k]);
+        }
+        stv<CPL>(p.zsplit + o, ah); stv<CPL>(p.zsplit + nn + o, al); stv<CPL>(p.zsplit + 2 * nn + o, bh); stv<CPL>(p.zsplit + 3 * nn + o, bl);
+      }
+      dd = warp_sum(dd);
+      if (lane == 0) { p.n1[g] = na; p.n2[g] = nb; p.diag[g] = dd; }
+    }
     if (last) {
       float a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -388,35 +420,12 @@ void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s
   }
 }
 
-// running stats of the compressor BN after B sequential per-graph updates (closed form, fixed order)
-// r_B = 0.9^B r_0 + sum_g 0.1 * 0.9^(B-1-g) stat_g ; graphs older than kEmaWindow contribute < 0.9^768 ~ 1e-35.
-constexpr int kEmaWindow = 768;
+// running stats of the compressor BN after B sequential per-graph updates: compressor_ema_body (side_jobs.cuh)
 template <int HID>
 __global__ void __launch_bounds__(1024)
 compressor_ema_kernel(const float* __restrict__ cstat, int B, float* __restrict__ running) {
   pdl_sync();
-  constexpr int kEmaSeg = 1024 / (2 * HID);     // 8 segments at HID = 64, 4 at HID = 128
-  __shared__ double s_part[kEmaSeg][2 * HID];
-  const int j = threadIdx.x % (2 * HID);  // 0..H-1 mean, H..2H-1 var
-  const int seg = threadIdx.x / (2 * HID);
-  const int g0 = B > kEmaWindow ? B - kEmaWindow : 0;
-  // newest graph first: weight 0.1 * 0.9^k for age k = B-1-g, advanced by a constant factor (two pow() per thread
-  // instead of one per term: the fp64 pow dominated this kernel)
-  double acc = 0.0;
-  double w = 0.1 * pow(0.9, (double)seg);
-  const double step = pow(0.9, (double)kEmaSeg);
-  for (int g = B - 1 - seg; g >= g0; g -= kEmaSeg) {
-    acc += w * (double)cstat[(size_t)g * 2 * HID + j];
-    w *= step;
-  }
-  s_part[seg][j] = acc;
-  __syncthreads();
-  if (seg == 0) {
-    double r = pow(0.9, (double)B) * (double)running[j];
-#pragma unroll
-    for (int k = 0; k < kEmaSeg; ++k) r += s_part[k][j];
-    running[j] = (float)r;
-  }
+  compressor_ema_body<HID, 1024>(cstat, B, running);
 }
 void launch_compressor_ema(const float* cstat, int B, float* running, int hidden, cudaStream_t s) {
   if (hidden == 64) launch_k((compressor_ema_kernel<64>), dim3(1), dim3(1024), 0, s, cstat, B, running);
@@ -447,7 +456,31 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
     const float n = (float)(v1 - v0);
     const float* gs = p.gstat + (size_t)g * 4 * HID;
     const V muH = ldv<CPL>(gs + c), sd = ldv<CPL>(gs + HID + c), muQ = ldv<CPL>(gs + 2 * HID + c), rstd = ldv<CPL>(gs + 3 * HID + c);
-    const V gcore = ldv<CPL>(p.g_core + (size_t)g * HID + c), gread = ldv<CPL>(p.g_readout + (size_t)g * HID + c);
+    V gcore, gread;
+    if (p.con_g1p) {
+      // (g - z_hat (z_hat . g)) / max(||z||, 1e-12) with g = scale / B * (sum of the column-split partials - the other view's z_hat)
+      const size_t o = (size_t)g * HID + c;
+      V g1 = zerov<CPL>(), g2 = zerov<CPL>();
+      for (int js = 0; js < p.con_jsplit; ++js) {
+        const V a = ldv<CPL>(p.con_g1p + (size_t)js * p.B * HID + o), bb = ldv<CPL>(p.con_g2p + (size_t)js * p.B * HID + o);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { g1.v[k] += a.v[k]; g2.v[k] += bb.v[k]; }
+      }
+      const V z1 = ldv<CPL>(p.con_z1 + o), z2 = ldv<CPL>(p.con_z2 + o);
+      const float kk = p.con_scale / (float)p.B;
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        g1.v[k] = kk * (g1.v[k] - z2.v[k]); g2.v[k] = kk * (g2.v[k] - z1.v[k]);
+        t1 = fmaf(z1.v[k], g1.v[k], t1); t2 = fmaf(z2.v[k], g2.v[k], t2);
+      }
+      const float d1 = warp_sum(t1), d2 = warp_sum(t2);
+      const float n1 = __ldg(p.con_n1 + g), n2 = __ldg(p.con_n2 + g);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { gcore.v[k] = (g1.v[k] - z1.v[k] * d1) / n1; gread.v[k] = (g2.v[k] - z2.v[k] * d2) / n2; }
+    } else {
+      gcore = ldv<CPL>(p.g_core + (size_t)g * HID + c); gread = ldv<CPL>(p.g_readout + (size_t)g * HID + c);
+    }
     const bool last = (g == p.B - 1) && (p.kl_scale != 0.f);
     V isd;
 #pragma unroll

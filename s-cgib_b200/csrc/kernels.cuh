@@ -16,6 +16,15 @@ void launch_transposes(const TransposeJobs& jobs, cudaStream_t s);
 void launch_bn_from_running(const float* running, const float* gamma, const float* beta, float* bn, int hidden, cudaStream_t s);
 void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int normalize, float* t, cudaStream_t s, bool out_bf16 = false);
 void launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
+// input projection + weight transposes + head-backward operand preparation in one launch (any part optional:
+// x == nullptr, jobs.n == 0, headW1 == nullptr)
+struct FwdPrepArgs {
+  TransposeJobs jobs;
+  const float* headW1 = nullptr; float *W1a = nullptr, *W1b = nullptr, *bn = nullptr, *cvec = nullptr; int hid = 64;
+  const float* x = nullptr; const float* Wt = nullptr; int N = 0, F = 0, normalize = 0; float* t = nullptr;
+  int nproj = 0;                       // set by the launcher
+};
+void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16);
 
 struct GinFwdArgs {
   const float* in;          // [*, KIN]  t (layer 0) or the previous layer's pre-BN output y
@@ -160,6 +169,9 @@ struct GraphGateFwdArgs {
   float* cstat;                          // optional [B][2][HID] compressor-BN batch mean / unbiased var per graph
   float* kl;                             // [1] KL loss (last graph)
   bf16_t* noisy_bf = nullptr;            // optional bf16 copy of noisy (bf16 mode: `a` operand of the head backward)
+  // optional (z1 != nullptr): the contrastive loss' row normalisation fused into the per-graph warp (normalize_kernel's
+  // outputs: z1 = core / max(||core||, 1e-12), z2 = readout / ..., norms, diag = z1 . z2, tf32 hi/lo copies)
+  float *z1 = nullptr, *z2 = nullptr, *n1 = nullptr, *n2 = nullptr, *diag = nullptr, *zsplit = nullptr;
 };
 void launch_graph_gate_fwd(const GraphGateFwdArgs& a, int hidden, cudaStream_t s);
 
@@ -185,6 +197,10 @@ struct GraphGateBwdArgs {
   float* part;                           // [grid][5*HID]: dgamma_c, dbeta_c, dwc2, dw_cand, (dbc2 at [4*HID])
   unsigned int* counter;
   float *d_gamma_c, *d_beta_c, *d_wc2, *d_bc2, *d_attn_w, *d_attn_b;   // final gradients
+  // optional (con_g1p != nullptr): contrastive_bwd_finalize fused into the per-graph warp - g_core / g_readout are formed
+  // from the contrastive kernel's column-split partials [con_jsplit][B][HID] (g_core / g_readout above are then unused)
+  const float *con_g1p = nullptr, *con_g2p = nullptr, *con_z1 = nullptr, *con_z2 = nullptr, *con_n1 = nullptr, *con_n2 = nullptr;
+  int con_jsplit = 0; float con_scale = 0.f;
 };
 void launch_graph_gate_bwd(const GraphGateBwdArgs& a, int hidden, cudaStream_t s);
 
@@ -262,8 +278,26 @@ struct LossFinalizeArgs {
 };
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s);
 
+// Horizontal fusion of the step's small serial jobs: the tcgen05 contrastive kernels run one CTA per SM on 128-row blocks
+// and leave SMs idle (128 of 148 CTAs at B = 4096), so independent latency-bound jobs of the same phase ride along as
+// EXTRA CTAs of those launches (side_jobs.cuh) instead of paying a launch + drain each:
+//   forward : recon_reduce (n_reduce CTAs), compressor_ema (n_ema = 0 | 1 CTA), and loss_finalize run by whichever CTA
+//             of the launch finishes last (`counter`, self-resetting);
+//   backward: recon_bwd (n_recon CTAs walking all row tiles).
+constexpr int kConSideCtas = 12;          // SMs contrastive_jsplit() leaves to the side jobs
+struct ConFwdSides {
+  const float* rpart = nullptr; int rgrid = 0; float* G = nullptr; float* edge = nullptr; int n_reduce = 0;
+  const float* cstat = nullptr; float* running = nullptr; int n_ema = 0;
+  int finalize = 0; LossFinalizeArgs fin; unsigned int* counter = nullptr;
+};
+struct ConBwdSides { int n_recon = 0; ReconBwdArgs recon; };
+void launch_contrastive_fwd_tc_sides(const ContrastiveFwdArgs& a, const ConFwdSides& sides, cudaStream_t s);
+void launch_contrastive_bwd_tc_sides(const ContrastiveBwdArgs& a, const float* zsplit, const ConBwdSides& sides, cudaStream_t s);
+
 // grads[off..off+len) = sum_c part[c*pstride + off + i] for each listed range
-struct ReduceRanges { int64_t off[40]; int64_t len[40]; int c0[40]; int c1[40]; int n; };   // partial rows [c0, c1) hold the range
+// partial rows [c0, c1) hold the range; ilv > 0: element i of the range goes to dst + (i / ilv) * 2 * ilv + i % ilv instead of
+// off + i (the head MLP's dW1 halves [2][H][H] -> [H][2H]: the former head_dw1_interleave kernel)
+struct ReduceRanges { int64_t off[40]; int64_t len[40]; int c0[40]; int c1[40]; int64_t dst[40] = {}; int ilv[40] = {}; int n; };
 void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
                             cudaStream_t s);
 

@@ -9,10 +9,11 @@
 //   loss = KL + recon + contrastive     exp_pretraining.py:321
 //   torch.optim.Adam(lr, wd=5e-5)       exp_pretraining.py:86, 112, 323
 #include "kernels.cuh"
+#include "side_jobs.cuh"
 
 namespace scgib {
 
-constexpr int GT = 128;
+constexpr int GT = kReconTile;
 constexpr int CT = 64;   // contrastive tile
 
 // ------------------------------------------------------------------------------------------------
@@ -80,60 +81,19 @@ void launch_recon_fwd(const ReconFwdArgs& a, int hidden, int grid, cudaStream_t 
 __global__ void __launch_bounds__(kThreads)
 recon_reduce_kernel(const float* __restrict__ part, int grid, float* __restrict__ G, float* __restrict__ edge_sum, int HID) {
   pdl_sync();
-  const int j = blockIdx.x * kThreads + threadIdx.x;
-  if (j > HID * HID) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // interleaved partial sums: independent loads in flight, fixed order
-  const size_t ST = (size_t)HID * HID + 4;
-  int c = 0;
-#pragma unroll 4
-  for (; c + 3 < grid; c += 4) {
-    s0 += (double)part[(size_t)c * ST + j]; s1 += (double)part[(size_t)(c + 1) * ST + j];
-    s2 += (double)part[(size_t)(c + 2) * ST + j]; s3 += (double)part[(size_t)(c + 3) * ST + j];
-  }
-  for (; c < grid; ++c) s0 += (double)part[(size_t)c * ST + j];
-  const double s = (s0 + s1) + (s2 + s3);
-  if (j < HID * HID) G[j] = (float)s; else edge_sum[0] = (float)s;
+  recon_reduce_body(part, grid, G, edge_sum, HID, (int)blockIdx.x, (int)gridDim.x);
 }
 void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum, int hidden, cudaStream_t s) {
   launch_k((recon_reduce_kernel), dim3((hidden * hidden + 1 + kThreads - 1) / kThreads), dim3(kThreads), 0, s, part, grid, G, edge_sum, hidden);
 }
 
 // recon backward: gZ = scale * (4/N) * (Z G - A Z)
-template <int HID> struct ReconBwdSmem { float z[GT * (HID + 4)]; float g[HID * HID]; };
-
 template <int HID>
 __global__ void __launch_bounds__(kThreads, HID == 64 ? 2 : 1)
 recon_bwd_kernel(ReconBwdArgs p) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ReconBwdSmem<HID>& sm = *reinterpret_cast<ReconBwdSmem<HID>*>(smem_raw);
-  constexpr int GLD = HID + 4;
-  using M = NNMap<GT, HID>;
-  load_matrix<HID>(sm.g, HID, p.G, HID);
-  const float k = p.scale * 4.f / (float)p.N;
-  const int n_tiles = (p.N + GT - 1) / GT;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int base = tile * GT;
-    __syncthreads();
-    load_row_tile<GT, HID>(sm.z, GLD, p.Z, base, p.N);
-    __syncthreads();
-    float acc[M::TM][4];
-#pragma unroll
-    for (int m = 0; m < M::TM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-    gemm_nn<GT, HID, HID>(sm.z, GLD, sm.g, HID, acc);
-    const int c0 = M::col0(), r0 = M::row0();
-#pragma unroll
-    for (int m = 0; m < M::TM; ++m) {
-      const int v = base + r0 + m;
-      if (v < p.N) {
-        float4 nb = make4(0.f);
-        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
-        for (int e = e0; e < e1; ++e) nb = add4(nb, ld4(p.Z + (size_t)__ldg(p.indices + e) * HID + c0));
-        st4(p.gZ + (size_t)v * HID + c0,
-            make_float4(k * (acc[m][0] - nb.x), k * (acc[m][1] - nb.y), k * (acc[m][2] - nb.z), k * (acc[m][3] - nb.w)));
-      }
-    }
-  }
+  recon_bwd_body<HID>(p, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
 template <int H>
 static void launch_recon_bwd_t(const ReconBwdArgs& a, cudaStream_t s) {
@@ -209,7 +169,7 @@ int contrastive_jsplit(int B) {
   // The tcgen05 kernels (contrastive_tc.cu) run one CTA per SM on 128-row blocks: split the column range so that
   // (row blocks) x (splits) fills the SMs in a single wave.  The FFMA kernels (64-row blocks, 2 CTAs per SM) accept the same value.
   const int iblocks = (B + 127) / 128;
-  int js = num_sms() / iblocks;
+  int js = (num_sms() - kConSideCtas) / iblocks;     // kConSideCtas SMs stay free for the side jobs of those launches
   const int jblocks = (B + CT - 1) / CT;
   if (js > jblocks) js = jblocks;
   if (js < 1) js = 1;
@@ -422,29 +382,7 @@ constexpr int kFin = 1024;     // one CTA; latency-bound (B rows x jsplit depend
 __global__ void __launch_bounds__(kFin)
 loss_finalize_kernel(LossFinalizeArgs p) {
   pdl_sync();
-  __shared__ double s_a[kFin], s_b[kFin];
-  double con = 0.0, fro = 0.0;
-  for (int i = threadIdx.x; i < p.B; i += kFin) {
-    float d = 0.f;
-    for (int js = 0; js < p.jsplit; ++js) d += p.rowsum[(size_t)js * p.B + i];
-    p.D[i] = d;
-    con += (double)(logf(d) - p.diag[i]);      // -log(exp(s_b(i,i)) / D_i)
-  }
-  if (!p.recon_override)
-    for (int j = threadIdx.x; j < p.hidden * p.hidden; j += kFin) { const double g = (double)p.G[j]; fro += g * g; }
-  s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
-  __syncthreads();
-  for (int o = kFin / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const float kl = p.kl[0];
-    const float c = (float)(s_a[0] / (double)p.B);
-    const float r = p.recon_override ? p.recon_override[0]
-                                     : (float)((s_b[0] - 2.0 * (double)p.edge_sum[0] + (double)p.E) / (double)p.N);
-    p.losses[0] = kl; p.losses[1] = c; p.losses[2] = r; p.losses[3] = kl + r + c;
-  }
+  loss_finalize_body<kFin>(p);
 }
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t s) { launch_k((loss_finalize_kernel), dim3(1), dim3(kFin), 0, s, a); }
 
@@ -470,7 +408,10 @@ reduce_partials_kernel(const float* __restrict__ part, int64_t pstride, int npar
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (sub == 0 && i < len) grads[off + i] = (float)s;
+    if (sub == 0 && i < len) {
+      const int ilv = r.ilv[blockIdx.y];
+      grads[ilv > 0 ? r.dst[blockIdx.y] + (i / ilv) * 2 * ilv + i % ilv : off + i] = (float)s;
+    }
   }
 }
 void launch_reduce_partials(const float* part, int64_t pstride, int nparts, const ReduceRanges& r, float* grads,
