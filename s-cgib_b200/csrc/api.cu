@@ -31,8 +31,14 @@ int bwd_tensor_core_mode() {
   if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
   return g_bwd_tc;
 }
+static int g_fwd4 = -1;
+int fwd_tc4_mode() {
+  if (g_fwd4 < 0) { const char* e = getenv("SCGIB_FWD4"); g_fwd4 = (e && e[0] == '1') ? 1 : 0; }
+  return g_fwd4;
+}
 static void launch_gin_fwd_any(const GinFwdArgs& a, int kin, cudaStream_t s) {      // op-level entry: hidden 64
   if (tensor_core_mode() == 0) launch_gin_fwd(a, kin, HID, s);
+  else if (kin == HID && !a.row_map && fwd_tc4_mode()) launch_gin_fwd_tc4(a, s);
   else launch_gin_fwd_tc3(a, kin, s);
 }
 
@@ -355,7 +361,8 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     if (bf) {
       PROF("gin_fwd_bf16.enc1+2", launch_gin_fwd_bf16(ga[0], &ga[1], kin, HID, s));
     } else if (tc64 && tensor_core_mode() != 0) {
-      PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
+      if (kin == HID && fwd_tc4_mode()) PROF("gin_fwd_tc4.enc1+2", launch_gin_fwd_tc4_pair(ga[0], ga[1], s));
+      else PROF("gin_fwd_tc.enc1+2", launch_gin_fwd_tc3_pair(ga[0], ga[1], kin, s));
     } else {
       for (int e = 0; e < 2; ++e) PROF(e == 0 ? "gin_fwd_ffma.enc1" : "gin_fwd_ffma.enc2", launch_gin_fwd(ga[e], kin, HID, s));
     }

@@ -53,6 +53,9 @@ int gin_fwd_grid(int V);
 void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s);        // FP32 FFMA tiles (gin_kernels.cu), hidden 64 / 128
 void launch_gin_fwd_tc3(const GinFwdArgs& a, int kin, cudaStream_t s);              // tcgen05 3xTF32, shared-memory window gather (gin_tc3.cu)
 void launch_gin_fwd_tc3_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, int kin, cudaStream_t s);
+void launch_gin_fwd_tc4(const GinFwdArgs& a, cudaStream_t s);                       // tcgen05, aggregation on the tensor cores too (gin_tc4.cu); KIN = 64
+void launch_gin_fwd_tc4_pair(const GinFwdArgs& a0, const GinFwdArgs& a1, cudaStream_t s);
+int fwd_tc4_mode();                                                       // SCGIB_FWD4: 1 = gin_tc4.cu for the KIN = 64 layers
 // bf16 mode (gin_bf16.cu, gin_bwd_bf16.cu): the float* activation fields of the argument blocks point to bf16 data
 size_t gin_fwd_bf16_part_floats(int hidden);
 void launch_gin_fwd_bf16(const GinFwdArgs& a0, const GinFwdArgs* a1, int kin, int hidden, cudaStream_t s);
