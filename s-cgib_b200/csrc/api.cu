@@ -31,6 +31,13 @@ int bwd_tensor_core_mode() {
   if (g_bwd_tc < 0) { const char* e = getenv("SCGIB_TC_BWD"); g_bwd_tc = (e && e[0] == '0') ? 0 : 1; }
   return g_bwd_tc;
 }
+// SCGIB_RECON_SIDE=1: the adjacency-reconstruction backward as side CTAs of the contrastive backward launch (measured: the
+// 20 SMs that launch leaves idle need longer for it than the separate 29 us launch on all SMs; default off)
+static bool recon_side_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SCGIB_RECON_SIDE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 static int g_fwd4 = -1;
 int fwd_tc4_mode() {
   if (g_fwd4 < 0) { const char* e = getenv("SCGIB_FWD4"); g_fwd4 = (e && e[0] == '1') ? 1 : 0; }
@@ -488,8 +495,10 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
     if (con_tc) {
       ConBwdSides sd;
-      if (!logm) { sd.recon = ra; sd.n_recon = max(1, num_sms() - ((b->B + 127) / 128) * js); }
+      const bool recon_side = !logm && recon_side_mode();
+      if (recon_side) { sd.recon = ra; sd.n_recon = max(1, num_sms() - ((b->B + 127) / 128) * js); }
       PROF("contrastive_bwd_tc", launch_contrastive_bwd_tc_sides(a, w.zsplit, sd, s));
+      if (!logm && !recon_side) PROF("recon_bwd", launch_recon_bwd(ra, HID, s));
     } else {
       PROF("contrastive_bwd_ffma", launch_contrastive_bwd(a, HID, s));
     }

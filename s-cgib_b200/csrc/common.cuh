@@ -67,6 +67,15 @@ __device__ __forceinline__ float4 relu4(float4 a) {
   return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
 }
 
+// (a, b) -> packed fp16 pairs of the two-term split v = hi + lo: hi = fp16(v), lo = fp16(v - hi) (UNSCALED residual: for
+// |v| <= 1 its absolute error is <= 2^-25, the fp16 subnormal spacing / 2); element a in the low 16 bits
+__device__ __forceinline__ void split_f16x2_plain(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  float ha, hb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(ha), "=f"(hb) : "r"(hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+
 // relu(BN(y)) for 4 consecutive channels: ((y - mean) * rstd) * gamma + beta
 struct Bn4 {
   float4 mean, rstd, gamma, beta;

@@ -378,15 +378,13 @@ graph_gate_fwd_kernel(GraphGateFwdArgs p) {
       for (int k = 0; k < CPL; ++k) { za.v[k] = core.v[k] / na; zb.v[k] = sH.v[k] / nb; dd = fmaf(za.v[k], zb.v[k], dd); }
       const size_t o = (size_t)g * HID + c;
       stv<CPL>(p.z1 + o, za); stv<CPL>(p.z2 + o, zb);
-      if (p.zsplit) {
-        const size_t nn = (size_t)p.B * HID;
-        V ah, al, bh, bl;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          ah.v[k] = tf32_rna_f(za.v[k]); al.v[k] = tf32_rna_f(za.v[k] - ah.v[k]);
-          bh.v[k] = tf32_rna_f(zb.v[k]); bl.v[k] = tf32_rna_f(zb.v[k] - bh.v[k]);
-        }
-        stv<CPL>(p.zsplit + o, ah); stv<CPL>(p.zsplit + nn + o, al); stv<CPL>(p.zsplit + 2 * nn + o, bh); stv<CPL>(p.zsplit + 3 * nn + o, bl);
+      if (p.zsplit) {      // fp16 hi / lo parts [4][B][HID] halves (z1 hi, z1 lo, z2 hi, z2 lo) for the tensor-core kernels (hidden 64)
+        uint32_t* zs = reinterpret_cast<uint32_t*>(p.zsplit);
+        const size_t nn = (size_t)p.B * HID / 2, o2 = o / 2;
+        uint32_t ah, al, bh, bl;
+        split_f16x2_plain(za.v[0], za.v[1], ah, al);
+        split_f16x2_plain(zb.v[0], zb.v[1], bh, bl);
+        if (CPL == 2) { zs[o2] = ah; zs[nn + o2] = al; zs[2 * nn + o2] = bh; zs[3 * nn + o2] = bl; }
       }
       dd = warp_sum(dd);
       if (lane == 0) { p.n1[g] = na; p.n2[g] = nb; p.diag[g] = dd; }

@@ -147,13 +147,13 @@ normalize_kernel(NormalizeArgs p) {
     const float2 za = make_float2(a.x / na, a.y / na), zb = make_float2(b.x / nb, b.y / nb);
     st2(p.z1 + (size_t)i * HID + c, za);
     st2(p.z2 + (size_t)i * HID + c, zb);
-    if (p.zsplit) {   // tf32 hi / lo parts for the tensor-core kernels: hi = rna(z), lo = rna(z - hi)
-      const size_t n = (size_t)p.B * HID, o = (size_t)i * HID + c;
-      const float2 ah = make_float2(tf32_round(za.x), tf32_round(za.y)), bh = make_float2(tf32_round(zb.x), tf32_round(zb.y));
-      st2(p.zsplit + o, ah);
-      st2(p.zsplit + n + o, make_float2(tf32_round(za.x - ah.x), tf32_round(za.y - ah.y)));
-      st2(p.zsplit + 2 * n + o, bh);
-      st2(p.zsplit + 3 * n + o, make_float2(tf32_round(zb.x - bh.x), tf32_round(zb.y - bh.y)));
+    if (p.zsplit) {   // fp16 hi / lo parts [4][B][HID] halves (z1 hi, z1 lo, z2 hi, z2 lo) for the tensor-core kernels
+      uint32_t* zs = reinterpret_cast<uint32_t*>(p.zsplit);
+      const size_t n = (size_t)p.B * HID / 2, o = ((size_t)i * HID + c) / 2;
+      uint32_t ah, al, bh, bl;
+      split_f16x2_plain(za.x, za.y, ah, al);
+      split_f16x2_plain(zb.x, zb.y, bh, bl);
+      zs[o] = ah; zs[n + o] = al; zs[2 * n + o] = bh; zs[3 * n + o] = bl;
     }
     const float d = warp_sum(za.x * zb.x + za.y * zb.y);
     if (lane == 0) { p.n1[i] = na; p.n2[i] = nb; p.diag[i] = d; }

@@ -67,6 +67,8 @@ template <int NT>
 __device__ __forceinline__ void loss_finalize_body(const LossFinalizeArgs& p) {
   __shared__ double s_a[NT], s_b[NT];
   double con = 0.0, fro = 0.0;
+  const bool act = threadIdx.x < NT;       // a CTA may have more threads than NT: the extra ones only join the barriers
+  if (act) {
   // four rows per thread and pass: 4 x jsplit independent loads in flight (the serial chain of L2 round trips is the whole
   // cost of this one-CTA job); every row's partial sums are still added in column-split order
   for (int i0 = threadIdx.x; i0 < p.B; i0 += 4 * NT) {
@@ -90,6 +92,7 @@ __device__ __forceinline__ void loss_finalize_body(const LossFinalizeArgs& p) {
     for (int j = threadIdx.x; j < p.hidden * p.hidden; j += NT) { const double g = (double)__ldcg(p.G + j); fro += g * g; }
   }
   s_a[threadIdx.x] = con; s_b[threadIdx.x] = fro;
+  }
   __syncthreads();
   for (int o = NT / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
