@@ -409,6 +409,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     HeadFwdArgs a{w.noisy, w.C, w.alpha, b->N, w.head_w1t, params + lo.off[SCGIB_P_HEAD_B1], w.head_w2t,
                   params + lo.off[SCGIB_P_HEAD_B2], interaction_map, bf ? nullptr : w.aC, bf ? nullptr : w.r_head, w.Z,
                   w.r_head_bf, w.aC_bf};       // bf16 mode: the backward's operands are kept in bf16 only
+    a.W1n = params + lo.off[SCGIB_P_HEAD_W1]; a.W2n = params + lo.off[SCGIB_P_HEAD_W2];
     PROF("head_fwd", launch_head_fwd(a, HID, s));
   }
   const int logm = b->recon_logm_steps;
@@ -1143,6 +1144,7 @@ extern "C" SCGIB_API int scgib_head_mlp_fwd_f32(const float* noisy, const float*
   jobs.job[1] = TransposeJob{W2, w.w2t, H, H};
   launch_transposes(jobs, s);
   HeadFwdArgs a{noisy, C, alpha, N, w.w1t, b1, w.w2t, b2, interaction_map, w.aC, w.r, w.Zc};
+  a.W1n = W1; a.W2n = W2;
   launch_head_fwd(a, H, s);
   cudaMemcpyAsync(Z, w.Zc, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
   return (int)cudaGetLastError();

@@ -76,6 +76,16 @@ __device__ __forceinline__ void split_f16x2_plain(float a, float b, uint32_t& hi
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 
+// the same with the residual SCALED by 2^11: lo' = fp16((v - hi) * 2048) stays in fp16's normal range whenever hi does, so
+// hi + 2^-11 lo' carries 22 significand bits for every magnitude (products with lo' land in separate accumulator columns
+// and are scaled back by 2^-11 in the epilogue)
+__device__ __forceinline__ void split_f16x2_s11(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  float ha, hb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(ha), "=f"(hb) : "r"(hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((b - hb) * 2048.f), "f"((a - ha) * 2048.f));
+}
+
 // relu(BN(y)) for 4 consecutive channels: ((y - mean) * rstd) * gamma + beta
 struct Bn4 {
   float4 mean, rstd, gamma, beta;

@@ -7,6 +7,7 @@
 //   compress / compression (Python loop)  models.py:595-604, 631-660
 //   attention (Python loop)               models.py:738-749
 //   self.MLP(interaction_map)             models.py:569-572, 676
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "side_jobs.cuh"
 
@@ -716,6 +717,13 @@ static void launch_head_fwd_t(const HeadFwdArgs& a, cudaStream_t s) {
   launch_k((head_fwd_kernel<H, HT>), dim3(grid), dim3(kThreads), sizeof(S), s, a);
 }
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s) {
+  const uintptr_t al32 = (uintptr_t)a.noisy | (uintptr_t)a.C | (uintptr_t)a.Z | (uintptr_t)a.r | (uintptr_t)a.aC | (uintptr_t)a.imap;
+  static int head_ffma = -1;                 // SCGIB_HEAD_FFMA=1: FFMA tiles also at hidden 64 (cross-check)
+  if (head_ffma < 0) { const char* e = getenv("SCGIB_HEAD_FFMA"); head_ffma = (e && e[0] == '1') ? 1 : 0; }
+  if (hidden == 64 && a.W1n && a.W2n && !a.r_bf && !a.aC_bf && (al32 & 31u) == 0 && tensor_core_mode() != 0 && !head_ffma) {   // 32-byte row accesses
+    launch_head_fwd_tc(a, s);
+    return;
+  }
   if (hidden == 64) launch_head_fwd_t<64, 64>(a, s); else launch_head_fwd_t<128, 32>(a, s);
 }
 

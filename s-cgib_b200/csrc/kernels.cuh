@@ -218,8 +218,11 @@ struct HeadFwdArgs {
   float* Z;                              // [N][HID]
   bf16_t* r_bf = nullptr;                // optional bf16 copies of r and alpha*C (bf16 mode: operands of the head backward)
   bf16_t* aC_bf = nullptr;
+  const float *W1n = nullptr, *W2n = nullptr;   // natural [HID][2*HID], [HID][HID]: when set (hidden 64, fp32 saves) the tensor-core
+                                                //  kernel head_tc.cu runs instead of the FFMA tiles
 };
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s);
+void launch_head_fwd_tc(const HeadFwdArgs& a, cudaStream_t s);
 
 // Head backward = the GIN backward kernel run on the two K = H halves of the first head layer (api.cu).
 // prep: dense copies W1a = W1[:, :HID], W1b = W1[:, HID:] and the identity BatchNorm-backward constants
