@@ -115,6 +115,7 @@ _PRIVATE_SIGNATURES = {
     "scgib_debug_bwd_trace": (c_int, [c_void_p, c_int]),
     "scgib_debug_bf16_trace": (c_int, [c_void_p, c_int]),
     "scgib_debug_tc4_trace": (c_int, [c_void_p, c_int]),
+    "scgib_debug_bwdh_trace": (c_int, [c_void_p, c_int]),
 }
 
 _lib = None

@@ -38,6 +38,11 @@ static bool recon_side_mode() {
   if (v < 0) { const char* e = getenv("SCGIB_RECON_SIDE"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+static int g_bwd_h = -1;
+int bwd_h_mode() {
+  if (g_bwd_h < 0) { const char* e = getenv("SCGIB_BWD_H"); g_bwd_h = (e && e[0] == '0') ? 0 : 1; }
+  return g_bwd_h;
+}
 static int g_fwd4 = -1;
 int fwd_tc4_mode() {
   if (g_fwd4 < 0) { const char* e = getenv("SCGIB_FWD4"); g_fwd4 = (e && e[0] == '1') ? 1 : 0; }
@@ -481,6 +486,11 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   if (b->recon_logm_steps > 0 && HID != 64 && !gZ_ext) return SCGIB_E_SHAPE;
 
   cudaMemsetAsync(w.counters, 0, 64 * sizeof(float), s);
+  // gin_bwd_h.cu (two-term fp16 splits) normalises the gradients of a launch by a power of two derived from max |g_o|: the kernel
+  // that produces g_o leaves it in one of these slots (zeroed above) with an order-independent atomicMax
+  const bool use_h = tc_bwd && bwd_h_mode() != 0;
+  unsigned int* gm_head = w.counters + 52;
+  auto gm_layer = [&](int e, int l) { return w.counters + 40 + e * 6 + l; };
   const int js = contrastive_jsplit(b->B);
   if (gZ_ext) {
     if (((uintptr_t)gZ_ext & 15u) != 0) return SCGIB_E_ALIGN;
@@ -494,6 +504,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     const bool con_tc = HID == 64 && use_tc_contrastive();
     const bool logm = b->recon_logm_steps > 0;
     ReconBwdArgs ra{w.Z, w.G, b->indptr, b->indices, b->N, s_rec, w.gZ};
+    if (use_h && !logm) ra.gmax = gm_head;          // max |gZ| for the head backward's gradient normalisation (gin_bwd_h.cu)
     if (con_tc) {
       ConBwdSides sd;
       const bool recon_side = !logm && recon_side_mode();
@@ -519,6 +530,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   {
     // (W1a / W1b / head_bn / head_cvec were prepared by the forward pass of this step: fwd_prep)
     if (bf) PROF("head_gz_bf16", launch_f32_to_bf16(w.gZ, w.gZ_bf, (size_t)b->N * HID, s));
+    if (use_h && (gZ_ext || b->recon_logm_steps > 0)) PROF("head_gz_absmax", launch_absmax(w.gZ, (size_t)b->N * HID, gm_head, s));
     GinBwdMainArgs m[2];
     for (int h = 0; h < 2; ++h) {
       m[h].g_o = w.gZ; m[h].y = w.Z; m[h].r = w.r_head; m[h].a = h == 0 ? w.noisy : w.aC;
@@ -527,6 +539,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       m[h].V = b->N; m[h].g_a = w.gI + (size_t)h * b->N * HID; m[h].part = w.ppart; m[h].pstride = lo.total;
       m[h].off_W1 = lo.off[SCGIB_P_HEAD_W1] + (int64_t)h * HID * HID; m[h].off_b1 = lo.off[SCGIB_P_HEAD_B1];
       m[h].off_W2 = lo.off[SCGIB_P_HEAD_W2]; m[h].off_b2 = lo.off[SCGIB_P_HEAD_B2];
+      m[h].gmax = gm_head;
     }
     if (bf) {
       // bf16 mode: the bf16 GIN backward kernel (single-pass bf16 MMAs) on bf16 copies of gZ / r / noisy / alpha C; gI stays fp32.
@@ -536,6 +549,8 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
         m[h].a = (const float*)(h == 0 ? w.noisy_bf : w.aC_bf);
       }
       PROF("head_bwd_bf16", launch_gin_bwd_main_bf16(m[0], &m[1], HID, HID, GP, s, true));
+    } else if (use_h) {
+      PROF("head_bwd_h", launch_gin_bwd_main_h_pair(m[0], m[1], GP, s));
     } else if (tc_bwd) {
       PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
     } else {
@@ -585,7 +600,9 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       q.part = e == 0 ? w.small_part : w.small_part2; q.counter = w.counters + (e == 0 ? 2 : 10);
       q.d_gamma = grads + lo.enc(e, l, L, SCGIB_ENC_GAMMA); q.d_beta = grads + lo.enc(e, l, L, SCGIB_ENC_BETA);
       q.cvec = w.cvec[e];
+      q.gmax = use_h ? gm_layer(e, l) : nullptr;
       GinBwdMainArgs& m = ma[e];
+      m.gmax = gm_layer(e, l);
       m.g_o = w.g_o[e]; m.y = w.y[e][l]; m.r = w.r[e][l]; m.a = w.a[e][l]; m.bn = w.bn[e][l]; m.cvec = w.cvec[e];
       m.W1 = params + lo.enc(e, l, L, SCGIB_ENC_W1); m.W2 = params + lo.enc(e, l, L, SCGIB_ENC_W2);
       m.V = V; m.g_a = l == 0 ? w.ga0[e] : w.Ga[e]; m.part = w.ppart; m.pstride = lo.total;
@@ -598,7 +615,9 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       continue;
     }
     PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], HID, s));
-    if (pair_main) {
+    if (use_h && kin == HID) {
+      PROF("gin_bwd_main_h.enc1+2", launch_gin_bwd_main_h_pair(ma[0], ma[1], GP, s));
+    } else if (pair_main) {
       PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
     } else {
       PROF("gin_bwd_main_ffma.enc1", launch_gin_bwd_main(ma[0], kin, HID, GP, s));

@@ -112,6 +112,22 @@ void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16) {
   else launch_k((fwd_prep_kernel<false>), dim3(grid), dim3(kThreads), 0, s, a);
 }
 
+__global__ void __launch_bounds__(kThreads) absmax_kernel(const float* __restrict__ x, size_t n4, unsigned int* __restrict__ slot) {
+  pdl_sync();
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) {
+    const float4 v = ld4(x + 4 * i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+void launch_absmax(const float* x, size_t n, unsigned int* slot, cudaStream_t s) {   // n multiple of 4
+  const size_t n4 = n / 4;
+  const int grid = (int)min((size_t)(4 * num_sms()), (n4 + kThreads - 1) / kThreads);
+  if (n4 > 0) launch_k((absmax_kernel), dim3(grid), dim3(kThreads), 0, s, x, n4, slot);
+}
+
 __global__ void __launch_bounds__(kThreads) f32_to_bf16_kernel(const float* __restrict__ in, bf16_t* __restrict__ out, size_t n4) {
   pdl_sync();
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads)
@@ -355,6 +371,7 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
   Bn4 bn;
   bn.load(p.bn, l * 4, HID);
   float4 db = make4(0.f), dg = make4(0.f);
+  float gm = 0.f;
   constexpr int NR = 4;
   for (int v0 = bid * RPC + hw; v0 < p.V; v0 += nblk * RPC * NR) {
     int vv[NR];
@@ -381,12 +398,17 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
       float4 gg = g[j];
       gg.x = o.x > 0.f ? gg.x : 0.f; gg.y = o.y > 0.f ? gg.y : 0.f; gg.z = o.z > 0.f ? gg.z : 0.f; gg.w = o.w > 0.f ? gg.w : 0.f;
       st4(p.g_o + (size_t)vv[j] * HID + l * 4, gg);
+      gm = fmaxf(fmaxf(gm, fmaxf(fabsf(gg.x), fabsf(gg.y))), fmaxf(fabsf(gg.z), fabsf(gg.w)));
       db = add4(db, gg);
       dg.x = fmaf(gg.x, xh.x, dg.x); dg.y = fmaf(gg.y, xh.y, dg.y); dg.z = fmaf(gg.z, xh.z, dg.z); dg.w = fmaf(gg.w, xh.w, dg.w);
     }
   }
   st4(s_red + hw * 2 * HID + l * 4, db);
   st4(s_red + hw * 2 * HID + HID + l * 4, dg);
+  if (p.gmax) {                  // max is order-independent: the atomic keeps the result deterministic
+    gm = warp_max(gm);
+    if ((threadIdx.x & 31) == 0 && gm > 0.f) atomicMax(p.gmax, __float_as_uint(gm));
+  }
   __syncthreads();
   if (threadIdx.x < 2 * HID) {
     float s = 0.f;

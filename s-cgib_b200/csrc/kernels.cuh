@@ -75,6 +75,7 @@ struct GinBwdPreArgs {
   unsigned int* counter;
   float *d_gamma, *d_beta;  // [HID] final gradients
   float* cvec;              // {c1, c2}[HID]
+  unsigned int* gmax = nullptr;   // optional: atomicMax of the bits of max |g_o| (zeroed by the caller): gradient scale of gin_bwd_h
 };
 struct GinBwdPrePair { GinBwdPreArgs a[2]; int split; };
 int gin_bwd_pre_grid(int V);
@@ -92,6 +93,7 @@ struct GinBwdMainArgs {
   float* part;              // per-CTA partial gradients: part[cta * pstride + off_*]
   int64_t pstride;
   int64_t off_W1, off_b1, off_W2, off_b2;
+  const unsigned int* gmax = nullptr;   // gin_bwd_h: bits of max |g_o| (left by the kernel that produced g_o)
 };
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s);      // FP32 FFMA tiles, hidden 64 / 128
 struct GinBwdMainPair {
@@ -106,6 +108,10 @@ int gin_bwd_pre_bf16_grid(int V, int hidden);
 void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, int hidden, cudaStream_t s);
 void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s,
                               bool ga_f32 = false);      // ga_f32: g_a is written as fp32 also for kin == hidden (head backward)
+void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int grid, cudaStream_t s,
+                                bool weights_from_prev_kernel = false);     // tcgen05, two-term fp16 splits, 128-row tiles (gin_bwd_h.cu); KIN = 64
+void launch_absmax(const float* x, size_t n, unsigned int* slot, cudaStream_t s);   // atomicMax(slot, bits of max |x|)
+int bwd_h_mode();                                                          // SCGIB_BWD_H: 1 (default) gin_bwd_h.cu for the KIN = 64 layers and the head
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
 
 struct InputProjBwdArgs {
@@ -251,6 +257,7 @@ void launch_recon_reduce(const float* part, int grid, float* G, float* edge_sum,
 struct ReconBwdArgs {
   const float* Z; const float* G; const int32_t* indptr; const int32_t* indices; int N;
   float scale; float* gZ;
+  unsigned int* gmax = nullptr;          // optional: atomicMax of the bits of max |gZ|
 };
 void launch_recon_bwd(const ReconBwdArgs& a, int hidden, cudaStream_t s);
 

@@ -120,6 +120,7 @@ __device__ __forceinline__ void recon_bwd_body(const ReconBwdArgs& p, unsigned c
   load_matrix<HID>(sm.g, HID, p.G, HID);
   const float k = p.scale * 4.f / (float)p.N;
   const int n_tiles = (p.N + GT - 1) / GT;
+  float gm = 0.f;
   for (int tile = idx; tile < n_tiles; tile += n) {
     const int base = tile * GT;
     __syncthreads();
@@ -152,10 +153,15 @@ __device__ __forceinline__ void recon_bwd_body(const ReconBwdArgs& p, unsigned c
       const int v = base + r0 + m;
       if (v < p.N) {
         const float4 t = EARLY ? nb[EARLY ? m : 0] : neigh(v);
-        st4(p.gZ + (size_t)v * HID + c0,
-            make_float4(k * (acc[m][0] - t.x), k * (acc[m][1] - t.y), k * (acc[m][2] - t.z), k * (acc[m][3] - t.w)));
+        const float4 o = make_float4(k * (acc[m][0] - t.x), k * (acc[m][1] - t.y), k * (acc[m][2] - t.z), k * (acc[m][3] - t.w));
+        st4(p.gZ + (size_t)v * HID + c0, o);
+        gm = fmaxf(fmaxf(gm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
       }
     }
+  }
+  if (p.gmax) {                  // max is order-independent: the atomic keeps the result deterministic
+    gm = warp_max(gm);
+    if ((threadIdx.x & 31) == 0 && gm > 0.f) atomicMax(p.gmax, __float_as_uint(gm));
   }
 }
 
