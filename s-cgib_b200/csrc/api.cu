@@ -550,7 +550,7 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       }
       PROF("head_bwd_bf16", launch_gin_bwd_main_bf16(m[0], &m[1], HID, HID, GP, s, true));
     } else if (use_h) {
-      PROF("head_bwd_h", launch_gin_bwd_main_h_pair(m[0], m[1], GP, s));
+      PROF("head_bwd_h", launch_gin_bwd_main_h_pair(m[0], m[1], HID, GP, s));
     } else if (tc_bwd) {
       PROF("head_bwd_tc", launch_gin_bwd_main_tc2_pair(m[0], m[1], HID, GP, s));
     } else {
@@ -615,8 +615,8 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
       continue;
     }
     PROF("gin_bwd_pre.enc1+2", launch_gin_bwd_pre_pair(pa[0], pa[1], HID, s));
-    if (use_h && kin == HID) {
-      PROF("gin_bwd_main_h.enc1+2", launch_gin_bwd_main_h_pair(ma[0], ma[1], GP, s));
+    if (use_h) {
+      PROF("gin_bwd_main_h.enc1+2", launch_gin_bwd_main_h_pair(ma[0], ma[1], kin, GP, s));
     } else if (pair_main) {
       PROF("gin_bwd_main_tc.enc1+2", launch_gin_bwd_main_tc2_pair(ma[0], ma[1], kin, GP, s));
     } else {

@@ -1,6 +1,7 @@
 // gin_bwd_h.cu - GIN layer backward (part 2) on tcgen05 with TWO-TERM FP16 operand splits: 128-row tiles, K = 16 MMAs.
 //
-// Same contract and math as gin_bwd_tc2.cu (reference: autograd of models.py:66-72), KIN = 64 layers and the head MLP:
+// Same contract and math as gin_bwd_tc2.cu (reference: autograd of models.py:66-72), every GIN layer (the 32-wide layer 0 runs
+// zero-padded to 64 input channels) and the head MLP:
 //   g_y = rstd * (gamma*g_o - c1 - yhat*c2);  G1: g_r = g_y W2;  G3: dW2 += g_y^T r;  g_u = g_r * [r > 0];
 //   G2: g_a = g_u W1;  G4: dW1 += g_u^T a;  db2 += sum g_y;  db1 += sum g_u.
 // gin_bwd_tc2 (3xTF32, K = 8 per MMA, 64-row tiles: 64 MMAs per 64 rows) is bound by the per-tile dependency chain and the
@@ -69,12 +70,13 @@ __device__ __forceinline__ void ld8cs(const float* p, float* v) {
 __device__ __forceinline__ float clamp16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
 // transposed weight tile for the input-gradient GEMMs: B[n = input channel][k = output channel] = 16 W[out][in], fp16 hi / lo
-__device__ __forceinline__ void stage_wt(unsigned char* hi_t, unsigned char* lo_t, const float* __restrict__ W, int tid, int nthreads) {
+// (`in` < 64 input channels: the missing rows of the tile are zero)
+__device__ __forceinline__ void stage_wt(unsigned char* hi_t, unsigned char* lo_t, const float* __restrict__ W, int in, int tid, int nthreads) {
   for (int i = tid; i < HID * 8; i += nthreads) {
     const int n = i & (HID - 1), c8 = i >> 6;                    // consecutive threads: consecutive input channels (coalesced)
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __ldg(W + (size_t)(c8 * 8 + q) * HID + n) * kWScale;
+    for (int q = 0; q < 8; ++q) v[q] = n < in ? __ldg(W + (size_t)(c8 * 8 + q) * in + n) * kWScale : 0.f;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) split_f16x2_plain(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
@@ -87,7 +89,8 @@ __device__ __forceinline__ void stage_wt(unsigned char* hi_t, unsigned char* lo_
 __global__ void __launch_bounds__(kThreadsB, 1)
 gin_bwd_h_kernel(GinBwdMainPair pp) {
   using L = Smem;
-  constexpr int KIN = HID;
+  constexpr int KIN = HID;                                    // tile width of a / g_a / W1t: narrower layers (kin = 32) are zero-padded
+  const int kin = pp.kin;
   const bool second = (int)blockIdx.x >= pp.split;
   const GinBwdMainArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
@@ -118,8 +121,8 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
   }
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
   if (pp.wait_first) pdl_sync();
-  stage_wt(smem + L::off_w2, smem + L::off_w2 + kWTile, p.W2, threadIdx.x, kThreadsB);
-  stage_wt(smem + L::off_w1, smem + L::off_w1 + kWTile, p.W1, threadIdx.x, kThreadsB);
+  stage_wt(smem + L::off_w2, smem + L::off_w2 + kWTile, p.W2, HID, threadIdx.x, kThreadsB);
+  stage_wt(smem + L::off_w1, smem + L::off_w1 + kWTile, p.W1, kin, threadIdx.x, kThreadsB);
   if (!pp.wait_first) pdl_sync();   // the weights above are parameters; bn / cvec / g_o / y / r / a / gmax below come from the previous kernels
   // BN-backward constants: g_y = ka*g_o - kd*y + (kd*mean - ke)      (ka = rstd*gamma, kd = rstd^2*c2, ke = rstd*c1)
   if (threadIdx.x < HID) {
@@ -170,7 +173,11 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       if (pt == 0) BWDH_TRACE(0, i);
       if (i + 1 < my_tiles) {                                   // next tile -> L2: 256 lines of 128 B per [128][64] fp32 tensor
         const size_t off = (size_t)tile_base(i + 1) * HID + (size_t)(pt & 255) * 32;
-        if (pt < 256 && off < (size_t)p.V * HID) { prefetch_l2(p.g_o + off); prefetch_l2(p.y + off); prefetch_l2(p.r + off); prefetch_l2(p.a + off); }
+        if (pt < 256 && off < (size_t)p.V * HID) {
+          prefetch_l2(p.g_o + off); prefetch_l2(p.y + off); prefetch_l2(p.r + off);
+          const size_t aoff = (size_t)tile_base(i + 1) * kin + (size_t)(pt & 255) * 32;
+          if ((pt & 255) * 32 < TM * kin && aoff < (size_t)p.V * kin) prefetch_l2(p.a + aoff);
+        }
       }
       bool waited = use == 0;
 #pragma unroll
@@ -234,7 +241,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
 #pragma unroll
       for (int j = 0; j < UPT; ++j) {
         const int v = base + r0 + RPP * j;
-        if (v < p.V) ld8cs(p.a + (size_t)v * KIN + c, aa[j]);
+        if (v < p.V && c < kin) ld8cs(p.a + (size_t)v * kin + c, aa[j]);
         else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) aa[j][q] = 0.f;
@@ -382,9 +389,9 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       const float k = invS * (1.f / kWScale);
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] = fmaf(t2[j], kLo, g[j]) * k;
-      if (gv < p.V) {
+      if (gv < p.V && c0 < kin) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) st8(p.g_a + (size_t)gv * KIN + c0 + 8 * j, g + 8 * j);
+        for (int j = 0; j < 4; ++j) st8(p.g_a + (size_t)gv * kin + c0 + 8 * j, g + 8 * j);
       }
       if (threadIdx.x == 0) BWDH_TRACE(10, i);
     };
@@ -425,13 +432,14 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       }
     }
     __syncthreads();
+    const int C = pass == 0 ? HID : kin;                // columns of the parameter (dW1 of a kin = 32 layer: [64][32])
     if (warp < 2) {
       const int o = warp * 32 + lane;
-      for (int j = 0; j < HID; j += 4) {
+      for (int j = 0; j < C; j += 4) {
         float4 v;
         v.x = fmaf(s_x[o * (HID + 1) + j], kLo, t[j]) * invS;         v.y = fmaf(s_x[o * (HID + 1) + j + 1], kLo, t[j + 1]) * invS;
         v.z = fmaf(s_x[o * (HID + 1) + j + 2], kLo, t[j + 2]) * invS; v.w = fmaf(s_x[o * (HID + 1) + j + 3], kLo, t[j + 3]) * invS;
-        st4(part + offW + (size_t)o * HID + j, v);
+        st4(part + offW + (size_t)o * C + j, v);
       }
     }
     __syncthreads();
@@ -458,12 +466,13 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
 
 // the same layer of both encoders (or the two K halves of the head MLP) in one launch: CTAs [0, split) write the partial
 // gradients of a0, [split, grid) of a1 (split as computed by pair_split on 128-row tile counts, as gin_bwd_tc2)
-void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int grid, cudaStream_t s, bool weights_from_prev_kernel) {
+void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s, bool weights_from_prev_kernel) {
   static bool once = (cudaFuncSetAttribute(bwdh::gin_bwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdh::Smem::total), true);
   (void)once;
   GinBwdMainPair pp;
   pp.a[0] = a0; pp.a[1] = a1;
   pp.wait_first = weights_from_prev_kernel ? 1 : 0;
+  pp.kin = kin;
   pp.split = pair_split(grid, (a0.V + 127) / 128, (a1.V + 127) / 128);
   static int tr = -1;
   if (tr < 0) { const char* e = getenv("SCGIB_DBG"); tr = (e && (atoi(e) & 2048)) ? 1 : 0; }

@@ -98,6 +98,7 @@ struct GinBwdMainArgs {
 void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid, cudaStream_t s);      // FP32 FFMA tiles, hidden 64 / 128
 struct GinBwdMainPair {
   GinBwdMainArgs a[2]; int split; int trace; int reverse = 0;
+  int kin = HID;            // gin_bwd_h: input width of the layer (32 | 64)
   int wait_first = 0;       // PDL: W1 / W2 are written by the kernel launched right before this one (the head backward's de-interleaved
                             //  W1 halves): wait for it before staging the weights instead of after
 };
@@ -108,8 +109,8 @@ int gin_bwd_pre_bf16_grid(int V, int hidden);
 void launch_gin_bwd_pre_bf16(const GinBwdPreArgs& a0, const GinBwdPreArgs* a1, int hidden, cudaStream_t s);
 void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1, int kin, int hidden, int grid, cudaStream_t s,
                               bool ga_f32 = false);      // ga_f32: g_a is written as fp32 also for kin == hidden (head backward)
-void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int grid, cudaStream_t s,
-                                bool weights_from_prev_kernel = false);     // tcgen05, two-term fp16 splits, 128-row tiles (gin_bwd_h.cu); KIN = 64
+void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s,
+                                bool weights_from_prev_kernel = false);     // tcgen05, two-term fp16 splits, 128-row tiles (gin_bwd_h.cu); kin 32 | 64
 void launch_absmax(const float* x, size_t n, unsigned int* slot, cudaStream_t s);   // atomicMax(slot, bits of max |x|)
 int bwd_h_mode();                                                          // SCGIB_BWD_H: 1 (default) gin_bwd_h.cu for the KIN = 64 layers and the head
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
