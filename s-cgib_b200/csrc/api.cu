@@ -38,6 +38,8 @@ static bool recon_side_mode() {
   if (v < 0) { const char* e = getenv("SCGIB_RECON_SIDE"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+// CTAs of recon_fwd (= its per-CTA partial Gram matrices): two resident CTAs per SM at hidden 64 overlap the copy / Gram / gather phases
+static int recon_fwd_grid() { return 2 * num_sms(); }
 static int g_bwd_h = -1;
 int bwd_h_mode() {
   if (g_bwd_h < 0) { const char* e = getenv("SCGIB_BWD_H"); g_bwd_h = (e && e[0] == '0') ? 0 : 1; }
@@ -213,7 +215,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.noisy = take((size_t)N * HID); w.Z = take((size_t)N * HID); w.r_head = take((size_t)N * HID);
   w.readout = take((size_t)B * HID); w.core = take((size_t)B * HID);
   w.gstat = take((size_t)B * 4 * HID); w.cstat = take((size_t)B * 2 * HID); w.kl = take(4);
-  w.rpart = take((size_t)num_sms() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
+  w.rpart = take((size_t)recon_fwd_grid() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
   const int js = contrastive_jsplit(B);
   w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID); w.zsplit = take((size_t)4 * B * HID);
   w.n1 = take(B); w.n2 = take(B); w.diag = take(B); w.D = take(B);
@@ -422,7 +424,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     PROF("logm_fwd", launch_logm_fwd(w.Z, b->graph_ptr, b->indptr, b->indices, b->B, b->N, logm, w.logm_walks, w.logm_gram,
                                      w.logm_pair, w.logm_loss, (int32_t*)(w.counters + 32), s));
   } else if (!features_only) {
-    const int grid = num_sms();
+    const int grid = recon_fwd_grid();
     ReconFwdArgs a{w.Z, b->indptr, b->indices, b->N, w.rpart};
     PROF("recon_fwd", launch_recon_fwd(a, HID, grid, s));
     if (!fuse_tail) PROF("recon_reduce", launch_recon_reduce(w.rpart, grid, w.G, w.edge, HID, s));
@@ -433,7 +435,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
     LossFinalizeArgs fin{w.rowsum, js, w.diag, b->B, w.G, w.edge, b->N, b->E, logm > 0 ? w.logm_loss : nullptr, w.kl, w.D, losses, HID};
     if (fuse_tail) {
       ConFwdSides sd;
-      if (logm <= 0) { sd.rpart = w.rpart; sd.rgrid = num_sms(); sd.G = w.G; sd.edge = w.edge; sd.n_reduce = 8; }
+      if (logm <= 0) { sd.rpart = w.rpart; sd.rgrid = recon_fwd_grid(); sd.G = w.G; sd.edge = w.edge; sd.n_reduce = 8; }
       if (bn_running && !eval) { sd.cstat = w.cstat; sd.running = bn_running + (size_t)2 * L * 2 * HID; sd.n_ema = 1; }
       sd.finalize = 1; sd.fin = fin; sd.counter = w.counters + 4;
       PROF("contrastive_fwd_tc", launch_contrastive_fwd_tc_sides(c, sd, s));
@@ -910,7 +912,7 @@ static LossOpWs loss_op_carve(int B, void* base) {
   size_t o = 0;
   auto take = [&](size_t nfloats) { float* r = (float*)(p + o); o += al(nfloats * sizeof(float)); return r; };
   const int js = contrastive_jsplit(B > 0 ? B : 1);
-  w.rpart = take((size_t)num_sms() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
+  w.rpart = take((size_t)recon_fwd_grid() * (HID * HID + 4)); w.G = take(HID * HID); w.edge = take(4);
   w.z1 = take((size_t)B * HID); w.z2 = take((size_t)B * HID); w.zsplit = take((size_t)4 * B * HID);
   w.n1 = take(B); w.n2 = take(B); w.diag = take(B); w.D = take(B); w.rowsum = take((size_t)js * B);
   w.g1p = take((size_t)js * B * HID); w.g2p = take((size_t)js * B * HID); w.kl = take(4); w.losses = take(4);

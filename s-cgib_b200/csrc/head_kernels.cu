@@ -717,10 +717,11 @@ static void launch_head_fwd_t(const HeadFwdArgs& a, cudaStream_t s) {
   launch_k((head_fwd_kernel<H, HT>), dim3(grid), dim3(kThreads), sizeof(S), s, a);
 }
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s) {
-  const uintptr_t al32 = (uintptr_t)a.noisy | (uintptr_t)a.C | (uintptr_t)a.Z | (uintptr_t)a.r | (uintptr_t)a.aC | (uintptr_t)a.imap;
+  const uintptr_t al32 = (uintptr_t)a.noisy | (uintptr_t)a.C | (uintptr_t)a.Z | (uintptr_t)a.r | (uintptr_t)a.aC | (uintptr_t)a.imap |
+                         (uintptr_t)a.r_bf | (uintptr_t)a.aC_bf;
   static int head_ffma = -1;                 // SCGIB_HEAD_FFMA=1: FFMA tiles also at hidden 64 (cross-check)
   if (head_ffma < 0) { const char* e = getenv("SCGIB_HEAD_FFMA"); head_ffma = (e && e[0] == '1') ? 1 : 0; }
-  if (hidden == 64 && a.W1n && a.W2n && !a.r_bf && !a.aC_bf && (al32 & 31u) == 0 && tensor_core_mode() != 0 && !head_ffma) {   // 32-byte row accesses
+  if (hidden == 64 && a.W1n && a.W2n && (al32 & 31u) == 0 && tensor_core_mode() != 0 && !head_ffma) {   // 32-byte row accesses
     launch_head_fwd_tc(a, s);
     return;
   }

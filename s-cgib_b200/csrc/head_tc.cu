@@ -11,7 +11,8 @@
 // MEMORY (16-bit A operand: two K values per column).
 // Producers build [noisy || alpha C] (never materialised in HBM unless the caller asks for interaction_map) with 32-byte
 // loads of 8 channels; alpha C and r are saved for the head backward.  Replaces the FP32-FFMA head_fwd_kernel (75 -> ~25 us
-// at N = 61 k rows), which remains the hidden-128 / bf16-mode / cross-check path.
+// at N = 61 k rows), which remains the hidden-128 / cross-check path (SCGIB_HEAD_FFMA=1).  bf16 mode: optional bf16 copies of
+// r and alpha C for its head backward.
 #include "kernels.cuh"
 #include "umma.cuh"
 
@@ -141,6 +142,9 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
           for (int q = 0; q < 8; ++q) v[j][q] *= al[j];
           if (gv < p.N) {
             if (second && p.aC) st8(p.aC + (size_t)gv * HID + c8 * 8, v[j]);
+            if (second && p.aC_bf)       // bf16 mode: the head backward's operand copy
+              *reinterpret_cast<uint4*>(p.aC_bf + (size_t)gv * HID + c8 * 8) =
+                  make_uint4(pack_bf16x2(v[j][0], v[j][1]), pack_bf16x2(v[j][2], v[j][3]), pack_bf16x2(v[j][4], v[j][5]), pack_bf16x2(v[j][6], v[j][7]));
             if (p.imap) st8(p.imap + (size_t)gv * 2 * HID + ch * 8, v[j]);
           }
           uint32_t hi[4], lo[4];
@@ -224,6 +228,13 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
       if (p.r && gv < p.N) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) st8(p.r + (size_t)gv * HID + c0 + 8 * j, v + 8 * j);
+      }
+      if (p.r_bf && gv < p.N) {      // bf16 mode: the head backward's operand copy
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(p.r_bf + (size_t)gv * HID + c0 + 8 * j) =
+              make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                         pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
       }
       tmem_st_wait();
       fence_before_sync();
