@@ -577,9 +577,13 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
     a.d_gamma_c = grads + lo.off[SCGIB_P_COMP_GAMMA]; a.d_beta_c = grads + lo.off[SCGIB_P_COMP_BETA];
     a.d_wc2 = grads + lo.off[SCGIB_P_COMP_W2]; a.d_bc2 = grads + lo.off[SCGIB_P_COMP_B2];
     a.d_attn_w = grads + lo.off[SCGIB_P_ATTN_W]; a.d_attn_b = grads + lo.off[SCGIB_P_ATTN_B];
+    a.gmax_q = use_h ? w.counters + 53 : nullptr;
     PROF("graph_gate_bwd", launch_graph_gate_bwd(a, HID, s));
   }
-  {
+  if (use_h) {      // compressor.0 backward = one linear layer on the fp16-split tensor-core kernel (half mode of gin_bwd_h.cu)
+    PROF("gate_lin_bwd_h", launch_linear_bwd_h(w.g_q, w.H, params + lo.off[SCGIB_P_COMP_W1], b->N, w.gH, w.head_bn, w.head_cvec,
+                                               w.counters + 53, w.ppart, lo.total, lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1], GP, s));
+  } else {
     GateLinBwdArgs a{w.g_q, w.H, b->N, params + lo.off[SCGIB_P_COMP_W1], w.gH, w.ppart, lo.total,
                      lo.off[SCGIB_P_COMP_W1], lo.off[SCGIB_P_COMP_B1]};
     PROF("gate_lin_bwd", launch_gate_lin_bwd(a, HID, GP, s));

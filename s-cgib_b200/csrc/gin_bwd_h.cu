@@ -8,7 +8,7 @@
 // ~54-cycle cost of each small MMA.  Here every operand is a two-term fp16 split (22 significand bits, as the 3xTF32 products):
 //   * forward activations r, a and the weights (x 2^4): v = hi + lo, lo = fp16(v - hi) UNSCALED (|v| = O(1): absolute error
 //     <= 2^-25), so their hi and lo products accumulate into the SAME columns;
-//   * gradients g_y, g_u: first normalised by a power of two S (max |g| of the launch -> ~2^-6: the producing kernel leaves
+//   * gradients g_y, g_u: first normalised by a power of two S (max |g| of the launch -> ~2^8: the producing kernel leaves
 //     max |g_o| in a device slot by an order-independent atomicMax, the BN-backward factors are known here), then
 //     v = hi + 2^-11 lo' with the residual SCALED into fp16's normal range: small gradient entries keep their relative
 //     precision; the lo' products land in separate accumulator columns / TMEM lanes and are folded in with 2^-11 by the epilogues.
@@ -86,11 +86,15 @@ __device__ __forceinline__ void stage_wt(unsigned char* hi_t, unsigned char* lo_
   }
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(kThreadsB, 1)
 gin_bwd_h_kernel(GinBwdMainPair pp) {
   using L = Smem;
   constexpr int KIN = HID;                                    // tile width of a / g_a / W1t: narrower layers (kin = 32) are zero-padded
   const int kin = pp.kin;
+  // half mode (one linear layer, the compressor's first: gH += g_q Wc1, dWc1 = g_q^T H, dbc1 = sum g_q): only G1 / G3 run,
+  // epilogue 1 adds g_r to the rows of g_a (in / out) instead of masking and re-splitting it; identity BN constants; r = H
+  constexpr bool half_mode = HALF;
   const bool second = (int)blockIdx.x >= pp.split;
   const GinBwdMainArgs& p = pp.a[second ? 1 : 0];
   const int bid = second ? (int)blockIdx.x - pp.split : (int)blockIdx.x;          // CTA index / count inside its problem
@@ -122,7 +126,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
   if (pp.wait_first) pdl_sync();
   stage_wt(smem + L::off_w2, smem + L::off_w2 + kWTile, p.W2, HID, threadIdx.x, kThreadsB);
-  stage_wt(smem + L::off_w1, smem + L::off_w1 + kWTile, p.W1, kin, threadIdx.x, kThreadsB);
+  if (!half_mode) stage_wt(smem + L::off_w1, smem + L::off_w1 + kWTile, p.W1, kin, threadIdx.x, kThreadsB);
   if (!pp.wait_first) pdl_sync();   // the weights above are parameters; bn / cvec / g_o / y / r / a / gmax below come from the previous kernels
   // BN-backward constants: g_y = ka*g_o - kd*y + (kd*mean - ke)      (ka = rstd*gamma, kd = rstd^2*c2, ke = rstd*c1)
   if (threadIdx.x < HID) {
@@ -136,8 +140,9 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *s_tmem;
-  // gradient normalisation: S = 2^e with S * max|g_o| * max|ka| ~ 2^-6 (the other BN-backward terms are of the same order; fp16
-  // leaves 2^22 of headroom above that, and values are clamped to the fp16 range before conversion)
+  // gradient normalisation: S = 2^e with S * max|g_o| * max|ka| in [2^7, 2^8): the other BN-backward terms are of the same order
+  // and g_u = g_r * mask sums 64 weighted terms, so fp16's 2^16 keeps 2^8 of headroom (values are clamped to the fp16 range
+  // before conversion), while entries down to 2^-22 of the largest one keep the full 22-bit two-term precision
   float S = 1.f;
   {
     float kamax = 0.f;
@@ -147,7 +152,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
     if (bound > 0.f && bound < 3.0e38f) {
       int e;
       (void)frexpf(bound, &e);                               // bound = m * 2^e, m in [0.5, 1)
-      S = exp2f((float)max(-100, min(100, -6 - e)));
+      S = exp2f((float)max(-100, min(100, 8 - e)));
     }
   }
   const float invS = 1.f / S;
@@ -193,7 +198,9 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) { go[0][q] = 0.f; yy[0][q] = 0.f; rr[0][q] = 0.f; }
         }
-        if (!waited) { mbar_wait(&bars[B_D2 + s], (uint32_t)((use - 1) & 1)); waited = true; if (pt == 0) BWDH_TRACE(1, i); }   // G2 / G4 of the stage's previous tile are done
+        if (!waited) {                                          // the stage's previous tile: G2 / G4 (half mode: G1 / G3) are done
+          mbar_wait(&bars[(half_mode ? B_D1 : B_D2) + s], (uint32_t)((use - 1) & 1)); waited = true; if (pt == 0) BWDH_TRACE(1, i);
+        }
         uint32_t hi[4], lo[4], rh[4], rl[4];
         unsigned bits = 0;
 #pragma unroll
@@ -236,6 +243,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       unsigned char* Y = Ys(s);
       // the next tile's g_y / r go into the other stage while the tensor pipe works on this one
       if (i + 1 < my_tiles) phase1(i + 1);
+      if (half_mode) continue;
       // ---- phase 2 of tile i: a rows -> (after G1 / G3 have read Y) -> Y
       float aa[UPT][8];                                         // the thread's a rows are in flight during the wait
 #pragma unroll
@@ -272,6 +280,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       const int s = i & 1, use = i >> 1;
       const uint32_t xh = smem_u32(Xs(s)), xl = xh + kTile, yh = smem_u32(Ys(s)), yl = yh + kTile;
       mbar_wait(&bars[B_FULL1 + s], (uint32_t)(use & 1));
+      if (half_mode && use > 0) mbar_wait(&bars[B_GU + s], (uint32_t)((use - 1) & 1));   // the epilogue has read this D1 buffer's previous tile
       fence_after_sync();
       if (lane == 0) BWDH_TRACE(5, i);
       const uint32_t d1 = tmem + kColD1 + s * 128;
@@ -321,7 +330,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
     if (my_tiles > 0) g13(0);
     for (int i = 0; i < my_tiles; ++i) {
       if (i + 1 < my_tiles) g13(i + 1);
-      g24(i);
+      if (!half_mode) g24(i);
     }
   } else {
     // =========================================================================== epilogue
@@ -341,6 +350,28 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       fence_after_sync();
       if (threadIdx.x == 0) BWDH_TRACE(7, i);
       const uint32_t d1 = tmem + tl + kColD1 + s * 128;
+      if (half_mode) {                                          // g_a rows (in / out) += g_r; nothing goes back to the tensor pipe
+        const int gv = tile_base(i) + row;
+        const float k = invS * (1.f / kWScale);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float g[16], t2[16], old[16];
+          tmem_ld16_nowait(d1 + c0 + 16 * cc, g);
+          tmem_ld16_nowait(d1 + HID + c0 + 16 * cc, t2);
+          if (gv < p.V) { ld8(p.g_a + (size_t)gv * HID + c0 + 16 * cc, old); ld8(p.g_a + (size_t)gv * HID + c0 + 16 * cc + 8, old + 8); }
+          tmem_ld_wait();
+          if (gv < p.V) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] += fmaf(t2[j], kLo, g[j]) * k;
+            st8(p.g_a + (size_t)gv * HID + c0 + 16 * cc, old);
+            st8(p.g_a + (size_t)gv * HID + c0 + 16 * cc + 8, old + 8);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_GU + s]);
+        return;
+      }
       const uint2 m = s_mask[s * TM + row];
       const unsigned mbits = half == 0 ? m.x : m.y;
 #pragma unroll
@@ -399,7 +430,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
     if (my_tiles > 0) epi1(0);
     for (int i = 0; i < my_tiles; ++i) {
       if (i + 1 < my_tiles) epi1(i + 1);
-      epi2(i);
+      if (!half_mode) epi2(i);
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) s_db1[row * (HID + 1) + c0 + j] = db1[j];
@@ -412,7 +443,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
   // dW2 / dW1 from tensor memory: accumulator row L (TMEM lane L): L < 64 = hi part of out-channel L, L >= 64 = lo' part of
   // out-channel L - 64 (both summed over B_hi + B_lo).  dW[o][i] = (row o + 2^-11 row 64 + o) / S.
   float* s_x = reinterpret_cast<float*>(smem);          // [64][HID + 1] exchange buffer (the stages are dead)
-  for (int pass = 0; pass < 2; ++pass) {                // pass 0: dW2, pass 1: dW1
+  for (int pass = 0; pass < (half_mode ? 1 : 2); ++pass) {   // pass 0: dW2, pass 1: dW1
     const uint32_t col = pass == 0 ? kColD3 : kColD4;
     const int64_t offW = pass == 0 ? p.off_W2 : p.off_W1;
     float t[64];
@@ -451,7 +482,7 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
       s0 += s_db1[r * (HID + 1) + threadIdx.x]; s1 += s_db1[(r + 1) * (HID + 1) + threadIdx.x];
       s2 += s_db1[(r + 2) * (HID + 1) + threadIdx.x]; s3 += s_db1[(r + 3) * (HID + 1) + threadIdx.x];
     }
-    part[p.off_b1 + threadIdx.x] = ((s0 + s1) + (s2 + s3)) * invS;
+    if (!half_mode) part[p.off_b1 + threadIdx.x] = ((s0 + s1) + (s2 + s3)) * invS;
     float sum = 0.f;
 #pragma unroll
     for (int g = 0; g < LT / 8; ++g) sum += s_db2[g * HID + threadIdx.x];
@@ -467,12 +498,13 @@ gin_bwd_h_kernel(GinBwdMainPair pp) {
 // the same layer of both encoders (or the two K halves of the head MLP) in one launch: CTAs [0, split) write the partial
 // gradients of a0, [split, grid) of a1 (split as computed by pair_split on 128-row tile counts, as gin_bwd_tc2)
 void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s, bool weights_from_prev_kernel) {
-  static bool once = (cudaFuncSetAttribute(bwdh::gin_bwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdh::Smem::total), true);
+  static bool once = (cudaFuncSetAttribute(bwdh::gin_bwd_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdh::Smem::total), true);
   (void)once;
   GinBwdMainPair pp;
   pp.a[0] = a0; pp.a[1] = a1;
   pp.wait_first = weights_from_prev_kernel ? 1 : 0;
   pp.kin = kin;
+  pp.half = 0;
   pp.split = pair_split(grid, (a0.V + 127) / 128, (a1.V + 127) / 128);
   static int tr = -1;
   if (tr < 0) { const char* e = getenv("SCGIB_DBG"); tr = (e && (atoi(e) & 2048)) ? 1 : 0; }
@@ -480,7 +512,21 @@ void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& 
   static int rev = -1;
   if (rev < 0) { const char* e = getenv("SCGIB_BWD_REV"); rev = (e && e[0] == '0') ? 0 : 1; }
   pp.reverse = rev;
-  launch_k((bwdh::gin_bwd_h_kernel), dim3(grid), dim3(bwdh::kThreadsB), bwdh::Smem::total, s, pp);
+  launch_k((bwdh::gin_bwd_h_kernel<false>), dim3(grid), dim3(bwdh::kThreadsB), bwdh::Smem::total, s, pp);
+}
+
+// one linear layer on the same kernel (half mode): g_in (in / out) += g W;  dW = g^T x;  db = sum g      (gate_lin_bwd on tcgen05)
+void launch_linear_bwd_h(const float* g, const float* x, const float* W, int V, float* g_in, const float* bn_identity, const float* cvec_zero,
+                         const unsigned int* gmax, float* part, int64_t pstride, int64_t off_W, int64_t off_b, int grid, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(bwdh::gin_bwd_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdh::Smem::total), true);
+  (void)once;
+  GinBwdMainPair pp;
+  GinBwdMainArgs a;
+  a.g_o = g; a.y = x; a.r = x; a.a = x; a.bn = bn_identity; a.cvec = cvec_zero; a.W1 = W; a.W2 = W; a.V = V; a.g_a = g_in;
+  a.part = part; a.pstride = pstride; a.off_W1 = off_W; a.off_b1 = off_b; a.off_W2 = off_W; a.off_b2 = off_b; a.gmax = gmax;
+  pp.a[0] = a; pp.a[1] = a;
+  pp.split = grid; pp.kin = HID; pp.half = 1; pp.wait_first = 0; pp.trace = 0; pp.reverse = 0;
+  launch_k((bwdh::gin_bwd_h_kernel<true>), dim3(grid), dim3(bwdh::kThreadsB), bwdh::Smem::total, s, pp);
 }
 
 }  // namespace scgib

@@ -431,26 +431,28 @@ void launch_compressor_ema(const float* cstat, int B, float* running, int hidden
   else launch_k((compressor_ema_kernel<128>), dim3(1), dim3(1024), 0, s, cstat, B, running);
 }
 
-template <int HID>
-__global__ void __launch_bounds__(kThreads)
+// NT threads per CTA (measured at B = 4096, hidden 64: 256 threads / 512 CTAs and 512 threads / 256 CTAs - at 128 registers or
+// capped to 64 with spills for two resident CTAs per SM - all take 88 us: the kernel is bound by the per-graph dependent chains)
+template <int HID, int NT>
+__global__ void __launch_bounds__(NT)
 graph_gate_bwd_kernel(GraphGateBwdArgs p) {
   pdl_sync();
   constexpr int CPL = HID / 32;
   using V = LaneVec<CPL>;
-  __shared__ __align__(16) float s_red[(kThreads / 32) * 5 * HID];
+  __shared__ __align__(16) float s_red[(NT / 32) * 5 * HID];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = CPL * lane;
   const V gam = ldv<CPL>(p.gamma_c + c), bet = ldv<CPL>(p.beta_c + c), w2 = ldv<CPL>(p.wc2 + c), wc = ldv<CPL>(p.w_cand + c);
   V a_dg = zerov<CPL>(), a_db = zerov<CPL>(), a_dw2 = zerov<CPL>(), a_dwc = zerov<CPL>();
-  float a_dbc2 = 0.f;
-  const int warps = gridDim.x * (kThreads / 32);
+  float a_dbc2 = 0.f, gqmax = 0.f;
+  const int warps = gridDim.x * (NT / 32);
   auto dot = [](const V& a, const V& b) {
     float r = a.v[0] * b.v[0];
 #pragma unroll
     for (int k = 1; k < CPL; ++k) r += a.v[k] * b.v[k];
     return r;
   };
-  for (int g = blockIdx.x * (kThreads / 32) + warp; g < p.B; g += warps) {
+  for (int g = blockIdx.x * (NT / 32) + warp; g < p.B; g += warps) {
     const int v0 = __ldg(p.graph_ptr + g), v1 = __ldg(p.graph_ptr + g + 1);
     const float n = (float)(v1 - v0);
     const float* gs = p.gstat + (size_t)g * 4 * HID;
@@ -590,22 +592,28 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
           gq.v[k] = rstd.v[k] * (gam.v[k] * go - m1.v[k] - qh * m2.v[k]);
         }
         stv<CPL>(p.g_q + (size_t)v * HID + c, gq);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) gqmax = fmaxf(gqmax, fabsf(gq.v[k]));
       }
     }
+  }
+  if (p.gmax_q) {                // max is order-independent: the atomic keeps the result deterministic
+    gqmax = warp_max(gqmax);
+    if (lane == 0 && gqmax > 0.f) atomicMax(p.gmax_q, __float_as_uint(gqmax));
   }
   // ---- parameter-gradient partials: warp -> CTA -> last CTA
   float* r = s_red + warp * 5 * HID;
   stv<CPL>(r + c, a_dg); stv<CPL>(r + HID + c, a_db); stv<CPL>(r + 2 * HID + c, a_dw2); stv<CPL>(r + 3 * HID + c, a_dwc);
   if (lane == 0) r[4 * HID] = a_dbc2;
   __syncthreads();
-  for (int j = threadIdx.x; j < 4 * HID + 1; j += kThreads) {
+  for (int j = threadIdx.x; j < 4 * HID + 1; j += NT) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += s_red[w * 5 * HID + j];
+    for (int w = 0; w < NT / 32; ++w) s += s_red[w * 5 * HID + j];
     p.part[(size_t)blockIdx.x * 5 * HID + j] = s;
   }
   if (!last_cta_arrives(p.counter)) return;
-  for (int j = threadIdx.x; j < 4 * HID + 1; j += kThreads) {
+  for (int j = threadIdx.x; j < 4 * HID + 1; j += NT) {
     // four interleaved partial sums: 32 independent loads in flight instead of a chain of ~300 L2 round trips
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const int nb = (int)gridDim.x;
@@ -628,9 +636,14 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
   }
 }
 void launch_graph_gate_bwd(const GraphGateBwdArgs& a, int hidden, cudaStream_t s) {
-  const int grid = min((a.B + 7) / 8, 4 * num_sms());   // latency-bound warp-per-graph loops: as many resident warps as fit
-  if (hidden == 64) launch_k((graph_gate_bwd_kernel<64>), dim3(grid), dim3(kThreads), 0, s, a);
-  else launch_k((graph_gate_bwd_kernel<128>), dim3(grid), dim3(kThreads), 0, s, a);
+  // latency-bound warp-per-graph loops: as many resident warps as fit
+  if (hidden == 64) {
+    const int grid = min((a.B + 7) / 8, 4 * num_sms());
+    launch_k((graph_gate_bwd_kernel<64, kThreads>), dim3(grid), dim3(kThreads), 0, s, a);
+  } else {
+    const int grid = min((a.B + 7) / 8, 4 * num_sms());
+    launch_k((graph_gate_bwd_kernel<128, kThreads>), dim3(grid), dim3(kThreads), 0, s, a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -99,6 +99,7 @@ void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid,
 struct GinBwdMainPair {
   GinBwdMainArgs a[2]; int split; int trace; int reverse = 0;
   int kin = HID;            // gin_bwd_h: input width of the layer (32 | 64)
+  int half = 0;             // gin_bwd_h: one linear layer only (G1 / G3; g_a rows += g_r)
   int wait_first = 0;       // PDL: W1 / W2 are written by the kernel launched right before this one (the head backward's de-interleaved
                             //  W1 halves): wait for it before staging the weights instead of after
 };
@@ -111,6 +112,8 @@ void launch_gin_bwd_main_bf16(const GinBwdMainArgs& a0, const GinBwdMainArgs* a1
                               bool ga_f32 = false);      // ga_f32: g_a is written as fp32 also for kin == hidden (head backward)
 void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& a1, int kin, int grid, cudaStream_t s,
                                 bool weights_from_prev_kernel = false);     // tcgen05, two-term fp16 splits, 128-row tiles (gin_bwd_h.cu); kin 32 | 64
+void launch_linear_bwd_h(const float* g, const float* x, const float* W, int V, float* g_in, const float* bn_identity, const float* cvec_zero,
+                         const unsigned int* gmax, float* part, int64_t pstride, int64_t off_W, int64_t off_b, int grid, cudaStream_t s);
 void launch_absmax(const float* x, size_t n, unsigned int* slot, cudaStream_t s);   // atomicMax(slot, bits of max |x|)
 int bwd_h_mode();                                                          // SCGIB_BWD_H: 1 (default) gin_bwd_h.cu for the KIN = 64 layers and the head
 int bwd_tensor_core_mode();                                                                // SCGIB_TC_BWD: 1 gin_bwd_tc2.cu (default), 0 FFMA cross-check
@@ -207,6 +210,7 @@ struct GraphGateBwdArgs {
   float* part;                           // [grid][5*HID]: dgamma_c, dbeta_c, dwc2, dw_cand, (dbc2 at [4*HID])
   unsigned int* counter;
   float *d_gamma_c, *d_beta_c, *d_wc2, *d_bc2, *d_attn_w, *d_attn_b;   // final gradients
+  unsigned int* gmax_q = nullptr;        // optional: atomicMax of the bits of max |g_q| (gradient scale of the tensor-core gate_lin backward)
   // optional (con_g1p != nullptr): contrastive_bwd_finalize fused into the per-graph warp - g_core / g_readout are formed
   // from the contrastive kernel's column-split partials [con_jsplit][B][HID] (g_core / g_readout above are then unused)
   const float *con_g1p = nullptr, *con_g2p = nullptr, *con_z1 = nullptr, *con_z2 = nullptr, *con_n1 = nullptr, *con_n2 = nullptr;
