@@ -72,6 +72,15 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// non-blocking test of an mbarrier phase (true: the phase with this parity has completed)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 template <int KIN, int PW>
 __global__ void __launch_bounds__((kEpiWarps + 1 + PW) * 32, 1)
 gin_fwd_tc3_kernel(GinFwdPair pp) {
@@ -187,10 +196,17 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
       prod_sync();
       if (pt == 0) TC3_TRACE(1, i);
       // ---- [2] one tile ahead: window of tile i+1 into the other stage (free once GEMM1 of tile i-1 has read it; its
-      //          mapped row ids arrived with the group above), indices of tile i+2, index range of tile i+3
-      if (i + 1 < my_tiles) {
-        if (i >= 1) mbar_wait(&bars[B_EMPTY_A + (s ^ 1)], (uint32_t)(((i - 1) >> 1) & 1));
-        copy_window(i + 1);
+      //          mapped row ids arrived with the group above), indices of tile i+2, index range of tile i+3.
+      //          GEMM1 of tile i-1 was issued only when the previous iteration ended, so the stage is normally NOT free yet:
+      //          waiting here cost ~1 us of every ~5.5 us tile period (role timeline).  If it is not free, the copy is issued
+      //          after the gather of this tile instead, and the window is pulled into L2 meanwhile so that the late copy is short.
+      bool window_issued = i + 1 >= my_tiles;
+      if (!window_issued) {
+        if (i < 1 || mbar_test(&bars[B_EMPTY_A + (s ^ 1)], (uint32_t)(((i - 1) >> 1) & 1))) { copy_window(i + 1); window_issued = true; }
+        else if (!p.row_map) {
+          const int ws1 = win_start(i + 1), wn1 = min(WIN, p.V - ws1);
+          for (int l = pt; l < wn1 * (KIN / 32); l += PT) prefetch_l2(p.in + (size_t)ws1 * KIN + (size_t)l * 32);
+        }
       }
       if (i + 2 < my_tiles) stage_indices(i + 2, nb_begin, nb_end);
       cp_async_commit();
@@ -225,6 +241,10 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
             agg[j] = add4(agg[j], act(h));
           }
         }
+      }
+      if (!window_issued) {                                     // (block-uniform) the deferred window copy: GEMM1 of tile i-1 is long done
+        mbar_wait(&bars[B_EMPTY_A + (s ^ 1)], (uint32_t)(((i - 1) >> 1) & 1));
+        copy_window(i + 1);
       }
       // ---- [4] every producer has finished reading the raw window: overwrite the stage with the hi/lo operand tiles
       prod_sync();
