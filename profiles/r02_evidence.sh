@@ -1,5 +1,6 @@
 # Round-2 evidence run (gpurun): GPU tests, smoke, every kept bench line, ncu launch list + full captures of the GIN kernels.
-#   gpurun --timeout 1500 -- 'bash profiles/r02_evidence.sh'   -> gpurun_out/ev/*; summarised into profiles/ by the commands in DESIGN.md
+#   gpurun --timeout 1500 -- 'bash profiles/r02_evidence.sh'   -> gpurun_out/ev/* (tests, bench lines, ncu launch list)
+#   gpurun --timeout 900 -- 'bash profiles/r02_evidence_ncu.sh' -> gpurun_out/*.ncu-rep (full captures; kept small: gpurun_out/ is capped at 64 MiB)
 set -x
 mkdir -p gpurun_out/ev
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/ev/pytest_gpu.txt
@@ -25,8 +26,4 @@ b finetune_pep_dims64_bf16 --workload finetune --shape peptides --batch 1024 --d
 b finetune_pcqm --workload finetune --shape pcqm --batch 4096 --no-cpu-baseline --steps 50
 b logm_k1 --recons_type logM --no-cpu-baseline --steps 50
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/plain_fp32.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 200 --csv --log-file gpurun_out/ev/r02_ncu_launches_fp32.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/ncu_launches.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/plain_fp32b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gin_ -s 24 -c 12 -f -o gpurun_out/r02_prof_fp32_gin python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/ncu_full.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --dtype bf16 > gpurun_out/ev/plain_bf16.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gin_ -s 24 -c 12 -f -o gpurun_out/r02_prof_bf16_gin python bench.py --steps 2 --warmup 3 --no-cpu-baseline --dtype bf16 > gpurun_out/ev/ncu_full_bf16.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/plain_fp32c.log 2>&1 && ncu --set full --clock-control none -k regex:"contrastive|head_fwd_tc|recon|graph_gate|gate_lin|input_proj|ego_pool|fwd_prep|reduce_partials" -s 20 -c 16 -f -o gpurun_out/r02_prof_fp32_other python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ev/ncu_full_other.log 2>&1
-tail -2 gpurun_out/ev/ncu_full.log
 cat gpurun_out/ev/pytest_gpu.txt gpurun_out/ev/smoke.txt
