@@ -890,11 +890,15 @@ extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int3
   q.src = g_next; q.indptr = indptr; q.indices = indptr ? indices : nullptr; q.map = nullptr;
   q.y = y; q.bn = bn; q.V = V; q.g_o = w.g_o; q.part = w.part2; q.counter = w.counter;
   q.d_gamma = dgamma; q.d_beta = dbeta; q.cvec = w.cvec;
+  const bool use_h = bwd_tensor_core_mode() != 0 && bwd_h_mode() != 0 && (((uintptr_t)y | (uintptr_t)r | (uintptr_t)a | (uintptr_t)g_a) & 31u) == 0;
+  q.gmax = use_h ? w.counter + 32 : nullptr;         // max |g_o| for the fp16-split kernel's gradient normalisation (zeroed above)
   launch_gin_bwd_pre(q, HID, s);
   GinBwdMainArgs m;
   m.g_o = w.g_o; m.y = y; m.r = r; m.a = a; m.bn = bn; m.cvec = w.cvec; m.W1 = W1; m.W2 = W2; m.V = V; m.g_a = g_a;
   m.part = w.ppart; m.pstride = w.pstride; m.off_W1 = w.off[0]; m.off_b1 = w.off[1]; m.off_W2 = w.off[2]; m.off_b2 = w.off[3];
-  if (bwd_tensor_core_mode() != 0) launch_gin_bwd_main_tc2(m, kin, GP, s);
+  m.gmax = w.counter + 32;
+  if (use_h) launch_gin_bwd_main_h(m, kin, GP, s);
+  else if (bwd_tensor_core_mode() != 0) launch_gin_bwd_main_tc2(m, kin, GP, s);
   else launch_gin_bwd_main(m, kin, HID, GP, s);
   // per-CTA partials -> the four gradient tensors (fixed order)
   float* outs[4] = {dW1, db1, dW2, db2};

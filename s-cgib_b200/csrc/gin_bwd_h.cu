@@ -515,6 +515,15 @@ void launch_gin_bwd_main_h_pair(const GinBwdMainArgs& a0, const GinBwdMainArgs& 
   launch_k((bwdh::gin_bwd_h_kernel<false>), dim3(grid), dim3(bwdh::kThreadsB), bwdh::Smem::total, s, pp);
 }
 
+void launch_gin_bwd_main_h(const GinBwdMainArgs& a, int kin, int grid, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(bwdh::gin_bwd_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdh::Smem::total), true);
+  (void)once;
+  GinBwdMainPair pp;
+  pp.a[0] = a; pp.a[1] = a;
+  pp.split = grid; pp.kin = kin; pp.half = 0; pp.wait_first = 0; pp.trace = 0; pp.reverse = 0;
+  launch_k((bwdh::gin_bwd_h_kernel<false>), dim3(grid), dim3(bwdh::kThreadsB), bwdh::Smem::total, s, pp);
+}
+
 // one linear layer on the same kernel (half mode): g_in (in / out) += g W;  dW = g^T x;  db = sum g      (gate_lin_bwd on tcgen05)
 void launch_linear_bwd_h(const float* g, const float* x, const float* W, int V, float* g_in, const float* bn_identity, const float* cvec_zero,
                          const unsigned int* gmax, float* part, int64_t pstride, int64_t off_W, int64_t off_b, int grid, cudaStream_t s) {

@@ -210,3 +210,20 @@ def test_device_loader_reshuffles_every_pass():
     assert not torch.equal(first, second) and torch.equal(first.sort()[0], second.sort()[0])
     loader.set_epoch(0)
     assert torch.equal(torch.cat([ids for ids in loader.id_batches()]).cpu(), first)      # the DP override still pins the order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"SCGIB_FWD4": "1"}, {"SCGIB_BWD_H": "0"}, {"SCGIB_HEAD_FFMA": "1", "SCGIB_CON_FFMA": "1"},
+                                 {"SCGIB_RECON_SIDE": "1"}], ids=["tc4_forward", "tc2_backward", "ffma_head_contrastive", "recon_side"])
+def test_implementation_switches_stay_parity_green(env):
+    """The experimental / cross-check kernels behind the environment switches pass the same parity tests as
+    the defaults: the tensor-core-aggregation forward gin_tc4, the 3xTF32 backward, the FFMA head / contrastive kernels with
+    the un-fused forward tail, recon_bwd as side CTAs.  The switches are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
+                        "gin_layer or golden_reference_parity or faithful_oracle or loss_operators"],
+                       cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
