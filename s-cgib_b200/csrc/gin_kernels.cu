@@ -631,8 +631,14 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
   pdl_sync();
   __shared__ float s_g[PT * (DTR + 1)];
   __shared__ float s_x[PT * (FP + 1)];
-  const int o = threadIdx.x & 31, fg = threadIdx.x >> 5;  // thread owns dWt[o][fg*4 .. fg*4+3]
+  const int o = threadIdx.x & 31, fg = threadIdx.x >> 5;  // wide features: thread owns dWt[o][fg*4 .. fg*4+3]
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // F <= 16 (molecular features: 9 / 11): thread (o, row slice fg) accumulates ALL features of the rows r = fg (mod 8) - a
+  // quarter of the shared-memory loads and FMAs of the padded mapping above; the 8 slices are summed once per CTA
+  const bool narrow = p.F <= 16;
+  float acc16[16];
+#pragma unroll
+  for (int f = 0; f < 16; ++f) acc16[f] = 0.f;
   const int tiles0 = (p.V[0] + PT - 1) / PT, tiles1 = (p.V[1] + PT - 1) / PT;
   for (int t = blockIdx.x; t < tiles0 + tiles1; t += gridDim.x) {
     const int set = t < tiles0 ? 0 : 1;
@@ -692,16 +698,42 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
       }
     }
     __syncthreads();
-    for (int r = 0; r < PT; ++r) {
-      const float g = s_g[r * (DTR + 1) + o];
-      const float* xr = s_x + r * (FP + 1) + fg * 4;
-      acc[0] = fmaf(g, xr[0], acc[0]); acc[1] = fmaf(g, xr[1], acc[1]);
-      acc[2] = fmaf(g, xr[2], acc[2]); acc[3] = fmaf(g, xr[3], acc[3]);
+    if (narrow) {
+      for (int r = fg; r < PT; r += kThreads / 32) {
+        const float g = s_g[r * (DTR + 1) + o];
+        const float* xr = s_x + r * (FP + 1);
+#pragma unroll
+        for (int f = 0; f < 16; ++f) acc16[f] = fmaf(g, xr[f], acc16[f]);
+      }
+    } else {
+      for (int r = 0; r < PT; ++r) {
+        const float g = s_g[r * (DTR + 1) + o];
+        const float* xr = s_x + r * (FP + 1) + fg * 4;
+        acc[0] = fmaf(g, xr[0], acc[0]); acc[1] = fmaf(g, xr[1], acc[1]);
+        acc[2] = fmaf(g, xr[2], acc[2]); acc[3] = fmaf(g, xr[3], acc[3]);
+      }
     }
   }
   float* part = p.part + (size_t)blockIdx.x * DTR * FP;
+  if (narrow) {                        // sum the 8 row slices in a fixed order (s_x is free: every tile is done)
+    __syncthreads();
+    float* s_acc = s_x;                // [8 slices][32 o][16 f]
 #pragma unroll
-  for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
+    for (int f = 0; f < 16; ++f) s_acc[(fg * 32 + o) * 16 + f] = acc16[f];
+    __syncthreads();
+    for (int i = threadIdx.x; i < DTR * FP; i += kThreads) {
+      const int oo = i / FP, f = i % FP;
+      float t = 0.f;
+      if (f < 16) {
+#pragma unroll
+        for (int sl = 0; sl < kThreads / 32; ++sl) t += s_acc[(sl * 32 + oo) * 16 + f];
+      }
+      part[i] = t;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
+  }
   if (!last_cta_arrives(p.counter)) return;
   // only the F real feature columns; four interleaved partial sums per output keep 32 loads in flight (the chain of
   // ~300 dependent L2 round trips was the whole cost of this kernel); combined in a fixed order

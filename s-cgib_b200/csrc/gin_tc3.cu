@@ -135,16 +135,33 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
 
   if (warp > kMmaWarp) {
     // =========================================================================== producers
-    constexpr int LPR = KIN / 4, RPP = PT / LPR, NR = (TM + RPP - 1) / RPP;   // lanes per row, rows per pass, passes (last one guarded)
+    // A lane owns EIGHT channels of a row (two float4: channel quads gl and gl + LPR, so that the 8 lanes of a row read 128
+    // contiguous bytes per load - no bank conflicts): the per-row index work of the gather (edge range, neighbour index, window
+    // offset, halo test) - most of the loop's instructions in the ncu source profile - is replicated in 8 instead of 16 lanes
+    constexpr int LPR = KIN / 8, RPP = PT / LPR, NR = (TM + RPP - 1) / RPP;   // lanes per row, rows per pass, passes (last one guarded)
     const int pt = (warp - (kMmaWarp + 1)) * 32 + lane;
     const int gl = pt % LPR, gr = pt / LPR;
     int* s_ip = reinterpret_cast<int*>(smem + L::off_ip);
     int* s_self = reinterpret_cast<int*>(smem + L::off_self);
     int* s_ix = reinterpret_cast<int*>(smem + L::off_ix);
-    Bn4 bn;
     const bool has_bn = (p.bn_in != nullptr);
-    if (has_bn) { bn.mean = ld4(s_bn + gl * 4); bn.rstd = ld4(s_bn + HID + gl * 4); bn.gamma = ld4(s_bn + 2 * HID + gl * 4); bn.beta = ld4(s_bn + 3 * HID + gl * 4); }
-    auto act = [&](float4 h) { return has_bn ? bn.act(h) : h; };
+    // relu(BN(y)) = max((y - mean) * (rstd * gamma) + beta, 0) for this lane's two channel quads
+    float4 mu[2], sc[2], be[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mu[h] = make4(0.f); sc[h] = make4(1.f); be[h] = make4(0.f);
+      if (has_bn) {
+        const int c = (gl + LPR * h) * 4;
+        const float4 rs = ld4(s_bn + HID + c), ga = ld4(s_bn + 2 * HID + c);
+        mu[h] = ld4(s_bn + c); be[h] = ld4(s_bn + 3 * HID + c);
+        sc[h] = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+      }
+    }
+    auto act = [&](float4 y, int h) {
+      if (!has_bn) return y;
+      return make_float4(fmaxf(fmaf(y.x - mu[h].x, sc[h].x, be[h].x), 0.f), fmaxf(fmaf(y.y - mu[h].y, sc[h].y, be[h].y), 0.f),
+                         fmaxf(fmaf(y.z - mu[h].z, sc[h].z, be[h].z), 0.f), fmaxf(fmaf(y.w - mu[h].w, sc[h].w, be[h].w), 0.f));
+    };
     auto prod_sync = [&]() { asm volatile("bar.sync 1, %0;" :: "n"(PT) : "memory"); };
     // raw window of stage s: plain row-major [WIN][KIN] at the start of the stage
     auto raw_of = [&](int s) { return reinterpret_cast<float*>(smem + L::off_stage + s * kStageBytes); };
@@ -217,7 +234,7 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
       const int* ix = s_ix + buf * kIdxCap;
       const float* raw = raw_of(s);
       const int e_begin = ip[0];
-      float4 agg[NR];
+      float4 agg[NR][2];
       int e0[NR], deg[NR], maxd = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
@@ -226,7 +243,9 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
         e0[j] = ip[r] - e_begin;
         deg[j] = ok ? ip[r + 1] - ip[r] : 0;
         maxd = max(maxd, deg[j]);
-        agg[j] = ok ? act(ld4(raw + (base - ws + r) * KIN + gl * 4)) : make4(0.f);
+        const float* src = raw + (base - ws + r) * KIN + gl * 4;
+        agg[j][0] = ok ? act(ld4(src), 0) : make4(0.f);
+        agg[j][1] = ok ? act(ld4(src + LPR * 4), 1) : make4(0.f);
       }
       for (int d = 0; d < maxd; ++d) {
 #pragma unroll
@@ -235,10 +254,10 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
             const int e = e0[j] + d;
             const int u = (e < kIdxCap) ? ix[e] : __ldg(p.indices + e_begin + e);
             const int ul = u - ws;
-            float4 h;
-            if ((unsigned)ul < (unsigned)WIN) h = ld4(raw + ul * KIN + gl * 4);
-            else h = ld4(p.in + (size_t)(p.row_map ? __ldg(p.row_map + u) : u) * KIN + gl * 4);   // neighbour beyond the halo
-            agg[j] = add4(agg[j], act(h));
+            const float* src = (unsigned)ul < (unsigned)WIN ? raw + ul * KIN + gl * 4
+                                                            : p.in + (size_t)(p.row_map ? __ldg(p.row_map + u) : u) * KIN + gl * 4;   // beyond the halo: global
+            agg[j][0] = add4(agg[j][0], act(ld4(src), 0));
+            agg[j][1] = add4(agg[j][1], act(ld4(src + LPR * 4), 1));
           }
         }
       }
@@ -255,8 +274,12 @@ gin_fwd_tc3_kernel(GinFwdPair pp) {
       for (int j = 0; j < NR; ++j) {
         const int r = gr + j * RPP;
         if (r < TM) {
-          if (p.a_out && base + r < p.V) st4_cs(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j]);
-          store_split4_s(hi, lo, TM, r, gl, agg[j]);
+          if (p.a_out && base + r < p.V) {
+            st4_cs(p.a_out + (size_t)(base + r) * KIN + gl * 4, agg[j][0]);
+            st4_cs(p.a_out + (size_t)(base + r) * KIN + (gl + LPR) * 4, agg[j][1]);
+          }
+          store_split4_s(hi, lo, TM, r, gl, agg[j][0]);
+          store_split4_s(hi, lo, TM, r, gl + LPR, agg[j][1]);
         }
       }
       fence_smem_to_async();
