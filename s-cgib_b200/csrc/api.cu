@@ -389,6 +389,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
   const bool fuse_tail = !features_only && tc64 && use_tc_contrastive();
   {
     GateLinFwdArgs a{w.y[0][L - 1], w.bn[0][L - 1], b->N, w.comp_w1t, params + lo.off[SCGIB_P_COMP_B1], w.H, w.q, bf};
+    a.Wc1n = params + lo.off[SCGIB_P_COMP_W1];
     PROF("gate_lin_fwd", launch_gate_lin_fwd(a, HID, s));
   }
   {

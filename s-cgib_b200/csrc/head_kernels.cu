@@ -131,6 +131,13 @@ static void launch_gate_lin_fwd_t(const GateLinFwdArgs& a, cudaStream_t s) {
   launch_k((gate_lin_fwd_kernel<BF, H>), dim3(grid), dim3(kThreads), sizeof(GateLinFwdSmem<H>), s, a);
 }
 void launch_gate_lin_fwd(const GateLinFwdArgs& a, int hidden, cudaStream_t s) {
+  static int gate_ffma = -1;                 // SCGIB_HEAD_FFMA=1: FFMA tiles also at hidden 64 (cross-check)
+  if (gate_ffma < 0) { const char* e = getenv("SCGIB_HEAD_FFMA"); gate_ffma = (e && e[0] == '1') ? 1 : 0; }
+  if (hidden == 64 && a.Wc1n && tensor_core_mode() != 0 && !gate_ffma &&
+      ((((uintptr_t)a.y | (uintptr_t)a.H | (uintptr_t)a.q) & 31u) == 0)) {
+    launch_gate_lin_fwd_tc(a, a.Wc1n, s);
+    return;
+  }
   if (hidden == 64) { if (a.y_bf16) launch_gate_lin_fwd_t<true, 64>(a, s); else launch_gate_lin_fwd_t<false, 64>(a, s); }
   else { if (a.y_bf16) launch_gate_lin_fwd_t<true, 128>(a, s); else launch_gate_lin_fwd_t<false, 128>(a, s); }
 }

@@ -71,6 +71,10 @@ __device__ __forceinline__ void stage_weight16(unsigned char* dst, const float* 
   }
 }
 
+// GATE = true: the compressor's first layer on the same pipeline (one GEMM): H = relu(BN(y)) is formed by the producers (and
+// stored), q = H Wc1^T + bc1 by epilogue 1; arguments: noisy = y, bn = {mean, rstd, gamma, beta}, W1n = Wc1 [64][64], b1 = bc1,
+// r = H (out), Z = q (out).
+template <bool GATE>
 __global__ void __launch_bounds__(kThreadsH, 1)
 head_fwd_tc_kernel(HeadFwdArgs p) {
   using L = Smem;
@@ -97,9 +101,12 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
   }
   if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
   // parameters only (they precede the programmatic-dependency wait: the weights are never written inside a step's forward)
-  stage_weight16<2 * HID>(smem + L::off_w1, p.W1n, threadIdx.x, kThreadsH);
-  stage_weight16<HID>(smem + L::off_w2, p.W2n, threadIdx.x, kThreadsH);
-  if (threadIdx.x < HID) { s_b1[threadIdx.x] = p.b1[threadIdx.x]; s_b2[threadIdx.x] = p.b2[threadIdx.x]; }
+  if (GATE) stage_weight16<HID>(smem + L::off_w1, p.W1n, threadIdx.x, kThreadsH);
+  else {
+    stage_weight16<2 * HID>(smem + L::off_w1, p.W1n, threadIdx.x, kThreadsH);
+    stage_weight16<HID>(smem + L::off_w2, p.W2n, threadIdx.x, kThreadsH);
+  }
+  if (threadIdx.x < HID) { s_b1[threadIdx.x] = p.b1[threadIdx.x]; s_b2[threadIdx.x] = GATE ? 0.f : p.b2[threadIdx.x]; }
   pdl_sync();
   fence_smem_to_async();
   fence_before_sync();
@@ -110,6 +117,55 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
   if (warp > kMmaWarp) {
     // =========================================================================== producers: [noisy || alpha C] -> fp16 hi / lo tiles
     const int pt = (warp - (kMmaWarp + 1)) * 32 + lane;
+    if (GATE) {
+      const int c8 = pt & 7, r0 = pt >> 3;                      // 8-channel chunk of the 64, first row (rows r0 + 32 j)
+      const int c = c8 * 8;
+      float mu[8], sc[8], be[8];                                // relu(BN(y)) = max((y - mean) * (rstd * gamma) + beta, 0)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { mu[q] = p.bn[c + q]; sc[q] = p.bn[HID + c + q] * p.bn[2 * HID + c + q]; be[q] = p.bn[3 * HID + c + q]; }
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i & 1, use = i >> 1;
+        const int base = tile_base(i);
+        if (use > 0) mbar_wait(&bars[B_EMPTY + s], (uint32_t)((use - 1) & 1));
+        unsigned char* ahi = smem + L::off_a + s * kStage;
+        unsigned char* alo = ahi + 2 * kABlk;
+        float v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int gv = base + r0 + 32 * j;
+          if (gv < p.N) {
+            if (p.in_bf16) {                                    // bf16 mode: y is bf16 storage
+              const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16_t*>(p.noisy) + (size_t)gv * HID + c);
+              v[j][0] = bf16_lo(w.x); v[j][1] = bf16_hi(w.x); v[j][2] = bf16_lo(w.y); v[j][3] = bf16_hi(w.y);
+              v[j][4] = bf16_lo(w.z); v[j][5] = bf16_hi(w.z); v[j][6] = bf16_lo(w.w); v[j][7] = bf16_hi(w.w);
+            } else {
+              ld8(p.noisy + (size_t)gv * HID + c, v[j]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[j][q] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = r0 + 32 * j, gv = base + r;
+          if (gv < p.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[j][q] = fmaxf(fmaf(v[j][q] - mu[q], sc[q], be[q]), 0.f);
+            st8(p.r + (size_t)gv * HID + c, v[j]);
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_f16x2_s11(fminf(v[j][2 * q], 65504.f), fminf(v[j][2 * q + 1], 65504.f), hi[q], lo[q]);
+          const int off = tile_b_off(r, c8);
+          *reinterpret_cast<uint4*>(ahi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(alo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_smem_to_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_FULL + s]);
+      }
+    } else {
     const int ch = pt & 15, r0 = pt >> 4;                       // this thread's 8-channel chunk of the 128 and its first row
     const bool second = ch >= 8;                                // alpha C half
     const int c8 = ch & 7;
@@ -159,6 +215,7 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_FULL + s]);
     }
+    }
   } else if (warp == kMmaWarp) {
     // =========================================================================== MMA issuer (converged warp, elected lane)
     const uint32_t w1 = smem_u32(smem + L::off_w1), w2 = smem_u32(smem + L::off_w2);
@@ -170,7 +227,7 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
       const uint32_t ah = smem_u32(smem + L::off_a + s * kStage), al = ah + 2 * kABlk;
       const uint32_t d = tmem + s * kStageCols + kColD1;
 #pragma unroll
-      for (int k = 0; k < 2 * HID / 16; ++k) {
+      for (int k = 0; k < (GATE ? HID : 2 * HID) / 16; ++k) {
         const uint32_t kb = (uint32_t)(k >> 2);
         const uint64_t db = desc_b_kmajor(w1 + kb * 2 * kW1Blk, k & 3);        // hi tile; the N = 128 view continues into the lo' tile
         mma_h(d, desc_b_kmajor(ah + kb * kABlk, k & 3), db, kId2, k > 0);
@@ -196,7 +253,7 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
     if (my_tiles > 0) gemm1(0);
     for (int i = 0; i < my_tiles; ++i) {
       if (i + 1 < my_tiles) gemm1(i + 1);
-      gemm2(i);
+      if (!GATE) gemm2(i);
     }
   } else {
     // =========================================================================== epilogue
@@ -218,6 +275,18 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
       tmem_ld16_nowait(t0 + kColD1 + HID + c0, *reinterpret_cast<float (*)[16]>(v2));
       tmem_ld16_nowait(t0 + kColD1 + HID + c0 + 16, *reinterpret_cast<float (*)[16]>(v2 + 16));
       tmem_ld_wait();
+      if (GATE) {                                               // q = H Wc1^T + bc1: no activation, nothing goes back to the tensor pipe
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_E2 + s]);           // the stage's TMEM columns may be overwritten by its next tile
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(fmaf(v2[j], kLoScale, v[j]), kInv, s_b1[c0 + j]);
+        if (gv < p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st8(p.Z + (size_t)gv * HID + c0 + 8 * j, v + 8 * j);
+        }
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(fmaf(v2[j], kLoScale, v[j]), kInv, s_b1[c0 + j]), 0.f);
       uint32_t hi[16], lo[16];
@@ -266,7 +335,7 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
     if (my_tiles > 0) epi1(0);
     for (int i = 0; i < my_tiles; ++i) {
       if (i + 1 < my_tiles) epi1(i + 1);
-      epi2(i);
+      if (!GATE) epi2(i);
     }
   }
   fence_before_sync();
@@ -276,10 +345,20 @@ head_fwd_tc_kernel(HeadFwdArgs p) {
 }  // namespace htc
 
 void launch_head_fwd_tc(const HeadFwdArgs& a, cudaStream_t s) {
-  static bool once = (cudaFuncSetAttribute(htc::head_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, htc::Smem::total), true);
+  static bool once = (cudaFuncSetAttribute(htc::head_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, htc::Smem::total), true);
   (void)once;
   const int grid = max(1, min((a.N + htc::TM - 1) / htc::TM, num_sms()));
-  launch_k((htc::head_fwd_tc_kernel), dim3(grid), dim3(htc::kThreadsH), htc::Smem::total, s, a);
+  launch_k((htc::head_fwd_tc_kernel<false>), dim3(grid), dim3(htc::kThreadsH), htc::Smem::total, s, a);
+}
+
+// H = relu(BN(y)); q = H Wc1^T + bc1 on the same pipeline (hidden 64, fp32 y)
+void launch_gate_lin_fwd_tc(const GateLinFwdArgs& g, const float* Wc1, cudaStream_t s) {
+  static bool once = (cudaFuncSetAttribute(htc::head_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, htc::Smem::total), true);
+  (void)once;
+  HeadFwdArgs a{};
+  a.noisy = g.y; a.bn = g.bn; a.N = g.N; a.W1n = Wc1; a.b1 = g.bc1; a.r = g.H; a.Z = g.q; a.in_bf16 = g.y_bf16;
+  const int grid = max(1, min((a.N + htc::TM - 1) / htc::TM, num_sms()));
+  launch_k((htc::head_fwd_tc_kernel<true>), dim3(grid), dim3(htc::kThreadsH), htc::Smem::total, s, a);
 }
 
 }  // namespace scgib

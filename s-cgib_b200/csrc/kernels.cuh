@@ -142,6 +142,7 @@ struct GateLinFwdArgs {
   const float* Wc1t; const float* bc1;   // Wc1t [HID][HID] k-major
   float* H; float* q;
   bool y_bf16 = false;
+  const float* Wc1n = nullptr;           // natural [HID][HID]: when set (hidden 64, fp32 y) the tensor-core kernel runs
 };
 void launch_gate_lin_fwd(const GateLinFwdArgs& a, int hidden, cudaStream_t s);
 
@@ -230,11 +231,14 @@ struct HeadFwdArgs {
   float* Z;                              // [N][HID]
   bf16_t* r_bf = nullptr;                // optional bf16 copies of r and alpha*C (bf16 mode: operands of the head backward)
   bf16_t* aC_bf = nullptr;
+  bool in_bf16 = false;                         // head_tc.cu GATE mode only: `noisy` (= y) is bf16 storage
+  const float* bn = nullptr;                    // head_tc.cu GATE mode only: {mean, rstd, gamma, beta}[HID] of the producing layer
   const float *W1n = nullptr, *W2n = nullptr;   // natural [HID][2*HID], [HID][HID]: when set (hidden 64, fp32 saves) the tensor-core
                                                 //  kernel head_tc.cu runs instead of the FFMA tiles
 };
 void launch_head_fwd(const HeadFwdArgs& a, int hidden, cudaStream_t s);
 void launch_head_fwd_tc(const HeadFwdArgs& a, cudaStream_t s);
+void launch_gate_lin_fwd_tc(const GateLinFwdArgs& g, const float* Wc1, cudaStream_t s);   // compressor.0 forward on the same tensor-core pipeline
 
 // Head backward = the GIN backward kernel run on the two K = H halves of the first head layer (api.cu).
 // prep: dense copies W1a = W1[:, :HID], W1b = W1[:, HID:] and the identity BatchNorm-backward constants
