@@ -164,12 +164,15 @@ struct Ws {
   float *rpart, *G, *edge;
   float *z1, *z2, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *g_core, *g_readout, *zsplit;
   float *gZ, *gI, *gp, *g_q, *gH, *gC, *g_o[2], *Ga[2], *ga0[2];
+  float* xagg[2];       // aggregated normalised features of the parent / ego rows, [V][xagg_stride] (transfer_d backward)
   float *logm_walks, *logm_gram, *logm_pair, *logm_loss;     // --recons_type logM (logm_kernels.cu)
   float *aC, *head_w1a, *head_w1b, *head_bn, *head_cvec;     // tensor-core head backward (the GIN backward kernel on two K halves)
   bf16_t *noisy_bf, *aC_bf, *r_head_bf, *gZ_bf;              // bf16 mode: its operands in bf16 (the bf16 GIN backward kernel)
   float* ppart;
   size_t bytes;
 };
+
+static inline int xagg_stride(const ScgibDims* d) { return (d->in_dim + 3) / 4 * 4; }
 
 static size_t small_part_floats(int N, int Ns, int HID) {
   const int Vmax = N > Ns ? N : Ns;
@@ -228,6 +231,7 @@ static Ws carve(const ScgibDims* d, const Layout& lo, int B, int N, int E, int N
   w.Ga[0] = take_act((size_t)N * HID); w.Ga[1] = take_act((size_t)Ns * HID);
   (void)Vmax;
   w.ga0[0] = take((size_t)N * DTR); w.ga0[1] = take((size_t)Ns * DTR);
+  w.xagg[0] = take((size_t)N * xagg_stride(d)); w.xagg[1] = take((size_t)Ns * xagg_stride(d));
   w.logm_walks = take((size_t)logm_max_steps() * N); w.logm_gram = take(B); w.logm_pair = take(N); w.logm_loss = take(4);
   w.aC = take((size_t)N * HID); w.head_w1a = take(HID * HID); w.head_w1b = take(HID * HID);
   w.head_bn = take(4 * HID); w.head_cvec = take(2 * HID);
@@ -347,6 +351,11 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       cudaMemcpyAsync(w.t, b->t_override, (size_t)b->N * DTR * sizeof(float), cudaMemcpyDeviceToDevice, s);
     else {
       pa.x = b->x; pa.Wt = params + lo.off[SCGIB_P_TRANSFER]; pa.N = b->N; pa.F = d->in_dim; pa.normalize = b->normalize_x; pa.t = w.t;
+      if (!eval) {      // the backward pass of this step contracts the layer-0 input gradients with the aggregated features
+        pa.xa_indptr[0] = b->indptr; pa.xa_indptr[1] = b->sub_indptr; pa.xa_indices[0] = b->indices; pa.xa_indices[1] = b->sub_indices;
+        pa.xa_map = b->ego_nodes; pa.xa_V[0] = b->N; pa.xa_V[1] = b->Ns;
+        pa.xagg[0] = w.xagg[0]; pa.xagg[1] = w.xagg[1]; pa.xa_stride = xagg_stride(d);
+      }
     }
     PROF("fwd_prep", launch_fwd_prep(pa, s, bf));
   }
@@ -633,10 +642,8 @@ static int backward_impl(const ScgibDims* d, const float* params, const ScgibBat
   }
   {
     InputProjBwdArgs a;
-    a.ga[0] = w.ga0[0]; a.ga[1] = w.ga0[1];
-    a.indptr[0] = b->indptr; a.indptr[1] = b->sub_indptr; a.indices[0] = b->indices; a.indices[1] = b->sub_indices;
-    a.map[0] = nullptr; a.map[1] = b->ego_nodes; a.V[0] = b->N; a.V[1] = b->Ns;
-    a.x = b->x; a.F = d->in_dim; a.normalize = b->normalize_x; a.part = w.small_part; a.counter = w.counters + 3;
+    a.ga[0] = w.ga0[0]; a.ga[1] = w.ga0[1]; a.xagg[0] = w.xagg[0]; a.xagg[1] = w.xagg[1]; a.xa_stride = xagg_stride(d);
+    a.V[0] = b->N; a.V[1] = b->Ns; a.F = d->in_dim; a.part = w.small_part; a.counter = w.counters + 3;
     a.d_Wt = grads + lo.off[SCGIB_P_TRANSFER];
     PROF("input_proj_bwd", launch_input_proj_bwd(a, s));
   }

@@ -57,11 +57,46 @@ void launch_input_proj_fwd(const float* x, const float* Wt, int N, int F, int no
 // (CTAs [0, nproj)), the k-major weight copies of the FFMA kernels (one CTA per job) and the head backward's operand
 // preparation (8 CTAs: W1a = W1[:, :H], W1b = W1[:, H:], identity BatchNorm-backward constants).
 // ------------------------------------------------------------------------------------------------
+// one thread per row of {parent rows, ego rows}: xagg_v = x_hat[p(v)] + sum_{u in N(v)} x_hat[p(u)], FC >= F columns in registers
+template <int FC>
+__device__ __forceinline__ void xagg_rows(const FwdPrepArgs& p, int cta) {
+  const int V0 = p.xa_V[0], V1 = p.xa_V[1], F = p.F;
+  for (int i = cta * kThreads + threadIdx.x; i < V0 + V1; i += p.nxagg * kThreads) {
+    const int set = i < V0 ? 0 : 1, v = set == 0 ? i : i - V0;
+    const int32_t* indices = p.xa_indices[set];
+    const int32_t* map = set == 0 ? nullptr : p.xa_map;
+    const int e0 = __ldg(p.xa_indptr[set] + v), e1 = __ldg(p.xa_indptr[set] + v + 1);
+    float acc[FC];
+#pragma unroll
+    for (int f = 0; f < FC; ++f) acc[f] = 0.f;
+    for (int e = e0 - 1; e < e1; ++e) {          // e0 - 1: the row itself
+      const int u = e < e0 ? v : __ldg(indices + e);
+      const float* xr = p.x + (size_t)(map ? __ldg(map + u) : u) * F;
+      float xv[FC];
+      float ss = 0.f;
+#pragma unroll
+      for (int f = 0; f < FC; ++f) { xv[f] = f < F ? __ldg(xr + f) : 0.f; ss = fmaf(xv[f], xv[f], ss); }
+      const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+#pragma unroll
+      for (int f = 0; f < FC; ++f) acc[f] = fmaf(xv[f], inv, acc[f]);
+    }
+    float* d = p.xagg[set] + (size_t)v * p.xa_stride;
+#pragma unroll
+    for (int f = 0; f < FC; f += 4)
+      if (f < p.xa_stride) st4(d + f, make_float4(acc[f], acc[f + 1], acc[f + 2], acc[f + 3]));
+  }
+}
+
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(kThreads) fwd_prep_kernel(FwdPrepArgs p) {
   pdl_sync();
   __shared__ __align__(16) float s_w[32 * DTR];  // [f][o]
-  const int b = (int)blockIdx.x;
+  int b = (int)blockIdx.x;
+  if (b < p.nxagg) {
+    if (p.F <= 12) xagg_rows<12>(p, b); else xagg_rows<32>(p, b);
+    return;
+  }
+  b -= p.nxagg;
   if (b < p.nproj) {
     const int F = p.F;
     for (int i = threadIdx.x; i < F * DTR; i += kThreads) {
@@ -106,7 +141,8 @@ __global__ void __launch_bounds__(kThreads) fwd_prep_kernel(FwdPrepArgs p) {
 }
 void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16) {
   a.nproj = a.x ? min((a.N + 31) / 32, 148 * 8) : 0;
-  const int grid = a.nproj + a.jobs.n + (a.headW1 ? 8 : 0);
+  a.nxagg = (a.x && a.xagg[0]) ? min((a.xa_V[0] + a.xa_V[1] + kThreads - 1) / kThreads, 148 * 8) : 0;
+  const int grid = a.nxagg + a.nproj + a.jobs.n + (a.headW1 ? 8 : 0);
   if (grid == 0) return;
   if (out_bf16) launch_k((fwd_prep_kernel<true>), dim3(grid), dim3(kThreads), 0, s, a);
   else launch_k((fwd_prep_kernel<false>), dim3(grid), dim3(kThreads), 0, s, a);
@@ -619,125 +655,80 @@ void launch_gin_bwd_main(const GinBwdMainArgs& a, int kin, int hidden, int grid,
 }
 
 // ------------------------------------------------------------------------------------------------
-// transfer_d backward: dWt[o][f] = sum_rows gt_row[o] * x_hat[map(row)][f],
-//   gt_row = Ga0_row + sum_{u in N(row)} Ga0_u   (layer-0 aggregation backward; Ga0 is [V][DTR])
+// transfer_d backward: dWt[o][f] = sum_rows gt_row[o] * x_hat[map(row)][f] with gt_row = Ga0_row + sum_{u in N(row)} Ga0_u
+// (layer-0 aggregation backward; Ga0 is [V][DTR]).  The adjacency is symmetric, so the gather moves to the features:
+//   dWt[o][f] = sum_u Ga0_u[o] * xagg_u[f],   xagg_u = x_hat[p(u)] + sum_{v in N(u)} x_hat[p(v)]
+// xagg is a constant of the batch, produced by side CTAs of the forward's prologue launch (fwd_prep); this kernel only
+// streams Ga0 and xagg (it was a latency-bound CSR gather of 128-byte rows before: 59 us at B = 4096).
 // Two row sets (parent batch, ego batch) in one launch; last CTA finalises into grads.
 // ------------------------------------------------------------------------------------------------
-constexpr int PT = 128;   // rows per tile
-constexpr int FP = 32;    // padded feature width
+constexpr int FP = 32;    // padded feature width of a partial row
+constexpr int IPB_THREADS = 1024;   // 32 warps per CTA, one CTA per SM: 148 partials for the final (last-CTA) reduction
 
-__global__ void __launch_bounds__(kThreads)
+// lane = output channel o of transfer_d; every warp streams 32-row blocks straight from global memory (coalesced 128-byte
+// Ga0 rows, xagg rows one per lane and broadcast by shuffles) into acc[f] = sum_r Ga0_r[o] xagg_r[f]
+template <int FC>
+__global__ void __launch_bounds__(IPB_THREADS, 1)
 input_proj_bwd_kernel(InputProjBwdArgs p) {
   pdl_sync();
-  __shared__ float s_g[PT * (DTR + 1)];
-  __shared__ float s_x[PT * (FP + 1)];
-  const int o = threadIdx.x & 31, fg = threadIdx.x >> 5;  // wide features: thread owns dWt[o][fg*4 .. fg*4+3]
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  // F <= 16 (molecular features: 9 / 11): thread (o, row slice fg) accumulates ALL features of the rows r = fg (mod 8) - a
-  // quarter of the shared-memory loads and FMAs of the padded mapping above; the 8 slices are summed once per CTA
-  const bool narrow = p.F <= 16;
-  float acc16[16];
+  __shared__ __align__(16) float s_red[32 * 32 * 4];     // [warp][o][4 features]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int V0 = p.V[0], Vt = p.V[0] + p.V[1], XS = p.xa_stride;
+  const int nwarps = (int)gridDim.x * 32;
+  const int gw = (int)blockIdx.x * 32 + warp;
+  for (int fb = 0; fb < XS; fb += FC) {      // FC feature columns per pass over the rows (one pass for F <= 16)
+  float acc[FC];
 #pragma unroll
-  for (int f = 0; f < 16; ++f) acc16[f] = 0.f;
-  const int tiles0 = (p.V[0] + PT - 1) / PT, tiles1 = (p.V[1] + PT - 1) / PT;
-  for (int t = blockIdx.x; t < tiles0 + tiles1; t += gridDim.x) {
-    const int set = t < tiles0 ? 0 : 1;
-    const int base = (set == 0 ? t : t - tiles0) * PT;
-    const int V = p.V[set];
-    const float* ga = p.ga[set];
-    const int32_t* indptr = p.indptr[set];
-    const int32_t* indices = p.indices[set];
-    const int32_t* map = p.map[set];
-    __syncthreads();
-    // x rows of the tile: issued first so that they are in flight during the gather (threads < PT own one row each)
-    float xv[9];
-    bool x_small = p.F <= 9, x_ok = false;
-    const float* xr = nullptr;
-    if (threadIdx.x < PT) {
-      const int v = base + threadIdx.x;
-      x_ok = v < V;
-      if (x_ok) {
-        xr = p.x + (size_t)(map ? __ldg(map + v) : v) * p.F;
-        if (x_small) {
+  for (int f = 0; f < FC; ++f) acc[f] = 0.f;
+  // blocks of 32 rows: lane j holds xagg of row j (coalesced), broadcast by shuffles against the row's Ga0 line
+  for (int rb = gw * 32; rb < Vt; rb += nwarps * 32) {
+    float4 xm[FC / 4];
+    {
+      const int r = rb + lane;
+      const int set = r < V0 ? 0 : 1, v = r < V0 ? r : r - V0;
+      const float* xr = p.xagg[set] + (size_t)v * XS + fb;
 #pragma unroll
-          for (int f = 0; f < 9; ++f) xv[f] = f < p.F ? __ldg(xr + f) : 0.f;
+      for (int q = 0; q < FC / 4; ++q) xm[q] = (r < Vt && fb + q * 4 < XS) ? ld4_cs(xr + q * 4) : make4(0.f);
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rb + j0 + j;
+        const int set = r < V0 ? 0 : 1, v = r < V0 ? r : r - V0;
+        g[j] = r < Vt ? __ldcs(p.ga[set] + (size_t)v * DTR + lane) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < FC / 4; ++q) {
+          acc[q * 4 + 0] = fmaf(g[j], __shfl_sync(0xffffffffu, xm[q].x, j0 + j), acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(g[j], __shfl_sync(0xffffffffu, xm[q].y, j0 + j), acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(g[j], __shfl_sync(0xffffffffu, xm[q].z, j0 + j), acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(g[j], __shfl_sync(0xffffffffu, xm[q].w, j0 + j), acc[q * 4 + 3]);
         }
-      }
-    }
-    {  // gather gt rows: 8 lanes x float4 per row, the thread's 4 rows in flight together (latency-bound gather)
-      const int l = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-      constexpr int NR = PT / (kThreads / 8);
-      int vv[NR];
-      float4 g[NR];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) vv[j] = base + r0 + j * (kThreads / 8);
-      gather_aggregate<DTR, NR>(ga, nullptr, indptr, indices, V, vv, l, nullptr, g);
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        float* d = s_g + (r0 + j * (kThreads / 8)) * (DTR + 1) + l * 4;
-        d[0] = g[j].x; d[1] = g[j].y; d[2] = g[j].z; d[3] = g[j].w;
-      }
-    }
-    if (threadIdx.x < PT) {  // x_hat rows -> shared memory
-      float* d = s_x + threadIdx.x * (FP + 1);
-      if (x_ok && x_small) {
-        float ss = 0.f;
-#pragma unroll
-        for (int f = 0; f < 9; ++f) ss = fmaf(xv[f], xv[f], ss);
-        const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-#pragma unroll
-        for (int f = 0; f < 9; ++f) d[f] = xv[f] * inv;
-        for (int f = 9; f < FP; ++f) d[f] = 0.f;
-      } else if (x_ok) {
-        float ss = 0.f;
-        for (int f = 0; f < p.F; ++f) { const float a = __ldg(xr + f); ss = fmaf(a, a, ss); }
-        const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-        for (int f = 0; f < FP; ++f) d[f] = f < p.F ? __ldg(xr + f) * inv : 0.f;
-      } else {
-        for (int f = 0; f < FP; ++f) d[f] = 0.f;
-      }
-    }
-    __syncthreads();
-    if (narrow) {
-      for (int r = fg; r < PT; r += kThreads / 32) {
-        const float g = s_g[r * (DTR + 1) + o];
-        const float* xr = s_x + r * (FP + 1);
-#pragma unroll
-        for (int f = 0; f < 16; ++f) acc16[f] = fmaf(g, xr[f], acc16[f]);
-      }
-    } else {
-      for (int r = 0; r < PT; ++r) {
-        const float g = s_g[r * (DTR + 1) + o];
-        const float* xr = s_x + r * (FP + 1) + fg * 4;
-        acc[0] = fmaf(g, xr[0], acc[0]); acc[1] = fmaf(g, xr[1], acc[1]);
-        acc[2] = fmaf(g, xr[2], acc[2]); acc[3] = fmaf(g, xr[3], acc[3]);
-      }
     }
   }
+  // CTA partial [o][f] (stride FP): the 32 warps are summed in a fixed order, four feature columns at a time
   float* part = p.part + (size_t)blockIdx.x * DTR * FP;
-  if (narrow) {                        // sum the 8 row slices in a fixed order (s_x is free: every tile is done)
-    __syncthreads();
-    float* s_acc = s_x;                // [8 slices][32 o][16 f]
 #pragma unroll
-    for (int f = 0; f < 16; ++f) s_acc[(fg * 32 + o) * 16 + f] = acc16[f];
+  for (int q = 0; q < FC / 4; ++q) {
     __syncthreads();
-    for (int i = threadIdx.x; i < DTR * FP; i += kThreads) {
-      const int oo = i / FP, f = i % FP;
+    st4(s_red + (warp * 32 + lane) * 4, make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int o = threadIdx.x >> 2, k = threadIdx.x & 3;
       float t = 0.f;
-      if (f < 16) {
 #pragma unroll
-        for (int sl = 0; sl < kThreads / 32; ++sl) t += s_acc[(sl * 32 + oo) * 16 + f];
-      }
-      part[i] = t;
+      for (int w = 0; w < 32; ++w) t += s_red[(w * 32 + o) * 4 + k];
+      part[o * FP + fb + q * 4 + k] = t;
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) part[o * FP + fg * 4 + i] = acc[i];
+  }
   }
   if (!last_cta_arrives(p.counter)) return;
-  // only the F real feature columns; four interleaved partial sums per output keep 32 loads in flight (the chain of
-  // ~300 dependent L2 round trips was the whole cost of this kernel); combined in a fixed order
-  for (int o2 = threadIdx.x; o2 < DTR * p.F; o2 += kThreads) {
+  // only the F real feature columns; interleaved partial sums keep the loads of a thread independent; fixed order
+  for (int o2 = threadIdx.x; o2 < DTR * p.F; o2 += IPB_THREADS) {
     const int oo = o2 / p.F, f = o2 % p.F;
     const float* src = p.part + oo * FP + f;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -756,10 +747,13 @@ input_proj_bwd_kernel(InputProjBwdArgs p) {
 }
 
 int input_proj_bwd_grid(int V0, int V1) {
-  return min((V0 + PT - 1) / PT + (V1 + PT - 1) / PT, 2 * num_sms());
+  (void)V0; (void)V1;
+  return num_sms();
 }
 void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s) {
-  launch_k((input_proj_bwd_kernel), dim3(input_proj_bwd_grid(a.V[0], a.V[1])), dim3(kThreads), 0, s, a);
+  const int grid = input_proj_bwd_grid(a.V[0], a.V[1]);
+  if (a.F <= 12) launch_k((input_proj_bwd_kernel<12>), dim3(grid), dim3(IPB_THREADS), 0, s, a);
+  else launch_k((input_proj_bwd_kernel<16>), dim3(grid), dim3(IPB_THREADS), 0, s, a);
 }
 
 }  // namespace scgib

@@ -69,7 +69,9 @@ ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
 }
 void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, int hidden, cudaStream_t s) {
   const int spc = kThreads / (hidden / 4);
-  const int grid = min((a.N + spc - 1) / spc, 16 * num_sms());
+  static int full = -1;          // SCGIB_EGO_GRID=full: one CTA pass per 16 seeds, no grid-stride tail (experiment)
+  if (full < 0) { const char* e = getenv("SCGIB_EGO_GRID"); full = (e && e[0] == 'f') ? 1 : 0; }
+  const int grid = full ? (a.N + spc - 1) / spc : min((a.N + spc - 1) / spc, 16 * num_sms());
   if (hidden == 64) {
     if (a.y_bf16) launch_k((ego_pool_fwd_kernel<true, 64>), dim3(grid), dim3(kThreads), 0, s, a);
     else launch_k((ego_pool_fwd_kernel<false, 64>), dim3(grid), dim3(kThreads), 0, s, a);
@@ -495,7 +497,7 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
     for (int k = 0; k < CPL; ++k) isd.v[k] = 1.f / (sd.v[k] + kKlEps);
     // ---- attention pass A: S = sum_v alpha_v (gT_v . C_v)
     float S = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int v = v0; v < v1; ++v) {
       const V gT = ldv<CPL>(p.gI2 + (size_t)v * p.gI_stride + c), C = ldv<CPL>(p.C + (size_t)v * HID + c);
       S += __ldg(p.alpha + v) * warp_sum(dot(gT, C));
@@ -576,18 +578,19 @@ graph_gate_bwd_kernel(GraphGateBwdArgs p) {
 #pragma unroll
     for (int k = 0; k < CPL; ++k) { m1.v[k] /= n; m2.v[k] /= n; }
     __syncwarp();
-    // ---- pass C: per-graph BN backward -> g_q
-    for (int vb = v0; vb < v1; vb += RB) {
-      float gpv[RB];
-      V q[RB];
+    // ---- pass C: per-graph BN backward -> g_q (two loads per row: 8 rows in flight)
+    constexpr int RBC = 8;
+    for (int vb = v0; vb < v1; vb += RBC) {
+      float gpv[RBC];
+      V q[RBC];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
+      for (int i = 0; i < RBC; ++i) {
         const int v = min(vb + i, v1 - 1);
         gpv[i] = __ldcg(p.gp + v);
         q[i] = ldv<CPL>(p.q + (size_t)v * HID + c);
       }
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
+      for (int i = 0; i < RBC; ++i) {
         const int v = vb + i;
         if (v >= v1) break;
         V gq;

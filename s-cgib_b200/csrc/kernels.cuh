@@ -22,7 +22,11 @@ struct FwdPrepArgs {
   TransposeJobs jobs;
   const float* headW1 = nullptr; float *W1a = nullptr, *W1b = nullptr, *bn = nullptr, *cvec = nullptr; int hid = 64;
   const float* x = nullptr; const float* Wt = nullptr; int N = 0, F = 0, normalize = 0; float* t = nullptr;
-  int nproj = 0;                       // set by the launcher
+  // aggregated normalised features xagg_v = x_hat[p(v)] + sum_{u in N(v)} x_hat[p(u)] of the parent rows and the ego rows
+  // (a constant of the batch: the transfer_d backward contracts the layer-0 input gradient with it, input_proj_bwd)
+  const int32_t* xa_indptr[2] = {nullptr, nullptr}; const int32_t* xa_indices[2] = {nullptr, nullptr};
+  const int32_t* xa_map = nullptr; int xa_V[2] = {0, 0}; float* xagg[2] = {nullptr, nullptr}; int xa_stride = 0;
+  int nproj = 0, nxagg = 0;            // set by the launcher
 };
 void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16);
 
@@ -121,13 +125,10 @@ int bwd_tensor_core_mode();                                                     
 
 struct InputProjBwdArgs {
   const float* ga[2];       // layer-0 input gradients of the two encoders, [V][DTR]
-  const int32_t* indptr[2];
-  const int32_t* indices[2];
-  const int32_t* map[2];    // row -> parent node (null = identity)
+  const float* xagg[2];     // aggregated normalised features of the rows, [V][xa_stride] (fwd_prep)
+  int xa_stride;
   int V[2];
-  const float* x;           // [N][F] features
   int F;
-  int normalize;            // apply F.normalize to x rows
   float* part;              // [grid][DTR*32]
   unsigned int* counter;
   float* d_Wt;              // [DTR][F]
