@@ -385,6 +385,76 @@ def run_finetune(args, emit):
 
 
 # ----------------------------------------------------------------------------------------------------
+def run_encoder_variant(args, emit):
+    """--encoder GraphSAGE / GCN (reference models.py:75-104): graphs/s of the pre-training step through the drop-in module
+    (models.Mainmodel composed from the operator kernels, s-cgib_b200/encoders.py) with torch.optim.Adam over the module's
+    parameters - the loop body of exp_pretraining.train_epoch_pre_training.  One GPU; `value` from batches resident in HBM,
+    `e2e` from pinned host batches with the per-step loss read."""
+    import types
+    import torch.nn.functional as F
+    import models as dropin_models
+    from scgib_b200.graph import khop_ego_batch
+    from scgib_b200.synth import synth_batch
+    dev = torch.device("cuda", 0)
+    H, B = args.dims, args.batch
+    ns = types.SimpleNamespace(recons_type="adj", useAtt=1, readout_f="sum", d_transfer=32, device=str(dev), batch_size=B,
+                               k_transition=args.k, dtype="fp32")
+    torch.manual_seed(0)
+    dm = dropin_models.Mainmodel(ns, 9, H, 4, 4, args.k, args.encoder).to(dev)
+    dm.train()
+    opt = torch.optim.Adam(dm.parameters(), lr=1e-4, weight_decay=5e-5)      # exp_pretraining.py:86
+    nb = 4
+    host = [synth_batch(1000 + i, B).pin_memory() for i in range(nb)]
+    resident = [h.to(dev) for h in host]
+    state = {}
+
+    def run_steps(src, steps, read):
+        for i in range(steps):
+            bg = src[i % nb].to(dev, non_blocking=True)
+            bx = F.normalize(bg.ndata["x"].float())
+            opt.zero_grad()
+            ego = khop_ego_batch(bg, args.k)
+            _, kl, con, rec = dm.forward(bg, bx, ego, None, None, 1, None, 2, dev, B)
+            loss = kl + rec + con
+            loss.backward()
+            opt.step()
+            if read:
+                state["loss"] = loss.detach().item()
+        state["shape"] = (bg.num_nodes(), bg.num_edges(), int(ego.sub_indptr.numel() - 1), int(ego.sub_indices.numel()))
+
+    def timed(src, steps, read):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_steps(src, steps, read); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    run_steps(resident, max(args.warmup, 3), False)
+    sampler = make_clock_sampler(0, 0)
+    sampler.start()
+    ms = timed(resident, args.steps, False)
+    clocks = sampler.stop()
+    run_steps(host, 3, True)
+    ms_e2e = timed(host, args.steps, True)
+    N, E, Ns, Es = state["shape"]
+    h2d = sum(t_.numel() * t_.element_size() for t_ in (host[0].graph_ptr, host[0].indptr, host[0].indices, host[0].ndata["x"]))
+    launches = {"GraphSAGE": 2 * (3 + 3 + 6 * 2 + 9), "GCN": 2 * (3 + 3 + 6 + 6)}[args.encoder] + 24
+    line = {"metric": "pretrain graphs/s (PCQM4Mv2-shape %s x%d k=%d, operator-composed step)" % (args.encoder, H, args.k),
+            "value": B * args.steps / (ms * 1e-3), "unit": "graphs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "S-CGIB pre-training step with --encoder %s (models.py:75-104): ego extraction + forward + backward + "
+                                   "torch Adam through models.Mainmodel, FP32 FFMA operator kernels, batch %d synthetic PCQM4Mv2-shape "
+                                   "graphs, k_transition=%d" % (args.encoder, B, args.k),
+                       "nodes": N, "edges": E, "ego_rows": Ns, "ego_edges": Es,
+                       "l2": "no flush: per-step working set exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches * args.steps}
+    emit(line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,6 +472,8 @@ def main():
     ap.add_argument("--dims", type=int, default=64, choices=[64, 128], help="hidden width (--dims of the reference CLI); 128 = BASELINE configs[4]")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
                     help="fp32 = the headline (reference precision); bf16 = bf16 activations + single-pass bf16 tensor-core MLPs in the GIN encoders")
+    ap.add_argument("--encoder", default="GIN", choices=["GIN", "GraphSAGE", "GCN"],
+                    help="GIN = the headline (fused tensor-core engine); GraphSAGE / GCN = the operator-composed variants (1 GPU)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -421,6 +493,12 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.encoder != "GIN":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+        if rank == 0:
+            run_encoder_variant(args, emit)
+        return
     if args.workload == "finetune":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")

@@ -30,7 +30,7 @@ def make_optimizer(model, lr):
     """reference exp_pretraining.py:86,112: Adam(lr, weight_decay=5e-5) over the model's parameters.  For the drop-in
     modules this is scgib_b200.optim.FlatAdam: the same update as ONE kernel over the flat parameter buffer (same
     zero_grad() / step() surface); SCGIB_TORCH_ADAM=1 keeps torch.optim.Adam on the parameter views."""
-    if hasattr(model, "_bridge") and os.environ.get("SCGIB_TORCH_ADAM", "0") != "1":
+    if getattr(model, "_bridge", None) is not None and os.environ.get("SCGIB_TORCH_ADAM", "0") != "1":
         from scgib_b200.optim import FlatAdam
         return FlatAdam(model, lr=lr, weight_decay=5e-5)
     return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=5e-5)

@@ -318,7 +318,7 @@ SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int
  * the units scgib_extract_forward/backward_f32 run fused.  hidden in {64, 128}.
  *
  *  scgib_core_gate_fwd/bwd_f32 : compress + compression (models.py:595-604, 631-660) on Hfeat = graph_features [N,H]
- *      (the Encoder1 output): q = compressor.0(H), per-graph BatchNorm (compressor.1, training mode), p = compressor.3(relu),
+ *      (the Encoder1 output, any sign): q = compressor.0(H), per-graph BatchNorm (compressor.1, training mode), p = compressor.3(relu),
  *      lambda = sigmoid(logit(eps(gate_u)) + p), noisy = lambda H + (1 - lambda) mu_g + feat_u (1 - lambda) sigma_g,
  *      graph_readout = sum_nodes(H), core_readout = sum_nodes(noisy), kl = KL of the LAST graph (models.py:657-659).
  *      bwd: gradients of <g_noisy, noisy> + <g_core, core_readout> + <g_readout, graph_readout> + kl_scale * kl; call after
@@ -355,6 +355,40 @@ SCGIB_API int scgib_head_mlp_bwd_f32(const float* gZ, const float* noisy, int32_
                                      void* workspace, size_t workspace_bytes, void* stream);
 SCGIB_API int scgib_segment_sum_bwd_f32(const float* g_out, const int32_t* seg_ptr, int32_t S, int32_t hidden, float* g_in,
                                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks of the --encoder GraphSAGE / GCN variants (models.py:75-104; csrc/encoder_ops.cu) and the transfer_d
+ * backward as operators.  FP32 FFMA tiles; widths W, K, O in {32, 64, 128, 256} (multiples of 32).  The adjacency is
+ * symmetric (molecular graphs and their induced ego-nets), so the backward of an aggregation is the same call with the two
+ * degree normalisations exchanged.
+ *
+ *  scgib_graph_aggregate_f32 : out[v] = (add ? add[v] : 0) + fd(deg v) sum_{u in N(v)} fs(deg u) in[map(u)]
+ *      norm codes: 0 = 1, 1 = 1 / max(deg, 1) (SAGEConv 'mean'), 2 = max(deg, 1)^-1/2 (GraphConv norm='both').
+ *  scgib_segment_sum_w_f32   : dgl.sum_nodes at any supported width.
+ *  scgib_linear_fwd_f32      : Y[V,O] = act(X0[map0] (.) (M0 > 0) W0 + X1 (.) (M1 > 0) W1 + bias); Wp is [O][Kp]
+ *      (nn.Linear, wp_kxo = 0) or [Kp][O] (GraphConv weight / a transposed product, wp_kxo = 1); Mp optional ReLU masks
+ *      (backward products g (.) (h > 0)); X1 NULL = one operand pair.
+ *  scgib_linear_bwd_w_f32    : dW (+)= (G (.) (M > 0))^T X[map] as [O][K] (kxo = 0) or [K][O] (kxo = 1), db (+)= column sums;
+ *      fixed-order two-stage reduction (bit-identical reruns).  O multiple of 64.  workspace 16-byte aligned.
+ *  scgib_transfer_bwd_f32    : d transfer_d.weight [32][F] = sum over two row sets of g_r (x) xrow_r, xrow_r = x_hat[p(r)]
+ *      (+ the x_hat rows of r's neighbours when a CSR is given).  workspace 256-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+SCGIB_API int scgib_graph_aggregate_f32(const float* in, int32_t W, const int32_t* row_map, const int32_t* indptr,
+                                        const int32_t* indices, int32_t V, int32_t src_norm, int32_t dst_norm,
+                                        const float* add, float* out, void* stream);
+SCGIB_API int scgib_segment_sum_w_f32(const float* in, const int32_t* seg_ptr, int32_t S, int32_t W, float* out, void* stream);
+SCGIB_API int scgib_linear_fwd_f32(const float* X0, const float* M0, const int32_t* map0, const float* W0, int32_t K0,
+                                   int32_t w0_kxo, const float* X1, const float* M1, const float* W1, int32_t K1,
+                                   int32_t w1_kxo, const float* bias, int32_t relu, int32_t V, int32_t O, float* Y, void* stream);
+SCGIB_API size_t scgib_linear_bwd_w_workspace_bytes(int32_t V, int32_t O, int32_t K);
+SCGIB_API int scgib_linear_bwd_w_f32(const float* G, const float* M, const float* X, const int32_t* map, int32_t V, int32_t O,
+                                     int32_t K, int32_t kxo, int32_t accumulate, float* dW, float* db, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+SCGIB_API size_t scgib_transfer_bwd_workspace_bytes(int32_t V0, int32_t V1, int32_t F);
+SCGIB_API int scgib_transfer_bwd_f32(const float* x, int32_t F, int32_t normalize, const float* g0, int32_t V0,
+                                     const int32_t* indptr0, const int32_t* indices0, const float* g1, int32_t V1,
+                                     const int32_t* indptr1, const int32_t* indices1, const int32_t* map1, float* dWt,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Debugging aid: byte offset of a named intermediate inside the pre-training workspace ("t", "H", "q", "C",
  * "alpha", "lam", "y<enc>_<layer>", "gH", ...), -1 if unknown.  Tests compare intermediates with the oracle. */

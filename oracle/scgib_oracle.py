@@ -154,6 +154,84 @@ class GIN(nn.Module):
         return act(h)
 
 
+class SAGEConvRef(nn.Module):
+    """DGL 1.1.x SAGEConv(in, out, 'mean') as models.py:94-96 builds it: rst = fc_self(h) + fc_neigh(mean_{u->v} h_u)
+    (mean = 0 for a node without in-edges; fc_self carries the bias, fc_neigh has none).  Written in the
+    aggregate-then-project order; DGL projects first when in > out (the same function)."""
+
+    def __init__(self, in_feats, out_feats):
+        super().__init__()
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_self = nn.Linear(in_feats, out_feats, bias=True)
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, g: TGraph, h):
+        deg = (g.indptr[1:] - g.indptr[:-1]).to(h.dtype).clamp(min=1)
+        neigh = torch.zeros_like(h).index_add(0, g.dst, h[g.src]) / deg[:, None]
+        return self.fc_self(h) + self.fc_neigh(neigh)
+
+
+class GraphSAGE(nn.Module):
+    """models.py:91-104: conv1, ReLU, conv2, ReLU, conv2 AGAIN (the forward never calls conv3: quirk kept), no final ReLU."""
+
+    def __init__(self, in_feats, h_feats):
+        super().__init__()
+        self.conv1 = SAGEConvRef(in_feats, h_feats)
+        self.conv2 = SAGEConvRef(h_feats, h_feats)
+        self.conv3 = SAGEConvRef(h_feats, h_feats)
+
+    def forward(self, g, h):
+        h = F.relu(self.conv1(g, h))
+        h = F.relu(self.conv2(g, h))
+        return self.conv2(g, h)
+
+
+class GraphConvRef(nn.Module):
+    """DGL 1.1.x GraphConv(in, out, norm='both', allow_zero_in_degree=True) as models.py:78-80 builds it:
+    rst = D_in^-1/2 A^T D_out^-1/2 h W + b, degrees clamped to 1, weight stored [in, out]."""
+
+    def __init__(self, in_feats, out_feats):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_feats, out_feats))
+        self.bias = nn.Parameter(torch.zeros(out_feats))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, g: TGraph, h):
+        # symmetric adjacency (bidirected molecular graphs and their induced ego-nets): in-degree = out-degree
+        nrm = torch.pow((g.indptr[1:] - g.indptr[:-1]).to(h.dtype).clamp(min=1), -0.5)
+        hs = h * nrm[:, None]
+        agg = torch.zeros_like(hs).index_add(0, g.dst, hs[g.src]) * nrm[:, None]
+        return agg @ self.weight + self.bias
+
+
+class GCN(nn.Module):
+    """models.py:75-88: widths in -> 2h -> 2h -> h, ReLU between, none after conv3."""
+
+    def __init__(self, num_features, hidden_dim=64):
+        super().__init__()
+        self.conv1 = GraphConvRef(num_features, hidden_dim * 2)
+        self.conv2 = GraphConvRef(hidden_dim * 2, hidden_dim * 2)
+        self.conv3 = GraphConvRef(hidden_dim * 2, hidden_dim)
+
+    def forward(self, g, h):
+        h = F.relu(self.conv1(g, h))
+        h = F.relu(self.conv2(g, h))
+        return self.conv3(g, h)
+
+
+def make_encoder(encoder, d_transfer, hidden_dim, num_gin_layers=4):
+    """models.py:573-587."""
+    if encoder == "GIN":
+        return GIN(d_transfer, hidden_dim, num_gin_layers)
+    if encoder == "GCN":
+        return GCN(d_transfer, hidden_dim)
+    if encoder == "GraphSAGE":
+        return GraphSAGE(d_transfer, hidden_dim)
+    raise SystemExit("Bug there is no pre-defined Encoders")
+
+
 class _LSTMHolder(nn.Module):
     """Stand-in for dgl.nn.Set2Set(hidden, 2, 1): only the parameter container (``s2s.lstm.*``)
     so that state_dict keys / parameter order / init RNG consumption match models.py:565."""
@@ -168,7 +246,7 @@ class OracleMainmodel(nn.Module):
     """models.py:546-782 (Mainmodel), GIN encoder, readout 'sum', recons_type 'adj', useAtt 1.
     Construction order follows models.py:547-593 so a seeded default init matches."""
 
-    def __init__(self, in_dim, hidden_dim=64, d_transfer=32, num_gin_layers=4):
+    def __init__(self, in_dim, hidden_dim=64, d_transfer=32, num_gin_layers=4, encoder="GIN"):
         super().__init__()
         self.hidden_dim = hidden_dim
         self.fc1 = nn.Linear(hidden_dim, 1)
@@ -181,8 +259,8 @@ class OracleMainmodel(nn.Module):
         self.reconstructX = nn.Sequential(nn.Linear(hidden_dim, d_transfer))
         self.MLP = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(),
                                  nn.Linear(hidden_dim, hidden_dim))
-        self.Encoder1 = GIN(d_transfer, hidden_dim, num_gin_layers)
-        self.Encoder2 = GIN(d_transfer, hidden_dim, num_gin_layers)
+        self.Encoder1 = make_encoder(encoder, d_transfer, hidden_dim, num_gin_layers)     # models.py:573-587
+        self.Encoder2 = make_encoder(encoder, d_transfer, hidden_dim, num_gin_layers)
         self.compressor = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim),
                                         nn.ReLU(), nn.Linear(hidden_dim, 1))
 

@@ -101,6 +101,17 @@ _SIGNATURES = {
     "scgib_head_mlp_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
     "scgib_head_mlp_bwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32] + [c_void_p] * 7 + [c_void_p, c_size_t, c_void_p]),
     "scgib_segment_sum_bwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "scgib_graph_aggregate_f32": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                          c_void_p, c_void_p]),
+    "scgib_segment_sum_w_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "scgib_linear_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "scgib_linear_bwd_w_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "scgib_linear_bwd_w_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scgib_transfer_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "scgib_transfer_bwd_f32": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scgib_profile_enable": (None, [c_int]),
     "scgib_profile_count": (c_int, []),
     "scgib_profile_get": (c_int, [c_int, POINTER(c_char_p), POINTER(c_float)]),

@@ -353,7 +353,7 @@ static int forward_impl(const ScgibDims* d, const float* params, float* bn_runni
       pa.x = b->x; pa.Wt = params + lo.off[SCGIB_P_TRANSFER]; pa.N = b->N; pa.F = d->in_dim; pa.normalize = b->normalize_x; pa.t = w.t;
       if (!eval) {      // the backward pass of this step contracts the layer-0 input gradients with the aggregated features
         pa.xa_indptr[0] = b->indptr; pa.xa_indptr[1] = b->sub_indptr; pa.xa_indices[0] = b->indices; pa.xa_indices[1] = b->sub_indices;
-        pa.xa_map = b->ego_nodes; pa.xa_V[0] = b->N; pa.xa_V[1] = b->Ns;
+        pa.xa_x = b->x; pa.xa_map = b->ego_nodes; pa.xa_V[0] = b->N; pa.xa_V[1] = b->Ns;
         pa.xagg[0] = w.xagg[0]; pa.xagg[1] = w.xagg[1]; pa.xa_stride = xagg_stride(d);
       }
     }
@@ -816,6 +816,43 @@ extern "C" SCGIB_API int scgib_input_proj_fwd_f32(const float* x, const float* W
   return (int)cudaGetLastError();
 }
 
+// transfer_d backward as an operator: dWt[o][f] = sum over both row sets of g_r[o] * xrow_r[f], xrow_r = x_hat[p(r)] (+ the
+// x_hat rows of r's neighbours when a CSR is given: the layer-0 aggregation backward of the GIN path moved to the features)
+extern "C" SCGIB_API size_t scgib_transfer_bwd_workspace_bytes(int32_t V0, int32_t V1, int32_t F) {
+  const size_t xs = (size_t)(F + 3) / 4 * 4;
+  return al((size_t)V0 * xs * 4) + al((size_t)V1 * xs * 4) + al((size_t)input_proj_bwd_grid(V0, V1) * DTR * 32 * 4) + 256;
+}
+extern "C" SCGIB_API int scgib_transfer_bwd_f32(const float* x, int32_t F, int32_t normalize, const float* g0, int32_t V0,
+                                                const int32_t* indptr0, const int32_t* indices0, const float* g1, int32_t V1,
+                                                const int32_t* indptr1, const int32_t* indices1, const int32_t* map1,
+                                                float* dWt, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !g0 || !dWt || !workspace || (V1 > 0 && (!g1 || !map1))) return SCGIB_E_NULL;
+  if (F < 1 || F > 32) return SCGIB_E_SHAPE;
+  if (V0 < 1 || V1 < 0) return SCGIB_E_RANGE;
+  if (((uintptr_t)workspace & 255u) != 0) return SCGIB_E_ALIGN;
+  if (workspace_bytes < scgib_transfer_bwd_workspace_bytes(V0, V1, F)) return SCGIB_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int xs = (F + 3) / 4 * 4;
+  char* p = (char*)workspace;
+  float* xa0 = (float*)p; p += al((size_t)V0 * xs * 4);
+  float* xa1 = (float*)p; p += al((size_t)V1 * xs * 4);
+  float* part = (float*)p; p += al((size_t)input_proj_bwd_grid(V0, V1) * DTR * 32 * 4);
+  unsigned int* counter = (unsigned int*)p;
+  cudaMemsetAsync(counter, 0, 64, s);
+  FwdPrepArgs pa;
+  pa.jobs.n = 0;
+  pa.F = F; pa.normalize = normalize;
+  pa.xa_indptr[0] = indptr0; pa.xa_indices[0] = indices0; pa.xa_indptr[1] = indptr1; pa.xa_indices[1] = indices1;
+  pa.xa_map = map1; pa.xa_V[0] = V0; pa.xa_V[1] = V1; pa.xagg[0] = xa0; pa.xagg[1] = xa1; pa.xa_stride = xs;
+  pa.xa_x = x;
+  launch_fwd_prep(pa, s, false);
+  InputProjBwdArgs a;
+  a.ga[0] = g0; a.ga[1] = g1 ? g1 : g0; a.xagg[0] = xa0; a.xagg[1] = xa1; a.xa_stride = xs;
+  a.V[0] = V0; a.V[1] = V1; a.F = F; a.part = part; a.counter = counter; a.d_Wt = dWt;
+  launch_input_proj_bwd(a, s);
+  return (int)cudaGetLastError();
+}
+
 extern "C" SCGIB_API size_t scgib_gin_workspace_bytes(int32_t V) {
   size_t part = (size_t)((V + 63) / 64) * 2 * HID * sizeof(float);
   const size_t part2 = (size_t)num_sms() * 3 * HID * sizeof(double);
@@ -1047,15 +1084,11 @@ extern "C" SCGIB_API int scgib_core_gate_fwd_f32(const float* Hfeat, const int32
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
   const int H = hidden;
-  TransposeJobs jobs;
-  jobs.n = 1;
-  jobs.job[0] = TransposeJob{Wc1, w.w1t, H, H};
-  launch_transposes(jobs, s);
-  // identity BatchNorm in front of the linear layer: Hfeat is already relu(BN(y)) >= 0, so relu(1 * (H - 0) * 1 + 0) = H
-  launch_identity_bn(w.bnid, H, s);
+  // Hfeat is used as given (signed features: the GraphSAGE / GCN encoders end without an activation, models.py:88, 103;
+  // the fused GIN path applies relu(BN(.)) on load instead): q = compressor.0(Hfeat) on the FP32 linear tiles
+  cudaMemcpyAsync(w.Hc, Hfeat, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
   cudaMemsetAsync(w.logit0, 0, (size_t)N * sizeof(float), s);
-  GateLinFwdArgs g{Hfeat, w.bnid, N, w.w1t, bc1, w.Hc, w.q, false};
-  launch_gate_lin_fwd(g, H, s);
+  launch_linear_plain(Hfeat, Wc1, bc1, N, H, H, w.q, s);
   GraphGateFwdArgs a;
   a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = w.Hc; a.q = w.q;
   a.gamma_c = gamma_c; a.beta_c = beta_c; a.wc2 = wc2; a.bc2 = bc2; a.gate_u = gate_u; a.feat_u = feat_u; a.logit = w.logit0;

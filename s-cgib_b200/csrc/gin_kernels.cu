@@ -65,13 +65,14 @@ __device__ __forceinline__ void xagg_rows(const FwdPrepArgs& p, int cta) {
     const int set = i < V0 ? 0 : 1, v = set == 0 ? i : i - V0;
     const int32_t* indices = p.xa_indices[set];
     const int32_t* map = set == 0 ? nullptr : p.xa_map;
-    const int e0 = __ldg(p.xa_indptr[set] + v), e1 = __ldg(p.xa_indptr[set] + v + 1);
+    const int32_t* ip = p.xa_indptr[set];          // null: the row itself only (x_hat[p(v)])
+    const int e0 = ip ? __ldg(ip + v) : 0, e1 = ip ? __ldg(ip + v + 1) : 0;
     float acc[FC];
 #pragma unroll
     for (int f = 0; f < FC; ++f) acc[f] = 0.f;
     for (int e = e0 - 1; e < e1; ++e) {          // e0 - 1: the row itself
       const int u = e < e0 ? v : __ldg(indices + e);
-      const float* xr = p.x + (size_t)(map ? __ldg(map + u) : u) * F;
+      const float* xr = p.xa_x + (size_t)(map ? __ldg(map + u) : u) * F;
       float xv[FC];
       float ss = 0.f;
 #pragma unroll
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) fwd_prep_kernel(FwdPrepArgs p) {
 }
 void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16) {
   a.nproj = a.x ? min((a.N + 31) / 32, 148 * 8) : 0;
-  a.nxagg = (a.x && a.xagg[0]) ? min((a.xa_V[0] + a.xa_V[1] + kThreads - 1) / kThreads, 148 * 8) : 0;
+  a.nxagg = (a.xa_x && a.xagg[0]) ? min((a.xa_V[0] + a.xa_V[1] + kThreads - 1) / kThreads, 148 * 8) : 0;
   const int grid = a.nxagg + a.nproj + a.jobs.n + (a.headW1 ? 8 : 0);
   if (grid == 0) return;
   if (out_bf16) launch_k((fwd_prep_kernel<true>), dim3(grid), dim3(kThreads), 0, s, a);

@@ -25,7 +25,7 @@ struct FwdPrepArgs {
   // aggregated normalised features xagg_v = x_hat[p(v)] + sum_{u in N(v)} x_hat[p(u)] of the parent rows and the ego rows
   // (a constant of the batch: the transfer_d backward contracts the layer-0 input gradient with it, input_proj_bwd)
   const int32_t* xa_indptr[2] = {nullptr, nullptr}; const int32_t* xa_indices[2] = {nullptr, nullptr};
-  const int32_t* xa_map = nullptr; int xa_V[2] = {0, 0}; float* xagg[2] = {nullptr, nullptr}; int xa_stride = 0;
+  const float* xa_x = nullptr; const int32_t* xa_map = nullptr; int xa_V[2] = {0, 0}; float* xagg[2] = {nullptr, nullptr}; int xa_stride = 0;
   int nproj = 0, nxagg = 0;            // set by the launcher
 };
 void launch_fwd_prep(FwdPrepArgs a, cudaStream_t s, bool out_bf16);
@@ -135,6 +135,10 @@ struct InputProjBwdArgs {
 };
 int input_proj_bwd_grid(int V0, int V1);
 void launch_input_proj_bwd(const InputProjBwdArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------- encoder_ops.cu
+// Y[V][O] = X[V][K] W^T + bias, W [O][K] (nn.Linear layout); K, O multiples of 32
+void launch_linear_plain(const float* X, const float* W, const float* bias, int V, int K, int O, float* Y, cudaStream_t s);
 
 // ---------------------------------------------------------------- head_kernels.cu
 // H = relu(BN(y_last)) materialised; q = H Wc1^T + bc1   (compressor.0, models.py:590)

@@ -212,9 +212,16 @@ class _Bridge:
         return params
 
 
-def _check_args(args, encoder):
-    if encoder != "GIN":
-        print("scgib_b200: only --encoder GIN is implemented on the B200 path (reference models.py:573-587)")
+def _check_composed_width(encoder, hidden_dim):
+    if encoder != "GIN" and int(hidden_dim) != HID:
+        raise NotImplementedError("--encoder %s runs at --dims 64 on the B200 path (the batch-loss operator entries are built "
+                                  "for hidden 64; --dims 128 is available with --encoder GIN)" % encoder)
+
+
+def _check_args(args, encoder, allowed=("GIN",)):
+    if encoder not in allowed:
+        # the reference's own unknown-encoder branch (models.py:585-587); Transformer is outside SURVEY section 8
+        print("scgib_b200: --encoder %s is not implemented on the B200 path for this class (available: %s)" % (encoder, ", ".join(allowed)))
         raise SystemExit()
     if getattr(args, "readout_f", "sum") != "sum" or getattr(args, "recons_type", "adj") not in ("adj", "logM") or \
             not getattr(args, "useAtt", 1):
@@ -248,6 +255,32 @@ class _HotPathMixin:
             return torch.rand(N).to(device, non_blocking=True), torch.rand(N, H, device=device)
         return torch.rand(N, device=device), torch.rand(N, H, device=device)
 
+    def _composed_inputs(self, batch_g, flatten_batch_subgraphs, device):
+        g = batch_g if batch_g.device == torch.device(device) else batch_g.to(device)
+        ego = flatten_batch_subgraphs
+        if not isinstance(ego, EgoBatch):
+            raise TypeError("flatten_batch_subgraphs must be an scgib_b200.graph.EgoBatch (khop_ego_batch)")
+        if ego.device != g.device:
+            ego = ego.to(g.device)
+        if g.device.type != "cuda":
+            raise RuntimeError("S-CGIB B200 path: the model must be on a CUDA device (no CPU fallback)")
+        return g, ego
+
+    def _forward_composed(self, batch_g, batch_x, flatten_batch_subgraphs, device):
+        """--encoder GraphSAGE / GCN: the step composed from operator kernels (encoders.py)."""
+        from . import encoders
+        if getattr(self, "recons_type", "adj") != "adj":
+            raise NotImplementedError("--recons_type logM runs with --encoder GIN on the B200 path")
+        g, ego = self._composed_inputs(batch_g, flatten_batch_subgraphs, device)
+        x = batch_x.to(g.device).float().contiguous()
+        gate_u, feat_u = self._noise(x.shape[0], g.device)
+        names = encoders.composed_param_names(self)
+        kl, con, rec = encoders.ComposedPretrainFn.apply(self, g, ego, x, gate_u.contiguous(), feat_u.contiguous(), names,
+                                                         *[encoders.resolve_param(self, n) for n in names])
+        if self.training:
+            encoders.inner_of(self).compressor[1].num_batches_tracked += g.batch_size     # one BatchNorm call per graph (models.py:642)
+        return None, kl, con, rec
+
     def forward(self, batch_g, batch_x, flatten_batch_subgraphs, batch_logMs, x_subs, current_epoch, edge_index,
                 k_transition, device, batch_size=16):
         """reference models.py:662-700 / 1158-1195 -> (None, KL_Loss, contrastive_loss, reconstruction_loss)."""
@@ -255,6 +288,8 @@ class _HotPathMixin:
         self.device = device
         if batch_size < batch_g.batch_size:
             raise NotImplementedError("batched_semi_loss with batch_size < number of graphs (never the case in the CLI)")
+        if getattr(self, "encoder_kind", "GIN") != "GIN":
+            return self._forward_composed(batch_g, batch_x, flatten_batch_subgraphs, device)
         params = self._bridge.sync(device)
         self._bridge.training = self.training
         b = self._device_batch(batch_g, batch_x, flatten_batch_subgraphs, device)
@@ -275,6 +310,13 @@ class _HotPathMixin:
     def extract_features(self, nodes_list, batch_g, batch_x, flatten_batch_subgraphs, x_subs, device):
         """reference models.py:702-750 (forward only here): ``batch_x`` is already transfer_d'ed [N, d_transfer].
         Returns (interaction_map [N,2d], KL_tensor, noisy_node_feature [N,d], graph_features_readout [B,d])."""
+        if getattr(self, "encoder_kind", "GIN") != "GIN":
+            from . import encoders
+            g, ego = self._composed_inputs(batch_g, flatten_batch_subgraphs, device)
+            gate_u, feat_u = self._noise(g.num_nodes(), g.device)
+            out, _ = encoders.composed_features(self, g, ego, batch_x.to(g.device).float().contiguous(), gate_u.contiguous(),
+                                                feat_u.contiguous())
+            return out["interaction_map"], out["kl"].clone(), out["noisy"], out["graph_readout"]
         br = getattr(self, "_bridge", None) or _Bridge(self, self.in_dim_raw, self.gin_layers)
         self._bridge = br
         br.sync(device)
@@ -292,7 +334,9 @@ class Mainmodel(_HotPathMixin, nn.Module):
 
     def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, encoder):
         super().__init__()
-        _check_args(args, encoder)
+        _check_args(args, encoder, allowed=("GIN", "GraphSAGE", "GCN"))
+        _check_composed_width(encoder, hidden_dim)
+        self.encoder_kind = encoder
         self.tau = 1.0
         self.recons_type = args.recons_type
         self.useAtt = args.useAtt
@@ -313,22 +357,28 @@ class Mainmodel(_HotPathMixin, nn.Module):
         self.reconstructX = nn.Sequential(nn.Linear(self.hidden_dim, self.in_dim))
         self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
                                  nn.Linear(self.hidden_dim, self.hidden_dim))
-        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
-        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        if encoder == "GIN":
+            self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+            self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        else:                       # models.py:576-581: composed from operator kernels, see encoders.py
+            from .encoders import make_encoder
+            self.Encoder1 = make_encoder(encoder, self.in_dim, hidden_dim)
+            self.Encoder2 = make_encoder(encoder, self.in_dim, hidden_dim)
         self.compressor = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.BatchNorm1d(self.hidden_dim),
                                         nn.ReLU(), nn.Linear(self.hidden_dim, 1))
-        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+        self._bridge = _Bridge(self, in_dim, self.gin_layers) if encoder == "GIN" else None
 
     def __getstate__(self):     # torch.save(model) (exp_pretraining.py:107): drop the engine, keep plain tensors
         st = self.__dict__.copy()
         st["_bridge"] = None
+        st.pop("_composed_last", None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         for p in self.parameters():
             p.data = p.data.clone()
-        self._bridge = _Bridge(self, self.in_dim_raw, self.gin_layers)
+        self._bridge = _Bridge(self, self.in_dim_raw, self.gin_layers) if getattr(self, "encoder_kind", "GIN") == "GIN" else None
 
 
 class Mainmodel_continue(_HotPathMixin, nn.Module):
@@ -337,7 +387,9 @@ class Mainmodel_continue(_HotPathMixin, nn.Module):
 
     def __init__(self, args, in_dim, hidden_dim, num_layers, num_heads, k_transition, num_classes, cp_filename, encoder):
         super().__init__()
-        _check_args(args, encoder)
+        _check_args(args, encoder, allowed=("GIN", "GraphSAGE", "GCN"))
+        _check_composed_width(encoder, hidden_dim)
+        self.encoder_kind = encoder
         self.tau = 1.0
         self.readout = args.readout_f
         self.gin_layers = int(getattr(args, "gin_layers", DEFAULT_GIN_LAYERS))
@@ -364,8 +416,13 @@ class Mainmodel_continue(_HotPathMixin, nn.Module):
                                      nn.Linear(self.hidden_dim, out_dim))
         self.MLP = nn.Sequential(nn.Linear(2 * self.hidden_dim, self.hidden_dim), nn.ReLU(),
                                  nn.Linear(self.hidden_dim, self.hidden_dim))
-        self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
-        self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        if encoder == "GIN":
+            self.Encoder1 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+            self.Encoder2 = GIN(self.in_dim, hidden_dim, self.gin_layers)
+        else:
+            from .encoders import make_encoder
+            self.Encoder1 = make_encoder(encoder, self.in_dim, hidden_dim)
+            self.Encoder2 = make_encoder(encoder, self.in_dim, hidden_dim)
         self.model = torch.load(cp_filename, map_location=args.device, weights_only=False)
         for p in self.model.parameters():
             p.requires_grad = True
@@ -373,7 +430,7 @@ class Mainmodel_continue(_HotPathMixin, nn.Module):
                                         nn.ReLU(), nn.Linear(self.hidden_dim, 1))
         self.reconstructX = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), nn.ReLU(),
                                           nn.Linear(self.hidden_dim, in_dim))
-        self._bridge = _Bridge(self, in_dim, self.gin_layers)
+        self._bridge = _Bridge(self, in_dim, self.gin_layers) if encoder == "GIN" else None
 
     __getstate__ = Mainmodel.__getstate__
     __setstate__ = Mainmodel.__setstate__

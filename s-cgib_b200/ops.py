@@ -2,6 +2,8 @@
 building blocks of the drop-in modules).  Every function requires CUDA tensors; nothing falls back to torch."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -213,3 +215,66 @@ def segment_sum_bwd(g_out, seg_ptr, rows):
     _lib.check(_lib.load().scgib_segment_sum_bwd_f32(_lib.ptr(g_out.contiguous()), _lib.ptr(seg_ptr), S, H, _lib.ptr(g_in), _stream(g_out)),
                "segment_sum_bwd")
     return g_in
+
+
+# ---------------------------------------------------------------- building blocks of --encoder GraphSAGE / GCN (csrc/encoder_ops.cu)
+NORM_NONE, NORM_MEAN, NORM_SQRT = 0, 1, 2
+
+
+def graph_aggregate(h, indptr, indices, src_norm, dst_norm, row_map=None, add=None):
+    """out[v] = (add[v]) + fd(deg v) sum_{u in N(v)} fs(deg u) h[map(u)]; the SAGEConv mean (NONE, MEAN), its backward
+    (MEAN, NONE) and the GraphConv normalised sum (SQRT, SQRT; self-adjoint) on the symmetric CSR."""
+    _cuda(h, indptr, indices)
+    V, W = indptr.numel() - 1, h.shape[1]
+    out = torch.empty(V, W, device=h.device)
+    _lib.check(_lib.load().scgib_graph_aggregate_f32(_lib.ptr(h), W, _lib.ptr(row_map), _lib.ptr(indptr), _lib.ptr(indices), V,
+                                                     src_norm, dst_norm, _lib.ptr(add), _lib.ptr(out), _stream(h)), "graph_aggregate")
+    return out
+
+
+def segment_sum_w(h, seg_ptr):
+    """dgl.sum_nodes at width 32 / 64 / 128 / 256."""
+    _cuda(h, seg_ptr)
+    S, W = seg_ptr.numel() - 1, h.shape[1]
+    out = torch.empty(S, W, device=h.device)
+    _lib.check(_lib.load().scgib_segment_sum_w_f32(_lib.ptr(h), _lib.ptr(seg_ptr), S, W, _lib.ptr(out), _stream(h)), "segment_sum_w")
+    return out
+
+
+def linear_fwd(X0, W0, O, w0_kxo=False, X1=None, W1=None, w1_kxo=False, bias=None, relu=False, map0=None, M0=None, M1=None, V=None):
+    """Y[V,O] = act(X0[map0] (.) (M0 > 0) W0 + X1 (.) (M1 > 0) W1 + bias); W [O,K] (nn.Linear) or [K,O] (w_kxo)."""
+    _cuda(X0, W0)
+    V = int(V if V is not None else (map0.numel() if map0 is not None else X0.shape[0]))
+    Y = torch.empty(V, O, device=X0.device)
+    _lib.check(_lib.load().scgib_linear_fwd_f32(_lib.ptr(X0), _lib.ptr(M0), _lib.ptr(map0), _lib.ptr(W0), X0.shape[1], int(w0_kxo),
+                                                _lib.ptr(X1), _lib.ptr(M1), _lib.ptr(W1), 0 if X1 is None else X1.shape[1],
+                                                int(w1_kxo), _lib.ptr(bias), int(relu), V, O, _lib.ptr(Y), _stream(X0)), "linear_fwd")
+    return Y
+
+
+def linear_bwd_w(G, X, dW, db=None, M=None, map=None, kxo=False, accumulate=False):
+    """dW (+)= (G (.) (M > 0))^T X[map] ([O,K], or [K,O] with kxo), db (+)= column sums; in place on dW / db."""
+    _cuda(G, X, dW)
+    lib = _lib.load()
+    V, O, K = G.shape[0], G.shape[1], X.shape[1]
+    ws = _ws(lib.scgib_linear_bwd_w_workspace_bytes(V, O, K), G.device)
+    _lib.check(lib.scgib_linear_bwd_w_f32(_lib.ptr(G), _lib.ptr(M), _lib.ptr(X), _lib.ptr(map), V, O, K, int(kxo), int(accumulate),
+                                          _lib.ptr(dW), _lib.ptr(db), _lib.ptr(ws), ws.numel(), _stream(G)), "linear_bwd_w")
+    return dW, db
+
+
+def transfer_bwd(x, g0, g1, map1, normalize=True, csr0=None, csr1=None):
+    """d transfer_d.weight [32, F] from the input gradients of the two row sets (parent rows / ego rows through map1)."""
+    _cuda(x, g0)
+    lib = _lib.load()
+    F, V0, V1 = x.shape[1], g0.shape[0], 0 if g1 is None else g1.shape[0]
+    dWt = torch.empty(DTR, F, device=x.device)
+    nbytes = lib.scgib_transfer_bwd_workspace_bytes(V0, V1, F)
+    ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=x.device)
+    off = (-ws.data_ptr()) % 256
+    ip0, ix0 = csr0 if csr0 is not None else (None, None)
+    ip1, ix1 = csr1 if csr1 is not None else (None, None)
+    _lib.check(lib.scgib_transfer_bwd_f32(_lib.ptr(x), F, int(normalize), _lib.ptr(g0), V0, _lib.ptr(ip0), _lib.ptr(ix0), _lib.ptr(g1), V1,
+                                          _lib.ptr(ip1), _lib.ptr(ix1), _lib.ptr(map1), _lib.ptr(dWt), ctypes.c_void_p(ws.data_ptr() + off),
+                                          int(nbytes), _stream(x)), "transfer_bwd")
+    return dWt

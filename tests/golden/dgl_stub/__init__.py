@@ -70,6 +70,61 @@ class GINConv(nn.Module):
         return rst
 
 
+class SAGEConv(nn.Module):
+    """dgl.nn.SAGEConv(in_feats, out_feats, 'mean'), restated from DGL 1.1.x: fc_neigh (no bias) on the mean of the
+    in-neighbours (zero for isolated nodes), fc_self (with the bias), Xavier-uniform weights with the ReLU gain.  The linear
+    map is applied before the aggregation when in_feats > out_feats (same function, the library's operation order)."""
+
+    def __init__(self, in_feats, out_feats, aggregator_type, feat_drop=0.0, bias=True, norm=None, activation=None):
+        super().__init__()
+        assert aggregator_type == "mean" and feat_drop == 0.0 and norm is None and activation is None
+        self._in, self._out = in_feats, out_feats
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_self = nn.Linear(in_feats, out_feats, bias=bias)
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, g, feat):
+        deg = torch.zeros(g._n, dtype=feat.dtype).index_add(0, g._dst, torch.ones(g._dst.numel(), dtype=feat.dtype))
+        lin_before_mp = self._in > self._out
+        src = self.fc_neigh(feat) if lin_before_mp else feat
+        neigh = torch.zeros(g._n, src.shape[1], dtype=feat.dtype).index_add(0, g._dst, src[g._src])
+        neigh = neigh / deg.clamp(min=1)[:, None]
+        if not lin_before_mp:
+            neigh = self.fc_neigh(neigh)
+        return self.fc_self(feat) + neigh
+
+
+class GraphConv(nn.Module):
+    """dgl.nn.pytorch.conv.GraphConv(in_feats, out_feats, norm='both', weight=True, bias=True,
+    allow_zero_in_degree=True), restated from DGL 1.1.x: D_out^-1/2 on the source rows, sum over the in-edges,
+    D_in^-1/2 on the result (degrees clamped to 1), weight [in, out] applied first when in_feats > out_feats."""
+
+    def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None,
+                 allow_zero_in_degree=False):
+        super().__init__()
+        assert norm == "both" and weight and bias and activation is None
+        self._in, self._out = in_feats, out_feats
+        self.weight = nn.Parameter(torch.Tensor(in_feats, out_feats))
+        self.bias = nn.Parameter(torch.Tensor(out_feats))
+        nn.init.xavier_uniform_(self.weight)
+        nn.init.zeros_(self.bias)
+
+    def forward(self, g, feat):
+        one = torch.ones(g._src.numel(), dtype=feat.dtype)
+        dout = torch.zeros(g._n, dtype=feat.dtype).index_add(0, g._src, one).clamp(min=1)
+        din = torch.zeros(g._n, dtype=feat.dtype).index_add(0, g._dst, one).clamp(min=1)
+        h = feat * torch.pow(dout, -0.5)[:, None]
+        if self._in > self._out:
+            h = torch.matmul(h, self.weight)
+            rst = torch.zeros(g._n, h.shape[1], dtype=feat.dtype).index_add(0, g._dst, h[g._src])
+        else:
+            rst = torch.zeros(g._n, h.shape[1], dtype=feat.dtype).index_add(0, g._dst, h[g._src])
+            rst = torch.matmul(rst, self.weight)
+        return rst * torch.pow(din, -0.5)[:, None] + self.bias
+
+
 class Set2Set(nn.Module):
     """dgl.nn.pytorch.glob.Set2Set(input_dim, n_iters, n_layers), restated from DGL 1.1.0: broadcast_nodes /
     softmax_nodes / sum_nodes are written out with segment ids."""
@@ -112,19 +167,19 @@ def _mod(name, **attrs):
 
 def install():
     """Register stand-ins for every third-party import at the top of reference models.py:4-35."""
-    dummy_names = ["GCNConv", "SAGEConv", "global_mean_pool", "AsGraphPredDataset", "GraphDataLoader",
+    dummy_names = ["GCNConv", "global_mean_pool", "AsGraphPredDataset", "GraphDataLoader",
                    "collate_dgl", "DglGraphPropPredDataset", "Evaluator", "AtomEncoder", "GraphConv",
                    "scatter_mean", "scatter_add", "scatter_std", "SumPooling", "GINDataset"]
     d = {n: _Dummy for n in dummy_names}
     dgl = _mod("dgl", sum_nodes=sum_nodes, StubGraph=StubGraph)
-    dgl.nn = _mod("dgl.nn", Set2Set=Set2Set, GraphConv=_Dummy, SAGEConv=_Dummy, GINConv=GINConv)
+    dgl.nn = _mod("dgl.nn", Set2Set=Set2Set, GraphConv=GraphConv, SAGEConv=SAGEConv, GINConv=GINConv)
     dgl.sparse = _mod("dgl.sparse")
     dgl.function = _mod("dgl.function")
     dgl.data = _mod("dgl.data", AsGraphPredDataset=_Dummy, GINDataset=_Dummy)
     dgl.dataloading = _mod("dgl.dataloading", GraphDataLoader=_Dummy)
     pt = _mod("dgl.nn.pytorch")
     pt.glob = _mod("dgl.nn.pytorch.glob", SumPooling=_Dummy)
-    pt.conv = _mod("dgl.nn.pytorch.conv", GINConv=GINConv, GraphConv=_Dummy)
+    pt.conv = _mod("dgl.nn.pytorch.conv", GINConv=GINConv, GraphConv=GraphConv)
     dgl.nn.pytorch = pt
     tg = _mod("torch_geometric")
     tg.nn = _mod("torch_geometric.nn", GCNConv=_Dummy, SAGEConv=_Dummy, global_mean_pool=_Dummy)

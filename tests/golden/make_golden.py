@@ -30,7 +30,7 @@ def load_reference_models(ref_root="/root/reference"):
     return importlib.import_module("models"), dgl_stub
 
 
-def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj", hidden=64):
+def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj", hidden=64, encoder="GIN"):
     g = synth_batch(seed, B)
     e = ego_batch_ref(g, k)
     s, d = g.edges()
@@ -43,7 +43,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj", hidden=6
 
     args = types.SimpleNamespace(recons_type=recons_type, useAtt=1, readout_f="sum", d_transfer=32, device="cpu")
     torch.manual_seed(seed)
-    model = ref_models.Mainmodel(args, 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k, encoder="GIN")
+    model = ref_models.Mainmodel(args, 9, hidden_dim=hidden, num_layers=4, num_heads=4, k_transition=k, encoder=encoder)
     model.train()
     state0 = {n: t.detach().clone() for n, t in model.state_dict().items()}
     batch_logMs = None
@@ -84,7 +84,7 @@ def make(seed, B, k, ref_models, dgl_stub, out_path, recons_type="adj", hidden=6
     used = set(grads) | {n for n in state0 if "running" in n or "num_batches" in n or n.endswith(".eps")}
     fx = dict(
         meta=dict(seed=seed, B=B, k=k, noise_seed=noise_seed, reference="models.py Mainmodel (unmodified) on dgl_stub",
-                  torch=torch.__version__, recons_type=recons_type, hidden=hidden),
+                  torch=torch.__version__, recons_type=recons_type, hidden=hidden, encoder=encoder),
         graph=dict(graph_ptr=g.graph_ptr, indptr=g.indptr, indices=g.indices, x=g.x),
         ego=dict(ego_ptr=e.ego_ptr, ego_nodes=e.ego_nodes, sub_indptr=e.sub_indptr, sub_indices=e.sub_indices),
         state={n: t for n, t in state0.items() if n in used},
@@ -235,3 +235,8 @@ if __name__ == "__main__":
     make(8, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "pretrain_h128_k1_b6.pt"), hidden=128)
     make(9, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "pretrain_h128_k2_b4.pt"), hidden=128)
     make_finetune(10, 5, 1, ref_models, dgl_stub, os.path.join(HERE, "finetune_h128_k1_b5.pt"), hidden=128)
+    # --encoder GraphSAGE / GCN (models.py:75-104): the same unmodified Mainmodel on the stub's SAGEConv / GraphConv
+    make(11, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "enc_sage_k1_b6.pt"), encoder="GraphSAGE")
+    make(12, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "enc_sage_k2_b4.pt"), encoder="GraphSAGE")
+    make(13, 6, 1, ref_models, dgl_stub, os.path.join(HERE, "enc_gcn_k1_b6.pt"), encoder="GCN")
+    make(14, 4, 2, ref_models, dgl_stub, os.path.join(HERE, "enc_gcn_k2_b4.pt"), encoder="GCN")

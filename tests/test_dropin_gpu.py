@@ -95,7 +95,7 @@ def test_exp_pretraining_cli_stages(tmp_path, monkeypatch):
 def test_unsupported_encoder_exits_like_reference():
     import models
     with pytest.raises(SystemExit):
-        models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GCN")
+        models.Mainmodel(_args(), 9, 64, 4, 4, 1, "Transformer")       # outside SURVEY section 8 (GraphSAGE / GCN: test_gpu_encoders.py)
 
 
 def test_extract_features_api():

@@ -21,7 +21,7 @@ def test_core_gate_op(H):
     nodes = g.batch_num_nodes().tolist()
     torch.manual_seed(H)
     m = OracleMainmodel(9, H).double()
-    Hf = torch.relu(torch.randn(g.num_nodes, H, dtype=torch.float64)).requires_grad_()
+    Hf = torch.randn(g.num_nodes, H, dtype=torch.float64).requires_grad_()      # signed: GraphSAGE / GCN encoders end without a ReLU
     gate_u, feat_u = draw_noise_like_reference(nodes, H, 5)
     noisy, _, KL_tensor = m.compression(Hf, nodes, gate_u.double(), feat_u.double())
     readout, core, kl = sum_nodes(tg, Hf), sum_nodes(tg, noisy), KL_tensor.mean()

@@ -11,7 +11,8 @@ from oracle.scgib_oracle import (OracleMainmodel, draw_noise_like_reference, nor
                                  tgraph_from_ego, tgraph_from_ref)
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pretrain_*.pt")) +
-              glob.glob(os.path.join(os.path.dirname(__file__), "golden", "logm_*.pt")))     # logm_*: --recons_type logM
+              glob.glob(os.path.join(os.path.dirname(__file__), "golden", "logm_*.pt")) +    # logm_*: --recons_type logM
+              glob.glob(os.path.join(os.path.dirname(__file__), "golden", "enc_*.pt")))      # enc_*: --encoder GraphSAGE / GCN
 
 
 def load_fixture(path):
@@ -26,7 +27,7 @@ def hidden_of_fixture(fx):
 
 
 def oracle_from_fixture(fx, dtype=torch.float32):
-    m = OracleMainmodel(9, hidden_of_fixture(fx), 32, 4)
+    m = OracleMainmodel(9, hidden_of_fixture(fx), 32, 4, encoder=fx["meta"].get("encoder", "GIN"))
     missing, unexpected = m.load_state_dict(fx["state"], strict=False)
     assert not unexpected
     m.train()
