@@ -336,6 +336,9 @@ SCGIB_API int scgib_core_gate_fwd_f32(const float* Hfeat, const int32_t* graph_p
                                       const float* wc2, const float* bc2, const float* gate_u, const float* feat_u,
                                       float* noisy, float* lam, float* graph_readout, float* core_readout, float* kl,
                                       void* workspace, size_t workspace_bytes, void* stream);
+/* running = {mean[H], var[H]} of compressor.1 after the B per-graph BatchNorm calls of the forward that filled `workspace`. */
+SCGIB_API int scgib_core_gate_ema_f32(int32_t B, int32_t N, int32_t hidden, float* running, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 SCGIB_API int scgib_core_gate_bwd_f32(const int32_t* graph_ptr, int32_t B, int32_t N, int32_t hidden, const float* Wc1,
                                       const float* gamma_c, const float* beta_c, const float* wc2, const float* feat_u,
                                       const float* g_noisy, const float* g_core, const float* g_readout, float kl_scale,

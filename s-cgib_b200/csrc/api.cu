@@ -1040,7 +1040,7 @@ extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* s
 // ---------------------------------------------------------------- op-level entries: core gate, attention, head MLP
 namespace scgib {
 struct GateOpWs {
-  float *Hc, *q, *gstat, *lam, *alpha0, *logit0, *zeros, *gp, *g_q, *gC, *w1t, *bnid, *part, *ppart, *kl;
+  float *Hc, *q, *gstat, *lam, *alpha0, *logit0, *zeros, *gp, *g_q, *gC, *w1t, *bnid, *part, *ppart, *kl, *cstat;
   unsigned int* counters;
   int64_t pstride;
   size_t bytes;
@@ -1058,6 +1058,7 @@ static GateOpWs gate_op_carve(int H, int B, int N, void* base) {
   w.ppart = take((size_t)num_sms() * w.pstride);
   w.kl = take(4);
   w.counters = (unsigned int*)take(64);
+  w.cstat = take((size_t)B * 2 * H);
   w.bytes = o;
   return w;
 }
@@ -1093,10 +1094,24 @@ extern "C" SCGIB_API int scgib_core_gate_fwd_f32(const float* Hfeat, const int32
   a.graph_ptr = graph_ptr; a.B = B; a.N = N; a.H = w.Hc; a.q = w.q;
   a.gamma_c = gamma_c; a.beta_c = beta_c; a.wc2 = wc2; a.bc2 = bc2; a.gate_u = gate_u; a.feat_u = feat_u; a.logit = w.logit0;
   a.noisy = noisy; a.lam = w.lam; a.alpha = w.alpha0; a.readout = graph_readout; a.core = core_readout; a.gstat = w.gstat;
-  a.eval_running = nullptr; a.cstat = nullptr; a.kl = w.kl;
+  a.eval_running = nullptr; a.cstat = w.cstat; a.kl = w.kl;      // per-graph batch statistics of q: scgib_core_gate_ema_f32
   launch_graph_gate_fwd(a, H, s);
   if (lam) cudaMemcpyAsync(lam, w.lam, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (kl) cudaMemcpyAsync(kl, w.kl, sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return (int)cudaGetLastError();
+}
+
+// compressor.1's running statistics after the B per-graph BatchNorm calls of the forward that filled `workspace`
+// (models.py:642: one nn.BatchNorm1d call per graph, momentum 0.1, unbiased variance): running = {mean[H], var[H]}
+extern "C" SCGIB_API int scgib_core_gate_ema_f32(int32_t B, int32_t N, int32_t hidden, float* running, void* workspace,
+                                                 size_t workspace_bytes, void* stream_) {
+  if (!running || !workspace) return SCGIB_E_NULL;
+  if (!hidden_ok(hidden)) return SCGIB_E_SHAPE;
+  if (B < 1 || N < 2) return SCGIB_E_RANGE;
+  if ((uintptr_t)workspace & 255u) return SCGIB_E_ALIGN;
+  const GateOpWs w = gate_op_carve(hidden, B, N, workspace);
+  if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
+  launch_compressor_ema(w.cstat, B, running, hidden, (cudaStream_t)stream_);
   return (int)cudaGetLastError();
 }
 

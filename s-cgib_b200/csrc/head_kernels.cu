@@ -67,7 +67,68 @@ ego_pool_fwd_kernel(EgoPoolFwdArgs p) {
     if (l == 0) p.logit[v] = d;
   }
 }
+// the same with TWO consecutive seeds per lane group: their rows are contiguous, so one unrolled pass over [r0, r2) keeps up to 8
+// independent row loads in flight per lane (one seed's ~3 rows leave the memory pipeline idle behind the ego_ptr -> row chain)
+template <bool BF, int HID>
+__global__ void __launch_bounds__(kThreads)
+ego_pool_fwd2_kernel(EgoPoolFwdArgs p) {
+  pdl_sync();
+  constexpr int LPR = HID / 4, SPC = kThreads / LPR;
+  const int l = threadIdx.x % LPR;
+  Bn4 b;
+  b.load(p.bn, l * 4, HID);
+  const float4 w = ldg4(p.w_cand + l * 4);
+  const unsigned hmask = LPR == 32 ? 0xffffffffu : ((threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu);
+  // the segment offsets of the NEXT pair are requested before this pair's rows are consumed (persistent grid: the
+  // ego_ptr -> rows dependency of one iteration overlaps the row loads of the previous one)
+  const int stride = 2 * gridDim.x * SPC;
+  int v = 2 * (blockIdx.x * SPC + (threadIdx.x / LPR));
+  int n0 = 0, n1 = 0, n2 = 0;
+  if (v < p.N) { n0 = __ldg(p.ego_ptr + v); n1 = __ldg(p.ego_ptr + v + 1); n2 = v + 1 < p.N ? __ldg(p.ego_ptr + v + 2) : n1; }
+  for (; v < p.N; v += stride) {
+    const bool two = v + 1 < p.N;
+    const int r0 = n0, r1 = n1, r2 = n2;
+    const int vn = v + stride;
+    if (vn < p.N) { n0 = __ldg(p.ego_ptr + vn); n1 = __ldg(p.ego_ptr + vn + 1); n2 = vn + 1 < p.N ? __ldg(p.ego_ptr + vn + 2) : n1; }
+    float4 accA = make4(0.f), accB = make4(0.f);
+    for (int rb = r0; rb < r2; rb += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = rb + i < r2 ? ld4a<BF>(p.y, (size_t)(rb + i) * HID + l * 4) : make4(0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (rb + i >= r2) break;
+        const float4 a = b.act(x[i]);
+        if (rb + i < r1) accA = add4(accA, a); else accB = add4(accB, a);
+      }
+    }
+    st4(p.C + (size_t)v * HID + l * 4, accA);
+    if (two) st4(p.C + (size_t)(v + 1) * HID + l * 4, accB);
+    float dA = accA.x * w.x + accA.y * w.y + accA.z * w.z + accA.w * w.w;
+    float dB = accB.x * w.x + accB.y * w.y + accB.z * w.z + accB.w * w.w;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) { dA += __shfl_xor_sync(hmask, dA, o); dB += __shfl_xor_sync(hmask, dB, o); }
+    if (l == 0) { p.logit[v] = dA; if (two) p.logit[v + 1] = dB; }
+  }
+}
+
 void launch_ego_pool_fwd(const EgoPoolFwdArgs& a, int hidden, cudaStream_t s) {
+  static int var2 = -1;          // SCGIB_EGO_VAR=1: one seed per lane group (the round-1 kernel)
+  if (var2 < 0) { const char* e = getenv("SCGIB_EGO_VAR"); var2 = (e && e[0] == '1') ? 0 : 1; }
+  if (var2) {
+    const int spc2 = 2 * (kThreads / (hidden / 4));
+    static int per_sm = -1;        // SCGIB_EGO_CTAS: resident CTAs per SM of the persistent grid (0 = one pass per CTA)
+    if (per_sm < 0) { const char* e = getenv("SCGIB_EGO_CTAS"); per_sm = e ? atoi(e) : 3; }
+    const int grid2 = min((a.N + spc2 - 1) / spc2, (per_sm > 0 ? per_sm : 16) * num_sms());
+    if (hidden == 64) {
+      if (a.y_bf16) launch_k((ego_pool_fwd2_kernel<true, 64>), dim3(grid2), dim3(kThreads), 0, s, a);
+      else launch_k((ego_pool_fwd2_kernel<false, 64>), dim3(grid2), dim3(kThreads), 0, s, a);
+    } else {
+      if (a.y_bf16) launch_k((ego_pool_fwd2_kernel<true, 128>), dim3(grid2), dim3(kThreads), 0, s, a);
+      else launch_k((ego_pool_fwd2_kernel<false, 128>), dim3(grid2), dim3(kThreads), 0, s, a);
+    }
+    return;
+  }
   const int spc = kThreads / (hidden / 4);
   static int full = -1;          // SCGIB_EGO_GRID=full: one CTA pass per 16 seeds, no grid-stride tail (experiment)
   if (full < 0) { const char* e = getenv("SCGIB_EGO_GRID"); full = (e && e[0] == 'f') ? 1 : 0; }

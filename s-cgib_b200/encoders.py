@@ -181,6 +181,8 @@ def composed_features(outer, g, ego, t, gate_u, feat_u):
     c = model.compressor
     gate = ops.CoreGate(Hd, _f(c[0].weight), _f(c[0].bias), _f(c[1].weight), _f(c[1].bias), _f(c[3].weight), _f(c[3].bias))
     noisy, lam, readout, core, kl = gate.forward(Hf, g.graph_ptr, gate_u, feat_u)
+    if outer.training:                  # compressor.1 running statistics: B sequential updates, one per graph (models.py:642)
+        gate.update_running(c[1].running_mean, c[1].running_var)
     C = ops.segment_sum_w(S, ego.ego_ptr)
     w_cand = _f(model.attn_layer.weight[0, Hd:])
     alpha, _ = ops.core_cand_attn_fwd(C, g.graph_ptr, w_cand)

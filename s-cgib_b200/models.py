@@ -256,6 +256,9 @@ class _HotPathMixin:
         return torch.rand(N, device=device), torch.rand(N, H, device=device)
 
     def _composed_inputs(self, batch_g, flatten_batch_subgraphs, device):
+        if not self.training:
+            raise NotImplementedError("model.eval() with --encoder GraphSAGE / GCN: the operator-composed step implements the "
+                                      "training-mode BatchNorm of the compressor (use --encoder GIN for eval-mode forwards)")
         g = batch_g if batch_g.device == torch.device(device) else batch_g.to(device)
         ego = flatten_batch_subgraphs
         if not isinstance(ego, EgoBatch):

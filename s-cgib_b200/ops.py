@@ -137,6 +137,14 @@ class CoreGate:
                                                _lib.ptr(kl), _lib.ptr(self.ws), self.ws.numel(), _stream(Hfeat)), "core_gate_fwd")
         return noisy, lam, readout, core, kl
 
+    def update_running(self, running_mean, running_var):
+        """compressor.1's running statistics after this forward's B per-graph BatchNorm calls (models.py:642), in place."""
+        graph_ptr, B, N, feat_u = self.saved
+        run = torch.stack([running_mean, running_var]).contiguous().float()
+        _lib.check(_lib.load().scgib_core_gate_ema_f32(B, N, self.H, _lib.ptr(run), _lib.ptr(self.ws), self.ws.numel(), _stream(run)),
+                   "core_gate_ema")
+        running_mean.copy_(run[0]); running_var.copy_(run[1])
+
     def backward(self, g_noisy, g_core, g_readout, kl_scale=1.0):
         lib, H = _lib.load(), self.H
         graph_ptr, B, N, feat_u = self.saved

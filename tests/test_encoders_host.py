@@ -74,6 +74,10 @@ class CoreGate:
         self.core = torch.zeros(B, Hf.shape[1]).index_add(0, seg, noisy)
         self.noisy, self.kl = noisy, KLt.mean()
         return noisy.detach(), None, self.readout.detach(), self.core.detach(), self.kl.detach().reshape(1)
+    def update_running(self, rm, rv):          # the stand-in's own BatchNorm started from the same default buffers
+        with torch.no_grad():
+            rm.copy_(self.m.compressor[1].running_mean); rv.copy_(self.m.compressor[1].running_var)
+
     def backward(self, g_noisy, g_core, g_readout, kl_scale=1.0):
         c = self.m.compressor
         ps = [c[0].weight, c[0].bias, c[1].weight, c[1].bias, c[3].weight, c[3].bias]
@@ -165,3 +169,5 @@ def test_composed_step_host_logic_matches_reference_golden(path, monkeypatch):
             continue
         assert rel(got[n], gref) <= 5e-5, (n, rel(got[n], gref))
     assert int(m.compressor[1].num_batches_tracked) == g.num_graphs
+    for n in ("compressor.1.running_mean", "compressor.1.running_var"):
+        assert rel(m.state_dict()[n], fx["state_after"][n]) <= 1e-5, n

@@ -173,6 +173,9 @@ def test_mainmodel_sage_gcn_matches_reference_golden(path, monkeypatch):
     last = m._composed_last
     for name in ("interaction_map", "Z", "noisy", "graph_readout"):
         assert rel(last[name], ref[name]) <= 1e-5, (name, rel(last[name], ref[name]))
+    for n in ("compressor.1.running_mean", "compressor.1.running_var"):      # B sequential per-graph updates (models.py:642)
+        assert rel(m.state_dict()[n].cpu(), fx["state_after"][n]) <= 1e-5, n
+    assert int(m.compressor[1].num_batches_tracked) == int(fx["state_after"]["compressor.1.num_batches_tracked"])
     got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
     assert set(fx["grads"]) <= set(got)
     gmax = max(float(v.abs().max()) for v in fx["grads"].values())
@@ -257,3 +260,14 @@ def test_sage_gcn_width_is_64():
     import models
     with pytest.raises(NotImplementedError):
         models.Mainmodel(_args(), 9, 128, 4, 4, 1, "GraphSAGE")
+
+
+def test_sage_gcn_eval_mode_fails_loudly():
+    """model.eval() would need the running statistics inside the per-graph BatchNorm: not built for the composed path."""
+    import models
+    from scgib_b200.graph import khop_ego_batch
+    g = synth_batch(5, 8)
+    m = models.Mainmodel(_args(), 9, 64, 4, 4, 1, "GCN").to(DEV).eval()
+    pg = product_graph(g, DEV)
+    with pytest.raises(NotImplementedError):
+        m.forward(pg, F.normalize(pg.ndata["x"].float()), khop_ego_batch(pg, 1), None, None, 1, None, 2, DEV, 16)
