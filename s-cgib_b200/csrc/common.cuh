@@ -176,74 +176,6 @@ __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, c
   }
 }
 
-// The same aggregation with the index chain taken out of the row loop (gin_bwd_pre): NbrIdx holds the CSR offsets and the
-// first four neighbour ids of NR rows; a persistent loop loads it for the NEXT group of rows while the current group's
-// feature rows are in flight, so an iteration exposes one memory latency (rows) instead of three (indptr -> indices -> rows).
-template <int NR>
-struct NbrIdx { int e0[NR], deg[NR], u[NR][4]; };
-
-template <int NR>
-__device__ __forceinline__ void nbr_offsets_load(const int32_t* __restrict__ indptr, int V, const int (&v)[NR], NbrIdx<NR>& x) {
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const bool ok = v[j] < V;
-    x.e0[j] = ok ? __ldg(indptr + v[j]) : 0;
-    x.deg[j] = ok ? __ldg(indptr + v[j] + 1) : 0;       // end offset until nbr_ids_load()
-  }
-}
-template <int NR>
-__device__ __forceinline__ void nbr_ids_load(const int32_t* __restrict__ indices, NbrIdx<NR>& x) {
-#pragma unroll
-  for (int j = 0; j < NR; ++j) x.deg[j] -= x.e0[j];
-#pragma unroll
-  for (int j = 0; j < NR; ++j)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) x.u[j][q] = x.deg[j] > q ? __ldg(indices + x.e0[j] + q) : -1;
-}
-// issue: the row itself and neighbour slots 0, 1
-template <int KIN, int NR>
-__device__ __forceinline__ void gather_rows_issue(const float* __restrict__ in, int V, const int (&v)[NR], const NbrIdx<NR>& x, int gl,
-                                                  float4 (&hs)[NR], float4 (&h0)[NR], float4 (&h1)[NR]) {
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    hs[j] = v[j] < V ? ld4(in + (size_t)v[j] * KIN + gl * 4) : make4(0.f);
-    h0[j] = x.u[j][0] >= 0 ? ld4(in + (size_t)x.u[j][0] * KIN + gl * 4) : make4(0.f);
-    h1[j] = x.u[j][1] >= 0 ? ld4(in + (size_t)x.u[j][1] * KIN + gl * 4) : make4(0.f);
-  }
-}
-// finish: slots 2, 3 from the prefetched ids, further slots through the CSR; neighbours are added in CSR order
-template <int KIN, int NR>
-__device__ __forceinline__ void gather_rows_finish(const float* __restrict__ in, const int32_t* __restrict__ indices, const NbrIdx<NR>& x,
-                                                   int gl, float4 (&hs)[NR], float4 (&h0)[NR], float4 (&h1)[NR], float4 (&acc)[NR]) {
-  int maxd = 0;
-#pragma unroll
-  for (int j = 0; j < NR; ++j) { acc[j] = add4(add4(hs[j], h0[j]), h1[j]); maxd = max(maxd, x.deg[j]); }
-  if (maxd > 2) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      h0[j] = x.u[j][2] >= 0 ? ld4(in + (size_t)x.u[j][2] * KIN + gl * 4) : make4(0.f);
-      h1[j] = x.u[j][3] >= 0 ? ld4(in + (size_t)x.u[j][3] * KIN + gl * 4) : make4(0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) acc[j] = add4(add4(acc[j], h0[j]), h1[j]);
-  }
-  for (int d = 4; d < maxd; d += 2) {
-    int u0[NR], u1[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      u0[j] = x.deg[j] > d ? __ldg(indices + x.e0[j] + d) : -1;
-      u1[j] = x.deg[j] > d + 1 ? __ldg(indices + x.e0[j] + d + 1) : -1;
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      h0[j] = u0[j] >= 0 ? ld4(in + (size_t)u0[j] * KIN + gl * 4) : make4(0.f);
-      h1[j] = u1[j] >= 0 ? ld4(in + (size_t)u1[j] * KIN + gl * 4) : make4(0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) acc[j] = add4(add4(acc[j], h0[j]), h1[j]);
-  }
-}
-
 // Deterministic sum of `n` per-CTA partials part[b * stride] (b = start, start + step, ...) in fp64, fixed order.  The
 // loads are independent of the adds, so the unrolled loop keeps several in flight (a hand-batched variant with an
 // explicit array of loads measured slower on B200).

@@ -393,7 +393,7 @@ void launch_gin_fwd(const GinFwdArgs& a, int kin, int hidden, cudaStream_t s) {
 //   g_o = G * [gamma*yhat+beta > 0] ; dbeta = sum g_o ; dgamma = sum g_o*yhat
 // Last CTA: dgamma/dbeta -> grads, and the BN-backward constants c1 = gamma*dbeta/V, c2 = gamma*dgamma/V.
 // ------------------------------------------------------------------------------------------------
-template <int HID, int MINB, bool PF>
+template <int HID, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 gin_bwd_pre_kernel(GinBwdPrePair pp) {
   pdl_sync();
@@ -410,37 +410,12 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
   float4 db = make4(0.f), dg = make4(0.f);
   float gm = 0.f;
   constexpr int NR = 4;
-  const int step = nblk * RPC * NR;
-  NbrIdx<NR> cur;
-  if (PF && p.indptr) {              // offsets / neighbour ids of the first group
-    int vv[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) vv[j] = bid * RPC + hw + j * nblk * RPC;
-    nbr_offsets_load<NR>(p.indptr, p.V, vv, cur);
-    nbr_ids_load<NR>(p.indices, cur);
-  }
-  for (int v0 = bid * RPC + hw; v0 < p.V; v0 += step) {
+  for (int v0 = bid * RPC + hw; v0 < p.V; v0 += nblk * RPC * NR) {
     int vv[NR];
     float4 g[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) vv[j] = v0 + j * nblk * RPC;
     float4 y[NR];   // issued first: independent of the gather's dependent index chain
-    if (PF && p.indptr) {
-      // software pipeline: (a) CSR offsets of the NEXT group, (b) this group's rows, (c) the next group's neighbour ids
-      // (waits for (a) only: the rows stay in flight), (d) consume the rows
-      int vn[NR];
-      NbrIdx<NR> nxt;
-#pragma unroll
-      for (int j = 0; j < NR; ++j) vn[j] = v0 + step + j * nblk * RPC;
-      nbr_offsets_load<NR>(p.indptr, p.V, vn, nxt);
-      float4 hs[NR], h0[NR], h1[NR];
-      gather_rows_issue<HID, NR>(p.src, p.V, vv, cur, l, hs, h0, h1);
-#pragma unroll
-      for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4_cs(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
-      nbr_ids_load<NR>(p.indices, nxt);
-      gather_rows_finish<HID, NR>(p.src, p.indices, cur, l, hs, h0, h1, g);
-      cur = nxt;
-    } else {
 #pragma unroll
     for (int j = 0; j < NR; ++j) y[j] = vv[j] < p.V ? ld4_cs(p.y + (size_t)vv[j] * HID + l * 4) : make4(0.f);
     if (p.indptr) {
@@ -451,7 +426,6 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
         g[j] = make4(0.f);
         if (vv[j] < p.V) g[j] = ld4(p.src + (size_t)(p.map ? __ldg(p.map + vv[j]) : vv[j]) * HID + l * 4);
       }
-    }
     }
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
@@ -501,7 +475,10 @@ gin_bwd_pre_kernel(GinBwdPrePair pp) {
 }
 
 // resident CTAs per SM of the gather kernels: SCGIB_PRE_OCC = 2 (default) | 3 | 4.  Measured on B200 (B = 4096): 52 / 58 / 59 us
-// per launch in fp32 and 42 / 63 / 68 us in bf16 - the register cap of the higher occupancies spills the rows in flight
+// per launch in fp32 and 42 / 63 / 68 us in bf16 - the register cap of the higher occupancies spills the rows in flight.
+// Also measured and NOT kept: the CSR index chain software-pipelined one row group ahead (offsets and the first four
+// neighbour ids of the next group requested while this group's rows are in flight): 63 instead of 52.6 us per launch at
+// 128 registers - the kernel is bound by its L2 / DRAM traffic, not by the dependent index loads.
 int gin_bwd_pre_occ() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SCGIB_PRE_OCC"); v = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 2; }
@@ -511,12 +488,9 @@ int gin_bwd_pre_grid(int V) { return min((V + 63) / 64, gin_bwd_pre_occ() * num_
 template <int H>
 static void launch_pre_t(const GinBwdPrePair& pp, int grid, cudaStream_t s) {
   const int occ = gin_bwd_pre_occ();
-  static int pf = -1;        // SCGIB_PRE_PF=0: the index chain inside the row loop (the round-1 / early round-2 kernel)
-  if (pf < 0) { const char* e = getenv("SCGIB_PRE_PF"); pf = (e && e[0] == '0') ? 0 : 1; }
-  if (occ == 2 && pf) launch_k((gin_bwd_pre_kernel<H, 2, true>), dim3(grid), dim3(kThreads), 0, s, pp);
-  else if (occ == 2) launch_k((gin_bwd_pre_kernel<H, 2, false>), dim3(grid), dim3(kThreads), 0, s, pp);
-  else if (occ == 3) launch_k((gin_bwd_pre_kernel<H, 3, false>), dim3(grid), dim3(kThreads), 0, s, pp);
-  else launch_k((gin_bwd_pre_kernel<H, 4, false>), dim3(grid), dim3(kThreads), 0, s, pp);
+  if (occ == 2) launch_k((gin_bwd_pre_kernel<H, 2>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else if (occ == 3) launch_k((gin_bwd_pre_kernel<H, 3>), dim3(grid), dim3(kThreads), 0, s, pp);
+  else launch_k((gin_bwd_pre_kernel<H, 4>), dim3(grid), dim3(kThreads), 0, s, pp);
 }
 
 void launch_gin_bwd_pre(const GinBwdPreArgs& a, int hidden, cudaStream_t s) {
