@@ -106,7 +106,8 @@ struct Bn4 {
 // 4 channels).  The gather is latency-bound, not bandwidth-bound (degree ~2, 256-byte rows), so it is organised for
 // memory-level parallelism: every dependent stage (indptr -> indices -> [row_map] -> feature rows) is issued for all
 // NR rows and for TWO neighbour slots at once before anything is consumed.  Neighbours are added in CSR order.
-template <int KIN, int NR>
+// SELF = false: the neighbour sum alone (A Z of the reconstruction loss)
+template <int KIN, int NR, bool SELF = true>
 __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, const int32_t* __restrict__ row_map,
                                                  const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                  int V, const int (&v)[NR], int gl, const Bn4* bn, float4 (&acc)[NR]) {
@@ -129,7 +130,7 @@ __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, c
   }
   float4 hs[NR];
 #pragma unroll
-  for (int j = 0; j < NR; ++j) hs[j] = v[j] < V ? ld4(in + (size_t)sv[j] * KIN + gl * 4) : make4(0.f);
+  for (int j = 0; j < NR; ++j) hs[j] = (SELF && v[j] < V) ? ld4(in + (size_t)sv[j] * KIN + gl * 4) : make4(0.f);
   if (row_map) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
@@ -146,7 +147,7 @@ __device__ __forceinline__ void gather_aggregate(const float* __restrict__ in, c
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
     acc[j] = make4(0.f);
-    if (v[j] < V) acc[j] = bn ? bn->act(hs[j]) : hs[j];
+    if (SELF && v[j] < V) acc[j] = bn ? bn->act(hs[j]) : hs[j];
     if (u0[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h0[j]) : h0[j]);
     if (u1[j] >= 0) acc[j] = add4(acc[j], bn ? bn->act(h1[j]) : h1[j]);
   }

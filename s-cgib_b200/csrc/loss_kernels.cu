@@ -43,14 +43,21 @@ recon_fwd_kernel(ReconFwdArgs p) {
     load_row_tile<GT, HID>(sm.z, GLD, p.Z, base, p.N);
     __syncthreads();
     gemm_tn<HID, HID>(sm.z, GLD, sm.z, GLD, GT, G);
-    for (int r = hw; r < GT; r += RPP) {
-      const int v = base + r;
-      if (v < p.N) {
-        float4 nb = make4(0.f);
-        const int e0 = __ldg(p.indptr + v), e1 = __ldg(p.indptr + v + 1);
-        for (int e = e0; e < e1; ++e) nb = add4(nb, ld4(p.Z + (size_t)__ldg(p.indices + e) * HID + l * 4));
-        const float4 zv = ld4(sm.z + r * GLD + l * 4);
-        ed += zv.x * nb.x + zv.y * nb.y + zv.z * nb.z + zv.w * nb.w;
+    // per-edge dots sum_v z_v . (A Z)_v: the neighbour sums of NR rows per lane group are gathered together (every stage of
+    // the indptr -> indices -> row chain issued for all of them at once; a row-at-a-time loop was the kernel's serial part)
+    constexpr int NR = 4;
+    for (int rb = hw; rb < GT; rb += RPP * NR) {
+      int vv[NR];
+      float4 nb[NR];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) vv[j] = (rb + j * RPP < GT) ? base + rb + j * RPP : p.N;
+      gather_aggregate<HID, NR, false>(p.Z, nullptr, p.indptr, p.indices, p.N, vv, l, nullptr, nb);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        if (vv[j] < p.N) {
+          const float4 zv = ld4(sm.z + (rb + j * RPP) * GLD + l * 4);
+          ed += zv.x * nb[j].x + zv.y * nb[j].y + zv.z * nb[j].z + zv.w * nb[j].w;
+        }
       }
     }
   }
