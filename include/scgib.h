@@ -307,6 +307,13 @@ SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indptr, const i
                                   float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream);
 SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int32_t B, float scale, float* loss,
                                     float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream);
+/* the same operators at hidden = 64 or 128 (the entries above are the hidden-64 instances) */
+SCGIB_API size_t scgib_loss_workspace_bytes_h(int32_t B, int32_t hidden);
+SCGIB_API int scgib_recon_adj_h_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
+                                    int32_t hidden, float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+SCGIB_API int scgib_contrastive_h_f32(const float* core, const float* readout, int32_t B, int32_t hidden, float scale, float* loss,
+                                      float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[s] = sum_{rows in segment s} f(in[row])  (dgl.sum_nodes, models.py:716,725,733,684);
  * f = relu(BN(.)) when bn = {mean,rstd,gamma,beta} is given, identity otherwise. */

@@ -89,6 +89,11 @@ _SIGNATURES = {
                                     c_size_t, c_void_p]),
     "scgib_contrastive_f32": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
+    "scgib_loss_workspace_bytes_h": (c_size_t, [c_int32, c_int32]),
+    "scgib_recon_adj_h_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
+    "scgib_contrastive_h_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
     "scgib_segment_sum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "scgib_core_gate_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "scgib_core_gate_fwd_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32] + [c_void_p] * 13 + [c_void_p, c_size_t, c_void_p]),

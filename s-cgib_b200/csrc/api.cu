@@ -959,7 +959,7 @@ extern "C" SCGIB_API int scgib_gin_layer_bwd_f32(const float* g_next, const int3
 // ---- loss operators (forward + gradient in one call; the units of the whole-step functions)
 namespace scgib {
 struct LossOpWs { float *rpart, *G, *edge, *z1, *z2, *zsplit, *n1, *n2, *diag, *D, *rowsum, *g1p, *g2p, *kl, *losses; size_t bytes; };
-static LossOpWs loss_op_carve(int B, void* base) {
+static LossOpWs loss_op_carve(int B, void* base, int HID = scgib::HID) {
   LossOpWs w;
   char* p = (char*)base;
   size_t o = 0;
@@ -975,13 +975,17 @@ static LossOpWs loss_op_carve(int B, void* base) {
 }  // namespace scgib
 
 extern "C" SCGIB_API size_t scgib_loss_workspace_bytes(int32_t B) { return B < 0 ? 0 : loss_op_carve(B, nullptr).bytes; }
+extern "C" SCGIB_API size_t scgib_loss_workspace_bytes_h(int32_t B, int32_t hidden) {
+  return (B < 0 || (hidden != 64 && hidden != 128)) ? 0 : loss_op_carve(B, nullptr, hidden).bytes;
+}
 
-extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
-                                   float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream_) {
+static int recon_adj_impl(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E, const int HID,
+                          float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!Z || !indptr || !loss || !workspace || (E > 0 && !indices)) return SCGIB_E_NULL;
+  if (HID != 64 && HID != 128) return SCGIB_E_SHAPE;
   if (N < 1 || E < 0) return SCGIB_E_RANGE;
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)Z & 15u) != 0 || ((uintptr_t)gZ & 15u) != 0) return SCGIB_E_ALIGN;
-  const LossOpWs w = loss_op_carve(1, workspace);
+  const LossOpWs w = loss_op_carve(1, workspace, HID);
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
   const int grid = num_sms();
@@ -991,7 +995,7 @@ extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indp
   cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
   cudaMemsetAsync(w.rowsum, 0, sizeof(float), s);
   cudaMemsetAsync(w.diag, 0, sizeof(float), s);
-  LossFinalizeArgs f{w.rowsum, 1, w.diag, 0, w.G, w.edge, N, E, nullptr, w.kl, w.D, w.losses};   // B = 0: only the recon term
+  LossFinalizeArgs f{w.rowsum, 1, w.diag, 0, w.G, w.edge, N, E, nullptr, w.kl, w.D, w.losses, HID};   // B = 0: only the recon term
   launch_loss_finalize(f, s);
   cudaMemcpyAsync(loss, w.losses + 2, sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (gZ) {
@@ -1001,33 +1005,54 @@ extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indp
   return (int)cudaGetLastError();
 }
 
-extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int32_t B, float scale, float* loss,
-                                     float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" SCGIB_API int scgib_recon_adj_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
+                                   float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes, void* stream_) {
+  return recon_adj_impl(Z, indptr, indices, N, E, HID, scale, loss, gZ, workspace, workspace_bytes, stream_);
+}
+extern "C" SCGIB_API int scgib_recon_adj_h_f32(const float* Z, const int32_t* indptr, const int32_t* indices, int32_t N, int32_t E,
+                                     int32_t hidden, float scale, float* loss, float* gZ, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
+  return recon_adj_impl(Z, indptr, indices, N, E, hidden, scale, loss, gZ, workspace, workspace_bytes, stream_);
+}
+
+static int contrastive_impl(const float* core, const float* readout, int32_t B, const int HID, float scale, float* loss,
+                            float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!core || !readout || !loss || !workspace) return SCGIB_E_NULL;
   if ((g_core == nullptr) != (g_readout == nullptr)) return SCGIB_E_NULL;
+  if (HID != 64 && HID != 128) return SCGIB_E_SHAPE;
   if (B < 1) return SCGIB_E_RANGE;
   if (((uintptr_t)workspace & 255u) != 0 || ((uintptr_t)core & 15u) != 0 || ((uintptr_t)readout & 15u) != 0) return SCGIB_E_ALIGN;
-  const LossOpWs w = loss_op_carve(B, workspace);
+  const LossOpWs w = loss_op_carve(B, workspace, HID);
   if (workspace_bytes < w.bytes) return SCGIB_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream_;
   const int js = contrastive_jsplit(B);
-  NormalizeArgs na{core, readout, B, w.z1, w.z2, w.n1, w.n2, w.diag, w.zsplit};
+  const bool tc = HID == 64 && use_tc_contrastive();          // the tcgen05 contrastive kernels are built for hidden 64
+  NormalizeArgs na{core, readout, B, w.z1, w.z2, w.n1, w.n2, w.diag, tc ? w.zsplit : nullptr};
   launch_normalize(na, HID, s);
   ContrastiveFwdArgs c{w.z1, w.z2, B, js, w.rowsum, w.zsplit};
-  if (use_tc_contrastive()) launch_contrastive_fwd_tc(c, s); else launch_contrastive_fwd(c, HID, s);
+  if (tc) launch_contrastive_fwd_tc(c, s); else launch_contrastive_fwd(c, HID, s);
   cudaMemsetAsync(w.kl, 0, 4 * sizeof(float), s);
   cudaMemsetAsync(w.G, 0, HID * HID * sizeof(float), s);
   cudaMemsetAsync(w.edge, 0, 4 * sizeof(float), s);
-  LossFinalizeArgs f{w.rowsum, js, w.diag, B, w.G, w.edge, 1, 0, nullptr, w.kl, w.D, w.losses};
+  LossFinalizeArgs f{w.rowsum, js, w.diag, B, w.G, w.edge, 1, 0, nullptr, w.kl, w.D, w.losses, HID};
   launch_loss_finalize(f, s);
   cudaMemcpyAsync(loss, w.losses + 1, sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (g_core) {
     ContrastiveBwdArgs a{w.z1, w.z2, w.D, B, js, w.g1p, w.g2p};
-    if (use_tc_contrastive()) launch_contrastive_bwd_tc(a, w.zsplit, s); else launch_contrastive_bwd(a, HID, s);
+    if (tc) launch_contrastive_bwd_tc(a, w.zsplit, s); else launch_contrastive_bwd(a, HID, s);
     ContrastiveBwdFinArgs fa{w.g1p, w.g2p, w.z1, w.z2, w.n1, w.n2, B, js, scale, g_core, g_readout};
     launch_contrastive_bwd_finalize(fa, HID, s);
   }
   return (int)cudaGetLastError();
+}
+extern "C" SCGIB_API int scgib_contrastive_f32(const float* core, const float* readout, int32_t B, float scale, float* loss,
+                                     float* g_core, float* g_readout, void* workspace, size_t workspace_bytes, void* stream_) {
+  return contrastive_impl(core, readout, B, HID, scale, loss, g_core, g_readout, workspace, workspace_bytes, stream_);
+}
+extern "C" SCGIB_API int scgib_contrastive_h_f32(const float* core, const float* readout, int32_t B, int32_t hidden, float scale,
+                                       float* loss, float* g_core, float* g_readout, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
+  return contrastive_impl(core, readout, B, hidden, scale, loss, g_core, g_readout, workspace, workspace_bytes, stream_);
 }
 
 extern "C" SCGIB_API int scgib_segment_sum_f32(const float* in, const int32_t* seg_ptr, int32_t S, const float* bn, float* out, void* stream) {

@@ -213,9 +213,8 @@ class _Bridge:
 
 
 def _check_composed_width(encoder, hidden_dim):
-    if encoder != "GIN" and int(hidden_dim) != HID:
-        raise NotImplementedError("--encoder %s runs at --dims 64 on the B200 path (the batch-loss operator entries are built "
-                                  "for hidden 64; --dims 128 is available with --encoder GIN)" % encoder)
+    if encoder != "GIN" and int(hidden_dim) not in (64, 128):
+        raise NotImplementedError("--encoder %s runs at --dims 64 or 128 on the B200 path" % encoder)
 
 
 def _check_args(args, encoder, allowed=("GIN",)):

@@ -89,9 +89,10 @@ def recon_adj(Z, indptr, indices, scale=1.0, want_grad=True):
     N, E = Z.shape[0], indices.numel()
     loss = torch.empty(1, device=Z.device)
     gZ = torch.empty_like(Z) if want_grad else None
-    ws = torch.empty(lib.scgib_loss_workspace_bytes(1) + 256, dtype=torch.uint8, device=Z.device)
-    _lib.check(lib.scgib_recon_adj_f32(_lib.ptr(Z), _lib.ptr(indptr), _lib.ptr(indices), N, E, float(scale), _lib.ptr(loss),
-                                       _lib.ptr(gZ), _lib.ptr(ws), ws.numel(), _stream(Z)), "recon_adj")
+    H = Z.shape[1]
+    ws = torch.empty(lib.scgib_loss_workspace_bytes_h(1, H) + 256, dtype=torch.uint8, device=Z.device)
+    _lib.check(lib.scgib_recon_adj_h_f32(_lib.ptr(Z), _lib.ptr(indptr), _lib.ptr(indices), N, E, H, float(scale), _lib.ptr(loss),
+                                         _lib.ptr(gZ), _lib.ptr(ws), ws.numel(), _stream(Z)), "recon_adj")
     return loss, gZ
 
 
@@ -104,10 +105,16 @@ def contrastive(core, readout, scale=1.0, want_grad=True):
     loss = torch.empty(1, device=core.device)
     g1 = torch.empty_like(core) if want_grad else None
     g2 = torch.empty_like(core) if want_grad else None
-    ws = torch.empty(lib.scgib_loss_workspace_bytes(B) + 256, dtype=torch.uint8, device=core.device)
-    _lib.check(lib.scgib_contrastive_f32(_lib.ptr(core), _lib.ptr(readout), B, float(scale), _lib.ptr(loss), _lib.ptr(g1),
-                                         _lib.ptr(g2), _lib.ptr(ws), ws.numel(), _stream(core)), "contrastive")
+    H = core.shape[1]
+    ws = torch.empty(lib.scgib_loss_workspace_bytes_h(B, H) + 256, dtype=torch.uint8, device=core.device)
+    _lib.check(lib.scgib_contrastive_h_f32(_lib.ptr(core), _lib.ptr(readout), B, H, float(scale), _lib.ptr(loss), _lib.ptr(g1),
+                                           _lib.ptr(g2), _lib.ptr(ws), ws.numel(), _stream(core)), "contrastive")
     return loss, g1, g2
+
+
+def _c32(t):
+    """contiguous fp32 view / copy (the kernels read raw pointers)."""
+    return t.detach().contiguous().float()
 
 
 def _ws(nbytes, dev):
@@ -233,6 +240,8 @@ def graph_aggregate(h, indptr, indices, src_norm, dst_norm, row_map=None, add=No
     """out[v] = (add[v]) + fd(deg v) sum_{u in N(v)} fs(deg u) h[map(u)]; the SAGEConv mean (NONE, MEAN), its backward
     (MEAN, NONE) and the GraphConv normalised sum (SQRT, SQRT; self-adjoint) on the symmetric CSR."""
     _cuda(h, indptr, indices)
+    h = _c32(h)
+    add = None if add is None else _c32(add)
     V, W = indptr.numel() - 1, h.shape[1]
     out = torch.empty(V, W, device=h.device)
     _lib.check(_lib.load().scgib_graph_aggregate_f32(_lib.ptr(h), W, _lib.ptr(row_map), _lib.ptr(indptr), _lib.ptr(indices), V,
@@ -243,6 +252,7 @@ def graph_aggregate(h, indptr, indices, src_norm, dst_norm, row_map=None, add=No
 def segment_sum_w(h, seg_ptr):
     """dgl.sum_nodes at width 32 / 64 / 128 / 256."""
     _cuda(h, seg_ptr)
+    h = _c32(h)
     S, W = seg_ptr.numel() - 1, h.shape[1]
     out = torch.empty(S, W, device=h.device)
     _lib.check(_lib.load().scgib_segment_sum_w_f32(_lib.ptr(h), _lib.ptr(seg_ptr), S, W, _lib.ptr(out), _stream(h)), "segment_sum_w")
@@ -252,6 +262,7 @@ def segment_sum_w(h, seg_ptr):
 def linear_fwd(X0, W0, O, w0_kxo=False, X1=None, W1=None, w1_kxo=False, bias=None, relu=False, map0=None, M0=None, M1=None, V=None):
     """Y[V,O] = act(X0[map0] (.) (M0 > 0) W0 + X1 (.) (M1 > 0) W1 + bias); W [O,K] (nn.Linear) or [K,O] (w_kxo)."""
     _cuda(X0, W0)
+    X0, W0, X1, W1, bias, M0, M1 = (None if t is None else _c32(t) for t in (X0, W0, X1, W1, bias, M0, M1))
     V = int(V if V is not None else (map0.numel() if map0 is not None else X0.shape[0]))
     Y = torch.empty(V, O, device=X0.device)
     _lib.check(_lib.load().scgib_linear_fwd_f32(_lib.ptr(X0), _lib.ptr(M0), _lib.ptr(map0), _lib.ptr(W0), X0.shape[1], int(w0_kxo),
@@ -263,6 +274,9 @@ def linear_fwd(X0, W0, O, w0_kxo=False, X1=None, W1=None, w1_kxo=False, bias=Non
 def linear_bwd_w(G, X, dW, db=None, M=None, map=None, kxo=False, accumulate=False):
     """dW (+)= (G (.) (M > 0))^T X[map] ([O,K], or [K,O] with kxo), db (+)= column sums; in place on dW / db."""
     _cuda(G, X, dW)
+    if not (dW.is_contiguous() and dW.dtype == torch.float32) or (db is not None and not db.is_contiguous()):
+        raise ValueError("linear_bwd_w writes dW / db in place: contiguous fp32 tensors")
+    G, X, M = _c32(G), _c32(X), None if M is None else _c32(M)
     lib = _lib.load()
     V, O, K = G.shape[0], G.shape[1], X.shape[1]
     ws = _ws(lib.scgib_linear_bwd_w_workspace_bytes(V, O, K), G.device)
@@ -274,6 +288,7 @@ def linear_bwd_w(G, X, dW, db=None, M=None, map=None, kxo=False, accumulate=Fals
 def transfer_bwd(x, g0, g1, map1, normalize=True, csr0=None, csr1=None):
     """d transfer_d.weight [32, F] from the input gradients of the two row sets (parent rows / ego rows through map1)."""
     _cuda(x, g0)
+    x, g0, g1 = _c32(x), _c32(g0), None if g1 is None else _c32(g1)
     lib = _lib.load()
     F, V0, V1 = x.shape[1], g0.shape[0], 0 if g1 is None else g1.shape[0]
     dWt = torch.empty(DTR, F, device=x.device)

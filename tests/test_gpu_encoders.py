@@ -186,7 +186,7 @@ def test_mainmodel_sage_gcn_matches_reference_golden(path, monkeypatch):
         assert rel(got[n].cpu(), gref) <= 2e-4, (n, rel(got[n].cpu(), gref))
 
 
-@pytest.mark.parametrize("encoder,hidden,k", [("GraphSAGE", 64, 1), ("GCN", 64, 2), ("GraphSAGE", 64, 3), ("GCN", 64, 1)])
+@pytest.mark.parametrize("encoder,hidden,k", [("GraphSAGE", 64, 1), ("GCN", 64, 2), ("GraphSAGE", 64, 3), ("GraphSAGE", 128, 2), ("GCN", 128, 1)])
 def test_mainmodel_sage_gcn_matches_oracle_batch(encoder, hidden, k, monkeypatch):
     g = synth_batch(91 + hidden + k, 200)
     e = ego_batch_ref(g, k)
@@ -255,11 +255,10 @@ def test_extract_features_api_with_gcn():
     assert torch.equal(imap[:, :64], noisy) and torch.isfinite(kl_t).all()
 
 
-def test_sage_gcn_width_is_64():
-    """the loss operator entries (scgib_recon_adj_f32 / scgib_contrastive_f32) are built for hidden 64: other widths fail loudly."""
+def test_sage_gcn_unsupported_width_fails_loudly():
     import models
     with pytest.raises(NotImplementedError):
-        models.Mainmodel(_args(), 9, 128, 4, 4, 1, "GraphSAGE")
+        models.Mainmodel(_args(), 9, 96, 4, 4, 1, "GraphSAGE")
 
 
 def test_sage_gcn_eval_mode_fails_loudly():
@@ -271,3 +270,28 @@ def test_sage_gcn_eval_mode_fails_loudly():
     pg = product_graph(g, DEV)
     with pytest.raises(NotImplementedError):
         m.forward(pg, F.normalize(pg.ndata["x"].float()), khop_ego_batch(pg, 1), None, None, 1, None, 2, DEV, 16)
+
+
+def test_loss_operators_hidden_128():
+    """scgib_recon_adj_h_f32 / scgib_contrastive_h_f32 at hidden 128 (value + gradient) against the oracle's dense formulas in fp64."""
+    from scgib_b200 import ops
+    from oracle.scgib_oracle import tgraph_from_ref as _tg
+    g = synth_batch(8, 120)
+    tg = _tg(g)
+    torch.manual_seed(9)
+    m = OracleMainmodel(9, 128).double()
+    Z = (torch.randn(g.num_nodes, 128, dtype=torch.float64) * 0.2).requires_grad_(True)
+    rec = m.loss_recon_adj(Z, tg)
+    rec.backward()
+    pg = product_graph(g, DEV)
+    loss, gZ = ops.recon_adj(Z.detach().float().to(DEV), pg.indptr, pg.indices, scale=0.5)
+    assert abs(float(loss) - float(rec)) <= 1e-5 * abs(float(rec))
+    assert rel(gZ.cpu(), 0.5 * Z.grad) <= 2e-5
+    for B in (7, 300):
+        core = (torch.randn(B, 128, dtype=torch.float64) * 2).requires_grad_(True)
+        ro = (torch.randn(B, 128, dtype=torch.float64) * 3).requires_grad_(True)
+        con = m.batched_semi_loss(core, ro, B)
+        con.backward()
+        loss, g1, g2 = ops.contrastive(core.detach().float().to(DEV), ro.detach().float().to(DEV), scale=2.0)
+        assert abs(float(loss) - float(con)) <= 1e-5 * abs(float(con)), B
+        assert rel(g1.cpu(), 2.0 * core.grad) <= 5e-5 and rel(g2.cpu(), 2.0 * ro.grad) <= 5e-5, B
