@@ -33,7 +33,8 @@ def make_optimizer(model, lr):
     if getattr(model, "_bridge", None) is not None and os.environ.get("SCGIB_TORCH_ADAM", "0") != "1":
         from scgib_b200.optim import FlatAdam
         return FlatAdam(model, lr=lr, weight_decay=5e-5)
-    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=5e-5)
+    from scgib_b200.optim import AllReduceAdam          # torch.optim.Adam (+ the gradient all-reduce under torchrun)
+    return AllReduceAdam(model.parameters(), lr=lr, weight_decay=5e-5)
 
 
 def run_pretraining(model, pre_train_loader1, optimizer, batch_size, device):

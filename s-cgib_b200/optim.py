@@ -73,3 +73,24 @@ class FlatAdam:
             eng.exp_avg.copy_(sd["exp_avg"])
             eng.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups[0].update(sd["param_groups"][0])
+
+
+class AllReduceAdam(torch.optim.Adam):
+    """``torch.optim.Adam`` over module parameters that averages the gradients over the data-parallel ranks first: ONE sum
+    all-reduce of the flattened gradients per step (the modules without a flat engine buffer: --encoder GraphSAGE / GCN).
+    Single process: plain Adam."""
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            grads = [p.grad for g in self.param_groups for p in g["params"] if p.grad is not None]
+            if grads:
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat /= dist.get_world_size()
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+        return super().step(closure)

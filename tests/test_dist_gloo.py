@@ -94,3 +94,44 @@ def test_two_rank_gloo_allreduce_matches_single_process():
         # workers run torch single-threaded, the check multi-threaded: fp32 summation order differs
         assert np.allclose(g, mean, rtol=1e-4, atol=1e-5 * np.abs(mean).max())
     assert np.array_equal(res[0][2], res[1][2])        # replicas stay bit-identical after the optimiser step
+
+
+def _worker_adam(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from scgib_b200 import dist as sdist
+    from scgib_b200.optim import AllReduceAdam
+    sdist.init_from_env("gloo")
+    torch.manual_seed(3)
+    ps = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(3))]
+    gen = torch.Generator().manual_seed(10 + rank)
+    ps[0].grad, ps[1].grad = torch.randn(5, 7, generator=gen), torch.randn(11, generator=gen)      # ps[2]: no gradient
+    opt = AllReduceAdam(ps, lr=1e-2, weight_decay=5e-5)
+    opt.step()
+    q.put((rank, [p.detach().numpy() for p in ps], [ps[0].grad.numpy(), ps[1].grad.numpy()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_allreduce_adam_keeps_module_parameter_replicas_identical():
+    """the optimiser of the modules without a flat engine buffer (--encoder GraphSAGE / GCN) under torchrun"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_adam, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    gens = [torch.Generator().manual_seed(10 + r) for r in range(world)]
+    g0 = [torch.randn(5, 7, generator=g) for g in gens]
+    g1 = [torch.randn(11, generator=g) for g in gens]
+    mean0, mean1 = ((g0[0] + g0[1]) / 2).numpy(), ((g1[0] + g1[1]) / 2).numpy()
+    for rank, params, grads in res:
+        assert np.allclose(grads[0], mean0, rtol=1e-6, atol=1e-7) and np.allclose(grads[1], mean1, rtol=1e-6, atol=1e-7)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, b)
