@@ -717,6 +717,23 @@ def main():
     hbm_kernels = {k_: {"algorithmic_bytes_per_launch": v, "GB/s": v / (kernels[k_]["ms_per_launch"] * 1e-3) / 1e9,
                         "frac": v / (kernels[k_]["ms_per_launch"] * 1e-3) / 1e9 / hbm}
                    for k_, v in hbm_alg.items() if k_ in kernels}
+    # next to the CUDA-event time (which carries ~4 us of launch + event latency per launch: a quarter of a 16 us kernel):
+    # the same kernels' durations in the committed ncu launch list of this command (cold-cache, serialised), headline config only
+    if not bf16 and args.batch == 4096 and args.k == 1 and H == 64 and args.recons_type == "adj":
+        try:
+            import csv
+            ncu_names = {"gin_bwd_pre.enc1+2": "gin_bwd_pre_kernel", "ego_pool_fwd": "ego_pool_fwd", "graph_gate_fwd": "graph_gate_fwd_kernel",
+                         "recon_bwd": "recon_bwd_kernel"}
+            rows = list(csv.DictReader(open(os.path.join(ROOT, "profiles", "r02_ncu_launches_fp32_summary.csv"))))
+            for k_, pat in ncu_names.items():
+                hit = [r for r in rows if pat in r["kernel"]]
+                if k_ in hbm_kernels and hit:
+                    us = float(hit[0]["total_us"]) / int(hit[0]["launches"])
+                    gbs = hbm_kernels[k_]["algorithmic_bytes_per_launch"] / (us * 1e-6) / 1e9
+                    hbm_kernels[k_]["ncu"] = {"us_per_launch": us, "GB/s": gbs, "frac": gbs / hbm,
+                                               "source": "profiles/r02_ncu_launches_fp32_summary.csv (launch list of this command)"}
+        except Exception:
+            pass
 
     if rank == 0:
         graphs = args.batch * world * args.steps
