@@ -256,9 +256,14 @@ void launch_linear_plain(const float* X, const float* W, const float* bias, int 
   launch_k((linear_fwd_kernel), dim3((V + LTM - 1) / LTM, O / LTN), dim3(kThreads), 0, s, a);
 }
 
-static int bwd_w_chunks(int V) {
-  const int c = (V + 511) / 512;
-  return c < 1 ? 1 : (c > 64 ? 64 : c);
+// row chunks of the weight-gradient reduction: enough (chunks x output tiles) CTAs for two per SM, at least 256 rows per chunk
+static int bwd_w_chunks(int V, int O, int K) {
+  int tiles = (O / WT) * ((K + WT - 1) / WT);
+  if (tiles < 1) tiles = 1;
+  int c = (2 * num_sms() + tiles - 1) / tiles;
+  const int cmax = (V + 255) / 256;
+  if (c > cmax) c = cmax;
+  return c < 1 ? 1 : c;
 }
 
 }  // namespace scgib
@@ -319,7 +324,7 @@ extern "C" SCGIB_API int scgib_linear_fwd_f32(const float* X0, const float* M0, 
 }
 
 extern "C" SCGIB_API size_t scgib_linear_bwd_w_workspace_bytes(int32_t V, int32_t O, int32_t K) {
-  return (size_t)bwd_w_chunks(V) * ((size_t)O * K + O) * sizeof(float) + 256;
+  return (size_t)bwd_w_chunks(V, O, K) * ((size_t)O * K + O) * sizeof(float) + 256;
 }
 
 // dW (+)= (G (.) (M > 0))^T X[map]  ([O][K], or [K][O] with kxo), db (+)= column sums (optional)
@@ -332,7 +337,7 @@ extern "C" SCGIB_API int scgib_linear_bwd_w_f32(const float* G, const float* M, 
   if (workspace_bytes < scgib_linear_bwd_w_workspace_bytes(V, O, K)) return SCGIB_E_WORKSPACE;
   if (((uintptr_t)workspace & 15u) != 0) return SCGIB_E_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  const int chunks = bwd_w_chunks(V);
+  const int chunks = bwd_w_chunks(V, O, K);
   LinearBwdWArgs a{G, M, X, map, V, O, K, ((V + chunks - 1) / chunks + WR - 1) / WR * WR, (float*)workspace};
   launch_k((linear_bwd_w_kernel), dim3(chunks, O / WT, (K + WT - 1) / WT), dim3(kThreads), 0, s, a);
   const int n = O * K + O;
